@@ -1,0 +1,161 @@
+/*
+ * kfb200.h -- C-ABI of the B200-native KinectFusion tracking-and-mapping core.
+ *
+ * This is the drop-in boundary.  It replaces, one for one, the
+ * host->device seam of baiyuntao00/SLAM-KinectFusion: the eleven free functions
+ * `kf::device::*` declared at kfusion/include/device_types.hpp:113-128 plus the
+ * two OpenCV-CUDA calls and the GpuMat upload/download/setTo traffic in
+ * kfusion/src/kinectfusion.cpp:39-65.  Each entry point cites the reference
+ * interface it replaces.  Plain C: opaque context, plain pointers and sizes,
+ * int return codes (0 = ok), no C++/torch/OpenCV types.
+ *
+ * Conventions
+ *   pose12 : float[12], the top three rows of the 4x4 matrix, row-major
+ *            (r00 r01 r02 tx r10 r11 r12 ty r20 r21 r22 tz) == cv::Affine3f::matrix.val[0..11]
+ *   map3   : float3 array-of-structs, 12 B per pixel, row-major (the reference's
+ *            continuous CV_32FC3 GpuMat, types.hpp:45-46); device storage is float4
+ *   volume : packed {int16 tsdf, int16 weight} voxels, linear index
+ *            x + y*X + z*X*Y (device_utils.cuh:30-37); the reference's 3 colour
+ *            bytes are write-only dead state and are dropped
+ *   Threading: one host thread per context; all work runs on a context-owned
+ *            non-blocking CUDA stream.  Functions that return host data block
+ *            until that data is valid; the others only enqueue.
+ *   There is NO CPU fallback: every compute entry point launches sm_100a kernels
+ *            and fails with KFB_ERR_CUDA if no such device is present.
+ */
+#ifndef KFB200_H
+#define KFB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KFB_MAX_LEVELS 8
+
+enum
+{
+    KFB_OK = 0,
+    KFB_ERR_INVALID = 1,     /* bad argument */
+    KFB_ERR_CUDA = 2,        /* CUDA runtime error, see kfb_last_error_string */
+    KFB_ERR_UNSUPPORTED = 3, /* e.g. dims[0] % 4 != 0 */
+    KFB_ERR_TRACKING = 4     /* reserved for host facades (icp_registration.cpp:35-37) */
+};
+
+/* kf::Intrinsics, kfusion/include/types.hpp:13-29 (the unused depth scale `c` omitted). */
+typedef struct
+{
+    int width, height;
+    float fx, fy, cx, cy;
+} kfb_intrinsics;
+
+/* kf::kinectfuison_params, kfusion/include/kinectfusion.h:9-30; defaults from
+ * kfusion/src/kinectfusion.cpp:167-190 via kfb_default_params(). */
+typedef struct
+{
+    int pyramid_height;            /* 3 */
+    float dfilter_dist;            /* 5.0 m */
+    int bfilter_kernel_size;       /* 5 */
+    float bfilter_spatial_sigma;   /* 10 */
+    float bfilter_color_sigma;     /* 10 (mm) */
+    float icp_dist_threshold;      /* 0.015 m */
+    float icp_angle_threshold;     /* 30 degrees */
+    int icp_iter_count[KFB_MAX_LEVELS]; /* indexed by level: {4,5,10} */
+    int volu_dims[3];              /* 512^3 */
+    float volu_range[3];           /* 3 m */
+    float volu_trun_dist;          /* 2.1 * range/dims */
+    int tsdf_max_weight;           /* 64 (the reference hard-codes MAX_WEIGHT, device_utils.cuh:5) */
+    int compat_icp_rows;           /* 1: reproduce the reference's truncated ICP grid (rigid_icp.cu:137-139) */
+    int compat_raycast_ts_sign;    /* 1: reproduce the reference's Ts sign (tsdf_volume.cu:246) */
+    /* z-slab sharding for volumes of 1024^3 and above: this context
+     * stores and updates planes [slab_z_begin - halo, slab_z_end + halo) only.
+     * 0,0 = the whole volume. */
+    int slab_z_begin, slab_z_end;
+} kfb_params;
+
+typedef struct kfb_ctx kfb_ctx;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+void kfb_default_params(kfb_params *p, int dims);                       /* kinectfusion.cpp:167-190 */
+int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_ctx **out);
+                                                                        /* kinectfusion.cpp:9-27, types.hpp:37-52, tsdf_volume.cpp:13-27 */
+void kfb_destroy(kfb_ctx *ctx);                                         /* kinectfusion.cpp:191-196 */
+const char *kfb_last_error_string(const kfb_ctx *ctx);                  /* safe_call.hpp:8-14 (returned, not printed) */
+int kfb_synchronize(kfb_ctx *ctx);                                      /* cudaDeviceSynchronize, tsdf_volume.cu:110 */
+int kfb_device_count(void);
+
+/* ---- volume ------------------------------------------------------------- */
+int kfb_reset_volume(kfb_ctx *ctx);                                     /* device::resetVolume, device_types.hpp:116 */
+int kfb_reset_frames(kfb_ctx *ctx);                                     /* Frame::reset, types.hpp:53-62 */
+
+/* ---- frame ingest + front end ---------------------------------------------- */
+/* GpuMat::upload of the f32 millimetre depth, kinectfusion.cpp:50.  `host` may be pageable
+ * or pinned; the copy is asynchronous on the context stream when pinned. */
+int kfb_upload_depth_mm(kfb_ctx *ctx, const float *host, int width, int height);
+/* cv::cuda::pyrDown x(L-1), cv::cuda::bilateralFilter xL, device::depthTruncation xL,
+ * device::getVertexmap xL, device::getNormalmap xL -- kinectfusion.cpp:54-75,
+ * device_types.hpp:122-124.  Fills the CURRENT frame's depth/vertex/normal pyramids. */
+int kfb_frontend(kfb_ctx *ctx);
+/* cframe->vmap.swap(pframe->vmap); cframe->nmap.swap(pframe->nmap) -- kinectfusion.cpp:88-89 */
+int kfb_swap_frames(kfb_ctx *ctx);
+
+/* ---- ICP ------------------------------------------------------------------ */
+/* device::rigidICP (device_types.hpp:127, rigid_icp.cu:135-169) for one pyramid level:
+ * projective association of the current maps (under pose12 = current estimate of
+ * cur->prev) against the previous/model maps, and the 27 unique sums of the 6x7
+ * normal equations in the reference's order.  Blocks until out27 is valid. */
+int kfb_icp_accumulate(kfb_ctx *ctx, int level, const float pose12[12], double out27[27]);
+
+/* ---- TSDF ---------------------------------------------------------------------- */
+/* device::integrate (device_types.hpp:118, tsdf_volume.cu:103-111) with the current
+ * frame's level-0 filtered depth.  vol2cam12 = camera_pose.inv() * volume_pose
+ * (tsdf_volume.cpp:50).  n_updated may be NULL; when non-NULL a counting variant of
+ * the kernel runs and the call blocks until the count is valid. */
+int kfb_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_updated);
+/* device::raycast (device_types.hpp:117, tsdf_volume.cu:264-273) into the PREVIOUS
+ * (model) frame's level-0 maps, misses written as zeros (pframe->reset(),
+ * kinectfusion.cpp:112).  cam2vol12 = volume_pose.inv()*camera_pose and
+ * rinv9 = its rotation inverted, row-major (tsdf_volume.cpp:59-61). */
+int kfb_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9]);
+/* device::resizePointsNormals x(L-1) on the model maps, kinectfusion.cpp:114-120. */
+int kfb_model_pyramid(kfb_ctx *ctx);
+
+/* ---- export ("next" rows) ------------------------------------------ */
+/* device::extract_points (device_types.hpp:128, tsdf_volume.cu:483-499) + the D2H of
+ * TSDFVolume::fetchPointCloud (tsdf_volume.cpp:63-84).  Writes up to `cap` xyz points
+ * (world frame via volpose12) to host_points3; *n_points = number written. */
+int kfb_extract_points(kfb_ctx *ctx, const float volpose12[12], float *host_points3, size_t cap, size_t *n_points);
+/* device::renderPhong / device::renderNormals (device_types.hpp:120-121) of the model
+ * maps + GpuMat::download (kinectfusion.cpp:33-47).  host_bgr: width*height*3 bytes. */
+int kfb_render_phong(kfb_ctx *ctx, const float eye3[3], uint8_t *host_bgr);
+int kfb_render_normals(kfb_ctx *ctx, uint8_t *host_bgr);
+
+/* ---- test / interop hooks (GpuMat::download/upload equivalents) --------------------- */
+enum { KFB_FRAME_CUR = 0, KFB_FRAME_PREV = 1 };
+int kfb_download_depth(kfb_ctx *ctx, int level, float *host);                 /* current frame, metres */
+int kfb_upload_depth_m(kfb_ctx *ctx, int level, const float *host);           /* inject filtered depth */
+int kfb_download_raw_depth(kfb_ctx *ctx, int level, float *host);             /* pyrDown chain, millimetres */
+int kfb_download_maps(kfb_ctx *ctx, int frame, int level, float *host_v3, float *host_n3);
+int kfb_upload_maps(kfb_ctx *ctx, int frame, int level, const float *host_v3, const float *host_n3);
+/* whole (slab of the) volume as int16 pairs in reference index order */
+int kfb_download_volume(kfb_ctx *ctx, int16_t *host);
+int kfb_upload_volume(kfb_ctx *ctx, const int16_t *host);
+size_t kfb_volume_voxels(const kfb_ctx *ctx);                                  /* voxels stored by this context */
+void kfb_level_intrinsics(const kfb_intrinsics *in, int level, kfb_intrinsics *out); /* types.hpp:18-28 */
+
+/* ---- measurement ------------------------------------------------------------------- */
+/* cudaEvent pool on the context stream: record slot i now; elapsed ms between slots. */
+int kfb_event_record(kfb_ctx *ctx, int slot);
+int kfb_event_elapsed_ms(kfb_ctx *ctx, int slot_a, int slot_b, float *ms);
+/* number of kernels this library has launched on this context since creation */
+uint64_t kfb_launch_count(const kfb_ctx *ctx);
+/* raw device pointers for zero-copy interop (NCCL / torch views); which: 0 volume,
+ * 1 prev vmap L0 (float4), 2 prev nmap L0 (float4), 3 cur depth L0 (float), 4 raycast hit-t (float) */
+void *kfb_device_ptr(kfb_ctx *ctx, int which);
+void *kfb_stream(kfb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KFB200_H */

@@ -695,19 +695,26 @@ int64_t kfo_extract_points(const int16_t *vol, const kfo_volume_desc *vd, const 
                     const float Fn = (float)vol[2 * j] * KFO_DIVSHORTMAX;
                     if (Wn == 0 || Fn == 1.f) continue;
                     if (!((F > 0 && Fn < 0) || (F < 0 && Fn > 0))) continue;
-                    float p[3] = {Vx, Vy, Vz};
-                    const float V = p[axis];
+                    const float Vv[3] = {Vx, Vy, Vz};
+                    const float V = Vv[axis];
                     const float Vn = V + vd->voxel_size[axis];
                     const float d_inv = 1.f / (fabsf(F) + fabsf(Fn));
-                    /* (V*|Fn| + Vn*|F|) * d_inv, contracted: fma(V,|Fn|, Vn*|F|) */
-                    p[axis] = fmaf(V, fabsf(Fn), Vn * fabsf(F)) * d_inv;
+                    /* (V*|Fn| + Vn*|F|) * d_inv as compiled: V*|Fn| rounded, |F|*Vn fused onto it */
+                    const float pi = fmaf(fabsf(F), Vn, V * fabsf(Fn)) * d_inv;
                     if (n < cap)
                     {
-                        float o[3];
-                        rot3(R, p[0], p[1], p[2], o);
-                        points3[3 * n + 0] = o[0] + t[0];
-                        points3[3 * n + 1] = o[1] + t[1];
-                        points3[3 * n + 2] = o[2] + t[2];
+                        /* aff.R * p + aff.t as compiled (loop-invariant products hoisted and rounded):
+                         *  x: fma(Vz,R2, fma(px,R0, Vy*R1));  y: fma(Vz,R2, fma(py,R1, Vx*R0));
+                         *  z: fma(pz,R2, Vy*R1 + Vx*R0) */
+                        for (int c = 0; c < 3; ++c)
+                        {
+                            const float r0 = R[3 * c], r1 = R[3 * c + 1], r2 = R[3 * c + 2];
+                            float o;
+                            if (axis == 0) o = fmaf(Vz, r2, fmaf(pi, r0, Vy * r1));
+                            else if (axis == 1) o = fmaf(Vz, r2, fmaf(pi, r1, Vx * r0));
+                            else o = fmaf(pi, r2, Vy * r1 + Vx * r0);
+                            points3[3 * n + c] = o + t[c];
+                        }
                     }
                     ++n;
                 }

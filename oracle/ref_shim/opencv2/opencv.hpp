@@ -15,6 +15,22 @@
 
 typedef unsigned char uchar;
 
+// Memory-safety interposer for the reference's ICP scratch: rigid_icp.cu:143
+// allocates pitch*nblocks BYTES but indexes rows with the pitch as an ELEMENT stride, which runs
+// up to ~46 KB past the allocation at pyramid levels 1-2.  The reference source stays unmodified;
+// only this allocation is enlarged so the harness cannot fault the GPU.  Results are unaffected.
+static inline cudaError_t kfshim_malloc_pitch(void **p, size_t *pitch, size_t width_bytes, size_t height)
+{
+    const size_t pb = (width_bytes + 511) / 512 * 512;
+    *pitch = pb;
+    const size_t rows = width_bytes / sizeof(float) + 1; // 27 rows are addressed
+    const size_t bytes = (rows * pb + height + 64) * sizeof(float);
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes);
+    return e;
+}
+#define cudaMallocPitch(p, pitch, w, h) kfshim_malloc_pitch((void **)(p), (pitch), (w), (h))
+
 #define CV_8UC3 16
 #define CV_32FC1 5
 #define CV_32FC3 21

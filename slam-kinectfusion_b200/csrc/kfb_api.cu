@@ -1,0 +1,377 @@
+// kfb_api.cu -- the C-ABI of include/kfb200.h: context lifetime, frame ingest, test hooks,
+// measurement helpers.  Compute entry points forward to the per-stage launchers.
+#include "kfb_common.cuh"
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+using namespace kfb;
+
+static thread_local std::string g_create_err;
+
+extern "C" {
+
+void kfb_level_intrinsics(const kfb_intrinsics *in, int level, kfb_intrinsics *out)
+{
+    // kf::Intrinsics::level, kfusion/include/types.hpp:18-28
+    if (level == 0) { *out = *in; return; }
+    const float s = powf(0.5f, (float)level);
+    out->width = in->width >> level;
+    out->height = in->height >> level;
+    out->fx = in->fx * s;
+    out->fy = in->fy * s;
+    out->cx = (in->cx + 0.5f) * s - 0.5f;
+    out->cy = (in->cy + 0.5f) * s - 0.5f;
+}
+
+void kfb_default_params(kfb_params *p, int dims)
+{
+    // kf::kinectfuison_params::default_params, kfusion/src/kinectfusion.cpp:167-190
+    memset(p, 0, sizeof(*p));
+    p->pyramid_height = 3;
+    p->bfilter_color_sigma = 10;
+    p->bfilter_spatial_sigma = 10;
+    p->bfilter_kernel_size = 5;
+    p->dfilter_dist = 5.f;
+    p->icp_angle_threshold = 30.f;
+    p->icp_dist_threshold = 0.015f;
+    p->icp_iter_count[0] = 4; p->icp_iter_count[1] = 5; p->icp_iter_count[2] = 10;
+    for (int i = 0; i < 3; ++i) { p->volu_dims[i] = dims; p->volu_range[i] = 3.f; }
+    p->volu_trun_dist = 2.1f * p->volu_range[0] / (float)p->volu_dims[0];
+    p->tsdf_max_weight = 64;
+    p->compat_icp_rows = 1;
+    p->compat_raycast_ts_sign = 1;
+    p->slab_z_begin = p->slab_z_end = 0;
+}
+
+int kfb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+#define KFB_HALO 3 // planes integrated redundantly on each side of a slab
+
+int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_ctx **out)
+{
+    if (!intr || !p || !out) return KFB_ERR_INVALID;
+    *out = nullptr;
+    if (p->pyramid_height < 1 || p->pyramid_height > KFB_MAX_LEVELS) return KFB_ERR_INVALID;
+    if (intr->width <= 0 || intr->height <= 0) return KFB_ERR_INVALID;
+    for (int i = 0; i < 3; ++i) if (p->volu_dims[i] < 4) return KFB_ERR_INVALID;
+    if (p->volu_dims[0] % 4 != 0) return KFB_ERR_UNSUPPORTED; // 128-bit voxel-row accesses
+    if ((intr->width >> (p->pyramid_height - 1)) < 3 || (intr->height >> (p->pyramid_height - 1)) < 3) return KFB_ERR_INVALID;
+    kfb_ctx *ctx = new (std::nothrow) kfb_ctx();
+    if (!ctx) return KFB_ERR_INVALID;
+    ctx->device = device;
+    ctx->intr = *intr;
+    ctx->p = *p;
+    ctx->levels = p->pyramid_height;
+    ctx->cur = 0; ctx->prev = 1;
+    ctx->launches = 0;
+    ctx->icp_seq = 0;
+    ctx->vol = nullptr; ctx->cloud = nullptr; ctx->cloud_cap = 0;
+    memset(ctx->L, 0, sizeof(ctx->L));
+    memset(ctx->events, 0, sizeof(ctx->events));
+    *out = ctx; // returned even on failure so the caller can read the error string, then destroy
+    KFB_CUDA(ctx, cudaSetDevice(device));
+    {
+        cudaDeviceProp prop;
+        KFB_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) { ctx->err = "kfb200 needs an sm_100a device (compute capability 10.x)"; return KFB_ERR_CUDA; }
+    }
+    KFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (int l = 0; l < ctx->levels; ++l)
+    {
+        kfb_intrinsics kl;
+        kfb_level_intrinsics(intr, l, &kl);
+        Level &L = ctx->L[l];
+        L.k.w = kl.width; L.k.h = kl.height; L.k.fx = kl.fx; L.k.fy = kl.fy; L.k.cx = kl.cx; L.k.cy = kl.cy;
+        const size_t n = (size_t)kl.width * kl.height;
+        KFB_CUDA(ctx, cudaMalloc(&L.raw, n * sizeof(float)));
+        KFB_CUDA(ctx, cudaMalloc(&L.depth, n * sizeof(float)));
+        for (int f = 0; f < 2; ++f)
+        {
+            KFB_CUDA(ctx, cudaMalloc(&L.v[f], n * sizeof(float4)));
+            KFB_CUDA(ctx, cudaMalloc(&L.n[f], n * sizeof(float4)));
+        }
+    }
+    // volume (or z-slab of it, with halo)
+    const int Z = p->volu_dims[2];
+    if (p->slab_z_end > p->slab_z_begin)
+    {
+        if (p->slab_z_begin < 0 || p->slab_z_end > Z) { ctx->err = "slab out of range"; return KFB_ERR_INVALID; }
+        ctx->z0 = p->slab_z_begin - KFB_HALO < 0 ? 0 : p->slab_z_begin - KFB_HALO;
+        ctx->z1 = p->slab_z_end + KFB_HALO > Z ? Z : p->slab_z_end + KFB_HALO;
+    }
+    else { ctx->z0 = 0; ctx->z1 = Z; }
+    ctx->vol_voxels = (size_t)p->volu_dims[0] * p->volu_dims[1] * (size_t)(ctx->z1 - ctx->z0);
+    for (int i = 0; i < 3; ++i) ctx->voxel_size[i] = p->volu_range[i] / (float)p->volu_dims[i]; // tsdf_volume.cpp:16
+    KFB_CUDA(ctx, cudaMalloc(&ctx->vol, ctx->vol_voxels * sizeof(uint32_t)));
+    const size_t n0 = (size_t)intr->width * intr->height;
+    KFB_CUDA(ctx, cudaMalloc(&ctx->tab_thr, n0 * sizeof(__half2)));
+    KFB_CUDA(ctx, cudaMalloc(&ctx->tab_exact, n0 * sizeof(float2)));
+    KFB_CUDA(ctx, cudaMalloc(&ctx->hit_t, n0 * sizeof(float)));
+    KFB_CUDA(ctx, cudaMalloc(&ctx->icp_partials, 1024 * 27 * sizeof(double)));
+    KFB_CUDA(ctx, cudaMalloc(&ctx->icp_ticket, sizeof(unsigned int)));
+    KFB_CUDA(ctx, cudaMemset(ctx->icp_ticket, 0, sizeof(unsigned int)));
+    KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->icp_host, sizeof(IcpHostResult), cudaHostAllocMapped));
+    memset((void *)ctx->icp_host, 0, sizeof(IcpHostResult));
+    KFB_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->icp_dev, (void *)ctx->icp_host, 0));
+    KFB_CUDA(ctx, cudaMalloc(&ctx->counters, 8 * sizeof(unsigned long long)));
+    KFB_CUDA(ctx, cudaMemset(ctx->counters, 0, 8 * sizeof(unsigned long long)));
+    KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->counters_host, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+    KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->pinned_depth, n0 * sizeof(float), cudaHostAllocDefault));
+    KFB_CUDA(ctx, cudaMalloc(&ctx->render_dev, n0 * 3));
+    KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->render_host, n0 * 3, cudaHostAllocDefault));
+    for (int i = 0; i < 64; ++i) KFB_CUDA(ctx, cudaEventCreate(&ctx->events[i]));
+    int rc = kfb_reset_frames(ctx);
+    if (rc) return rc;
+    rc = kfb_reset_volume(ctx);
+    if (rc) return rc;
+    KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KFB_OK;
+}
+
+void kfb_destroy(kfb_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int l = 0; l < KFB_MAX_LEVELS; ++l)
+    {
+        Level &L = ctx->L[l];
+        if (L.raw) cudaFree(L.raw);
+        if (L.depth) cudaFree(L.depth);
+        for (int f = 0; f < 2; ++f) { if (L.v[f]) cudaFree(L.v[f]); if (L.n[f]) cudaFree(L.n[f]); }
+    }
+    if (ctx->vol) cudaFree(ctx->vol);
+    if (ctx->tab_thr) cudaFree(ctx->tab_thr);
+    if (ctx->tab_exact) cudaFree(ctx->tab_exact);
+    if (ctx->hit_t) cudaFree(ctx->hit_t);
+    if (ctx->icp_partials) cudaFree(ctx->icp_partials);
+    if (ctx->icp_ticket) cudaFree(ctx->icp_ticket);
+    if (ctx->icp_host) cudaFreeHost((void *)ctx->icp_host);
+    if (ctx->counters) cudaFree(ctx->counters);
+    if (ctx->counters_host) cudaFreeHost(ctx->counters_host);
+    if (ctx->pinned_depth) cudaFreeHost(ctx->pinned_depth);
+    if (ctx->render_dev) cudaFree(ctx->render_dev);
+    if (ctx->render_host) cudaFreeHost(ctx->render_host);
+    if (ctx->cloud) cudaFree(ctx->cloud);
+    for (int i = 0; i < 64; ++i) if (ctx->events[i]) cudaEventDestroy(ctx->events[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    cudaGetLastError();
+    delete ctx;
+}
+
+const char *kfb_last_error_string(const kfb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int kfb_synchronize(kfb_ctx *ctx)
+{
+    KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KFB_OK;
+}
+
+int kfb_reset_volume(kfb_ctx *ctx) { return launch_reset_volume(ctx); }
+
+int kfb_reset_frames(kfb_ctx *ctx)
+{
+    for (int l = 0; l < ctx->levels; ++l)
+    {
+        Level &L = ctx->L[l];
+        const size_t n = (size_t)L.k.w * L.k.h;
+        KFB_CUDA(ctx, cudaMemsetAsync(L.raw, 0, n * sizeof(float), ctx->stream));
+        KFB_CUDA(ctx, cudaMemsetAsync(L.depth, 0, n * sizeof(float), ctx->stream));
+        for (int f = 0; f < 2; ++f)
+        {
+            KFB_CUDA(ctx, cudaMemsetAsync(L.v[f], 0, n * sizeof(float4), ctx->stream));
+            KFB_CUDA(ctx, cudaMemsetAsync(L.n[f], 0, n * sizeof(float4), ctx->stream));
+        }
+    }
+    return KFB_OK;
+}
+
+int kfb_upload_depth_mm(kfb_ctx *ctx, const float *host, int width, int height)
+{
+    if (!host || width != ctx->intr.width || height != ctx->intr.height) { ctx->err = "depth size mismatch"; return KFB_ERR_INVALID; }
+    const size_t bytes = (size_t)width * height * sizeof(float);
+    // pinned host memory goes straight over; pageable memory is staged through the context's pinned buffer
+    cudaPointerAttributes at;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&at, host) == cudaSuccess) pinned = (at.type == cudaMemoryTypeHost);
+    else cudaGetLastError();
+    if (!pinned)
+    {
+        KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // staging buffer may still be in flight
+        memcpy(ctx->pinned_depth, host, bytes);
+        host = ctx->pinned_depth;
+    }
+    KFB_CUDA(ctx, cudaMemcpyAsync(ctx->L[0].raw, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return KFB_OK;
+}
+
+int kfb_frontend(kfb_ctx *ctx) { return launch_frontend(ctx); }
+
+int kfb_swap_frames(kfb_ctx *ctx)
+{
+    const int t = ctx->cur; ctx->cur = ctx->prev; ctx->prev = t;
+    return KFB_OK;
+}
+
+int kfb_icp_accumulate(kfb_ctx *ctx, int level, const float pose12[12], double out27[27])
+{
+    if (!pose12 || !out27) return KFB_ERR_INVALID;
+    return launch_icp(ctx, level, pose12, out27);
+}
+
+int kfb_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_updated)
+{
+    if (!vol2cam12) return KFB_ERR_INVALID;
+    return launch_integrate(ctx, vol2cam12, n_updated);
+}
+
+int kfb_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9])
+{
+    if (!cam2vol12 || !rinv9) return KFB_ERR_INVALID;
+    return launch_raycast(ctx, cam2vol12, rinv9);
+}
+
+int kfb_model_pyramid(kfb_ctx *ctx) { return launch_model_pyramid(ctx); }
+
+int kfb_extract_points(kfb_ctx *ctx, const float volpose12[12], float *host_points3, size_t cap, size_t *n_points)
+{
+    if (!volpose12 || !host_points3 || !n_points || cap == 0) return KFB_ERR_INVALID;
+    return launch_extract(ctx, volpose12, host_points3, cap, n_points);
+}
+
+int kfb_render_phong(kfb_ctx *ctx, const float eye3[3], uint8_t *host_bgr)
+{
+    if (!eye3 || !host_bgr) return KFB_ERR_INVALID;
+    return launch_render(ctx, 1, eye3, host_bgr);
+}
+int kfb_render_normals(kfb_ctx *ctx, uint8_t *host_bgr)
+{
+    if (!host_bgr) return KFB_ERR_INVALID;
+    const float z[3] = {0, 0, 0};
+    return launch_render(ctx, 0, z, host_bgr);
+}
+
+// ---- hooks ----------------------------------------------------------------------------------------
+static int check_level(kfb_ctx *ctx, int level)
+{
+    if (level < 0 || level >= ctx->levels) { ctx->err = "level out of range"; return KFB_ERR_INVALID; }
+    return KFB_OK;
+}
+
+int kfb_download_depth(kfb_ctx *ctx, int level, float *host)
+{
+    if (check_level(ctx, level)) return KFB_ERR_INVALID;
+    const Level &L = ctx->L[level];
+    KFB_CUDA(ctx, cudaMemcpyAsync(host, L.depth, (size_t)L.k.w * L.k.h * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KFB_OK;
+}
+int kfb_download_raw_depth(kfb_ctx *ctx, int level, float *host)
+{
+    if (check_level(ctx, level)) return KFB_ERR_INVALID;
+    const Level &L = ctx->L[level];
+    KFB_CUDA(ctx, cudaMemcpyAsync(host, L.raw, (size_t)L.k.w * L.k.h * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KFB_OK;
+}
+int kfb_upload_depth_m(kfb_ctx *ctx, int level, const float *host)
+{
+    if (check_level(ctx, level)) return KFB_ERR_INVALID;
+    const Level &L = ctx->L[level];
+    KFB_CUDA(ctx, cudaMemcpyAsync(L.depth, host, (size_t)L.k.w * L.k.h * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KFB_OK;
+}
+int kfb_download_maps(kfb_ctx *ctx, int frame, int level, float *host_v3, float *host_n3)
+{
+    if (check_level(ctx, level)) return KFB_ERR_INVALID;
+    const Level &L = ctx->L[level];
+    const int f = frame == KFB_FRAME_CUR ? ctx->cur : ctx->prev;
+    const size_t n = (size_t)L.k.w * L.k.h;
+    float *tmp = nullptr;
+    KFB_CUDA(ctx, cudaMalloc(&tmp, n * 3 * sizeof(float)));
+    int rc = KFB_OK;
+    for (int m = 0; m < 2 && rc == KFB_OK; ++m)
+    {
+        float *dst = m == 0 ? host_v3 : host_n3;
+        if (!dst) continue;
+        rc = launch_map_convert(ctx, m == 0 ? L.v[f] : L.n[f], tmp, n);
+        if (rc == KFB_OK && cudaMemcpyAsync(dst, tmp, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = KFB_ERR_CUDA;
+        if (rc == KFB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = KFB_ERR_CUDA;
+    }
+    cudaFree(tmp);
+    if (rc == KFB_ERR_CUDA && ctx->err.empty()) ctx->err = cudaGetErrorString(cudaGetLastError());
+    return rc;
+}
+int kfb_upload_maps(kfb_ctx *ctx, int frame, int level, const float *host_v3, const float *host_n3)
+{
+    if (check_level(ctx, level)) return KFB_ERR_INVALID;
+    const Level &L = ctx->L[level];
+    const int f = frame == KFB_FRAME_CUR ? ctx->cur : ctx->prev;
+    const size_t n = (size_t)L.k.w * L.k.h;
+    float *tmp = nullptr;
+    KFB_CUDA(ctx, cudaMalloc(&tmp, n * 3 * sizeof(float)));
+    int rc = KFB_OK;
+    for (int m = 0; m < 2 && rc == KFB_OK; ++m)
+    {
+        const float *src = m == 0 ? host_v3 : host_n3;
+        if (!src) continue;
+        if (cudaMemcpyAsync(tmp, src, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) rc = KFB_ERR_CUDA;
+        if (rc == KFB_OK) rc = launch_map_convert_in(ctx, tmp, m == 0 ? L.v[f] : L.n[f], n);
+        if (rc == KFB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = KFB_ERR_CUDA;
+    }
+    cudaFree(tmp);
+    if (rc == KFB_ERR_CUDA && ctx->err.empty()) ctx->err = cudaGetErrorString(cudaGetLastError());
+    return rc;
+}
+int kfb_download_volume(kfb_ctx *ctx, int16_t *host)
+{
+    KFB_CUDA(ctx, cudaMemcpyAsync(host, ctx->vol, ctx->vol_voxels * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KFB_OK;
+}
+int kfb_upload_volume(kfb_ctx *ctx, const int16_t *host)
+{
+    KFB_CUDA(ctx, cudaMemcpyAsync(ctx->vol, host, ctx->vol_voxels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KFB_OK;
+}
+size_t kfb_volume_voxels(const kfb_ctx *ctx) { return ctx->vol_voxels; }
+
+// ---- measurement ------------------------------------------------------------------------------------
+int kfb_event_record(kfb_ctx *ctx, int slot)
+{
+    if (slot < 0 || slot >= 64) return KFB_ERR_INVALID;
+    KFB_CUDA(ctx, cudaEventRecord(ctx->events[slot], ctx->stream));
+    return KFB_OK;
+}
+int kfb_event_elapsed_ms(kfb_ctx *ctx, int a, int b, float *ms)
+{
+    if (a < 0 || a >= 64 || b < 0 || b >= 64 || !ms) return KFB_ERR_INVALID;
+    KFB_CUDA(ctx, cudaEventSynchronize(ctx->events[b]));
+    KFB_CUDA(ctx, cudaEventElapsedTime(ms, ctx->events[a], ctx->events[b]));
+    return KFB_OK;
+}
+uint64_t kfb_launch_count(const kfb_ctx *ctx) { return ctx->launches; }
+void *kfb_device_ptr(kfb_ctx *ctx, int which)
+{
+    switch (which)
+    {
+    case 0: return ctx->vol;
+    case 1: return ctx->L[0].v[ctx->prev];
+    case 2: return ctx->L[0].n[ctx->prev];
+    case 3: return ctx->L[0].depth;
+    case 4: return ctx->hit_t;
+    default: return nullptr;
+    }
+}
+void *kfb_stream(kfb_ctx *ctx) { return (void *)ctx->stream; }
+
+} // extern "C"

@@ -1,0 +1,153 @@
+"""ctypes binding of the C++ host facade (libkfusion_b200.so): kf::kinectfusion driven exactly
+as an application drives the reference's class (kfusion/include/kinectfusion.h:31-73)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .binding import Intrinsics, KfbError, KFB_MAX_LEVELS, load_library, Context
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+_vp = C.c_void_p
+
+
+class HostParams(C.Structure):
+    _fields_ = [("pyramid_height", C.c_int), ("dfilter_dist", C.c_float), ("bfilter_kernel_size", C.c_int),
+                ("bfilter_spatial_sigma", C.c_float), ("bfilter_color_sigma", C.c_float),
+                ("icp_dist_threshold", C.c_float), ("icp_angle_threshold", C.c_float),
+                ("icp_iter_count", C.c_int * KFB_MAX_LEVELS), ("volu_dims", C.c_int * 3),
+                ("volu_range", C.c_float * 3), ("volu_pose", C.c_float * 12), ("volu_trun_dist", C.c_float),
+                ("tsdf_max_weight", C.c_int), ("compat_icp_rows", C.c_int), ("compat_raycast_ts_sign", C.c_int),
+                ("device", C.c_int)]
+
+
+def host_library_path():
+    return os.path.join(_HERE, "libkfusion_b200.so")
+
+
+def load_host_library():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    load_library()  # dependency, loads libkfb200.so first (fails loudly if missing)
+    path = host_library_path()
+    if not os.path.exists(path):
+        raise KfbError(f"{path} is missing: build it with __graft_entry__.build()")
+    L = C.CDLL(path)
+    sig = {
+        "kfh_default_params": (None, [C.POINTER(HostParams), C.c_int]),
+        "kfh_create": (_vp, [C.POINTER(Intrinsics), C.POINTER(HostParams)]),
+        "kfh_last_error": (C.c_char_p, []),
+        "kfh_destroy": (None, [_vp]),
+        "kfh_reset": (None, [_vp]),
+        "kfh_pipeline": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+        "kfh_frame_count": (C.c_int, [_vp]),
+        "kfh_num_poses": (C.c_int, [_vp]),
+        "kfh_get_pose": (None, [_vp, C.c_int, _vp]),
+        "kfh_context": (_vp, [_vp]),
+        "kfh_render": (C.c_int, [_vp, C.c_int, _vp]),
+        "kfh_extract_pointcloud": (C.c_long, [_vp, _vp, C.c_long]),
+        "kfh_save_pointcloud": (C.c_int, [_vp, C.c_char_p]),
+        "kfh_icp_solve": (C.c_int, [_vp, _vp]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype, f.argtypes = res, args
+    _LIB = L
+    return L
+
+
+def default_host_params(dims=512):
+    p = HostParams()
+    load_host_library().kfh_default_params(C.byref(p), int(dims))
+    return p
+
+
+def icp_solve(sums27):
+    s = np.ascontiguousarray(sums27, np.float64)
+    x = np.zeros(6, np.float64)
+    rc = load_host_library().kfh_icp_solve(s.ctypes.data_as(_vp), x.ctypes.data_as(_vp))
+    return rc, x
+
+
+class _BorrowedContext(Context):
+    """A Context view over the kfb_ctx owned by a kf::kinectfusion (test hooks only)."""
+
+    def __init__(self, handle, intr, params):  # noqa: D401 - no kfb_create here
+        self.lib = load_library()
+        self.h = _vp(handle)
+        self.intr, self.params = intr, params
+
+    def close(self):
+        self.h = None
+
+
+class KinectFusion:
+    """kf::kinectfusion(intr, params).pipeline(cmap, dmap) -- the public API a user calls."""
+
+    def __init__(self, intr, params=None):
+        self.lib = load_host_library()
+        self.intr = intr
+        self.params = params if params is not None else default_host_params(512)
+        self.h = self.lib.kfh_create(C.byref(intr), C.byref(self.params))
+        if not self.h:
+            raise KfbError("kf::kinectfusion construction failed: " + self.lib.kfh_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.kfh_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def pipeline(self, depth_mm):
+        """depth_mm: float32 HxW millimetres (numpy, pageable or pinned)."""
+        d = np.ascontiguousarray(depth_mm, np.float32)
+        self._keep = d
+        return self.lib.kfh_pipeline(self.h, d.ctypes.data_as(_vp), d.shape[1], d.shape[0])
+
+    def pipeline_ptr(self, ptr, w, h):
+        return self.lib.kfh_pipeline(self.h, ptr, w, h)
+
+    def reset(self):
+        self.lib.kfh_reset(self.h)
+
+    @property
+    def frame_count(self):
+        return self.lib.kfh_frame_count(self.h)
+
+    def pose(self, idx=-1):
+        p = np.empty(12, np.float32)
+        self.lib.kfh_get_pose(self.h, idx, p.ctypes.data_as(_vp))
+        return p
+
+    def poses(self):
+        return np.stack([self.pose(i) for i in range(self.lib.kfh_num_poses(self.h))])
+
+    def context(self):
+        from .binding import Params
+        p = Params()
+        load_library().kfb_default_params(C.byref(p), int(self.params.volu_dims[0]))
+        for i in range(3):
+            p.volu_dims[i] = self.params.volu_dims[i]
+            p.volu_range[i] = self.params.volu_range[i]
+        p.pyramid_height = self.params.pyramid_height
+        return _BorrowedContext(self.lib.kfh_context(self.h), self.intr, p)
+
+    def render(self, normal=False):
+        out = np.empty((self.intr.height, self.intr.width, 3), np.uint8)
+        self.lib.kfh_render(self.h, int(normal), out.ctypes.data_as(_vp))
+        return out
+
+    def extract_pointcloud(self, cap=10_000_000):
+        pts = np.empty((cap, 3), np.float32)
+        n = self.lib.kfh_extract_pointcloud(self.h, pts.ctypes.data_as(_vp), cap)
+        return pts[:min(n, cap)].copy()
+
+    def save_pointcloud(self, path):
+        self.lib.kfh_save_pointcloud(self.h, path.encode())

@@ -1,0 +1,120 @@
+// c_api.cpp -- extern "C" handle API over kf::kinectfusion so the facade can be driven from
+// ctypes (tests, bench.py) exactly as a C++ application drives the reference's class.
+#include <kinectfusion.h>
+#include <cstring>
+#include <string>
+
+struct kfh_params
+{
+    int pyramid_height;
+    float dfilter_dist;
+    int bfilter_kernel_size;
+    float bfilter_spatial_sigma, bfilter_color_sigma;
+    float icp_dist_threshold, icp_angle_threshold;
+    int icp_iter_count[KFB_MAX_LEVELS];
+    int volu_dims[3];
+    float volu_range[3];
+    float volu_pose[12];
+    float volu_trun_dist;
+    int tsdf_max_weight;
+    int compat_icp_rows, compat_raycast_ts_sign;
+    int device;
+};
+
+static thread_local std::string g_err;
+
+extern "C" {
+
+void kfh_default_params(kfh_params *o, int dims)
+{
+    kf::kinectfuison_params p = kf::kinectfuison_params::default_params();
+    std::memset(o, 0, sizeof(*o));
+    o->pyramid_height = p.pyramid_height;
+    o->dfilter_dist = p.dfilter_dist;
+    o->bfilter_kernel_size = p.bfilter_kernel_size;
+    o->bfilter_spatial_sigma = p.bfilter_spatial_sigma;
+    o->bfilter_color_sigma = p.bfilter_color_sigma;
+    o->icp_dist_threshold = p.icp_dist_threshold;
+    o->icp_angle_threshold = p.icp_angle__threshold;
+    for (size_t i = 0; i < p.icp_iter_count.size(); ++i) o->icp_iter_count[i] = p.icp_iter_count[i];
+    for (int i = 0; i < 3; ++i) { o->volu_dims[i] = dims; o->volu_range[i] = p.volu_range(i); }
+    p.volu_pose.to12(o->volu_pose);
+    o->volu_trun_dist = 2.1f * p.volu_range(0) / (float)dims;
+    o->tsdf_max_weight = p.tsdf_max_weight;
+    o->compat_icp_rows = 1;
+    o->compat_raycast_ts_sign = 1;
+    o->device = 0;
+}
+
+void *kfh_create(const kfb_intrinsics *k, const kfh_params *q)
+{
+    try
+    {
+        kf::Intrinsics intr{k->width, k->height, k->fx, k->fy, k->cx, k->cy};
+        kf::kinectfuison_params p = kf::kinectfuison_params::default_params();
+        p.pyramid_height = q->pyramid_height;
+        p.dfilter_dist = q->dfilter_dist;
+        p.bfilter_kernel_size = q->bfilter_kernel_size;
+        p.bfilter_spatial_sigma = q->bfilter_spatial_sigma;
+        p.bfilter_color_sigma = q->bfilter_color_sigma;
+        p.icp_dist_threshold = q->icp_dist_threshold;
+        p.icp_angle__threshold = q->icp_angle_threshold;
+        p.icp_iter_count.assign(q->icp_iter_count, q->icp_iter_count + q->pyramid_height);
+        for (int i = 0; i < 3; ++i) { p.volu_dims(i) = q->volu_dims[i]; p.volu_range(i) = q->volu_range[i]; }
+        p.volu_pose = cv::Affine3f::from12(q->volu_pose);
+        p.volu_trun_dist = q->volu_trun_dist;
+        p.tsdf_max_weight = q->tsdf_max_weight;
+        p.compat_icp_rows = q->compat_icp_rows;
+        p.compat_raycast_ts_sign = q->compat_raycast_ts_sign;
+        p.device = q->device;
+        return new kf::kinectfusion(intr, p);
+    }
+    catch (const std::exception &e)
+    {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+const char *kfh_last_error(void) { return g_err.c_str(); }
+void kfh_destroy(void *h) { delete static_cast<kf::kinectfusion *>(h); }
+void kfh_reset(void *h) { static_cast<kf::kinectfusion *>(h)->reset(); }
+/* returns 0 ok, 1 tracking failure (reset done, kinectfusion.cpp:97-102) */
+int kfh_pipeline(void *h, const float *depth_mm, int width, int height)
+{
+    kf::kinectfusion *k = static_cast<kf::kinectfusion *>(h);
+    k->pipeline(depth_mm, width, height);
+    return k->last_tracking_ok ? 0 : 1;
+}
+int kfh_frame_count(void *h) { return static_cast<kf::kinectfusion *>(h)->frame_count; }
+int kfh_num_poses(void *h) { return (int)static_cast<kf::kinectfusion *>(h)->pose_record.size(); }
+void kfh_get_pose(void *h, int idx, float pose12[12])
+{
+    kf::kinectfusion *k = static_cast<kf::kinectfusion *>(h);
+    if (idx < 0 || idx >= (int)k->pose_record.size()) idx = (int)k->pose_record.size() - 1;
+    k->pose_record[idx].to12(pose12);
+}
+void *kfh_context(void *h) { return static_cast<kf::kinectfusion *>(h)->context(); }
+int kfh_render(void *h, int normal, uint8_t *bgr)
+{
+    kf::kinectfusion *k = static_cast<kf::kinectfusion *>(h);
+    cv::Mat m = k->getRenderMap(normal ? kf::kinectfusion::NORMAL : kf::kinectfusion::PHONG);
+    std::memcpy(bgr, m.ptr<uint8_t>(), (size_t)m.rows * m.cols * 3);
+    return 0;
+}
+/* extracePointcloud(): returns N, copies up to cap points */
+long kfh_extract_pointcloud(void *h, float *points3, long cap)
+{
+    kf::kinectfusion *k = static_cast<kf::kinectfusion *>(h);
+    cv::Mat m = k->extracePointcloud();
+    const long n = m.cols < cap ? m.cols : cap;
+    if (n > 0) std::memcpy(points3, m.ptr<float>(), (size_t)n * 12);
+    return m.cols;
+}
+int kfh_save_pointcloud(void *h, const char *path)
+{
+    static_cast<kf::kinectfusion *>(h)->savePointcloud(path);
+    return 0;
+}
+int kfh_icp_solve(const double in27[27], double x6[6]) { return kf::ICPRegistration::solve(in27, x6) ? 0 : 1; }
+
+} // extern "C"

@@ -1,0 +1,92 @@
+// icp_registration.cpp -- coarse-to-fine ICP loop and the host 6x6 solve
+// (mirrors kfusion/src/icp_registration.cpp:3-45 of the reference).
+#include <icp_registration.hpp>
+#include <safe_call.hpp>
+#include <cstring>
+
+kf::ICPRegistration::ICPRegistration(const float d, const float a) : dist_thres(d)
+{
+    angle_thres = sinf(deg2rad(a)); // icp_registration.cpp:5 -- the gate is a sine
+}
+void kf::ICPRegistration::setMaxDistThres(const float v) { dist_thres = v; }
+void kf::ICPRegistration::setMaxAngleThres(const float v) { angle_thres = deg2rad(v); } // sic, as the reference (:10)
+void kf::ICPRegistration::setIterationNum(const std::vector<int> &iters_) { iters = iters_; }
+void kf::ICPRegistration::setIntrinsics(const Intrinsics intrs_) { intrs = intrs_; }
+
+// rigid_icp.cu:156-165 (unpack) + icp_registration.cpp:35-39 (guard + solve)
+bool kf::ICPRegistration::solve(const double in27[27], double x6[6])
+{
+    double A[6][6], b[6];
+    int s = 0;
+    for (int i = 0; i < 6; ++i)
+        for (int j = i; j < 7; ++j)
+        {
+            const double v = in27[s++];
+            if (j == 6) b[i] = v;
+            else A[i][j] = A[j][i] = v;
+        }
+    // determinant by LU with partial pivoting (cv::determinant on a Matx66d)
+    double M[6][7];
+    for (int i = 0; i < 6; ++i) { for (int j = 0; j < 6; ++j) M[i][j] = A[i][j]; M[i][6] = b[i]; }
+    double det = 1.0;
+    bool singular = false;
+    for (int c = 0; c < 6; ++c)
+    {
+        int p = c;
+        for (int r = c + 1; r < 6; ++r) if (std::fabs(M[r][c]) > std::fabs(M[p][c])) p = r;
+        if (M[p][c] == 0.0 || std::isnan(M[p][c])) { det = std::isnan(M[p][c]) ? NAN : 0.0; singular = true; break; }
+        if (p != c) { for (int j = 0; j < 7; ++j) std::swap(M[c][j], M[p][j]); det = -det; }
+        det *= M[c][c];
+        for (int r = c + 1; r < 6; ++r)
+        {
+            const double f = M[r][c] / M[c][c];
+            for (int j = c; j < 7; ++j) M[r][j] -= f * M[c][j];
+        }
+    }
+    if (singular || std::fabs(det) < 1e-15 || std::isnan(det)) return false;
+    // Cholesky A = L L^T (north star), LU back-substitution if A is not numerically PD
+    double L[6][6];
+    bool ok = true;
+    std::memset(L, 0, sizeof(L));
+    for (int i = 0; i < 6 && ok; ++i)
+        for (int j = 0; j <= i; ++j)
+        {
+            double sum = A[i][j];
+            for (int q = 0; q < j; ++q) sum -= L[i][q] * L[j][q];
+            if (i == j) { if (!(sum > 0.0)) { ok = false; break; } L[i][i] = std::sqrt(sum); }
+            else L[i][j] = sum / L[j][j];
+        }
+    if (ok)
+    {
+        double y[6];
+        for (int i = 0; i < 6; ++i) { double sum = b[i]; for (int q = 0; q < i; ++q) sum -= L[i][q] * y[q]; y[i] = sum / L[i][i]; }
+        for (int i = 5; i >= 0; --i) { double sum = y[i]; for (int q = i + 1; q < 6; ++q) sum -= L[q][i] * x6[q]; x6[i] = sum / L[i][i]; }
+    }
+    else
+    {
+        for (int i = 5; i >= 0; --i) { double sum = M[i][6]; for (int q = i + 1; q < 6; ++q) sum -= M[i][q] * x6[q]; x6[i] = sum / M[i][i]; }
+    }
+    return true;
+}
+
+bool kf::ICPRegistration::rigidTransform(cv::Affine3f &camera_pose, const cv::Affine3f /*prepose*/, const Frame *cframe, const Frame * /*pframe*/)
+{
+    // The reference's `camera_pose.Identity()` (:18) is a no-op on a default-constructed pose; same start here.
+    camera_pose = cv::Affine3f::Identity();
+    kfb_ctx *ctx = cframe->dev->ctx;
+    for (int level = (int)iters.size() - 1; level >= 0; level--)
+    {
+        for (int i = 0; i < iters[level]; i++)
+        {
+            float pose12[12];
+            double sums[27], x[6];
+            camera_pose.to12(pose12);
+            if (kfbSafeCall(ctx, kfb_icp_accumulate(ctx, level, pose12, sums)) != KFB_OK) return false;
+            if (!solve(sums, x)) return false;
+            // Tinc = Affine3f(rvec = x[0..2] (float), t = x[3..5]); pose = pose * Tinc (right-multiply, :41-42)
+            cv::Affine3f Tinc(cv::Vec3f((float)x[0], (float)x[1], (float)x[2]), cv::Vec3f((float)x[3], (float)x[4], (float)x[5]));
+            camera_pose = camera_pose * Tinc;
+        }
+    }
+    return true;
+}

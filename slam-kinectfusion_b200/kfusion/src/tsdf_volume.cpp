@@ -1,0 +1,58 @@
+// tsdf_volume.cpp -- kf::TSDFVolume host side: pose algebra and hand-off to the C-ABI
+// (mirrors kfusion/src/tsdf_volume.cpp:13-84 of the reference).
+#include <tsdf_volume.hpp>
+#include <safe_call.hpp>
+
+namespace kf
+{
+std::vector<int16_t> TSDFVolume::Data()
+{
+    std::vector<int16_t> out(2 * kfb_volume_voxels(dev->ctx));
+    kfbSafeCall(dev->ctx, kfb_download_volume(dev->ctx, out.data()));
+    return out;
+}
+cv::Vec3f TSDFVolume::VoxelSize() { return voxel_size; }
+cv::Vec3f TSDFVolume::SceneSize() { return scene_size; }
+cv::Vec3i TSDFVolume::Dims() { return dims; }
+void TSDFVolume::setTrunDist(const float v) { trun_dist = v; }
+void TSDFVolume::setMaxWeight(const int w) { max_weight = w; }
+void TSDFVolume::setPose(const cv::Affine3f p) { volume_pose = p; }
+void TSDFVolume::setIntrinsics(const Intrinsics i) { intr = i; }
+
+TSDFVolume::TSDFVolume(const DeviceContextPtr &dev_, const cv::Vec3f scene_size_, const cv::Vec3i dims_)
+    : dev(dev_), scene_size(scene_size_), dims(dims_)
+{
+    voxel_size = cv::Vec3f(scene_size_(0) / dims_(0), scene_size_(1) / dims_(1), scene_size_(2) / dims_(2)); // :16
+    reset();
+}
+void TSDFVolume::reset() { if (dev) kfbSafeCall(dev->ctx, kfb_reset_volume(dev->ctx)); }
+void TSDFVolume::release() { dev.reset(); }
+
+void TSDFVolume::integrate(const cv::Affine3f &camera_pose)
+{
+    const cv::Affine3f vol2cam = camera_pose.inv() * volume_pose; // :50
+    float p[12];
+    vol2cam.to12(p);
+    kfbSafeCall(dev->ctx, kfb_integrate(dev->ctx, p, nullptr));
+}
+void TSDFVolume::raycast(const cv::Affine3f &camera_pose)
+{
+    const cv::Affine3f cam2vol = volume_pose.inv() * camera_pose; // :59
+    // cam2vol.rotation().inv(DECOMP_SVD) (:61): inverse of the rotation block
+    cv::Affine3f rot_only(cam2vol.rotation(), cv::Vec3f(0.f, 0.f, 0.f));
+    const cv::Matx33f Rinv = rot_only.inv().rotation();
+    float p[12];
+    cam2vol.to12(p);
+    kfbSafeCall(dev->ctx, kfb_raycast(dev->ctx, p, Rinv.val));
+}
+cv::Mat TSDFVolume::fetchPointCloud()
+{
+    enum { DEFAULT_CLOUD_BUFFER_SIZE = 10 * 1000 * 1000 }; // :65-68
+    std::vector<float> pts((size_t)DEFAULT_CLOUD_BUFFER_SIZE * 3);
+    float vp[12];
+    volume_pose.to12(vp);
+    size_t n = 0;
+    kfbSafeCall(dev->ctx, kfb_extract_points(dev->ctx, vp, pts.data(), DEFAULT_CLOUD_BUFFER_SIZE, &n));
+    return cv::Mat(1, (int)n, cv::CV_32FC3, pts.data());
+}
+} // namespace kf
