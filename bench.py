@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py -- the KinectFusion hot path on B200, measured per the driver contract.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is one full frame of the hot path over one synthetic 640x480 depth image:
+front end (pyrDown, bilateral, vertex/normal maps) + 3-level ICP (10/5/4 iterations, host 6x6
+solve) + TSDF integration + raycast + model-map pyramid.
+
+  N = 1   workload = BASELINE.json configs[1]: 640x480 depth, 512^3 TSDF over 3 m, 300-frame looped
+          synthetic trajectory (analytic box+sphere room).  `ms_per_step` IS the headline
+          "frame device-ms at 640x480/512^3".
+  N > 1   the volume is the only part of the path that shards: z-slab sharded
+          volume with ~512^3 voxels per GPU (640^3 / 812^3 / 1024^3 at N = 2 / 4 / 8), every rank
+          integrating its slab of the same frame with no data-path collective => "weak".
+
+`value` = TSDF voxel-updates/s sustained over whole frames = (voxels passing the reference's update
+predicate per frame, summed over ranks) / (device time per frame, max over ranks).  Both arms see
+the same frames, so the ratio of the two arms' values is the frame-rate ratio.  The kernel-only
+integration rate is in `roofline` (8 B per updated voxel against the measured HBM copy bandwidth).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "TSDF voxel-updates/s sustained over full frames (frame device-ms at 640x480/512^3 = ms_per_step)"
+UNIT = "voxel-updates/s"
+WEAK_DIMS = {1: 512, 2: 640, 4: 812, 8: 1024}
+
+
+def measured_peak_hbm():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def oracle_frames_per_s(dims, frames, threads):
+    """CPU baseline: the oracle's whole pipeline (oracle/kf_oracle.c, OpenMP) on a bounded sample."""
+    from oracle import kfo
+    kfo.build()
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    K = kfo.intr()
+    kf = kfo.Kinfu(K, kfo.default_params(dims))
+    t_frames, U = [], []
+    for i, (pose, d) in enumerate(frames):
+        t0 = time.perf_counter()
+        rc = kf.pipeline(d)
+        dt = time.perf_counter() - t0
+        assert rc == 0
+        if i >= 1:                 # frame 1 is the bootstrap (no ICP / raycast), like the reference's timer
+            t_frames.append(dt)
+            U.append(kf.last_updated)
+    return float(np.mean(U)) / float(np.mean(t_frames)), float(np.mean(t_frames)), float(np.mean(U))
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's implementation of the path on this box.  The reference is
+    CUDA-only and needs OpenCV-CUDA for its host pipeline, which does not exist here, so this arm is
+    the scalar/OpenMP oracle port on the host cores (kind "port"); the reference's own kernels rebuilt
+    for sm_100a (oracle/_ref) are timed per stage in profiles/ and tests/test_ref_ab.py."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from slam_kinectfusion_b200 import synth
+    import slam_kinectfusion_b200 as kfb
+    dims = WEAK_DIMS.get(args.gpus, 512) if args.dims is None else args.dims
+    if args.gpus > 1:
+        dims = 512   # the port times the per-GPU share of the weak-scaled job: one 512^3-voxel frame
+    cores = os.cpu_count() or 1
+    K = kfb.Intrinsics(**kfb.SENSORS["kinect1"])
+    n = 1 + args.warmup + args.steps
+    n = min(n, 1 + 2 + 6)         # bounded sample: ~1.5 s per 512^3 frame on 16 cores
+    frames = synth.sequence(n, K)
+    t0 = time.perf_counter()
+    value, sec_per_frame, U = oracle_frames_per_s(dims, frames, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": n - 1, "warmup": 0, "ms_per_step": sec_per_frame * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 -> int16 tsdf", "data": "synthetic",
+        "config": {"workload": f"640x480 depth, {dims}^3 TSDF over 3 m, ICP 10/5/4, synthetic box+sphere room trajectory",
+                   "l2": "inputs larger than L2 (volume swept every frame)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n - 1} frames after the bootstrap frame, whole pipeline, OpenMP over {cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import slam_kinectfusion_b200 as kfb
+    from slam_kinectfusion_b200 import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+
+    dims = args.dims if args.dims else WEAK_DIMS.get(world, 512)
+    K = kfb.Intrinsics(**kfb.SENSORS["kinect1"])
+    W, S = args.warmup, args.steps
+    n_frames = 1 + W + S                       # frame 0 bootstraps the volume (no ICP / raycast)
+    frames = synth.sequence(n_frames, K)
+    w, h = K.width, K.height
+    frame_bytes = w * h * 4
+
+    # inputs: pinned host copies (e2e) and device-resident copies (device-timed value)
+    host_pin = torch.empty((n_frames, h, w), dtype=torch.float32).pin_memory()
+    for i, (_, d) in enumerate(frames):
+        host_pin[i].copy_(torch.from_numpy(d))
+    dev_frames = host_pin.to(f"cuda:{local}", non_blocking=False)
+    torch.cuda.synchronize()
+
+    hp = kfb.default_host_params(dims)
+    hp.device = local
+    if world > 1:
+        from slam_kinectfusion_b200 import sharded
+        return sharded.run_bench(args, dist, rank, world, local, dims, K, frames, host_pin, dev_frames,
+                                 METRIC, UNIT, measured_peak_hbm, ClockSampler)
+
+    kf = kfb.KinectFusion(K, hp)
+    ctx = kf.context()
+
+    def run(seq_ptrs, timed_from):
+        """Feed frames; returns (device ms over the timed part, wall s over the timed part, launches)."""
+        kf.reset()
+        l0 = t0 = None
+        for i, ptr in enumerate(seq_ptrs):
+            if i == timed_from:
+                ctx.synchronize()
+                l0 = ctx.launch_count()
+                ctx.event_record(0)
+                t0 = time.perf_counter()
+            rc = kf.pipeline_ptr(ptr, w, h)
+            if rc != 0:
+                raise SystemExit(f"tracking failure at frame {i}")
+            _ = kf.pose()                      # the frame's result on the host (ICP sums already crossed PCIe)
+        ctx.event_record(1)
+        ctx.synchronize()
+        wall = time.perf_counter() - t0
+        return ctx.event_elapsed_ms(0, 1), wall, ctx.launch_count() - l0
+
+    dptr = [dev_frames[i].data_ptr() for i in range(n_frames)]
+    hptr = [host_pin[i].data_ptr() for i in range(n_frames)]
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    dev_ms, _, launches = run(dptr, 1 + W)
+    clocks = sampler.stop()
+    ms_per_frame = dev_ms / S
+    e2e_ms, e2e_wall, _ = run(hptr, 1 + W)
+    e2e_ms_per_frame = max(e2e_ms, e2e_wall * 1e3) / S
+    poses = kf.poses()
+
+    # ---- outside the timed region: updated-voxel counts and the integrate kernel's own duration
+    ctx.set_profiling(True)
+    volpose = np.array(hp.volu_pose, np.float32).reshape(3, 4)
+
+    def vol2cam(p12):
+        P = np.vstack([np.asarray(p12, np.float64).reshape(3, 4), [0, 0, 0, 1]])
+        V = np.vstack([volpose.astype(np.float64), [0, 0, 0, 1]])
+        return (np.linalg.inv(P) @ V)[:3].astype(np.float32).reshape(12)
+
+    U, k_ms, rc_ms = [], [], []
+    for i in range(1 + W, n_frames, max(1, S // 16)):
+        ctx.upload_depth_mm_ptr(dptr[i], w, h)
+        ctx.frontend()
+        v2c = vol2cam(poses[i])
+        U.append(ctx.integrate(v2c, count=True))
+        for _ in range(3):
+            ctx.integrate(v2c)
+            k_ms.append(ctx.event_elapsed_ms(60, 61))
+    ctx.set_profiling(False)
+    U_mean = float(np.mean(U))
+    k_ms_mean = float(np.mean(k_ms))
+    peak, peak_src = measured_peak_hbm()
+    achieved = 8.0 * U_mean / (k_ms_mean * 1e-3) / 1e9
+    swept = dims * dims * (dims - 1)
+
+    # ---- CPU baseline (oracle port) on a bounded sample, rank 0 / N = 1 only
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        nb = 1 + 6
+        cval, csec, cU = oracle_frames_per_s(dims, frames[:nb], cores)
+        cpu = {"value": cval, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{nb - 1} frames after the bootstrap frame of the same sequence, whole pipeline "
+                         f"(oracle/kf_oracle.c, OpenMP {cores} threads), {csec * 1e3:.0f} ms/frame"}
+
+    line = {
+        "metric": METRIC, "value": U_mean / (ms_per_frame * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": S, "warmup": W,
+        "ms_per_step": ms_per_frame, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 -> int16 tsdf", "data": "synthetic",
+        "config": {"workload": f"640x480 depth, {dims}^3 TSDF over 3 m, ICP 10/5/4, 300-frame looped synthetic "
+                               "box+sphere room trajectory (BASELINE configs[1])",
+                   "l2": f"inputs larger than L2: the {dims ** 3 * 4 >> 20} MiB volume is swept by integrate and raycast every frame",
+                   "frames_timed": S, "updated_voxels_per_frame": U_mean, "swept_voxels_per_frame": swept},
+        "frame_device_ms": ms_per_frame,
+        "e2e": {"value": U_mean / (e2e_ms_per_frame * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_per_frame,
+                "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": 19 * 27 * 8,
+                "api": "kf::kinectfusion::pipeline(depth_mm) via libkfusion_b200.so, pinned host frames"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "integrate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "kernel_ms": k_ms_mean, "algorithmic_bytes": 8.0 * U_mean,
+                     "dense_model_gbs": 8.0 * swept / (k_ms_mean * 1e-3) / 1e9},
+        "clocks": clocks,
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dims", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

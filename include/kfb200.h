@@ -90,8 +90,9 @@ int kfb_reset_volume(kfb_ctx *ctx);                                     /* devic
 int kfb_reset_frames(kfb_ctx *ctx);                                     /* Frame::reset, types.hpp:53-62 */
 
 /* ---- frame ingest + front end ---------------------------------------------- */
-/* GpuMat::upload of the f32 millimetre depth, kinectfusion.cpp:50.  `host` may be pageable
- * or pinned; the copy is asynchronous on the context stream when pinned. */
+/* GpuMat::upload of the f32 millimetre depth, kinectfusion.cpp:50.  `host` may be pageable or
+ * pinned host memory (asynchronous on the context stream when pinned) or a device pointer
+ * (frame already resident in HBM: device-to-device copy). */
 int kfb_upload_depth_mm(kfb_ctx *ctx, const float *host, int width, int height);
 /* cv::cuda::pyrDown x(L-1), cv::cuda::bilateralFilter xL, device::depthTruncation xL,
  * device::getVertexmap xL, device::getNormalmap xL -- kinectfusion.cpp:54-75,
@@ -148,6 +149,9 @@ void kfb_level_intrinsics(const kfb_intrinsics *in, int level, kfb_intrinsics *o
 /* cudaEvent pool on the context stream: record slot i now; elapsed ms between slots. */
 int kfb_event_record(kfb_ctx *ctx, int slot);
 int kfb_event_elapsed_ms(kfb_ctx *ctx, int slot_a, int slot_b, float *ms);
+/* opt-in stage profiling: when on, launchers bracket their main kernel with events in reserved
+ * slots (integrate: 60/61, raycast: 58/59) so a caller can read that kernel's own duration. */
+int kfb_set_profiling(kfb_ctx *ctx, int on);
 /* number of kernels this library has launched on this context since creation */
 uint64_t kfb_launch_count(const kfb_ctx *ctx);
 /* raw device pointers for zero-copy interop (NCCL / torch views); which: 0 volume,

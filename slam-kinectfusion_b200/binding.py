@@ -99,6 +99,7 @@ def load_library():
         "kfb_level_intrinsics": (None, [IP, C.c_int, IP]),
         "kfb_event_record": (C.c_int, [_vp, C.c_int]),
         "kfb_event_elapsed_ms": (C.c_int, [_vp, C.c_int, C.c_int, _fp]),
+        "kfb_set_profiling": (C.c_int, [_vp, C.c_int]),
         "kfb_launch_count": (C.c_uint64, [_vp]),
         "kfb_device_ptr": (_vp, [_vp, C.c_int]),
         "kfb_stream": (_vp, [_vp]),
@@ -273,6 +274,9 @@ class Context:
         ms = C.c_float(0)
         self._ck(self.lib.kfb_event_elapsed_ms(self.h, a, b, C.byref(ms)))
         return ms.value
+
+    def set_profiling(self, on):
+        self._ck(self.lib.kfb_set_profiling(self.h, int(bool(on))))
 
     def launch_count(self):
         return self.lib.kfb_launch_count(self.h)

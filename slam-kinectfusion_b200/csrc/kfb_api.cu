@@ -71,6 +71,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->levels = p->pyramid_height;
     ctx->cur = 0; ctx->prev = 1;
     ctx->launches = 0;
+    ctx->profiling = 0;
     ctx->icp_seq = 0;
     ctx->vol = nullptr; ctx->cloud = nullptr; ctx->cloud_cap = 0;
     memset(ctx->L, 0, sizeof(ctx->L));
@@ -197,18 +198,20 @@ int kfb_upload_depth_mm(kfb_ctx *ctx, const float *host, int width, int height)
 {
     if (!host || width != ctx->intr.width || height != ctx->intr.height) { ctx->err = "depth size mismatch"; return KFB_ERR_INVALID; }
     const size_t bytes = (size_t)width * height * sizeof(float);
-    // pinned host memory goes straight over; pageable memory is staged through the context's pinned buffer
+    // pinned host memory goes straight over; device memory is copied D2D (frames already resident in
+    // HBM); pageable memory is staged through the context's pinned buffer
     cudaPointerAttributes at;
-    bool pinned = false;
-    if (cudaPointerGetAttributes(&at, host) == cudaSuccess) pinned = (at.type == cudaMemoryTypeHost);
+    bool direct = false;
+    if (cudaPointerGetAttributes(&at, host) == cudaSuccess)
+        direct = (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
     else cudaGetLastError();
-    if (!pinned)
+    if (!direct)
     {
         KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // staging buffer may still be in flight
         memcpy(ctx->pinned_depth, host, bytes);
         host = ctx->pinned_depth;
     }
-    KFB_CUDA(ctx, cudaMemcpyAsync(ctx->L[0].raw, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    KFB_CUDA(ctx, cudaMemcpyAsync(ctx->L[0].raw, host, bytes, cudaMemcpyDefault, ctx->stream));
     return KFB_OK;
 }
 
@@ -359,6 +362,7 @@ int kfb_event_elapsed_ms(kfb_ctx *ctx, int a, int b, float *ms)
     KFB_CUDA(ctx, cudaEventElapsedTime(ms, ctx->events[a], ctx->events[b]));
     return KFB_OK;
 }
+int kfb_set_profiling(kfb_ctx *ctx, int on) { ctx->profiling = on; return KFB_OK; }
 uint64_t kfb_launch_count(const kfb_ctx *ctx) { return ctx->launches; }
 void *kfb_device_ptr(kfb_ctx *ctx, int which)
 {

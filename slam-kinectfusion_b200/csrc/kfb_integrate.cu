@@ -274,8 +274,10 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
     }
     else
     {
+        if (ctx->profiling) cudaEventRecord(ctx->events[60], ctx->stream);
         integrate_kernel<2, false><<<grid, block, 0, ctx->stream>>>(a);
         KFB_LAUNCH_CHECK(ctx);
+        if (ctx->profiling) cudaEventRecord(ctx->events[61], ctx->stream);
     }
     return KFB_OK;
 }

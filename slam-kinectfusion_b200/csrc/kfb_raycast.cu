@@ -190,8 +190,10 @@ int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9]
     a.hit_t = ctx->hit_t;
     a.ts_sign_compat = ctx->p.compat_raycast_ts_sign;
     dim3 block(8, 16), grid((a.k.w + 7) / 8, (a.k.h + 15) / 16);
+    if (ctx->profiling) cudaEventRecord(ctx->events[58], ctx->stream);
     raycast_kernel<<<grid, block, 0, ctx->stream>>>(a);
     KFB_LAUNCH_CHECK(ctx);
+    if (ctx->profiling) cudaEventRecord(ctx->events[59], ctx->stream);
     return KFB_OK;
 }
 

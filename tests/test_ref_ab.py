@@ -82,7 +82,7 @@ def test_raycast_bit_exact(kfo, kfb, kref):
         rv_v, rv_n, _ = rv.raycast(c2v, rinv, Ko)
         ctx.raycast(c2v, rinv)
         gv, gn = ctx.download_maps(1, 0)
-        assert (rv_v[..., 2] != 0).mean() > 0.9
+        assert (rv_v[..., 2] != 0).mean() > 0.8
         assert np.array_equal(gv, rv_v) and np.array_equal(gn, rv_n)
         # model pyramid
         ctx.model_pyramid()
