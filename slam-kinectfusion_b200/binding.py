@@ -82,6 +82,9 @@ def load_library():
         "kfb_frontend": (C.c_int, [_vp]),
         "kfb_swap_frames": (C.c_int, [_vp]),
         "kfb_icp_accumulate": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+        "kfb_icp_begin": (C.c_int, [_vp, _vp]),
+        "kfb_icp_step": (C.c_int, [_vp, _vp, _vp]),
+        "kfb_icp_end": (C.c_int, [_vp]),
         "kfb_integrate": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint64)]),
         "kfb_raycast": (C.c_int, [_vp, _vp, _vp]),
         "kfb_model_pyramid": (C.c_int, [_vp]),
@@ -103,6 +106,7 @@ def load_library():
         "kfb_launch_count": (C.c_uint64, [_vp]),
         "kfb_device_ptr": (_vp, [_vp, C.c_int]),
         "kfb_stream": (_vp, [_vp]),
+        "kfb_debug_icp_stamps": (None, [_vp, _vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -182,6 +186,19 @@ class Context:
         out = np.empty(27, np.float64)
         self._ck(self.lib.kfb_icp_accumulate(self.h, int(level), _ptr(p), _ptr(out)))
         return out
+
+    def icp_begin(self, iters_per_level):
+        it = (C.c_int * KFB_MAX_LEVELS)(*list(iters_per_level) + [0] * (KFB_MAX_LEVELS - len(iters_per_level)))
+        self._ck(self.lib.kfb_icp_begin(self.h, it))
+
+    def icp_step(self, pose12):
+        p = _f32(pose12)
+        out = np.empty(27, np.float64)
+        self._ck(self.lib.kfb_icp_step(self.h, _ptr(p), _ptr(out)))
+        return out
+
+    def icp_end(self):
+        self._ck(self.lib.kfb_icp_end(self.h))
 
     def integrate(self, vol2cam12, count=False):
         p = _f32(vol2cam12)
@@ -283,6 +300,11 @@ class Context:
 
     def device_ptr(self, which):
         return self.lib.kfb_device_ptr(self.h, which)
+
+    def debug_icp_stamps(self):
+        out = np.zeros((32, 8), np.uint64)
+        self.lib.kfb_debug_icp_stamps(self.h, _ptr(out))
+        return out
 
     def stream(self):
         return self.lib.kfb_stream(self.h)

@@ -74,6 +74,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->profiling = 0;
     ctx->icp_seq = 0;
     ctx->vol = nullptr; ctx->cloud = nullptr; ctx->cloud_cap = 0;
+    ctx->icp_host = nullptr; ctx->icp_gate_host = nullptr; ctx->icp_devgate = nullptr;
     memset(ctx->L, 0, sizeof(ctx->L));
     memset(ctx->events, 0, sizeof(ctx->events));
     *out = ctx; // returned even on failure so the caller can read the error string, then destroy
@@ -121,6 +122,12 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->icp_host, sizeof(IcpHostResult), cudaHostAllocMapped));
     memset((void *)ctx->icp_host, 0, sizeof(IcpHostResult));
     KFB_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->icp_dev, (void *)ctx->icp_host, 0));
+    KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->icp_gate_host, sizeof(IcpHostGate), cudaHostAllocMapped));
+    memset((void *)ctx->icp_gate_host, 0, sizeof(IcpHostGate));
+    KFB_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->icp_gate_dev, (void *)ctx->icp_gate_host, 0));
+    memset(&ctx->icp_sched, 0, sizeof(ctx->icp_sched));
+    KFB_CUDA(ctx, cudaMalloc(&ctx->icp_devgate, sizeof(IcpDevGate)));
+    KFB_CUDA(ctx, cudaMemset(ctx->icp_devgate, 0, sizeof(IcpDevGate)));
     KFB_CUDA(ctx, cudaMalloc(&ctx->counters, 8 * sizeof(unsigned long long)));
     KFB_CUDA(ctx, cudaMemset(ctx->counters, 0, 8 * sizeof(unsigned long long)));
     KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->counters_host, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
@@ -155,6 +162,8 @@ void kfb_destroy(kfb_ctx *ctx)
     if (ctx->icp_partials) cudaFree(ctx->icp_partials);
     if (ctx->icp_ticket) cudaFree(ctx->icp_ticket);
     if (ctx->icp_host) cudaFreeHost((void *)ctx->icp_host);
+    if (ctx->icp_gate_host) cudaFreeHost((void *)ctx->icp_gate_host);
+    if (ctx->icp_devgate) cudaFree(ctx->icp_devgate);
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->counters_host) cudaFreeHost(ctx->counters_host);
     if (ctx->pinned_depth) cudaFreeHost(ctx->pinned_depth);
@@ -228,6 +237,18 @@ int kfb_icp_accumulate(kfb_ctx *ctx, int level, const float pose12[12], double o
     if (!pose12 || !out27) return KFB_ERR_INVALID;
     return launch_icp(ctx, level, pose12, out27);
 }
+
+int kfb_icp_begin(kfb_ctx *ctx, const int iters_per_level[KFB_MAX_LEVELS])
+{
+    if (!iters_per_level) return KFB_ERR_INVALID;
+    return icp_begin(ctx, iters_per_level);
+}
+int kfb_icp_step(kfb_ctx *ctx, const float pose12[12], double out27[27])
+{
+    if (!pose12 || !out27) return KFB_ERR_INVALID;
+    return icp_step(ctx, pose12, out27);
+}
+int kfb_icp_end(kfb_ctx *ctx) { return icp_end(ctx); }
 
 int kfb_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_updated)
 {
@@ -377,5 +398,9 @@ void *kfb_device_ptr(kfb_ctx *ctx, int which)
     }
 }
 void *kfb_stream(kfb_ctx *ctx) { return (void *)ctx->stream; }
+void kfb_debug_icp_stamps(kfb_ctx *ctx, uint64_t out256[256])
+{
+    for (int i = 0; i < 256; ++i) out256[i] = ctx->icp_host->stamps[i / 8][i % 8];
+}
 
 } // extern "C"

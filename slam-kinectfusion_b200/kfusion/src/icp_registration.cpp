@@ -74,19 +74,28 @@ bool kf::ICPRegistration::rigidTransform(cv::Affine3f &camera_pose, const cv::Af
     // The reference's `camera_pose.Identity()` (:18) is a no-op on a default-constructed pose; same start here.
     camera_pose = cv::Affine3f::Identity();
     kfb_ctx *ctx = cframe->dev->ctx;
-    for (int level = (int)iters.size() - 1; level >= 0; level--)
+    // The loop below is the reference's (:21-43); the device side of every iteration was enqueued ahead
+    // of time by kfb_icp_begin and is released by kfb_icp_step, so no launch latency sits between the
+    // host solve and the next accumulation.
+    int sched[KFB_MAX_LEVELS] = {0};
+    for (size_t l = 0; l < iters.size() && l < KFB_MAX_LEVELS; ++l) sched[l] = iters[l];
+    if (kfbSafeCall(ctx, kfb_icp_begin(ctx, sched)) != KFB_OK) return false;
+    bool ok = true;
+    for (int level = (int)iters.size() - 1; level >= 0 && ok; level--)
     {
-        for (int i = 0; i < iters[level]; i++)
+        for (int i = 0; i < iters[level] && ok; i++)
         {
             float pose12[12];
             double sums[27], x[6];
             camera_pose.to12(pose12);
-            if (kfbSafeCall(ctx, kfb_icp_accumulate(ctx, level, pose12, sums)) != KFB_OK) return false;
-            if (!solve(sums, x)) return false;
+            if (kfbSafeCall(ctx, kfb_icp_step(ctx, pose12, sums)) != KFB_OK) { ok = false; break; }
+            if (!solve(sums, x)) { ok = false; break; }
             // Tinc = Affine3f(rvec = x[0..2] (float), t = x[3..5]); pose = pose * Tinc (right-multiply, :41-42)
             cv::Affine3f Tinc(cv::Vec3f((float)x[0], (float)x[1], (float)x[2]), cv::Vec3f((float)x[3], (float)x[4], (float)x[5]));
             camera_pose = camera_pose * Tinc;
         }
     }
+    kfbSafeCall(ctx, kfb_icp_end(ctx));
+    if (!ok) return false;
     return true;
 }

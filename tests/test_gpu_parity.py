@@ -285,6 +285,45 @@ def test_icp_sums_vs_oracle(kfo, kfb, compat_rows):
     assert np.array_equal(a, b)
 
 
+def test_icp_gated_schedule_equals_direct(kfo, kfb):
+    """The pre-enqueued, host-gated schedule (kfb_icp_begin/step/end) returns bit-identical sums to the
+    direct call, survives early termination (tracking failure) and leaves the context reusable."""
+    Ko, Kb, Po, Pb = make_pair(kfo, kfb, 64, 640, 480)
+    cur = kfo.frontend(kfo.render_depth_mm(kfo.trajectory_pose(7), Ko), Ko)
+    pre = kfo.frontend(kfo.render_depth_mm(kfo.trajectory_pose(6), Ko), Ko)
+    ctx = _ctx(kfb, Kb, Pb)
+    for l in range(3):
+        ctx.upload_maps(0, l, cur[l][1], cur[l][2])
+        ctx.upload_maps(1, l, pre[l][1], pre[l][2])
+    iters = [4, 5, 10]
+    for trial in range(3):
+        pose = kfo.identity()
+        ctx.icp_begin(iters)
+        direct = []
+        for level in (2, 1, 0):
+            for i in range(iters[level]):
+                got = ctx.icp_step(pose)
+                direct.append((level, pose.copy(), got))
+                rc, x = kfo.icp_solve(got)
+                assert rc == 0
+                pose = kfo.pose_apply_increment(pose, x)
+        ctx.icp_end()
+        for level, p, got in direct[::4]:
+            assert np.array_equal(ctx.icp_accumulate(level, p), got)
+    # early exit after 3 of 19 iterations: the remaining gated kernels must retire through the abort gate
+    ctx.icp_begin(iters)
+    for i in range(3):
+        ctx.icp_step(kfo.identity())
+    ctx.icp_end()
+    ctx.synchronize()
+    a = ctx.icp_accumulate(2, kfo.identity())
+    ctx.icp_begin(iters)
+    b = ctx.icp_step(kfo.identity())
+    ctx.icp_end()
+    ctx.synchronize()
+    assert np.array_equal(a, b)
+
+
 def test_icp_degenerate_inputs(kfo, kfb):
     Ko, Kb, Po, Pb = make_pair(kfo, kfb, 64, 320, 240)
     ctx = _ctx(kfb, Kb, Pb)

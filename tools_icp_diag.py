@@ -1,0 +1,41 @@
+import sys, time
+import numpy as np
+sys.path.insert(0, '.')
+import slam_kinectfusion_b200 as kfb
+from slam_kinectfusion_b200 import synth
+K = kfb.Intrinsics(**kfb.SENSORS["kinect1"])
+ctx = kfb.Context(K, kfb.default_params(128))
+f0 = synth.render_depth_mm(synth.trajectory_pose(0)); f1 = synth.render_depth_mm(synth.trajectory_pose(1))
+ctx.upload_depth_mm(f0); ctx.frontend(); ctx.swap_frames(); ctx.upload_depth_mm(f1); ctx.frontend(); ctx.synchronize()
+I = np.zeros(12, np.float32); I[0] = I[5] = I[10] = 1
+iters = [4, 5, 10]
+for trial in range(4):
+    ts = []
+    t0 = time.perf_counter(); ctx.icp_begin(iters); tb = time.perf_counter() - t0
+    for k in range(19):
+        t1 = time.perf_counter(); ctx.icp_step(I); ts.append((time.perf_counter() - t1) * 1e6)
+    t2 = time.perf_counter(); ctx.icp_end(); te = time.perf_counter() - t2
+    print("begin us", round(tb * 1e6, 1), "end us", round(te * 1e6, 1), "steps us", [round(t, 1) for t in ts], "total ms", round((time.perf_counter() - t0) * 1e3, 3))
+for l in (2, 1, 0):
+    t0 = time.perf_counter()
+    for _ in range(50): ctx.icp_accumulate(l, I)
+    print("direct level", l, (time.perf_counter() - t0) / 50 * 1e6, "us")
+
+import time
+# gated chain through the C++ facade-equivalent loop: phases per iteration
+from slam_kinectfusion_b200 import host as H
+for trial in range(2):
+    pose = I.copy()
+    ctx.icp_begin(iters)
+    for k in range(19):
+        s27 = ctx.icp_step(pose)
+    ctx.icp_end(); ctx.synchronize(); time.sleep(0.01)
+st = ctx.debug_icp_stamps().astype(np.int64)
+order = np.argsort(st[:, 7])[-19:]
+S = st[order]
+print("seq", S[:, 7] - S[0, 7])
+print("kernel phases ns (acc, red+ticket, final, post, fence+flag):")
+print(np.median(S[:, 1:6] - S[:, 0:5], axis=0))
+print("flag posted -> next pose fetched (host turnaround seen by GPU) ns:", (S[:-1, 6] - S[:-1, 5]))
+print("pose fetched -> next kernel's reducing block entry ns:", (S[1:, 0] - S[:-1, 6]))
+print("iteration period ns:", np.diff(S[:, 5]))
