@@ -84,6 +84,10 @@ void kfb_destroy(kfb_ctx *ctx);                                         /* kinec
 const char *kfb_last_error_string(const kfb_ctx *ctx);                  /* safe_call.hpp:8-14 (returned, not printed) */
 int kfb_synchronize(kfb_ctx *ctx);                                      /* cudaDeviceSynchronize, tsdf_volume.cu:110 */
 int kfb_device_count(void);
+/* Run all further work of this context on a caller-owned CUDA stream (cudaStream_t), e.g. the stream a
+ * torch.distributed / NCCL communicator orders its collectives against.  The reference runs everything
+ * on the legacy default stream (all `<<<grid, block>>>` launches); this is the explicit equivalent. */
+int kfb_set_stream(kfb_ctx *ctx, void *cuda_stream);
 
 /* ---- volume ------------------------------------------------------------- */
 int kfb_reset_volume(kfb_ctx *ctx);                                     /* device::resetVolume, device_types.hpp:116 */
@@ -130,6 +134,14 @@ int kfb_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_updated);
 int kfb_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9]);
 /* device::resizePointsNormals x(L-1) on the model maps, kinectfusion.cpp:114-120. */
 int kfb_model_pyramid(kfb_ctx *ctx);
+/* z-slab sharded volumes (no reference counterpart, the reference is single-GPU): a slab
+ * context's kfb_raycast marches only the ray samples whose voxel lies in its slab and records, per pixel,
+ * the ray length of its first terminal event (hit or back-face stop; +inf if none) in the key buffer
+ * kfb_device_ptr(ctx, 4).  After the per-pixel minimum of the keys over all slabs has been formed
+ * (all-reduce MIN), kfb_composite_mask zeroes this context's model vertex/normal maps wherever it does not
+ * hold the winning key, so that an integer SUM reduction of the maps over the slabs yields exactly the
+ * single-GPU raycast. */
+int kfb_composite_mask(kfb_ctx *ctx, const float *min_key_dev);
 
 /* ---- export ("next" rows) ------------------------------------------ */
 /* device::extract_points (device_types.hpp:128, tsdf_volume.cu:483-499) + the D2H of
@@ -164,7 +176,7 @@ int kfb_set_profiling(kfb_ctx *ctx, int on);
 /* number of kernels this library has launched on this context since creation */
 uint64_t kfb_launch_count(const kfb_ctx *ctx);
 /* raw device pointers for zero-copy interop (NCCL / torch views); which: 0 volume,
- * 1 prev vmap L0 (float4), 2 prev nmap L0 (float4), 3 cur depth L0 (float), 4 raycast hit-t (float) */
+ * 1 prev vmap L0 (float4), 2 prev nmap L0 (float4), 3 cur depth L0 (float), 4 raycast event keys (float) */
 void *kfb_device_ptr(kfb_ctx *ctx, int which);
 void *kfb_stream(kfb_ctx *ctx);
 /* debug: ring of the last 32 ICP launches (row = sequence number % 32), %globaltimer (ns) at the phase

@@ -76,6 +76,8 @@ def load_library():
         "kfb_last_error_string": (C.c_char_p, [_vp]),
         "kfb_synchronize": (C.c_int, [_vp]),
         "kfb_device_count": (C.c_int, []),
+        "kfb_set_stream": (C.c_int, [_vp, _vp]),
+        "kfb_composite_mask": (C.c_int, [_vp, _vp]),
         "kfb_reset_volume": (C.c_int, [_vp]),
         "kfb_reset_frames": (C.c_int, [_vp]),
         "kfb_upload_depth_mm": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
@@ -212,6 +214,12 @@ class Context:
     def raycast(self, cam2vol12, rinv9):
         p, r = _f32(cam2vol12), _f32(rinv9)
         self._ck(self.lib.kfb_raycast(self.h, _ptr(p), _ptr(r)))
+
+    def set_stream(self, cuda_stream):
+        self._ck(self.lib.kfb_set_stream(self.h, _vp(int(cuda_stream))))
+
+    def composite_mask(self, min_key_ptr):
+        self._ck(self.lib.kfb_composite_mask(self.h, _vp(int(min_key_ptr))))
 
     def model_pyramid(self):
         self._ck(self.lib.kfb_model_pyramid(self.h))

@@ -74,6 +74,11 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->profiling = 0;
     ctx->icp_seq = 0;
     ctx->vol = nullptr; ctx->cloud = nullptr; ctx->cloud_cap = 0;
+    ctx->tab_thrz = nullptr; ctx->tab_exact = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->bricks = nullptr;
+    ctx->bdist = ctx->bdist_tmp = ctx->bdist_tmp2 = nullptr; ctx->bdirty = nullptr;
+    ctx->hit_t = nullptr; ctx->icp_partials = nullptr; ctx->icp_ticket = nullptr; ctx->counters = nullptr;
+    ctx->counters_host = nullptr; ctx->pinned_depth = nullptr; ctx->render_dev = nullptr; ctx->render_host = nullptr;
+    ctx->stream = nullptr; ctx->own_stream = 1;
     ctx->icp_host = nullptr; ctx->icp_gate_host = nullptr; ctx->icp_devgate = nullptr;
     memset(ctx->L, 0, sizeof(ctx->L));
     memset(ctx->events, 0, sizeof(ctx->events));
@@ -113,7 +118,22 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     for (int i = 0; i < 3; ++i) ctx->voxel_size[i] = p->volu_range[i] / (float)p->volu_dims[i]; // tsdf_volume.cpp:16
     KFB_CUDA(ctx, cudaMalloc(&ctx->vol, ctx->vol_voxels * sizeof(uint32_t)));
     const size_t n0 = (size_t)intr->width * intr->height;
-    KFB_CUDA(ctx, cudaMalloc(&ctx->tab_thr, n0 * sizeof(__half2)));
+    KFB_CUDA(ctx, cudaMalloc(&ctx->tab_thrz, n0 * sizeof(float2)));
+    if (p->tsdf_max_weight < 1 || p->tsdf_max_weight > 32767) { ctx->err = "tsdf_max_weight must be in [1, 32767]"; return KFB_ERR_INVALID; }
+    KFB_CUDA(ctx, cudaMalloc(&ctx->wtab, (size_t)(p->tsdf_max_weight + 1) * sizeof(float4)));
+    KFB_CUDA(ctx, cudaMalloc(&ctx->zexit, sizeof(float)));
+    ctx->bdim[0] = (p->volu_dims[0] + 7) >> 3;
+    ctx->bdim[1] = (p->volu_dims[1] + 7) >> 3;
+    ctx->bz0 = ctx->z0 >> 3;
+    ctx->bdim[2] = ((ctx->z1 - 1) >> 3) - ctx->bz0 + 1;
+    {
+        const size_t nb = (size_t)ctx->bdim[0] * ctx->bdim[1] * ctx->bdim[2];
+        KFB_CUDA(ctx, cudaMalloc(&ctx->bricks, nb));
+        KFB_CUDA(ctx, cudaMalloc(&ctx->bdist, nb));
+        KFB_CUDA(ctx, cudaMalloc(&ctx->bdist_tmp, nb));
+        KFB_CUDA(ctx, cudaMalloc(&ctx->bdist_tmp2, nb));
+        KFB_CUDA(ctx, cudaMalloc(&ctx->bdirty, sizeof(int)));
+    }
     KFB_CUDA(ctx, cudaMalloc(&ctx->tab_exact, n0 * sizeof(float2)));
     KFB_CUDA(ctx, cudaMalloc(&ctx->hit_t, n0 * sizeof(float)));
     KFB_CUDA(ctx, cudaMalloc(&ctx->icp_partials, 1024 * 27 * sizeof(double)));
@@ -137,6 +157,8 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     for (int i = 0; i < 64; ++i) KFB_CUDA(ctx, cudaEventCreate(&ctx->events[i]));
     int rc = kfb_reset_frames(ctx);
     if (rc) return rc;
+    rc = launch_build_wtab(ctx);
+    if (rc) return rc;
     rc = kfb_reset_volume(ctx);
     if (rc) return rc;
     KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -156,7 +178,14 @@ void kfb_destroy(kfb_ctx *ctx)
         for (int f = 0; f < 2; ++f) { if (L.v[f]) cudaFree(L.v[f]); if (L.n[f]) cudaFree(L.n[f]); }
     }
     if (ctx->vol) cudaFree(ctx->vol);
-    if (ctx->tab_thr) cudaFree(ctx->tab_thr);
+    if (ctx->tab_thrz) cudaFree(ctx->tab_thrz);
+    if (ctx->wtab) cudaFree(ctx->wtab);
+    if (ctx->zexit) cudaFree(ctx->zexit);
+    if (ctx->bricks) cudaFree(ctx->bricks);
+    if (ctx->bdist) cudaFree(ctx->bdist);
+    if (ctx->bdist_tmp) cudaFree(ctx->bdist_tmp);
+    if (ctx->bdist_tmp2) cudaFree(ctx->bdist_tmp2);
+    if (ctx->bdirty) cudaFree(ctx->bdirty);
     if (ctx->tab_exact) cudaFree(ctx->tab_exact);
     if (ctx->hit_t) cudaFree(ctx->hit_t);
     if (ctx->icp_partials) cudaFree(ctx->icp_partials);
@@ -171,7 +200,7 @@ void kfb_destroy(kfb_ctx *ctx)
     if (ctx->render_host) cudaFreeHost(ctx->render_host);
     if (ctx->cloud) cudaFree(ctx->cloud);
     for (int i = 0; i < 64; ++i) if (ctx->events[i]) cudaEventDestroy(ctx->events[i]);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
     cudaGetLastError();
     delete ctx;
 }
@@ -181,6 +210,16 @@ const char *kfb_last_error_string(const kfb_ctx *ctx) { return ctx ? ctx->err.c_
 int kfb_synchronize(kfb_ctx *ctx)
 {
     KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return KFB_OK;
+}
+
+int kfb_set_stream(kfb_ctx *ctx, void *stream)
+{
+    if (ctx->icp_sched.active) { ctx->err = "kfb_set_stream inside an ICP schedule"; return KFB_ERR_INVALID; }
+    KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)stream;
+    ctx->own_stream = 0;
     return KFB_OK;
 }
 
@@ -263,6 +302,12 @@ int kfb_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9])
 }
 
 int kfb_model_pyramid(kfb_ctx *ctx) { return launch_model_pyramid(ctx); }
+
+int kfb_composite_mask(kfb_ctx *ctx, const float *min_key_dev)
+{
+    if (!min_key_dev) return KFB_ERR_INVALID;
+    return launch_composite_mask(ctx, min_key_dev);
+}
 
 int kfb_extract_points(kfb_ctx *ctx, const float volpose12[12], float *host_points3, size_t cap, size_t *n_points)
 {
@@ -364,6 +409,8 @@ int kfb_download_volume(kfb_ctx *ctx, int16_t *host)
 int kfb_upload_volume(kfb_ctx *ctx, const int16_t *host)
 {
     KFB_CUDA(ctx, cudaMemcpyAsync(ctx->vol, host, ctx->vol_voxels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = launch_rebuild_bricks(ctx);
+    if (rc) return rc;
     KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KFB_OK;
 }

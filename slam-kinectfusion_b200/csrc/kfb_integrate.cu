@@ -8,18 +8,42 @@
 // update arithmetic are the reference's, rounding for rounding:
 //   * vc(z) is the reference's running sum, vc = fma(voxel_size.x, R[:,2], vc), replayed
 //     from z = 1 (also across z-chunks / z-slabs) so every plane sees identical bits;
+//     it is carried as packed f32x2 pairs and advanced with FFMA2 (two IEEE fmas per issue);
 //   * pixel = round-half-even(fma(vc.x * MUFU.RCP(vc.z), fx, cx)), done with the 2^23
 //     magic-number add so it stays off the conversion pipe;
 //   * sdf = depth - |vc| / lambda is only evaluated exactly inside a narrow band around
-//     the surface: a per-pixel table of conservative |vc|^2 thresholds (fp16, rounded
-//     outward) classifies "certainly free space => tsdf == 1.0f exactly" and "certainly
-//     behind the surface => rejected" without the two sqrt/rcp chains.  The thresholds
-//     are proved conservative in build_tables_kernel, so classification never changes a
-//     result, only skips work.
+//     the surface: a per-pixel table of conservative vc.z thresholds classifies
+//     "certainly free space => tsdf == 1.0f exactly" and "certainly behind the surface =>
+//     rejected" with two compares.  The thresholds are proved conservative in
+//     build_tables_kernel, so classification never changes a result, only skips work.
+// The kernel was instruction-issue bound (profiles/r01_v1_*), so everything that is not the
+// reference's arithmetic was removed from the per-voxel path:
+//   * a per-thread conservative frustum interval [za, zb] in z (vc(z) is affine in z, so the four
+//     image-border inequalities, vc.z > 0 and vc.z <= max accepted depth are half-lines in z):
+//     planes before za only replay the running sum, planes after zb are not visited at all, and
+//     inside the interval the exact per-voxel predicate still decides;
+//   * the update runs without the quarter-rate XU pipe: int->float by magic-number add, the
+//     reciprocal of weight+1 from a device-built table of MUFU.RCP results, float->int
+//     truncation by an RZ add of 2^23;
+//   * when a thread's four voxels hold the same word and receive the same tsdf (free space),
+//     the update is computed once; stores whose value equals the loaded one are dropped.
+// Side product for the raycaster: every write of a negative tsdf marks the 8^3 bricks within two
+// voxels of it in a byte map (kfb_raycast.cu skips bricks that cannot contain a sign change).
 #include "kfb_common.cuh"
+#include <cmath>
+#include <cstdlib>
 
 namespace kfb
 {
+
+struct CullPlane // conservative half-line in z: g0(x, y) + z * g1 >= 0
+{
+    float a, b, g;  // g0 = a*vc.x + b*vc.y + g*vc.z at z = 0
+    float slack;    // added to g0 (float-evaluation and running-sum error bounds)
+    float ninv;     // -1 / g1
+    int kind;       // 0: z >= g0*ninv, 1: z <= g0*ninv, 2: constant (g0 < 0 => empty), 3: ignore
+};
+#define KFB_NCULL 6
 
 struct IntegrateArgs
 {
@@ -33,9 +57,15 @@ struct IntegrateArgs
     float trunc;
     float fx, fy, cx, cy;
     int w, h;
-    const __half2 *thr;
+    const float2 *thrz;
     const float2 *exact;
+    const float4 *wtab;
+    const float *zexit;
     int max_weight;
+    uint8_t *bricks;
+    int *bdirty;         // set when a brick flag flips 0 -> 1 (the distance map must be rebuilt)
+    int bx, by, bz, bz0; // brick grid dims (x, y, stored z bricks) and first stored z brick
+    CullPlane cull[KFB_NCULL];
     unsigned long long *counter;
 };
 
@@ -43,50 +73,238 @@ struct IntegrateArgs
 #define KFB_MAGIC_I 0x4B400000
 #define KFB_SKIP (-4.0f)
 
+// ---- packed f32x2 helpers (sm_100a FFMA2 / FMUL2 / FADD2: two IEEE-rounded ops per issue) ------------
+// NOTE: ptxas contracts mul.rn.f32x2 followed by add.rn.f32x2 into one FFMA2 (checked in SASS); this file
+// never feeds a packed mul into a packed add, only mul -> fma and fma -> add, which cannot be contracted.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // ---- per-pixel tables ---------------------------------------------------------------
 // exact[p] = {depth, MUFU.RCP(lambda)} with lambda = sqrt(((u-cx)/fx)^2 + ((v-cy)/fy)^2 + 1)
 // computed with the reference's operations (tsdf_volume.cu:65-68, device_utils.cuh:22-27).
-// thr[p]   = {hi2, lo2}:  |vc|^2 <= hi2  ==> the reference's tsdf is exactly 1.0f
-//                         |vc|^2 >  lo2  ==> the reference rejects the voxel (sdf < -trunc)
-// Proof sketch (all quantities positive, eps = 2^-24):
+// thrz[p]  = {hi_z, lo_z}:  vc.z <= hi_z  ==> the reference's tsdf is exactly 1.0f
+//                           vc.z >  lo_z  ==> the reference rejects the voxel (sdf < -trunc)
+// Proof sketch (all quantities positive, eps = 2^-24).  Step 1, in terms of d2 = |vc|^2 as the kernel
+// computes it:
 //   nrm = sqrt_rn(d2) in sqrt(d2)(1 +- eps); il = MUFU.RCP(lambda) in (1/lambda)(1 +- 2^-22);
 //   nsdf = RN(il*nrm - depth).  With T = trunc(1+1e-5):
-//   d2 <= ((depth - T - 1e-6) lambda)^2 (1-8e-6) => il*nrm <= depth - T (reals) => -nsdf >= T
+//   d2 <= hi2 := ((depth - T - 1e-6) lambda)^2 (1-8e-6) => il*nrm <= depth - T (reals) => -nsdf >= T
 //        => MUFU.RCP(trunc) * (-nsdf) >= (1+1e-5)(1-2^-22)(1-eps) > 1 => fmin(1, .) == 1.
-//   d2 >  ((depth + T + 1e-6) lambda)^2 (1+8e-6) => il*nrm - depth > T > trunc => nsdf > trunc.
-//   The 1e-6 absorbs the float rounding of depth -+ T (depth < 8 m); fp16 conversion rounds
-//   hi2 down and lo2 up.  Invalid depth (<= 0 or NaN) => {-1, -1}: everything rejected, as the
-//   reference does (`depth <= 0` skip; NaN depth makes sdf NaN, which fails `sdf >= -trunc`).
+//   d2 >  lo2 := ((depth + T + 1e-6) lambda)^2 (1+8e-6) => il*nrm - depth > T > trunc => nsdf > trunc.
+//   The 1e-6 absorbs the float rounding of depth -+ T (depth < 8 m).
+// Step 2, from d2 to vc.z.  A voxel that lands on pixel (u, v) has round(fma(qx, fx, cx)) == u with
+// qx = RN(MUFU.RCP(vc.z) * vc.x), so |vc.x / vc.z - (u-cx)/fx| <= hx := 0.501/fx (0.5 px of rounding
+// plus < 0.001 px for the fma rounding and the 2^-21 relative error of rcp*mul), likewise hy.  Hence
+//   vc.z^2 Lmin^2 <= d2_real <= vc.z^2 Lmax^2,  Lmax^2 = 1 + (|lx|+hx)^2 + (|ly|+hy)^2,
+//                                              Lmin^2 = 1 + max(|lx|-hx,0)^2 + max(|ly|-hy,0)^2,
+// and d2 (three float ops) is within (1 +- 4 eps) of d2_real.  So
+//   vc.z <= hi_z := sqrt(hi2)/Lmax (1-1e-6) => d2 <= hi2,     vc.z > lo_z := sqrt(lo2)/Lmin (1+1e-6) => d2 > lo2.
+// Invalid depth (<= 0 or NaN) => {-1, -1}: everything rejected, as the reference does (`depth <= 0`
+// skip; NaN depth makes sdf NaN, which fails `sdf >= -trunc`).
+// *zexit = max lo_z over the image: a voxel with vc.z above it is rejected whatever pixel it lands on.
 __global__ void build_tables_kernel(const float *__restrict__ depth, int w, int h, float fx, float fy, float cx,
-                                    float cy, float trunc, __half2 *__restrict__ thr, float2 *__restrict__ exact)
+                                    float cy, float trunc, float2 *__restrict__ thrz, float2 *__restrict__ exact,
+                                    float *__restrict__ zexit)
 {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y * blockDim.y + threadIdx.y;
-    if (u >= w || v >= h) return;
-    const int p = v * w + u;
-    const float d = depth[p];
-    const float lx = __fmul_rn(rcp_fdividef(fx), __fsub_rn((float)u, cx));
-    const float ly = __fmul_rn(rcp_fdividef(fy), __fsub_rn((float)v, cy));
-    const float lam = __fsqrt_rn(__fadd_rn(__fmaf_rn(lx, lx, __fmul_rn(ly, ly)), 1.0f));
-    const float il = rcp_fdividef(lam);
-    exact[p] = make_float2(d, il);
-    float hi2 = -1.f, lo2 = -1.f;
-    if (d > 0.f)
+    float lo_z = -1.f;
+    if (u < w && v < h)
     {
-        const float T = trunc * 1.00001f;
-        const float a = d - T - 1e-6f;
-        if (a > 0.f)
+        const int p = v * w + u;
+        const float d = depth[p];
+        const float lx = __fmul_rn(rcp_fdividef(fx), __fsub_rn((float)u, cx));
+        const float ly = __fmul_rn(rcp_fdividef(fy), __fsub_rn((float)v, cy));
+        const float lam = __fsqrt_rn(__fadd_rn(__fmaf_rn(lx, lx, __fmul_rn(ly, ly)), 1.0f));
+        const float il = rcp_fdividef(lam);
+        exact[p] = make_float2(d, il);
+        float hi_z = -1.f;
+        if (d > 0.f)
         {
-            const float b = a * lam;
-            hi2 = b * b * (1.f - 8e-6f);
+            const float hx = 0.501f / fx, hy = 0.501f / fy;
+            const float ax = fabsf(lx), ay = fabsf(ly);
+            const float lmax2 = 1.f + (ax + hx) * (ax + hx) + (ay + hy) * (ay + hy);
+            const float mx = fmaxf(ax - hx, 0.f), my = fmaxf(ay - hy, 0.f);
+            const float lmin2 = 1.f + mx * mx + my * my;
+            const float T = trunc * 1.00001f;
+            const float a = d - T - 1e-6f;
+            if (a > 0.f)
+            {
+                const float b = a * lam;
+                const float hi2 = b * b * (1.f - 8e-6f);
+                hi_z = sqrtf(hi2 / lmax2) * (1.f - 1e-6f);
+            }
+            const float c = (d + T + 1e-6f) * lam;
+            const float lo2 = c * c * (1.f + 8e-6f);
+            lo_z = sqrtf(lo2 / lmin2) * (1.f + 1e-6f);
         }
-        const float c = (d + T + 1e-6f) * lam;
-        lo2 = c * c * (1.f + 8e-6f);
+        thrz[p] = make_float2(hi_z, lo_z);
     }
-    thr[p] = __halves2half2(__float2half_rd(hi2), __float2half_ru(lo2));
+    // image-wide max of lo_z (positive floats order like their bit patterns)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lo_z = fmaxf(lo_z, __shfl_xor_sync(0xffffffffu, lo_z, o));
+    if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && lo_z > 0.f) atomicMax((int *)zexit, __float_as_int(lo_z));
+}
+
+// wtab[wt] = {(float)wt, MUFU.RCP(wt + 1), bits(min(wt + 1, max_weight) << 16), 0}: the weight-dependent
+// operands of the running mean (tsdf_volume.cu:72-77), produced by the same device instructions the
+// update would execute.
+__global__ void build_wtab_kernel(float4 *__restrict__ wtab, int max_weight)
+{
+    const int wt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (wt > max_weight) return;
+    const int wp1 = wt + 1;
+    wtab[wt] = make_float4((float)wt, rcp_fdividef((float)wp1), __uint_as_float((unsigned)min(wp1, max_weight) << 16), 0.f);
+}
+
+// ---- the update (tsdf_volume.cu:69-79) ---------------------------------------------------
+// generic form, any stored word
+__device__ __noinline__ unsigned int update_generic(unsigned int wv, float t, int max_weight)
+{
+    const int tsv = (int)(short)(wv & 0xffffu);
+    const int wt = (int)(short)(wv >> 16);
+    const float pre = __fmul_rn((float)tsv, KFB_DIVSHORTMAX);
+    const int wp1 = wt + 1;
+    const float rd = rcp_fdividef((float)wp1);
+    const float nt = __fmul_rn(rd, __fmaf_rn(pre, (float)wt, t));
+    int q = __float2int_rz(__fmul_rn(nt, (float)KFB_SHORTMAX));
+    q = max(-KFB_SHORTMAX, min(KFB_SHORTMAX, q));
+    const int nw = min(wp1, max_weight);
+    return ((unsigned)q & 0xffffu) | ((unsigned)nw << 16);
+}
+// same result without the XU pipe for weights in [0, max_weight] (everything this library ever writes)
+__device__ __forceinline__ unsigned int update_word(unsigned int wv, float t, const IntegrateArgs &a)
+{
+    const int wt = (int)wv >> 16;
+    if ((unsigned)wt > (unsigned)a.max_weight) return update_generic(wv, t, a.max_weight);
+    const float4 e = __ldg(a.wtab + wt);
+    const int tsv = (int)(short)(wv & 0xffffu);
+    const float tsf = __fsub_rn(__int_as_float(KFB_MAGIC_I + tsv), KFB_MAGIC_F);     // (float)tsv, exact
+    const float pre = __fmul_rn(tsf, KFB_DIVSHORTMAX);
+    const float nt = __fmul_rn(e.y, __fmaf_rn(pre, e.x, t));
+    const float s = __fmul_rn(nt, (float)KFB_SHORTMAX);                               // |s| < 2^16 here
+    int qa = __float_as_int(__fadd_rz(fabsf(s), 8388608.0f)) - 0x4B000000;            // trunc(|s|)
+    qa = min(qa, KFB_SHORTMAX);
+    const int q = s < 0.f ? -qa : qa;
+    return ((unsigned)q & 0xffffu) | __float_as_uint(e.z);
+}
+
+// exact sdf evaluation for a voxel in the band around the surface (tsdf_volume.cu:63-71)
+__device__ __forceinline__ float band_tsdf(const IntegrateArgs &a, unsigned long long xy, float cz, int p, float rtrunc)
+{
+    float vxk, vyk;
+    unpack2(xy, vxk, vyk);
+    const float2 e = __ldg(a.exact + p);
+    const float d2 = dot3c(vxk, vyk, cz, vxk, vyk, cz);
+    const float nsdf = __fmaf_rn(e.y, __fsqrt_rn(d2), -e.x);
+    return nsdf <= a.trunc ? fminf(1.f, __fmul_rn(rtrunc, -nsdf)) : KFB_SKIP;
+}
+// exact per-voxel predicate + tsdf for any vc.z (cameras inside the volume); cold path
+__device__ __forceinline__ float classify_generic(const IntegrateArgs &a, float cx_, float cy_, float cz, float rtrunc)
+{
+    float t = KFB_SKIP;
+    if (!(cz <= 0.f))
+    {
+        float qx, qy;
+        if (cz >= KFB_FLT_MIN)
+        {
+            const float r = mufu_rcp(cz);
+            qx = __fmul_rn(r, cx_);
+            qy = __fmul_rn(r, cy_);
+        }
+        else
+        {
+            qx = __fdividef(cx_, cz);
+            qy = __fdividef(cy_, cz);
+        }
+        const int ui = __float_as_int(__fadd_rn(__fmaf_rn(qx, a.fx, a.cx), KFB_MAGIC_F)) - KFB_MAGIC_I;
+        const int vi = __float_as_int(__fadd_rn(__fmaf_rn(qy, a.fy, a.cy), KFB_MAGIC_F)) - KFB_MAGIC_I;
+        if ((unsigned)ui < (unsigned)a.w && (unsigned)vi < (unsigned)a.h)
+        {
+            const int p = vi * a.w + ui;
+            const float2 e = __ldg(a.exact + p);
+            if (e.x > 0.f)
+            {
+                const float d2 = dot3c(cx_, cy_, cz, cx_, cy_, cz);
+                const float nsdf = __fmaf_rn(e.y, __fsqrt_rn(d2), -e.x);
+                if (nsdf <= a.trunc) t = fminf(1.f, __fmul_rn(rtrunc, -nsdf));
+            }
+        }
+    }
+    return t;
+}
+
+// bricks within two voxels of a sample that just turned negative (see kfb_raycast.cu for why two)
+__device__ __noinline__ void mark_bricks(uint8_t *flags, int *dirty, int gbx, int gby, int gbz, int gbz0, int x0, int y, int z)
+{
+    const int bx0 = max(x0 - 2, 0) >> 3, bx1 = min((x0 + 5) >> 3, gbx - 1);
+    const int by0 = max(y - 2, 0) >> 3, by1 = min((y + 2) >> 3, gby - 1);
+    const int bz0 = max((max(z - 2, 0) >> 3) - gbz0, 0), bz1 = min(((z + 2) >> 3) - gbz0, gbz - 1);
+    for (int bz = bz0; bz <= bz1; ++bz)
+        for (int by = by0; by <= by1; ++by)
+            for (int bx = bx0; bx <= bx1; ++bx)
+            {
+                uint8_t *f = flags + ((size_t)bz * gby + by) * gbx + bx;
+                if (*f == 0) { *f = 1; *dirty = 1; }
+            }
+}
+
+// phase B of one plane: running weighted mean, re-encode, store (tsdf_volume.cu:69-79)
+template <bool COUNT>
+__device__ __forceinline__ void update_quad(const IntegrateArgs &a, uint4 *vp, const uint4 wd, const float t[4], int x0, int y, int z,
+                                            unsigned int &n_upd)
+{
+    uint4 o = wd;
+    const bool uni = (wd.x == wd.y) & (wd.x == wd.z) & (wd.x == wd.w) & (t[0] == t[1]) & (t[0] == t[2]) & (t[0] == t[3]);
+    if (uni)
+    {
+        o.x = o.y = o.z = o.w = update_word(wd.x, t[0], a);
+        if (COUNT) n_upd += 4;
+    }
+    else
+    {
+        if (t[0] != KFB_SKIP) { o.x = update_word(wd.x, t[0], a); if (COUNT) ++n_upd; }
+        if (t[1] != KFB_SKIP) { o.y = update_word(wd.y, t[1], a); if (COUNT) ++n_upd; }
+        if (t[2] != KFB_SKIP) { o.z = update_word(wd.z, t[2], a); if (COUNT) ++n_upd; }
+        if (t[3] != KFB_SKIP) { o.w = update_word(wd.w, t[3], a); if (COUNT) ++n_upd; }
+    }
+    if ((o.x != wd.x) | (o.y != wd.y) | (o.z != wd.z) | (o.w != wd.w))
+    {
+        __stcs(vp, o);
+        // a voxel that turns negative here (it was not before) activates the bricks around it
+        if (((o.x & ~wd.x) | (o.y & ~wd.y) | (o.z & ~wd.z) | (o.w & ~wd.w)) & 0x8000u)
+            mark_bricks(a.bricks, a.bdirty, a.bx, a.by, a.bz, a.bz0, x0, y, z);
+    }
 }
 
 // ---- the sweep ------------------------------------------------------------------------
+#define KFB_BAND (-8.0f)
 template <int U, bool COUNT>
 __global__ void __launch_bounds__(128) integrate_kernel(const IntegrateArgs a)
 {
@@ -99,7 +317,8 @@ __global__ void __launch_bounds__(128) integrate_kernel(const IntegrateArgs a)
     if (zstart >= zend) return;
 
     // vc at z = 0: R * (x*vs.x, y*vs.y, 0*vs.z) + t   (tsdf_volume.cu:49-50)
-    float vx[4], vy[4], vz[4];
+    unsigned long long xy[4], zz[2];
+    float z0v[4];
     {
         const float py = __fmul_rn((float)y, a.vsy);
         const float pz = __fmul_rn(0.f, a.vsz);
@@ -108,121 +327,196 @@ __global__ void __launch_bounds__(128) integrate_kernel(const IntegrateArgs a)
         {
             const float px = __fmul_rn((float)(x0 + k), a.vsx);
             const float3 r = rot3(a.pose.R, px, py, pz);
-            vx[k] = __fadd_rn(r.x, a.pose.t[0]);
-            vy[k] = __fadd_rn(r.y, a.pose.t[1]);
-            vz[k] = __fadd_rn(r.z, a.pose.t[2]);
+            z0v[k] = __fadd_rn(r.z, a.pose.t[2]);
+            xy[k] = pack2(__fadd_rn(r.x, a.pose.t[0]), __fadd_rn(r.y, a.pose.t[1]));
+        }
+        zz[0] = pack2(z0v[0], z0v[1]);
+        zz[1] = pack2(z0v[2], z0v[3]);
+    }
+    // conservative frustum interval of this thread's four columns (never excludes a voxel the exact
+    // predicate would accept: each plane is relaxed by `slack` and the bound is widened by one step)
+    float lo = (float)zstart, hi = (float)(zend - 1);
+    {
+        float ax, ay, bx_, by_;
+        unpack2(xy[0], ax, ay);
+        unpack2(xy[3], bx_, by_);
+        const float zx = __ldg(a.zexit);
+#pragma unroll
+        for (int c = 0; c < KFB_NCULL; ++c)
+        {
+            const CullPlane &cp = a.cull[c];
+            if (cp.kind == 3) continue;
+            const float ga = fmaf(cp.a, ax, fmaf(cp.b, ay, cp.g * z0v[0]));
+            const float gb = fmaf(cp.a, bx_, fmaf(cp.b, by_, cp.g * z0v[3]));
+            float g0 = fmaxf(ga, gb) + cp.slack;
+            if (c == KFB_NCULL - 1) g0 += zx; // vc.z <= zexit
+            const float zc = g0 * cp.ninv;
+            if (cp.kind == 0) lo = fmaxf(lo, zc - 1.f);
+            else if (cp.kind == 1) hi = fminf(hi, zc + 1.f);
+            else if (g0 < 0.f) hi = -1.f;
         }
     }
-    const float sx = a.pose.R.m[2], sy = a.pose.R.m[5], sz = a.pose.R.m[8];
-    // replay of the reference's running sum up to the first plane of this chunk (tsdf_volume.cu:56)
-    for (int z = 1; z < zstart; ++z)
+    lo = fminf(lo, (float)zend);
+    hi = fmaxf(hi, (float)zstart - 2.f);
+    const int za = max(zstart, (int)floorf(lo));
+    const int zb = min(zend - 1, (int)ceilf(hi));
+    if (za > zb) return;
+
+    const float sz = a.pose.R.m[8];
+    const unsigned long long vs2 = pack2(a.vsx, a.vsx), sxy = pack2(a.pose.R.m[2], a.pose.R.m[5]), szz = pack2(sz, sz);
+    // replay of the reference's running sum up to the first visited plane (tsdf_volume.cu:56)
+#pragma unroll 4
+    for (int z = 1; z < za; ++z)
     {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-        {
-            vx[k] = __fmaf_rn(a.vsx, sx, vx[k]);
-            vy[k] = __fmaf_rn(a.vsx, sy, vy[k]);
-            vz[k] = __fmaf_rn(a.vsx, sz, vz[k]);
-        }
+        for (int k = 0; k < 4; ++k) xy[k] = ffma2(vs2, sxy, xy[k]);
+        zz[0] = ffma2(vs2, szz, zz[0]);
+        zz[1] = ffma2(vs2, szz, zz[1]);
+    }
+    // fast path needs vc.z >= FLT_MIN on every visited plane; vc.z is affine in z up to the running-sum
+    // drift (millimetres at most), so the two ends decide with a 1 cm margin
+    bool fast;
+    {
+        const float span = (float)(zb - za + 1) * __fmul_rn(a.vsx, sz);
+        float c0, c1, c2, c3;
+        unpack2(zz[0], c0, c1);
+        unpack2(zz[1], c2, c3);
+        const float m = fminf(fminf(c0, c1), fminf(c2, c3)); // plane za - 1
+        fast = fminf(m, m + span) > 0.01f;
     }
 
     const float rtrunc = rcp_fdividef(a.trunc);
     const size_t plane4 = ((size_t)a.X * a.Y) >> 2; // uint4 per plane
-    uint4 *vp = reinterpret_cast<uint4 *>(a.vol) + ((size_t)(zstart - a.z_store0) * a.Y + y) * (a.X >> 2) + (x0 >> 2);
+    uint4 *vp = reinterpret_cast<uint4 *>(a.vol) + ((size_t)(za - a.z_store0) * a.Y + y) * (a.X >> 2) + (x0 >> 2);
     unsigned int n_upd = 0;
 
-    for (int z = zstart; z < zend; z += U)
+    if (!fast)
     {
-        float ts[U][4];
+        // cold path (camera within a centimetre of this column's planes): one plane at a time, any vc.z
+        for (int z = za; z <= zb; ++z, vp += plane4)
+        {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) xy[k] = ffma2(vs2, sxy, xy[k]);
+            zz[0] = ffma2(vs2, szz, zz[0]);
+            zz[1] = ffma2(vs2, szz, zz[1]);
+            float cz[4], t[4];
+            unpack2(zz[0], cz[0], cz[1]);
+            unpack2(zz[1], cz[2], cz[3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+            {
+                float vxk, vyk;
+                unpack2(xy[k], vxk, vyk);
+                t[k] = classify_generic(a, vxk, vyk, cz[k], rtrunc);
+            }
+            if ((t[0] != KFB_SKIP) | (t[1] != KFB_SKIP) | (t[2] != KFB_SKIP) | (t[3] != KFB_SKIP))
+                update_quad<COUNT>(a, vp, __ldcs(vp), t, x0, y, z, n_upd);
+        }
+        if (COUNT && n_upd) atomicAdd(a.counter, (unsigned long long)n_upd);
+        return;
+    }
+
+    const unsigned long long fxy = pack2(a.fx, a.fy), cxy = pack2(a.cx, a.cy), magic2 = pack2(KFB_MAGIC_F, KFB_MAGIC_F);
+    for (int z = za; z <= zb; z += U)
+    {
+        float ts[U][4], cz[U][4];
+        int pix[U][4];
+        float2 th[U][4];
+        unsigned long long sxyv[U][4];
+        // ---- phase A1: advance, project, issue all threshold loads -------------------------------
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) xy[k] = ffma2(vs2, sxy, xy[k]);
+            zz[0] = ffma2(vs2, szz, zz[0]);
+            zz[1] = ffma2(vs2, szz, zz[1]);
+            unpack2(zz[0], cz[u][0], cz[u][1]);
+            unpack2(zz[1], cz[u][2], cz[u][3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+            {
+                sxyv[u][k] = xy[k];
+                const float r = mufu_rcp(cz[u][k]);
+                const unsigned long long q = fmul2(pack2(r, r), xy[k]);
+                const unsigned long long m = fadd2(ffma2(q, fxy, cxy), magic2);
+                float mu, mv;
+                unpack2(m, mu, mv);
+                const int ui = __float_as_int(mu) - KFB_MAGIC_I;
+                const int vi = __float_as_int(mv) - KFB_MAGIC_I;
+                const bool ok = ((unsigned)ui < (unsigned)a.w) & ((unsigned)vi < (unsigned)a.h) & (z + u <= zb);
+                pix[u][k] = ok ? vi * a.w + ui : -1;
+                th[u][k] = __ldg(a.thrz + max(pix[u][k], 0));
+            }
+        }
+        // ---- phase A2: classify against the thresholds; exact sdf only in the band -------------------
+        bool band = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+            {
+                float t = cz[u][k] <= th[u][k].x ? 1.0f : (cz[u][k] > th[u][k].y ? KFB_SKIP : KFB_BAND);
+                t = pix[u][k] < 0 ? KFB_SKIP : t;
+                band |= (t == KFB_BAND);
+                ts[u][k] = t;
+            }
+        if (band)
+        {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (ts[u][k] == KFB_BAND) ts[u][k] = band_tsdf(a, sxyv[u][k], cz[u][k], pix[u][k], rtrunc);
+        }
+        // ---- loads, then phase B ------------------------------------------------------------------------
         uint4 word[U];
         bool need[U];
-        // ---- phase A: advance, classify, issue loads -------------------------------------
 #pragma unroll
         for (int u = 0; u < U; ++u)
         {
-            need[u] = false;
-            if (z + u < zend)
-            {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                {
-                    vx[k] = __fmaf_rn(a.vsx, sx, vx[k]);
-                    vy[k] = __fmaf_rn(a.vsx, sy, vy[k]);
-                    vz[k] = __fmaf_rn(a.vsx, sz, vz[k]);
-                    float t = KFB_SKIP;
-                    const float cz = vz[k];
-                    if (!(cz <= 0.f))
-                    {
-                        float qx, qy;
-                        if (cz >= KFB_FLT_MIN)
-                        {
-                            const float r = mufu_rcp(cz);
-                            qx = __fmul_rn(r, vx[k]);
-                            qy = __fmul_rn(r, vy[k]);
-                        }
-                        else
-                        {
-                            qx = __fdividef(vx[k], cz);
-                            qy = __fdividef(vy[k], cz);
-                        }
-                        const int ui = __float_as_int(__fadd_rn(__fmaf_rn(qx, a.fx, a.cx), KFB_MAGIC_F)) - KFB_MAGIC_I;
-                        const int vi = __float_as_int(__fadd_rn(__fmaf_rn(qy, a.fy, a.cy), KFB_MAGIC_F)) - KFB_MAGIC_I;
-                        if ((unsigned)ui < (unsigned)a.w && (unsigned)vi < (unsigned)a.h)
-                        {
-                            const int p = vi * a.w + ui;
-                            const float2 th = __half22float2(__ldg(a.thr + p));
-                            const float d2 = dot3c(vx[k], vy[k], cz, vx[k], vy[k], cz);
-                            if (d2 <= th.x)
-                                t = 1.0f;
-                            else if (!(d2 > th.y))
-                            {
-                                const float2 e = __ldg(a.exact + p);
-                                const float nsdf = __fmaf_rn(e.y, __fsqrt_rn(d2), -e.x);
-                                if (nsdf <= a.trunc) t = fminf(1.f, __fmul_rn(rtrunc, -nsdf));
-                            }
-                        }
-                    }
-                    ts[u][k] = t;
-                    need[u] = need[u] || (t != KFB_SKIP);
-                }
-                if (need[u]) word[u] = __ldcs(vp + (size_t)u * plane4);
-            }
+            need[u] = (ts[u][0] != KFB_SKIP) | (ts[u][1] != KFB_SKIP) | (ts[u][2] != KFB_SKIP) | (ts[u][3] != KFB_SKIP);
+            if (need[u]) word[u] = __ldcs(vp + (size_t)u * plane4);
         }
-        // ---- phase B: running weighted mean, re-encode, store (tsdf_volume.cu:69-79) --------
 #pragma unroll
         for (int u = 0; u < U; ++u)
-        {
-            if (need[u])
-            {
-                unsigned int wv[4] = {word[u].x, word[u].y, word[u].z, word[u].w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                {
-                    if (ts[u][k] != KFB_SKIP)
-                    {
-                        const int tsv = (int)(short)(wv[k] & 0xffffu);
-                        const int wt = (int)(short)(wv[k] >> 16);
-                        const float pre = __fmul_rn((float)tsv, KFB_DIVSHORTMAX);
-                        const int wp1 = wt + 1;
-                        const float rd = rcp_fdividef((float)wp1);
-                        const float nt = __fmul_rn(rd, __fmaf_rn(pre, (float)wt, ts[u][k]));
-                        int q = __float2int_rz(__fmul_rn(nt, (float)KFB_SHORTMAX));
-                        q = max(-KFB_SHORTMAX, min(KFB_SHORTMAX, q));
-                        const int nw = min(wp1, a.max_weight);
-                        wv[k] = ((unsigned)q & 0xffffu) | ((unsigned)nw << 16);
-                        if (COUNT) ++n_upd;
-                    }
-                }
-                __stcs(vp + (size_t)u * plane4, make_uint4(wv[0], wv[1], wv[2], wv[3]));
-            }
-        }
+            if (need[u]) update_quad<COUNT>(a, vp + (size_t)u * plane4, word[u], ts[u], x0, y, z + u, n_upd);
         vp += (size_t)U * plane4;
     }
-    if (COUNT)
+    if (COUNT && n_upd) atomicAdd(a.counter, (unsigned long long)n_upd); // threads leave at different times: no shuffles
+}
+
+// Conservative frustum planes for this launch (see CullPlane).  vc(x, y, z) = P0(x, y) + z * S in exact
+// arithmetic; the float running sum drifts from it by at most E = planes * 2^-24 * max|vc| per component.
+static void make_cull_planes(const kfb_ctx *ctx, const IntegrateArgs &a, CullPlane out[KFB_NCULL])
+{
+    const Intr &k = ctx->L[0].k;
+    const double S[3] = {(double)a.vsx * a.pose.R.m[2], (double)a.vsx * a.pose.R.m[5], (double)a.vsx * a.pose.R.m[8]};
+    const double M = fabs(a.pose.t[0]) + fabs(a.pose.t[1]) + fabs(a.pose.t[2]) +
+                     (double)ctx->p.volu_range[0] + ctx->p.volu_range[1] + ctx->p.volu_range[2] +
+                     (double)a.vsx * ctx->p.volu_dims[2] * 1.01;
+    const double E = ((double)ctx->p.volu_dims[2] + 16.0) * 1.2e-7 * M;
+    const double mp = 0.01; // pixels: float error of the projection arithmetic
+    const bool sane = k.cx >= 0.f && k.cx <= (float)(k.w - 1) && k.cy >= 0.f && k.cy <= (float)(k.h - 1) && k.fx > 0.f && k.fy > 0.f;
+    const double pl[KFB_NCULL][3] = {
+        {(double)k.fx, 0.0, (double)k.cx + 0.5 + mp},                // u >= -0.5
+        {-(double)k.fx, 0.0, (double)k.w - 0.5 + mp - (double)k.cx}, // u <= w - 0.5
+        {0.0, (double)k.fy, (double)k.cy + 0.5 + mp},                // v >= -0.5
+        {0.0, -(double)k.fy, (double)k.h - 0.5 + mp - (double)k.cy}, // v <= h - 0.5
+        {0.0, 0.0, 1.0},                                             // vc.z > 0
+        {0.0, 0.0, -1.0},                                            // vc.z <= *zexit (added on the device)
+    };
+    for (int c = 0; c < KFB_NCULL; ++c)
     {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) n_upd += __shfl_xor_sync(0xffffffffu, n_upd, o);
-        if ((threadIdx.x & 31) == 0 && n_upd) atomicAdd(a.counter, (unsigned long long)n_upd);
+        CullPlane &o = out[c];
+        const double n1 = fabs(pl[c][0]) + fabs(pl[c][1]) + fabs(pl[c][2]);
+        const double g1 = pl[c][0] * S[0] + pl[c][1] * S[1] + pl[c][2] * S[2];
+        o.a = (float)pl[c][0]; o.b = (float)pl[c][1]; o.g = (float)pl[c][2];
+        o.slack = (float)((E + 2e-6 * M) * n1 * 1.01 + 1e-6);
+        o.ninv = 0.f;
+        if (!sane && c < 4) { o.kind = 3; continue; }
+        if (fabs(g1) < 1e-9 * n1) o.kind = 2;
+        else { o.kind = g1 > 0 ? 0 : 1; o.ninv = (float)(-1.0 / g1); }
     }
 }
 
@@ -230,9 +524,10 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
 {
     const Intr &k = ctx->L[0].k;
     {
+        KFB_CUDA(ctx, cudaMemsetAsync(ctx->zexit, 0, sizeof(float), ctx->stream));
         dim3 b(32, 8), g((k.w + 31) / 32, (k.h + 7) / 8);
         build_tables_kernel<<<g, b, 0, ctx->stream>>>(ctx->L[0].depth, k.w, k.h, k.fx, k.fy, k.cx, k.cy,
-                                                     ctx->p.volu_trun_dist, ctx->tab_thr, ctx->tab_exact);
+                                                     ctx->p.volu_trun_dist, ctx->tab_thrz, ctx->tab_exact, ctx->zexit);
         KFB_LAUNCH_CHECK(ctx);
     }
     IntegrateArgs a;
@@ -247,18 +542,26 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
     a.trunc = ctx->p.volu_trun_dist;
     a.fx = k.fx; a.fy = k.fy; a.cx = k.cx; a.cy = k.cy;
     a.w = k.w; a.h = k.h;
-    a.thr = ctx->tab_thr;
+    a.thrz = ctx->tab_thrz;
     a.exact = ctx->tab_exact;
+    a.wtab = ctx->wtab;
+    a.zexit = ctx->zexit;
     a.max_weight = ctx->p.tsdf_max_weight;
+    a.bricks = ctx->bricks;
+    a.bdirty = ctx->bdirty;
+    a.bx = ctx->bdim[0]; a.by = ctx->bdim[1]; a.bz = ctx->bdim[2]; a.bz0 = ctx->bz0;
     a.counter = ctx->counters;
+    make_cull_planes(ctx, a, a.cull);
+    if (getenv("KFB_INTEGRATE_NOCULL"))
+        for (int c = 0; c < KFB_NCULL; ++c) a.cull[c].kind = 3;
 
     const int planes = a.ze - a.zb;
     if (planes <= 0) return KFB_OK;
-    // z-chunking trades replayed running-sum adds for resident warps; small volumes need it
-    // to fill 148 SMs.  KFB_INTEGRATE_ZCHUNKS overrides for tuning.
+    // z-chunking trades replayed running-sum adds for resident warps and load balance (the visited
+    // interval differs per column).  KFB_INTEGRATE_ZCHUNKS overrides for tuning.
     const long cols = ((long)(a.X + 127) / 128) * ((a.Y + 3) / 4);
     int zc = 1;
-    while (cols * zc < 148L * 8 && zc < 16 && planes / (zc * 2) >= 32) zc *= 2;
+    while (cols * zc < 148L * 12 && zc < 16 && planes / (zc * 2) >= 32) zc *= 2;
     if (const char *e = getenv("KFB_INTEGRATE_ZCHUNKS")) zc = atoi(e) > 0 ? atoi(e) : zc;
     a.zchunk = (planes + zc - 1) / zc;
     dim3 block(32, 4), grid((a.X + 127) / 128, (a.Y + 3) / 4, zc);
@@ -279,6 +582,89 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
         KFB_LAUNCH_CHECK(ctx);
         if (ctx->profiling) cudaEventRecord(ctx->events[61], ctx->stream);
     }
+    return launch_brick_distance(ctx);
+}
+
+int launch_build_wtab(kfb_ctx *ctx)
+{
+    const int n = ctx->p.tsdf_max_weight + 1;
+    build_wtab_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(ctx->wtab, ctx->p.tsdf_max_weight);
+    KFB_LAUNCH_CHECK(ctx);
+    return KFB_OK;
+}
+
+// ---- brick map maintenance -------------------------------------------------------------------------
+// full rescan (after kfb_upload_volume): same marking rule as the integrate kernel
+__global__ void rebuild_bricks_kernel(const IntegrateArgs a, int zs0, int zs1)
+{
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x0 >= a.X || y >= a.Y) return;
+    const size_t plane4 = ((size_t)a.X * a.Y) >> 2;
+    const uint4 *vp = reinterpret_cast<const uint4 *>(a.vol) + (size_t)y * (a.X >> 2) + (x0 >> 2);
+    for (int z = zs0 + blockIdx.z; z < zs1; z += gridDim.z)
+    {
+        const uint4 o = __ldg(vp + (size_t)(z - zs0) * plane4);
+        if ((o.x | o.y | o.z | o.w) & 0x8000u) mark_bricks(a.bricks, a.bdirty, a.bx, a.by, a.bz, a.bz0, x0, y, z);
+    }
+}
+
+int launch_rebuild_bricks(kfb_ctx *ctx)
+{
+    const size_t nb = (size_t)ctx->bdim[0] * ctx->bdim[1] * ctx->bdim[2];
+    KFB_CUDA(ctx, cudaMemsetAsync(ctx->bricks, 0, nb, ctx->stream));
+    IntegrateArgs a;
+    memset(&a, 0, sizeof(a));
+    a.vol = ctx->vol;
+    a.X = ctx->p.volu_dims[0]; a.Y = ctx->p.volu_dims[1];
+    a.bricks = ctx->bricks;
+    a.bdirty = ctx->bdirty;
+    a.bx = ctx->bdim[0]; a.by = ctx->bdim[1]; a.bz = ctx->bdim[2]; a.bz0 = ctx->bz0;
+    dim3 block(32, 4), grid((a.X / 4 + 31) / 32, (a.Y + 3) / 4, 32);
+    rebuild_bricks_kernel<<<grid, block, 0, ctx->stream>>>(a, ctx->z0, ctx->z1);
+    KFB_LAUNCH_CHECK(ctx);
+    KFB_CUDA(ctx, cudaMemsetAsync(ctx->bdirty, 1, sizeof(int), ctx->stream)); // non-zero: force a distance rebuild
+    return launch_brick_distance(ctx);
+}
+
+// ---- brick distance map ----------------------------------------------------------------------------
+// bdist[b] = min(KFB_BDIST_CAP, Chebyshev distance in bricks from b to the nearest active brick), 0 for an
+// active brick.  Three separable passes: d(b) = min over offsets j along the axis of max(src(b + j), |j|).
+// Every pass returns at once unless a brick flag has flipped since the last rebuild (*dirty != 0); flags
+// only ever flip 0 -> 1 between resets, so a clean map stays exact.
+__global__ void brick_distance_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int bx, int by, int bz, int axis,
+                                      const int *__restrict__ dirty, int from_flags)
+{
+    if (*dirty == 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = bx * by * bz;
+    if (i >= n) return;
+    const int x = i % bx, y = (i / bx) % by, z = i / (bx * by);
+    const int pos = axis == 0 ? x : (axis == 1 ? y : z);
+    const int len = axis == 0 ? bx : (axis == 1 ? by : bz);
+    const int stride = axis == 0 ? 1 : (axis == 1 ? bx : bx * by);
+    int best = KFB_BDIST_CAP;
+    const int j0 = max(-KFB_BDIST_CAP, -pos), j1 = min(KFB_BDIST_CAP, len - 1 - pos);
+    for (int j = j0; j <= j1; ++j)
+    {
+        int v = src[i + j * stride];
+        if (from_flags) v = v ? 0 : KFB_BDIST_CAP;
+        best = min(best, max(v, abs(j)));
+    }
+    dst[i] = (uint8_t)best;
+}
+
+int launch_brick_distance(kfb_ctx *ctx)
+{
+    const int n = ctx->bdim[0] * ctx->bdim[1] * ctx->bdim[2];
+    const int blocks = (n + 255) / 256;
+    brick_distance_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bricks, ctx->bdist_tmp, ctx->bdim[0], ctx->bdim[1], ctx->bdim[2], 0, ctx->bdirty, 1);
+    KFB_LAUNCH_CHECK(ctx);
+    brick_distance_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bdist_tmp, ctx->bdist_tmp2, ctx->bdim[0], ctx->bdim[1], ctx->bdim[2], 1, ctx->bdirty, 0);
+    KFB_LAUNCH_CHECK(ctx);
+    brick_distance_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bdist_tmp2, ctx->bdist, ctx->bdim[0], ctx->bdim[1], ctx->bdim[2], 2, ctx->bdirty, 0);
+    KFB_LAUNCH_CHECK(ctx);
+    KFB_CUDA(ctx, cudaMemsetAsync(ctx->bdirty, 0, sizeof(int), ctx->stream));
     return KFB_OK;
 }
 
@@ -286,6 +672,10 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
 int launch_reset_volume(kfb_ctx *ctx)
 {
     KFB_CUDA(ctx, cudaMemsetAsync(ctx->vol, 0, ctx->vol_voxels * sizeof(uint32_t), ctx->stream));
+    const size_t nb = (size_t)ctx->bdim[0] * ctx->bdim[1] * ctx->bdim[2];
+    KFB_CUDA(ctx, cudaMemsetAsync(ctx->bricks, 0, nb, ctx->stream));
+    KFB_CUDA(ctx, cudaMemsetAsync(ctx->bdist, KFB_BDIST_CAP, nb, ctx->stream)); // no active brick anywhere
+    KFB_CUDA(ctx, cudaMemsetAsync(ctx->bdirty, 0, sizeof(int), ctx->stream));
     return KFB_OK;
 }
 

@@ -5,10 +5,21 @@
 // nearest-neighbour sample for the sign test, first +->- pair => vertex at
 // ray_len -/+ vs*cur/(cur-next) (the reference's sign quirk behind compat_raycast_ts_sign),
 // normal = normalised central difference of six trilinear fetches, outputs rotated back to the
-// camera frame, explicit zeros on a miss.  Structure is new: a warp owns an 8x4 pixel tile (coherent
-// rays), the march is software-pipelined in batches (sample positions do not depend on fetched
-// values, so KFB_RC_BATCH independent gathers are in flight per ray before the first sign test),
-// and the running sums `nextp += dir*voxel_size`, `ray_len += step` are replayed exactly.
+// camera frame, explicit zeros on a miss.  The running sums `nextp += dir*voxel_size` and
+// `ray_len += step` are replayed exactly, step for step.  Structure is new:
+//   * a warp owns an 8x4 pixel tile (coherent rays);
+//   * empty-space skipping that cannot change a result: a terminal event (hit or back-face stop) needs
+//     one negative and one positive sample in consecutive steps, and consecutive samples are at most two
+//     voxels apart per axis, so a sample whose 8^3 brick has no negative voxel within two voxels (the byte
+//     map kfb_integrate.cu maintains) can take part in no event.  Such samples are not fetched (they count
+//     as NaN, which the reference's `isnan(next)` test already skips); a Chebyshev distance map over the
+//     bricks says how many further steps provably stay clear of every such brick, and those steps are run
+//     with the four running-sum instructions only;
+//   * index rounding by magic-number add instead of F2I (the quarter-rate conversion pipe);
+//   * z-slab mode (sharded volumes): samples outside the stored planes are "not mine"
+//     (NaN), events are evaluated only when the `next` sample's voxel plane is owned by this slab, and the
+//     ray length of the first terminal event is written as an order-preserving key for the cross-slab
+//     composite (kfb_composite_mask).
 #include "kfb_common.cuh"
 
 namespace kfb
@@ -18,39 +29,41 @@ struct RaycastArgs
 {
     const uint32_t *vol;
     int X, Y, Z;          // global dims
-    int z_store0;         // first stored plane
+    int zs0, zs1;         // stored planes [zs0, zs1)
+    int zo0, zo1;         // owned planes  [zo0, zo1)
     Pose pose;            // cam2vol
     Mat3 rinv;
     Intr k;
     float vs[3], vsinv[3], gd[3], range[3];
     float step_len;
     float4 *vmap, *nmap;
-    float *hit_t;
+    float *key;
     int ts_sign_compat;
+    const uint8_t *bdist;
+    int bx, by, bz, bz0;
 };
 
-#define KFB_RC_BATCH 4
+#define KFB_RC_MAGIC_F 12582912.0f
+#define KFB_RC_MAGIC_I 0x4B400000
+#define KFB_QNAN __int_as_float(0x7fffffff)
+
+// __float2int_rn for |v| < 2^22 (larger magnitudes and NaN come out far outside any volume)
+__device__ __forceinline__ int rn_magic(float v) { return __float_as_int(__fadd_rn(v, KFB_RC_MAGIC_F)) - KFB_RC_MAGIC_I; }
+// (float)i for |i| < 2^22
+__device__ __forceinline__ float i2f_magic(int i) { return __fsub_rn(__int_as_float(KFB_RC_MAGIC_I + i), KFB_RC_MAGIC_F); }
 
 __device__ __forceinline__ float vox_tsdf(const RaycastArgs &a, int x, int y, int z)
 {
-    const size_t i = ((size_t)(z - a.z_store0) * a.Y + y) * a.X + x;
+    z = min(max(z, a.zs0), a.zs1 - 1); // slab mode: never read outside the stored planes
+    const size_t i = ((size_t)(z - a.zs0) * a.Y + y) * a.X + x;
     const short s = __ldg(reinterpret_cast<const short *>(a.vol + i)); // low half = tsdf
     return __fmul_rn((float)s, KFB_DIVSHORTMAX);
-}
-// raycasthelper::voxel2tsdf (tsdf_volume.cu:178-191)
-__device__ __forceinline__ float fetch_nn(const RaycastArgs &a, float px, float py, float pz)
-{
-    const int x = __float2int_rn(__fmul_rn(px, a.vsinv[0]));
-    const int y = __float2int_rn(__fmul_rn(py, a.vsinv[1]));
-    const int z = __float2int_rn(__fmul_rn(pz, a.vsinv[2]));
-    if (x >= a.X - 1 || y >= a.Y - 1 || z >= a.Z - 1 || x < 1 || y < 1 || z < 1) return __int_as_float(0x7fffffff);
-    return vox_tsdf(a, x, y, z);
 }
 // interpolate (tsdf_volume.cu:137-161)
 __device__ float interp(const RaycastArgs &a, float fx, float fy, float fz)
 {
     const int gx = __float2int_rd(fx), gy = __float2int_rd(fy), gz = __float2int_rd(fz);
-    if (gx < 0 || gx >= a.X - 1 || gy < 0 || gy >= a.Y - 1 || gz < 0 || gz >= a.Z - 1) return __int_as_float(0x7fffffff);
+    if (gx < 0 || gx >= a.X - 1 || gy < 0 || gy >= a.Y - 1 || gz < 0 || gz >= a.Z - 1) return KFB_QNAN;
     const float fa = __fsub_rn(fx, (float)gx), fb = __fsub_rn(fy, (float)gy), fc = __fsub_rn(fz, (float)gz);
     const float a1 = __fsub_rn(1.f, fa), b1 = __fsub_rn(1.f, fb), c1 = __fsub_rn(1.f, fc);
     const float v000 = vox_tsdf(a, gx, gy, gz), v001 = vox_tsdf(a, gx, gy, gz + 1);
@@ -69,15 +82,74 @@ __device__ float interp(const RaycastArgs &a, float fx, float fy, float fz)
     return t;
 }
 
+struct RaySkip // per-ray constants of the skip computation, voxel units
+{
+    float sgn[3];   // sign of the per-step move along each axis (+1 / -1)
+    float inv[3];   // 1 / |move per step|  (1e30 when the ray does not move along the axis)
+};
+
+enum { ST_FETCH = 0, ST_NAN = 1, ST_LEAVE = 2 };
+#define KFB_RC_BATCH 4
+
+// raycasthelper::voxel2tsdf (tsdf_volume.cu:178-191) with brick / slab knowledge, split into "where" and
+// "load".  ST_FETCH: the sample must be read (*addr).  ST_NAN: the sample is NaN for the march -- outside the
+// volume interior, outside this slab's stored planes, or in a brick that cannot take part in an event --
+// and `cnt` further steps are guaranteed to be NaN for the same reason.  ST_LEAVE: the ray moves away from
+// the stored planes for good.  `own` = the sample's voxel plane belongs to this slab.
+__device__ __forceinline__ int classify(const RaycastArgs &a, const RaySkip &rs, float px, float py, float pz, bool &own,
+                                        int &cnt, const short *&addr)
+{
+    const float qx = __fmul_rn(px, a.vsinv[0]), qy = __fmul_rn(py, a.vsinv[1]), qz = __fmul_rn(pz, a.vsinv[2]);
+    const int x = rn_magic(qx), y = rn_magic(qy), z = rn_magic(qz);
+    own = false; cnt = 0; addr = nullptr;
+    if ((unsigned)(x - 1) >= (unsigned)(a.X - 2) || (unsigned)(y - 1) >= (unsigned)(a.Y - 2) || (unsigned)(z - 1) >= (unsigned)(a.Z - 2))
+        return ST_NAN;
+    if (z < a.zs0 || z >= a.zs1)
+    {
+        // outside the stored planes: steps until the sample can reach them (1.5 voxels of margin for the
+        // drift of the replayed running sum over a long run)
+        const bool below = z < a.zs0;
+        const bool toward = below ? rs.sgn[2] > 0.f : rs.sgn[2] < 0.f;
+        if (!toward) return ST_LEAVE;
+        const float dist = below ? __fsub_rn((float)a.zs0 - 2.0f, qz) : __fsub_rn(qz, (float)a.zs1 + 1.0f);
+        const float s = __fmul_rn(dist, rs.inv[2]);
+        cnt = s > 1.f ? (int)fminf(s, 1e6f) - 1 : 0;
+        return ST_NAN;
+    }
+    own = z >= a.zo0 && z < a.zo1;
+    // Chebyshev distance D (in bricks) to the nearest brick that may hold a negative voxel; 0 = such a brick.
+    // Index moves by at most n + 1 per axis over n steps, an active brick is at least (D-1)*8 + 1 voxels
+    // away along some axis, so the next (D-1)*8 - 1 samples cannot lie in one.
+    const int D = __ldg(a.bdist + ((size_t)((z >> 3) - a.bz0) * a.by + (y >> 3)) * a.bx + (x >> 3));
+    if (D == 0)
+    {
+        addr = reinterpret_cast<const short *>(a.vol + ((size_t)(z - a.zs0) * a.Y + y) * a.X + x); // low half = tsdf
+        return ST_FETCH;
+    }
+    cnt = max((D - 1) * 8 - 1, 0);
+    return ST_NAN;
+}
+__device__ __forceinline__ float load_tsdf(const short *addr)
+{
+    const int s = __ldg(addr);
+    return __fmul_rn(i2f_magic(s), KFB_DIVSHORTMAX);
+}
+
+// The march is warp-cooperative: all rays of an 8x4 tile step together.  When no ray of the warp needs a
+// fetch for its next sample, the warp skips the minimum of the rays' guaranteed-NaN step counts with the
+// running-sum instructions only; otherwise KFB_RC_BATCH steps are classified and their loads issued before
+// the first sign test (sample positions do not depend on fetched values).  Candidate hits are parked and
+// their normals are computed after the march, when the warp has reconverged.
 __global__ void __launch_bounds__(128) raycast_kernel(const RaycastArgs a)
 {
+    const unsigned FULL = 0xffffffffu;
     // warp = 8x4 pixel tile; block = 8x16 pixels
     const int x = blockIdx.x * 8 + threadIdx.x;
     const int y = blockIdx.y * 16 + threadIdx.y;
-    if (x >= a.k.w || y >= a.k.h) return;
+    const bool inside = x < a.k.w && y < a.k.h;
     const int pix = y * a.k.w + x;
     float4 vout = make_float4(0.f, 0.f, 0.f, 0.f), nout = vout;
-    float t_hit = __int_as_float(0x7f800000); // +inf = miss
+    float key = __int_as_float(0x7f800000); // +inf = no event
 
     const float ox = a.pose.t[0], oy = a.pose.t[1], oz = a.pose.t[2];
     // reproj(x, y, 1) and ray direction (tsdf_volume.cu:217-220)
@@ -100,72 +172,176 @@ __global__ void __launch_bounds__(128) raycast_kernel(const RaycastArgs a)
     const float tnear = fmaxf(fmaxf(mnx, mny), fmaxf(mnx, mnz));
     const float tfar = fminf(fminf(mxx, mxy), fminf(mxx, mxz));
     float ray_len = fmaxf(tnear, 0.f);
-    if (!(ray_len >= tfar))
+    bool marching = inside && !(ray_len >= tfar);
+
+    RaySkip rs;
+    {
+        // move per step in voxel units: dir * vs * (1/vs), slightly overestimated so step counts err low
+        const float mx = fabsf(dx) * a.vs[0] * a.vsinv[0] * 1.0001f, my = fabsf(dy) * a.vs[1] * a.vsinv[1] * 1.0001f,
+                    mz = fabsf(dz) * a.vs[2] * a.vsinv[2] * 1.0001f;
+        rs.sgn[0] = dx < 0.f ? -1.f : 1.f; rs.sgn[1] = dy < 0.f ? -1.f : 1.f; rs.sgn[2] = dz < 0.f ? -1.f : 1.f;
+        rs.inv[0] = mx > 1e-30f ? 1.f / mx : 1e30f;
+        rs.inv[1] = my > 1e-30f ? 1.f / my : 1e30f;
+        rs.inv[2] = mz > 1e-30f ? 1.f / mz : 1e30f;
+    }
+    float nx = 0.f, ny = 0.f, nz = 0.f, tnext = KFB_QNAN;
+    if (marching)
     {
         ray_len = __fadd_rn(ray_len, a.step_len);
-        float nx = __fmaf_rn(dx, ray_len, ox), ny = __fmaf_rn(dy, ray_len, oy), nz = __fmaf_rn(dz, ray_len, oz);
-        float tnext = fetch_nn(a, nx, ny, nz);
-        bool done = false;
-        while (!done && ray_len < tfar)
+        nx = __fmaf_rn(dx, ray_len, ox); ny = __fmaf_rn(dy, ray_len, oy); nz = __fmaf_rn(dz, ray_len, oz);
+        bool own; int cnt; const short *addr;
+        const int st = classify(a, rs, nx, ny, nz, own, cnt, addr);
+        if (st == ST_FETCH) tnext = load_tsdf(addr);
+        if (st == ST_LEAVE) marching = false;
+    }
+    // parked candidate hit
+    bool pend = false;
+    float c_tcur = 0.f, c_tnext = 0.f, c_len = 0.f;
+
+    for (;;)
+    {
+        // ---- march ----------------------------------------------------------------------------------
+        for (;;)
         {
+            const bool alive = marching && ray_len < tfar;
+            if (!__any_sync(FULL, alive)) break;
+            float qx[KFB_RC_BATCH], qy[KFB_RC_BATCH], qz[KFB_RC_BATCH];
+            int st[KFB_RC_BATCH], cnt0 = 0;
+            bool own[KFB_RC_BATCH];
+            const short *addr[KFB_RC_BATCH];
+            qx[0] = __fmaf_rn(dx, a.vs[0], nx); qy[0] = __fmaf_rn(dy, a.vs[1], ny); qz[0] = __fmaf_rn(dz, a.vs[2], nz);
+            st[0] = ST_NAN; own[0] = false; addr[0] = nullptr;
+            if (alive) st[0] = classify(a, rs, qx[0], qy[0], qz[0], own[0], cnt0, addr[0]);
+            if (__all_sync(FULL, !alive || st[0] != ST_FETCH))
+            {
+                // no ray of the warp needs this sample: it is NaN for all; then skip what every ray can skip
+                int nskip = __reduce_min_sync(FULL, (alive && st[0] == ST_NAN) ? cnt0 : 0x7fffffff);
+                if (nskip == 0x7fffffff) nskip = 0;
+                if (alive)
+                {
+                    if (st[0] == ST_LEAVE) marching = false;
+                    nx = qx[0]; ny = qy[0]; nz = qz[0];
+                    tnext = KFB_QNAN;
+                    ray_len = __fadd_rn(ray_len, a.step_len);
+                }
+#pragma unroll 4
+                for (int i = 0; i < nskip; ++i)
+                {
+                    if (marching && ray_len < tfar)
+                    {
+                        nx = __fmaf_rn(dx, a.vs[0], nx); ny = __fmaf_rn(dy, a.vs[1], ny); nz = __fmaf_rn(dz, a.vs[2], nz);
+                        ray_len = __fadd_rn(ray_len, a.step_len);
+                    }
+                }
+                continue;
+            }
+            // ---- batch: classify the following steps too, issue all loads, then test in order ------------
+#pragma unroll
+            for (int b = 1; b < KFB_RC_BATCH; ++b)
+            {
+                qx[b] = __fmaf_rn(dx, a.vs[0], qx[b - 1]); qy[b] = __fmaf_rn(dy, a.vs[1], qy[b - 1]); qz[b] = __fmaf_rn(dz, a.vs[2], qz[b - 1]);
+                st[b] = ST_NAN; own[b] = false; addr[b] = nullptr;
+                int c;
+                if (alive) st[b] = classify(a, rs, qx[b], qy[b], qz[b], own[b], c, addr[b]);
+            }
             float val[KFB_RC_BATCH];
 #pragma unroll
-            for (int b = 0; b < KFB_RC_BATCH; ++b)
-            {
-                nx = __fmaf_rn(dx, a.vs[0], nx);
-                ny = __fmaf_rn(dy, a.vs[1], ny);
-                nz = __fmaf_rn(dz, a.vs[2], nz);
-                val[b] = fetch_nn(a, nx, ny, nz);
-            }
+            for (int b = 0; b < KFB_RC_BATCH; ++b) val[b] = (alive && st[b] == ST_FETCH) ? load_tsdf(addr[b]) : KFB_QNAN;
 #pragma unroll
             for (int b = 0; b < KFB_RC_BATCH; ++b)
             {
-                if (!done && ray_len < tfar)
+                if (marching && ray_len < tfar)
                 {
                     const float tcur = tnext;
                     tnext = val[b];
-                    if (!isnan(tnext))
+                    nx = qx[b]; ny = qy[b]; nz = qz[b];
+                    if (st[b] == ST_LEAVE) marching = false;
+                    else if (own[b] && !isnan(tnext))
                     {
                         if (tcur < 0.f && tnext > 0.f)
-                            done = true; // back face: stop, no hit (tsdf_volume.cu:242-243)
+                        {
+                            key = ray_len; // back face: stop, no hit (tsdf_volume.cu:242-243)
+                            marching = false;
+                        }
                         else if (tcur > 0.f && tnext < 0.f)
                         {
-                            const float q = rcp_fdividef(__fsub_rn(tcur, tnext));
-                            const float num = __fmul_rn(tcur, a.vs[0]);
-                            const float Ts = a.ts_sign_compat ? __fmaf_rn(q, -num, ray_len) : __fmaf_rn(q, num, ray_len);
-                            const float vx = __fmaf_rn(dx, Ts, ox), vy = __fmaf_rn(dy, Ts, oy), vz = __fmaf_rn(dz, Ts, oz);
-                            // compute_normal (tsdf_volume.cu:192-209)
-                            const float sx = __fmul_rn(vx, a.vsinv[0]), sy = __fmul_rn(vy, a.vsinv[1]), sz = __fmul_rn(vz, a.vsinv[2]);
-                            const float Fx1 = interp(a, __fmul_rn(__fadd_rn(vx, a.gd[0]), a.vsinv[0]), sy, sz);
-                            const float Fx2 = interp(a, __fmul_rn(__fsub_rn(vx, a.gd[0]), a.vsinv[0]), sy, sz);
-                            const float Fy1 = interp(a, sx, __fmul_rn(__fadd_rn(vy, a.gd[1]), a.vsinv[1]), sz);
-                            const float Fy2 = interp(a, sx, __fmul_rn(__fsub_rn(vy, a.gd[1]), a.vsinv[1]), sz);
-                            const float Fz1 = interp(a, sx, sy, __fmul_rn(__fadd_rn(vz, a.gd[2]), a.vsinv[2]));
-                            const float Fz2 = interp(a, sx, sy, __fmul_rn(__fsub_rn(vz, a.gd[2]), a.vsinv[2]));
-                            float gx = __fdividef(__fsub_rn(Fx1, Fx2), a.gd[0]);
-                            float gy = __fdividef(__fsub_rn(Fy1, Fy2), a.gd[1]);
-                            float gz = __fdividef(__fsub_rn(Fz1, Fz2), a.gd[2]);
-                            const float t = __fsqrt_rn(dot3c(gx, gy, gz, gx, gy, gz));
-                            gx = __fdividef(gx, t); gy = __fdividef(gy, t); gz = __fdividef(gz, t);
-                            if (!isnan(__fmul_rn(__fmul_rn(gx, gy), gz)))
-                            {
-                                const float3 nn = rot3(a.rinv, gx, gy, gz);
-                                const float3 vv = rot3(a.rinv, __fsub_rn(vx, ox), __fsub_rn(vy, oy), __fsub_rn(vz, oz));
-                                nout = make_float4(nn.x, nn.y, nn.z, 0.f);
-                                vout = make_float4(vv.x, vv.y, vv.z, 0.f);
-                                t_hit = Ts;
-                                done = true;
-                            }
+                            pend = true; // normal is computed after the march (may resume if it is NaN)
+                            c_tcur = tcur; c_tnext = tnext; c_len = ray_len;
+                            marching = false;
                         }
                     }
                     ray_len = __fadd_rn(ray_len, a.step_len);
                 }
             }
         }
+        // ---- parked candidates: vertex + normal (tsdf_volume.cu:244-259) -----------------------------------
+        bool resumed = false;
+        if (pend)
+        {
+            pend = false;
+            const float q = rcp_fdividef(__fsub_rn(c_tcur, c_tnext));
+            const float num = __fmul_rn(c_tcur, a.vs[0]);
+            const float Ts = a.ts_sign_compat ? __fmaf_rn(q, -num, c_len) : __fmaf_rn(q, num, c_len);
+            const float vx = __fmaf_rn(dx, Ts, ox), vy = __fmaf_rn(dy, Ts, oy), vz = __fmaf_rn(dz, Ts, oz);
+            // compute_normal (tsdf_volume.cu:192-209)
+            const float ux = __fmul_rn(vx, a.vsinv[0]), uy = __fmul_rn(vy, a.vsinv[1]), uz = __fmul_rn(vz, a.vsinv[2]);
+            const float Fx1 = interp(a, __fmul_rn(__fadd_rn(vx, a.gd[0]), a.vsinv[0]), uy, uz);
+            const float Fx2 = interp(a, __fmul_rn(__fsub_rn(vx, a.gd[0]), a.vsinv[0]), uy, uz);
+            const float Fy1 = interp(a, ux, __fmul_rn(__fadd_rn(vy, a.gd[1]), a.vsinv[1]), uz);
+            const float Fy2 = interp(a, ux, __fmul_rn(__fsub_rn(vy, a.gd[1]), a.vsinv[1]), uz);
+            const float Fz1 = interp(a, ux, uy, __fmul_rn(__fadd_rn(vz, a.gd[2]), a.vsinv[2]));
+            const float Fz2 = interp(a, ux, uy, __fmul_rn(__fsub_rn(vz, a.gd[2]), a.vsinv[2]));
+            float gx = __fdividef(__fsub_rn(Fx1, Fx2), a.gd[0]);
+            float gy = __fdividef(__fsub_rn(Fy1, Fy2), a.gd[1]);
+            float gz = __fdividef(__fsub_rn(Fz1, Fz2), a.gd[2]);
+            const float t = __fsqrt_rn(dot3c(gx, gy, gz, gx, gy, gz));
+            gx = __fdividef(gx, t); gy = __fdividef(gy, t); gz = __fdividef(gz, t);
+            if (!isnan(__fmul_rn(__fmul_rn(gx, gy), gz)))
+            {
+                const float3 nn = rot3(a.rinv, gx, gy, gz);
+                const float3 vv = rot3(a.rinv, __fsub_rn(vx, ox), __fsub_rn(vy, oy), __fsub_rn(vz, oz));
+                nout = make_float4(nn.x, nn.y, nn.z, 0.f);
+                vout = make_float4(vv.x, vv.y, vv.z, 0.f);
+                key = c_len;
+            }
+            else
+            {
+                marching = true; // the reference keeps marching after a NaN normal
+                resumed = true;
+            }
+        }
+        if (!__any_sync(FULL, resumed)) break;
     }
-    a.vmap[pix] = vout;
-    a.nmap[pix] = nout;
-    if (a.hit_t) a.hit_t[pix] = t_hit;
+    if (inside)
+    {
+        a.vmap[pix] = vout;
+        a.nmap[pix] = nout;
+        a.key[pix] = key;
+    }
+}
+
+// cross-slab composite, step 2 (see include/kfb200.h): keep the payload only where this slab holds the
+// winning (smallest) event key; ties cannot occur between slabs because a step has exactly one owner.
+__global__ void composite_mask_kernel(const float *__restrict__ key, const float *__restrict__ min_key, float4 *__restrict__ vmap,
+                                      float4 *__restrict__ nmap, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float k = key[i];
+    if (!(k == min_key[i]) || k == __int_as_float(0x7f800000))
+    {
+        vmap[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        nmap[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+int launch_composite_mask(kfb_ctx *ctx, const float *min_key)
+{
+    const Intr &k = ctx->L[0].k;
+    const int n = k.w * k.h;
+    composite_mask_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->hit_t, min_key, ctx->L[0].v[ctx->prev], ctx->L[0].n[ctx->prev], n);
+    KFB_LAUNCH_CHECK(ctx);
+    return KFB_OK;
 }
 
 int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9])
@@ -173,7 +349,10 @@ int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9]
     RaycastArgs a;
     a.vol = ctx->vol;
     a.X = ctx->p.volu_dims[0]; a.Y = ctx->p.volu_dims[1]; a.Z = ctx->p.volu_dims[2];
-    a.z_store0 = ctx->z0;
+    a.zs0 = ctx->z0; a.zs1 = ctx->z1;
+    const bool slab = ctx->p.slab_z_end > ctx->p.slab_z_begin;
+    a.zo0 = slab ? ctx->p.slab_z_begin : 0;
+    a.zo1 = slab ? ctx->p.slab_z_end : a.Z;
     a.pose = make_pose(cam2vol12);
     for (int i = 0; i < 9; ++i) a.rinv.m[i] = rinv9[i];
     a.k = ctx->L[0].k;
@@ -187,8 +366,10 @@ int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9]
     a.step_len = ctx->voxel_size[0];            // tsdf_volume.cu:174
     a.vmap = ctx->L[0].v[ctx->prev];
     a.nmap = ctx->L[0].n[ctx->prev];
-    a.hit_t = ctx->hit_t;
+    a.key = ctx->hit_t;
     a.ts_sign_compat = ctx->p.compat_raycast_ts_sign;
+    a.bdist = ctx->bdist;
+    a.bx = ctx->bdim[0]; a.by = ctx->bdim[1]; a.bz = ctx->bdim[2]; a.bz0 = ctx->bz0;
     dim3 block(8, 16), grid((a.k.w + 7) / 8, (a.k.h + 15) / 16);
     if (ctx->profiling) cudaEventRecord(ctx->events[58], ctx->stream);
     raycast_kernel<<<grid, block, 0, ctx->stream>>>(a);
