@@ -112,11 +112,12 @@ int kfb_swap_frames(kfb_ctx *ctx);
  * normal equations in the reference's order.  Blocks until out27 is valid. */
 int kfb_icp_accumulate(kfb_ctx *ctx, int level, const float pose12[12], double out27[27]);
 /* The same operation for the whole coarse-to-fine loop of ICPRegistration::rigidTransform
- * (icp_registration.cpp:21-43) without per-iteration launch latency: kfb_icp_begin enqueues the
- * schedule's kernels ahead of time (iters_per_level[l] iterations at level l, coarsest level first);
- * each kernel waits on the GPU until kfb_icp_step publishes that iteration's pose in mapped host
- * memory, then posts its 27 sums back; the host solves 6x6 between steps exactly as with
- * kfb_icp_accumulate.  kfb_icp_end retires any iterations not stepped (tracking failure). */
+ * (icp_registration.cpp:21-43) without per-iteration launch latency: kfb_icp_begin declares the
+ * schedule (iters_per_level[l] iterations at level l, coarsest level first); the first kfb_icp_step
+ * starts ONE persistent kernel that runs every iteration, waiting on the GPU until kfb_icp_step publishes
+ * that iteration's pose in mapped host memory and posting its 27 sums back; the host solves 6x6 between
+ * steps exactly as with kfb_icp_accumulate.  kfb_icp_end retires any iterations not stepped (tracking
+ * failure). */
 int kfb_icp_begin(kfb_ctx *ctx, const int iters_per_level[KFB_MAX_LEVELS]);
 int kfb_icp_step(kfb_ctx *ctx, const float pose12[12], double out27[27]);
 int kfb_icp_end(kfb_ctx *ctx);
@@ -179,10 +180,6 @@ uint64_t kfb_launch_count(const kfb_ctx *ctx);
  * 1 prev vmap L0 (float4), 2 prev nmap L0 (float4), 3 cur depth L0 (float), 4 raycast event keys (float) */
 void *kfb_device_ptr(kfb_ctx *ctx, int which);
 void *kfb_stream(kfb_ctx *ctx);
-/* debug: ring of the last 32 ICP launches (row = sequence number % 32), %globaltimer (ns) at the phase
- * boundaries of the reducing block: entry, accumulate done, elected last, final sums ready, sums
- * posted, flag posted, next pose fetched from the host gate (0 if none), sequence number */
-void kfb_debug_icp_stamps(kfb_ctx *ctx, uint64_t out256[256]);
 
 #ifdef __cplusplus
 }

@@ -10,6 +10,29 @@ using namespace kfb;
 
 static thread_local std::string g_create_err;
 
+namespace kfb
+{
+int join_front(kfb_ctx *ctx)
+{
+    if (ctx->front_pending)
+    {
+        KFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_front, 0));
+        ctx->front_pending = 0;
+    }
+    return KFB_OK;
+}
+int fork_front(kfb_ctx *ctx)
+{
+    KFB_CUDA(ctx, cudaStreamWaitEvent(ctx->fstream, ctx->ev_free, 0));
+    return KFB_OK;
+}
+int mark_free(kfb_ctx *ctx)
+{
+    KFB_CUDA(ctx, cudaEventRecord(ctx->ev_free, ctx->stream));
+    return KFB_OK;
+}
+} // namespace kfb
+
 extern "C" {
 
 void kfb_level_intrinsics(const kfb_intrinsics *in, int level, kfb_intrinsics *out)
@@ -79,6 +102,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->hit_t = nullptr; ctx->icp_partials = nullptr; ctx->icp_ticket = nullptr; ctx->counters = nullptr;
     ctx->counters_host = nullptr; ctx->pinned_depth = nullptr; ctx->render_dev = nullptr; ctx->render_host = nullptr;
     ctx->stream = nullptr; ctx->own_stream = 1;
+    ctx->fstream = nullptr; ctx->ev_front = nullptr; ctx->ev_free = nullptr; ctx->front_pending = 0;
     ctx->icp_host = nullptr; ctx->icp_gate_host = nullptr; ctx->icp_devgate = nullptr;
     memset(ctx->L, 0, sizeof(ctx->L));
     memset(ctx->events, 0, sizeof(ctx->events));
@@ -88,8 +112,13 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
         cudaDeviceProp prop;
         KFB_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
         if (prop.major < 10) { ctx->err = "kfb200 needs an sm_100a device (compute capability 10.x)"; return KFB_ERR_CUDA; }
+        ctx->sm_count = prop.multiProcessorCount;
     }
     KFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    KFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->fstream, cudaStreamNonBlocking));
+    KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_front, cudaEventDisableTiming));
+    KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_free, cudaEventDisableTiming));
+    KFB_CUDA(ctx, cudaEventRecord(ctx->ev_free, ctx->stream));
     for (int l = 0; l < ctx->levels; ++l)
     {
         kfb_intrinsics kl;
@@ -169,7 +198,11 @@ void kfb_destroy(kfb_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->fstream) cudaStreamSynchronize(ctx->fstream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev_front) cudaEventDestroy(ctx->ev_front);
+    if (ctx->ev_free) cudaEventDestroy(ctx->ev_free);
+    if (ctx->fstream) cudaStreamDestroy(ctx->fstream);
     for (int l = 0; l < KFB_MAX_LEVELS; ++l)
     {
         Level &L = ctx->L[l];
@@ -207,8 +240,12 @@ void kfb_destroy(kfb_ctx *ctx)
 
 const char *kfb_last_error_string(const kfb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+#define KFB_JOIN(ctx) do { const int _rc = join_front(ctx); if (_rc) return _rc; } while (0)
+
 int kfb_synchronize(kfb_ctx *ctx)
 {
+    KFB_JOIN(ctx);
+    KFB_CUDA(ctx, cudaStreamSynchronize(ctx->fstream));
     KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KFB_OK;
 }
@@ -216,17 +253,20 @@ int kfb_synchronize(kfb_ctx *ctx)
 int kfb_set_stream(kfb_ctx *ctx, void *stream)
 {
     if (ctx->icp_sched.active) { ctx->err = "kfb_set_stream inside an ICP schedule"; return KFB_ERR_INVALID; }
+    KFB_CUDA(ctx, cudaStreamSynchronize(ctx->fstream));
+    ctx->front_pending = 0;
     KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)stream;
     ctx->own_stream = 0;
-    return KFB_OK;
+    return mark_free(ctx);
 }
 
 int kfb_reset_volume(kfb_ctx *ctx) { return launch_reset_volume(ctx); }
 
 int kfb_reset_frames(kfb_ctx *ctx)
 {
+    KFB_JOIN(ctx);
     for (int l = 0; l < ctx->levels; ++l)
     {
         Level &L = ctx->L[l];
@@ -239,7 +279,7 @@ int kfb_reset_frames(kfb_ctx *ctx)
             KFB_CUDA(ctx, cudaMemsetAsync(L.n[f], 0, n * sizeof(float4), ctx->stream));
         }
     }
-    return KFB_OK;
+    return mark_free(ctx);
 }
 
 int kfb_upload_depth_mm(kfb_ctx *ctx, const float *host, int width, int height)
@@ -255,11 +295,15 @@ int kfb_upload_depth_mm(kfb_ctx *ctx, const float *host, int width, int height)
     else cudaGetLastError();
     if (!direct)
     {
-        KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); // staging buffer may still be in flight
+        KFB_CUDA(ctx, cudaStreamSynchronize(ctx->fstream)); // staging buffer may still be in flight
         memcpy(ctx->pinned_depth, host, bytes);
         host = ctx->pinned_depth;
     }
-    KFB_CUDA(ctx, cudaMemcpyAsync(ctx->L[0].raw, host, bytes, cudaMemcpyDefault, ctx->stream));
+    const int rc = fork_front(ctx);
+    if (rc) return rc;
+    KFB_CUDA(ctx, cudaMemcpyAsync(ctx->L[0].raw, host, bytes, cudaMemcpyDefault, ctx->fstream));
+    KFB_CUDA(ctx, cudaEventRecord(ctx->ev_front, ctx->fstream));
+    ctx->front_pending = 1;
     return KFB_OK;
 }
 
@@ -267,6 +311,7 @@ int kfb_frontend(kfb_ctx *ctx) { return launch_frontend(ctx); }
 
 int kfb_swap_frames(kfb_ctx *ctx)
 {
+    KFB_JOIN(ctx);
     const int t = ctx->cur; ctx->cur = ctx->prev; ctx->prev = t;
     return KFB_OK;
 }
@@ -274,6 +319,7 @@ int kfb_swap_frames(kfb_ctx *ctx)
 int kfb_icp_accumulate(kfb_ctx *ctx, int level, const float pose12[12], double out27[27])
 {
     if (!pose12 || !out27) return KFB_ERR_INVALID;
+    KFB_JOIN(ctx);
     return launch_icp(ctx, level, pose12, out27);
 }
 
@@ -285,6 +331,7 @@ int kfb_icp_begin(kfb_ctx *ctx, const int iters_per_level[KFB_MAX_LEVELS])
 int kfb_icp_step(kfb_ctx *ctx, const float pose12[12], double out27[27])
 {
     if (!pose12 || !out27) return KFB_ERR_INVALID;
+    KFB_JOIN(ctx);
     return icp_step(ctx, pose12, out27);
 }
 int kfb_icp_end(kfb_ctx *ctx) { return icp_end(ctx); }
@@ -292,6 +339,7 @@ int kfb_icp_end(kfb_ctx *ctx) { return icp_end(ctx); }
 int kfb_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_updated)
 {
     if (!vol2cam12) return KFB_ERR_INVALID;
+    KFB_JOIN(ctx);
     return launch_integrate(ctx, vol2cam12, n_updated);
 }
 
@@ -336,6 +384,7 @@ static int check_level(kfb_ctx *ctx, int level)
 
 int kfb_download_depth(kfb_ctx *ctx, int level, float *host)
 {
+    KFB_JOIN(ctx);
     if (check_level(ctx, level)) return KFB_ERR_INVALID;
     const Level &L = ctx->L[level];
     KFB_CUDA(ctx, cudaMemcpyAsync(host, L.depth, (size_t)L.k.w * L.k.h * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -344,6 +393,7 @@ int kfb_download_depth(kfb_ctx *ctx, int level, float *host)
 }
 int kfb_download_raw_depth(kfb_ctx *ctx, int level, float *host)
 {
+    KFB_JOIN(ctx);
     if (check_level(ctx, level)) return KFB_ERR_INVALID;
     const Level &L = ctx->L[level];
     KFB_CUDA(ctx, cudaMemcpyAsync(host, L.raw, (size_t)L.k.w * L.k.h * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -352,6 +402,7 @@ int kfb_download_raw_depth(kfb_ctx *ctx, int level, float *host)
 }
 int kfb_upload_depth_m(kfb_ctx *ctx, int level, const float *host)
 {
+    KFB_JOIN(ctx);
     if (check_level(ctx, level)) return KFB_ERR_INVALID;
     const Level &L = ctx->L[level];
     KFB_CUDA(ctx, cudaMemcpyAsync(L.depth, host, (size_t)L.k.w * L.k.h * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
@@ -360,6 +411,7 @@ int kfb_upload_depth_m(kfb_ctx *ctx, int level, const float *host)
 }
 int kfb_download_maps(kfb_ctx *ctx, int frame, int level, float *host_v3, float *host_n3)
 {
+    KFB_JOIN(ctx);
     if (check_level(ctx, level)) return KFB_ERR_INVALID;
     const Level &L = ctx->L[level];
     const int f = frame == KFB_FRAME_CUR ? ctx->cur : ctx->prev;
@@ -381,6 +433,7 @@ int kfb_download_maps(kfb_ctx *ctx, int frame, int level, float *host_v3, float 
 }
 int kfb_upload_maps(kfb_ctx *ctx, int frame, int level, const float *host_v3, const float *host_n3)
 {
+    KFB_JOIN(ctx);
     if (check_level(ctx, level)) return KFB_ERR_INVALID;
     const Level &L = ctx->L[level];
     const int f = frame == KFB_FRAME_CUR ? ctx->cur : ctx->prev;
@@ -419,6 +472,7 @@ size_t kfb_volume_voxels(const kfb_ctx *ctx) { return ctx->vol_voxels; }
 // ---- measurement ------------------------------------------------------------------------------------
 int kfb_event_record(kfb_ctx *ctx, int slot)
 {
+    KFB_JOIN(ctx);
     if (slot < 0 || slot >= 64) return KFB_ERR_INVALID;
     KFB_CUDA(ctx, cudaEventRecord(ctx->events[slot], ctx->stream));
     return KFB_OK;
@@ -445,9 +499,5 @@ void *kfb_device_ptr(kfb_ctx *ctx, int which)
     }
 }
 void *kfb_stream(kfb_ctx *ctx) { return (void *)ctx->stream; }
-void kfb_debug_icp_stamps(kfb_ctx *ctx, uint64_t out256[256])
-{
-    for (int i = 0; i < 256; ++i) out256[i] = ctx->icp_host->stamps[i / 8][i % 8];
-}
 
 } // extern "C"

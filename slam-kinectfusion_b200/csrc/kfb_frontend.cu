@@ -223,12 +223,14 @@ int launch_map_convert_in(kfb_ctx *ctx, const float *src3, float4 *dst, size_t n
 
 int launch_frontend(kfb_ctx *ctx)
 {
+    int rcf = fork_front(ctx);
+    if (rcf) return rcf;
     const int L = ctx->levels;
     for (int l = 1; l < L; ++l)
     {
         const Intr &s = ctx->L[l - 1].k, &d = ctx->L[l].k;
         dim3 b(32, 8), g((d.w + 31) / 32, (d.h + 7) / 8);
-        pyrdown_kernel<<<g, b, 0, ctx->stream>>>(ctx->L[l - 1].raw, s.w, s.h, ctx->L[l].raw, d.w, d.h);
+        pyrdown_kernel<<<g, b, 0, ctx->fstream>>>(ctx->L[l - 1].raw, s.w, s.h, ctx->L[l].raw, d.w, d.h);
         KFB_LAUNCH_CHECK(ctx);
     }
     FrontArgs a;
@@ -253,10 +255,12 @@ int launch_frontend(kfb_ctx *ctx)
     a.max_dist = ctx->p.dfilter_dist;
     const Intr &k0 = ctx->L[0].k;
     dim3 b(FT_W, FT_H), g((k0.w + FT_W - 1) / FT_W, (k0.h + FT_H - 1) / FT_H, L);
-    bilateral_kernel<<<g, b, 0, ctx->stream>>>(a);
+    bilateral_kernel<<<g, b, 0, ctx->fstream>>>(a);
     KFB_LAUNCH_CHECK(ctx);
-    vertex_normal_kernel<<<g, b, 0, ctx->stream>>>(a);
+    vertex_normal_kernel<<<g, b, 0, ctx->fstream>>>(a);
     KFB_LAUNCH_CHECK(ctx);
+    KFB_CUDA(ctx, cudaEventRecord(ctx->ev_front, ctx->fstream));
+    ctx->front_pending = 1;
     return KFB_OK;
 }
 

@@ -32,34 +32,44 @@ struct IcpArgs
     unsigned int *ticket;
     IcpHostResult *out;         // mapped host memory
     unsigned long long seq;
-    const IcpHostGate *gate;    // mapped host memory: pose published by the host (gated schedule)
-    IcpDevGate *devgate;        // device memory: pose handed from one gated launch to the next
-    int poll_next;              // this launch's tail fetches the next pose from the host gate
 };
 
 #define ICP_THREADS 256
 
-// findCoresp (rigid_icp.cu:46-80) + row (rigid_icp.cu:85-95)
-__device__ __forceinline__ bool icp_row(const IcpArgs &a, int x, int y, float row[7])
+// findCoresp (rigid_icp.cu:46-80) + row (rigid_icp.cu:85-95), split so that the loads of several pixels can
+// be in flight together: (1) current vertex/normal -> transformed point s and the model pixel it projects to,
+// (2) the two model-map gathers, (3) gates + row.
+struct IcpProbe
 {
+    float sx, sy, sz;
+    float4 nc4;
+    int j; // model pixel, -1 = no correspondence
+};
+__device__ __forceinline__ void icp_probe(const IcpArgs &a, int p, int npix, IcpProbe &o)
+{
+    o.j = -1;
+    if (p >= npix) return;
+    const int y = p / a.cov_w, x = p - y * a.cov_w;
     const int i = y * a.k.w + x;
-    const float4 nc4 = __ldg(a.cur_n + i);
-    if (isnan(nc4.x)) return false;
+    o.nc4 = __ldg(a.cur_n + i);
     const float4 vc4 = __ldg(a.cur_v + i);
+    if (isnan(o.nc4.x)) return;
     const float3 r = rot3(a.pose.R, vc4.x, vc4.y, vc4.z);
-    const float sx = __fadd_rn(r.x, a.pose.t[0]), sy = __fadd_rn(r.y, a.pose.t[1]), sz = __fadd_rn(r.z, a.pose.t[2]);
+    o.sx = __fadd_rn(r.x, a.pose.t[0]); o.sy = __fadd_rn(r.y, a.pose.t[1]); o.sz = __fadd_rn(r.z, a.pose.t[2]);
     // Intrs::proj (device_utils.cuh:15-21)
-    const float qx = __fdividef(sx, sz), qy = __fdividef(sy, sz);
+    const float qx = __fdividef(o.sx, o.sz), qy = __fdividef(o.sy, o.sz);
     const int px = __float2int_rn(__fmaf_rn(qx, a.k.fx, a.k.cx));
     const int py = __float2int_rn(__fmaf_rn(qy, a.k.fy, a.k.cy));
-    if (!(sz > 0.f && px >= 0 && py >= 0 && px < a.k.w && py < a.k.h)) return false;
-    const int j = py * a.k.w + px;
-    const float4 vp = __ldg(a.pre_v + j);
+    if (!(o.sz > 0.f && px >= 0 && py >= 0 && px < a.k.w && py < a.k.h)) return;
+    o.j = py * a.k.w + px;
+}
+__device__ __forceinline__ bool icp_row(const IcpArgs &a, const IcpProbe &o, const float4 vp, const float4 np, float row[7])
+{
+    const float sx = o.sx, sy = o.sy, sz = o.sz;
     const float dx = __fsub_rn(sx, vp.x), dy = __fsub_rn(sy, vp.y), dz = __fsub_rn(sz, vp.z);
     const float dist = __fsqrt_rn(dot3c(dx, dy, dz, dx, dy, dz));
     if (!(dist <= a.dist_thres)) return false;
-    const float3 nc = rot3(a.pose.R, nc4.x, nc4.y, nc4.z);
-    const float4 np = __ldg(a.pre_n + j);
+    const float3 nc = rot3(a.pose.R, o.nc4.x, o.nc4.y, o.nc4.z);
     const float cx = __fmaf_rn(nc.y, np.z, -__fmul_rn(nc.z, np.y));
     const float cy = __fmaf_rn(nc.z, np.x, -__fmul_rn(nc.x, np.z));
     const float cz = __fmaf_rn(nc.x, np.y, -__fmul_rn(nc.y, np.x));
@@ -93,66 +103,128 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     return t;
 }
 
-// GATED launches were enqueued ahead of time (kfb_icp_begin/step): their pose is not a launch
-// parameter but sits in device memory (IcpDevGate), put there by the tail of the previous launch.
-// That tail -- ONE thread of the last block, after it has posted the 27 sums -- polls the host's
-// mapped gate for the next pose (or an abort), so exactly one PCIe reader exists at any time and
-// the launch latency of iteration k+1 overlaps iteration k and the host's 6x6 solve.  The poll is
-// bounded (KFB_ICP_GATE_TIMEOUT_NS); on timeout or abort the device gate is invalidated and every
-// later gated launch returns at once.
-template <bool GATED>
-__global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpArgs a0)
+// ---- shared pieces ------------------------------------------------------------------------------------
+struct IcpLevel
 {
-    IcpArgs a = a0;
-    if (GATED)
+    const float4 *cur_v, *cur_n, *pre_v, *pre_n;
+    Intr k;
+    int cov_w, cov_h;
+};
+
+#define ICP_BATCH 4
+__device__ __forceinline__ void icp_accumulate_pixels(const IcpArgs &a, double acc[27], int first, int stride)
+{
+    const int npix = a.cov_w * a.cov_h;
+    for (int p0 = first; p0 < npix; p0 += ICP_BATCH * stride)
     {
-        if (a.devgate->seq != a.seq) return; // uniform: written before this launch started
+        IcpProbe pr[ICP_BATCH];
+        float4 vp[ICP_BATCH], np[ICP_BATCH];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) a.pose.R.m[i] = a.devgate->pose[4 * (i / 3) + (i % 3)];
+        for (int b = 0; b < ICP_BATCH; ++b) icp_probe(a, p0 + b * stride, npix, pr[b]);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) a.pose.t[i] = a.devgate->pose[4 * i + 3];
+        for (int b = 0; b < ICP_BATCH; ++b)
+        {
+            const int j = max(pr[b].j, 0);
+            vp[b] = __ldg(a.pre_v + j);
+            np[b] = __ldg(a.pre_n + j);
+        }
+        // pixels are accumulated in increasing p within a thread: the order is fixed => reproducible sums
+#pragma unroll
+        for (int b = 0; b < ICP_BATCH; ++b)
+        {
+            float row[7];
+            if (pr[b].j >= 0 && icp_row(a, pr[b], vp[b], np[b], row))
+            {
+                int s = 0;
+#pragma unroll
+                for (int i = 0; i < 6; ++i)
+#pragma unroll
+                    for (int j = i; j < 7; ++j) acc[s++] += (double)__fmul_rn(row[i], row[j]);
+            }
+        }
     }
-    const unsigned long long ts0 = globaltimer_ns();
+}
+// warp reduction by transposition (lane l ends up owning value l: 31 exchanges instead of 27 five-step trees),
+// then one shared stage; threads 0..26 end up with the block's sums (valid for threadIdx.x < 27)
+__device__ __forceinline__ double icp_block_reduce(double acc[27], double (*sm)[27])
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = i < 27 ? acc[i] : 0.0;
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1)
+    {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i)
+        {
+            const double send = up ? v[i] : v[i + half];
+            const double keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    if (lane < 27) sm[warp][lane] = v[0];
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x < 27)
+    {
+#pragma unroll
+        for (int w = 0; w < ICP_THREADS / 32; ++w) s += sm[w][threadIdx.x];
+    }
+    return s;
+}
+// last block: fixed-order sum of the per-block partials.  Thread t owns value v = t & 31 over the block
+// slice {t >> 5, t >> 5 + 8, ...}: all loads of a thread are independent (one L2 round trip), the summation
+// order is a fixed function of the grid size => bit-reproducible.  Lanes 0..26 of warp 0 return the totals.
+__device__ __forceinline__ double icp_final_reduce(const double *partials, int nb, double (*red)[28])
+{
+    const int v = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (v < 27)
+    {
+        const int stride = ICP_THREADS / 32;
+        int bb = slice;
+        for (; bb + 3 * stride < nb; bb += 4 * stride)
+        {
+            const double p0 = __ldcg(partials + (size_t)bb * 27 + v);
+            const double p1 = __ldcg(partials + (size_t)(bb + stride) * 27 + v);
+            const double p2 = __ldcg(partials + (size_t)(bb + 2 * stride) * 27 + v);
+            const double p3 = __ldcg(partials + (size_t)(bb + 3 * stride) * 27 + v);
+            s0 += p0; s1 += p1; s2 += p2; s3 += p3;
+        }
+        for (; bb < nb; bb += stride) s0 += __ldcg(partials + (size_t)bb * 27 + v);
+        red[slice][v] = (s0 + s1) + (s2 + s3);
+    }
+    __syncthreads();
+    double fin = 0.0;
+    if (threadIdx.x < 27)
+    {
+#pragma unroll
+        for (int w = 0; w < ICP_THREADS / 32; ++w) fin += red[w][threadIdx.x];
+    }
+    return fin;
+}
+// result chunk i = {sum_i, tag}: one aligned 16-byte store per lane, the tag (sequence number) travels with
+// the value, so the host needs no separate flag and the device no system fence
+__device__ __forceinline__ void icp_post(IcpHostResult *out, int i, double v, unsigned long long seq)
+{
+    asm volatile("st.volatile.global.v2.b64 [%0], {%1, %2};" ::"l"(&out->chunk[i]), "l"(__double_as_longlong(v)), "l"(seq) : "memory");
+}
+
+// one accumulation, pose by parameter (kfb_icp_accumulate)
+__global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpArgs a)
+{
     double acc[27];
 #pragma unroll
     for (int i = 0; i < 27; ++i) acc[i] = 0.0;
-
-    const int npix = a.cov_w * a.cov_h;
-    for (int p = blockIdx.x * ICP_THREADS + threadIdx.x; p < npix; p += gridDim.x * ICP_THREADS)
-    {
-        const int y = p / a.cov_w, x = p - y * a.cov_w;
-        float row[7];
-        if (icp_row(a, x, y, row))
-        {
-            int s = 0;
-#pragma unroll
-            for (int i = 0; i < 6; ++i)
-#pragma unroll
-                for (int j = i; j < 7; ++j) acc[s++] += (double)__fmul_rn(row[i], row[j]);
-        }
-    }
-    const unsigned long long ts1 = globaltimer_ns();
-    // warp tree
-#pragma unroll
-    for (int i = 0; i < 27; ++i)
-    {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_down_sync(0xffffffffu, acc[i], o);
-    }
+    icp_accumulate_pixels(a, acc, blockIdx.x * ICP_THREADS + threadIdx.x, gridDim.x * ICP_THREADS);
     __shared__ double sm[ICP_THREADS / 32][27];
+    __shared__ double red[ICP_THREADS / 32][28];
     __shared__ bool is_last;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0)
-    {
-#pragma unroll
-        for (int i = 0; i < 27; ++i) sm[warp][i] = acc[i];
-    }
-    __syncthreads();
+    const double s = icp_block_reduce(acc, sm);
     if (threadIdx.x < 27)
     {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < ICP_THREADS / 32; ++w) s += sm[w][threadIdx.x];
         a.partials[(size_t)blockIdx.x * 27 + threadIdx.x] = s;
         __threadfence();
     }
@@ -164,88 +236,134 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpArgs a0)
     }
     __syncthreads();
     if (!is_last) return;
-    const unsigned long long ts2 = globaltimer_ns();
     __threadfence();
-    // last block: fixed-order sum of the per-block partials.  Thread t owns value v = t & 31 over the
-    // block slice {t >> 5, t >> 5 + 8, ...}: all loads of a thread are independent (one L2 round trip),
-    // the summation order is a fixed function of the grid size => bit-reproducible.
+    const double fin = icp_final_reduce(a.partials, (int)gridDim.x, red);
+    if (threadIdx.x < 27) icp_post(a.out, threadIdx.x, fin, a.seq);
+}
+
+// ---- the whole coarse-to-fine loop in ONE persistent kernel ----------------------------------------------
+// kfb_icp_begin/step/end: the grid (one CTA per SM, all co-resident) runs every iteration of the
+// schedule.  Per iteration: all CTAs accumulate their pixels and publish a partial; the last CTA to arrive
+// (ticket) reduces, posts the 27 tagged sums to mapped host memory, then ONE thread polls the host's mapped
+// gate for the next pose (or an abort) -- exactly one PCIe reader -- and releases the other CTAs through a
+// device-memory gate they spin on.  No kernel boundary, no launch and no system fence sits between the host's
+// 6x6 solve and the next accumulation.  The poll is bounded (KFB_ICP_GATE_TIMEOUT_NS): on timeout or abort
+// every CTA leaves.
+struct IcpPersistArgs
+{
+    IcpLevel lv[KFB_MAX_LEVELS];
+    int iters[KFB_MAX_LEVELS];
+    int levels, total;
+    float dist_thres, sine_thres;
+    double *partials;
+    unsigned int *ticket;
+    IcpHostResult *out;
+    const IcpHostGate *gate;
+    IcpDevGate *devgate;
+    unsigned long long seq0;   // iteration k carries sequence number seq0 + k + 1
+    float pose0[12];
+};
+
+__global__ void __launch_bounds__(ICP_THREADS) icp_persistent_kernel(const IcpPersistArgs P)
+{
+    __shared__ double sm[ICP_THREADS / 32][27];
     __shared__ double red[ICP_THREADS / 32][28];
-    {
-        const int v = threadIdx.x & 31, slice = threadIdx.x >> 5;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        if (v < 27)
-        {
-            const int nb = (int)gridDim.x, stride = ICP_THREADS / 32;
-            int bb = slice;
-            for (; bb + 3 * stride < nb; bb += 4 * stride)
-            {
-                const double p0 = __ldcg(a.partials + (size_t)bb * 27 + v);
-                const double p1 = __ldcg(a.partials + (size_t)(bb + stride) * 27 + v);
-                const double p2 = __ldcg(a.partials + (size_t)(bb + 2 * stride) * 27 + v);
-                const double p3 = __ldcg(a.partials + (size_t)(bb + 3 * stride) * 27 + v);
-                s0 += p0; s1 += p1; s2 += p2; s3 += p3;
-            }
-            for (; bb < nb; bb += stride) s0 += __ldcg(a.partials + (size_t)bb * 27 + v);
-            red[slice][v] = (s0 + s1) + (s2 + s3);
-        }
-    }
+    __shared__ bool is_last;
+    __shared__ int go;          // 1: pose valid, 0: leave
+    __shared__ float spose[12];
+    IcpArgs a;
+    a.dist_thres = P.dist_thres; a.sine_thres = P.sine_thres;
+    if (threadIdx.x < 12) spose[threadIdx.x] = P.pose0[threadIdx.x];
     __syncthreads();
-    const unsigned long long ts3 = globaltimer_ns();
-    // one thread posts the 27 sums to mapped host memory, one system fence, then the flag
-    if (warp == 0)
+    int k = 0;
+    for (int level = P.levels - 1; level >= 0; --level)
     {
-        double fin = 0.0;
-        if (lane < 27)
+        const IcpLevel &L = P.lv[level];
+        a.cur_v = L.cur_v; a.cur_n = L.cur_n; a.pre_v = L.pre_v; a.pre_n = L.pre_n;
+        a.k = L.k; a.cov_w = L.cov_w; a.cov_h = L.cov_h;
+        for (int it = 0; it < P.iters[level]; ++it, ++k)
         {
+            const unsigned long long seq = P.seq0 + (unsigned long long)k + 1ull;
 #pragma unroll
-            for (int w = 0; w < ICP_THREADS / 32; ++w) fin += red[w][lane];
-        }
+            for (int i = 0; i < 9; ++i) a.pose.R.m[i] = spose[4 * (i / 3) + (i % 3)];
 #pragma unroll
-        for (int i = 0; i < 27; ++i)
-        {
-            const double v = __shfl_sync(0xffffffffu, fin, i);
-            if (lane == 0) a.out->sums[i] = v;
-        }
-        if (lane == 0)
-        {
-            const unsigned long long ts4 = globaltimer_ns();
-            __threadfence_system();
-            a.out->seq = a.seq;
-            const unsigned long long ts5 = globaltimer_ns();
-            volatile unsigned long long *st = a.out->stamps[a.seq & 31];
-            st[0] = ts0; st[1] = ts1; st[2] = ts2; st[3] = ts3; st[4] = ts4; st[5] = ts5; st[6] = 0; st[7] = a.seq;
-            if (a.poll_next)
+            for (int i = 0; i < 3; ++i) a.pose.t[i] = spose[4 * i + 3];
+            double acc[27];
+#pragma unroll
+            for (int i = 0; i < 27; ++i) acc[i] = 0.0;
+            icp_accumulate_pixels(a, acc, blockIdx.x * ICP_THREADS + threadIdx.x, gridDim.x * ICP_THREADS);
+            const double s = icp_block_reduce(acc, sm);
+            if (threadIdx.x < 27)
             {
-                // Gate: four 16-byte chunks {3 pose floats, tag}; the host rewrites each chunk with one
-                // aligned 16-byte store and the tag is the low 32 bits of the sequence number, so a chunk is
-                // either wholly old or wholly new and one poll (4 loads in flight) yields a consistent pose.
-                const unsigned long long want = a.seq + 1ull;
-                const unsigned int tag = (unsigned int)want;
+                P.partials[(size_t)blockIdx.x * 27 + threadIdx.x] = s;
+                __threadfence();
+            }
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                const unsigned int t = atomicInc(P.ticket, gridDim.x - 1);
+                is_last = (t == gridDim.x - 1);
+            }
+            __syncthreads();
+            const bool last_iter = (k + 1 == P.total);
+            if (is_last)
+            {
+                __threadfence();
+                const double fin = icp_final_reduce(P.partials, (int)gridDim.x, red);
+                if (threadIdx.x < 27) icp_post(P.out, threadIdx.x, fin, seq);
+                if (threadIdx.x == 0 && !last_iter)
+                {
+                    // Gate: four 16-byte chunks {3 pose floats, tag}; the host rewrites each chunk with one
+                    // aligned 16-byte store and the tag is the low 32 bits of the sequence number, so a chunk is
+                    // either wholly old or wholly new and one poll (4 loads in flight) yields a consistent pose.
+                    const unsigned long long want = seq + 1ull;
+                    const unsigned int tag = (unsigned int)want;
+                    const unsigned long long t0 = globaltimer_ns();
+                    bool ok = false;
+                    float4 c0, c1, c2, c3;
+                    for (;;)
+                    {
+                        c0 = ld_volatile_f4(P.gate->chunk);
+                        c1 = ld_volatile_f4(P.gate->chunk + 4);
+                        c2 = ld_volatile_f4(P.gate->chunk + 8);
+                        c3 = ld_volatile_f4(P.gate->chunk + 12);
+                        const unsigned long long ab = ld_volatile_u64(&P.gate->abort_upto);
+                        if (ab >= want) break;
+                        if (__float_as_uint(c0.w) == tag && __float_as_uint(c1.w) == tag && __float_as_uint(c2.w) == tag &&
+                            __float_as_uint(c3.w) == tag) { ok = true; break; }
+                        if (globaltimer_ns() - t0 > KFB_ICP_GATE_TIMEOUT_NS) break;
+                    }
+                    float *d = P.devgate->pose; // chunk r = {R[r][0..2]}, chunk 3 = t
+                    if (ok)
+                    {
+                        d[0] = c0.x; d[1] = c0.y; d[2] = c0.z; d[3] = c3.x;
+                        d[4] = c1.x; d[5] = c1.y; d[6] = c1.z; d[7] = c3.y;
+                        d[8] = c2.x; d[9] = c2.y; d[10] = c2.z; d[11] = c3.z;
+                    }
+                    __threadfence();
+                    // release: seq = want (go) or want | 1<<63 (leave)
+                    *(volatile unsigned long long *)&P.devgate->seq = ok ? want : (want | (1ull << 63));
+                }
+            }
+            if (last_iter) return;
+            // every CTA (the last one included) picks the next pose up from the device gate
+            if (threadIdx.x == 0)
+            {
+                const unsigned long long want = seq + 1ull;
+                unsigned long long v;
                 const unsigned long long t0 = globaltimer_ns();
-                bool ok = false;
-                float4 c0, c1, c2, c3;
                 for (;;)
                 {
-                    c0 = ld_volatile_f4(a.gate->chunk);
-                    c1 = ld_volatile_f4(a.gate->chunk + 4);
-                    c2 = ld_volatile_f4(a.gate->chunk + 8);
-                    c3 = ld_volatile_f4(a.gate->chunk + 12);
-                    const unsigned long long ab = ld_volatile_u64(&a.gate->abort_upto);
-                    if (ab >= want) break;
-                    if (__float_as_uint(c0.w) == tag && __float_as_uint(c1.w) == tag && __float_as_uint(c2.w) == tag &&
-                        __float_as_uint(c3.w) == tag) { ok = true; break; }
-                    if (globaltimer_ns() - t0 > KFB_ICP_GATE_TIMEOUT_NS) break;
+                    v = ld_volatile_u64(&P.devgate->seq);
+                    if ((v & ~(1ull << 63)) == want) break;
+                    if (globaltimer_ns() - t0 > 2ull * KFB_ICP_GATE_TIMEOUT_NS) { v = 1ull << 63; break; }
                 }
-                if (ok)
-                {
-                    float *d = a.devgate->pose; // chunk r = {R[r][0..2]}, chunk 3 = t
-                    d[0] = c0.x; d[1] = c0.y; d[2] = c0.z; d[3] = c3.x;
-                    d[4] = c1.x; d[5] = c1.y; d[6] = c1.z; d[7] = c3.y;
-                    d[8] = c2.x; d[9] = c2.y; d[10] = c2.z; d[11] = c3.z;
-                }
-                a.devgate->seq = ok ? want : 0ull;
-                st[6] = globaltimer_ns();
+                go = (v >> 63) ? 0 : 1;
             }
+            __syncthreads();
+            if (!go) return;
+            if (threadIdx.x < 12) spose[threadIdx.x] = __ldcg(P.devgate->pose + threadIdx.x);
+            __syncthreads();
         }
     }
 }
@@ -264,36 +382,40 @@ static int icp_setup(kfb_ctx *ctx, int level, IcpArgs &a, int &blocks)
     a.partials = ctx->icp_partials;
     a.ticket = ctx->icp_ticket;
     a.out = ctx->icp_dev;
-    a.gate = ctx->icp_gate_dev;
-    a.devgate = ctx->icp_devgate;
-    a.poll_next = 0;
-    const int npix = a.cov_w * a.cov_h;
-    // latency-bound at the coarse levels: one pixel per thread until the grid covers 2 CTAs/SM
-    blocks = (npix + ICP_THREADS - 1) / ICP_THREADS;
-    if (blocks > 296) blocks = 296;
+    // one CTA per SM at every level (two were measured slower: the ticket / final stage grows), for the direct and the persistent kernel alike: the pixel -> thread
+    // mapping and hence the summation order is a function of the SM count only => identical bits
+    blocks = a.cov_w * a.cov_h > 0 ? ctx->sm_count : 0;
     return KFB_OK;
 }
 
-// spin on the mapped result flag (with a stream query as the failure detector)
+// spin on the tagged result chunks in mapped host memory (with a stream query as the failure detector)
 static int icp_wait(kfb_ctx *ctx, unsigned long long seq, double out27[27])
 {
-    IcpHostResult *h = ctx->icp_host;
+    volatile IcpHostResult *h = ctx->icp_host;
     unsigned long spins = 0;
-    while (h->seq != seq)
+    for (;;)
     {
+        int ready = 0;
+        for (int i = 0; i < 27; ++i) ready += (h->chunk[i].tag == seq);
+        if (ready == 27) break;
         if ((++spins & 0xfffff) == 0)
         {
             cudaError_t q = cudaStreamQuery(ctx->stream);
             if (q != cudaSuccess && q != cudaErrorNotReady) KFB_CUDA(ctx, q);
-            if (q == cudaSuccess && h->seq != seq)
+            if (q == cudaSuccess)
             {
                 KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                if (h->seq != seq) { ctx->err = "icp result flag never arrived"; return KFB_ERR_CUDA; }
+                ready = 0;
+                for (int i = 0; i < 27; ++i) ready += (h->chunk[i].tag == seq);
+                if (ready == 27) break;
+                ctx->err = "icp result never arrived (gate timeout or abort)";
+                return KFB_ERR_CUDA;
             }
         }
     }
     __sync_synchronize();
-    for (int i = 0; i < 27; ++i) out27[i] = h->sums[i];
+    // a chunk is written by one aligned 16-byte store, so value and tag arrive together
+    for (int i = 0; i < 27; ++i) out27[i] = h->chunk[i].value;
     return KFB_OK;
 }
 
@@ -310,43 +432,12 @@ int launch_icp(kfb_ctx *ctx, int level, const float pose12[12], double out27[27]
         for (int i = 0; i < 27; ++i) out27[i] = 0.0;
         return KFB_OK;
     }
-    icp_kernel<false><<<blocks, ICP_THREADS, 0, ctx->stream>>>(a);
+    icp_kernel<<<blocks, ICP_THREADS, 0, ctx->stream>>>(a);
     KFB_LAUNCH_CHECK(ctx);
     return icp_wait(ctx, a.seq, out27);
 }
 
-// ---- gated, pre-enqueued schedule ---------------------------------------------------------------------
-// Launch k of the schedule carries sequence number seq0 + k + 1.  Launch 0 takes its pose as a
-// parameter (it is launched by the first kfb_icp_step); every launch but the last polls the host gate
-// for its successor's pose in its tail.
-static int icp_enqueue_next(kfb_ctx *ctx, const float *pose12_first)
-{
-    IcpSchedule &S = ctx->icp_sched;
-    if (S.enq >= S.total) return KFB_OK;
-    int k = S.enq, level = ctx->levels - 1; // flat index -> (level, iteration), coarse to fine
-    while (level >= 0 && k >= S.iters[level]) { k -= S.iters[level]; --level; }
-    IcpArgs a;
-    int blocks = 0;
-    const int rc = icp_setup(ctx, level, a, blocks);
-    if (rc) return rc;
-    if (blocks <= 0) { ctx->err = "icp level has no pixels to visit"; return KFB_ERR_INVALID; }
-    a.seq = S.seq0 + (unsigned long long)S.enq + 1ull;
-    a.poll_next = (S.enq + 1 < S.total) ? 1 : 0;
-    if (pose12_first)
-    {
-        a.pose = make_pose(pose12_first);
-        icp_kernel<false><<<blocks, ICP_THREADS, 0, ctx->stream>>>(a);
-    }
-    else
-    {
-        a.pose = make_pose(S.identity);
-        icp_kernel<true><<<blocks, ICP_THREADS, 0, ctx->stream>>>(a);
-    }
-    KFB_LAUNCH_CHECK(ctx);
-    ++S.enq;
-    return KFB_OK;
-}
-
+// ---- persistent schedule -------------------------------------------------------------------------------
 int icp_begin(kfb_ctx *ctx, const int *iters_per_level)
 {
     IcpSchedule &S = ctx->icp_sched;
@@ -358,10 +449,46 @@ int icp_begin(kfb_ctx *ctx, const int *iters_per_level)
         if (S.iters[l] < 0) S.iters[l] = 0;
         S.total += S.iters[l];
     }
-    for (int i = 0; i < 12; ++i) S.identity[i] = (i % 5 == 0) ? 1.f : 0.f;
     S.seq0 = ctx->icp_seq;
     S.enq = S.done = 0;
     S.active = 1;
+    return KFB_OK;
+}
+
+static int icp_launch_persistent(kfb_ctx *ctx, const float pose12[12])
+{
+    IcpSchedule &S = ctx->icp_sched;
+    IcpPersistArgs P;
+    memset(&P, 0, sizeof(P));
+    int max_pix = 0;
+    for (int l = 0; l < ctx->levels; ++l)
+    {
+        IcpArgs a;
+        int blocks = 0;
+        const int rc = icp_setup(ctx, l, a, blocks);
+        if (rc) return rc;
+        if (S.iters[l] > 0 && a.cov_w * a.cov_h <= 0) { ctx->err = "icp level has no pixels to visit"; return KFB_ERR_INVALID; }
+        P.lv[l].cur_v = a.cur_v; P.lv[l].cur_n = a.cur_n; P.lv[l].pre_v = a.pre_v; P.lv[l].pre_n = a.pre_n;
+        P.lv[l].k = a.k; P.lv[l].cov_w = a.cov_w; P.lv[l].cov_h = a.cov_h;
+        P.iters[l] = S.iters[l];
+        P.dist_thres = a.dist_thres; P.sine_thres = a.sine_thres;
+        if (S.iters[l] > 0 && a.cov_w * a.cov_h > max_pix) max_pix = a.cov_w * a.cov_h;
+    }
+    P.levels = ctx->levels;
+    P.total = S.total;
+    P.partials = ctx->icp_partials;
+    P.ticket = ctx->icp_ticket;
+    P.out = ctx->icp_dev;
+    P.gate = ctx->icp_gate_dev;
+    P.devgate = ctx->icp_devgate;
+    P.seq0 = S.seq0;
+    memcpy(P.pose0, pose12, sizeof(P.pose0));
+    // every CTA must be resident at once (they wait on each other): one per SM (see icp_setup)
+    const int blocks = ctx->sm_count;
+    (void)max_pix;
+    icp_persistent_kernel<<<blocks, ICP_THREADS, 0, ctx->stream>>>(P);
+    KFB_LAUNCH_CHECK(ctx);
+    S.enq = S.total;
     return KFB_OK;
 }
 
@@ -373,15 +500,13 @@ int icp_step(kfb_ctx *ctx, const float pose12[12], double out27[27])
     int rc;
     if (S.done == 0)
     {
-        rc = icp_enqueue_next(ctx, pose12); // head of the chain: pose by parameter
+        rc = icp_launch_persistent(ctx, pose12); // first pose by parameter
         if (rc) return rc;
-        for (int d = 0; d < KFB_ICP_LOOKAHEAD; ++d)
-            if ((rc = icp_enqueue_next(ctx, nullptr)) != KFB_OK) return rc;
     }
     else
     {
-        // publish this iteration's pose: payload first, then the flag (x86 TSO + compiler barriers);
-        // the tail of the previous launch is polling for it
+        // publish this iteration's pose: four tagged 16-byte chunks (x86 TSO keeps each store whole);
+        // the last CTA of the previous iteration is polling for it
         IcpHostGate *g = ctx->icp_gate_host;
         const unsigned int tag = (unsigned int)seq;
         float tagf;
@@ -395,7 +520,6 @@ int icp_step(kfb_ctx *ctx, const float pose12[12], double out27[27])
         _mm_store_ps((float *)g->chunk + 8, k2);
         _mm_store_ps((float *)g->chunk + 12, k3);
         _mm_sfence();
-        if ((rc = icp_enqueue_next(ctx, nullptr)) != KFB_OK) return rc; // keep the queue KFB_ICP_LOOKAHEAD deep
     }
     rc = icp_wait(ctx, seq, out27);
     if (rc) return rc;
@@ -408,16 +532,16 @@ int icp_end(kfb_ctx *ctx)
 {
     IcpSchedule &S = ctx->icp_sched;
     if (!S.active) return KFB_OK;
-    // launches enqueued but never fed a pose (early exit / tracking failure) retire through the abort
-    // gate: the polling tail invalidates the device gate and the rest return at once
-    const unsigned long long last = S.seq0 + (unsigned long long)S.enq;
-    if (S.done < S.enq)
+    // iterations never fed a pose (early exit / tracking failure) retire through the abort gate: the polling
+    // thread releases every CTA with the leave bit
+    const unsigned long long last = S.seq0 + (unsigned long long)S.total;
+    if (S.enq > 0 && S.done < S.total)
     {
         volatile IcpHostGate *g = ctx->icp_gate_host;
         g->abort_upto = last;
         __sync_synchronize();
     }
-    ctx->icp_seq = last > ctx->icp_seq ? last : ctx->icp_seq;
+    if (S.enq > 0) ctx->icp_seq = last > ctx->icp_seq ? last : ctx->icp_seq;
     S.active = 0;
     return KFB_OK;
 }

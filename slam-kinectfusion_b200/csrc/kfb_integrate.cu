@@ -529,6 +529,8 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
         build_tables_kernel<<<g, b, 0, ctx->stream>>>(ctx->L[0].depth, k.w, k.h, k.fx, k.fy, k.cx, k.cy,
                                                      ctx->p.volu_trun_dist, ctx->tab_thrz, ctx->tab_exact, ctx->zexit);
         KFB_LAUNCH_CHECK(ctx);
+        const int rcm = mark_free(ctx); // the filtered depth has been consumed: the next front end may overwrite it
+        if (rcm) return rcm;
     }
     IntegrateArgs a;
     a.vol = ctx->vol;
@@ -561,7 +563,7 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
     // interval differs per column).  KFB_INTEGRATE_ZCHUNKS overrides for tuning.
     const long cols = ((long)(a.X + 127) / 128) * ((a.Y + 3) / 4);
     int zc = 1;
-    while (cols * zc < 148L * 12 && zc < 16 && planes / (zc * 2) >= 32) zc *= 2;
+    while (cols * zc < 148L * 24 && zc < 16 && planes / (zc * 2) >= 32) zc *= 2;
     if (const char *e = getenv("KFB_INTEGRATE_ZCHUNKS")) zc = atoi(e) > 0 ? atoi(e) : zc;
     a.zchunk = (planes + zc - 1) / zc;
     dim3 block(32, 4), grid((a.X + 127) / 128, (a.Y + 3) / 4, zc);

@@ -21,21 +21,3 @@ for l in (2, 1, 0):
     for _ in range(50): ctx.icp_accumulate(l, I)
     print("direct level", l, (time.perf_counter() - t0) / 50 * 1e6, "us")
 
-import time
-# gated chain through the C++ facade-equivalent loop: phases per iteration
-from slam_kinectfusion_b200 import host as H
-for trial in range(2):
-    pose = I.copy()
-    ctx.icp_begin(iters)
-    for k in range(19):
-        s27 = ctx.icp_step(pose)
-    ctx.icp_end(); ctx.synchronize(); time.sleep(0.01)
-st = ctx.debug_icp_stamps().astype(np.int64)
-order = np.argsort(st[:, 7])[-19:]
-S = st[order]
-print("seq", S[:, 7] - S[0, 7])
-print("kernel phases ns (acc, red+ticket, final, post, fence+flag):")
-print(np.median(S[:, 1:6] - S[:, 0:5], axis=0))
-print("flag posted -> next pose fetched (host turnaround seen by GPU) ns:", (S[:-1, 6] - S[:-1, 5]))
-print("pose fetched -> next kernel's reducing block entry ns:", (S[1:, 0] - S[:-1, 6]))
-print("iteration period ns:", np.diff(S[:, 5]))
