@@ -105,35 +105,84 @@ def oracle_frames_per_s(dims, frames, threads):
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's implementation of the path on this box.  The reference is
-    CUDA-only and needs OpenCV-CUDA for its host pipeline, which does not exist here, so this arm is
-    the scalar/OpenMP oracle port on the host cores (kind "port"); the reference's own kernels rebuilt
-    for sm_100a (oracle/_ref) are timed per stage in profiles/ and tests/test_ref_ab.py."""
+    """`--impl reference`: the reference's implementation of the path on this box, none of this repo's kernels
+    on it.  The reference is CUDA-only, so when its kernels were compiled here (oracle/_ref/libkf_ref.so: the
+    three .cu files of the reference, unmodified, for sm_100a) and a GPU is present, this arm runs the
+    reference's own frame loop over ITS kernels on the same B200 (oracle/ref_harness.cu: its 8-byte voxel, its
+    per-iteration cudaMalloc/memcpy in rigidICP, its cudaDeviceSynchronize; the two un-vendored OpenCV-CUDA
+    calls are stood in for by plain kernels in the harness) -- kind "reference".  Otherwise it is the
+    scalar/OpenMP oracle port on the host cores -- kind "port".  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from slam_kinectfusion_b200 import synth
     import slam_kinectfusion_b200 as kfb
-    dims = WEAK_DIMS.get(args.gpus, 512) if args.dims is None else args.dims
-    if args.gpus > 1:
-        dims = 512   # the port times the per-GPU share of the weak-scaled job: one 512^3-voxel frame
+    dims = 512 if args.dims is None else args.dims      # N > 1: the per-GPU share of the weak-scaled job
     cores = os.cpu_count() or 1
     K = kfb.Intrinsics(**kfb.SENSORS["kinect1"])
-    n = 1 + args.warmup + args.steps
-    n = min(n, 1 + 2 + 6)         # bounded sample: ~1.5 s per 512^3 frame on 16 cores
-    frames = synth.sequence(n, K)
-    t0 = time.perf_counter()
-    value, sec_per_frame, U = oracle_frames_per_s(dims, frames, cores)
+    W, S = args.warmup, args.steps
+    t_start = time.perf_counter()
+    from oracle import kref, kfo
+    gpu = False
+    if kref.available():
+        try:
+            import torch
+            gpu = torch.cuda.is_available()
+        except Exception:
+            gpu = False
+    workload = f"640x480 depth, {dims}^3 TSDF over 3 m, ICP 10/5/4, synthetic box+sphere room trajectory"
+    if gpu:
+        import torch
+        S = min(S, 100)
+        n = 1 + W + S
+        frames = synth.sequence(n, K)
+        pin = torch.empty((n, K.height, K.width), dtype=torch.float32).pin_memory()
+        for i, (_, d) in enumerate(frames):
+            pin[i].copy_(torch.from_numpy(d))
+        volpose = np.array(kfo.default_params(dims).volu_pose, np.float32)
+        rk = kref.RefKinfu(K, dims, volpose)
+        for i in range(n):
+            if i == 1 + W:
+                kref.lib().ref_device_sync()
+                kref.event_tic()
+                t0 = time.perf_counter()
+            if rk.pipeline_ptr(pin[i].data_ptr()) != 0:
+                raise SystemExit(f"reference pipeline lost tracking at frame {i}")
+        ms = kref.event_toc_ms()
+        wall = time.perf_counter() - t0
+        ms_per_frame = max(ms, wall * 1e3) / S
+        # updated voxels per frame: a property of the workload (frames + poses); counted by the oracle on a sample
+        Ko = kfo.intr()
+        vd = kfo.volume_desc(dims)
+        U = []
+        for i in (1 + W, n - 1):
+            vol = kfo.new_volume(vd)
+            dm = kfo.frontend(frames[i][1], Ko, levels=1)[0][0]
+            U.append(kfo.integrate(vol, vd, kfo.pose_mul(kfo.pose_inv(frames[i][0]), volpose), dm, Ko))
+            del vol
+        U_mean = float(np.mean(U))
+        value = U_mean / (ms_per_frame * 1e-3)
+        kind, ncores = "reference", 1
+        sample = (f"{S} frames after {W} warm-up frames: the reference's own CUDA kernels (oracle/_ref, sm_100a rebuild) "
+                  f"driven by its frame loop on this GPU, host frames in pinned memory, 1 host thread; {ms_per_frame:.3f} ms/frame")
+        steps = S
+    else:
+        n = min(1 + W + S, 1 + 2 + 6)         # bounded sample: ~0.35 s per 512^3 frame on 16 cores
+        frames = synth.sequence(n, K)
+        value, sec_per_frame, U_mean = oracle_frames_per_s(dims, frames, cores)
+        ms_per_frame = sec_per_frame * 1e3
+        kind, ncores = "port", cores
+        sample = f"{n - 1} frames after the bootstrap frame, whole pipeline (oracle/kf_oracle.c), OpenMP over {cores} threads"
+        steps, W = n - 1, 0
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": n - 1, "warmup": 0, "ms_per_step": sec_per_frame * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": W, "ms_per_step": ms_per_frame, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32 -> int16 tsdf", "data": "synthetic",
-        "config": {"workload": f"640x480 depth, {dims}^3 TSDF over 3 m, ICP 10/5/4, synthetic box+sphere room trajectory",
-                   "l2": "inputs larger than L2 (volume swept every frame)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n - 1} frames after the bootstrap frame, whole pipeline, OpenMP over {cores} threads"},
+        "config": {"workload": workload, "l2": "inputs larger than L2 (volume swept every frame)",
+                   "updated_voxels_per_frame": U_mean},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_start,
     }
     print(json.dumps(line))
 

@@ -544,11 +544,15 @@ typedef struct
     int X, Y, Z;
     size_t plane;
     float vsinv[3], gd[3];
+    int zs0, zs1; /* stored planes [zs0, zs1): vol points at plane zs0 (z-slab shards) */
+    int zo0, zo1; /* owned planes */
 } rc_ctx;
 
 static inline float vox_tsdf(const rc_ctx *c, int x, int y, int z)
 {
-    return (float)c->vol[2 * ((size_t)x + (size_t)y * c->X + (size_t)z * c->plane)] * KFO_DIVSHORTMAX;
+    if (z < c->zs0) z = c->zs0;
+    if (z >= c->zs1) z = c->zs1 - 1;
+    return (float)c->vol[2 * ((size_t)x + (size_t)y * c->X + (size_t)(z - c->zs0) * c->plane)] * KFO_DIVSHORTMAX;
 }
 /* tsdf_volume.cu:178-191 */
 static inline float voxel2tsdf(const rc_ctx *c, float px, float py, float pz)
@@ -557,6 +561,18 @@ static inline float voxel2tsdf(const rc_ctx *c, float px, float py, float pz)
     const int y = f2i_rn(py * c->vsinv[1]);
     const int z = f2i_rn(pz * c->vsinv[2]);
     if (x >= c->X - 1 || y >= c->Y - 1 || z >= c->Z - 1 || x < 1 || y < 1 || z < 1) return NAN;
+    return vox_tsdf(c, x, y, z);
+}
+/* slab variant: NaN outside the stored planes; *own = the sample's voxel plane is owned by the slab */
+static inline float voxel2tsdf_slab(const rc_ctx *c, float px, float py, float pz, int *own)
+{
+    const int x = f2i_rn(px * c->vsinv[0]);
+    const int y = f2i_rn(py * c->vsinv[1]);
+    const int z = f2i_rn(pz * c->vsinv[2]);
+    *own = 0;
+    if (x >= c->X - 1 || y >= c->Y - 1 || z >= c->Z - 1 || x < 1 || y < 1 || z < 1) return NAN;
+    if (z < c->zs0 || z >= c->zs1) return NAN;
+    *own = z >= c->zo0 && z < c->zo1;
     return vox_tsdf(c, x, y, z);
 }
 /* tsdf_volume.cu:137-161 */
@@ -578,11 +594,20 @@ static inline float interpolate(const rc_ctx *c, float fx, float fy, float fz)
     return t;
 }
 
+/* Slab semantics (test model of kfb_raycast on a z-slab context + kfb_composite_mask): `vol` holds planes
+ * [zs0, zs1) only; a sample outside them is NaN; a (cur, next) pair is evaluated only if next's voxel plane
+ * is in [zo0, zo1); key[pixel] = ray_len of the first terminal event (hit or back-face stop), +inf if none.
+ * With zs = [0, Z) and zo = [0, Z) this is the reference's raycast. */
+void kfo_raycast_slab(const int16_t *vol, const kfo_volume_desc *vd, const float cam2vol[12], const float rinv9[9],
+                      const kfo_intr *k, float *vmap3, float *nmap3, float *key, int zs0, int zs1, int zo0, int zo1,
+                      int compat_ts_sign);
+
 void kfo_raycast(const int16_t *vol, const kfo_volume_desc *vd, const float cam2vol[12], const float rinv9[9],
                  const kfo_intr *k, float *vmap3, float *nmap3, int64_t *n_steps, int compat_ts_sign)
 {
     rc_ctx c;
     c.vol = vol;
+    c.zs0 = 0; c.zs1 = vd->dims[2]; c.zo0 = 0; c.zo1 = vd->dims[2];
     c.X = vd->dims[0]; c.Y = vd->dims[1]; c.Z = vd->dims[2];
     c.plane = (size_t)c.X * c.Y;
     for (int i = 0; i < 3; ++i) { c.vsinv[i] = 1.f / vd->voxel_size[i]; c.gd[i] = vd->voxel_size[i] * 0.5f; }
@@ -658,6 +683,88 @@ void kfo_raycast(const int16_t *vol, const kfo_volume_desc *vd, const float cam2
             }
         }
     if (n_steps) *n_steps = steps;
+}
+
+void kfo_raycast_slab(const int16_t *vol, const kfo_volume_desc *vd, const float cam2vol[12], const float rinv9[9],
+                      const kfo_intr *k, float *vmap3, float *nmap3, float *key, int zs0, int zs1, int zo0, int zo1,
+                      int compat_ts_sign)
+{
+    rc_ctx c;
+    c.vol = vol;
+    c.zs0 = zs0; c.zs1 = zs1; c.zo0 = zo0; c.zo1 = zo1;
+    c.X = vd->dims[0]; c.Y = vd->dims[1]; c.Z = vd->dims[2];
+    c.plane = (size_t)c.X * c.Y;
+    for (int i = 0; i < 3; ++i) { c.vsinv[i] = 1.f / vd->voxel_size[i]; c.gd[i] = vd->voxel_size[i] * 0.5f; }
+    const float step_len = vd->voxel_size[0];
+    float R[9];
+    pose_R9(cam2vol, R);
+    const float ox = cam2vol[3], oy = cam2vol[7], oz = cam2vol[11];
+    const int w = k->width, h = k->height;
+    const float rfx = KFO_RCP(k->fx), rfy = KFO_RCP(k->fy);
+    const float rgx = KFO_RCP(c.gd[0]), rgy = KFO_RCP(c.gd[1]), rgz = KFO_RCP(c.gd[2]);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+        {
+            float *vo = vmap3 + 3 * ((size_t)y * w + x);
+            float *no = nmap3 + 3 * ((size_t)y * w + x);
+            vo[0] = vo[1] = vo[2] = no[0] = no[1] = no[2] = 0.f;
+            key[(size_t)y * w + x] = INFINITY;
+            const float px = rfx * ((float)x - k->cx), py = rfy * ((float)y - k->cy);
+            float dx = fmaf(px, R[0], py * R[1]) + R[2];
+            float dy = fmaf(px, R[3], py * R[4]) + R[5];
+            float dz = fmaf(px, R[6], py * R[7]) + R[8];
+            {
+                const float rt = KFO_RCP(sqrtf(dot3c(dx, dy, dz, dx, dy, dz)));
+                dx = rt * dx; dy = rt * dy; dz = rt * dz;
+            }
+            const float ix = 1.f / dx, iy = 1.f / dy, iz = 1.f / dz;
+            const float bx = ix * (0.f - ox), by = iy * (0.f - oy), bz = iz * (0.f - oz);
+            const float tx_ = ix * (vd->range[0] - ox), ty_ = iy * (vd->range[1] - oy), tz_ = iz * (vd->range[2] - oz);
+            const float mnx = fminf(tx_, bx), mny = fminf(ty_, by), mnz = fminf(tz_, bz);
+            const float mxx = fmaxf(tx_, bx), mxy = fmaxf(ty_, by), mxz = fmaxf(tz_, bz);
+            const float tnear = fmaxf(fmaxf(mnx, mny), fmaxf(mnx, mnz));
+            const float tfar = fminf(fminf(mxx, mxy), fminf(mxx, mxz));
+            float ray_len = fmaxf(tnear, 0.f);
+            if (ray_len >= tfar) continue;
+            ray_len += step_len;
+            float nx_ = fmaf(dx, ray_len, ox), ny_ = fmaf(dy, ray_len, oy), nz_ = fmaf(dz, ray_len, oz);
+            int own;
+            float tnext = voxel2tsdf_slab(&c, nx_, ny_, nz_, &own);
+            for (; ray_len < tfar; ray_len += step_len)
+            {
+                nx_ = fmaf(dx, vd->voxel_size[0], nx_);
+                ny_ = fmaf(dy, vd->voxel_size[1], ny_);
+                nz_ = fmaf(dz, vd->voxel_size[2], nz_);
+                const float tcur = tnext;
+                tnext = voxel2tsdf_slab(&c, nx_, ny_, nz_, &own);
+                if (isnan(tnext) || !own) continue;
+                if (tcur < 0.f && tnext > 0.f) { key[(size_t)y * w + x] = ray_len; break; }
+                if (tcur > 0.f && tnext < 0.f)
+                {
+                    const float q = KFO_RCP(tcur - tnext);
+                    const float num = tcur * vd->voxel_size[0];
+                    const float Ts = compat_ts_sign ? fmaf(q, -num, ray_len) : fmaf(q, num, ray_len);
+                    const float vx = fmaf(dx, Ts, ox), vy = fmaf(dy, Ts, oy), vz = fmaf(dz, Ts, oz);
+                    const float Fx1 = interpolate(&c, (vx + c.gd[0]) * c.vsinv[0], vy * c.vsinv[1], vz * c.vsinv[2]);
+                    const float Fx2 = interpolate(&c, (vx - c.gd[0]) * c.vsinv[0], vy * c.vsinv[1], vz * c.vsinv[2]);
+                    const float Fy1 = interpolate(&c, vx * c.vsinv[0], (vy + c.gd[1]) * c.vsinv[1], vz * c.vsinv[2]);
+                    const float Fy2 = interpolate(&c, vx * c.vsinv[0], (vy - c.gd[1]) * c.vsinv[1], vz * c.vsinv[2]);
+                    const float Fz1 = interpolate(&c, vx * c.vsinv[0], vy * c.vsinv[1], (vz + c.gd[2]) * c.vsinv[2]);
+                    const float Fz2 = interpolate(&c, vx * c.vsinv[0], vy * c.vsinv[1], (vz - c.gd[2]) * c.vsinv[2]);
+                    float gx = rgx * (Fx1 - Fx2), gy = rgy * (Fy1 - Fy2), gz = rgz * (Fz1 - Fz2);
+                    const float rn = KFO_RCP(sqrtf(dot3c(gx, gy, gz, gx, gy, gz)));
+                    gx = rn * gx; gy = rn * gy; gz = rn * gz;
+                    if (!isnan((gx * gy) * gz))
+                    {
+                        rot3(rinv9, gx, gy, gz, no);
+                        rot3(rinv9, vx - ox, vy - oy, vz - oz, vo);
+                        key[(size_t)y * w + x] = ray_len;
+                        break;
+                    }
+                }
+            }
+        }
 }
 
 /* ======================================================================

@@ -84,6 +84,10 @@ void kfo_integrate(int16_t *vol, const kfo_volume_desc *vd, const float vol2cam[
                    const float *depth_m, const kfo_intr *k, int z_begin, int z_end, int64_t *n_updated);
 void kfo_raycast(const int16_t *vol, const kfo_volume_desc *vd, const float cam2vol[12], const float rinv9[9],
                  const kfo_intr *k, float *vmap3, float *nmap3, int64_t *n_steps, int compat_ts_sign);
+/* z-slab variant (test model of the sharded raycast): see kf_oracle.c */
+void kfo_raycast_slab(const int16_t *vol, const kfo_volume_desc *vd, const float cam2vol[12], const float rinv9[9],
+                      const kfo_intr *k, float *vmap3, float *nmap3, float *key, int zs0, int zs1, int zo0, int zo1,
+                      int compat_ts_sign);
 /* Point-cloud extraction (tsdf_volume.cu:307-481); returns the number of points written (<= cap). */
 int64_t kfo_extract_points(const int16_t *vol, const kfo_volume_desc *vd, const float volpose[12],
                            float *points3, int64_t cap);

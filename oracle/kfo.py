@@ -79,6 +79,7 @@ def lib():
         "kfo_rodrigues": (None, [_fp, _fp]),
         "kfo_integrate": (None, [_sp, VP, _fp, _fp, IP, C.c_int, C.c_int, _i64p]),
         "kfo_raycast": (None, [_sp, VP, _fp, _fp, IP, _fp, _fp, _i64p, C.c_int]),
+        "kfo_raycast_slab": (None, [_sp, VP, _fp, _fp, IP, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
         "kfo_extract_points": (C.c_int64, [_sp, VP, _fp, _fp, C.c_int64]),
         "kfo_render_phong": (None, [_fp, _fp, C.c_int, C.c_int, _fp, _bp]),
         "kfo_render_normals": (None, [_fp, C.c_int, C.c_int, _bp]),
@@ -274,6 +275,16 @@ def raycast(vol, vd, cam2vol, K, compat_ts_sign=1):
     lib().kfo_raycast(vol.reshape(-1), C.byref(vd), np.ascontiguousarray(cam2vol, np.float32), rot_inv(cam2vol),
                       C.byref(K), v, n, C.byref(steps), compat_ts_sign)
     return v, n, steps.value
+
+
+def raycast_slab(vol_slab, vd, cam2vol, K, zs0, zs1, zo0, zo1, compat_ts_sign=1):
+    """vol_slab holds planes [zs0, zs1) of the volume; returns (vmap, nmap, key)."""
+    v = np.empty((K.height, K.width, 3), np.float32)
+    n = np.empty((K.height, K.width, 3), np.float32)
+    key = np.empty((K.height, K.width), np.float32)
+    lib().kfo_raycast_slab(np.ascontiguousarray(vol_slab).reshape(-1), C.byref(vd), np.ascontiguousarray(cam2vol, np.float32),
+                           rot_inv(cam2vol), C.byref(K), v, n, key, zs0, zs1, zo0, zo1, compat_ts_sign)
+    return v, n, key
 
 
 def extract_points(vol, vd, volpose, cap=10_000_000):

@@ -38,6 +38,15 @@ def lib():
         L.ref_rigid_icp.restype = C.c_float
         L.ref_rigid_icp.argtypes = [_vp] * 4 + [C.c_int, C.c_int] + [C.c_float] * 4 + [_vp, C.c_float, C.c_float, _vp, _vp, C.c_int]
         L.ref_last_cuda_error.restype = C.c_int
+        L.ref_kinfu_create.restype = _vp
+        L.ref_kinfu_create.argtypes = [C.c_int, C.c_int] + [C.c_float] * 4 + [C.c_int, C.c_float, _vp]
+        L.ref_kinfu_destroy.argtypes = [_vp]
+        L.ref_kinfu_reset.argtypes = [_vp]
+        L.ref_kinfu_get_pose.argtypes = [_vp, _vp]
+        L.ref_kinfu_pipeline.restype = C.c_int
+        L.ref_kinfu_pipeline.argtypes = [_vp, _vp]
+        L.ref_event_ms.restype = C.c_float
+        L.ref_event_ms.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -90,6 +99,44 @@ class RefVolume:
         pts = np.empty((cap, 3), np.float32)
         n = lib().ref_extract_points(self.h, _p(p), _p(pts), cap)
         return pts[:n].copy()
+
+
+class RefKinfu:
+    """The reference's whole frame loop over its own kernels (ref_harness.cu: ref_kinfu_*)."""
+
+    def __init__(self, K, dims, volpose12, rng=3.0):
+        vp = _f(volpose12)
+        self.h = lib().ref_kinfu_create(K.width, K.height, K.fx, K.fy, K.cx, K.cy, int(dims), float(rng), _p(vp))
+        if not self.h:
+            raise RuntimeError("reference pipeline allocation failed")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ref_kinfu_destroy(self.h)
+            self.h = None
+
+    def reset(self):
+        lib().ref_kinfu_reset(self.h)
+
+    def pipeline_ptr(self, ptr):
+        return lib().ref_kinfu_pipeline(self.h, _vp(int(ptr)))
+
+    def pipeline(self, depth_mm):
+        d = _f(depth_mm)
+        return lib().ref_kinfu_pipeline(self.h, _p(d))
+
+    def pose(self):
+        p = np.empty(12, np.float32)
+        lib().ref_kinfu_get_pose(self.h, _p(p))
+        return p
+
+
+def event_tic():
+    lib().ref_event_ms(0)
+
+
+def event_toc_ms():
+    return lib().ref_event_ms(1)
 
 
 def depth_truncation(depth_mm_filtered, max_dist=5.0):

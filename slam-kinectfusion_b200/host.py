@@ -10,6 +10,8 @@ from .binding import Intrinsics, KfbError, KFB_MAX_LEVELS, load_library, Context
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 _vp = C.c_void_p
+BCAST_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_float), C.c_void_p)
+COMPOSITE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
 
 class HostParams(C.Structure):
@@ -19,7 +21,8 @@ class HostParams(C.Structure):
                 ("icp_iter_count", C.c_int * KFB_MAX_LEVELS), ("volu_dims", C.c_int * 3),
                 ("volu_range", C.c_float * 3), ("volu_pose", C.c_float * 12), ("volu_trun_dist", C.c_float),
                 ("tsdf_max_weight", C.c_int), ("compat_icp_rows", C.c_int), ("compat_raycast_ts_sign", C.c_int),
-                ("device", C.c_int)]
+                ("device", C.c_int), ("slab_z_begin", C.c_int), ("slab_z_end", C.c_int), ("shard_rank", C.c_int),
+                ("shard_world", C.c_int)]
 
 
 def host_library_path():
@@ -50,6 +53,7 @@ def load_host_library():
         "kfh_extract_pointcloud": (C.c_long, [_vp, _vp, C.c_long]),
         "kfh_save_pointcloud": (C.c_int, [_vp, C.c_char_p]),
         "kfh_icp_solve": (C.c_int, [_vp, _vp]),
+        "kfh_set_shard_comm": (None, [_vp, BCAST_FN, COMPOSITE_FN, _vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -114,6 +118,14 @@ class KinectFusion:
     def pipeline_ptr(self, ptr, w, h):
         return self.lib.kfh_pipeline(self.h, ptr, w, h)
 
+    def last_error(self):
+        return self.lib.kfh_last_error().decode()
+
+    def set_shard_comm(self, broadcast_pose, composite):
+        """broadcast_pose(msg13: ctypes float*) -> int, composite() -> int (kf::ShardComm)."""
+        self._cb = (BCAST_FN(lambda p, u: int(broadcast_pose(p))), COMPOSITE_FN(lambda u: int(composite())))
+        self.lib.kfh_set_shard_comm(self.h, self._cb[0], self._cb[1], None)
+
     def reset(self):
         self.lib.kfh_reset(self.h)
 
@@ -137,6 +149,7 @@ class KinectFusion:
             p.volu_dims[i] = self.params.volu_dims[i]
             p.volu_range[i] = self.params.volu_range[i]
         p.pyramid_height = self.params.pyramid_height
+        p.slab_z_begin, p.slab_z_end = self.params.slab_z_begin, self.params.slab_z_end
         return _BorrowedContext(self.lib.kfh_context(self.h), self.intr, p)
 
     def render(self, normal=False):

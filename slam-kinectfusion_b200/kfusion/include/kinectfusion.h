@@ -36,6 +36,22 @@ struct kinectfuison_params
     int compat_icp_rows = 1;
     int compat_raycast_ts_sign = 1;
     int device = 0;
+    //// z-slab sharding (volumes of 1024^3 and above): this instance stores and updates planes
+    //// [slab_z_begin, slab_z_end) (+ halo) of the volume; 0,0 = the whole volume
+    int slab_z_begin = 0, slab_z_end = 0;
+    int shard_rank = 0, shard_world = 1;
+};
+
+// Collectives a sharded instance needs, supplied by the launcher (one process per GPU; the bench harness
+// implements them with torch.distributed / NCCL on the context's stream).  Both return 0 on success.
+struct ShardComm
+{
+    // msg13 = {tracking_ok, pose12 of the new global camera pose}: valid on rank 0 on entry, on every rank on return
+    int (*broadcast_pose)(float *msg13, void *user) = nullptr;
+    // cross-slab raycast composite after kfb_raycast: all-reduce MIN of the event keys, kfb_composite_mask,
+    // integer SUM reduction of the model maps to rank 0 (include/kfb200.h, kfb_composite_mask)
+    int (*composite)(void *user) = nullptr;
+    void *user = nullptr;
 };
 
 class kinectfusion
@@ -60,6 +76,7 @@ public:
     cv::Affine3f getCurCameraPose();
     void release();
 
+    void setShardComm(const ShardComm &c) { comm = c; }
     kfb_ctx *context() { return dev ? dev->ctx : nullptr; }
     const Frame *currentFrame() const { return &cframe; }
     const Frame *modelFrame() const { return &pframe; }
@@ -82,6 +99,7 @@ private:
     ICPRegistration icp;
     Intrinsics intr_;
     kinectfuison_params params_;
+    ShardComm comm;
     cv::Mat points_array;
 };
 } // namespace kf

@@ -19,6 +19,7 @@ struct kfh_params
     int tsdf_max_weight;
     int compat_icp_rows, compat_raycast_ts_sign;
     int device;
+    int slab_z_begin, slab_z_end, shard_rank, shard_world;
 };
 
 static thread_local std::string g_err;
@@ -44,6 +45,8 @@ void kfh_default_params(kfh_params *o, int dims)
     o->compat_icp_rows = 1;
     o->compat_raycast_ts_sign = 1;
     o->device = 0;
+    o->slab_z_begin = o->slab_z_end = 0;
+    o->shard_rank = 0; o->shard_world = 1;
 }
 
 void *kfh_create(const kfb_intrinsics *k, const kfh_params *q)
@@ -67,6 +70,8 @@ void *kfh_create(const kfb_intrinsics *k, const kfh_params *q)
         p.compat_icp_rows = q->compat_icp_rows;
         p.compat_raycast_ts_sign = q->compat_raycast_ts_sign;
         p.device = q->device;
+        p.slab_z_begin = q->slab_z_begin; p.slab_z_end = q->slab_z_end;
+        p.shard_rank = q->shard_rank; p.shard_world = q->shard_world > 0 ? q->shard_world : 1;
         return new kf::kinectfusion(intr, p);
     }
     catch (const std::exception &e)
@@ -82,8 +87,16 @@ void kfh_reset(void *h) { static_cast<kf::kinectfusion *>(h)->reset(); }
 int kfh_pipeline(void *h, const float *depth_mm, int width, int height)
 {
     kf::kinectfusion *k = static_cast<kf::kinectfusion *>(h);
-    k->pipeline(depth_mm, width, height);
+    try { k->pipeline(depth_mm, width, height); }
+    catch (const std::exception &e) { g_err = e.what(); return 2; }
     return k->last_tracking_ok ? 0 : 1;
+}
+/* collectives of a z-slab sharded instance (kf::ShardComm) */
+void kfh_set_shard_comm(void *h, int (*bcast)(float *, void *), int (*composite)(void *), void *user)
+{
+    kf::ShardComm c;
+    c.broadcast_pose = bcast; c.composite = composite; c.user = user;
+    static_cast<kf::kinectfusion *>(h)->setShardComm(c);
 }
 int kfh_frame_count(void *h) { return static_cast<kf::kinectfusion *>(h)->frame_count; }
 int kfh_num_poses(void *h) { return (int)static_cast<kf::kinectfusion *>(h)->pose_record.size(); }

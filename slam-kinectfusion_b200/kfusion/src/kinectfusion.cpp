@@ -25,6 +25,8 @@ kf::kinectfusion::kinectfusion(const kf::Intrinsics intr, const kf::kinectfuison
     p.tsdf_max_weight = params_.tsdf_max_weight;
     p.compat_icp_rows = params_.compat_icp_rows;
     p.compat_raycast_ts_sign = params_.compat_raycast_ts_sign;
+    p.slab_z_begin = params_.slab_z_begin;
+    p.slab_z_end = params_.slab_z_end;
     const kfb_intrinsics ki = intr_.abi();
     dev = std::make_shared<DeviceContext>();
     const int rc = kfb_create(&ki, &p, params_.device, &dev->ctx);
@@ -85,19 +87,31 @@ void kf::kinectfusion::pipeline(const float *depth_mm, int width, int height)
         frame_count++;
         return;
     }
-    // icp: transform of the current frame towards the previous one
-    cv::Affine3f cam_pose;
-    if (!icp.rigidTransform(cam_pose, pose_record.back(), &cframe, &pframe))
+    const bool sharded = params_.shard_world > 1;
+    if (sharded && (!comm.broadcast_pose || !comm.composite)) throw std::runtime_error("kf::kinectfusion: sharded instance without ShardComm");
+    // icp: transform of the current frame towards the previous one.  Sharded: ICP stays on rank 0 (it owns
+    // the composited model maps) and only the pose travels.
+    float msg[13] = {0.f};
+    if (params_.shard_rank == 0)
+    {
+        cv::Affine3f cam_pose;
+        const bool ok = icp.rigidTransform(cam_pose, pose_record.back(), &cframe, &pframe);
+        msg[0] = ok ? 1.f : 0.f;
+        if (ok) (pose_record.back() * cam_pose).to12(msg + 1);
+    }
+    if (sharded && comm.broadcast_pose(msg, comm.user) != 0) throw std::runtime_error("kf::kinectfusion: pose broadcast failed");
+    if (msg[0] == 0.f)
     {
         last_tracking_ok = false;
         std::cout << "tracking fail!" << std::endl;
         reset();
         return;
     }
-    pose_record.push_back((pose_record.back() * cam_pose));
+    pose_record.push_back(cv::Affine3f::from12(msg + 1));
     vdata->integrate(pose_record.back());
     vdata->raycast(pose_record.back());
-    kfbSafeCall(dev->ctx, kfb_model_pyramid(dev->ctx));
+    if (sharded && comm.composite(comm.user) != 0) throw std::runtime_error("kf::kinectfusion: raycast composite failed");
+    if (params_.shard_rank == 0) kfbSafeCall(dev->ctx, kfb_model_pyramid(dev->ctx));
     std::chrono::duration<double, std::milli> ms = std::chrono::steady_clock::now() - start_time;
     frame_time = std::to_string(ms.count());
     frame_count++;

@@ -440,3 +440,111 @@ def test_full_size_properties_512(kfo, kfb):
     assert np.median(err) < 0.0124 and np.percentile(err, 99) < 0.05   # within trunc (quirk bias <= 2 voxels); silhouettes looser
     nrm = np.linalg.norm(gn[hit], axis=1)
     assert np.abs(nrm - 1).max() < 1e-3
+
+
+# ------------------------------------------------------------------------------- z-slab sharding (§8e)
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_contexts_compose_to_single_gpu_result(kfo, kfb, world):
+    """Slab contexts (here all on one GPU) integrate only their planes (+halo) and raycast only their ray
+    segments; volumes must equal the corresponding planes of the single-context volume bit for bit, and the
+    min-key composite (kfb_composite_mask semantics) must equal the single-context raycast bit for bit."""
+    import ctypes as C
+    from slam_kinectfusion_b200 import sharded
+    dims = 128
+    Ko, Kb, Po, Pb = make_pair(kfo, kfb, dims, 320, 240)
+    volpose = np.array(Po.volu_pose, np.float32)
+    full = _ctx(kfb, Kb, Pb)
+    slabs = []
+    for r in range(world):
+        P = kfb.default_params(dims)
+        P.slab_z_begin, P.slab_z_end = sharded.slab_range(dims, world, r)
+        slabs.append(_ctx(kfb, Kb, P))
+    for k in (0, 4, 8):
+        pose = kfo.trajectory_pose(k)
+        d = kfo.render_depth_mm(pose, Ko)
+        v2c = kfo.pose_mul(kfo.pose_inv(pose), volpose)
+        for c in [full] + slabs:
+            c.upload_depth_mm(d)
+            c.frontend()
+            c.integrate(v2c)
+    fvol = full.download_volume()
+    for r, c in enumerate(slabs):
+        s0, s1 = sharded.stored_range(dims, world, r)
+        assert np.array_equal(c.download_volume(), fvol[s0:s1])
+    c2v = kfo.pose_mul(kfo.pose_inv(volpose), kfo.trajectory_pose(9))
+    rinv = kfo.rot_inv(c2v)
+    full.raycast(c2v, rinv)
+    fv, fn = full.download_maps(1, 0)
+    assert (fv[..., 2] != 0).mean() > 0.9
+    h, w = fv.shape[:2]
+    keys, maps = [], []
+    for c in slabs:
+        c.raycast(c2v, rinv)
+        maps.append(c.download_maps(1, 0))
+        k = np.empty(h * w, np.float32)
+        c.synchronize()
+        _cuda_memcpy_d2h(k, c.device_ptr(4))
+        keys.append(k.reshape(h, w))
+    keys = np.stack(keys)
+    # (a) slab raycast == oracle slab semantics on the same volume (hits up to MUFU.RCP-level ties)
+    for r, c in enumerate(slabs):
+        s0, s1 = sharded.stored_range(dims, world, r)
+        zb, ze = sharded.slab_range(dims, world, r)
+        ov, on, ok = kfo.raycast_slab(fvol[s0:s1], kfo.volume_desc(dims), c2v, Ko, s0, s1, zb, ze)
+        assert (np.isfinite(ok) != np.isfinite(keys[r])).sum() <= 8
+        both = np.isfinite(ok) & np.isfinite(keys[r]) & (ov[..., 2] != 0) & (maps[r][0][..., 2] != 0)
+        if both.any():
+            assert np.median(np.abs(maps[r][0] - ov)[both]) < 2e-6
+    # (b) composite through kfb_composite_mask + integer sum == single-context raycast, bit for bit
+    min_key = keys.min(axis=0).astype(np.float32)
+    dmin = _cuda_alloc_copy(min_key)
+    acc_v = np.zeros((h, w, 3), np.int64)
+    acc_n = np.zeros((h, w, 3), np.int64)
+    for c in slabs:
+        c.composite_mask(dmin)
+        mv, mn = c.download_maps(1, 0)
+        acc_v += mv.view(np.int32)
+        acc_n += mn.view(np.int32)
+    _cuda_free(dmin)
+    assert np.array_equal(acc_v.astype(np.int32), fv.view(np.int32))
+    assert np.array_equal(acc_n.astype(np.int32), fn.view(np.int32))
+    srt = np.sort(keys, axis=0)
+    assert not (np.isfinite(srt[0]) & (srt[0] == srt[1])).any()   # an event has exactly one owner
+
+
+def _cudart():
+    import ctypes as C
+    for name in ("libcudart.so", "libcudart.so.12"):
+        try:
+            return C.CDLL(name)
+        except OSError:
+            continue
+    import glob
+    import torch
+    cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "cuda_runtime", "lib", "libcudart.so*"))
+    return C.CDLL(cands[0])
+
+
+def _cuda_memcpy_d2h(arr, dptr):
+    import ctypes as C
+    rt = _cudart()
+    rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    assert rt.cudaMemcpy(arr.ctypes.data_as(C.c_void_p), C.c_void_p(dptr), arr.nbytes, 2) == 0
+
+
+def _cuda_alloc_copy(arr):
+    import ctypes as C
+    rt = _cudart()
+    p = C.c_void_p()
+    rt.cudaMalloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    rt.cudaMemcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    assert rt.cudaMalloc(C.byref(p), arr.nbytes) == 0
+    assert rt.cudaMemcpy(p, arr.ctypes.data_as(C.c_void_p), arr.nbytes, 1) == 0
+    return p.value
+
+
+def _cuda_free(p):
+    import ctypes as C
+    rt = _cudart()
+    rt.cudaFree.argtypes = [C.c_void_p]
+    rt.cudaFree(C.c_void_p(p))

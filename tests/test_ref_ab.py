@@ -170,3 +170,20 @@ def test_render_matches(kfo, kfb, kref):
         ours = ctx.render_phong(eye) if phong else ctx.render_normals()
         d = np.abs(ref.astype(np.int16) - ours.astype(np.int16))
         assert d.max() <= 1 and (d > 0).mean() < 0.01   # powf ulp at a truncating cast
+
+
+def test_reference_frame_loop_tracks_like_ours(kfo, kfb, kref):
+    """The `--impl reference` baseline driver (the reference's kernels under its own frame loop, oracle/
+    ref_harness.cu ref_kinfu_*) and the product see the same frames: poses must agree to the 1e-4 budget."""
+    Ko = kfo.intr()
+    Kb = kfb.Intrinsics(**kfb.SENSORS["kinect1"])
+    dims = 128
+    hp = kfb.default_host_params(dims)
+    ours = kfb.KinectFusion(Kb, hp)
+    ref = kref.RefKinfu(Kb, dims, np.array(hp.volu_pose, np.float32))
+    for k in range(6):
+        d = kfo.render_depth_mm(kfo.trajectory_pose(k), Ko)
+        assert ours.pipeline(d) == 0
+        assert ref.pipeline(d) == 0
+        assert np.abs(ours.pose() - ref.pose()).max() < 1e-4, (k, ours.pose(), ref.pose())
+        assert np.abs(ours.pose() - kfo.trajectory_pose(k)).max() < 5e-3
