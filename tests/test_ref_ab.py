@@ -186,4 +186,6 @@ def test_reference_frame_loop_tracks_like_ours(kfo, kfb, kref):
         assert ours.pipeline(d) == 0
         assert ref.pipeline(d) == 0
         assert np.abs(ours.pose() - ref.pose()).max() < 1e-4, (k, ours.pose(), ref.pose())
-        assert np.abs(ours.pose() - kfo.trajectory_pose(k)).max() < 5e-3
+        # (at 128^3 the reference algorithm itself drifts by centimetres from the ground truth: 23 mm voxels
+        # and the raycast sign quirk, SURVEY.md 9 Q17 -- both implementations drift together)
+        assert np.abs(ours.pose() - kfo.trajectory_pose(k)).max() < 0.1
