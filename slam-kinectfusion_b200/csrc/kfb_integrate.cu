@@ -62,6 +62,7 @@ struct IntegrateArgs
     const float4 *wtab;
     const float *zexit;
     int max_weight;
+    int use_jump, jump_min; // exact jump of the running sum for prefixes of at least jump_min planes
     uint8_t *bricks;
     int *bdirty;         // set when a brick flag flips 0 -> 1 (the distance map must be rebuilt)
     int bx, by, bz, bz0; // brick grid dims (x, y, stored z bricks) and first stored z brick
@@ -181,6 +182,93 @@ __global__ void build_wtab_kernel(float4 *__restrict__ wtab, int max_weight)
     if (wt > max_weight) return;
     const int wp1 = wt + 1;
     wtab[wt] = make_float4((float)wt, rcp_fdividef((float)wp1), __uint_as_float((unsigned)min(wp1, max_weight) << 16), 0.f);
+}
+
+// ---- exact jump of the reference's running sum ---------------------------------------------------------
+// v_{k+1} = RN(v_k + c) with c = a*b exact (fma).  While v stays inside one binade [2^e, 2^(e+1)) its ulp u is
+// constant and v = M*u with an integer mantissa M, so RN(v + c) = (M + RN(c/u))*u unless c/u lies exactly half
+// way between two integers (then tie-to-even depends on M's parity; the code falls back to single steps).
+// Hence n steps inside a binade are one integer multiply-add on M, exactly.  Everything is integer arithmetic
+// (FP64 is slow on this part): c = +-Mc * 2^ec with the 48-bit product of the two mantissas, c/u is a shift of
+// Mc.  The four voxels of a thread share c and nearly always share binade and sign, so the per-step increment
+// is derived once; steps that could leave the binade, and anything irregular (zero, subnormal, huge ratios,
+// ties), are taken as real fma steps.  Bit-identical to n sequential fmas
+// (tests/test_gpu_parity.py::test_integrate_jump_equals_replay).
+__device__ __noinline__ void jump4(float v[4], float a, float b, int n)
+{
+    const unsigned ab = __float_as_uint(a), bb = __float_as_uint(b);
+    const int ea = (int)((ab >> 23) & 0xff), eb = (int)((bb >> 23) & 0xff);
+    const bool c_ok = ea > 0 && ea < 255 && eb > 0 && eb < 255;                       // both normal
+    const unsigned long long Mc = (unsigned long long)((ab & 0x7fffffu) | 0x800000u) * (unsigned long long)((bb & 0x7fffffu) | 0x800000u);
+    const unsigned sc = (ab ^ bb) >> 31;                                               // sign of c
+    if ((ab << 1) == 0u || (bb << 1) == 0u)
+    {
+        // c == +-0: RN(v + c) == v for every step (a -0.0 becomes +0.0 on the first one, as in the reference)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __fmaf_rn(a, b, v[k]);
+        return;
+    }
+    while (n > 0)
+    {
+        const unsigned v0 = __float_as_uint(v[0]);
+        const int e0 = (int)((v0 >> 23) & 0xff);
+        bool regular = c_ok && n >= 4 && e0 > 0 && e0 < 255;
+        unsigned mmin = 0xffffffffu, mmax = 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            const unsigned vb = __float_as_uint(v[k]);
+            regular = regular && ((vb >> 23) == (v0 >> 23));                            // same sign and exponent
+            const unsigned m = (vb & 0x7fffffu) | 0x800000u;
+            mmin = min(mmin, m);
+            mmax = max(mmax, m);
+        }
+        int m_steps = 0;
+        unsigned kq = 0;
+        bool grow = false;
+        if (regular)
+        {
+            // c / u = Mc * 2^sh with sh = (ea - 127) + (eb - 127) - 46 - (e0 - 127 - 23)
+            const int sh = ea + eb - e0 - 150;
+            if (sh >= 0) regular = false;                       // |c| >= 2^46 ulps: leaves the binade at once
+            else
+            {
+                const int t = -sh;
+                if (t >= 49) return;                            // |c| < u/2: every step rounds back, v never moves again
+                const unsigned long long q = Mc >> t, rem = Mc & ((1ull << t) - 1ull), half = 1ull << (t - 1);
+                if (rem == half || q >= (1ull << 24)) regular = false; // tie, or more than a binade per step
+                else
+                {
+                    kq = (unsigned)q + (rem > half ? 1u : 0u);
+                    if (kq == 0u) return;
+                    grow = (sc == (v0 >> 31));                  // |v| grows when c and v have the same sign
+                    const float dist = grow ? (float)(int)(0xffffffu - mmax) : (float)((int)mmin - 0x800001);
+                    // conservative floor(dist / kq): rcp.approx and the multiply err by < 2^-21 relative
+                    const float mf = dist * mufu_rcp((float)kq) * (1.f - 9.5367431640625e-7f);
+                    m_steps = min((int)mf, n);
+                }
+            }
+        }
+        if (regular && m_steps >= 1)
+        {
+            const unsigned add = (unsigned)m_steps * kq;        // <= 2^24
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+            {
+                const unsigned vb = __float_as_uint(v[k]);
+                const unsigned m = (vb & 0x7fffffu) | 0x800000u;
+                const unsigned mn = grow ? m + add : m - add;   // stays in [2^23 + 1, 2^24 - 1]
+                v[k] = __uint_as_float((vb & 0xff800000u) | (mn & 0x7fffffu));
+            }
+            n -= m_steps;
+        }
+        else
+        {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = __fmaf_rn(a, b, v[k]);
+            --n;
+        }
+    }
 }
 
 // ---- the update (tsdf_volume.cu:69-79) ---------------------------------------------------
@@ -364,14 +452,33 @@ __global__ void __launch_bounds__(128) integrate_kernel(const IntegrateArgs a)
 
     const float sz = a.pose.R.m[8];
     const unsigned long long vs2 = pack2(a.vsx, a.vsx), sxy = pack2(a.pose.R.m[2], a.pose.R.m[5]), szz = pack2(sz, sz);
-    // replay of the reference's running sum up to the first visited plane (tsdf_volume.cu:56)
-#pragma unroll 4
-    for (int z = 1; z < za; ++z)
+    // the reference's running sum up to the first visited plane (tsdf_volume.cu:56): exact jump when the
+    // prefix is long, plain replay otherwise
+    if (a.use_jump && za - 1 >= a.jump_min)
     {
+        float jx[4], jy[4], jz[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) xy[k] = ffma2(vs2, sxy, xy[k]);
-        zz[0] = ffma2(vs2, szz, zz[0]);
-        zz[1] = ffma2(vs2, szz, zz[1]);
+        for (int k = 0; k < 4; ++k) unpack2(xy[k], jx[k], jy[k]);
+        unpack2(zz[0], jz[0], jz[1]);
+        unpack2(zz[1], jz[2], jz[3]);
+        jump4(jx, a.vsx, a.pose.R.m[2], za - 1);
+        jump4(jy, a.vsx, a.pose.R.m[5], za - 1);
+        jump4(jz, a.vsx, sz, za - 1);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xy[k] = pack2(jx[k], jy[k]);
+        zz[0] = pack2(jz[0], jz[1]);
+        zz[1] = pack2(jz[2], jz[3]);
+    }
+    else
+    {
+#pragma unroll 4
+        for (int z = 1; z < za; ++z)
+        {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) xy[k] = ffma2(vs2, sxy, xy[k]);
+            zz[0] = ffma2(vs2, szz, zz[0]);
+            zz[1] = ffma2(vs2, szz, zz[1]);
+        }
     }
     // fast path needs vc.z >= FLT_MIN on every visited plane; vc.z is affine in z up to the running-sum
     // drift (millimetres at most), so the two ends decide with a 1 cm margin
@@ -549,6 +656,10 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
     a.wtab = ctx->wtab;
     a.zexit = ctx->zexit;
     a.max_weight = ctx->p.tsdf_max_weight;
+    a.use_jump = getenv("KFB_INTEGRATE_NOJUMP") ? 0 : 1;
+    // measured on B200: a jump costs about as much as 600 replayed planes (warps that straddle vc.x == 0 walk
+    // many binades), so it pays for far z-slabs / large volumes, not for the z-chunks of a 512^3 sweep
+    a.jump_min = getenv("KFB_INTEGRATE_JUMPMIN") ? atoi(getenv("KFB_INTEGRATE_JUMPMIN")) : 640;
     a.bricks = ctx->bricks;
     a.bdirty = ctx->bdirty;
     a.bx = ctx->bdim[0]; a.by = ctx->bdim[1]; a.bz = ctx->bdim[2]; a.bz0 = ctx->bz0;

@@ -140,12 +140,12 @@ __device__ __forceinline__ float load_tsdf(const short *addr)
 // running-sum instructions only; otherwise KFB_RC_BATCH steps are classified and their loads issued before
 // the first sign test (sample positions do not depend on fetched values).  Candidate hits are parked and
 // their normals are computed after the march, when the warp has reconverged.
-__global__ void __launch_bounds__(128) raycast_kernel(const RaycastArgs a)
+__global__ void __launch_bounds__(32) raycast_kernel(const RaycastArgs a)
 {
     const unsigned FULL = 0xffffffffu;
-    // warp = 8x4 pixel tile; block = 8x16 pixels
+    // block = warp = 8x4 pixel tile (rays of very different length share nothing: fine-grained scheduling)
     const int x = blockIdx.x * 8 + threadIdx.x;
-    const int y = blockIdx.y * 16 + threadIdx.y;
+    const int y = blockIdx.y * 4 + threadIdx.y;
     const bool inside = x < a.k.w && y < a.k.h;
     const int pix = y * a.k.w + x;
     float4 vout = make_float4(0.f, 0.f, 0.f, 0.f), nout = vout;
@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(128) raycast_kernel(const RaycastArgs a)
         rs.inv[1] = my > 1e-30f ? 1.f / my : 1e30f;
         rs.inv[2] = mz > 1e-30f ? 1.f / mz : 1e30f;
     }
+    const float rstep = 1.f / a.step_len;
     float nx = 0.f, ny = 0.f, nz = 0.f, tnext = KFB_QNAN;
     if (marching)
     {
@@ -214,8 +215,16 @@ __global__ void __launch_bounds__(128) raycast_kernel(const RaycastArgs a)
             if (alive) st[0] = classify(a, rs, qx[0], qy[0], qz[0], own[0], cnt0, addr[0]);
             if (__all_sync(FULL, !alive || st[0] != ST_FETCH))
             {
-                // no ray of the warp needs this sample: it is NaN for all; then skip what every ray can skip
-                int nskip = __reduce_min_sync(FULL, (alive && st[0] == ST_NAN) ? cnt0 : 0x7fffffff);
+                // no ray of the warp needs this sample: it is NaN for all; then skip what every ray can skip.
+                // A ray's count is also capped by its remaining steps to tfar (conservatively), so the skip
+                // loop needs no per-step exit test; rays that are not marching keep their state untouched.
+                int mine = 0x7fffffff;
+                if (alive && st[0] == ST_NAN)
+                {
+                    const float rem = __fmul_rn(__fsub_rn(tfar, ray_len), rstep) - 3.f;
+                    mine = min(cnt0, rem > 0.f ? (int)fminf(rem, 1e6f) : 0);
+                }
+                int nskip = __reduce_min_sync(FULL, mine);
                 if (nskip == 0x7fffffff) nskip = 0;
                 if (alive)
                 {
@@ -224,10 +233,10 @@ __global__ void __launch_bounds__(128) raycast_kernel(const RaycastArgs a)
                     tnext = KFB_QNAN;
                     ray_len = __fadd_rn(ray_len, a.step_len);
                 }
-#pragma unroll 4
-                for (int i = 0; i < nskip; ++i)
+                if (marching && alive)
                 {
-                    if (marching && ray_len < tfar)
+#pragma unroll 4
+                    for (int i = 0; i < nskip; ++i)
                     {
                         nx = __fmaf_rn(dx, a.vs[0], nx); ny = __fmaf_rn(dy, a.vs[1], ny); nz = __fmaf_rn(dz, a.vs[2], nz);
                         ray_len = __fadd_rn(ray_len, a.step_len);
@@ -370,7 +379,7 @@ int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9]
     a.ts_sign_compat = ctx->p.compat_raycast_ts_sign;
     a.bdist = ctx->bdist;
     a.bx = ctx->bdim[0]; a.by = ctx->bdim[1]; a.bz = ctx->bdim[2]; a.bz0 = ctx->bz0;
-    dim3 block(8, 16), grid((a.k.w + 7) / 8, (a.k.h + 15) / 16);
+    dim3 block(8, 4), grid((a.k.w + 7) / 8, (a.k.h + 3) / 4);
     if (ctx->profiling) cudaEventRecord(ctx->events[58], ctx->stream);
     raycast_kernel<<<grid, block, 0, ctx->stream>>>(a);
     KFB_LAUNCH_CHECK(ctx);

@@ -442,6 +442,51 @@ def test_full_size_properties_512(kfo, kfb):
     assert np.abs(nrm - 1).max() < 1e-3
 
 
+def test_integrate_jump_equals_replay(kfo, kfb):
+    """The closed-form jump of the float running sum (kfb_integrate.cu: jump4) against plain replay
+    (KFB_INTEGRATE_NOJUMP=1): volumes must be bit-identical for poses whose vc.x / vc.y cross zero and
+    binade boundaries inside the skipped prefix, for several z-chunk counts and for a far z-slab."""
+    dims = 256
+    Ko, Kb, Po, Pb = make_pair(kfo, kfb, dims, 320, 240)
+    volpose = np.array(Po.volu_pose, np.float32)
+    rng = np.random.default_rng(7)
+    poses = [kfo.trajectory_pose(k) for k in (0, 40, 75)]
+    for _ in range(3):                      # extra rotations (a few degrees about random axes) + offsets
+        w = rng.normal(size=3); w *= 0.12 / np.linalg.norm(w)
+        th = np.linalg.norm(w); kx = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]) / th
+        R = np.eye(3) + np.sin(th) * kx + (1 - np.cos(th)) * kx @ kx
+        t = rng.normal(size=3) * 0.05
+        poses.append(np.concatenate([R, t[:, None]], axis=1).astype(np.float32).reshape(12))
+    Pslab = kfb.default_params(dims)
+    Pslab.slab_z_begin, Pslab.slab_z_end = 192, 256
+    saved = {k: os.environ.get(k) for k in ("KFB_INTEGRATE_NOJUMP", "KFB_INTEGRATE_ZCHUNKS", "KFB_INTEGRATE_JUMPMIN")}
+    os.environ["KFB_INTEGRATE_JUMPMIN"] = "16"
+    try:
+        for P, chunks in ((Pb, "1"), (Pb, "4"), (Pb, "16"), (Pslab, "2")):
+            vols = []
+            for nojump in (False, True):
+                if nojump:
+                    os.environ["KFB_INTEGRATE_NOJUMP"] = "1"
+                else:
+                    os.environ.pop("KFB_INTEGRATE_NOJUMP", None)
+                os.environ["KFB_INTEGRATE_ZCHUNKS"] = chunks
+                ctx = _ctx(kfb, Kb, P)
+                for pose in poses:
+                    ctx.upload_depth_mm(kfo.render_depth_mm(pose, Ko))
+                    ctx.frontend()
+                    ctx.integrate(kfo.pose_mul(kfo.pose_inv(pose), volpose))
+                vols.append(ctx.download_volume())
+                ctx.close()
+            assert vols[0][..., 1].max() >= 3
+            assert np.array_equal(vols[0], vols[1]), chunks
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 # ------------------------------------------------------------------------------- z-slab sharding (§8e)
 @pytest.mark.parametrize("world", [2, 3])
 def test_slab_contexts_compose_to_single_gpu_result(kfo, kfb, world):

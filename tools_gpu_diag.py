@@ -21,12 +21,14 @@ def main():
         return float(np.median(ts)), float(np.min(ts))
     ctx.upload_depth_mm(frames[0])
     print("frontend ms", timed(ctx.frontend))
-    v2c = kfo.pose_mul(kfo.pose_inv(kfo.identity()), volpose)
+    cam = kfo.trajectory_pose(40)
+    ctx.upload_depth_mm(kfo.render_depth_mm(cam, Ko)); ctx.frontend()
+    v2c = kfo.pose_mul(kfo.pose_inv(cam), volpose)
     U = ctx.integrate(v2c, count=True)
     print("U", U)
     t = timed(lambda: ctx.integrate(v2c))
     print("integrate ms", t, "GB/s (8U/t)", 8 * U / (t[0] * 1e-3) / 1e9)
-    c2v = kfo.pose_mul(kfo.pose_inv(volpose), kfo.identity())
+    c2v = kfo.pose_mul(kfo.pose_inv(volpose), cam)
     rinv = kfo.rot_inv(c2v)
     print("raycast ms", timed(lambda: ctx.raycast(c2v, rinv)))
     print("pyramid ms", timed(ctx.model_pyramid))
