@@ -97,7 +97,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->profiling = 0;
     ctx->icp_seq = 0;
     ctx->vol = nullptr; ctx->cloud = nullptr; ctx->cloud_cap = 0;
-    ctx->tab_thrz = nullptr; ctx->tab_exact = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->bricks = nullptr;
+    ctx->tab_thrz = nullptr; ctx->tab_exact = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->bricks = nullptr; ctx->states = nullptr; ctx->states_bytes = 0;
     ctx->bdist = ctx->bdist_tmp = ctx->bdist_tmp2 = nullptr; ctx->bdirty = nullptr;
     ctx->hit_t = nullptr; ctx->icp_partials = nullptr; ctx->icp_ticket = nullptr; ctx->counters = nullptr;
     ctx->counters_host = nullptr; ctx->pinned_depth = nullptr; ctx->render_dev = nullptr; ctx->render_host = nullptr;
@@ -214,6 +214,7 @@ void kfb_destroy(kfb_ctx *ctx)
     if (ctx->tab_thrz) cudaFree(ctx->tab_thrz);
     if (ctx->wtab) cudaFree(ctx->wtab);
     if (ctx->zexit) cudaFree(ctx->zexit);
+    if (ctx->states) cudaFree(ctx->states);
     if (ctx->bricks) cudaFree(ctx->bricks);
     if (ctx->bdist) cudaFree(ctx->bdist);
     if (ctx->bdist_tmp) cudaFree(ctx->bdist_tmp);

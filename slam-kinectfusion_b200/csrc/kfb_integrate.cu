@@ -58,6 +58,8 @@ struct IntegrateArgs
     float fx, fy, cx, cy;
     int w, h;
     const float2 *thrz;
+    unsigned long long *states; // [chunk][6][X/4 * Y]: packed vc of every thread after plane zstart(chunk) - 1
+    int nchunks;
     const float2 *exact;
     const float4 *wtab;
     const float *zexit;
@@ -393,8 +395,11 @@ __device__ __forceinline__ void update_quad(const IntegrateArgs &a, uint4 *vp, c
 
 // ---- the sweep ------------------------------------------------------------------------
 #define KFB_BAND (-8.0f)
+#ifndef KFB_INT_MINB
+#define KFB_INT_MINB 8
+#endif
 template <int U, bool COUNT>
-__global__ void __launch_bounds__(128) integrate_kernel(const IntegrateArgs a)
+__global__ void __launch_bounds__(128, KFB_INT_MINB) integrate_kernel(const IntegrateArgs a)
 {
     const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
     const int y = blockIdx.y * 4 + threadIdx.y;
@@ -452,27 +457,17 @@ __global__ void __launch_bounds__(128) integrate_kernel(const IntegrateArgs a)
 
     const float sz = a.pose.R.m[8];
     const unsigned long long vs2 = pack2(a.vsx, a.vsx), sxy = pack2(a.pose.R.m[2], a.pose.R.m[5]), szz = pack2(sz, sz);
-    // the reference's running sum up to the first visited plane (tsdf_volume.cu:56): exact jump when the
-    // prefix is long, plain replay otherwise
-    if (a.use_jump && za - 1 >= a.jump_min)
+    // the reference's running sum (tsdf_volume.cu:56) up to the first visited plane: column_states_kernel has
+    // stored vc after plane zstart - 1 for every chunk; only the planes zstart .. za - 1 are replayed here
     {
-        float jx[4], jy[4], jz[4];
+        const size_t nthr = (size_t)(a.X >> 2) * a.Y;
+        const unsigned long long *st = a.states + (size_t)blockIdx.z * 6 * nthr + (size_t)y * (a.X >> 2) + (x0 >> 2);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) unpack2(xy[k], jx[k], jy[k]);
-        unpack2(zz[0], jz[0], jz[1]);
-        unpack2(zz[1], jz[2], jz[3]);
-        jump4(jx, a.vsx, a.pose.R.m[2], za - 1);
-        jump4(jy, a.vsx, a.pose.R.m[5], za - 1);
-        jump4(jz, a.vsx, sz, za - 1);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) xy[k] = pack2(jx[k], jy[k]);
-        zz[0] = pack2(jz[0], jz[1]);
-        zz[1] = pack2(jz[2], jz[3]);
-    }
-    else
-    {
+        for (int k = 0; k < 4; ++k) xy[k] = __ldg(st + (size_t)k * nthr);
+        zz[0] = __ldg(st + 4 * nthr);
+        zz[1] = __ldg(st + 5 * nthr);
 #pragma unroll 4
-        for (int z = 1; z < za; ++z)
+        for (int z = zstart; z < za; ++z)
         {
 #pragma unroll
             for (int k = 0; k < 4; ++k) xy[k] = ffma2(vs2, sxy, xy[k]);
@@ -527,9 +522,10 @@ __global__ void __launch_bounds__(128) integrate_kernel(const IntegrateArgs a)
     for (int z = za; z <= zb; z += U)
     {
         float ts[U][4], cz[U][4];
-        int pix[U][4];
+        unsigned int pix[U][4];
         float2 th[U][4];
         unsigned long long sxyv[U][4];
+        const unsigned int last_pix = (unsigned int)(a.w * a.h - 1);
         // ---- phase A1: advance, project, issue all threshold loads -------------------------------
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -551,9 +547,12 @@ __global__ void __launch_bounds__(128) integrate_kernel(const IntegrateArgs a)
                 unpack2(m, mu, mv);
                 const int ui = __float_as_int(mu) - KFB_MAGIC_I;
                 const int vi = __float_as_int(mv) - KFB_MAGIC_I;
-                const bool ok = ((unsigned)ui < (unsigned)a.w) & ((unsigned)vi < (unsigned)a.h) & (z + u <= zb);
-                pix[u][k] = ok ? vi * a.w + ui : -1;
-                th[u][k] = __ldg(a.thrz + max(pix[u][k], 0));
+                const bool ok = ((unsigned)ui < (unsigned)a.w) & ((unsigned)vi < (unsigned)a.h);
+                // an out-of-image voxel is classified as "behind everything": vc.z = +inf fails `<= hi_z` and
+                // passes `> lo_z` for whatever (clamped) table entry it reads
+                cz[u][k] = ok ? cz[u][k] : __int_as_float(0x7f800000);
+                pix[u][k] = min((unsigned int)(vi * a.w + ui), last_pix);
+                th[u][k] = __ldg(a.thrz + pix[u][k]);
             }
         }
         // ---- phase A2: classify against the thresholds; exact sdf only in the band -------------------
@@ -563,8 +562,7 @@ __global__ void __launch_bounds__(128) integrate_kernel(const IntegrateArgs a)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
             {
-                float t = cz[u][k] <= th[u][k].x ? 1.0f : (cz[u][k] > th[u][k].y ? KFB_SKIP : KFB_BAND);
-                t = pix[u][k] < 0 ? KFB_SKIP : t;
+                const float t = cz[u][k] <= th[u][k].x ? 1.0f : (cz[u][k] > th[u][k].y ? KFB_SKIP : KFB_BAND);
                 band |= (t == KFB_BAND);
                 ts[u][k] = t;
             }
@@ -574,7 +572,7 @@ __global__ void __launch_bounds__(128) integrate_kernel(const IntegrateArgs a)
             for (int u = 0; u < U; ++u)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (ts[u][k] == KFB_BAND) ts[u][k] = band_tsdf(a, sxyv[u][k], cz[u][k], pix[u][k], rtrunc);
+                    if (ts[u][k] == KFB_BAND) ts[u][k] = band_tsdf(a, sxyv[u][k], cz[u][k], (int)pix[u][k], rtrunc);
         }
         // ---- loads, then phase B ------------------------------------------------------------------------
         uint4 word[U];
@@ -582,7 +580,7 @@ __global__ void __launch_bounds__(128) integrate_kernel(const IntegrateArgs a)
 #pragma unroll
         for (int u = 0; u < U; ++u)
         {
-            need[u] = (ts[u][0] != KFB_SKIP) | (ts[u][1] != KFB_SKIP) | (ts[u][2] != KFB_SKIP) | (ts[u][3] != KFB_SKIP);
+            need[u] = ((ts[u][0] != KFB_SKIP) | (ts[u][1] != KFB_SKIP) | (ts[u][2] != KFB_SKIP) | (ts[u][3] != KFB_SKIP)) & (z + u <= zb);
             if (need[u]) word[u] = __ldcs(vp + (size_t)u * plane4);
         }
 #pragma unroll
@@ -591,6 +589,64 @@ __global__ void __launch_bounds__(128) integrate_kernel(const IntegrateArgs a)
         vp += (size_t)U * plane4;
     }
     if (COUNT && n_upd) atomicAdd(a.counter, (unsigned long long)n_upd); // threads leave at different times: no shuffles
+}
+
+// vc of every thread's four columns at the start of every z-chunk, by the reference's recurrence from z = 1
+// (exact jump for a long prefix in front of a far z-slab).  One sequential pass per column instead of one
+// replay per chunk.
+__global__ void __launch_bounds__(128) column_states_kernel(const IntegrateArgs a)
+{
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 4 + threadIdx.y;
+    if (x0 >= a.X || y >= a.Y) return;
+    float vx[4], vy[4], vz[4];
+    {
+        const float py = __fmul_rn((float)y, a.vsy);
+        const float pz = __fmul_rn(0.f, a.vsz);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            const float px = __fmul_rn((float)(x0 + k), a.vsx);
+            const float3 r = rot3(a.pose.R, px, py, pz);
+            vx[k] = __fadd_rn(r.x, a.pose.t[0]);
+            vy[k] = __fadd_rn(r.y, a.pose.t[1]);
+            vz[k] = __fadd_rn(r.z, a.pose.t[2]);
+        }
+    }
+    const float sx = a.pose.R.m[2], sy = a.pose.R.m[5], sz = a.pose.R.m[8];
+    int done = 0; // planes applied so far
+    if (a.use_jump && a.zb - 1 >= a.jump_min)
+    {
+        jump4(vx, a.vsx, sx, a.zb - 1);
+        jump4(vy, a.vsx, sy, a.zb - 1);
+        jump4(vz, a.vsx, sz, a.zb - 1);
+        done = a.zb - 1;
+    }
+    unsigned long long xy[4], zz[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xy[k] = pack2(vx[k], vy[k]);
+    zz[0] = pack2(vz[0], vz[1]);
+    zz[1] = pack2(vz[2], vz[3]);
+    const unsigned long long vs2 = pack2(a.vsx, a.vsx), sxy = pack2(sx, sy), szz = pack2(sz, sz);
+    const size_t nthr = (size_t)(a.X >> 2) * a.Y;
+    unsigned long long *st = a.states + (size_t)y * (a.X >> 2) + (x0 >> 2);
+    for (int c = 0; c < a.nchunks; ++c)
+    {
+        const int target = a.zb + c * a.zchunk - 1; // state after this plane
+#pragma unroll 4
+        for (; done < target; ++done)
+        {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) xy[k] = ffma2(vs2, sxy, xy[k]);
+            zz[0] = ffma2(vs2, szz, zz[0]);
+            zz[1] = ffma2(vs2, szz, zz[1]);
+        }
+        unsigned long long *o = st + (size_t)c * 6 * nthr;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[(size_t)k * nthr] = xy[k];
+        o[4 * nthr] = zz[0];
+        o[5 * nthr] = zz[1];
+    }
 }
 
 // Conservative frustum planes for this launch (see CullPlane).  vc(x, y, z) = P0(x, y) + z * S in exact
@@ -670,13 +726,32 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
 
     const int planes = a.ze - a.zb;
     if (planes <= 0) return KFB_OK;
-    // z-chunking trades replayed running-sum adds for resident warps and load balance (the visited
-    // interval differs per column).  KFB_INTEGRATE_ZCHUNKS overrides for tuning.
-    const long cols = ((long)(a.X + 127) / 128) * ((a.Y + 3) / 4);
-    int zc = 1;
-    while (cols * zc < 148L * 24 && zc < 16 && planes / (zc * 2) >= 32) zc *= 2;
+    // z-chunks give resident warps and load balance (the visited interval differs per column); the running
+    // sum at each chunk start comes from column_states_kernel, so chunks cost no replay.  48 B per thread per
+    // chunk of state: bounded to ~64 MB.  KFB_INTEGRATE_ZCHUNKS overrides for tuning.
+    const size_t nthr = (size_t)(a.X >> 2) * a.Y;
+    int zc = (planes + 31) / 32;
+    if (zc > 16) zc = 16;
+    while (zc > 1 && (size_t)zc * 48 * nthr > ((size_t)64 << 20)) --zc;
     if (const char *e = getenv("KFB_INTEGRATE_ZCHUNKS")) zc = atoi(e) > 0 ? atoi(e) : zc;
+    if (zc > planes) zc = planes;
     a.zchunk = (planes + zc - 1) / zc;
+    a.nchunks = zc;
+    {
+        const size_t need = (size_t)zc * 48 * nthr;
+        if (need > ctx->states_bytes)
+        {
+            KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (ctx->states) cudaFree(ctx->states);
+            ctx->states = nullptr; ctx->states_bytes = 0;
+            KFB_CUDA(ctx, cudaMalloc(&ctx->states, need));
+            ctx->states_bytes = need;
+        }
+        a.states = ctx->states;
+        dim3 sb(32, 4), sg((a.X + 127) / 128, (a.Y + 3) / 4);
+        column_states_kernel<<<sg, sb, 0, ctx->stream>>>(a);
+        KFB_LAUNCH_CHECK(ctx);
+    }
     dim3 block(32, 4), grid((a.X + 127) / 128, (a.Y + 3) / 4, zc);
     if (n_updated)
     {
@@ -691,7 +766,10 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
     else
     {
         if (ctx->profiling) cudaEventRecord(ctx->events[60], ctx->stream);
-        integrate_kernel<2, false><<<grid, block, 0, ctx->stream>>>(a);
+        const int U = getenv("KFB_INTEGRATE_U") ? atoi(getenv("KFB_INTEGRATE_U")) : 2;
+        if (U == 1) integrate_kernel<1, false><<<grid, block, 0, ctx->stream>>>(a);
+        else if (U == 4) integrate_kernel<4, false><<<grid, block, 0, ctx->stream>>>(a);
+        else integrate_kernel<2, false><<<grid, block, 0, ctx->stream>>>(a);
         KFB_LAUNCH_CHECK(ctx);
         if (ctx->profiling) cudaEventRecord(ctx->events[61], ctx->stream);
     }
