@@ -97,12 +97,12 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->profiling = 0;
     ctx->icp_seq = 0;
     ctx->vol = nullptr; ctx->cloud = nullptr; ctx->cloud_cap = 0;
-    ctx->tab_thrz = nullptr; ctx->tab_exact = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->bricks = nullptr; ctx->states = nullptr; ctx->states_bytes = 0;
+    ctx->tab_thrz = nullptr; ctx->tab_exact = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->zmip = nullptr; ctx->bricks = nullptr; ctx->states = nullptr; ctx->states_bytes = 0;
     ctx->bdist = ctx->bdist_tmp = ctx->bdist_tmp2 = nullptr; ctx->bdirty = nullptr;
     ctx->hit_t = nullptr; ctx->icp_partials = nullptr; ctx->icp_ticket = nullptr; ctx->counters = nullptr;
     ctx->counters_host = nullptr; ctx->pinned_depth = nullptr; ctx->render_dev = nullptr; ctx->render_host = nullptr;
     ctx->stream = nullptr; ctx->own_stream = 1;
-    ctx->fstream = nullptr; ctx->ev_front = nullptr; ctx->ev_free = nullptr; ctx->front_pending = 0;
+    ctx->fstream = nullptr; ctx->ev_front = nullptr; ctx->ev_free = nullptr; ctx->ev_tables_free = nullptr; ctx->front_pending = 0;
     ctx->icp_host = nullptr; ctx->icp_gate_host = nullptr; ctx->icp_devgate = nullptr;
     memset(ctx->L, 0, sizeof(ctx->L));
     memset(ctx->events, 0, sizeof(ctx->events));
@@ -118,6 +118,8 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     KFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->fstream, cudaStreamNonBlocking));
     KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_front, cudaEventDisableTiming));
     KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_free, cudaEventDisableTiming));
+    KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_tables_free, cudaEventDisableTiming));
+    KFB_CUDA(ctx, cudaEventRecord(ctx->ev_tables_free, ctx->stream));
     KFB_CUDA(ctx, cudaEventRecord(ctx->ev_free, ctx->stream));
     for (int l = 0; l < ctx->levels; ++l)
     {
@@ -151,6 +153,15 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     if (p->tsdf_max_weight < 1 || p->tsdf_max_weight > 32767) { ctx->err = "tsdf_max_weight must be in [1, 32767]"; return KFB_ERR_INVALID; }
     KFB_CUDA(ctx, cudaMalloc(&ctx->wtab, (size_t)(p->tsdf_max_weight + 1) * sizeof(float4)));
     KFB_CUDA(ctx, cudaMalloc(&ctx->zexit, sizeof(float)));
+    {
+        int off = 0;
+        for (int i = 0; i < 6; ++i)
+        {
+            ctx->mip_off[i] = off;
+            off += ((intr->width + (1 << (i + 2)) - 1) >> (i + 2)) * ((intr->height + (1 << (i + 2)) - 1) >> (i + 2));
+        }
+        KFB_CUDA(ctx, cudaMalloc(&ctx->zmip, (size_t)off * sizeof(float)));
+    }
     ctx->bdim[0] = (p->volu_dims[0] + 7) >> 3;
     ctx->bdim[1] = (p->volu_dims[1] + 7) >> 3;
     ctx->bz0 = ctx->z0 >> 3;
@@ -202,6 +213,7 @@ void kfb_destroy(kfb_ctx *ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->ev_front) cudaEventDestroy(ctx->ev_front);
     if (ctx->ev_free) cudaEventDestroy(ctx->ev_free);
+    if (ctx->ev_tables_free) cudaEventDestroy(ctx->ev_tables_free);
     if (ctx->fstream) cudaStreamDestroy(ctx->fstream);
     for (int l = 0; l < KFB_MAX_LEVELS; ++l)
     {
@@ -214,6 +226,7 @@ void kfb_destroy(kfb_ctx *ctx)
     if (ctx->tab_thrz) cudaFree(ctx->tab_thrz);
     if (ctx->wtab) cudaFree(ctx->wtab);
     if (ctx->zexit) cudaFree(ctx->zexit);
+    if (ctx->zmip) cudaFree(ctx->zmip);
     if (ctx->states) cudaFree(ctx->states);
     if (ctx->bricks) cudaFree(ctx->bricks);
     if (ctx->bdist) cudaFree(ctx->bdist);
@@ -260,6 +273,7 @@ int kfb_set_stream(kfb_ctx *ctx, void *stream)
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)stream;
     ctx->own_stream = 0;
+    KFB_CUDA(ctx, cudaEventRecord(ctx->ev_tables_free, ctx->stream));
     return mark_free(ctx);
 }
 
@@ -279,6 +293,11 @@ int kfb_reset_frames(kfb_ctx *ctx)
             KFB_CUDA(ctx, cudaMemsetAsync(L.v[f], 0, n * sizeof(float4), ctx->stream));
             KFB_CUDA(ctx, cudaMemsetAsync(L.n[f], 0, n * sizeof(float4), ctx->stream));
         }
+    }
+    if (ctx->zmip)
+    {
+        const int rc = launch_build_tables(ctx, ctx->stream); // tables of the (now empty) depth image
+        if (rc) return rc;
     }
     return mark_free(ctx);
 }
@@ -407,6 +426,11 @@ int kfb_upload_depth_m(kfb_ctx *ctx, int level, const float *host)
     if (check_level(ctx, level)) return KFB_ERR_INVALID;
     const Level &L = ctx->L[level];
     KFB_CUDA(ctx, cudaMemcpyAsync(L.depth, host, (size_t)L.k.w * L.k.h * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    if (level == 0)
+    {
+        const int rc = launch_build_tables(ctx, ctx->stream);
+        if (rc) return rc;
+    }
     KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KFB_OK;
 }

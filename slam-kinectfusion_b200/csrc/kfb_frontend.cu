@@ -259,6 +259,10 @@ int launch_frontend(kfb_ctx *ctx)
     KFB_LAUNCH_CHECK(ctx);
     vertex_normal_kernel<<<g, b, 0, ctx->fstream>>>(a);
     KFB_LAUNCH_CHECK(ctx);
+    // integrate's per-pixel tables of this depth image, once the previous frame's integrate has read the old ones
+    KFB_CUDA(ctx, cudaStreamWaitEvent(ctx->fstream, ctx->ev_tables_free, 0));
+    const int rct = launch_build_tables(ctx, ctx->fstream);
+    if (rct) return rct;
     KFB_CUDA(ctx, cudaEventRecord(ctx->ev_front, ctx->fstream));
     ctx->front_pending = 1;
     return KFB_OK;

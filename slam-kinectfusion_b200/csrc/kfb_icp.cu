@@ -498,6 +498,17 @@ int icp_step(kfb_ctx *ctx, const float pose12[12], double out27[27])
     if (!S.active || S.done >= S.total) { ctx->err = "icp_step outside an active schedule"; return KFB_ERR_INVALID; }
     const unsigned long long seq = S.seq0 + (unsigned long long)S.done + 1ull;
     int rc;
+    if (getenv("KFB_ICP_DIRECT"))
+    {
+        // profiling aid: one ordinary launch per iteration (kernel replay by a profiler breaks the host/device
+        // handshake of the persistent kernel).  Same sums, bit for bit (see icp_setup).
+        int k = S.done, level = ctx->levels - 1;
+        while (level >= 0 && k >= S.iters[level]) { k -= S.iters[level]; --level; }
+        rc = launch_icp(ctx, level, pose12, out27);
+        if (rc) return rc;
+        ++S.done;
+        return KFB_OK;
+    }
     if (S.done == 0)
     {
         rc = icp_launch_persistent(ctx, pose12); // first pose by parameter

@@ -63,6 +63,9 @@ struct IntegrateArgs
     const float2 *exact;
     const float4 *wtab;
     const float *zexit;
+    const float *zmip;          // max-pyramid of lo_z, levels 2..7 (tiles of 4..128 px), see build_zmip_kernel
+    int mip_off[6], mip_w[6];
+    float Sx, Sy, Sz, invSz, driftE; // per-plane step of vc (float), 1/Sz, bound on the running-sum drift
     int max_weight;
     int use_jump, jump_min; // exact jump of the running sum for prefixes of at least jump_min planes
     uint8_t *bricks;
@@ -173,6 +176,67 @@ __global__ void build_tables_kernel(const float *__restrict__ depth, int w, int 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lo_z = fmaxf(lo_z, __shfl_xor_sync(0xffffffffu, lo_z, o));
     if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && lo_z > 0.f) atomicMax((int *)zexit, __float_as_int(lo_z));
+}
+
+// Max-pyramid of lo_z over the image: level l (2..7) holds, per 2^l x 2^l pixel tile, the largest vc.z any
+// pixel of the tile would still accept.  One block builds all levels of a 128 x 128 pixel region.
+__global__ void __launch_bounds__(256) build_zmip_kernel(const float2 *__restrict__ thrz, int w, int h, float *__restrict__ mip,
+                                                         int o2, int o3, int o4, int o5, int o6, int o7)
+{
+    __shared__ float s2[32][33], s3[16][17], s4[8][9], s5[4][5], s6[2][3];
+    const int rx = blockIdx.x * 128, ry = blockIdx.y * 128, t = threadIdx.x;
+    const int w2 = (w + 3) >> 2, w3 = (w + 7) >> 3, w4 = (w + 15) >> 4, w5 = (w + 31) >> 5, w6 = (w + 63) >> 6, w7 = (w + 127) >> 7;
+    for (int i = t; i < 1024; i += 256)
+    {
+        const int ty = i >> 5, tx = i & 31;
+        float m = -1.f;
+        for (int dy = 0; dy < 4; ++dy)
+            for (int dx = 0; dx < 4; ++dx)
+            {
+                const int x = rx + tx * 4 + dx, y = ry + ty * 4 + dy;
+                if (x < w && y < h) m = fmaxf(m, thrz[(size_t)y * w + x].y);
+            }
+        s2[ty][tx] = m;
+        const int gx = (rx >> 2) + tx, gy = (ry >> 2) + ty;
+        if (gx < w2 && gy < ((h + 3) >> 2)) mip[o2 + gy * w2 + gx] = m;
+    }
+    __syncthreads();
+    {
+        const int ty = t >> 4, tx = t & 15;
+        const float m = fmaxf(fmaxf(s2[2 * ty][2 * tx], s2[2 * ty][2 * tx + 1]), fmaxf(s2[2 * ty + 1][2 * tx], s2[2 * ty + 1][2 * tx + 1]));
+        s3[ty][tx] = m;
+        const int gx = (rx >> 3) + tx, gy = (ry >> 3) + ty;
+        if (gx < w3 && gy < ((h + 7) >> 3)) mip[o3 + gy * w3 + gx] = m;
+    }
+    __syncthreads();
+    if (t < 64)
+    {
+        const int ty = t >> 3, tx = t & 7;
+        const float m = fmaxf(fmaxf(s3[2 * ty][2 * tx], s3[2 * ty][2 * tx + 1]), fmaxf(s3[2 * ty + 1][2 * tx], s3[2 * ty + 1][2 * tx + 1]));
+        s4[ty][tx] = m;
+        const int gx = (rx >> 4) + tx, gy = (ry >> 4) + ty;
+        if (gx < w4 && gy < ((h + 15) >> 4)) mip[o4 + gy * w4 + gx] = m;
+    }
+    __syncthreads();
+    if (t < 16)
+    {
+        const int ty = t >> 2, tx = t & 3;
+        const float m = fmaxf(fmaxf(s4[2 * ty][2 * tx], s4[2 * ty][2 * tx + 1]), fmaxf(s4[2 * ty + 1][2 * tx], s4[2 * ty + 1][2 * tx + 1]));
+        s5[ty][tx] = m;
+        const int gx = (rx >> 5) + tx, gy = (ry >> 5) + ty;
+        if (gx < w5 && gy < ((h + 31) >> 5)) mip[o5 + gy * w5 + gx] = m;
+    }
+    __syncthreads();
+    if (t < 4)
+    {
+        const int ty = t >> 1, tx = t & 1;
+        const float m = fmaxf(fmaxf(s5[2 * ty][2 * tx], s5[2 * ty][2 * tx + 1]), fmaxf(s5[2 * ty + 1][2 * tx], s5[2 * ty + 1][2 * tx + 1]));
+        s6[ty][tx] = m;
+        const int gx = (rx >> 6) + tx, gy = (ry >> 6) + ty;
+        if (gx < w6 && gy < ((h + 63) >> 6)) mip[o6 + gy * w6 + gx] = m;
+    }
+    __syncthreads();
+    if (t == 0) mip[o7 + blockIdx.y * w7 + blockIdx.x] = fmaxf(fmaxf(s6[0][0], s6[0][1]), fmaxf(s6[1][0], s6[1][1]));
 }
 
 // wtab[wt] = {(float)wt, MUFU.RCP(wt + 1), bits(min(wt + 1, max_weight) << 16), 0}: the weight-dependent
@@ -365,6 +429,33 @@ __device__ __noinline__ void mark_bricks(uint8_t *flags, int *dirty, int gbx, in
             }
 }
 
+// Conservative interval [lo, hi] of planes in [zstart, zend) on which any of a thread's four columns can pass the
+// reference's predicate (never excludes a voxel the exact predicate would accept: each plane is relaxed by `slack`
+// and the bound is widened by one step).  (ax, ay, az) / (bx, by, bz) = vc of the first / last column at z = 0.
+__device__ __forceinline__ void frustum_interval(const IntegrateArgs &a, float ax, float ay, float az, float bx, float by, float bz,
+                                                 int zstart, int zend, float &lo, float &hi)
+{
+    lo = (float)zstart;
+    hi = (float)(zend - 1);
+    const float zx = __ldg(a.zexit);
+#pragma unroll
+    for (int c = 0; c < KFB_NCULL; ++c)
+    {
+        const CullPlane &cp = a.cull[c];
+        if (cp.kind == 3) continue;
+        const float ga = fmaf(cp.a, ax, fmaf(cp.b, ay, cp.g * az));
+        const float gb = fmaf(cp.a, bx, fmaf(cp.b, by, cp.g * bz));
+        float g0 = fmaxf(ga, gb) + cp.slack;
+        if (c == KFB_NCULL - 1) g0 += zx; // vc.z <= zexit
+        const float zc = g0 * cp.ninv;
+        if (cp.kind == 0) lo = fmaxf(lo, zc - 1.f);
+        else if (cp.kind == 1) hi = fminf(hi, zc + 1.f);
+        else if (g0 < 0.f) hi = -1.f;
+    }
+    lo = fminf(lo, (float)zend);
+    hi = fmaxf(hi, (float)zstart - 2.f);
+}
+
 // phase B of one plane: running weighted mean, re-encode, store (tsdf_volume.cu:69-79)
 template <bool COUNT>
 __device__ __forceinline__ void update_quad(const IntegrateArgs &a, uint4 *vp, const uint4 wd, const float t[4], int x0, int y, int z,
@@ -426,34 +517,63 @@ __global__ void __launch_bounds__(128, KFB_INT_MINB) integrate_kernel(const Inte
         zz[0] = pack2(z0v[0], z0v[1]);
         zz[1] = pack2(z0v[2], z0v[3]);
     }
-    // conservative frustum interval of this thread's four columns (never excludes a voxel the exact
-    // predicate would accept: each plane is relaxed by `slack` and the bound is widened by one step)
-    float lo = (float)zstart, hi = (float)(zend - 1);
+    // conservative frustum interval of this thread's four columns (see frustum_interval)
+    float lo, hi;
     {
         float ax, ay, bx_, by_;
         unpack2(xy[0], ax, ay);
         unpack2(xy[3], bx_, by_);
-        const float zx = __ldg(a.zexit);
+        frustum_interval(a, ax, ay, z0v[0], bx_, by_, z0v[3], zstart, zend, lo, hi);
+    }
+    const int za = max(zstart, (int)floorf(lo));
+    int zb = min(zend - 1, (int)ceilf(hi));
+    if (za > zb) return;
+    // Occlusion cut: over planes [za, zb] the four columns project into a pixel rectangle (a line segment per
+    // column; computed from the affine model and widened by the drift bound).  A voxel is rejected once vc.z
+    // exceeds lo_z of its pixel, hence certainly once it exceeds the maximum of lo_z over that rectangle, which
+    // the max-pyramid gives with four lookups.  Planes beyond that are never visited.
+    if (a.Sz > 1e-6f)
+    {
+        float ax, ay, bx_, by_;
+        unpack2(xy[0], ax, ay);
+        unpack2(xy[3], bx_, by_);
+        float umin = 1e30f, umax = -1e30f, vmin = 1e30f, vmax = -1e30f, zmin = 1e30f;
 #pragma unroll
-        for (int c = 0; c < KFB_NCULL; ++c)
+        for (int e = 0; e < 2; ++e)
         {
-            const CullPlane &cp = a.cull[c];
-            if (cp.kind == 3) continue;
-            const float ga = fmaf(cp.a, ax, fmaf(cp.b, ay, cp.g * z0v[0]));
-            const float gb = fmaf(cp.a, bx_, fmaf(cp.b, by_, cp.g * z0v[3]));
-            float g0 = fmaxf(ga, gb) + cp.slack;
-            if (c == KFB_NCULL - 1) g0 += zx; // vc.z <= zexit
-            const float zc = g0 * cp.ninv;
-            if (cp.kind == 0) lo = fmaxf(lo, zc - 1.f);
-            else if (cp.kind == 1) hi = fminf(hi, zc + 1.f);
-            else if (g0 < 0.f) hi = -1.f;
+            const float zf = (float)(e ? zb : za);
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+            {
+                const float X = fmaf(zf, a.Sx, k ? bx_ : ax), Y = fmaf(zf, a.Sy, k ? by_ : ay), Zc = fmaf(zf, a.Sz, k ? z0v[3] : z0v[0]);
+                const float r = 1.f / fmaxf(Zc, 1e-3f);
+                const float u = fmaf(a.fx * X, r, a.cx), v = fmaf(a.fy * Y, r, a.cy);
+                umin = fminf(umin, u); umax = fmaxf(umax, u);
+                vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+                zmin = fminf(zmin, Zc);
+            }
+        }
+        if (zmin > 0.05f)
+        {
+            // pixel error of the model: (fx + |u - cx|) * E / z per axis, plus rounding to the nearest pixel
+            const float pad = 1.5f + (a.fx + a.fy + (float)(a.w + a.h)) * a.driftE / zmin;
+            const int u0 = max((int)floorf(fmaxf(umin - pad, -1e6f)), 0), u1 = min((int)ceilf(fminf(umax + pad, 1e6f)), a.w - 1);
+            const int v0 = max((int)floorf(fmaxf(vmin - pad, -1e6f)), 0), v1 = min((int)ceilf(fminf(vmax + pad, 1e6f)), a.h - 1);
+            if (u0 > u1 || v0 > v1) return; // never inside the image on these planes
+            const int span = max(u1 - u0, v1 - v0) + 1;
+            const int l = max(32 - __clz(span - 1), 2);
+            if (l <= 7)
+            {
+                const float *m = a.zmip + a.mip_off[l - 2];
+                const int mw = a.mip_w[l - 2];
+                const float zmax = fmaxf(fmaxf(__ldg(m + (v0 >> l) * mw + (u0 >> l)), __ldg(m + (v0 >> l) * mw + (u1 >> l))),
+                                         fmaxf(__ldg(m + (v1 >> l) * mw + (u0 >> l)), __ldg(m + (v1 >> l) * mw + (u1 >> l))));
+                const float zc = (zmax + 2.f * a.driftE - fminf(z0v[0], z0v[3])) * a.invSz + 1.f;
+                zb = min(zb, (int)ceilf(fminf(zc, 1e6f)));
+                if (za > zb) return;
+            }
         }
     }
-    lo = fminf(lo, (float)zend);
-    hi = fmaxf(hi, (float)zstart - 2.f);
-    const int za = max(zstart, (int)floorf(lo));
-    const int zb = min(zend - 1, (int)ceilf(hi));
-    if (za > zb) return;
 
     const float sz = a.pose.R.m[8];
     const unsigned long long vs2 = pack2(a.vsx, a.vsx), sxy = pack2(a.pose.R.m[2], a.pose.R.m[5]), szz = pack2(sz, sz);
@@ -613,6 +733,15 @@ __global__ void __launch_bounds__(128) column_states_kernel(const IntegrateArgs 
             vz[k] = __fadd_rn(r.z, a.pose.t[2]);
         }
     }
+    // columns that never enter the frustum need no states (their sweep threads return before reading them), and
+    // no chunk past the last visited plane does
+    int z_last;
+    {
+        float lo, hi;
+        frustum_interval(a, vx[0], vy[0], vz[0], vx[3], vy[3], vz[3], a.zb, a.ze, lo, hi);
+        if (max(a.zb, (int)floorf(lo)) > min(a.ze - 1, (int)ceilf(hi))) return;
+        z_last = min(a.ze - 1, (int)ceilf(hi));
+    }
     const float sx = a.pose.R.m[2], sy = a.pose.R.m[5], sz = a.pose.R.m[8];
     int done = 0; // planes applied so far
     if (a.use_jump && a.zb - 1 >= a.jump_min)
@@ -633,6 +762,7 @@ __global__ void __launch_bounds__(128) column_states_kernel(const IntegrateArgs 
     for (int c = 0; c < a.nchunks; ++c)
     {
         const int target = a.zb + c * a.zchunk - 1; // state after this plane
+        if (target + 1 > z_last) break;
 #pragma unroll 4
         for (; done < target; ++done)
         {
@@ -683,18 +813,26 @@ static void make_cull_planes(const kfb_ctx *ctx, const IntegrateArgs &a, CullPla
     }
 }
 
+// Per-pixel tables of the current filtered depth (thresholds, exact operands, max-pyramid, zexit).  They depend
+// on the depth image only, so the front end builds them on its own stream, off the frame's critical path.
+int launch_build_tables(kfb_ctx *ctx, cudaStream_t stream)
+{
+    const Intr &k = ctx->L[0].k;
+    KFB_CUDA(ctx, cudaMemsetAsync(ctx->zexit, 0, sizeof(float), stream));
+    dim3 b(32, 8), g((k.w + 31) / 32, (k.h + 7) / 8);
+    build_tables_kernel<<<g, b, 0, stream>>>(ctx->L[0].depth, k.w, k.h, k.fx, k.fy, k.cx, k.cy, ctx->p.volu_trun_dist, ctx->tab_thrz,
+                                            ctx->tab_exact, ctx->zexit);
+    KFB_LAUNCH_CHECK(ctx);
+    dim3 mg((k.w + 127) / 128, (k.h + 127) / 128);
+    build_zmip_kernel<<<mg, 256, 0, stream>>>(ctx->tab_thrz, k.w, k.h, ctx->zmip, ctx->mip_off[0], ctx->mip_off[1], ctx->mip_off[2],
+                                              ctx->mip_off[3], ctx->mip_off[4], ctx->mip_off[5]);
+    KFB_LAUNCH_CHECK(ctx);
+    return KFB_OK;
+}
+
 int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_updated)
 {
     const Intr &k = ctx->L[0].k;
-    {
-        KFB_CUDA(ctx, cudaMemsetAsync(ctx->zexit, 0, sizeof(float), ctx->stream));
-        dim3 b(32, 8), g((k.w + 31) / 32, (k.h + 7) / 8);
-        build_tables_kernel<<<g, b, 0, ctx->stream>>>(ctx->L[0].depth, k.w, k.h, k.fx, k.fy, k.cx, k.cy,
-                                                     ctx->p.volu_trun_dist, ctx->tab_thrz, ctx->tab_exact, ctx->zexit);
-        KFB_LAUNCH_CHECK(ctx);
-        const int rcm = mark_free(ctx); // the filtered depth has been consumed: the next front end may overwrite it
-        if (rcm) return rcm;
-    }
     IntegrateArgs a;
     a.vol = ctx->vol;
     a.X = ctx->p.volu_dims[0];
@@ -721,6 +859,16 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
     a.bx = ctx->bdim[0]; a.by = ctx->bdim[1]; a.bz = ctx->bdim[2]; a.bz0 = ctx->bz0;
     a.counter = ctx->counters;
     make_cull_planes(ctx, a, a.cull);
+    a.zmip = ctx->zmip;
+    for (int i = 0; i < 6; ++i) { a.mip_off[i] = ctx->mip_off[i]; a.mip_w[i] = (k.w + (1 << (i + 2)) - 1) >> (i + 2); }
+    a.Sx = a.vsx * a.pose.R.m[2]; a.Sy = a.vsx * a.pose.R.m[5]; a.Sz = a.vsx * a.pose.R.m[8];
+    a.invSz = a.Sz > 1e-6f ? 1.f / a.Sz : 0.f;
+    {
+        const double M = fabs(a.pose.t[0]) + fabs(a.pose.t[1]) + fabs(a.pose.t[2]) + (double)ctx->p.volu_range[0] + ctx->p.volu_range[1] +
+                         ctx->p.volu_range[2] + (double)a.vsx * ctx->p.volu_dims[2] * 1.01;
+        a.driftE = (float)(((double)ctx->p.volu_dims[2] + 16.0) * 1.2e-7 * M + 4e-6 * M); // as in make_cull_planes + float model evaluation
+    }
+    if (getenv("KFB_INTEGRATE_NOCULL") || getenv("KFB_INTEGRATE_NOOCC")) a.Sz = 0.f;
     if (getenv("KFB_INTEGRATE_NOCULL"))
         for (int c = 0; c < KFB_NCULL; ++c) a.cull[c].kind = 3;
 
@@ -773,6 +921,7 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
         KFB_LAUNCH_CHECK(ctx);
         if (ctx->profiling) cudaEventRecord(ctx->events[61], ctx->stream);
     }
+    KFB_CUDA(ctx, cudaEventRecord(ctx->ev_tables_free, ctx->stream)); // the next frame's tables may now be built
     return launch_brick_distance(ctx);
 }
 
