@@ -197,6 +197,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     if args.gpus != world and world > 1:
@@ -221,8 +222,12 @@ def run_ours(args):
     hp.device = local
     if world > 1:
         from slam_kinectfusion_b200 import sharded
-        return sharded.run_bench(args, dist, rank, world, local, dims, K, frames, host_pin, dev_frames,
-                                 METRIC, UNIT, measured_peak_hbm, ClockSampler)
+        try:
+            return sharded.run_bench(args, dist, rank, world, local, dims, K, frames, host_pin, dev_frames,
+                                     METRIC, UNIT, measured_peak_hbm, ClockSampler)
+        finally:
+            dist.barrier()
+            dist.destroy_process_group()
 
     kf = kfb.KinectFusion(K, hp)
     ctx = kf.context()

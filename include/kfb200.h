@@ -177,7 +177,8 @@ int kfb_set_profiling(kfb_ctx *ctx, int on);
 /* number of kernels this library has launched on this context since creation */
 uint64_t kfb_launch_count(const kfb_ctx *ctx);
 /* raw device pointers for zero-copy interop (NCCL / torch views); which: 0 volume,
- * 1 prev vmap L0 (float4), 2 prev nmap L0 (float4), 3 cur depth L0 (float), 4 raycast event keys (float) */
+ * 1 prev vmap L0 (float4; the nmap follows it contiguously), 2 prev nmap L0 (float4), 3 cur depth L0 (float),
+ * 4 raycast event keys (float) */
 void *kfb_device_ptr(kfb_ctx *ctx, int which);
 void *kfb_stream(kfb_ctx *ctx);
 

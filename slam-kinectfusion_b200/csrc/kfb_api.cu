@@ -132,8 +132,10 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
         KFB_CUDA(ctx, cudaMalloc(&L.depth, n * sizeof(float)));
         for (int f = 0; f < 2; ++f)
         {
-            KFB_CUDA(ctx, cudaMalloc(&L.v[f], n * sizeof(float4)));
-            KFB_CUDA(ctx, cudaMalloc(&L.n[f], n * sizeof(float4)));
+            // vertex and normal map of a frame share one allocation (n = v + pixels): the cross-slab composite
+            // reduces both with a single collective
+            KFB_CUDA(ctx, cudaMalloc(&L.v[f], 2 * n * sizeof(float4)));
+            L.n[f] = L.v[f] + n;
         }
     }
     // volume (or z-slab of it, with halo)
@@ -220,7 +222,7 @@ void kfb_destroy(kfb_ctx *ctx)
         Level &L = ctx->L[l];
         if (L.raw) cudaFree(L.raw);
         if (L.depth) cudaFree(L.depth);
-        for (int f = 0; f < 2; ++f) { if (L.v[f]) cudaFree(L.v[f]); if (L.n[f]) cudaFree(L.n[f]); }
+        for (int f = 0; f < 2; ++f) { if (L.v[f]) cudaFree(L.v[f]); }
     }
     if (ctx->vol) cudaFree(ctx->vol);
     if (ctx->tab_thrz) cudaFree(ctx->tab_thrz);

@@ -8,7 +8,8 @@ voxel lies in its slab, and the first terminal ray event over all slabs is selec
     reduce(SUM, int32 view) of the maps to rank 0 (x + 0 == x exactly in integers, so the composite is
     bit-identical to the single-GPU raycast)
 
-ICP stays on rank 0 (it owns the composited model maps); only {tracking_ok, 4x3 pose} is broadcast.
+ICP stays on rank 0 (it owns the composited model maps); only {tracking_ok, 4x3 pose} is handed to the other
+ranks (shared-memory mailbox on the node, or torch.distributed broadcast with KFB_POSE_NCCL=1).
 The frame logic itself is the C++ facade's (kf::kinectfusion with kf::ShardComm callbacks); this module
 supplies the two collectives and the launch/bench glue.  `composite` and `broadcast_pose` are written
 against plain tensors so the same code runs over gloo on CPU tensors in tests/test_sharded.py.
@@ -41,16 +42,76 @@ def broadcast_pose(dist, msg13, device):
     return t.cpu().numpy()
 
 
-def composite(dist, keys, vmap_i32, nmap_i32, mask_fn, dst=0):
-    """keys: float32 tensor [P]; vmap_i32 / nmap_i32: int32 views of the slab's model maps; mask_fn(min_keys)
-    zeroes the maps where this rank does not hold the winning key.  After the call rank `dst` holds the
-    composite in its maps (in place)."""
-    min_keys = keys.clone()
+def composite(dist, keys, maps_i32, mask_fn, dst=0, scratch=None):
+    """keys: float32 tensor [P]; maps_i32: int32 view of the slab's model vertex+normal maps (one contiguous
+    buffer); mask_fn(min_keys) zeroes the maps where this rank does not hold the winning key.  After the call
+    rank `dst` holds the composite in its maps (in place)."""
+    min_keys = scratch if scratch is not None else keys.clone()
+    if scratch is not None:
+        min_keys.copy_(keys)
     dist.all_reduce(min_keys, op=dist.ReduceOp.MIN)
     mask_fn(min_keys)
-    dist.reduce(vmap_i32, dst=dst, op=dist.ReduceOp.SUM)
-    dist.reduce(nmap_i32, dst=dst, op=dist.ReduceOp.SUM)
+    dist.reduce(maps_i32, dst=dst, op=dist.ReduceOp.SUM)
     return min_keys
+
+
+class PoseMailbox:
+    """{tracking_ok, pose12} from rank 0 to the other ranks of the same node through POSIX shared memory (52
+    bytes + a sequence number; all ranks of a sharded volume sit on one NVLink box).  This is launcher
+    plumbing, not a data-path collective; `broadcast_pose` over torch.distributed is the portable equivalent."""
+
+    def __init__(self, dist, rank, tag, world=None):
+        from multiprocessing import shared_memory
+        self.rank = rank
+        self.world = world if world is not None else dist.get_world_size()
+        name = f"kfb_pose_{tag}"
+        size = 1024
+        if rank == 0:
+            try:
+                old = shared_memory.SharedMemory(name=name)
+                old.close()
+                old.unlink()
+            except FileNotFoundError:
+                pass
+            self.shm = shared_memory.SharedMemory(name=name, create=True, size=size)
+            self.shm.buf[:size] = bytes(size)
+        dist.barrier()
+        if rank != 0:
+            self.shm = shared_memory.SharedMemory(name=name)
+        self.seq_view = np.ndarray((1,), np.int64, self.shm.buf, 0)
+        self.ack_view = np.ndarray((64,), np.int64, self.shm.buf, 64)     # one acknowledgement counter per rank
+        self.msg_view = np.ndarray((13,), np.float32, self.shm.buf, 640)
+        self.seq = 0
+        dist.barrier()
+
+    def _spin(self, cond):
+        spins = 0
+        while not cond():
+            spins += 1
+            if spins > 100_000_000:
+                raise TimeoutError("pose mailbox: peer never arrived")
+
+    def exchange(self, msg13):
+        """msg13: numpy float32[13], valid on rank 0 on entry, on every rank on return."""
+        self.seq += 1
+        if self.rank == 0:
+            # every reader has taken the previous message before it is overwritten
+            self._spin(lambda: all(self.ack_view[r] >= self.seq - 1 for r in range(1, self.world)))
+            self.msg_view[:] = msg13
+            self.seq_view[0] = self.seq          # x86 TSO: payload before flag
+        else:
+            self._spin(lambda: self.seq_view[0] >= self.seq)
+            msg13[:] = self.msg_view
+            self.ack_view[self.rank] = self.seq
+
+    def close(self):
+        try:
+            self.seq_view = self.msg_view = self.ack_view = None
+            self.shm.close()
+            if self.rank == 0:
+                self.shm.unlink()
+        except Exception:
+            pass
 
 
 class DevView:
@@ -82,21 +143,24 @@ class ShardedKinectFusion:
         # all device work of the context and the collectives are ordered on torch's current stream
         self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self.P = K.width * K.height
+        self.mailbox = PoseMailbox(dist, rank, os.environ.get("MASTER_PORT", "0")) if os.environ.get("KFB_POSE_NCCL") is None else None
+        self.min_keys = torch.empty(self.P, dtype=torch.float32, device=self.device)
         self.kf.set_shard_comm(self._bcast, self._composite)
 
     def _views(self):
         # the model maps swap buffers on the bootstrap frame: take the pointers per call (cheap)
         d = self.device
         keys = dev_tensor(self.ctx.device_ptr(4), (self.P,), "<f4", d)
-        v = dev_tensor(self.ctx.device_ptr(1), (self.P * 4,), "<i4", d)
-        n = dev_tensor(self.ctx.device_ptr(2), (self.P * 4,), "<i4", d)
-        return keys, v, n
+        maps = dev_tensor(self.ctx.device_ptr(1), (self.P * 8,), "<i4", d)   # vertex map + normal map, contiguous
+        return keys, maps
 
     def _bcast(self, p):
         try:
             msg = np.ctypeslib.as_array(p, shape=(13,))
-            out = broadcast_pose(self.dist, msg, self.device)
-            msg[:] = out
+            if self.mailbox is not None:
+                self.mailbox.exchange(msg)
+            else:
+                msg[:] = broadcast_pose(self.dist, msg, self.device)
             return 0
         except Exception as e:  # noqa: BLE001 - reported through the C return code
             print("broadcast_pose failed:", e, flush=True)
@@ -104,8 +168,8 @@ class ShardedKinectFusion:
 
     def _composite(self):
         try:
-            keys, v, n = self._views()
-            composite(self.dist, keys, v, n, lambda mk: self.ctx.composite_mask(mk.data_ptr()))
+            keys, maps = self._views()
+            composite(self.dist, keys, maps, lambda mk: self.ctx.composite_mask(mk.data_ptr()), scratch=self.min_keys)
             return 0
         except Exception as e:  # noqa: BLE001
             print("composite failed:", e, flush=True)
@@ -113,6 +177,12 @@ class ShardedKinectFusion:
 
     def pipeline_ptr(self, ptr, w, h):
         return self.kf.pipeline_ptr(ptr, w, h)
+
+    def close(self):
+        if self.mailbox is not None:
+            self.dist.barrier()
+            self.mailbox.close()
+            self.mailbox = None
 
 
 def run_bench(args, dist, rank, world, local, dims, K, frames, host_pin, dev_frames, METRIC, UNIT, measured_peak_hbm,
@@ -189,6 +259,7 @@ def run_bench(args, dist, rank, world, local, dims, K, frames, host_pin, dev_fra
     stat = torch.tensor([float(np.mean(U)) * own_frac, float(np.mean(U)), float(np.mean(k_ms))], device=dev, dtype=torch.float64)
     gathered = [torch.zeros_like(stat) for _ in range(world)]
     dist.all_gather(gathered, stat)
+    skf.close()
     if rank != 0:
         return
     U_owned = sum(float(g[0]) for g in gathered)
@@ -205,7 +276,7 @@ def run_bench(args, dist, rank, world, local, dims, K, frames, host_pin, dev_fra
                                "ICP 10/5/4 on rank 0, per-slab raycast + first-hit composite, 300-frame looped synthetic trajectory",
                    "l2": "inputs larger than L2: every rank sweeps its >= 512 MiB slab each frame",
                    "frames_timed": S, "updated_voxels_per_frame": U_owned, "swept_voxels_per_frame": dims * dims * (dims - 1),
-                   "collectives_per_frame": "broadcast 52 B, all_reduce(min) 1.2 MB, 2 x reduce(sum) 4.9 MB"},
+                   "collectives_per_frame": "pose mailbox 52 B (shared memory), all_reduce(min) 1.2 MB, reduce(sum) 9.8 MB"},
         "frame_device_ms": ms_per_frame,
         "e2e": {"value": U_owned / (e2e_ms / S * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / S,
                 "h2d_bytes_per_step": w * h * 4 * world, "d2h_bytes_per_step": 19 * 27 * 16 + 52 * world,

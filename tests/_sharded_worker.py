@@ -44,7 +44,9 @@ def main():
     v, n, key = kfo.raycast_slab(slab, vd, c2v, K, zs0, zs1, zb, ze)
     v4 = np.zeros((h * w, 4), np.float32); v4[:, :3] = v.reshape(-1, 3)
     n4 = np.zeros((h * w, 4), np.float32); n4[:, :3] = n.reshape(-1, 3)
-    tv, tn, tk = torch.from_numpy(v4.view(np.int32).reshape(-1)), torch.from_numpy(n4.view(np.int32).reshape(-1)), torch.from_numpy(key.reshape(-1))
+    both = np.concatenate([v4, n4])            # vertex map then normal map, contiguous like the device buffer
+    v4, n4 = both[:h * w], both[h * w:]
+    tm, tk = torch.from_numpy(both.view(np.int32).reshape(-1)), torch.from_numpy(key.reshape(-1))
 
     def mask_fn(min_keys):          # CPU model of kfb_composite_mask
         mk = min_keys.numpy()
@@ -52,7 +54,17 @@ def main():
         v4[lose] = 0
         n4[lose] = 0
 
-    sharded.composite(dist, tk, tv, tn, mask_fn)
+    sharded.composite(dist, tk, tm, mask_fn)
+    # the shared-memory pose mailbox (same node) must deliver what rank 0 wrote
+    mb = sharded.PoseMailbox(dist, rank, f"test{os.environ['MASTER_PORT']}")
+    for it in range(3):
+        m2 = np.zeros(13, np.float32)
+        if rank == 0:
+            m2[:] = np.arange(13) + it
+        mb.exchange(m2)
+        assert np.array_equal(m2, np.arange(13, dtype=np.float32) + it)
+    dist.barrier()
+    mb.close()
     if rank == 0:
         # single-GPU truth: the full volume integrated over all planes, full raycast
         full = kfo.new_volume(vd)
