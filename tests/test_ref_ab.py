@@ -189,3 +189,69 @@ def test_reference_frame_loop_tracks_like_ours(kfo, kfb, kref):
         # (at 128^3 the reference algorithm itself drifts by centimetres from the ground truth: 23 mm voxels
         # and the raycast sign quirk, SURVEY.md 9 Q17 -- both implementations drift together)
         assert np.abs(ours.pose() - kfo.trajectory_pose(k)).max() < 0.1
+
+
+def _rot(axis, deg):
+    a = np.deg2rad(deg)
+    c, s = np.cos(a), np.sin(a)
+    R = {"x": [[1, 0, 0], [0, c, -s], [0, s, c]], "y": [[c, 0, s], [0, 1, 0], [-s, 0, c]], "z": [[c, -s, 0], [s, c, 0], [0, 0, 1]]}[axis]
+    return np.array(R, np.float64)
+
+
+def _pose12(R, t):
+    return np.concatenate([R, np.asarray(t, np.float64)[:, None]], axis=1).astype(np.float32).reshape(12)
+
+
+@pytest.mark.parametrize("sensor,case", [
+    ("kinect2", "yaw40_pitch25"),        # large rotation: every frustum plane changes its z-direction
+    ("realsense720", "roll90"),          # image rows along the volume's y axis, 1280x720
+    ("kinect1", "inside_volume"),        # camera inside the volume: vc.z <= 0 and ~0 planes (generic path)
+    ("kinect1", "looking_back"),         # volume traversed against its z axis (vc.z decreases with z)
+    ("kinect2", "wide_fov"),             # fx = 80: whole volume in view (dense-update micro-config geometry)
+])
+def test_integrate_raycast_bit_exact_geometries(kfo, kfb, kref, sensor, case):
+    """Culling (frustum interval, occlusion cut, column states, generic path) must never change a result:
+    volumes and raycasts equal the reference kernels' bit for bit under awkward geometries and all sensors."""
+    dims = 128
+    kw = dict(kfb.SENSORS[sensor])
+    if case == "wide_fov":
+        kw.update(fx=80.0, fy=80.0)
+    Ko, Kb = kfo.Intr(**kw), kfb.Intrinsics(**kw)
+    Pb = kfb.default_params(dims)
+    volpose = np.array(kfo.default_params(dims).volu_pose, np.float32)
+    if case == "yaw40_pitch25":
+        cams = [_pose12(_rot("y", 40) @ _rot("x", 25), [-1.0, 0.6, 0.2]), _pose12(_rot("y", -35) @ _rot("x", -20), [0.9, -0.5, 0.3])]
+    elif case == "roll90":
+        cams = [_pose12(_rot("z", 90), [0.05, 0.0, 0.0]), _pose12(_rot("z", 93) @ _rot("y", 4), [0.0, 0.05, 0.02])]
+    elif case == "inside_volume":
+        cams = [_pose12(_rot("y", 10), [0.1, 0.0, 1.0]), _pose12(_rot("x", -8), [0.0, 0.1, 1.2])]
+    elif case == "looking_back":
+        cams = [_pose12(_rot("y", 180), [0.0, 0.0, 4.0]), _pose12(_rot("y", 172) @ _rot("x", 5), [0.1, 0.0, 3.9])]
+    else:
+        cams = [kfo.identity(), kfo.trajectory_pose(20)]
+    ctx = kfb.Context(Kb, Pb)
+    rv = kref.RefVolume(dims)
+    rv.upload(np.zeros((dims, dims, dims, 2), np.int16))
+    rng = np.random.default_rng(11)
+    for cam in cams:
+        d = kfo.render_depth_mm(cam, Ko)
+        if case == "wide_fov":
+            d[:] = 4000.0
+        dm = kfo.frontend(d, Ko, levels=1)[0][0]
+        dm[rng.random(dm.shape) < 0.02] = 0.0
+        v2c = kfo.pose_mul(kfo.pose_inv(cam), volpose)
+        ctx.upload_depth_m(0, dm)
+        U = ctx.integrate(v2c, count=True)
+        rv.integrate(v2c, dm, Ko)
+        ours, ref = ctx.download_volume(), rv.download()
+        assert np.array_equal(ours, ref), (case, U)
+        assert U == int((ref[..., 1] > 0).sum()) or len(cams) > 1
+    assert (ref[..., 1] > 0).sum() > 1000
+    for cam in cams:
+        c2v = kfo.pose_mul(kfo.pose_inv(volpose), cam)
+        rinv = kfo.rot_inv(c2v)
+        ctx.raycast(c2v, rinv)
+        gv, gn = ctx.download_maps(1, 0)
+        wv, wn, _ = rv.raycast(c2v, rinv, Ko)
+        assert np.array_equal(gv.view(np.int32), wv.view(np.int32)), case
+        assert np.array_equal(gn.view(np.int32), wn.view(np.int32)), case
