@@ -38,6 +38,15 @@ UNIT = "voxel-updates/s"
 WEAK_DIMS = {1: 512, 2: 640, 4: 812, 8: 1024}
 
 
+def ncu_traffic():
+    """dram bytes per launch of the integrate kernel from the committed ncu --set full capture (profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_integrate_traffic.json")) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak_hbm():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -308,11 +317,11 @@ def run_ours(args):
                    "frames_timed": S, "updated_voxels_per_frame": U_mean, "swept_voxels_per_frame": swept},
         "frame_device_ms": ms_per_frame,
         "e2e": {"value": U_mean / (e2e_ms_per_frame * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_per_frame,
-                "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": 19 * 27 * 8,
+                "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": 19 * 27 * 16,
                 "api": "kf::kinectfusion::pipeline(depth_mm) via libkfusion_b200.so, pinned host frames"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "integrate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                      "kernel_ms": k_ms_mean, "algorithmic_bytes": 8.0 * U_mean,
                      "dense_model_gbs": 8.0 * swept / (k_ms_mean * 1e-3) / 1e9},
         "clocks": clocks,
