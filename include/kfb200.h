@@ -181,6 +181,10 @@ uint64_t kfb_launch_count(const kfb_ctx *ctx);
  * 4 raycast event keys (float) */
 void *kfb_device_ptr(kfb_ctx *ctx, int which);
 void *kfb_stream(kfb_ctx *ctx);
+/* debug: %globaltimer (ns) at the phase boundaries of the most recent ICP iteration of the persistent kernel, as
+ * seen by the reducing CTA: iteration entry, accumulation done, elected last, final sums ready, sums posted,
+ * next pose seen in the host gate, other CTAs released, (unused) */
+void kfb_debug_icp_stamps(kfb_ctx *ctx, uint64_t out8[8]);
 
 #ifdef __cplusplus
 }

@@ -108,6 +108,7 @@ def load_library():
         "kfb_launch_count": (C.c_uint64, [_vp]),
         "kfb_device_ptr": (_vp, [_vp, C.c_int]),
         "kfb_stream": (_vp, [_vp]),
+        "kfb_debug_icp_stamps": (None, [_vp, _vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -307,6 +308,11 @@ class Context:
 
     def device_ptr(self, which):
         return self.lib.kfb_device_ptr(self.h, which)
+
+    def debug_icp_stamps(self):
+        out = np.zeros(8, np.uint64)
+        self.lib.kfb_debug_icp_stamps(self.h, _ptr(out))
+        return out
 
     def stream(self):
         return self.lib.kfb_stream(self.h)

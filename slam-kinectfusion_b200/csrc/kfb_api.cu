@@ -526,5 +526,9 @@ void *kfb_device_ptr(kfb_ctx *ctx, int which)
     }
 }
 void *kfb_stream(kfb_ctx *ctx) { return (void *)ctx->stream; }
+void kfb_debug_icp_stamps(kfb_ctx *ctx, uint64_t out8[8])
+{
+    for (int i = 0; i < 8; ++i) out8[i] = ctx->icp_host->stamps[i];
+}
 
 } // extern "C"

@@ -34,7 +34,7 @@ struct IcpArgs
     unsigned long long seq;
 };
 
-#define ICP_THREADS 256
+#define ICP_THREADS 512
 
 // findCoresp (rigid_icp.cu:46-80) + row (rigid_icp.cu:85-95), split so that the loads of several pixels can
 // be in flight together: (1) current vertex/normal -> transformed point s and the model pixel it projects to,
@@ -288,10 +288,12 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_persistent_kernel(const IcpPe
             for (int i = 0; i < 9; ++i) a.pose.R.m[i] = spose[4 * (i / 3) + (i % 3)];
 #pragma unroll
             for (int i = 0; i < 3; ++i) a.pose.t[i] = spose[4 * i + 3];
+            const unsigned long long ts0 = globaltimer_ns();
             double acc[27];
 #pragma unroll
             for (int i = 0; i < 27; ++i) acc[i] = 0.0;
             icp_accumulate_pixels(a, acc, blockIdx.x * ICP_THREADS + threadIdx.x, gridDim.x * ICP_THREADS);
+            const unsigned long long ts1 = globaltimer_ns();
             const double s = icp_block_reduce(acc, sm);
             if (threadIdx.x < 27)
             {
@@ -308,9 +310,16 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_persistent_kernel(const IcpPe
             const bool last_iter = (k + 1 == P.total);
             if (is_last)
             {
+                const unsigned long long ts2 = globaltimer_ns();
                 __threadfence();
                 const double fin = icp_final_reduce(P.partials, (int)gridDim.x, red);
+                const unsigned long long ts3 = globaltimer_ns();
                 if (threadIdx.x < 27) icp_post(P.out, threadIdx.x, fin, seq);
+                if (threadIdx.x == 0)
+                {
+                    volatile unsigned long long *st = P.out->stamps; // debug hook, see kfb_debug_icp_stamps
+                    st[0] = ts0; st[1] = ts1; st[2] = ts2; st[3] = ts3; st[4] = globaltimer_ns();
+                }
                 if (threadIdx.x == 0 && !last_iter)
                 {
                     // Gate: four 16-byte chunks {3 pose floats, tag}; the host rewrites each chunk with one
@@ -340,9 +349,11 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_persistent_kernel(const IcpPe
                         d[4] = c1.x; d[5] = c1.y; d[6] = c1.z; d[7] = c3.y;
                         d[8] = c2.x; d[9] = c2.y; d[10] = c2.z; d[11] = c3.z;
                     }
+                    ((volatile unsigned long long *)P.out->stamps)[5] = globaltimer_ns(); // pose seen
                     __threadfence();
                     // release: seq = want (go) or want | 1<<63 (leave)
                     *(volatile unsigned long long *)&P.devgate->seq = ok ? want : (want | (1ull << 63));
+                    ((volatile unsigned long long *)P.out->stamps)[6] = globaltimer_ns();
                 }
             }
             if (last_iter) return;

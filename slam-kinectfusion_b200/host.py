@@ -53,6 +53,7 @@ def load_host_library():
         "kfh_extract_pointcloud": (C.c_long, [_vp, _vp, C.c_long]),
         "kfh_save_pointcloud": (C.c_int, [_vp, C.c_char_p]),
         "kfh_icp_solve": (C.c_int, [_vp, _vp]),
+        "kfh_icp_probe": (C.c_int, [_vp, _vp, _vp, C.c_int]),
         "kfh_set_shard_comm": (None, [_vp, BCAST_FN, COMPOSITE_FN, _vp]),
     }
     for name, (res, args) in sig.items():
@@ -66,6 +67,14 @@ def default_host_params(dims=512):
     p = HostParams()
     load_host_library().kfh_default_params(C.byref(p), int(dims))
     return p
+
+
+def icp_probe(ctx, iters=(4, 5, 10)):
+    """Wall-clock microseconds of every kfb_icp_step of one schedule, measured in C++ (diagnostic)."""
+    it = (C.c_int * KFB_MAX_LEVELS)(*list(iters) + [0] * (KFB_MAX_LEVELS - len(iters)))
+    out = np.zeros(64, np.float64)
+    n = load_host_library().kfh_icp_probe(ctx.h, it, out.ctypes.data_as(_vp), 64)
+    return out[:max(n, 0)]
 
 
 def icp_solve(sums27):

@@ -128,6 +128,26 @@ int kfh_save_pointcloud(void *h, const char *path)
     static_cast<kf::kinectfusion *>(h)->savePointcloud(path);
     return 0;
 }
+/* diagnostic: wall-clock microseconds of every kfb_icp_step of one schedule (identity poses, no solve) */
+int kfh_icp_probe(void *kfb_ctx_handle, const int *iters_per_level, double *us_out, int cap)
+{
+    kfb_ctx *ctx = static_cast<kfb_ctx *>(kfb_ctx_handle);
+    const float I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    int sched[KFB_MAX_LEVELS] = {0}, total = 0;
+    for (int l = 0; l < KFB_MAX_LEVELS; ++l) { sched[l] = iters_per_level[l]; total += sched[l]; }
+    if (kfb_icp_begin(ctx, sched) != KFB_OK) return -1;
+    double sums[27];
+    int n = 0;
+    for (int k = 0; k < total; ++k)
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        if (kfb_icp_step(ctx, I, sums) != KFB_OK) { kfb_icp_end(ctx); return -2; }
+        const std::chrono::duration<double, std::micro> dt = std::chrono::steady_clock::now() - t0;
+        if (n < cap) us_out[n++] = dt.count();
+    }
+    kfb_icp_end(ctx);
+    return n;
+}
 int kfh_icp_solve(const double in27[27], double x6[6]) { return kf::ICPRegistration::solve(in27, x6) ? 0 : 1; }
 
 } // extern "C"

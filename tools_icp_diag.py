@@ -21,3 +21,27 @@ for l in (2, 1, 0):
     for _ in range(50): ctx.icp_accumulate(l, I)
     print("direct level", l, (time.perf_counter() - t0) / 50 * 1e6, "us")
 
+
+from slam_kinectfusion_b200 import host as H
+for trial in range(3):
+    us = H.icp_probe(ctx)
+    print("C++ step us", [round(float(u), 1) for u in us], "total", round(float(us.sum()), 1))
+
+# phase stamps: step through a schedule, reading the stamps after each step (python-paced, so host gaps are long)
+ctx.icp_begin(iters)
+prev = None
+rows = []
+for k in range(19):
+    ctx.icp_step(I)
+    time.sleep(0.0005)
+    st = ctx.debug_icp_stamps().astype(np.int64)
+    rows.append(st.copy())
+ctx.icp_end()
+R = np.array(rows)
+print("acc ns", (R[:, 1] - R[:, 0]).tolist())
+print("reduce+ticket ns", (R[:, 2] - R[:, 1]).tolist())
+print("final ns", (R[:, 3] - R[:, 2]).tolist())
+print("post ns", (R[:, 4] - R[:, 3]).tolist())
+# stamps 5/6 of row k were written by the tail that preceded iteration k (the poll that fetched ITS pose)
+print("release ns (pose seen -> released)", (R[1:, 6] - R[1:, 5]).tolist())
+print("released -> entry ns", (R[1:, 0] - R[1:, 6]).tolist())
