@@ -96,6 +96,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->launches = 0;
     ctx->profiling = 0;
     ctx->icp_seq = 0;
+    ctx->pyramid_fresh = 0;
     ctx->vol = nullptr; ctx->cloud = nullptr; ctx->cloud_cap = 0;
     ctx->tab_thrz = nullptr; ctx->tab_exact = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->zmip = nullptr; ctx->bricks = nullptr; ctx->states = nullptr; ctx->states_bytes = 0;
     ctx->bdist = ctx->bdist_tmp = ctx->bdist_tmp2 = nullptr; ctx->bdirty = nullptr;
@@ -334,6 +335,7 @@ int kfb_frontend(kfb_ctx *ctx) { return launch_frontend(ctx); }
 int kfb_swap_frames(kfb_ctx *ctx)
 {
     KFB_JOIN(ctx);
+    ctx->pyramid_fresh = 0;
     const int t = ctx->cur; ctx->cur = ctx->prev; ctx->prev = t;
     return KFB_OK;
 }
@@ -461,6 +463,7 @@ int kfb_download_maps(kfb_ctx *ctx, int frame, int level, float *host_v3, float 
 int kfb_upload_maps(kfb_ctx *ctx, int frame, int level, const float *host_v3, const float *host_n3)
 {
     KFB_JOIN(ctx);
+    ctx->pyramid_fresh = 0;
     if (check_level(ctx, level)) return KFB_ERR_INVALID;
     const Level &L = ctx->L[level];
     const int f = frame == KFB_FRAME_CUR ? ctx->cur : ctx->prev;

@@ -270,6 +270,7 @@ int launch_frontend(kfb_ctx *ctx)
 
 int launch_model_pyramid(kfb_ctx *ctx)
 {
+    if (ctx->pyramid_fresh) { ctx->pyramid_fresh = 0; return KFB_OK; } // done by the raycast epilogue
     for (int l = 1; l < ctx->levels; ++l)
     {
         const Intr &s = ctx->L[l - 1].k, &d = ctx->L[l].k;

@@ -41,6 +41,8 @@ struct RaycastArgs
     int ts_sign_compat;
     const uint8_t *bdist;
     int bx, by, bz, bz0;
+    int fuse_pyramid;     // write levels 1 and 2 of the model maps from the warp tile (single-GPU, aligned image sizes)
+    float4 *pyr_v[2], *pyr_n[2];
 };
 
 #define KFB_RC_MAGIC_F 12582912.0f
@@ -327,6 +329,46 @@ __global__ void __launch_bounds__(32) raycast_kernel(const RaycastArgs a)
         a.nmap[pix] = nout;
         a.key[pix] = key;
     }
+    // ---- model pyramid (device::resizePointsNormals, image_process.cu:95-135) as an epilogue: the warp tile
+    // holds complete 2x2 and 4x4 pixel groups, so levels 1 and 2 come from register shuffles in the
+    // reference's summation order ((d00 + d01) + d10) + d11, * 0.25, zero when any vertex x is NaN.
+    if (a.fuse_pyramid)
+    {
+        const int lane = threadIdx.y * 8 + threadIdx.x;
+        float4 v = vout, n = nout;
+        int lw = a.k.w, lx = x, ly = y;
+#pragma unroll
+        for (int l = 1; l <= 2; ++l)
+        {
+            const int dxl = 1 << (l - 1), dyl = 8 << (l - 1); // lane distance of the +x / +y neighbour at this level
+            float4 v01, v10, v11, n01, n10, n11;
+            v01.x = __shfl_down_sync(FULL, v.x, dxl); v01.y = __shfl_down_sync(FULL, v.y, dxl); v01.z = __shfl_down_sync(FULL, v.z, dxl);
+            v10.x = __shfl_down_sync(FULL, v.x, dyl); v10.y = __shfl_down_sync(FULL, v.y, dyl); v10.z = __shfl_down_sync(FULL, v.z, dyl);
+            v11.x = __shfl_down_sync(FULL, v.x, dxl + dyl); v11.y = __shfl_down_sync(FULL, v.y, dxl + dyl); v11.z = __shfl_down_sync(FULL, v.z, dxl + dyl);
+            n01.x = __shfl_down_sync(FULL, n.x, dxl); n01.y = __shfl_down_sync(FULL, n.y, dxl); n01.z = __shfl_down_sync(FULL, n.z, dxl);
+            n10.x = __shfl_down_sync(FULL, n.x, dyl); n10.y = __shfl_down_sync(FULL, n.y, dyl); n10.z = __shfl_down_sync(FULL, n.z, dyl);
+            n11.x = __shfl_down_sync(FULL, n.x, dxl + dyl); n11.y = __shfl_down_sync(FULL, n.y, dxl + dyl); n11.z = __shfl_down_sync(FULL, n.z, dxl + dyl);
+            float4 vo = make_float4(0.f, 0.f, 0.f, 0.f), no = vo;
+            if (!isnan(__fmul_rn(__fmul_rn(__fmul_rn(v.x, v01.x), v10.x), v11.x)))
+            {
+                vo.x = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(v.x, v01.x), v10.x), v11.x), 0.25f);
+                vo.y = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(v.y, v01.y), v10.y), v11.y), 0.25f);
+                vo.z = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(v.z, v01.z), v10.z), v11.z), 0.25f);
+                no.x = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(n.x, n01.x), n10.x), n11.x), 0.25f);
+                no.y = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(n.y, n01.y), n10.y), n11.y), 0.25f);
+                no.z = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(n.z, n01.z), n10.z), n11.z), 0.25f);
+            }
+            v = vo; n = no;
+            lw >>= 1; lx >>= 1; ly >>= 1;
+            const int mask = (1 << l) - 1;
+            if (((threadIdx.x & mask) == 0) && ((threadIdx.y & mask) == 0))
+            {
+                a.pyr_v[l - 1][ly * lw + lx] = v;
+                a.pyr_n[l - 1][ly * lw + lx] = n;
+            }
+        }
+        (void)lane;
+    }
 }
 
 // cross-slab composite, step 2 (see include/kfb200.h): keep the payload only where this slab holds the
@@ -379,6 +421,14 @@ int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9]
     a.ts_sign_compat = ctx->p.compat_raycast_ts_sign;
     a.bdist = ctx->bdist;
     a.bx = ctx->bdim[0]; a.by = ctx->bdim[1]; a.bz = ctx->bdim[2]; a.bz0 = ctx->bz0;
+    // the model pyramid rides along when the tile grid is exact and nothing has to be composited first
+    a.fuse_pyramid = (!slab && ctx->levels == 3 && a.k.w % 8 == 0 && a.k.h % 4 == 0 && !getenv("KFB_RAYCAST_NOFUSE")) ? 1 : 0;
+    for (int l = 1; l <= 2; ++l)
+    {
+        a.pyr_v[l - 1] = a.fuse_pyramid ? ctx->L[l].v[ctx->prev] : nullptr;
+        a.pyr_n[l - 1] = a.fuse_pyramid ? ctx->L[l].n[ctx->prev] : nullptr;
+    }
+    ctx->pyramid_fresh = a.fuse_pyramid;
     dim3 block(8, 4), grid((a.k.w + 7) / 8, (a.k.h + 3) / 4);
     if (ctx->profiling) cudaEventRecord(ctx->events[58], ctx->stream);
     raycast_kernel<<<grid, block, 0, ctx->stream>>>(a);
