@@ -114,10 +114,14 @@ int kfb_icp_accumulate(kfb_ctx *ctx, int level, const float pose12[12], double o
 /* The same operation for the whole coarse-to-fine loop of ICPRegistration::rigidTransform
  * (icp_registration.cpp:21-43) without per-iteration launch latency: kfb_icp_begin declares the
  * schedule (iters_per_level[l] iterations at level l, coarsest level first); the first kfb_icp_step
- * starts ONE persistent kernel that runs every iteration, waiting on the GPU until kfb_icp_step publishes
- * that iteration's pose in mapped host memory and posting its 27 sums back; the host solves 6x6 between
- * steps exactly as with kfb_icp_accumulate.  kfb_icp_end retires any iterations not stepped (tracking
- * failure). */
+ * starts ONE persistent kernel that runs every iteration and posts its 27 sums into mapped host memory; the
+ * host solves 6x6 between steps exactly as with kfb_icp_accumulate and publishes each pose in mapped host
+ * memory.  The kernel does not wait for that round trip: it predicts the pose with the host's arithmetic and
+ * verifies the prediction bit for bit against the host's pose one iteration later (repeating the iteration on
+ * a mismatch), so every step returns exactly what kfb_icp_accumulate would for the pose passed in -- PROVIDED
+ * the caller's update is the reference's (icp_registration.cpp:35-42: solve, Rodrigues, pose * Tinc); any other
+ * update rule is still handled correctly, through mispredictions.  KFB_ICP_NOSPEC=1 disables the prediction.
+ * kfb_icp_end retires any iterations not stepped (tracking failure). */
 int kfb_icp_begin(kfb_ctx *ctx, const int iters_per_level[KFB_MAX_LEVELS]);
 int kfb_icp_step(kfb_ctx *ctx, const float pose12[12], double out27[27]);
 int kfb_icp_end(kfb_ctx *ctx);
@@ -183,8 +187,10 @@ void *kfb_device_ptr(kfb_ctx *ctx, int which);
 void *kfb_stream(kfb_ctx *ctx);
 /* debug: %globaltimer (ns) at the phase boundaries of the most recent ICP iteration of the persistent kernel, as
  * seen by the reducing CTA: iteration entry, accumulation done, elected last, final sums ready, sums posted,
- * next pose seen in the host gate, other CTAs released, (unused) */
+ * orders for the next round ready, other CTAs released, number of mispredicted (repeated) iterations since creation */
 void kfb_debug_icp_stamps(kfb_ctx *ctx, uint64_t out8[8]);
+/* debug: per iteration (row = iteration index % 32) {entry, final sums ready, validated + posted, grid released} */
+void kfb_debug_icp_ring(kfb_ctx *ctx, uint64_t out128[128]);
 
 #ifdef __cplusplus
 }

@@ -109,6 +109,7 @@ def load_library():
         "kfb_device_ptr": (_vp, [_vp, C.c_int]),
         "kfb_stream": (_vp, [_vp]),
         "kfb_debug_icp_stamps": (None, [_vp, _vp]),
+        "kfb_debug_icp_ring": (None, [_vp, _vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -312,6 +313,11 @@ class Context:
     def debug_icp_stamps(self):
         out = np.zeros(8, np.uint64)
         self.lib.kfb_debug_icp_stamps(self.h, _ptr(out))
+        return out
+
+    def debug_icp_ring(self):
+        out = np.zeros((32, 4), np.uint64)
+        self.lib.kfb_debug_icp_ring(self.h, _ptr(out))
         return out
 
     def stream(self):

@@ -104,7 +104,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->counters_host = nullptr; ctx->pinned_depth = nullptr; ctx->render_dev = nullptr; ctx->render_host = nullptr;
     ctx->stream = nullptr; ctx->own_stream = 1;
     ctx->fstream = nullptr; ctx->ev_front = nullptr; ctx->ev_free = nullptr; ctx->ev_tables_free = nullptr; ctx->front_pending = 0;
-    ctx->icp_host = nullptr; ctx->icp_gate_host = nullptr; ctx->icp_devgate = nullptr;
+    ctx->icp_host = nullptr; ctx->icp_gate_host = nullptr; ctx->icp_devgate = nullptr; ctx->icp_mirror = nullptr;
     memset(ctx->L, 0, sizeof(ctx->L));
     memset(ctx->events, 0, sizeof(ctx->events));
     *out = ctx; // returned even on failure so the caller can read the error string, then destroy
@@ -191,6 +191,9 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     memset(&ctx->icp_sched, 0, sizeof(ctx->icp_sched));
     KFB_CUDA(ctx, cudaMalloc(&ctx->icp_devgate, sizeof(IcpDevGate)));
     KFB_CUDA(ctx, cudaMemset(ctx->icp_devgate, 0, sizeof(IcpDevGate)));
+    KFB_CUDA(ctx, cudaMalloc(&ctx->icp_mirror, 8192));
+    KFB_CUDA(ctx, cudaMemset(ctx->icp_mirror, 0, 8192));
+    ctx->icp_round = 0;
     KFB_CUDA(ctx, cudaMalloc(&ctx->counters, 8 * sizeof(unsigned long long)));
     KFB_CUDA(ctx, cudaMemset(ctx->counters, 0, 8 * sizeof(unsigned long long)));
     KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->counters_host, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
@@ -243,6 +246,7 @@ void kfb_destroy(kfb_ctx *ctx)
     if (ctx->icp_host) cudaFreeHost((void *)ctx->icp_host);
     if (ctx->icp_gate_host) cudaFreeHost((void *)ctx->icp_gate_host);
     if (ctx->icp_devgate) cudaFree(ctx->icp_devgate);
+    if (ctx->icp_mirror) cudaFree(ctx->icp_mirror);
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->counters_host) cudaFreeHost(ctx->counters_host);
     if (ctx->pinned_depth) cudaFreeHost(ctx->pinned_depth);
@@ -532,6 +536,10 @@ void *kfb_stream(kfb_ctx *ctx) { return (void *)ctx->stream; }
 void kfb_debug_icp_stamps(kfb_ctx *ctx, uint64_t out8[8])
 {
     for (int i = 0; i < 8; ++i) out8[i] = ctx->icp_host->stamps[i];
+}
+void kfb_debug_icp_ring(kfb_ctx *ctx, uint64_t out128[128])
+{
+    for (int i = 0; i < 128; ++i) out128[i] = ctx->icp_host->post_ns[i / 4][i % 4];
 }
 
 } // extern "C"

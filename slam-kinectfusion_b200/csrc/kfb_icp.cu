@@ -34,7 +34,8 @@ struct IcpArgs
     unsigned long long seq;
 };
 
-#define ICP_THREADS 512
+#define ICP_THREADS 480                 // worker threads of a CTA (15 warps); the persistent kernel adds one service warp
+#define ICP_BAR() asm volatile("bar.sync 1, 480;" ::: "memory") // barrier over the workers only
 
 // findCoresp (rigid_icp.cu:46-80) + row (rigid_icp.cu:85-95), split so that the loads of several pixels can
 // be in flight together: (1) current vertex/normal -> transformed point s and the model pixel it projects to,
@@ -165,7 +166,7 @@ __device__ __forceinline__ double icp_block_reduce(double acc[27], double (*sm)[
         }
     }
     if (lane < 27) sm[warp][lane] = v[0];
-    __syncthreads();
+    ICP_BAR();
     double s = 0.0;
     if (threadIdx.x < 27)
     {
@@ -196,7 +197,7 @@ __device__ __forceinline__ double icp_final_reduce(const double *partials, int n
         for (; bb < nb; bb += stride) s0 += __ldcg(partials + (size_t)bb * 27 + v);
         red[slice][v] = (s0 + s1) + (s2 + s3);
     }
-    __syncthreads();
+    ICP_BAR();
     double fin = 0.0;
     if (threadIdx.x < 27)
     {
@@ -228,13 +229,13 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpArgs a)
         a.partials[(size_t)blockIdx.x * 27 + threadIdx.x] = s;
         __threadfence();
     }
-    __syncthreads();
+    ICP_BAR();
     if (threadIdx.x == 0)
     {
         const unsigned int t = atomicInc(a.ticket, gridDim.x - 1); // wraps to 0 on the last block
         is_last = (t == gridDim.x - 1);
     }
-    __syncthreads();
+    ICP_BAR();
     if (!is_last) return;
     __threadfence();
     const double fin = icp_final_reduce(a.partials, (int)gridDim.x, red);
@@ -242,13 +243,24 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpArgs a)
 }
 
 // ---- the whole coarse-to-fine loop in ONE persistent kernel ----------------------------------------------
-// kfb_icp_begin/step/end: the grid (one CTA per SM, all co-resident) runs every iteration of the
-// schedule.  Per iteration: all CTAs accumulate their pixels and publish a partial; the last CTA to arrive
-// (ticket) reduces, posts the 27 tagged sums to mapped host memory, then ONE thread polls the host's mapped
-// gate for the next pose (or an abort) -- exactly one PCIe reader -- and releases the other CTAs through a
-// device-memory gate they spin on.  No kernel boundary, no launch and no system fence sits between the host's
-// 6x6 solve and the next accumulation.  The poll is bounded (KFB_ICP_GATE_TIMEOUT_NS): on timeout or abort
-// every CTA leaves.
+// kfb_icp_begin/step/end: the grid (one CTA per SM, all co-resident) runs every iteration of the schedule.
+// Per iteration: all CTAs accumulate their pixels and publish a partial; the last CTA to arrive (ticket)
+// reduces and posts the 27 tagged sums to mapped host memory, where the host does the reference's 6x6 solve
+// and publishes the next pose in its mapped gate.  The PCIe round trip of that exchange is taken off the
+// critical path by SPECULATION: the last CTA also solves the system itself, with the host's operations in the
+// host's order (IEEE double add/mul/div/sqrt are exactly rounded on both sides; only sin/cos may differ in the
+// last bit, which survives the cast to float with probability ~2^-29), and releases the grid with that pose at
+// once.  A service warp of CTA 0 -- the only PCIe reader -- mirrors each pose the host publishes into device
+// memory; at the end of a speculative iteration the pose it used is compared, bit for bit, with the host's:
+// equal => its sums are posted, different => the iteration is repeated with the host's pose.  The host's solve
+// stays authoritative and every result equals the non-speculative schedule's (KFB_ICP_NOSPEC=1 runs that).
+// Polls are bounded (KFB_ICP_GATE_TIMEOUT_NS); on timeout or abort every CTA leaves.
+#define ICP_MIRROR_RING 64
+struct IcpMirror // device memory, written by the service warp
+{
+    unsigned long long tag[ICP_MIRROR_RING];   // seq of the iteration the pose is for; | 1<<63 = abort
+    float pose[ICP_MIRROR_RING][12];
+};
 struct IcpPersistArgs
 {
     IcpLevel lv[KFB_MAX_LEVELS];
@@ -260,122 +272,311 @@ struct IcpPersistArgs
     IcpHostResult *out;
     const IcpHostGate *gate;
     IcpDevGate *devgate;
+    IcpMirror *mirror;
     unsigned long long seq0;   // iteration k carries sequence number seq0 + k + 1
+    unsigned long long round0; // release counter base (monotonic across schedules)
+    int speculate;
     float pose0[12];
 };
 
-__global__ void __launch_bounds__(ICP_THREADS) icp_persistent_kernel(const IcpPersistArgs P)
+// the host's ICPRegistration::solve (LDL^T branch) + Tinc + camera_pose * Tinc (kfusion/src/icp_registration.cpp,
+// cvlite.hpp), operation for operation.  false: the system is not numerically positive definite (no prediction).
+__device__ __noinline__ bool icp_predict_pose(const double *in27, const float *cur, float *out)
+{
+    double A[6][6], b[6], L[6][6], d[6], inv[6], t[6][6], z[6], x[6];
+    {
+        int s = 0;
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = i; j < 7; ++j)
+            {
+                const double v = in27[s++];
+                if (j == 6) b[i] = v;
+                else A[i][j] = A[j][i] = v;
+            }
+    }
+    // A = L D L^T with one reciprocal per column, the host's sequence (icp_registration.cpp: solve)
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+    {
+        double dj = A[j][j];
+#pragma unroll
+        for (int q = 0; q < j; ++q) { t[j][q] = __dmul_rn(L[j][q], d[q]); dj = __dsub_rn(dj, __dmul_rn(L[j][q], t[j][q])); }
+        if (!(dj > 0.0)) return false;
+        d[j] = dj;
+        inv[j] = __ddiv_rn(1.0, dj);
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i)
+        {
+            double sum = A[i][j];
+#pragma unroll
+            for (int q = 0; q < j; ++q) sum = __dsub_rn(sum, __dmul_rn(L[i][q], t[j][q]));
+            L[i][j] = __dmul_rn(sum, inv[j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+    {
+        double sum = b[i];
+#pragma unroll
+        for (int q = 0; q < i; ++q) sum = __dsub_rn(sum, __dmul_rn(L[i][q], z[q]));
+        z[i] = sum;
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i)
+    {
+        double sum = __dmul_rn(z[i], inv[i]);
+#pragma unroll
+        for (int q = i + 1; q < 6; ++q) sum = __dsub_rn(sum, __dmul_rn(L[q][i], x[q]));
+        x[i] = sum;
+    }
+    // Tinc = Affine3f(rvec = (float)x[0..2], t = (float)x[3..5]): Rodrigues in double, stored as float
+    float T[12] = {1.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
+    const double rx = (double)(float)x[0], ry = (double)(float)x[1], rz = (double)(float)x[2];
+    const double theta = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry)), __dmul_rn(rz, rz)));
+    if (theta >= 2.220446049250313e-16)
+    {
+        double sn, c;
+        sincos(theta, &sn, &c);
+        const double c1 = __dsub_rn(1.0, c), it = __ddiv_rn(1.0, theta);
+        const double ux = __dmul_rn(rx, it), uy = __dmul_rn(ry, it), uz = __dmul_rn(rz, it);
+        const double xx = __dmul_rn(__dmul_rn(c1, ux), ux), yy = __dmul_rn(__dmul_rn(c1, uy), uy), zz = __dmul_rn(__dmul_rn(c1, uz), uz);
+        const double xy = __dmul_rn(__dmul_rn(c1, ux), uy), xz = __dmul_rn(__dmul_rn(c1, ux), uz), yz = __dmul_rn(__dmul_rn(c1, uy), uz);
+        const double sx = __dmul_rn(sn, ux), sy = __dmul_rn(sn, uy), sz = __dmul_rn(sn, uz);
+        T[0] = (float)__dadd_rn(c, xx);  T[1] = (float)__dsub_rn(xy, sz); T[2] = (float)__dadd_rn(xz, sy);
+        T[4] = (float)__dadd_rn(xy, sz); T[5] = (float)__dadd_rn(c, yy);  T[6] = (float)__dsub_rn(yz, sx);
+        T[8] = (float)__dsub_rn(xz, sy); T[9] = (float)__dadd_rn(yz, sx); T[10] = (float)__dadd_rn(c, zz);
+    }
+    T[3] = (float)x[3]; T[7] = (float)x[4]; T[11] = (float)x[5];
+    // camera_pose * Tinc (cvlite.hpp operator*): s = 0; s += a(i,q) * b(q,j) for q = 0..2; j == 3: s += a(i,3)
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 4; ++j)
+        {
+            float acc = 0.f;
+            for (int q = 0; q < 3; ++q) acc = __fadd_rn(acc, __fmul_rn(cur[4 * i + q], T[4 * q + j]));
+            if (j == 3) acc = __fadd_rn(acc, cur[4 * i + 3]);
+            out[4 * i + j] = acc;
+        }
+    return true;
+}
+
+enum { ICP_CMD_RUN = 0, ICP_CMD_LEAVE = 1 };
+
+__global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const IcpPersistArgs P)
 {
     __shared__ double sm[ICP_THREADS / 32][27];
     __shared__ double red[ICP_THREADS / 32][28];
+    __shared__ double fin27[27];
     __shared__ bool is_last;
-    __shared__ int go;          // 1: pose valid, 0: leave
-    __shared__ float spose[12];
+    __shared__ int s_cmd, s_iter, s_spec, s_ok, s_pred;
+    __shared__ float spose[12], npose[12], hpose[12];
+
+    // ---- service warp: CTA 0 mirrors the host's poses into device memory; elsewhere it has nothing to do -------
+    if (threadIdx.x >= ICP_THREADS)
+    {
+        if (blockIdx.x != 0 || threadIdx.x != ICP_THREADS) return;
+        for (int j = 1; j < P.total; ++j)
+        {
+            // Gate: four 16-byte chunks {3 pose floats, tag}; the host rewrites each chunk with one aligned
+            // 16-byte store and the tag is the low 32 bits of the sequence number, so a chunk is either wholly
+            // old or wholly new and one poll (4 loads in flight) yields a consistent pose.
+            const unsigned long long want = P.seq0 + (unsigned long long)j + 1ull;
+            const unsigned int tag = (unsigned int)want;
+            const unsigned long long t0 = globaltimer_ns();
+            bool ok = false;
+            float4 c0, c1, c2, c3;
+            for (;;)
+            {
+                c0 = ld_volatile_f4(P.gate->chunk);
+                c1 = ld_volatile_f4(P.gate->chunk + 4);
+                c2 = ld_volatile_f4(P.gate->chunk + 8);
+                c3 = ld_volatile_f4(P.gate->chunk + 12);
+                const unsigned long long ab = ld_volatile_u64(&P.gate->abort_upto);
+                if (ab >= want) break;
+                if (__float_as_uint(c0.w) == tag && __float_as_uint(c1.w) == tag && __float_as_uint(c2.w) == tag &&
+                    __float_as_uint(c3.w) == tag) { ok = true; break; }
+                if (globaltimer_ns() - t0 > KFB_ICP_GATE_TIMEOUT_NS) break;
+            }
+            if (!ok)
+            {
+                // abort / timeout: every pose still awaited is answered with "leave"
+                for (int r = j; r < P.total; ++r)
+                    *(volatile unsigned long long *)&P.mirror->tag[r % ICP_MIRROR_RING] = (P.seq0 + (unsigned long long)r + 1ull) | (1ull << 63);
+                return;
+            }
+            volatile float *d = P.mirror->pose[j % ICP_MIRROR_RING]; // chunk r = {R[r][0..2]}, chunk 3 = t
+            d[0] = c0.x; d[1] = c0.y; d[2] = c0.z; d[3] = c3.x;
+            d[4] = c1.x; d[5] = c1.y; d[6] = c1.z; d[7] = c3.y;
+            d[8] = c2.x; d[9] = c2.y; d[10] = c2.z; d[11] = c3.z;
+            __threadfence();
+            *(volatile unsigned long long *)&P.mirror->tag[j % ICP_MIRROR_RING] = want;
+        }
+        return;
+    }
+
+    // ---- workers --------------------------------------------------------------------------------------------
     IcpArgs a;
     a.dist_thres = P.dist_thres; a.sine_thres = P.sine_thres;
     if (threadIdx.x < 12) spose[threadIdx.x] = P.pose0[threadIdx.x];
-    __syncthreads();
-    int k = 0;
-    for (int level = P.levels - 1; level >= 0; --level)
+    int k = 0, spec_used = 0;
+    unsigned long long round = P.round0;
+    ICP_BAR();
+    for (;;)
     {
+        // level of iteration k (coarse to fine)
+        int level = P.levels - 1, kk = k;
+        while (level > 0 && kk >= P.iters[level]) { kk -= P.iters[level]; --level; }
         const IcpLevel &L = P.lv[level];
         a.cur_v = L.cur_v; a.cur_n = L.cur_n; a.pre_v = L.pre_v; a.pre_n = L.pre_n;
         a.k = L.k; a.cov_w = L.cov_w; a.cov_h = L.cov_h;
-        for (int it = 0; it < P.iters[level]; ++it, ++k)
+        const unsigned long long seq = P.seq0 + (unsigned long long)k + 1ull;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) a.pose.R.m[i] = spose[4 * (i / 3) + (i % 3)];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) a.pose.t[i] = spose[4 * i + 3];
+        const unsigned long long ts0 = globaltimer_ns();
+        double acc[27];
+#pragma unroll
+        for (int i = 0; i < 27; ++i) acc[i] = 0.0;
+        icp_accumulate_pixels(a, acc, blockIdx.x * ICP_THREADS + threadIdx.x, gridDim.x * ICP_THREADS);
+        const unsigned long long ts1 = globaltimer_ns();
+        const double s = icp_block_reduce(acc, sm);
+        if (threadIdx.x < 27)
         {
-            const unsigned long long seq = P.seq0 + (unsigned long long)k + 1ull;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) a.pose.R.m[i] = spose[4 * (i / 3) + (i % 3)];
-#pragma unroll
-            for (int i = 0; i < 3; ++i) a.pose.t[i] = spose[4 * i + 3];
-            const unsigned long long ts0 = globaltimer_ns();
-            double acc[27];
-#pragma unroll
-            for (int i = 0; i < 27; ++i) acc[i] = 0.0;
-            icp_accumulate_pixels(a, acc, blockIdx.x * ICP_THREADS + threadIdx.x, gridDim.x * ICP_THREADS);
-            const unsigned long long ts1 = globaltimer_ns();
-            const double s = icp_block_reduce(acc, sm);
-            if (threadIdx.x < 27)
-            {
-                P.partials[(size_t)blockIdx.x * 27 + threadIdx.x] = s;
-                __threadfence();
-            }
-            __syncthreads();
+            P.partials[(size_t)blockIdx.x * 27 + threadIdx.x] = s;
+            __threadfence();
+        }
+        ICP_BAR();
+        if (threadIdx.x == 0)
+        {
+            const unsigned int t = atomicInc(P.ticket, gridDim.x - 1);
+            is_last = (t == gridDim.x - 1);
+        }
+        ICP_BAR();
+        if (is_last)
+        {
+            const unsigned long long ts2 = globaltimer_ns();
+            __threadfence();
+            const double fin = icp_final_reduce(P.partials, (int)gridDim.x, red);
+            if (threadIdx.x < 27) fin27[threadIdx.x] = fin;
+            const unsigned long long ts3 = globaltimer_ns();
+            ICP_BAR(); // fin27 visible
+            // (1) thread 0: a speculative iteration is only as good as its pose -- compare with the host's, bit for
+            //     bit (hpose = the host's pose for this iteration).  Concurrently thread 32 (another warp) predicts
+            //     the next pose from the sums; the prediction is only used if (1) passes.
             if (threadIdx.x == 0)
             {
-                const unsigned int t = atomicInc(P.ticket, gridDim.x - 1);
-                is_last = (t == gridDim.x - 1);
+                int ok = 1, cmd = ICP_CMD_RUN;
+                if (spec_used)
+                {
+                    const int slot = k % ICP_MIRROR_RING;
+                    const unsigned long long t0 = globaltimer_ns();
+                    unsigned long long v;
+                    for (;;)
+                    {
+                        v = ld_volatile_u64(&P.mirror->tag[slot]);
+                        if ((v & ~(1ull << 63)) == seq) break;
+                        if (globaltimer_ns() - t0 > 2ull * KFB_ICP_GATE_TIMEOUT_NS) { v = 1ull << 63; break; }
+                    }
+                    if (v >> 63) cmd = ICP_CMD_LEAVE;
+                    else
+                    {
+                        for (int i = 0; i < 12; ++i)
+                        {
+                            const float h = __ldcg(&P.mirror->pose[slot][i]);
+                            hpose[i] = h;
+                            if (__float_as_uint(h) != __float_as_uint(spose[i])) ok = 0;
+                        }
+                    }
+                }
+                s_ok = ok; s_cmd = cmd;
             }
-            __syncthreads();
-            const bool last_iter = (k + 1 == P.total);
-            if (is_last)
+            if (threadIdx.x == 32) s_pred = (P.speculate && k + 1 < P.total) ? (icp_predict_pose(fin27, spose, npose) ? 1 : 0) : 0;
+            ICP_BAR();
+            if (s_cmd == ICP_CMD_RUN && s_ok)
             {
-                const unsigned long long ts2 = globaltimer_ns();
-                __threadfence();
-                const double fin = icp_final_reduce(P.partials, (int)gridDim.x, red);
-                const unsigned long long ts3 = globaltimer_ns();
-                if (threadIdx.x < 27) icp_post(P.out, threadIdx.x, fin, seq);
+                if (threadIdx.x < 27) icp_post(P.out, threadIdx.x, fin27[threadIdx.x], seq);
                 if (threadIdx.x == 0)
                 {
                     volatile unsigned long long *st = P.out->stamps; // debug hook, see kfb_debug_icp_stamps
                     st[0] = ts0; st[1] = ts1; st[2] = ts2; st[3] = ts3; st[4] = globaltimer_ns();
-                }
-                if (threadIdx.x == 0 && !last_iter)
-                {
-                    // Gate: four 16-byte chunks {3 pose floats, tag}; the host rewrites each chunk with one
-                    // aligned 16-byte store and the tag is the low 32 bits of the sequence number, so a chunk is
-                    // either wholly old or wholly new and one poll (4 loads in flight) yields a consistent pose.
-                    const unsigned long long want = seq + 1ull;
-                    const unsigned int tag = (unsigned int)want;
-                    const unsigned long long t0 = globaltimer_ns();
-                    bool ok = false;
-                    float4 c0, c1, c2, c3;
-                    for (;;)
-                    {
-                        c0 = ld_volatile_f4(P.gate->chunk);
-                        c1 = ld_volatile_f4(P.gate->chunk + 4);
-                        c2 = ld_volatile_f4(P.gate->chunk + 8);
-                        c3 = ld_volatile_f4(P.gate->chunk + 12);
-                        const unsigned long long ab = ld_volatile_u64(&P.gate->abort_upto);
-                        if (ab >= want) break;
-                        if (__float_as_uint(c0.w) == tag && __float_as_uint(c1.w) == tag && __float_as_uint(c2.w) == tag &&
-                            __float_as_uint(c3.w) == tag) { ok = true; break; }
-                        if (globaltimer_ns() - t0 > KFB_ICP_GATE_TIMEOUT_NS) break;
-                    }
-                    float *d = P.devgate->pose; // chunk r = {R[r][0..2]}, chunk 3 = t
-                    if (ok)
-                    {
-                        d[0] = c0.x; d[1] = c0.y; d[2] = c0.z; d[3] = c3.x;
-                        d[4] = c1.x; d[5] = c1.y; d[6] = c1.z; d[7] = c3.y;
-                        d[8] = c2.x; d[9] = c2.y; d[10] = c2.z; d[11] = c3.z;
-                    }
-                    ((volatile unsigned long long *)P.out->stamps)[5] = globaltimer_ns(); // pose seen
-                    __threadfence();
-                    // release: seq = want (go) or want | 1<<63 (leave)
-                    *(volatile unsigned long long *)&P.devgate->seq = ok ? want : (want | (1ull << 63));
-                    ((volatile unsigned long long *)P.out->stamps)[6] = globaltimer_ns();
+                    volatile unsigned long long *pr = P.out->post_ns[k & 31];
+                    pr[0] = ts0; pr[1] = ts3; pr[2] = st[4];
                 }
             }
-            if (last_iter) return;
-            // every CTA (the last one included) picks the next pose up from the device gate
+            // (2) decide what the grid does next
             if (threadIdx.x == 0)
             {
-                const unsigned long long want = seq + 1ull;
-                unsigned long long v;
-                const unsigned long long t0 = globaltimer_ns();
-                for (;;)
+                int cmd = s_cmd, iter = k, spec = 0;
+                const float *next = npose;
+                if (cmd == ICP_CMD_RUN)
                 {
-                    v = ld_volatile_u64(&P.devgate->seq);
-                    if ((v & ~(1ull << 63)) == want) break;
-                    if (globaltimer_ns() - t0 > 2ull * KFB_ICP_GATE_TIMEOUT_NS) { v = 1ull << 63; break; }
+                    if (!s_ok)
+                    {
+                        iter = k; spec = 0; next = hpose;                 // repeat iteration k with the host's pose
+                        ((volatile unsigned long long *)P.out->stamps)[7] += 1ull; // debug: mispredictions since creation
+                    }
+                    else if (k + 1 == P.total) cmd = ICP_CMD_LEAVE;       // schedule complete
+                    else
+                    {
+                        iter = k + 1;
+                        spec = s_pred;
+                        if (!spec)
+                        {
+                            // no prediction: wait for the host's pose (mirrored by the service warp)
+                            const int slot = iter % ICP_MIRROR_RING;
+                            const unsigned long long want = seq + 1ull, t0 = globaltimer_ns();
+                            unsigned long long v;
+                            for (;;)
+                            {
+                                v = ld_volatile_u64(&P.mirror->tag[slot]);
+                                if ((v & ~(1ull << 63)) == want) break;
+                                if (globaltimer_ns() - t0 > 2ull * KFB_ICP_GATE_TIMEOUT_NS) { v = 1ull << 63; break; }
+                            }
+                            if (v >> 63) cmd = ICP_CMD_LEAVE;
+                            else
+                            {
+                                for (int i = 0; i < 12; ++i) hpose[i] = __ldcg(&P.mirror->pose[slot][i]);
+                                next = hpose;
+                            }
+                        }
+                    }
                 }
-                go = (v >> 63) ? 0 : 1;
+                volatile IcpDevGate *g = P.devgate;
+                for (int i = 0; i < 12; ++i) g->pose[i] = next[i];
+                g->cmd = cmd; g->iter = iter; g->spec = spec;
+                ((volatile unsigned long long *)P.out->stamps)[5] = globaltimer_ns();
+                __threadfence();
+                g->seq = round + 1ull; // release
+                ((volatile unsigned long long *)P.out->stamps)[6] = globaltimer_ns();
+                ((volatile unsigned long long *)P.out->post_ns[k & 31])[3] = globaltimer_ns();
             }
-            __syncthreads();
-            if (!go) return;
-            if (threadIdx.x < 12) spose[threadIdx.x] = __ldcg(P.devgate->pose + threadIdx.x);
-            __syncthreads();
         }
+        // every CTA (the last one included) picks its orders up from the device gate
+        if (threadIdx.x == 0)
+        {
+            const unsigned long long want = round + 1ull, t0 = globaltimer_ns();
+            int cmd = ICP_CMD_RUN;
+            for (;;)
+            {
+                if (ld_volatile_u64(&P.devgate->seq) == want) break;
+                if (globaltimer_ns() - t0 > 3ull * KFB_ICP_GATE_TIMEOUT_NS) { cmd = ICP_CMD_LEAVE; break; }
+            }
+            if (cmd == ICP_CMD_RUN)
+            {
+                cmd = __ldcg(&P.devgate->cmd);
+                s_iter = __ldcg(&P.devgate->iter);
+                s_spec = __ldcg(&P.devgate->spec);
+            }
+            s_cmd = cmd;
+        }
+        ICP_BAR();
+        if (s_cmd != ICP_CMD_RUN) return;
+        if (threadIdx.x < 12) spose[threadIdx.x] = __ldcg(P.devgate->pose + threadIdx.x);
+        k = s_iter; spec_used = s_spec;
+        ++round;
+        ICP_BAR();
     }
 }
 
@@ -492,12 +693,16 @@ static int icp_launch_persistent(kfb_ctx *ctx, const float pose12[12])
     P.out = ctx->icp_dev;
     P.gate = ctx->icp_gate_dev;
     P.devgate = ctx->icp_devgate;
+    P.mirror = (IcpMirror *)ctx->icp_mirror;
     P.seq0 = S.seq0;
+    P.round0 = ctx->icp_round;
+    ctx->icp_round += (unsigned long long)(4 * S.total + 8); // rounds this launch can consume (repeats included)
+    P.speculate = getenv("KFB_ICP_NOSPEC") ? 0 : 1;
     memcpy(P.pose0, pose12, sizeof(P.pose0));
     // every CTA must be resident at once (they wait on each other): one per SM (see icp_setup)
     const int blocks = ctx->sm_count;
     (void)max_pix;
-    icp_persistent_kernel<<<blocks, ICP_THREADS, 0, ctx->stream>>>(P);
+    icp_persistent_kernel<<<blocks, ICP_THREADS + 32, 0, ctx->stream>>>(P);
     KFB_LAUNCH_CHECK(ctx);
     S.enq = S.total;
     return KFB_OK;

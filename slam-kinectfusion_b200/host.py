@@ -46,6 +46,7 @@ def load_host_library():
         "kfh_reset": (None, [_vp]),
         "kfh_pipeline": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
         "kfh_frame_count": (C.c_int, [_vp]),
+        "kfh_last_icp_us": (C.c_double, [_vp]),
         "kfh_num_poses": (C.c_int, [_vp]),
         "kfh_get_pose": (None, [_vp, C.c_int, _vp]),
         "kfh_context": (_vp, [_vp]),
@@ -137,6 +138,9 @@ class KinectFusion:
 
     def reset(self):
         self.lib.kfh_reset(self.h)
+
+    def last_icp_us(self):
+        return self.lib.kfh_last_icp_us(self.h)
 
     @property
     def frame_count(self):

@@ -87,6 +87,7 @@ public:
     int frame_count;
     std::vector<cv::Affine3f> pose_record;
     bool last_tracking_ok = true;
+    double last_icp_us = 0.0; // wall time of the last ICPRegistration::rigidTransform (diagnostic)
 
 private:
     void imageProcess(const float *depth_mm, int width, int height);

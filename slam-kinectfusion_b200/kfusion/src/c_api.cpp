@@ -98,6 +98,7 @@ void kfh_set_shard_comm(void *h, int (*bcast)(float *, void *), int (*composite)
     c.broadcast_pose = bcast; c.composite = composite; c.user = user;
     static_cast<kf::kinectfusion *>(h)->setShardComm(c);
 }
+double kfh_last_icp_us(void *h) { return static_cast<kf::kinectfusion *>(h)->last_icp_us; }
 int kfh_frame_count(void *h) { return static_cast<kf::kinectfusion *>(h)->frame_count; }
 int kfh_num_poses(void *h) { return (int)static_cast<kf::kinectfusion *>(h)->pose_record.size(); }
 void kfh_get_pose(void *h, int idx, float pose12[12])

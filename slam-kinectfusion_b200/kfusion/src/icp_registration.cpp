@@ -44,23 +44,31 @@ bool kf::ICPRegistration::solve(const double in27[27], double x6[6])
         }
     }
     if (singular || std::fabs(det) < 1e-15 || std::isnan(det)) return false;
-    // Cholesky A = L L^T (north star), LU back-substitution if A is not numerically PD
-    double L[6][6];
+    // Cholesky in its square-root-free form A = L D L^T with one reciprocal per column (north star: host 6x6
+    // Cholesky solve); LU back-substitution if A is not numerically positive definite.  The device predicts
+    // the next pose with EXACTLY this operation sequence (csrc/kfb_icp.cu: icp_predict_pose) -- keep the two in
+    // step: every product, difference and reciprocal below is one IEEE double operation (-ffp-contract=off).
+    double L[6][6], d[6], inv[6], t[6][6];
     bool ok = true;
-    std::memset(L, 0, sizeof(L));
-    for (int i = 0; i < 6 && ok; ++i)
-        for (int j = 0; j <= i; ++j)
+    for (int j = 0; j < 6 && ok; ++j)
+    {
+        double dj = A[j][j];
+        for (int q = 0; q < j; ++q) { t[j][q] = L[j][q] * d[q]; dj -= L[j][q] * t[j][q]; }
+        if (!(dj > 0.0)) { ok = false; break; }
+        d[j] = dj;
+        inv[j] = 1.0 / dj;
+        for (int i = j + 1; i < 6; ++i)
         {
             double sum = A[i][j];
-            for (int q = 0; q < j; ++q) sum -= L[i][q] * L[j][q];
-            if (i == j) { if (!(sum > 0.0)) { ok = false; break; } L[i][i] = std::sqrt(sum); }
-            else L[i][j] = sum / L[j][j];
+            for (int q = 0; q < j; ++q) sum -= L[i][q] * t[j][q];
+            L[i][j] = sum * inv[j];
         }
+    }
     if (ok)
     {
-        double y[6];
-        for (int i = 0; i < 6; ++i) { double sum = b[i]; for (int q = 0; q < i; ++q) sum -= L[i][q] * y[q]; y[i] = sum / L[i][i]; }
-        for (int i = 5; i >= 0; --i) { double sum = y[i]; for (int q = i + 1; q < 6; ++q) sum -= L[q][i] * x6[q]; x6[i] = sum / L[i][i]; }
+        double z[6];
+        for (int i = 0; i < 6; ++i) { double sum = b[i]; for (int q = 0; q < i; ++q) sum -= L[i][q] * z[q]; z[i] = sum; }
+        for (int i = 5; i >= 0; --i) { double sum = z[i] * inv[i]; for (int q = i + 1; q < 6; ++q) sum -= L[q][i] * x6[q]; x6[i] = sum; }
     }
     else
     {

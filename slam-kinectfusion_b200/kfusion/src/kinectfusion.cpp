@@ -95,7 +95,9 @@ void kf::kinectfusion::pipeline(const float *depth_mm, int width, int height)
     if (params_.shard_rank == 0)
     {
         cv::Affine3f cam_pose;
+        const auto t_icp = std::chrono::steady_clock::now();
         const bool ok = icp.rigidTransform(cam_pose, pose_record.back(), &cframe, &pframe);
+        last_icp_us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_icp).count();
         msg[0] = ok ? 1.f : 0.f;
         if (ok) (pose_record.back() * cam_pose).to12(msg + 1);
     }

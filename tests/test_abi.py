@@ -96,5 +96,7 @@ def test_host_solve_matches_oracle(kfb, kfo):
         rc_h, x_h = host.icp_solve(s27)
         rc_o, x_o = kfo.icp_solve(s27)
         assert rc_h == rc_o == 0
-        np.testing.assert_array_equal(x_h, x_o)
+        # the facade factors A = L D L^T with reciprocals (the sequence the device mirrors for its pose
+        # prediction), the oracle uses the textbook Cholesky: same solution to rounding
+        np.testing.assert_allclose(x_h, x_o, rtol=1e-9, atol=1e-13)
     assert host.icp_solve(np.zeros(27))[0] == 1

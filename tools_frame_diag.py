@@ -1,0 +1,38 @@
+"""Scratch diagnostics on the GPU box: per-frame ICP wall time and misprediction count through the C++ facade."""
+import sys
+import numpy as np
+sys.path.insert(0, '.')
+import slam_kinectfusion_b200 as kfb
+from slam_kinectfusion_b200 import synth
+K = kfb.Intrinsics(**kfb.SENSORS["kinect1"])
+kf = kfb.KinectFusion(K, kfb.default_host_params(512))
+frames = synth.sequence(40, K)
+us = []
+for i, (_, d) in enumerate(frames):
+    assert kf.pipeline(d) == 0
+    if i >= 5:
+        us.append(kf.last_icp_us())
+ctx = kf.context()
+print("icp us per frame: median %.1f min %.1f max %.1f" % (np.median(us), np.min(us), np.max(us)))
+print("mispredicted iterations since creation:", int(ctx.debug_icp_stamps()[7]), "of", 19 * 39)
+
+# serialized frames (sync between frames): ICP wall time is pure, frame wall = sum of the stages
+import time
+kf.reset()
+fr, ic = [], []
+for i, (_, d) in enumerate(frames):
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    assert kf.pipeline(d) == 0
+    ctx.synchronize()
+    if i >= 5:
+        fr.append((time.perf_counter() - t0) * 1e6)
+        ic.append(kf.last_icp_us())
+print("serialized: frame us median %.1f, icp us median %.1f, rest %.1f" % (np.median(fr), np.median(ic), np.median(fr) - np.median(ic)))
+
+R = ctx.debug_icp_ring().astype(np.int64)[:19]
+print("per-iteration ns: entry->final", (R[:, 1] - R[:, 0]).tolist())
+print("final->posted (validation wait)", (R[:, 2] - R[:, 1]).tolist())
+print("posted->released (predict)", (R[:-1, 3] - R[:-1, 2]).tolist())
+print("released->next entry", (R[1:, 0] - R[:-1, 3]).tolist())
+print("period", np.diff(R[:, 0]).tolist())
