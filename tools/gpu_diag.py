@@ -1,7 +1,7 @@
 """Scratch diagnostics run on the GPU box (prints stage timings and parity stats)."""
 import sys, time, json
 import numpy as np
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import slam_kinectfusion_b200 as kfb
 from oracle import kfo
 

@@ -1,6 +1,6 @@
 import sys, time
 import numpy as np
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import slam_kinectfusion_b200 as kfb
 from slam_kinectfusion_b200 import synth
 K = kfb.Intrinsics(**kfb.SENSORS["kinect1"])
