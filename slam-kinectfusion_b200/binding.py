@@ -78,6 +78,10 @@ def load_library():
         "kfb_device_count": (C.c_int, []),
         "kfb_set_stream": (C.c_int, [_vp, _vp]),
         "kfb_composite_mask": (C.c_int, [_vp, _vp]),
+        "kfb_ipc_export": (C.c_int, [_vp, C.c_int, _vp]),
+        "kfb_shard_attach": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+        "kfb_shard_composite": (C.c_int, [_vp]),
+        "kfb_shard_attached": (C.c_int, [_vp]),
         "kfb_reset_volume": (C.c_int, [_vp]),
         "kfb_reset_frames": (C.c_int, [_vp]),
         "kfb_upload_depth_mm": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
@@ -221,6 +225,21 @@ class Context:
 
     def composite_mask(self, min_key_ptr):
         self._ck(self.lib.kfb_composite_mask(self.h, _vp(int(min_key_ptr))))
+
+    def ipc_export(self):
+        """256 bytes: the four CUDA IPC handles (keys, maps slot 0, maps slot 1, flag) of this context."""
+        buf = np.zeros(4 * 64, np.uint8)
+        for w in range(4):
+            self._ck(self.lib.kfb_ipc_export(self.h, w, _vp(buf.ctypes.data + 64 * w)))
+        return buf
+
+    def shard_attach(self, rank, world, handles):
+        h = np.ascontiguousarray(handles, np.uint8)
+        assert h.size == world * 256
+        self._ck(self.lib.kfb_shard_attach(self.h, int(rank), int(world), _ptr(h)))
+
+    def shard_composite(self):
+        self._ck(self.lib.kfb_shard_composite(self.h))
 
     def model_pyramid(self):
         self._ck(self.lib.kfb_model_pyramid(self.h))

@@ -97,6 +97,8 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->profiling = 0;
     ctx->icp_seq = 0;
     ctx->pyramid_fresh = 0;
+    ctx->shard_rank = 0; ctx->shard_world = 0; ctx->shard_flag = nullptr; ctx->shard_seq = 0;
+    memset(ctx->peer_keys, 0, sizeof(ctx->peer_keys)); memset(ctx->peer_maps, 0, sizeof(ctx->peer_maps)); memset(ctx->peer_flag, 0, sizeof(ctx->peer_flag));
     ctx->vol = nullptr; ctx->cloud = nullptr; ctx->cloud_cap = 0;
     ctx->tab_thrz = nullptr; ctx->tab_exact = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->zmip = nullptr; ctx->bricks = nullptr; ctx->states = nullptr; ctx->states_bytes = 0;
     ctx->bdist = ctx->bdist_tmp = ctx->bdist_tmp2 = nullptr; ctx->bdirty = nullptr;
@@ -179,6 +181,8 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     }
     KFB_CUDA(ctx, cudaMalloc(&ctx->tab_exact, n0 * sizeof(float2)));
     KFB_CUDA(ctx, cudaMalloc(&ctx->hit_t, n0 * sizeof(float)));
+    KFB_CUDA(ctx, cudaMalloc(&ctx->shard_flag, 256));
+    KFB_CUDA(ctx, cudaMemset(ctx->shard_flag, 0, 256));
     KFB_CUDA(ctx, cudaMalloc(&ctx->icp_partials, 1024 * 27 * sizeof(double)));
     KFB_CUDA(ctx, cudaMalloc(&ctx->icp_ticket, sizeof(unsigned int)));
     KFB_CUDA(ctx, cudaMemset(ctx->icp_ticket, 0, sizeof(unsigned int)));
@@ -241,6 +245,15 @@ void kfb_destroy(kfb_ctx *ctx)
     if (ctx->bdirty) cudaFree(ctx->bdirty);
     if (ctx->tab_exact) cudaFree(ctx->tab_exact);
     if (ctx->hit_t) cudaFree(ctx->hit_t);
+    for (int r = 0; r < ctx->shard_world && r < 16; ++r)
+        if (r != ctx->shard_rank)
+        {
+            if (ctx->peer_keys[r]) cudaIpcCloseMemHandle(ctx->peer_keys[r]);
+            if (ctx->peer_maps[0][r]) cudaIpcCloseMemHandle(ctx->peer_maps[0][r]);
+            if (ctx->peer_maps[1][r]) cudaIpcCloseMemHandle(ctx->peer_maps[1][r]);
+            if (ctx->peer_flag[r]) cudaIpcCloseMemHandle(ctx->peer_flag[r]);
+        }
+    if (ctx->shard_flag) cudaFree(ctx->shard_flag);
     if (ctx->icp_partials) cudaFree(ctx->icp_partials);
     if (ctx->icp_ticket) cudaFree(ctx->icp_ticket);
     if (ctx->icp_host) cudaFreeHost((void *)ctx->icp_host);
@@ -378,6 +391,54 @@ int kfb_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9])
 }
 
 int kfb_model_pyramid(kfb_ctx *ctx) { return launch_model_pyramid(ctx); }
+
+static void *shard_export_ptr(kfb_ctx *ctx, int which)
+{
+    switch (which)
+    {
+    case 0: return ctx->hit_t;
+    case 1: return ctx->L[0].v[0];
+    case 2: return ctx->L[0].v[1];
+    case 3: return ctx->shard_flag;
+    default: return nullptr;
+    }
+}
+int kfb_ipc_export(kfb_ctx *ctx, int which, void *handle64)
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == KFB_IPC_HANDLE_BYTES, "IPC handle size");
+    void *p = shard_export_ptr(ctx, which);
+    if (!p || !handle64) return KFB_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    KFB_CUDA(ctx, cudaIpcGetMemHandle(&h, p));
+    memcpy(handle64, &h, sizeof(h));
+    return KFB_OK;
+}
+int kfb_shard_attach(kfb_ctx *ctx, int rank, int world, const void *handles)
+{
+    if (world < 2 || world > 16 || rank < 0 || rank >= world || !handles) return KFB_ERR_INVALID;
+    if (ctx->shard_world) { ctx->err = "already attached"; return KFB_ERR_INVALID; }
+    const unsigned char *hb = (const unsigned char *)handles;
+    for (int r = 0; r < world; ++r)
+    {
+        void *ptr[4];
+        for (int w = 0; w < 4; ++w)
+        {
+            if (r == rank) { ptr[w] = shard_export_ptr(ctx, w); continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, hb + ((size_t)r * 4 + w) * KFB_IPC_HANDLE_BYTES, sizeof(h));
+            KFB_CUDA(ctx, cudaIpcOpenMemHandle(&ptr[w], h, cudaIpcMemLazyEnablePeerAccess));
+        }
+        ctx->peer_keys[r] = ptr[0]; ctx->peer_maps[0][r] = ptr[1]; ctx->peer_maps[1][r] = ptr[2]; ctx->peer_flag[r] = ptr[3];
+    }
+    ctx->shard_rank = rank; ctx->shard_world = world; ctx->shard_seq = 0;
+    return KFB_OK;
+}
+int kfb_shard_attached(const kfb_ctx *ctx) { return ctx->shard_world > 0; }
+int kfb_shard_composite(kfb_ctx *ctx)
+{
+    if (!ctx->shard_world) { ctx->err = "kfb_shard_composite without kfb_shard_attach"; return KFB_ERR_INVALID; }
+    return launch_shard_composite(ctx);
+}
 
 int kfb_composite_mask(kfb_ctx *ctx, const float *min_key_dev)
 {

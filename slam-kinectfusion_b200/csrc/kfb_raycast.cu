@@ -395,6 +395,80 @@ int launch_composite_mask(kfb_ctx *ctx, const float *min_key)
     return KFB_OK;
 }
 
+// ---- composite over NVLink peer memory (kfb_shard_composite) ---------------------------------------------------
+struct ShardArgs
+{
+    const float *keys[16];
+    const float4 *maps[16];                  // vertex map, then normal map (contiguous), of every rank's model slot
+    const volatile unsigned long long *flag[16];
+    float4 *out;                             // rank 0's own model maps
+    int world, self, npix;
+    unsigned long long seq;
+};
+__global__ void shard_signal_kernel(unsigned long long *flag, unsigned long long seq)
+{
+    __threadfence_system(); // the raycast kernel before this launch has completed: publish its results to the peers
+    *(volatile unsigned long long *)flag = seq;
+}
+__global__ void __launch_bounds__(256) shard_composite_kernel(const ShardArgs a)
+{
+    // wait until every slab of this frame has been raycast (flags live in the peers' memory, read over NVLink)
+    if (threadIdx.x < a.world)
+    {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+        while (*a.flag[threadIdx.x] < a.seq)
+        {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            if (t - t0 > 2000000000ull) break; // 2 s: a peer died; leave rather than hang the GPU
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.npix; i += gridDim.x * blockDim.x)
+    {
+        float best = __int_as_float(0x7f800000);
+        int win = -1;
+#pragma unroll 4
+        for (int r = 0; r < a.world; ++r)
+        {
+            const float k = __ldcv(a.keys[r] + i);
+            if (k < best) { best = k; win = r; }
+        }
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f), n = v;
+        if (win >= 0)
+        {
+            v = __ldcv(a.maps[win] + i);
+            n = __ldcv(a.maps[win] + a.npix + i);
+        }
+        if (win != a.self) { a.out[i] = v; a.out[a.npix + i] = n; }
+    }
+}
+
+int launch_shard_composite(kfb_ctx *ctx)
+{
+    const Intr &k = ctx->L[0].k;
+    const unsigned long long seq = ++ctx->shard_seq;
+    shard_signal_kernel<<<1, 1, 0, ctx->stream>>>(ctx->shard_flag, seq);
+    KFB_LAUNCH_CHECK(ctx);
+    if (ctx->shard_rank != 0) return KFB_OK;
+    ShardArgs a;
+    memset(&a, 0, sizeof(a));
+    for (int r = 0; r < ctx->shard_world; ++r)
+    {
+        a.keys[r] = (const float *)ctx->peer_keys[r];
+        a.maps[r] = (const float4 *)ctx->peer_maps[ctx->prev][r];
+        a.flag[r] = (const volatile unsigned long long *)ctx->peer_flag[r];
+    }
+    a.out = ctx->L[0].v[ctx->prev];
+    a.world = ctx->shard_world; a.self = ctx->shard_rank; a.npix = k.w * k.h; a.seq = seq;
+    shard_composite_kernel<<<148 * 2, 256, 0, ctx->stream>>>(a);
+    KFB_LAUNCH_CHECK(ctx);
+    ctx->pyramid_fresh = 0;
+    return KFB_OK;
+}
+
 int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9])
 {
     RaycastArgs a;

@@ -112,7 +112,13 @@ void kf::kinectfusion::pipeline(const float *depth_mm, int width, int height)
     pose_record.push_back(cv::Affine3f::from12(msg + 1));
     vdata->integrate(pose_record.back());
     vdata->raycast(pose_record.back());
-    if (sharded && comm.composite(comm.user) != 0) throw std::runtime_error("kf::kinectfusion: raycast composite failed");
+    if (sharded)
+    {
+        // first-hit composite over the slabs: one kernel over NVLink peer memory when the launcher attached the
+        // peers (kfb_shard_attach), else the launcher's collectives
+        if (kfb_shard_attached(dev->ctx)) kfbSafeCall(dev->ctx, kfb_shard_composite(dev->ctx));
+        else if (comm.composite(comm.user) != 0) throw std::runtime_error("kf::kinectfusion: raycast composite failed");
+    }
     if (params_.shard_rank == 0) kfbSafeCall(dev->ctx, kfb_model_pyramid(dev->ctx));
     std::chrono::duration<double, std::milli> ms = std::chrono::steady_clock::now() - start_time;
     frame_time = std::to_string(ms.count());

@@ -3,6 +3,9 @@
 [g*Z/G, (g+1)*Z/G) (+ a 3-plane halo integrated redundantly, no exchange), marches the ray samples whose
 voxel lies in its slab, and the first terminal ray event over all slabs is selected with two collectives:
 
+  (default) ONE kernel on rank 0 over NVLink peer memory (CUDA IPC, kfb_shard_attach / kfb_shard_composite): it
+    waits for every slab's "done" flag, reads the peers' event keys, and pulls the winner's vertex and normal;
+  (KFB_COMPOSITE_NCCL=1) the same selection with two collectives:
     all_reduce(MIN) over the per-pixel event keys (ray length of the slab's first hit / back-face stop)
     kfb_composite_mask: every rank zeroes its vertex / normal maps where it does not hold the winning key
     reduce(SUM, int32 view) of the maps to rank 0 (x + 0 == x exactly in integers, so the composite is
@@ -145,14 +148,24 @@ class ShardedKinectFusion:
         self.P = K.width * K.height
         self.mailbox = PoseMailbox(dist, rank, os.environ.get("MASTER_PORT", "0")) if os.environ.get("KFB_POSE_NCCL") is None else None
         self.min_keys = torch.empty(self.P, dtype=torch.float32, device=self.device)
+        self._view_cache = {}
         self.kf.set_shard_comm(self._bcast, self._composite)
+        self.p2p = os.environ.get("KFB_COMPOSITE_NCCL") is None
+        if self.p2p:
+            # exchange CUDA IPC handles once; from then on the composite is one kernel over NVLink peer memory
+            mine = torch.from_numpy(self.ctx.ipc_export()).to(self.device)
+            allh = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            self.ctx.shard_attach(rank, world, torch.stack(allh).cpu().numpy().reshape(-1))
 
     def _views(self):
         # the model maps swap buffers on the bootstrap frame: take the pointers per call (cheap)
         d = self.device
-        keys = dev_tensor(self.ctx.device_ptr(4), (self.P,), "<f4", d)
-        maps = dev_tensor(self.ctx.device_ptr(1), (self.P * 8,), "<i4", d)   # vertex map + normal map, contiguous
-        return keys, maps
+        pk, pm = self.ctx.device_ptr(4), self.ctx.device_ptr(1)
+        if (pk, pm) not in self._view_cache:
+            self._view_cache[(pk, pm)] = (dev_tensor(pk, (self.P,), "<f4", d),
+                                          dev_tensor(pm, (self.P * 8,), "<i4", d))   # vertex map + normal map, contiguous
+        return self._view_cache[(pk, pm)]
 
     def _bcast(self, p):
         try:
@@ -276,8 +289,9 @@ def run_bench(args, dist, rank, world, local, dims, K, frames, host_pin, dev_fra
                                "ICP 10/5/4 on rank 0, per-slab raycast + first-hit composite, 300-frame looped synthetic trajectory",
                    "l2": "inputs larger than L2: every rank sweeps its >= 512 MiB slab each frame",
                    "frames_timed": S, "updated_voxels_per_frame": U_owned, "swept_voxels_per_frame": dims * dims * (dims - 1),
-                   "collectives_per_frame": "pose mailbox 52 B (shared memory), all_reduce(min) 1.2 MB, reduce(sum) 9.8 MB"},
+                   "collectives_per_frame": ("pose mailbox 52 B (shared memory); composite = one kernel over NVLink peer memory" if skf.p2p else "pose mailbox 52 B (shared memory), all_reduce(min) 1.2 MB, reduce(sum) 9.8 MB")},
         "frame_device_ms": ms_per_frame,
+        "final_pose": [float(x) for x in poses[-1]],
         "e2e": {"value": U_owned / (e2e_ms / S * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / S,
                 "h2d_bytes_per_step": w * h * 4 * world, "d2h_bytes_per_step": 19 * 27 * 16 + 52 * world,
                 "api": "kf::kinectfusion::pipeline(depth_mm) on every rank (z-slab sharded, kf::ShardComm over NCCL), pinned host frames"},
