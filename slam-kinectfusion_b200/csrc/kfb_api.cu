@@ -165,7 +165,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
             ctx->mip_off[i] = off;
             off += ((intr->width + (1 << (i + 2)) - 1) >> (i + 2)) * ((intr->height + (1 << (i + 2)) - 1) >> (i + 2));
         }
-        KFB_CUDA(ctx, cudaMalloc(&ctx->zmip, (size_t)off * sizeof(float)));
+        KFB_CUDA(ctx, cudaMalloc(&ctx->zmip, (size_t)off * sizeof(float2)));
     }
     ctx->bdim[0] = (p->volu_dims[0] + 7) >> 3;
     ctx->bdim[1] = (p->volu_dims[1] + 7) >> 3;

@@ -63,10 +63,11 @@ struct IntegrateArgs
     const float2 *exact;
     const float4 *wtab;
     const float *zexit;
-    const float *zmip;          // max-pyramid of lo_z, levels 2..7 (tiles of 4..128 px), see build_zmip_kernel
+    const float2 *zmip;         // pyramid of {max lo_z, min hi_z}, levels 2..7 (tiles of 4..128 px), see build_zmip_kernel
     int mip_off[6], mip_w[6];
     float Sx, Sy, Sz, invSz, driftE; // per-plane step of vc (float), 1/Sz, bound on the running-sum drift
     int max_weight;
+    int no_fastpath;            // KFB_INTEGRATE_NOFAST: disable the deep-free-space path (tuning / testing)
     int use_jump, jump_min; // exact jump of the running sum for prefixes of at least jump_min planes
     uint8_t *bricks;
     int *bdirty;         // set when a brick flag flips 0 -> 1 (the distance map must be rebuilt)
@@ -178,23 +179,31 @@ __global__ void build_tables_kernel(const float *__restrict__ depth, int w, int 
     if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && lo_z > 0.f) atomicMax((int *)zexit, __float_as_int(lo_z));
 }
 
-// Max-pyramid of lo_z over the image: level l (2..7) holds, per 2^l x 2^l pixel tile, the largest vc.z any
-// pixel of the tile would still accept.  One block builds all levels of a 128 x 128 pixel region.
-__global__ void __launch_bounds__(256) build_zmip_kernel(const float2 *__restrict__ thrz, int w, int h, float *__restrict__ mip,
+// Pyramid over the image of {max lo_z, min hi_z}: level l (2..7) holds, per 2^l x 2^l pixel tile, the largest
+// vc.z any pixel of the tile would still accept and the largest vc.z that is free space (tsdf == 1) for EVERY
+// pixel of the tile (-1 as soon as one pixel has no valid depth).  One block builds all levels of a 128 x 128
+// pixel region.
+__device__ __forceinline__ float2 mm2(float2 a, float2 b) { return make_float2(fmaxf(a.x, b.x), fminf(a.y, b.y)); }
+__global__ void __launch_bounds__(256) build_zmip_kernel(const float2 *__restrict__ thrz, int w, int h, float2 *__restrict__ mip,
                                                          int o2, int o3, int o4, int o5, int o6, int o7)
 {
-    __shared__ float s2[32][33], s3[16][17], s4[8][9], s5[4][5], s6[2][3];
+    __shared__ float2 s2[32][33], s3[16][17], s4[8][9], s5[4][5], s6[2][3];
     const int rx = blockIdx.x * 128, ry = blockIdx.y * 128, t = threadIdx.x;
     const int w2 = (w + 3) >> 2, w3 = (w + 7) >> 3, w4 = (w + 15) >> 4, w5 = (w + 31) >> 5, w6 = (w + 63) >> 6, w7 = (w + 127) >> 7;
+    const float2 none = make_float2(-1.f, 3.0e38f); // neutral element (tiles outside the image)
     for (int i = t; i < 1024; i += 256)
     {
         const int ty = i >> 5, tx = i & 31;
-        float m = -1.f;
+        float2 m = none;
         for (int dy = 0; dy < 4; ++dy)
             for (int dx = 0; dx < 4; ++dx)
             {
                 const int x = rx + tx * 4 + dx, y = ry + ty * 4 + dy;
-                if (x < w && y < h) m = fmaxf(m, thrz[(size_t)y * w + x].y);
+                if (x < w && y < h)
+                {
+                    const float2 th = thrz[(size_t)y * w + x]; // {hi_z, lo_z}
+                    m = mm2(m, make_float2(th.y, th.x));
+                }
             }
         s2[ty][tx] = m;
         const int gx = (rx >> 2) + tx, gy = (ry >> 2) + ty;
@@ -203,7 +212,7 @@ __global__ void __launch_bounds__(256) build_zmip_kernel(const float2 *__restric
     __syncthreads();
     {
         const int ty = t >> 4, tx = t & 15;
-        const float m = fmaxf(fmaxf(s2[2 * ty][2 * tx], s2[2 * ty][2 * tx + 1]), fmaxf(s2[2 * ty + 1][2 * tx], s2[2 * ty + 1][2 * tx + 1]));
+        const float2 m = mm2(mm2(s2[2 * ty][2 * tx], s2[2 * ty][2 * tx + 1]), mm2(s2[2 * ty + 1][2 * tx], s2[2 * ty + 1][2 * tx + 1]));
         s3[ty][tx] = m;
         const int gx = (rx >> 3) + tx, gy = (ry >> 3) + ty;
         if (gx < w3 && gy < ((h + 7) >> 3)) mip[o3 + gy * w3 + gx] = m;
@@ -212,7 +221,7 @@ __global__ void __launch_bounds__(256) build_zmip_kernel(const float2 *__restric
     if (t < 64)
     {
         const int ty = t >> 3, tx = t & 7;
-        const float m = fmaxf(fmaxf(s3[2 * ty][2 * tx], s3[2 * ty][2 * tx + 1]), fmaxf(s3[2 * ty + 1][2 * tx], s3[2 * ty + 1][2 * tx + 1]));
+        const float2 m = mm2(mm2(s3[2 * ty][2 * tx], s3[2 * ty][2 * tx + 1]), mm2(s3[2 * ty + 1][2 * tx], s3[2 * ty + 1][2 * tx + 1]));
         s4[ty][tx] = m;
         const int gx = (rx >> 4) + tx, gy = (ry >> 4) + ty;
         if (gx < w4 && gy < ((h + 15) >> 4)) mip[o4 + gy * w4 + gx] = m;
@@ -221,7 +230,7 @@ __global__ void __launch_bounds__(256) build_zmip_kernel(const float2 *__restric
     if (t < 16)
     {
         const int ty = t >> 2, tx = t & 3;
-        const float m = fmaxf(fmaxf(s4[2 * ty][2 * tx], s4[2 * ty][2 * tx + 1]), fmaxf(s4[2 * ty + 1][2 * tx], s4[2 * ty + 1][2 * tx + 1]));
+        const float2 m = mm2(mm2(s4[2 * ty][2 * tx], s4[2 * ty][2 * tx + 1]), mm2(s4[2 * ty + 1][2 * tx], s4[2 * ty + 1][2 * tx + 1]));
         s5[ty][tx] = m;
         const int gx = (rx >> 5) + tx, gy = (ry >> 5) + ty;
         if (gx < w5 && gy < ((h + 31) >> 5)) mip[o5 + gy * w5 + gx] = m;
@@ -230,13 +239,13 @@ __global__ void __launch_bounds__(256) build_zmip_kernel(const float2 *__restric
     if (t < 4)
     {
         const int ty = t >> 1, tx = t & 1;
-        const float m = fmaxf(fmaxf(s5[2 * ty][2 * tx], s5[2 * ty][2 * tx + 1]), fmaxf(s5[2 * ty + 1][2 * tx], s5[2 * ty + 1][2 * tx + 1]));
+        const float2 m = mm2(mm2(s5[2 * ty][2 * tx], s5[2 * ty][2 * tx + 1]), mm2(s5[2 * ty + 1][2 * tx], s5[2 * ty + 1][2 * tx + 1]));
         s6[ty][tx] = m;
         const int gx = (rx >> 6) + tx, gy = (ry >> 6) + ty;
         if (gx < w6 && gy < ((h + 63) >> 6)) mip[o6 + gy * w6 + gx] = m;
     }
     __syncthreads();
-    if (t == 0) mip[o7 + blockIdx.y * w7 + blockIdx.x] = fmaxf(fmaxf(s6[0][0], s6[0][1]), fmaxf(s6[1][0], s6[1][1]));
+    if (t == 0) mip[o7 + blockIdx.y * w7 + blockIdx.x] = mm2(mm2(s6[0][0], s6[0][1]), mm2(s6[1][0], s6[1][1]));
 }
 
 // wtab[wt] = {(float)wt, MUFU.RCP(wt + 1), bits(min(wt + 1, max_weight) << 16), 0}: the weight-dependent
@@ -486,14 +495,19 @@ __device__ __forceinline__ void update_quad(const IntegrateArgs &a, uint4 *vp, c
 
 // ---- the sweep ------------------------------------------------------------------------
 #define KFB_BAND (-8.0f)
+#ifndef KFB_INT_PX
+#define KFB_INT_PX 4 // threads of a warp along x (each owns 4 voxels); 32 / KFB_INT_PX rows
+#endif
 #ifndef KFB_INT_MINB
 #define KFB_INT_MINB 8
 #endif
 template <int U, bool COUNT>
 __global__ void __launch_bounds__(128, KFB_INT_MINB) integrate_kernel(const IntegrateArgs a)
 {
-    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int y = blockIdx.y * 4 + threadIdx.y;
+    // a warp owns a compact 32 x 4 voxel patch (8 threads x 4 rows; 128 B per row): its columns see nearly the
+    // same part of the image, so warp-level decisions (fast path, loop bounds) are mostly unanimous
+    const int x0 = (blockIdx.x * (4 * KFB_INT_PX) + threadIdx.y * KFB_INT_PX + (threadIdx.x & (KFB_INT_PX - 1))) * 4;
+    const int y = blockIdx.y * (32 / KFB_INT_PX) + (threadIdx.x / KFB_INT_PX);
     if (x0 >= a.X || y >= a.Y) return;
 
     const int zstart = a.zb + blockIdx.z * a.zchunk;
@@ -528,6 +542,7 @@ __global__ void __launch_bounds__(128, KFB_INT_MINB) integrate_kernel(const Inte
     const int za = max(zstart, (int)floorf(lo));
     int zb = min(zend - 1, (int)ceilf(hi));
     if (za > zb) return;
+    bool deep_free = false;
     // Occlusion cut: over planes [za, zb] the four columns project into a pixel rectangle (a line segment per
     // column; computed from the affine model and widened by the drift bound).  A voxel is rejected once vc.z
     // exceeds lo_z of its pixel, hence certainly once it exceeds the maximum of lo_z over that rectangle, which
@@ -557,22 +572,54 @@ __global__ void __launch_bounds__(128, KFB_INT_MINB) integrate_kernel(const Inte
         {
             // pixel error of the model: (fx + |u - cx|) * E / z per axis, plus rounding to the nearest pixel
             const float pad = 1.5f + (a.fx + a.fy + (float)(a.w + a.h)) * a.driftE / zmin;
+            const bool all_inside = umin - pad >= 0.f && umax + pad <= (float)(a.w - 1) && vmin - pad >= 0.f && vmax + pad <= (float)(a.h - 1);
             const int u0 = max((int)floorf(fmaxf(umin - pad, -1e6f)), 0), u1 = min((int)ceilf(fminf(umax + pad, 1e6f)), a.w - 1);
             const int v0 = max((int)floorf(fmaxf(vmin - pad, -1e6f)), 0), v1 = min((int)ceilf(fminf(vmax + pad, 1e6f)), a.h - 1);
             if (u0 > u1 || v0 > v1) return; // never inside the image on these planes
             const int span = max(u1 - u0, v1 - v0) + 1;
-            const int l = max(32 - __clz(span - 1), 2);
+            // tiles a quarter of the span wide: the rectangle is covered by at most 5 x 5 of them
+            const int l = max(32 - __clz(span - 1) - 2, 2);
             if (l <= 7)
             {
-                const float *m = a.zmip + a.mip_off[l - 2];
+                const float2 *m = a.zmip + a.mip_off[l - 2];
                 const int mw = a.mip_w[l - 2];
-                const float zmax = fmaxf(fmaxf(__ldg(m + (v0 >> l) * mw + (u0 >> l)), __ldg(m + (v0 >> l) * mw + (u1 >> l))),
-                                         fmaxf(__ldg(m + (v1 >> l) * mw + (u0 >> l)), __ldg(m + (v1 >> l) * mw + (u1 >> l))));
-                const float zc = (zmax + 2.f * a.driftE - fminf(z0v[0], z0v[3])) * a.invSz + 1.f;
+                float2 q = make_float2(-1.f, 3.0e38f);
+                for (int ty = v0 >> l; ty <= (v1 >> l); ++ty)
+                    for (int tx = u0 >> l; tx <= (u1 >> l); ++tx) q = mm2(q, __ldg(m + ty * mw + tx));
+                const float zc = (q.x + 2.f * a.driftE - fminf(z0v[0], z0v[3])) * a.invSz + 1.f;
                 zb = min(zb, (int)ceilf(fminf(zc, 1e6f)));
                 if (za > zb) return;
+                // Deep free space: every pixel the columns can land on (all inside the image) still sees free
+                // space at the largest vc.z of the interval => every voxel of [za, zb] passes the predicate with
+                // tsdf == 1.0f exactly; neither projection nor running sums are needed.
+                const float vz_max = fmaf((float)zb, a.Sz, fmaxf(z0v[0], z0v[3])) + 2.f * a.driftE;
+                deep_free = all_inside && vz_max <= q.y && !a.no_fastpath;
             }
         }
+    }
+    // the fast path only pays when the whole warp takes it (otherwise the warp would run both paths in turn)
+    {
+        const unsigned act = __activemask();
+        deep_free = __ballot_sync(act, deep_free) == act;
+    }
+    if (deep_free)
+    {
+        const size_t plane4 = ((size_t)a.X * a.Y) >> 2;
+        uint4 *vp = reinterpret_cast<uint4 *>(a.vol) + ((size_t)(za - a.z_store0) * a.Y + y) * (a.X >> 2) + (x0 >> 2);
+        const float ones[4] = {1.f, 1.f, 1.f, 1.f};
+        unsigned int n_upd = 0;
+        int z = za;
+        for (; z + 3 <= zb; z += 4, vp += 4 * plane4)
+        {
+            const uint4 w0 = __ldcs(vp), w1 = __ldcs(vp + plane4), w2 = __ldcs(vp + 2 * plane4), w3 = __ldcs(vp + 3 * plane4);
+            update_quad<COUNT>(a, vp, w0, ones, x0, y, z, n_upd);
+            update_quad<COUNT>(a, vp + plane4, w1, ones, x0, y, z + 1, n_upd);
+            update_quad<COUNT>(a, vp + 2 * plane4, w2, ones, x0, y, z + 2, n_upd);
+            update_quad<COUNT>(a, vp + 3 * plane4, w3, ones, x0, y, z + 3, n_upd);
+        }
+        for (; z <= zb; ++z, vp += plane4) update_quad<COUNT>(a, vp, __ldcs(vp), ones, x0, y, z, n_upd);
+        if (COUNT && n_upd) atomicAdd(a.counter, (unsigned long long)n_upd);
+        return;
     }
 
     const float sz = a.pose.R.m[8];
@@ -850,6 +897,7 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
     a.wtab = ctx->wtab;
     a.zexit = ctx->zexit;
     a.max_weight = ctx->p.tsdf_max_weight;
+    a.no_fastpath = getenv("KFB_INTEGRATE_NOFAST") ? 1 : 0;
     a.use_jump = getenv("KFB_INTEGRATE_NOJUMP") ? 0 : 1;
     // measured on B200: a jump costs about as much as 600 replayed planes (warps that straddle vc.x == 0 walk
     // many binades), so it pays for far z-slabs / large volumes, not for the z-chunks of a 512^3 sweep
@@ -900,7 +948,7 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
         column_states_kernel<<<sg, sb, 0, ctx->stream>>>(a);
         KFB_LAUNCH_CHECK(ctx);
     }
-    dim3 block(32, 4), grid((a.X + 127) / 128, (a.Y + 3) / 4, zc);
+    dim3 block(32, 4), grid((a.X + 16 * KFB_INT_PX - 1) / (16 * KFB_INT_PX), (a.Y + 32 / KFB_INT_PX - 1) / (32 / KFB_INT_PX), zc);
     if (n_updated)
     {
         KFB_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
