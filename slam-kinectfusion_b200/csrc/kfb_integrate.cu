@@ -782,12 +782,13 @@ __global__ void __launch_bounds__(128) column_states_kernel(const IntegrateArgs 
     }
     // columns that never enter the frustum need no states (their sweep threads return before reading them), and
     // no chunk past the last visited plane does
-    int z_last;
+    int z_first, z_last;
     {
         float lo, hi;
         frustum_interval(a, vx[0], vy[0], vz[0], vx[3], vy[3], vz[3], a.zb, a.ze, lo, hi);
-        if (max(a.zb, (int)floorf(lo)) > min(a.ze - 1, (int)ceilf(hi))) return;
+        z_first = max(a.zb, (int)floorf(lo));
         z_last = min(a.ze - 1, (int)ceilf(hi));
+        if (z_first > z_last) return;
     }
     const float sx = a.pose.R.m[2], sy = a.pose.R.m[5], sz = a.pose.R.m[8];
     int done = 0; // planes applied so far
@@ -818,6 +819,7 @@ __global__ void __launch_bounds__(128) column_states_kernel(const IntegrateArgs 
             zz[0] = ffma2(vs2, szz, zz[0]);
             zz[1] = ffma2(vs2, szz, zz[1]);
         }
+        if (target + a.zchunk < z_first) continue; // the chunk ends before the first visited plane: nobody reads its state
         unsigned long long *o = st + (size_t)c * 6 * nthr;
 #pragma unroll
         for (int k = 0; k < 4; ++k) o[(size_t)k * nthr] = xy[k];
