@@ -17,6 +17,7 @@
 #include "kfb_common.cuh"
 #include <xmmintrin.h>
 #include <cstring>
+#include <algorithm>
 
 namespace kfb
 {
@@ -26,6 +27,7 @@ struct IcpArgs
     const float4 *cur_v, *cur_n, *pre_v, *pre_n;
     Intr k;
     int cov_w, cov_h; // pixels visited: [0,cov_w) x [0,cov_h)
+    int stride;       // threads of the full grid (SMs x ICP_THREADS): the pixel -> thread map does not depend on how many CTAs take part
     Pose pose;
     float dist_thres, sine_thres;
     double *partials;           // [gridDim.x][27]
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpArgs a)
     double acc[27];
 #pragma unroll
     for (int i = 0; i < 27; ++i) acc[i] = 0.0;
-    icp_accumulate_pixels(a, acc, blockIdx.x * ICP_THREADS + threadIdx.x, gridDim.x * ICP_THREADS);
+    icp_accumulate_pixels(a, acc, blockIdx.x * ICP_THREADS + threadIdx.x, a.stride);
     __shared__ double sm[ICP_THREADS / 32][27];
     __shared__ double red[ICP_THREADS / 32][28];
     __shared__ bool is_last;
@@ -436,29 +438,36 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
 #pragma unroll
         for (int i = 0; i < 3; ++i) a.pose.t[i] = spose[4 * i + 3];
         const unsigned long long ts0 = globaltimer_ns();
-        double acc[27];
+        // only the CTAs that own pixels at this level take part in the reduction (the others would add zeros)
+        const int nact = min((int)gridDim.x, (a.cov_w * a.cov_h + ICP_THREADS - 1) / ICP_THREADS);
+        unsigned long long ts1 = ts0;
+        if (threadIdx.x == 0) is_last = false;
+        if ((int)blockIdx.x < nact)
+        {
+            double acc[27];
 #pragma unroll
-        for (int i = 0; i < 27; ++i) acc[i] = 0.0;
-        icp_accumulate_pixels(a, acc, blockIdx.x * ICP_THREADS + threadIdx.x, gridDim.x * ICP_THREADS);
-        const unsigned long long ts1 = globaltimer_ns();
-        const double s = icp_block_reduce(acc, sm);
-        if (threadIdx.x < 27)
-        {
-            P.partials[(size_t)blockIdx.x * 27 + threadIdx.x] = s;
-            __threadfence();
-        }
-        ICP_BAR();
-        if (threadIdx.x == 0)
-        {
-            const unsigned int t = atomicInc(P.ticket, gridDim.x - 1);
-            is_last = (t == gridDim.x - 1);
+            for (int i = 0; i < 27; ++i) acc[i] = 0.0;
+            icp_accumulate_pixels(a, acc, blockIdx.x * ICP_THREADS + threadIdx.x, gridDim.x * ICP_THREADS);
+            ts1 = globaltimer_ns();
+            const double s = icp_block_reduce(acc, sm);
+            if (threadIdx.x < 27)
+            {
+                P.partials[(size_t)blockIdx.x * 27 + threadIdx.x] = s;
+                __threadfence();
+            }
+            ICP_BAR();
+            if (threadIdx.x == 0)
+            {
+                const unsigned int t = atomicInc(P.ticket, nact - 1);
+                is_last = (t == (unsigned)(nact - 1));
+            }
         }
         ICP_BAR();
         if (is_last)
         {
             const unsigned long long ts2 = globaltimer_ns();
             __threadfence();
-            const double fin = icp_final_reduce(P.partials, (int)gridDim.x, red);
+            const double fin = icp_final_reduce(P.partials, nact, red);
             if (threadIdx.x < 27) fin27[threadIdx.x] = fin;
             const unsigned long long ts3 = globaltimer_ns();
             ICP_BAR(); // fin27 visible
@@ -596,7 +605,9 @@ static int icp_setup(kfb_ctx *ctx, int level, IcpArgs &a, int &blocks)
     a.out = ctx->icp_dev;
     // one CTA per SM at every level (two were measured slower: the ticket / final stage grows), for the direct and the persistent kernel alike: the pixel -> thread
     // mapping and hence the summation order is a function of the SM count only => identical bits
-    blocks = a.cov_w * a.cov_h > 0 ? ctx->sm_count : 0;
+    a.stride = ctx->sm_count * ICP_THREADS;
+    const int npix = a.cov_w * a.cov_h;
+    blocks = npix > 0 ? std::min(ctx->sm_count, (npix + ICP_THREADS - 1) / ICP_THREADS) : 0; // CTAs that own pixels
     return KFB_OK;
 }
 
