@@ -498,15 +498,18 @@ __device__ __forceinline__ void update_quad(const IntegrateArgs &a, uint4 *vp, c
 #ifndef KFB_INT_PX
 #define KFB_INT_PX 4 // threads of a warp along x (each owns 4 voxels); 32 / KFB_INT_PX rows
 #endif
+#ifndef KFB_INT_WARPS
+#define KFB_INT_WARPS 4 // warps per block (one warp per block was measured slower: 32k tiny blocks per chunk layer)
+#endif
 #ifndef KFB_INT_MINB
 #define KFB_INT_MINB 8
 #endif
 template <int U, bool COUNT>
-__global__ void __launch_bounds__(128, KFB_INT_MINB) integrate_kernel(const IntegrateArgs a)
+__global__ void __launch_bounds__(32 * KFB_INT_WARPS, KFB_INT_MINB * 4 / KFB_INT_WARPS) integrate_kernel(const IntegrateArgs a)
 {
     // a warp owns a compact 32 x 4 voxel patch (8 threads x 4 rows; 128 B per row): its columns see nearly the
     // same part of the image, so warp-level decisions (fast path, loop bounds) are mostly unanimous
-    const int x0 = (blockIdx.x * (4 * KFB_INT_PX) + threadIdx.y * KFB_INT_PX + (threadIdx.x & (KFB_INT_PX - 1))) * 4;
+    const int x0 = (blockIdx.x * (KFB_INT_WARPS * KFB_INT_PX) + threadIdx.y * KFB_INT_PX + (threadIdx.x & (KFB_INT_PX - 1))) * 4;
     const int y = blockIdx.y * (32 / KFB_INT_PX) + (threadIdx.x / KFB_INT_PX);
     if (x0 >= a.X || y >= a.Y) return;
 
@@ -950,7 +953,7 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
         column_states_kernel<<<sg, sb, 0, ctx->stream>>>(a);
         KFB_LAUNCH_CHECK(ctx);
     }
-    dim3 block(32, 4), grid((a.X + 16 * KFB_INT_PX - 1) / (16 * KFB_INT_PX), (a.Y + 32 / KFB_INT_PX - 1) / (32 / KFB_INT_PX), zc);
+    dim3 block(32, KFB_INT_WARPS), grid((a.X + 4 * KFB_INT_WARPS * KFB_INT_PX - 1) / (4 * KFB_INT_WARPS * KFB_INT_PX), (a.Y + 32 / KFB_INT_PX - 1) / (32 / KFB_INT_PX), zc);
     if (n_updated)
     {
         KFB_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
