@@ -30,6 +30,7 @@
 // Side product for the raycaster: every write of a negative tsdf marks the 8^3 bricks within two
 // voxels of it in a byte map (kfb_raycast.cu skips bricks that cannot contain a sign change).
 #include "kfb_common.cuh"
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
@@ -929,11 +930,12 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
     if (planes <= 0) return KFB_OK;
     // z-chunks give resident warps and load balance (the visited interval differs per column); the running
     // sum at each chunk start comes from column_states_kernel, so chunks cost no replay.  48 B per thread per
-    // chunk of state: bounded to ~64 MB.  KFB_INTEGRATE_ZCHUNKS overrides for tuning.
+    // chunk of state: bounded to max(64 MB, 1/32 of the volume).  KFB_INTEGRATE_ZCHUNKS overrides for tuning.
     const size_t nthr = (size_t)(a.X >> 2) * a.Y;
     int zc = (planes + 31) / 32;
     if (zc > 16) zc = 16;
-    while (zc > 1 && (size_t)zc * 48 * nthr > ((size_t)64 << 20)) --zc;
+    const size_t state_cap = std::max((size_t)64 << 20, ctx->vol_voxels * sizeof(uint32_t) / 32); // <= 3 % of the volume
+    while (zc > 1 && (size_t)zc * 48 * nthr > state_cap) --zc;
     if (const char *e = getenv("KFB_INTEGRATE_ZCHUNKS")) zc = atoi(e) > 0 ? atoi(e) : zc;
     if (zc > planes) zc = planes;
     a.zchunk = (planes + zc - 1) / zc;
