@@ -93,6 +93,7 @@ def load_library():
         "kfb_icp_end": (C.c_int, [_vp]),
         "kfb_integrate": (C.c_int, [_vp, _vp, C.POINTER(C.c_uint64)]),
         "kfb_raycast": (C.c_int, [_vp, _vp, _vp]),
+        "kfb_integrate_plane_histogram": (C.c_int, [_vp, _vp, _vp]),
         "kfb_model_pyramid": (C.c_int, [_vp]),
         "kfb_extract_points": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
         "kfb_render_phong": (C.c_int, [_vp, _vp, _vp]),
@@ -215,6 +216,12 @@ class Context:
             return n.value
         self._ck(self.lib.kfb_integrate(self.h, _ptr(p), None))
         return None
+
+    def plane_histogram(self, vol2cam12):
+        p = _f32(vol2cam12)
+        out = np.zeros(int(self.params.volu_dims[2]), np.uint32)
+        self._ck(self.lib.kfb_integrate_plane_histogram(self.h, _ptr(p), _ptr(out)))
+        return out
 
     def raycast(self, cam2vol12, rinv9):
         p, r = _f32(cam2vol12), _f32(rinv9)

@@ -384,6 +384,13 @@ int kfb_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_updated)
     return launch_integrate(ctx, vol2cam12, n_updated);
 }
 
+int kfb_integrate_plane_histogram(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *host_hist)
+{
+    if (!vol2cam12 || !host_hist) return KFB_ERR_INVALID;
+    KFB_JOIN(ctx);
+    return launch_plane_histogram(ctx, vol2cam12, host_hist);
+}
+
 int kfb_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9])
 {
     if (!cam2vol12 || !rinv9) return KFB_ERR_INVALID;

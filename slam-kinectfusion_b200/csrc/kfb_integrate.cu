@@ -32,6 +32,7 @@
 #include "kfb_common.cuh"
 #include <algorithm>
 #include <cmath>
+#include <vector>
 #include <cstdlib>
 
 namespace kfb
@@ -1060,6 +1061,63 @@ int launch_brick_distance(kfb_ctx *ctx)
     brick_distance_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bdist_tmp2, ctx->bdist, ctx->bdim[0], ctx->bdim[1], ctx->bdim[2], 2, ctx->bdirty, 0);
     KFB_LAUNCH_CHECK(ctx);
     KFB_CUDA(ctx, cudaMemsetAsync(ctx->bdirty, 0, sizeof(int), ctx->stream));
+    return KFB_OK;
+}
+
+// ---- work histogram over planes (slab balancing for sharded volumes) -----------------------------------------
+// Number of 4-voxel groups the sweep would visit on every plane of the WHOLE volume for this depth image and
+// pose (frustum interval only; independent of the volume's content and of the planes this context stores).
+// Written as a difference array: +1 at the first visited plane, -1 after the last.
+__global__ void __launch_bounds__(128) plane_histogram_kernel(const IntegrateArgs a, int Z, int *__restrict__ diff)
+{
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int y = blockIdx.y * 4 + threadIdx.y;
+    if (x0 >= a.X || y >= a.Y) return;
+    float vx[2], vy[2], vz[2];
+    const float py = __fmul_rn((float)y, a.vsy);
+    const float pz = __fmul_rn(0.f, a.vsz);
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+    {
+        const float px = __fmul_rn((float)(x0 + 3 * k), a.vsx);
+        const float3 r = rot3(a.pose.R, px, py, pz);
+        vx[k] = __fadd_rn(r.x, a.pose.t[0]);
+        vy[k] = __fadd_rn(r.y, a.pose.t[1]);
+        vz[k] = __fadd_rn(r.z, a.pose.t[2]);
+    }
+    float lo, hi;
+    frustum_interval(a, vx[0], vy[0], vz[0], vx[1], vy[1], vz[1], 1, Z, lo, hi);
+    const int za = max(1, (int)floorf(lo)), zb = min(Z - 1, (int)ceilf(hi));
+    if (za > zb) return;
+    atomicAdd(diff + za, 1);
+    atomicAdd(diff + zb + 1, -1);
+}
+
+int launch_plane_histogram(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *host_hist)
+{
+    const Intr &k = ctx->L[0].k;
+    const int Z = ctx->p.volu_dims[2];
+    IntegrateArgs a;
+    memset(&a, 0, sizeof(a));
+    a.X = ctx->p.volu_dims[0]; a.Y = ctx->p.volu_dims[1];
+    a.pose = make_pose(vol2cam12);
+    a.vsx = ctx->voxel_size[0]; a.vsy = ctx->voxel_size[1]; a.vsz = ctx->voxel_size[2];
+    a.fx = k.fx; a.fy = k.fy; a.cx = k.cx; a.cy = k.cy; a.w = k.w; a.h = k.h;
+    a.zexit = ctx->zexit;
+    make_cull_planes(ctx, a, a.cull);
+    int *diff = nullptr;
+    KFB_CUDA(ctx, cudaMalloc(&diff, (size_t)(Z + 2) * sizeof(int)));
+    KFB_CUDA(ctx, cudaMemsetAsync(diff, 0, (size_t)(Z + 2) * sizeof(int), ctx->stream));
+    dim3 block(32, 4), grid((a.X + 127) / 128, (a.Y + 3) / 4);
+    plane_histogram_kernel<<<grid, block, 0, ctx->stream>>>(a, Z, diff);
+    ctx->launches++;
+    std::vector<int> h((size_t)Z + 2);
+    cudaError_t e = cudaMemcpyAsync(h.data(), diff, h.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(diff);
+    KFB_CUDA(ctx, e);
+    long run = 0;
+    for (int z = 0; z < Z; ++z) { run += h[z]; host_hist[z] = (uint32_t)(run > 0 ? run : 0); }
     return KFB_OK;
 }
 

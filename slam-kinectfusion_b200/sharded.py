@@ -32,9 +32,45 @@ def slab_range(Z, world, rank):
     return (rank * Z) // world, ((rank + 1) * Z) // world
 
 
-def stored_range(Z, world, rank):
-    zb, ze = slab_range(Z, world, rank)
+def stored_range(Z, world, rank, bounds=None):
+    zb, ze = (bounds[rank], bounds[rank + 1]) if bounds is not None else slab_range(Z, world, rank)
     return max(zb - HALO, 0), min(ze + HALO, Z)
+
+
+def balanced_bounds(hist, world, min_planes=8):
+    """Slab boundaries b[0] = 0 < b[1] < ... < b[world] = Z such that every slab carries about the same
+    integration work.  hist[z] = visited 4-voxel groups on plane z (kfb_integrate_plane_histogram); a small
+    constant per plane stands for the per-plane overheads.  Deterministic: every rank computes the same."""
+    h = np.asarray(hist, np.float64)
+    Z = len(h)
+    work = h + 0.02 * max(float(h.max()), 1.0)
+    cum = np.concatenate([[0.0], np.cumsum(work)])
+    b = [0]
+    for r in range(1, world):
+        z = int(np.searchsorted(cum, cum[-1] * r / world))
+        z = max(z, b[-1] + min_planes)
+        z = min(z, Z - (world - r) * min_planes)
+        b.append(z)
+    b.append(Z)
+    return b
+
+
+def measure_plane_histogram(K, hp, depth_mm, device):
+    """Work histogram of the first frame at the bootstrap pose (identity), from a throw-away context that stores
+    only a handful of planes."""
+    from . import binding
+    p = binding.default_params(int(hp.volu_dims[0]))
+    for i in range(3):
+        p.volu_dims[i] = hp.volu_dims[i]
+        p.volu_range[i] = hp.volu_range[i]
+    p.volu_trun_dist = hp.volu_trun_dist
+    p.slab_z_begin, p.slab_z_end = 1, 2
+    ctx = binding.Context(K, p, device=device)
+    ctx.upload_depth_mm(depth_mm)
+    ctx.frontend()
+    hist = ctx.plane_histogram(np.array(hp.volu_pose, np.float32))   # vol2cam at the identity camera pose = volume pose
+    ctx.close()
+    return hist
 
 
 def broadcast_pose(dist, msg13, device):
@@ -132,13 +168,20 @@ def dev_tensor(ptr, shape, typestr, device):
 class ShardedKinectFusion:
     """kf::kinectfusion on one z-slab of the volume; `dist` is an initialised torch.distributed (NCCL)."""
 
-    def __init__(self, K, hp, dist, rank, world, local):
+    def __init__(self, K, hp, dist, rank, world, local, first_depth=None):
+        """first_depth: the first frame (mm).  When given, slab heights are balanced by the integration work it
+        implies (balanced_bounds); otherwise the volume is cut into equal slabs."""
         import torch
         from . import host
         self.dist, self.rank, self.world = dist, rank, world
         self.device = torch.device("cuda", local)
         Z = hp.volu_dims[2]
-        hp.slab_z_begin, hp.slab_z_end = slab_range(Z, world, rank)
+        self.bounds = None
+        if first_depth is not None and os.environ.get("KFB_SLABS_EQUAL") is None:
+            self.bounds = balanced_bounds(measure_plane_histogram(K, hp, first_depth, local), world)
+            hp.slab_z_begin, hp.slab_z_end = self.bounds[rank], self.bounds[rank + 1]
+        else:
+            hp.slab_z_begin, hp.slab_z_end = slab_range(Z, world, rank)
         hp.shard_rank, hp.shard_world = rank, world
         hp.device = local
         self.kf = host.KinectFusion(K, hp)
@@ -208,7 +251,7 @@ def run_bench(args, dist, rank, world, local, dims, K, frames, host_pin, dev_fra
     n_frames = len(frames)
     w, h = K.width, K.height
     hp = host.default_host_params(dims)
-    skf = ShardedKinectFusion(K, hp, dist, rank, world, local)
+    skf = ShardedKinectFusion(K, hp, dist, rank, world, local, first_depth=frames[0][1])
     ctx = skf.ctx
     dev = torch.device("cuda", local)
 
@@ -266,8 +309,8 @@ def run_bench(args, dist, rank, world, local, dims, K, frames, host_pin, dev_fra
             ctx.integrate(v2c)
             k_ms.append(ctx.event_elapsed_ms(60, 61))
     ctx.set_profiling(False)
-    zs0, zs1 = stored_range(dims, world, rank)
-    zb, ze = slab_range(dims, world, rank)
+    zs0, zs1 = stored_range(dims, world, rank, skf.bounds)
+    zb, ze = (skf.bounds[rank], skf.bounds[rank + 1]) if skf.bounds is not None else slab_range(dims, world, rank)
     own_frac = (ze - max(zb, 1)) / max(zs1 - max(zs0, 1), 1)   # halo planes are integrated redundantly: not counted
     stat = torch.tensor([float(np.mean(U)) * own_frac, float(np.mean(U)), float(np.mean(k_ms))], device=dev, dtype=torch.float64)
     gathered = [torch.zeros_like(stat) for _ in range(world)]
@@ -291,6 +334,7 @@ def run_bench(args, dist, rank, world, local, dims, K, frames, host_pin, dev_fra
                    "frames_timed": S, "updated_voxels_per_frame": U_owned, "swept_voxels_per_frame": dims * dims * (dims - 1),
                    "collectives_per_frame": ("pose mailbox 52 B (shared memory); composite = one kernel over NVLink peer memory" if skf.p2p else "pose mailbox 52 B (shared memory), all_reduce(min) 1.2 MB, reduce(sum) 9.8 MB")},
         "frame_device_ms": ms_per_frame,
+        "slab_bounds": skf.bounds if skf.bounds is not None else [slab_range(dims, world, r)[0] for r in range(world)] + [dims],
         "final_pose": [float(x) for x in poses[-1]],
         "e2e": {"value": U_owned / (e2e_ms / S * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / S,
                 "h2d_bytes_per_step": w * h * 4 * world, "d2h_bytes_per_step": 19 * 27 * 16 + 52 * world,

@@ -24,6 +24,25 @@ def test_slab_partition_covers_volume_once(kfb):
             assert (owned == 1).all()
 
 
+def test_balanced_bounds_properties(kfb):
+    from slam_kinectfusion_b200 import sharded
+    rng = np.random.default_rng(3)
+    for Z in (64, 512, 2048):
+        for world in (2, 4, 8):
+            hist = np.zeros(Z)
+            a, b = sorted(rng.integers(1, Z, 2))
+            hist[a:b + 1] = np.linspace(10, 1000, b + 1 - a) ** 1.5       # work concentrated in a band of planes
+            bd = sharded.balanced_bounds(hist, world, min_planes=4)
+            assert bd[0] == 0 and bd[-1] == Z and len(bd) == world + 1
+            assert all(bd[i + 1] - bd[i] >= 4 for i in range(world))
+            work = hist + 0.02 * hist.max()
+            per = [work[bd[i]:bd[i + 1]].sum() for i in range(world)]
+            if Z >= 512:
+                assert max(per) < 1.5 * (sum(per) / world) + work.max() * 8   # balanced up to plane granularity / minimum height
+            s0, s1 = sharded.stored_range(Z, world, 1, bd)
+            assert s0 == max(bd[1] - sharded.HALO, 0) and s1 == min(bd[2] + sharded.HALO, Z)
+
+
 def test_slab_raycast_oracle_equals_full_single_process(kfo, kfb):
     """The slab semantics themselves (no collectives): min-key composite of 3 slabs == full raycast, bit for bit."""
     from slam_kinectfusion_b200 import sharded
