@@ -415,6 +415,50 @@ def test_pipeline_vs_oracle_poses(kfo, kfb):
     assert len(pts) > 1000
 
 
+@pytest.mark.parametrize("sensor", ["kinect2", "realsense720"])
+def test_pipeline_other_sensors_vs_oracle_poses(kfo, kfb, sensor):
+    """BASELINE configs[2]: the other sensor resolutions the reference supports (512x424, 1280x720), whole
+    pipeline through the facade against the oracle pipeline; the 1e-4 m / 1e-4 rad pose budget."""
+    from slam_kinectfusion_b200 import host
+    kw = kfb.SENSORS[sensor]
+    Ko, Kb = kfo.Intr(**kw), kfb.Intrinsics(**kw)
+    dims = 128
+    okf = kfo.Kinfu(Ko, kfo.default_params(dims))
+    gkf = host.KinectFusion(Kb, kfb.default_host_params(dims))
+    for k in range(6):
+        d = kfo.render_depth_mm(kfo.trajectory_pose(k), Ko)
+        assert okf.pipeline(d) == 0 and gkf.pipeline(d) == 0
+        po, pg = okf.pose().reshape(3, 4).astype(np.float64), gkf.pose().reshape(3, 4).astype(np.float64)
+        assert np.abs(po[:, 3] - pg[:, 3]).max() < 1e-4
+        dR = po[:, :3].T @ pg[:, :3]
+        # rotation angle from the antisymmetric part (arccos of the trace loses everything below 3e-4 rad in f32)
+        ang = 0.5 * np.linalg.norm([dR[2, 1] - dR[1, 2], dR[0, 2] - dR[2, 0], dR[1, 0] - dR[0, 1]])
+        assert ang < 1e-4, ang
+
+
+def test_large_volume_1024_properties(kfo, kfb):
+    """BASELINE configs[3] size on one GPU (1024^3 = 4 GiB packed): the update count doubles per axis as
+    expected (about 8x the 512^3 anchor), the predicate is idempotent, and a raycast of the integrated room
+    hits nearly everywhere and reproduces the depth it was built from to within the truncation distance."""
+    Ko = kfo.intr()
+    Kb = kfb.Intrinsics(**kfb.SENSORS["kinect1"])
+    ctx = _ctx(kfb, Kb, kfb.default_params(1024))
+    d = kfo.render_depth_mm(kfo.identity(), Ko)
+    ctx.upload_depth_mm(d)
+    ctx.frontend()
+    volpose = np.array(kfo.default_params(1024).volu_pose, np.float32)
+    U = ctx.integrate(volpose, count=True)
+    assert 7.6 * 35_941_951 < U < 8.2 * 35_941_951
+    assert ctx.integrate(volpose, count=True) == U
+    c2v = kfo.pose_mul(kfo.pose_inv(volpose), kfo.identity())
+    ctx.raycast(c2v, kfo.rot_inv(c2v))
+    gv, gn = ctx.download_maps(1, 0)
+    hit = gv[..., 2] != 0
+    assert hit.mean() > 0.98
+    err = np.abs(gv[..., 2] - ctx.download_depth(0))[hit]
+    assert np.median(err) < 0.0062 and np.percentile(err, 99) < 0.03
+
+
 def test_full_size_properties_512(kfo, kfb):
     """BASELINE configs[1] size (640x480, 512^3) through size-independent properties: U equals the
     SURVEY anchor, plane 0 untouched, weights == number of passing integrations, raycast of the
