@@ -54,6 +54,8 @@ def load_host_library():
         "kfh_extract_pointcloud": (C.c_long, [_vp, _vp, C.c_long]),
         "kfh_save_pointcloud": (C.c_int, [_vp, C.c_char_p]),
         "kfh_icp_solve": (C.c_int, [_vp, _vp]),
+        "kfh_save_poses": (C.c_int, [_vp, C.c_char_p]),
+        "kfh_read_intrinsics": (C.c_int, [C.c_char_p, _vp]),
         "kfh_icp_probe": (C.c_int, [_vp, _vp, _vp, C.c_int]),
         "kfh_set_shard_comm": (None, [_vp, BCAST_FN, COMPOSITE_FN, _vp]),
     }
@@ -76,6 +78,13 @@ def icp_probe(ctx, iters=(4, 5, 10)):
     out = np.zeros(64, np.float64)
     n = load_host_library().kfh_icp_probe(ctx.h, it, out.ctypes.data_as(_vp), 64)
     return out[:max(n, 0)]
+
+
+def read_intrinsics(path):
+    """Dataset intr.txt -> (fx, cx, fy, cy, depth scale), or None (depth_sensor.cpp:23-46)."""
+    out = np.zeros(5, np.float32)
+    rc = load_host_library().kfh_read_intrinsics(str(path).encode(), out.ctypes.data_as(_vp))
+    return None if rc else out
 
 
 def icp_solve(sums27):
@@ -177,3 +186,6 @@ class KinectFusion:
 
     def save_pointcloud(self, path):
         self.lib.kfh_save_pointcloud(self.h, path.encode())
+
+    def save_poses(self, path):
+        return self.lib.kfh_save_poses(self.h, str(path).encode())

@@ -110,5 +110,10 @@ namespace kf
 namespace file
 {
 void exportPly(const std::string &filename, cv::Mat pointcloud);
+// camera trajectory in the reference's format (main.cpp:94-98: `outfile << pose.matrix << std::endl`, the
+// cv::Matx stream form "[a, b, c, d;\n e, ...]"), one 4x4 per pose
+bool exportPoses(const std::string &filename, const std::vector<cv::Affine3f> &poses);
+// the dataset's intr.txt (depth_sensor.cpp:23-46): up to nine numbers, those > 0.1 are fx, cx, fy, cy, depth scale
+bool readIntrinsics(const std::string &filename, kf::Intrinsics &intr);
 }
 }

@@ -149,6 +149,19 @@ int kfh_icp_probe(void *kfb_ctx_handle, const int *iters_per_level, double *us_o
     kfb_icp_end(ctx);
     return n;
 }
+int kfh_save_poses(void *h, const char *path)
+{
+    kf::kinectfusion *k = static_cast<kf::kinectfusion *>(h);
+    return kf::file::exportPoses(path, k->pose_record) ? 0 : 1;
+}
+/* out5 = fx, cx, fy, cy, depth scale */
+int kfh_read_intrinsics(const char *path, float out5[5])
+{
+    kf::Intrinsics k{0, 0, 0.f, 0.f, 0.f, 0.f};
+    if (!kf::file::readIntrinsics(path, k)) return 1;
+    out5[0] = k.fx; out5[1] = k.cx; out5[2] = k.fy; out5[3] = k.cy; out5[4] = k.c;
+    return 0;
+}
 int kfh_icp_solve(const double in27[27], double x6[6]) { return kf::ICPRegistration::solve(in27, x6) ? 0 : 1; }
 
 } // extern "C"

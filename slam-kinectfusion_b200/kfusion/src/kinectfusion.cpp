@@ -165,6 +165,39 @@ void kf::file::exportPly(const std::string &filename, cv::Mat pointcloud)
     }
 }
 
+// main.cpp:94-98
+bool kf::file::exportPoses(const std::string &filename, const std::vector<cv::Affine3f> &poses)
+{
+    std::ofstream out{filename};
+    if (!out.is_open()) return false;
+    out.precision(8); // cv::Formatter default for float
+    for (const cv::Affine3f &p : poses)
+    {
+        out << "[";
+        for (int i = 0; i < 4; ++i)
+        {
+            for (int j = 0; j < 4; ++j) out << p.matrix(i, j) << (j < 3 ? ", " : "");
+            out << (i < 3 ? ";\n " : "]");
+        }
+        out << std::endl;
+    }
+    return true;
+}
+
+// depth_sensor.cpp:23-46
+bool kf::file::readIntrinsics(const std::string &filename, kf::Intrinsics &intr)
+{
+    std::ifstream in{filename};
+    if (!in.is_open()) return false;
+    std::vector<float> v;
+    float t = 0;
+    for (int i = 0; i < 9 && (in >> t); ++i)
+        if (t > 0.1f) v.push_back(t);
+    if (v.size() != 5) return false;
+    intr.fx = v[0]; intr.cx = v[1]; intr.fy = v[2]; intr.cy = v[3]; intr.c = v[4];
+    return true;
+}
+
 kf::kinectfuison_params kf::kinectfuison_params::default_params()
 {
     kf::kinectfuison_params p;

@@ -100,3 +100,15 @@ def test_host_solve_matches_oracle(kfb, kfo):
         # prediction), the oracle uses the textbook Cholesky: same solution to rounding
         np.testing.assert_allclose(x_h, x_o, rtol=1e-9, atol=1e-13)
     assert host.icp_solve(np.zeros(27))[0] == 1
+
+
+def test_read_intrinsics_follows_reference_rule(tmp_path, kfb):
+    """depth_sensor.cpp:23-46: nine numbers of a 3x3 K, those > 0.1 in reading order are fx, cx, fy, cy, scale."""
+    from slam_kinectfusion_b200 import host
+    f = tmp_path / "intr.txt"
+    f.write_text("525.0 0 319.5\n0 525.0 239.5\n0 0 1\n")
+    got = host.read_intrinsics(f)
+    assert got is not None and np.allclose(got, [525.0, 319.5, 525.0, 239.5, 1.0])
+    f.write_text("525.0 0 319.5\n")
+    assert host.read_intrinsics(f) is None
+    assert host.read_intrinsics(tmp_path / "missing.txt") is None

@@ -413,6 +413,16 @@ def test_pipeline_vs_oracle_poses(kfo, kfb):
     assert img.shape == (h, w, 3) and img.any()
     pts = gkf.extract_pointcloud()
     assert len(pts) > 1000
+    # trajectory export in the reference's stream format (main.cpp:94-98)
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "poses.txt")
+        assert gkf.save_poses(path) == 0
+        txt = open(path).read()
+        mats = [m for m in txt.replace("\n", " ").split("]") if "[" in m]
+        assert len(mats) == len(gkf.poses())
+        first = np.array([[float(v) for v in row.split(",")] for row in mats[0].split("[")[1].split(";")])
+        assert np.array_equal(first, np.eye(4))
 
 
 @pytest.mark.parametrize("sensor", ["kinect2", "realsense720"])
