@@ -541,6 +541,48 @@ def test_integrate_jump_equals_replay(kfo, kfb):
                 os.environ[k] = v
 
 
+def test_integrate_switches_bit_identical(kfo, kfb):
+    """Every work-skipping device (frustum interval, occlusion cut, deep-free-space path, z-chunking, planes per
+    iteration) must leave the volume bit-identical: compare each switch against the plain sweep."""
+    dims = 256
+    Ko, Kb, Po, Pb = make_pair(kfo, kfb, dims, 640, 480)
+    volpose = np.array(Po.volu_pose, np.float32)
+    poses = [kfo.trajectory_pose(k) for k in (0, 25, 60)]
+    frames = [kfo.render_depth_mm(p, Ko) for p in poses]
+    keys = ("KFB_INTEGRATE_NOCULL", "KFB_INTEGRATE_NOOCC", "KFB_INTEGRATE_NOFAST", "KFB_INTEGRATE_ZCHUNKS", "KFB_INTEGRATE_U")
+    saved = {k: os.environ.get(k) for k in keys}
+
+    def run(env):
+        for k in keys:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        ctx = _ctx(kfb, Kb, Pb)
+        n = 0
+        for pose, d in zip(poses, frames):
+            ctx.upload_depth_mm(d)
+            ctx.frontend()
+            n += ctx.integrate(kfo.pose_mul(kfo.pose_inv(pose), volpose), count=True)
+            ctx.integrate(kfo.pose_mul(kfo.pose_inv(pose), volpose))
+        vol = ctx.download_volume()
+        ctx.close()
+        return vol, n
+
+    try:
+        plain, n_plain = run({"KFB_INTEGRATE_NOCULL": "1", "KFB_INTEGRATE_NOFAST": "1", "KFB_INTEGRATE_ZCHUNKS": "1"})
+        assert plain[..., 1].max() >= 6
+        for env in ({}, {"KFB_INTEGRATE_NOFAST": "1"}, {"KFB_INTEGRATE_NOOCC": "1"}, {"KFB_INTEGRATE_ZCHUNKS": "3"},
+                    {"KFB_INTEGRATE_U": "1"}, {"KFB_INTEGRATE_U": "4"}):
+            vol, n = run(env)
+            assert n == n_plain, env
+            assert np.array_equal(vol, plain), env
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
 # ------------------------------------------------------------------------------- z-slab sharding (§8e)
 @pytest.mark.parametrize("world", [2, 3])
 def test_slab_contexts_compose_to_single_gpu_result(kfo, kfb, world):
