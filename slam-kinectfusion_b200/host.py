@@ -55,6 +55,8 @@ def load_host_library():
         "kfh_save_pointcloud": (C.c_int, [_vp, C.c_char_p]),
         "kfh_icp_solve": (C.c_int, [_vp, _vp]),
         "kfh_save_poses": (C.c_int, [_vp, C.c_char_p]),
+        "kfh_save_volume": (C.c_int, [_vp, C.c_char_p]),
+        "kfh_load_volume": (C.c_int, [_vp, C.c_char_p]),
         "kfh_read_intrinsics": (C.c_int, [C.c_char_p, _vp]),
         "kfh_icp_probe": (C.c_int, [_vp, _vp, _vp, C.c_int]),
         "kfh_set_shard_comm": (None, [_vp, BCAST_FN, COMPOSITE_FN, _vp]),
@@ -186,6 +188,12 @@ class KinectFusion:
 
     def save_pointcloud(self, path):
         self.lib.kfh_save_pointcloud(self.h, path.encode())
+
+    def save_volume(self, path):
+        return self.lib.kfh_save_volume(self.h, str(path).encode())
+
+    def load_volume(self, path):
+        return self.lib.kfh_load_volume(self.h, str(path).encode())
 
     def save_poses(self, path):
         return self.lib.kfh_save_poses(self.h, str(path).encode())

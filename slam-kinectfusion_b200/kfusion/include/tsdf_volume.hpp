@@ -28,6 +28,10 @@ public:
     cv::Vec3f SceneSize();
     cv::Vec3i Dims();
     std::vector<int16_t> Data(); // packed {tsdf, weight} pairs, reference index order
+    // volume checkpoint (no reference counterpart): header {magic, dims[3], range[3], trunc}
+    // + the packed voxels in reference index order
+    bool save(const std::string &path);
+    bool load(const std::string &path);
 
 private:
     DeviceContextPtr dev;

@@ -149,6 +149,8 @@ int kfh_icp_probe(void *kfb_ctx_handle, const int *iters_per_level, double *us_o
     kfb_icp_end(ctx);
     return n;
 }
+int kfh_save_volume(void *h, const char *path) { return static_cast<kf::kinectfusion *>(h)->volume()->save(path) ? 0 : 1; }
+int kfh_load_volume(void *h, const char *path) { return static_cast<kf::kinectfusion *>(h)->volume()->load(path) ? 0 : 1; }
 int kfh_save_poses(void *h, const char *path)
 {
     kf::kinectfusion *k = static_cast<kf::kinectfusion *>(h);

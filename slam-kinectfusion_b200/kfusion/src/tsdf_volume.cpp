@@ -2,6 +2,8 @@
 // (mirrors kfusion/src/tsdf_volume.cpp:13-84 of the reference).
 #include <tsdf_volume.hpp>
 #include <safe_call.hpp>
+#include <cstdio>
+#include <cstring>
 
 namespace kf
 {
@@ -10,6 +12,49 @@ std::vector<int16_t> TSDFVolume::Data()
     std::vector<int16_t> out(2 * kfb_volume_voxels(dev->ctx));
     kfbSafeCall(dev->ctx, kfb_download_volume(dev->ctx, out.data()));
     return out;
+}
+namespace
+{
+struct CheckpointHeader
+{
+    char magic[8]; // "KFB200V1"
+    int32_t dims[3];
+    float range[3];
+    float trunc;
+    uint64_t voxels;
+};
+} // namespace
+bool TSDFVolume::save(const std::string &path)
+{
+    const std::vector<int16_t> data = Data();
+    CheckpointHeader h;
+    std::memcpy(h.magic, "KFB200V1", 8);
+    for (int i = 0; i < 3; ++i) { h.dims[i] = dims(i); h.range[i] = scene_size(i); }
+    h.trunc = trun_dist;
+    h.voxels = data.size() / 2;
+    std::FILE *f = std::fopen(path.c_str(), "wb");
+    if (!f) return false;
+    bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 && std::fwrite(data.data(), sizeof(int16_t), data.size(), f) == data.size();
+    ok = (std::fclose(f) == 0) && ok;
+    return ok;
+}
+bool TSDFVolume::load(const std::string &path)
+{
+    std::FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    CheckpointHeader h;
+    bool ok = std::fread(&h, sizeof(h), 1, f) == 1 && std::memcmp(h.magic, "KFB200V1", 8) == 0;
+    for (int i = 0; i < 3 && ok; ++i) ok = h.dims[i] == dims(i) && h.range[i] == scene_size(i);
+    ok = ok && h.voxels == kfb_volume_voxels(dev->ctx);
+    std::vector<int16_t> data;
+    if (ok)
+    {
+        data.resize(2 * (size_t)h.voxels);
+        ok = std::fread(data.data(), sizeof(int16_t), data.size(), f) == data.size();
+    }
+    std::fclose(f);
+    if (!ok) return false;
+    return kfbSafeCall(dev->ctx, kfb_upload_volume(dev->ctx, data.data())) == KFB_OK;
 }
 cv::Vec3f TSDFVolume::VoxelSize() { return voxel_size; }
 cv::Vec3f TSDFVolume::SceneSize() { return scene_size; }

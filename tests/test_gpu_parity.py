@@ -423,6 +423,20 @@ def test_pipeline_vs_oracle_poses(kfo, kfb):
         assert len(mats) == len(gkf.poses())
         first = np.array([[float(v) for v in row.split(",")] for row in mats[0].split("[")[1].split(";")])
         assert np.array_equal(first, np.eye(4))
+        # volume checkpoint: a second instance loads it and raycasts the same model
+        vpath = os.path.join(td, "volume.kfb")
+        assert gkf.save_volume(vpath) == 0
+        other = host.KinectFusion(Kb, Ph)
+        assert other.load_volume(vpath) == 0
+        assert np.array_equal(other.context().download_volume(), gkf.context().download_volume())
+        volpose = np.array(Ph.volu_pose, np.float32)
+        c2v = kfo.pose_mul(kfo.pose_inv(volpose), gkf.pose())
+        for kfx in (gkf, other):
+            kfx.context().raycast(c2v, kfo.rot_inv(c2v))
+        va, na = gkf.context().download_maps(1, 0)
+        vb, nb = other.context().download_maps(1, 0)
+        assert np.array_equal(va.view(np.int32), vb.view(np.int32)) and np.array_equal(na.view(np.int32), nb.view(np.int32))
+        assert other.load_volume(os.path.join(td, "poses.txt")) == 1     # not a checkpoint
 
 
 @pytest.mark.parametrize("sensor", ["kinect2", "realsense720"])
