@@ -63,6 +63,7 @@ struct IntegrateArgs
     int w, h;
     const float2 *thrz;
     unsigned long long *states; // [chunk][6][X/4 * Y]: packed vc of every thread after plane zstart(chunk) - 1
+    int2 *col_range;            // [X/4 * Y]: first and last plane of the column group's frustum interval (empty: {1, 0})
     int nchunks;
     const float2 *exact;
     const float4 *wtab;
@@ -521,34 +522,27 @@ __global__ void __launch_bounds__(32 * KFB_INT_WARPS, KFB_INT_MINB * 4 / KFB_INT
     const int zend = min(zstart + a.zchunk, a.ze);
     if (zstart >= zend) return;
 
-    // vc at z = 0: R * (x*vs.x, y*vs.y, 0*vs.z) + t   (tsdf_volume.cu:49-50)
+    // whole-column frustum interval, computed once per column by column_states_kernel (see frustum_interval)
+    const int2 cr = __ldg(a.col_range + (size_t)y * (a.X >> 2) + (x0 >> 2));
+    const int za = max(zstart, cr.x);
+    int zb = min(zend - 1, cr.y);
+    if (za > zb) return;
+    // vc at z = 0 of the first and the last of the four columns: R * (x*vs.x, y*vs.y, 0*vs.z) + t
+    // (tsdf_volume.cu:49-50); the running sums themselves come from the stored chunk states below
     unsigned long long xy[4], zz[2];
     float z0v[4];
     {
         const float py = __fmul_rn((float)y, a.vsy);
         const float pz = __fmul_rn(0.f, a.vsz);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < 4; k += 3)
         {
             const float px = __fmul_rn((float)(x0 + k), a.vsx);
             const float3 r = rot3(a.pose.R, px, py, pz);
             z0v[k] = __fadd_rn(r.z, a.pose.t[2]);
             xy[k] = pack2(__fadd_rn(r.x, a.pose.t[0]), __fadd_rn(r.y, a.pose.t[1]));
         }
-        zz[0] = pack2(z0v[0], z0v[1]);
-        zz[1] = pack2(z0v[2], z0v[3]);
     }
-    // conservative frustum interval of this thread's four columns (see frustum_interval)
-    float lo, hi;
-    {
-        float ax, ay, bx_, by_;
-        unpack2(xy[0], ax, ay);
-        unpack2(xy[3], bx_, by_);
-        frustum_interval(a, ax, ay, z0v[0], bx_, by_, z0v[3], zstart, zend, lo, hi);
-    }
-    const int za = max(zstart, (int)floorf(lo));
-    int zb = min(zend - 1, (int)ceilf(hi));
-    if (za > zb) return;
     bool deep_free = false;
     // Occlusion cut: over planes [za, zb] the four columns project into a pixel rectangle (a line segment per
     // column; computed from the affine model and widened by the drift bound).  A voxel is rejected once vc.z
@@ -795,6 +789,7 @@ __global__ void __launch_bounds__(128) column_states_kernel(const IntegrateArgs 
         frustum_interval(a, vx[0], vy[0], vz[0], vx[3], vy[3], vz[3], a.zb, a.ze, lo, hi);
         z_first = max(a.zb, (int)floorf(lo));
         z_last = min(a.ze - 1, (int)ceilf(hi));
+        a.col_range[(size_t)y * (a.X >> 2) + (x0 >> 2)] = make_int2(z_first, z_last);
         if (z_first > z_last) return;
     }
     const float sx = a.pose.R.m[2], sy = a.pose.R.m[5], sz = a.pose.R.m[8];
@@ -944,7 +939,7 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
     a.zchunk = (planes + zc - 1) / zc;
     a.nchunks = zc;
     {
-        const size_t need = (size_t)zc * 48 * nthr;
+        const size_t need = (size_t)zc * 48 * nthr + nthr * sizeof(int2);
         if (need > ctx->states_bytes)
         {
             KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -954,6 +949,7 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
             ctx->states_bytes = need;
         }
         a.states = ctx->states;
+        a.col_range = reinterpret_cast<int2 *>(ctx->states + (size_t)zc * 6 * nthr);
         dim3 sb(32, 4), sg((a.X + 127) / 128, (a.Y + 3) / 4);
         column_states_kernel<<<sg, sb, 0, ctx->stream>>>(a);
         KFB_LAUNCH_CHECK(ctx);
