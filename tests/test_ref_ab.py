@@ -255,3 +255,45 @@ def test_integrate_raycast_bit_exact_geometries(kfo, kfb, kref, sensor, case):
         wv, wn, _ = rv.raycast(c2v, rinv, Ko)
         assert np.array_equal(gv.view(np.int32), wv.view(np.int32)), case
         assert np.array_equal(gn.view(np.int32), wn.view(np.int32)), case
+
+
+def test_ragged_sizes_bit_exact(kfo, kfb, kref):
+    """Image sizes that are no multiple of any tile (331 x 250) and a volume whose size is no power of two
+    (100^3, 13 bricks per axis with a partial last brick): front end against the oracle, integrate / raycast /
+    model pyramid against the reference kernels, bit for bit."""
+    w, h, dims = 331, 250, 100
+    s = w / 640.0
+    kw = dict(width=w, height=h, fx=525.0 * s, fy=525.0 * s, cx=(319.5 + 0.5) * s - 0.5, cy=(239.5 + 0.5) * h / 480.0 - 0.5)
+    Ko, Kb = kfo.Intr(**kw), kfb.Intrinsics(**kw)
+    Pb = kfb.default_params(dims)
+    volpose = np.array(kfo.default_params(dims).volu_pose, np.float32)
+    ctx = kfb.Context(Kb, Pb)
+    rv = kref.RefVolume(dims)
+    rv.upload(np.zeros((dims, dims, dims, 2), np.int16))
+    for k in (0, 9, 18):
+        cam = kfo.trajectory_pose(k)
+        d = kfo.render_depth_mm(cam, Ko)
+        lv = kfo.frontend(d, Ko)
+        ctx.upload_depth_mm(d)
+        ctx.frontend()
+        for l in range(3):
+            assert np.array_equal(ctx.download_raw_depth(l), lv[l][3]) if len(lv[l]) > 3 else True
+            gd = ctx.download_depth(l)
+            assert np.array_equal(gd == 0, lv[l][0] == 0)
+            assert np.abs(gd - lv[l][0]).max() < 2e-6
+        dm = ctx.download_depth(0)
+        v2c = kfo.pose_mul(kfo.pose_inv(cam), volpose)
+        ctx.integrate(v2c)
+        rv.integrate(v2c, dm, Ko)
+    assert np.array_equal(ctx.download_volume(), rv.download())
+    c2v = kfo.pose_mul(kfo.pose_inv(volpose), kfo.trajectory_pose(12))
+    rinv = kfo.rot_inv(c2v)
+    ctx.raycast(c2v, rinv)
+    ctx.model_pyramid()
+    gv, gn = ctx.download_maps(1, 0)
+    wv, wn, _ = rv.raycast(c2v, rinv, Ko)
+    assert (wv[..., 2] != 0).mean() > 0.5
+    assert np.array_equal(gv.view(np.int32), wv.view(np.int32)) and np.array_equal(gn.view(np.int32), wn.view(np.int32))
+    v1, n1 = kref.resize_maps(wv, wn)
+    g1v, g1n = ctx.download_maps(1, 1)
+    assert np.array_equal(g1v.view(np.int32), v1.view(np.int32)) and np.array_equal(g1n.view(np.int32), n1.view(np.int32))
