@@ -884,6 +884,7 @@ int launch_build_tables(kfb_ctx *ctx, cudaStream_t stream)
 int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_updated)
 {
     const Intr &k = ctx->L[0].k;
+    if (ctx->profiling) cudaEventRecord(ctx->events[56], ctx->stream); // whole call: 56 .. 57
     IntegrateArgs a;
     a.vol = ctx->vol;
     a.X = ctx->p.volu_dims[0];
@@ -976,7 +977,9 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
         if (ctx->profiling) cudaEventRecord(ctx->events[61], ctx->stream);
     }
     KFB_CUDA(ctx, cudaEventRecord(ctx->ev_tables_free, ctx->stream)); // the next frame's tables may now be built
-    return launch_brick_distance(ctx);
+    const int rcd = launch_brick_distance(ctx);
+    if (ctx->profiling) cudaEventRecord(ctx->events[57], ctx->stream);
+    return rcd;
 }
 
 int launch_build_wtab(kfb_ctx *ctx)

@@ -36,3 +36,16 @@ print("final->posted (validation wait)", (R[:, 2] - R[:, 1]).tolist())
 print("posted->released (predict)", (R[:-1, 3] - R[:-1, 2]).tolist())
 print("released->next entry", (R[1:, 0] - R[:-1, 3]).tolist())
 print("period", np.diff(R[:, 0]).tolist())
+
+# device-side stage times of pipelined frames (events recorded by the library when profiling is on)
+kf.reset()
+ctx.set_profiling(True)
+rows = []
+for i, (_, d) in enumerate(frames):
+    assert kf.pipeline(d) == 0
+    if i >= 5:
+        ctx.synchronize()      # events of this frame are complete (serialises the frames: stage times only)
+        rows.append((ctx.event_elapsed_ms(56, 57), ctx.event_elapsed_ms(60, 61), ctx.event_elapsed_ms(57, 58), ctx.event_elapsed_ms(58, 59)))
+ctx.set_profiling(False)
+R = np.array(rows) * 1e3
+print("us: integrate call %.1f (kernel %.1f), gap to raycast %.1f, raycast %.1f" % tuple(np.median(R, axis=0)))
