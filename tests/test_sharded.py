@@ -100,3 +100,28 @@ def test_composite_protocol_gloo_world2(tmp_path, kfo, kfb):
     assert all(p.returncode == 0 for p in procs), "\n".join(logs)
     ok_v, ok_n, hits = map(int, out.read_text().split())
     assert ok_v == 1 and ok_n == 1 and hits > 1000
+
+
+@pytest.mark.gpu
+def test_two_gpu_sharded_run_equals_single_gpu(kfb):
+    """End to end on real GPUs (skipped on a single-GPU box): two z-slab ranks under torchrun (peer-memory
+    composite, balanced slabs, pose mailbox) must track EXACTLY like one GPU holding the whole volume -- the
+    slab volumes and the composite are bit-identical, hence so are the ICP sums and the poses."""
+    import json
+    if kfb.load_library().kfb_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from slam_kinectfusion_b200 import synth
+    dims, steps, warm = 256, 6, 3
+    env = dict(os.environ)
+    env.pop("RANK", None)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", str(29600 + os.getpid() % 300), os.path.join(ROOT, "bench.py"), "--gpus", "2", "--dims", str(dims),
+                          "--steps", str(steps), "--warmup", str(warm)], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["n_gpus"] == 2 and line["value"] > 0
+    K = kfb.Intrinsics(**kfb.SENSORS["kinect1"])
+    kf = kfb.KinectFusion(K, kfb.default_host_params(dims))
+    for _, d in synth.sequence(1 + warm + steps, K):
+        assert kf.pipeline(d) == 0
+    assert np.array_equal(np.asarray(line["final_pose"], np.float32), kf.pose())
