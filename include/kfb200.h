@@ -98,6 +98,10 @@ int kfb_reset_frames(kfb_ctx *ctx);                                     /* Frame
  * pinned host memory (asynchronous on the context stream when pinned) or a device pointer
  * (frame already resident in HBM: device-to-device copy). */
 int kfb_upload_depth_mm(kfb_ctx *ctx, const float *host, int width, int height);
+/* The same from the sensor's native 16-bit millimetre image (what depth_sensor.cpp:186-196 converts to float on
+ * the host before the upload): half the PCIe bytes, the conversion to f32 runs on the device.  Pinned host or
+ * device pointers are used in place, pageable ones are staged. */
+int kfb_upload_depth_mm_u16(kfb_ctx *ctx, const uint16_t *host, int width, int height);
 /* cv::cuda::pyrDown x(L-1), cv::cuda::bilateralFilter xL, device::depthTruncation xL,
  * device::getVertexmap xL, device::getNormalmap xL -- kinectfusion.cpp:54-75,
  * device_types.hpp:122-124.  Fills the CURRENT frame's depth/vertex/normal pyramids. */

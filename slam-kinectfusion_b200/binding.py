@@ -85,6 +85,7 @@ def load_library():
         "kfb_reset_volume": (C.c_int, [_vp]),
         "kfb_reset_frames": (C.c_int, [_vp]),
         "kfb_upload_depth_mm": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+        "kfb_upload_depth_mm_u16": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
         "kfb_frontend": (C.c_int, [_vp]),
         "kfb_swap_frames": (C.c_int, [_vp]),
         "kfb_icp_accumulate": (C.c_int, [_vp, C.c_int, _vp, _vp]),
@@ -179,6 +180,11 @@ class Context:
         d = _f32(depth_mm)
         self._keep = d
         self._ck(self.lib.kfb_upload_depth_mm(self.h, _ptr(d), d.shape[1], d.shape[0]))
+
+    def upload_depth_mm_u16(self, depth_mm_u16):
+        d = np.ascontiguousarray(depth_mm_u16, dtype=np.uint16)
+        self._keep = d
+        self._ck(self.lib.kfb_upload_depth_mm_u16(self.h, _ptr(d), d.shape[1], d.shape[0]))
 
     def upload_depth_mm_ptr(self, ptr, w, h):
         self._ck(self.lib.kfb_upload_depth_mm(self.h, ptr, w, h))

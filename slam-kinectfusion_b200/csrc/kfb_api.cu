@@ -103,7 +103,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->tab_thrz = nullptr; ctx->tab_exact = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->zmip = nullptr; ctx->bricks = nullptr; ctx->states = nullptr; ctx->states_bytes = 0;
     ctx->bdist = ctx->bdist_tmp = ctx->bdist_tmp2 = nullptr; ctx->bdirty = nullptr;
     ctx->hit_t = nullptr; ctx->icp_partials = nullptr; ctx->icp_ticket = nullptr; ctx->counters = nullptr;
-    ctx->counters_host = nullptr; ctx->pinned_depth = nullptr; ctx->render_dev = nullptr; ctx->render_host = nullptr;
+    ctx->counters_host = nullptr; ctx->pinned_depth = nullptr; ctx->depth_u16 = nullptr; ctx->render_dev = nullptr; ctx->render_host = nullptr;
     ctx->stream = nullptr; ctx->own_stream = 1;
     ctx->fstream = nullptr; ctx->ev_front = nullptr; ctx->ev_free = nullptr; ctx->ev_tables_free = nullptr; ctx->front_pending = 0;
     ctx->icp_host = nullptr; ctx->icp_gate_host = nullptr; ctx->icp_devgate = nullptr; ctx->icp_mirror = nullptr;
@@ -202,6 +202,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     KFB_CUDA(ctx, cudaMemset(ctx->counters, 0, 8 * sizeof(unsigned long long)));
     KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->counters_host, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
     KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->pinned_depth, n0 * sizeof(float), cudaHostAllocDefault));
+    KFB_CUDA(ctx, cudaMalloc(&ctx->depth_u16, n0 * sizeof(uint16_t)));
     KFB_CUDA(ctx, cudaMalloc(&ctx->render_dev, n0 * 3));
     KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->render_host, n0 * 3, cudaHostAllocDefault));
     for (int i = 0; i < 64; ++i) KFB_CUDA(ctx, cudaEventCreate(&ctx->events[i]));
@@ -263,6 +264,7 @@ void kfb_destroy(kfb_ctx *ctx)
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->counters_host) cudaFreeHost(ctx->counters_host);
     if (ctx->pinned_depth) cudaFreeHost(ctx->pinned_depth);
+    if (ctx->depth_u16) cudaFree(ctx->depth_u16);
     if (ctx->render_dev) cudaFree(ctx->render_dev);
     if (ctx->render_host) cudaFreeHost(ctx->render_host);
     if (ctx->cloud) cudaFree(ctx->cloud);
@@ -342,6 +344,31 @@ int kfb_upload_depth_mm(kfb_ctx *ctx, const float *host, int width, int height)
     const int rc = fork_front(ctx);
     if (rc) return rc;
     KFB_CUDA(ctx, cudaMemcpyAsync(ctx->L[0].raw, host, bytes, cudaMemcpyDefault, ctx->fstream));
+    KFB_CUDA(ctx, cudaEventRecord(ctx->ev_front, ctx->fstream));
+    ctx->front_pending = 1;
+    return KFB_OK;
+}
+
+int kfb_upload_depth_mm_u16(kfb_ctx *ctx, const uint16_t *host, int width, int height)
+{
+    if (!host || width != ctx->intr.width || height != ctx->intr.height) { ctx->err = "depth size mismatch"; return KFB_ERR_INVALID; }
+    const size_t n = (size_t)width * height, bytes = n * sizeof(uint16_t);
+    cudaPointerAttributes at;
+    bool direct = false;
+    if (cudaPointerGetAttributes(&at, host) == cudaSuccess)
+        direct = (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
+    else cudaGetLastError();
+    if (!direct)
+    {
+        KFB_CUDA(ctx, cudaStreamSynchronize(ctx->fstream)); // staging buffer may still be in flight
+        memcpy(ctx->pinned_depth, host, bytes);             // the f32 staging buffer is large enough
+        host = reinterpret_cast<const uint16_t *>(ctx->pinned_depth);
+    }
+    int rc = fork_front(ctx);
+    if (rc) return rc;
+    KFB_CUDA(ctx, cudaMemcpyAsync(ctx->depth_u16, host, bytes, cudaMemcpyDefault, ctx->fstream));
+    rc = launch_u16_to_f32(ctx, ctx->depth_u16, ctx->L[0].raw, n, ctx->fstream);
+    if (rc) return rc;
     KFB_CUDA(ctx, cudaEventRecord(ctx->ev_front, ctx->fstream));
     ctx->front_pending = 1;
     return KFB_OK;

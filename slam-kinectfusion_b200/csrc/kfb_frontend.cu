@@ -268,6 +268,18 @@ int launch_frontend(kfb_ctx *ctx)
     return KFB_OK;
 }
 
+__global__ void u16_to_f32_kernel(const uint16_t *__restrict__ src, float *__restrict__ dst, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (float)src[i]; // exact: the sensor's millimetres, as depth_sensor.cpp:192 converts them
+}
+int launch_u16_to_f32(kfb_ctx *ctx, const uint16_t *src, float *dst, size_t n, cudaStream_t stream)
+{
+    u16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, dst, n);
+    KFB_LAUNCH_CHECK(ctx);
+    return KFB_OK;
+}
+
 int launch_model_pyramid(kfb_ctx *ctx)
 {
     if (ctx->pyramid_fresh) { ctx->pyramid_fresh = 0; return KFB_OK; } // done by the raycast epilogue

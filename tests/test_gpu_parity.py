@@ -52,6 +52,23 @@ def test_frontend_all_sensors(kfo, kfb, sensor):
         assert _nan_mask_equal(gn, wn)   # NaN = invalid normal, 0 = border (§9 Q6), bit-exact masks
 
 
+def test_u16_ingest_equals_f32_ingest(kfo, kfb):
+    """The 16-bit millimetre upload (sensor-native) gives exactly the front end of the f32 upload."""
+    Ko, Kb, Po, Pb = make_pair(kfo, kfb, 64, 640, 480)
+    d = kfo.render_depth_mm(kfo.trajectory_pose(3), Ko)
+    a, b = _ctx(kfb, Kb, Pb), _ctx(kfb, Kb, Pb)
+    a.upload_depth_mm(d)
+    a.frontend()
+    b.upload_depth_mm_u16(d.astype(np.uint16))
+    b.frontend()
+    for l in range(3):
+        assert np.array_equal(a.download_raw_depth(l), b.download_raw_depth(l))
+        assert np.array_equal(a.download_depth(l), b.download_depth(l))
+        va, na = a.download_maps(0, l)
+        vb, nb = b.download_maps(0, l)
+        assert np.array_equal(va.view(np.int32), vb.view(np.int32)) and np.array_equal(na.view(np.int32), nb.view(np.int32))
+
+
 def test_pyrdown_bit_exact(kfo, kfb):
     """pyrDown (raw millimetre chain, REFLECT_101) is bit-exact against the oracle's FMA chain."""
     for sensor in ("kinect1", "kinect2"):
