@@ -1,19 +1,20 @@
-// kfb_icp.cu -- projective-data-association point-to-plane ICP, one fused kernel per
-// iteration (replaces kf::device::rigidICP, kfusion/src/rigid_icp.cu:46-169).
+// kfb_icp.cu -- projective-data-association point-to-plane ICP (replaces kf::device::rigidICP,
+// kfusion/src/rigid_icp.cu:46-169, and the device side of ICPRegistration::rigidTransform's loop,
+// kfusion/src/icp_registration.cpp:21-43).
 //
-// One launch does correspondence search, gating, the residual row [s x n, n, n.(d-s)] and the
-// 27 unique products of the 6x7 normal equations, reduces them with warp-shuffle trees, one
-// shared-memory stage per block, and a single-pass grid reduction (last-block-done ticket,
-// fixed summation order => bit-reproducible), and writes the 27 sums straight into mapped
-// pinned host memory followed by a sequence flag.  The host spins on the flag: no cudaMemcpy,
-// no allocation, no second kernel, no device sync per iteration (the reference does
-// 2 launches + 2 cudaMalloc + 2 cudaFree + a blocking memcpy).
+// One accumulation does correspondence search, gating, the residual row [s x n, n, n.(d-s)] and the 27 unique
+// products of the 6x7 normal equations, reduces them with a transposing warp exchange, one shared-memory stage
+// per block and a single-pass grid reduction (last-block-done ticket, fixed summation order => bit-reproducible),
+// and writes the 27 sums as tagged 16-byte chunks straight into mapped pinned host memory.  The host spins on
+// the tags: no cudaMemcpy, no allocation, no second kernel, no device sync per iteration (the reference does
+// 2 launches + 2 cudaMalloc + 2 cudaFree + a blocking memcpy).  Two drivers share the code:
+// icp_kernel (one launch per kfb_icp_accumulate) and icp_persistent_kernel (the whole schedule in one launch,
+// with the host round trip hidden by verified pose prediction -- see the comment at that kernel).
 //
-// Numerics: products are f32 exactly as in the reference
-// (`smem[tid] = row[i]*row[j]`), sums are carried in f64 end to end (the reference rounds
-// per-32x32-tile sums to f32 in between; the difference is ~1e-7 relative per entry and far
-// below the 1e-4 pose tolerance).  Coverage: compat_icp_rows reproduces the reference's
-// truncated grid floor(w/32) x floor(h/32) tiles (§9 Q7).
+// Numerics: products are f32 exactly as in the reference (`smem[tid] = row[i]*row[j]`),
+// sums are carried in f64 end to end (the reference rounds per-32x32-tile sums to f32 in between; the
+// difference is ~1e-7 relative per entry and far below the 1e-4 pose tolerance).  Coverage: compat_icp_rows
+// reproduces the reference's truncated grid floor(w/32) x floor(h/32) tiles (§9 Q7).
 #include "kfb_common.cuh"
 #include <xmmintrin.h>
 #include <cstring>

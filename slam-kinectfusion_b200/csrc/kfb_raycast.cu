@@ -7,7 +7,10 @@
 // normal = normalised central difference of six trilinear fetches, outputs rotated back to the
 // camera frame, explicit zeros on a miss.  The running sums `nextp += dir*voxel_size` and
 // `ray_len += step` are replayed exactly, step for step.  Structure is new:
-//   * a warp owns an 8x4 pixel tile (coherent rays);
+//   * a warp owns an 8x4 pixel tile (coherent rays) and marches it cooperatively: when no ray needs a fetch the
+//     warp skips the minimum of the rays' safe step counts, otherwise four steps are classified and their loads
+//     issued before the first sign test; candidate hits are parked and their normals computed after the march;
+//     the two coarser levels of the model pyramid are written from the tile by register shuffles;
 //   * empty-space skipping that cannot change a result: a terminal event (hit or back-face stop) needs
 //     one negative and one positive sample in consecutive steps, and consecutive samples are at most two
 //     voxels apart per axis, so a sample whose 8^3 brick has no negative voxel within two voxels (the byte
