@@ -308,7 +308,7 @@ __device__ __noinline__ bool icp_predict_pose(const double *in27, const float *c
         for (int q = 0; q < j; ++q) { t[j][q] = __dmul_rn(L[j][q], d[q]); dj = __dsub_rn(dj, __dmul_rn(L[j][q], t[j][q])); }
         if (!(dj > 0.0)) return false;
         d[j] = dj;
-        inv[j] = __ddiv_rn(1.0, dj);
+        inv[j] = __drcp_rn(dj);
 #pragma unroll
         for (int i = j + 1; i < 6; ++i)
         {
@@ -342,7 +342,7 @@ __device__ __noinline__ bool icp_predict_pose(const double *in27, const float *c
     {
         double sn, c;
         sincos(theta, &sn, &c);
-        const double c1 = __dsub_rn(1.0, c), it = __ddiv_rn(1.0, theta);
+        const double c1 = __dsub_rn(1.0, c), it = __drcp_rn(theta);
         const double ux = __dmul_rn(rx, it), uy = __dmul_rn(ry, it), uz = __dmul_rn(rz, it);
         const double xx = __dmul_rn(__dmul_rn(c1, ux), ux), yy = __dmul_rn(__dmul_rn(c1, uy), uy), zz = __dmul_rn(__dmul_rn(c1, uz), uz);
         const double xy = __dmul_rn(__dmul_rn(c1, ux), uy), xz = __dmul_rn(__dmul_rn(c1, ux), uz), yz = __dmul_rn(__dmul_rn(c1, uy), uz);
