@@ -73,6 +73,7 @@ struct IntegrateArgs
     float Sx, Sy, Sz, invSz, driftE; // per-plane step of vc (float), 1/Sz, bound on the running-sum drift
     int max_weight;
     int no_fastpath;            // KFB_INTEGRATE_NOFAST: disable the deep-free-space path (tuning / testing)
+    int diag;                   // KFB_INTEGRATE_DIAG (timing experiments ONLY, results are wrong): 1 = general-path warps return, 2 = fast-path warps return
     int use_jump, jump_min; // exact jump of the running sum for prefixes of at least jump_min planes
     uint8_t *bricks;
     int *bdirty;         // set when a brick flag flips 0 -> 1 (the distance map must be rebuilt)
@@ -367,6 +368,18 @@ __device__ __noinline__ unsigned int update_generic(unsigned int wv, float t, in
     return ((unsigned)q & 0xffffu) | ((unsigned)nw << 16);
 }
 // same result without the XU pipe for weights in [0, max_weight] (everything this library ever writes)
+__device__ __forceinline__ unsigned int update_word_e(unsigned int wv, float t, const float4 e)
+{
+    const int tsv = (int)(short)(wv & 0xffffu);
+    const float tsf = __fsub_rn(__int_as_float(KFB_MAGIC_I + tsv), KFB_MAGIC_F);     // (float)tsv, exact
+    const float pre = __fmul_rn(tsf, KFB_DIVSHORTMAX);
+    const float nt = __fmul_rn(e.y, __fmaf_rn(pre, e.x, t));
+    const float s = __fmul_rn(nt, (float)KFB_SHORTMAX);                               // |s| < 2^16 here
+    int qa = __float_as_int(__fadd_rz(fabsf(s), 8388608.0f)) - 0x4B000000;            // trunc(|s|)
+    qa = min(qa, KFB_SHORTMAX);
+    const int q = s < 0.f ? -qa : qa;
+    return ((unsigned)q & 0xffffu) | __float_as_uint(e.z);
+}
 __device__ __forceinline__ unsigned int update_word(unsigned int wv, float t, const IntegrateArgs &a)
 {
     const int wt = (int)wv >> 16;
@@ -384,11 +397,10 @@ __device__ __forceinline__ unsigned int update_word(unsigned int wv, float t, co
 }
 
 // exact sdf evaluation for a voxel in the band around the surface (tsdf_volume.cu:63-71)
-__device__ __forceinline__ float band_tsdf(const IntegrateArgs &a, unsigned long long xy, float cz, int p, float rtrunc)
+__device__ __forceinline__ float band_tsdf(const IntegrateArgs &a, unsigned long long xy, float cz, const float2 e, float rtrunc)
 {
     float vxk, vyk;
     unpack2(xy, vxk, vyk);
-    const float2 e = __ldg(a.exact + p);
     const float d2 = dot3c(vxk, vyk, cz, vxk, vyk, cz);
     const float nsdf = __fmaf_rn(e.y, __fsqrt_rn(d2), -e.x);
     return nsdf <= a.trunc ? fminf(1.f, __fmul_rn(rtrunc, -nsdf)) : KFB_SKIP;
@@ -431,16 +443,23 @@ __device__ __forceinline__ float classify_generic(const IntegrateArgs &a, float 
 // bricks within two voxels of a sample that just turned negative (see kfb_raycast.cu for why two)
 __device__ __noinline__ void mark_bricks(uint8_t *flags, int *dirty, int gbx, int gby, int gbz, int gbz0, int x0, int y, int z)
 {
+    // each axis reaches at most two bricks (x: 8 voxels from x0 - 2; y, z: +-2): the <= 8 flags are read together
     const int bx0 = max(x0 - 2, 0) >> 3, bx1 = min((x0 + 5) >> 3, gbx - 1);
     const int by0 = max(y - 2, 0) >> 3, by1 = min((y + 2) >> 3, gby - 1);
     const int bz0 = max((max(z - 2, 0) >> 3) - gbz0, 0), bz1 = min(((z + 2) >> 3) - gbz0, gbz - 1);
-    for (int bz = bz0; bz <= bz1; ++bz)
-        for (int by = by0; by <= by1; ++by)
-            for (int bx = bx0; bx <= bx1; ++bx)
-            {
-                uint8_t *f = flags + ((size_t)bz * gby + by) * gbx + bx;
-                if (*f == 0) { *f = 1; *dirty = 1; }
-            }
+    if (bz1 < bz0 || by1 < by0 || bx1 < bx0) return;
+    uint8_t *f[8];
+    uint8_t v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        f[i] = flags + ((size_t)((i & 4) ? bz1 : bz0) * gby + ((i & 2) ? by1 : by0)) * gbx + ((i & 1) ? bx1 : bx0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = *f[i];
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (v[i] == 0) { *f[i] = 1; any = true; }
+    if (any) *dirty = 1;
 }
 
 // Conservative interval [lo, hi] of planes in [zstart, zend) on which any of a thread's four columns can pass the
@@ -484,10 +503,26 @@ __device__ __forceinline__ void update_quad(const IntegrateArgs &a, uint4 *vp, c
     }
     else
     {
-        if (t[0] != KFB_SKIP) { o.x = update_word(wd.x, t[0], a); if (COUNT) ++n_upd; }
-        if (t[1] != KFB_SKIP) { o.y = update_word(wd.y, t[1], a); if (COUNT) ++n_upd; }
-        if (t[2] != KFB_SKIP) { o.z = update_word(wd.z, t[2], a); if (COUNT) ++n_upd; }
-        if (t[3] != KFB_SKIP) { o.w = update_word(wd.w, t[3], a); if (COUNT) ++n_upd; }
+        const unsigned int w0 = wd.x >> 16, w1 = wd.y >> 16, w2 = wd.z >> 16, w3 = wd.w >> 16, mw = (unsigned)a.max_weight;
+        if (max(max(w0, w1), max(w2, w3)) <= mw)
+        {
+            // the four table entries together (one latency), then branch-free selects
+            const float4 e0 = __ldg(a.wtab + w0), e1 = __ldg(a.wtab + w1), e2 = __ldg(a.wtab + w2), e3 = __ldg(a.wtab + w3);
+            const unsigned int n0 = update_word_e(wd.x, t[0], e0), n1 = update_word_e(wd.y, t[1], e1);
+            const unsigned int n2 = update_word_e(wd.z, t[2], e2), n3 = update_word_e(wd.w, t[3], e3);
+            o.x = t[0] != KFB_SKIP ? n0 : wd.x;
+            o.y = t[1] != KFB_SKIP ? n1 : wd.y;
+            o.z = t[2] != KFB_SKIP ? n2 : wd.z;
+            o.w = t[3] != KFB_SKIP ? n3 : wd.w;
+            if (COUNT) n_upd += (t[0] != KFB_SKIP) + (t[1] != KFB_SKIP) + (t[2] != KFB_SKIP) + (t[3] != KFB_SKIP);
+        }
+        else
+        {
+            if (t[0] != KFB_SKIP) { o.x = update_word(wd.x, t[0], a); if (COUNT) ++n_upd; }
+            if (t[1] != KFB_SKIP) { o.y = update_word(wd.y, t[1], a); if (COUNT) ++n_upd; }
+            if (t[2] != KFB_SKIP) { o.z = update_word(wd.z, t[2], a); if (COUNT) ++n_upd; }
+            if (t[3] != KFB_SKIP) { o.w = update_word(wd.w, t[3], a); if (COUNT) ++n_upd; }
+        }
     }
     if ((o.x != wd.x) | (o.y != wd.y) | (o.z != wd.z) | (o.w != wd.w))
     {
@@ -543,7 +578,8 @@ __global__ void __launch_bounds__(32 * KFB_INT_WARPS, KFB_INT_MINB * 4 / KFB_INT
             xy[k] = pack2(__fadd_rn(r.x, a.pose.t[0]), __fadd_rn(r.y, a.pose.t[1]));
         }
     }
-    bool deep_free = false;
+    // last plane of this thread's interval that certainly still is deep free space (za - 1: none)
+    int free_end = za - 1;
     // Occlusion cut: over planes [za, zb] the four columns project into a pixel rectangle (a line segment per
     // column; computed from the affine model and widened by the drift bound).  A voxel is rejected once vc.z
     // exceeds lo_z of its pixel, hence certainly once it exceeds the maximum of lo_z over that rectangle, which
@@ -562,7 +598,7 @@ __global__ void __launch_bounds__(32 * KFB_INT_WARPS, KFB_INT_MINB * 4 / KFB_INT
             for (int k = 0; k < 2; ++k)
             {
                 const float X = fmaf(zf, a.Sx, k ? bx_ : ax), Y = fmaf(zf, a.Sy, k ? by_ : ay), Zc = fmaf(zf, a.Sz, k ? z0v[3] : z0v[0]);
-                const float r = 1.f / fmaxf(Zc, 1e-3f);
+                const float r = mufu_rcp(fmaxf(Zc, 1e-3f)); // approximate is fine: the rectangle is padded below
                 const float u = fmaf(a.fx * X, r, a.cx), v = fmaf(a.fy * Y, r, a.cy);
                 umin = fminf(umin, u); umax = fmaxf(umax, u);
                 vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
@@ -572,7 +608,7 @@ __global__ void __launch_bounds__(32 * KFB_INT_WARPS, KFB_INT_MINB * 4 / KFB_INT
         if (zmin > 0.05f)
         {
             // pixel error of the model: (fx + |u - cx|) * E / z per axis, plus rounding to the nearest pixel
-            const float pad = 1.5f + (a.fx + a.fy + (float)(a.w + a.h)) * a.driftE / zmin;
+            const float pad = 1.5f + (a.fx + a.fy + (float)(a.w + a.h)) * a.driftE * (1.001f * mufu_rcp(zmin));
             const bool all_inside = umin - pad >= 0.f && umax + pad <= (float)(a.w - 1) && vmin - pad >= 0.f && vmax + pad <= (float)(a.h - 1);
             const int u0 = max((int)floorf(fmaxf(umin - pad, -1e6f)), 0), u1 = min((int)ceilf(fminf(umax + pad, 1e6f)), a.w - 1);
             const int v0 = max((int)floorf(fmaxf(vmin - pad, -1e6f)), 0), v1 = min((int)ceilf(fminf(vmax + pad, 1e6f)), a.h - 1);
@@ -590,27 +626,40 @@ __global__ void __launch_bounds__(32 * KFB_INT_WARPS, KFB_INT_MINB * 4 / KFB_INT
                 const float zc = (q.x + 2.f * a.driftE - fminf(z0v[0], z0v[3])) * a.invSz + 1.f;
                 zb = min(zb, (int)ceilf(fminf(zc, 1e6f)));
                 if (za > zb) return;
-                // Deep free space: every pixel the columns can land on (all inside the image) still sees free
-                // space at the largest vc.z of the interval => every voxel of [za, zb] passes the predicate with
-                // tsdf == 1.0f exactly; neither projection nor running sums are needed.
-                const float vz_max = fmaf((float)zb, a.Sz, fmaxf(z0v[0], z0v[3])) + 2.f * a.driftE;
-                deep_free = all_inside && vz_max <= q.y && !a.no_fastpath;
+                // Deep free space: while the largest vc.z of a plane (+ drift) does not exceed the smallest hi_z
+                // of the pixels the columns can land on (all inside the image), every voxel of that plane passes
+                // the predicate with tsdf == 1.0f exactly; neither projection nor running sums are needed.
+                // vc.z grows with z (Sz > 0), so these planes are a prefix [za, free_end] of the interval.
+                if (all_inside && !a.no_fastpath)
+                {
+                    const float zmaxv = fmaxf(z0v[0], z0v[3]), e2 = 2.f * a.driftE;
+                    int zf = min(zb, (int)floorf(fminf(fmaxf((q.y - e2 - zmaxv) * a.invSz, -1.f), 1e6f)));
+                    // the estimate may be off by rounding: step back until the exact test holds
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+                        if (zf >= za && fmaf((float)zf, a.Sz, zmaxv) + e2 > q.y) --zf;
+                    if (zf >= za && fmaf((float)zf, a.Sz, zmaxv) + e2 <= q.y) free_end = zf;
+                }
             }
         }
     }
-    // the fast path only pays when the whole warp takes it (otherwise the warp would run both paths in turn)
+    // The fast prefix only pays for planes on which the WHOLE warp takes it (a mixed plane would run both paths
+    // in turn): planes up to the warp's smallest free_end.  Whatever set of lanes votes together, a lane's own
+    // free_end is >= the minimum it receives, so the split can never change a result.
+    int zfw;
     {
         const unsigned act = __activemask();
-        deep_free = __ballot_sync(act, deep_free) == act;
+        zfw = __reduce_min_sync(act, free_end);
     }
-    if (deep_free)
+    unsigned int n_upd = 0;
+    const size_t plane4 = ((size_t)a.X * a.Y) >> 2; // uint4 per plane
+    if (!(a.diag & 2))
     {
-        const size_t plane4 = ((size_t)a.X * a.Y) >> 2;
+        const int pe = min(zfw, zb);
         uint4 *vp = reinterpret_cast<uint4 *>(a.vol) + ((size_t)(za - a.z_store0) * a.Y + y) * (a.X >> 2) + (x0 >> 2);
         const float ones[4] = {1.f, 1.f, 1.f, 1.f};
-        unsigned int n_upd = 0;
         int z = za;
-        for (; z + 3 <= zb; z += 4, vp += 4 * plane4)
+        for (; z + 3 <= pe; z += 4, vp += 4 * plane4)
         {
             const uint4 w0 = __ldcs(vp), w1 = __ldcs(vp + plane4), w2 = __ldcs(vp + 2 * plane4), w3 = __ldcs(vp + 3 * plane4);
             update_quad<COUNT>(a, vp, w0, ones, x0, y, z, n_upd);
@@ -618,10 +667,14 @@ __global__ void __launch_bounds__(32 * KFB_INT_WARPS, KFB_INT_MINB * 4 / KFB_INT
             update_quad<COUNT>(a, vp + 2 * plane4, w2, ones, x0, y, z + 2, n_upd);
             update_quad<COUNT>(a, vp + 3 * plane4, w3, ones, x0, y, z + 3, n_upd);
         }
-        for (; z <= zb; ++z, vp += plane4) update_quad<COUNT>(a, vp, __ldcs(vp), ones, x0, y, z, n_upd);
+        for (; z <= pe; ++z, vp += plane4) update_quad<COUNT>(a, vp, __ldcs(vp), ones, x0, y, z, n_upd);
+    }
+    if (zfw >= zb || (a.diag & 1))
+    {
         if (COUNT && n_upd) atomicAdd(a.counter, (unsigned long long)n_upd);
         return;
     }
+    const int za_g = max(za, zfw + 1); // first plane of the general path
 
     const float sz = a.pose.R.m[8];
     const unsigned long long vs2 = pack2(a.vsx, a.vsx), sxy = pack2(a.pose.R.m[2], a.pose.R.m[5]), szz = pack2(sz, sz);
@@ -635,7 +688,7 @@ __global__ void __launch_bounds__(32 * KFB_INT_WARPS, KFB_INT_MINB * 4 / KFB_INT
         zz[0] = __ldg(st + 4 * nthr);
         zz[1] = __ldg(st + 5 * nthr);
 #pragma unroll 4
-        for (int z = zstart; z < za; ++z)
+        for (int z = zstart; z < za_g; ++z)
         {
 #pragma unroll
             for (int k = 0; k < 4; ++k) xy[k] = ffma2(vs2, sxy, xy[k]);
@@ -647,7 +700,7 @@ __global__ void __launch_bounds__(32 * KFB_INT_WARPS, KFB_INT_MINB * 4 / KFB_INT
     // drift (millimetres at most), so the two ends decide with a 1 cm margin
     bool fast;
     {
-        const float span = (float)(zb - za + 1) * __fmul_rn(a.vsx, sz);
+        const float span = (float)(zb - za_g + 1) * __fmul_rn(a.vsx, sz);
         float c0, c1, c2, c3;
         unpack2(zz[0], c0, c1);
         unpack2(zz[1], c2, c3);
@@ -656,14 +709,12 @@ __global__ void __launch_bounds__(32 * KFB_INT_WARPS, KFB_INT_MINB * 4 / KFB_INT
     }
 
     const float rtrunc = rcp_fdividef(a.trunc);
-    const size_t plane4 = ((size_t)a.X * a.Y) >> 2; // uint4 per plane
-    uint4 *vp = reinterpret_cast<uint4 *>(a.vol) + ((size_t)(za - a.z_store0) * a.Y + y) * (a.X >> 2) + (x0 >> 2);
-    unsigned int n_upd = 0;
+    uint4 *vp = reinterpret_cast<uint4 *>(a.vol) + ((size_t)(za_g - a.z_store0) * a.Y + y) * (a.X >> 2) + (x0 >> 2);
 
     if (!fast)
     {
         // cold path (camera within a centimetre of this column's planes): one plane at a time, any vc.z
-        for (int z = za; z <= zb; ++z, vp += plane4)
+        for (int z = za_g; z <= zb; ++z, vp += plane4)
         {
 #pragma unroll
             for (int k = 0; k < 4; ++k) xy[k] = ffma2(vs2, sxy, xy[k]);
@@ -687,7 +738,7 @@ __global__ void __launch_bounds__(32 * KFB_INT_WARPS, KFB_INT_MINB * 4 / KFB_INT
     }
 
     const unsigned long long fxy = pack2(a.fx, a.fy), cxy = pack2(a.cx, a.cy), magic2 = pack2(KFB_MAGIC_F, KFB_MAGIC_F);
-    for (int z = za; z <= zb; z += U)
+    for (int z = za_g; z <= zb; z += U)
     {
         float ts[U][4], cz[U][4];
         unsigned int pix[U][4];
@@ -736,11 +787,21 @@ __global__ void __launch_bounds__(32 * KFB_INT_WARPS, KFB_INT_MINB * 4 / KFB_INT
             }
         if (band)
         {
+            // all exact-depth entries first (the addresses are valid for every voxel), so that the warp waits for
+            // one load latency and not for one per voxel a lane happens to have in the band
+            float2 ex[U][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ex[u][k] = __ldg(a.exact + pix[u][k]);
 #pragma unroll
             for (int u = 0; u < U; ++u)
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    if (ts[u][k] == KFB_BAND) ts[u][k] = band_tsdf(a, sxyv[u][k], cz[u][k], (int)pix[u][k], rtrunc);
+                {
+                    const float tb = band_tsdf(a, sxyv[u][k], cz[u][k], ex[u][k], rtrunc);
+                    ts[u][k] = ts[u][k] == KFB_BAND ? tb : ts[u][k];
+                }
         }
         // ---- loads, then phase B ------------------------------------------------------------------------
         uint4 word[U];
@@ -903,6 +964,7 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
     a.zexit = ctx->zexit;
     a.max_weight = ctx->p.tsdf_max_weight;
     a.no_fastpath = getenv("KFB_INTEGRATE_NOFAST") ? 1 : 0;
+    a.diag = getenv("KFB_INTEGRATE_DIAG") ? atoi(getenv("KFB_INTEGRATE_DIAG")) : 0;
     a.use_jump = getenv("KFB_INTEGRATE_NOJUMP") ? 0 : 1;
     // measured on B200: a jump costs about as much as 600 replayed planes (warps that straddle vc.x == 0 walk
     // many binades), so it pays for far z-slabs / large volumes, not for the z-chunks of a 512^3 sweep
@@ -929,11 +991,11 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
     if (planes <= 0) return KFB_OK;
     // z-chunks give resident warps and load balance (the visited interval differs per column); the running
     // sum at each chunk start comes from column_states_kernel, so chunks cost no replay.  48 B per thread per
-    // chunk of state: bounded to max(64 MB, 1/32 of the volume).  KFB_INTEGRATE_ZCHUNKS overrides for tuning.
+    // chunk of state: bounded to max(128 MB, 1/32 of the volume).  KFB_INTEGRATE_ZCHUNKS overrides for tuning.
     const size_t nthr = (size_t)(a.X >> 2) * a.Y;
-    int zc = (planes + 31) / 32;
-    if (zc > 16) zc = 16;
-    const size_t state_cap = std::max((size_t)64 << 20, ctx->vol_voxels * sizeof(uint32_t) / 32); // <= 3 % of the volume
+    int zc = (planes + 15) / 16;
+    if (zc > 32) zc = 32;
+    const size_t state_cap = std::max((size_t)128 << 20, ctx->vol_voxels * sizeof(uint32_t) / 32); // <= 3 % of the volume
     while (zc > 1 && (size_t)zc * 48 * nthr > state_cap) --zc;
     if (const char *e = getenv("KFB_INTEGRATE_ZCHUNKS")) zc = atoi(e) > 0 ? atoi(e) : zc;
     if (zc > planes) zc = planes;
