@@ -100,6 +100,10 @@ __device__ __forceinline__ float4 ld_volatile_f4(const volatile float *p)
     asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void st_volatile_f4(float *p, const float4 v)
+{
+    asm volatile("st.volatile.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {
     unsigned long long t;
@@ -507,17 +511,13 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
             if (s_cmd == ICP_CMD_RUN && s_ok)
             {
                 if (threadIdx.x < 27) icp_post(P.out, threadIdx.x, fin27[threadIdx.x], seq);
-                if (threadIdx.x == 0)
-                {
-                    volatile unsigned long long *st = P.out->stamps; // debug hook, see kfb_debug_icp_stamps
-                    st[0] = ts0; st[1] = ts1; st[2] = ts2; st[3] = ts3; st[4] = globaltimer_ns();
-                    volatile unsigned long long *pr = P.out->post_ns[k & 31];
-                    pr[0] = ts0; pr[1] = ts3; pr[2] = st[4];
-                }
             }
             // (2) decide what the grid does next
             if (threadIdx.x == 0)
             {
+                const unsigned long long ts4 = globaltimer_ns();
+                const bool posted = s_cmd == ICP_CMD_RUN && s_ok;
+                const int k_posted = k;
                 int cmd = s_cmd, iter = k, spec = 0;
                 const float *next = npose;
                 if (cmd == ICP_CMD_RUN)
@@ -553,40 +553,72 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
                         }
                     }
                 }
-                volatile IcpDevGate *g = P.devgate;
-                for (int i = 0; i < 12; ++i) g->pose[i] = next[i];
-                g->cmd = cmd; g->iter = iter; g->spec = spec;
-                ((volatile unsigned long long *)P.out->stamps)[5] = globaltimer_ns();
-                __threadfence();
-                g->seq = round + 1ull; // release
-                ((volatile unsigned long long *)P.out->stamps)[6] = globaltimer_ns();
-                ((volatile unsigned long long *)P.out->post_ns[k & 31])[3] = globaltimer_ns();
+                const unsigned long long ts5 = globaltimer_ns();
+                {
+                    // release: four self-validating chunks (see IcpDevGate).  Nothing else has to be ordered before
+                    // them: the partials were consumed above, the ticket has wrapped to zero by itself.
+                    const unsigned int tag = ((unsigned int)((round + 1ull) & 0xfffffull) << 12) | ((unsigned int)(iter & 0xff) << 4) |
+                                             ((unsigned int)(spec & 1) << 2) | (unsigned int)(cmd & 3);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                    {
+                        if (c < 3) st_volatile_f4(P.devgate->chunk + 4 * c, make_float4(next[4 * c], next[4 * c + 1], next[4 * c + 2], __uint_as_float(tag)));
+                        else st_volatile_f4(P.devgate->chunk + 12, make_float4(next[3], next[7], next[11], __uint_as_float(tag)));
+                    }
+                }
+                // debug hooks (kfb_debug_icp_stamps / _ring): host-memory stores, after the release on purpose
+                const unsigned long long ts6 = globaltimer_ns();
+                volatile unsigned long long *st = P.out->stamps;
+                if (posted)
+                {
+                    st[0] = ts0; st[1] = ts1; st[2] = ts2; st[3] = ts3; st[4] = ts4;
+                    volatile unsigned long long *pr = P.out->post_ns[k_posted & 31];
+                    pr[0] = ts0; pr[1] = ts3; pr[2] = ts4; pr[3] = ts6;
+                }
+                st[5] = ts5; st[6] = ts6;
             }
         }
         // every CTA (the last one included) picks its orders up from the device gate
         if (threadIdx.x == 0)
         {
-            const unsigned long long want = round + 1ull, t0 = globaltimer_ns();
+            const unsigned int want = (unsigned int)((round + 1ull) & 0xfffffull);
+            const unsigned long long t0 = globaltimer_ns();
             int cmd = ICP_CMD_RUN;
+            float4 c0, c1, c2, c3;
             for (;;)
             {
-                if (ld_volatile_u64(&P.devgate->seq) == want) break;
+                // one load per poll (the chunk written last) keeps the pollers out of the writer's way; CTAs without
+                // pixels at this level are in no hurry at all
+                c3 = ld_volatile_f4(P.devgate->chunk + 12);
+                if ((__float_as_uint(c3.w) >> 12) == want)
+                {
+                    c0 = ld_volatile_f4(P.devgate->chunk);
+                    c1 = ld_volatile_f4(P.devgate->chunk + 4);
+                    c2 = ld_volatile_f4(P.devgate->chunk + 8);
+                    const unsigned int t = __float_as_uint(c3.w);
+                    if (__float_as_uint(c0.w) == t && __float_as_uint(c1.w) == t && __float_as_uint(c2.w) == t) break;
+                }
+                else if ((int)blockIdx.x >= nact) __nanosleep(200);
                 if (globaltimer_ns() - t0 > 3ull * KFB_ICP_GATE_TIMEOUT_NS) { cmd = ICP_CMD_LEAVE; break; }
             }
             if (cmd == ICP_CMD_RUN)
             {
-                cmd = __ldcg(&P.devgate->cmd);
-                s_iter = __ldcg(&P.devgate->iter);
-                s_spec = __ldcg(&P.devgate->spec);
+                const unsigned int t = __float_as_uint(c0.w);
+                cmd = (int)(t & 3u);
+                s_iter = (int)((t >> 4) & 0xffu);
+                s_spec = (int)((t >> 2) & 1u);
+                // rows 0..2 without the translation, then the translation column
+                spose[0] = c0.x; spose[1] = c0.y; spose[2] = c0.z;
+                spose[4] = c1.x; spose[5] = c1.y; spose[6] = c1.z;
+                spose[8] = c2.x; spose[9] = c2.y; spose[10] = c2.z;
+                spose[3] = c3.x; spose[7] = c3.y; spose[11] = c3.z;
             }
             s_cmd = cmd;
         }
         ICP_BAR();
         if (s_cmd != ICP_CMD_RUN) return;
-        if (threadIdx.x < 12) spose[threadIdx.x] = __ldcg(P.devgate->pose + threadIdx.x);
         k = s_iter; spec_used = s_spec;
         ++round;
-        ICP_BAR();
     }
 }
 
