@@ -198,7 +198,7 @@ void kfb_level_intrinsics(const kfb_intrinsics *in, int level, kfb_intrinsics *o
 int kfb_event_record(kfb_ctx *ctx, int slot);
 int kfb_event_elapsed_ms(kfb_ctx *ctx, int slot_a, int slot_b, float *ms);
 /* opt-in stage profiling: when on, launchers bracket their main kernel with events in reserved
- * slots (integrate kernel: 60/61, whole kfb_integrate call: 56/57, raycast: 58/59) so a caller can read that
+ * slots (persistent ICP kernel: 54/55, integrate kernel: 60/61, whole kfb_integrate call: 56/57, raycast: 58/59) so a caller can read that
  * kernel's own duration. */
 int kfb_set_profiling(kfb_ctx *ctx, int on);
 /* number of kernels this library has launched on this context since creation */

@@ -746,8 +746,10 @@ static int icp_launch_persistent(kfb_ctx *ctx, const float pose12[12])
     // every CTA must be resident at once (they wait on each other): one per SM (see icp_setup)
     const int blocks = ctx->sm_count;
     (void)max_pix;
+    if (ctx->profiling) cudaEventRecord(ctx->events[54], ctx->stream); // the frame's whole ICP: 54 .. 55
     icp_persistent_kernel<<<blocks, ICP_THREADS + 32, 0, ctx->stream>>>(P);
     KFB_LAUNCH_CHECK(ctx);
+    if (ctx->profiling) cudaEventRecord(ctx->events[55], ctx->stream);
     S.enq = S.total;
     return KFB_OK;
 }

@@ -49,3 +49,17 @@ for i, (_, d) in enumerate(frames):
 ctx.set_profiling(False)
 R = np.array(rows) * 1e3
 print("us: integrate call %.1f (kernel %.1f), gap to raycast %.1f, raycast %.1f" % tuple(np.median(R, axis=0)))
+
+# the same, pipelined (a synchronize only after every 4th frame, whose events are then read)
+kf.reset()
+ctx.set_profiling(True)
+rows = []
+for i, (_, d) in enumerate(frames):
+    assert kf.pipeline(d) == 0
+    if i >= 5 and i % 4 == 0:
+        ctx.synchronize()
+        rows.append((ctx.event_elapsed_ms(54, 55), ctx.event_elapsed_ms(55, 56), ctx.event_elapsed_ms(56, 57), ctx.event_elapsed_ms(57, 58),
+                     ctx.event_elapsed_ms(58, 59), ctx.event_elapsed_ms(54, 59)))
+ctx.set_profiling(False)
+R = np.array(rows) * 1e3
+print("pipelined us: icp kernel %.1f, gap %.1f, integrate call %.1f, gap %.1f, raycast %.1f; icp start -> raycast end %.1f" % tuple(np.median(R, axis=0)))
