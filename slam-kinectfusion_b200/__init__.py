@@ -9,4 +9,5 @@ compute call requires the built extension and a Blackwell GPU and fails loudly o
 from .binding import (KfbError, Context, Params, Intrinsics, default_params, load_library,  # noqa: F401
                       library_path, SENSORS, exported_symbols)
 from .build import build_all  # noqa: F401
-from .host import KinectFusion, HostParams, default_host_params, load_host_library, host_library_path  # noqa: F401,E402
+from .host import (KinectFusion, HostParams, default_host_params, load_host_library, host_library_path,  # noqa: F401,E402
+                   DatasetSensor, write_png_gray16, write_png_rgb8, read_intrinsics)

@@ -59,6 +59,13 @@ def load_host_library():
         "kfh_load_volume": (C.c_int, [_vp, C.c_char_p]),
         "kfh_read_intrinsics": (C.c_int, [C.c_char_p, _vp]),
         "kfh_icp_probe": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+        "kfh_sensor_open": (_vp, [C.c_char_p]),
+        "kfh_sensor_close": (None, [_vp]),
+        "kfh_sensor_info": (C.c_int, [_vp, _vp]),
+        "kfh_sensor_get_frame": (C.c_int, [_vp, _vp, _vp]),
+        "kfh_sensor_error": (C.c_char_p, [_vp]),
+        "kfh_png_write_gray16": (C.c_int, [C.c_char_p, _vp, C.c_int, C.c_int]),
+        "kfh_png_write_rgb8": (C.c_int, [C.c_char_p, _vp, C.c_int, C.c_int]),
         "kfh_set_shard_comm": (None, [_vp, BCAST_FN, COMPOSITE_FN, _vp]),
     }
     for name, (res, args) in sig.items():
@@ -87,6 +94,65 @@ def read_intrinsics(path):
     out = np.zeros(5, np.float32)
     rc = load_host_library().kfh_read_intrinsics(str(path).encode(), out.ctypes.data_as(_vp))
     return None if rc else out
+
+
+class DatasetSensor:
+    """The reference's dataset frame source (depth_sensor.cpp:11-46,186-196): color/*.png, depth/*.png (16-bit mm),
+    intr.txt.  Iterating yields (bgr uint8 [h, w, 3], depth_mm float32 [h, w])."""
+
+    def __init__(self, path):
+        self.lib = load_host_library()
+        self.h = self.lib.kfh_sensor_open(str(path).encode())
+        if not self.h:
+            raise FileNotFoundError(f"error: no camera! ({path})")
+        info = np.zeros(8, np.float32)
+        self.lib.kfh_sensor_info(self.h, info.ctypes.data_as(_vp))
+        self.width, self.height = int(info[0]), int(info[1])
+        self.fx, self.cx, self.fy, self.cy, self.scale = (float(v) for v in info[2:7])
+
+    def frames_left(self):
+        info = np.zeros(8, np.float32)
+        self.lib.kfh_sensor_info(self.h, info.ctypes.data_as(_vp))
+        return int(info[7])
+
+    def get_frame(self):
+        depth = np.empty((self.height, self.width), np.float32)
+        bgr = np.empty((self.height, self.width, 3), np.uint8)
+        rc = self.lib.kfh_sensor_get_frame(self.h, depth.ctypes.data_as(_vp), bgr.ctypes.data_as(_vp))
+        if rc == 2:
+            raise ValueError("frame size differs from the first colour image")
+        return None if rc else (bgr, depth)
+
+    def last_error(self):
+        return self.lib.kfh_sensor_error(self.h).decode()
+
+    def __iter__(self):
+        while True:
+            f = self.get_frame()
+            if f is None:
+                return
+            yield f
+
+    def close(self):
+        if self.h:
+            self.lib.kfh_sensor_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def write_png_gray16(path, img):
+    a = np.ascontiguousarray(img, np.uint16)
+    return load_host_library().kfh_png_write_gray16(str(path).encode(), a.ctypes.data_as(_vp), a.shape[1], a.shape[0]) == 0
+
+
+def write_png_rgb8(path, img):
+    a = np.ascontiguousarray(img, np.uint8)
+    return load_host_library().kfh_png_write_rgb8(str(path).encode(), a.ctypes.data_as(_vp), a.shape[1], a.shape[0]) == 0
 
 
 def icp_solve(sums27):

@@ -1,6 +1,7 @@
 // c_api.cpp -- extern "C" handle API over kf::kinectfusion so the facade can be driven from
 // ctypes (tests, bench.py) exactly as a C++ application drives the reference's class.
 #include <kinectfusion.h>
+#include <depth_sensor.h>
 #include <cstring>
 #include <string>
 
@@ -164,6 +165,36 @@ int kfh_read_intrinsics(const char *path, float out5[5])
     out5[0] = k.fx; out5[1] = k.cx; out5[2] = k.fy; out5[3] = k.cy; out5[4] = k.c;
     return 0;
 }
+/* dataset frame source (depth_sensor.h): open -> handle or NULL; info8 = width, height, fx, cx, fy, cy, scale, frames left */
+void *kfh_sensor_open(const char *path)
+{
+    depth_sensor *s = new depth_sensor();
+    if (!s->open(path)) { delete s; return nullptr; }
+    return s;
+}
+void kfh_sensor_close(void *h) { delete static_cast<depth_sensor *>(h); }
+int kfh_sensor_info(void *h, float info8[8])
+{
+    const depth_sensor *s = static_cast<depth_sensor *>(h);
+    info8[0] = (float)s->params.width; info8[1] = (float)s->params.height;
+    info8[2] = s->params.fx; info8[3] = s->params.cx; info8[4] = s->params.fy; info8[5] = s->params.cy; info8[6] = s->params.c;
+    info8[7] = (float)s->framesLeft();
+    return 0;
+}
+/* next frame: depth_mm [h*w] float, bgr [h*w*3] (either may be NULL); 0 ok, 1 exhausted / undecodable, 2 size changed */
+int kfh_sensor_get_frame(void *h, float *depth_mm, unsigned char *bgr)
+{
+    depth_sensor *s = static_cast<depth_sensor *>(h);
+    if (!s->getFrame()) return 1;
+    const size_t n = (size_t)s->params.width * s->params.height;
+    if ((size_t)s->depth_map.rows * s->depth_map.cols != n || (size_t)s->color_map.rows * s->color_map.cols != n) return 2;
+    if (depth_mm) std::memcpy(depth_mm, s->depth_map.ptr<float>(), n * sizeof(float));
+    if (bgr) std::memcpy(bgr, s->color_map.ptr<unsigned char>(), n * 3);
+    return 0;
+}
+const char *kfh_sensor_error(void *h) { return static_cast<depth_sensor *>(h)->lastError().c_str(); }
+int kfh_png_write_gray16(const char *path, const unsigned short *pix, int w, int h) { return kf::png::write_gray16(path, pix, w, h) ? 0 : 1; }
+int kfh_png_write_rgb8(const char *path, const unsigned char *rgb, int w, int h) { return kf::png::write_rgb8(path, rgb, w, h) ? 0 : 1; }
 int kfh_icp_solve(const double in27[27], double x6[6]) { return kf::ICPRegistration::solve(in27, x6) ? 0 : 1; }
 
 } // extern "C"
