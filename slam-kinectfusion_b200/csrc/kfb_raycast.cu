@@ -57,24 +57,27 @@ __device__ __forceinline__ int rn_magic(float v) { return __float_as_int(__fadd_
 // (float)i for |i| < 2^22
 __device__ __forceinline__ float i2f_magic(int i) { return __fsub_rn(__int_as_float(KFB_RC_MAGIC_I + i), KFB_RC_MAGIC_F); }
 
+// SLAB = false: the context stores the whole volume (zs0 = zo0 = bz0 = 0, zs1 = zo1 = Z); the slab tests fold away
+template <bool SLAB>
 __device__ __forceinline__ float vox_tsdf(const RaycastArgs &a, int x, int y, int z)
 {
-    z = min(max(z, a.zs0), a.zs1 - 1); // slab mode: never read outside the stored planes
-    const size_t i = ((size_t)(z - a.zs0) * a.Y + y) * a.X + x;
+    if (SLAB) z = min(max(z, a.zs0), a.zs1 - 1); // slab mode: never read outside the stored planes
+    const size_t i = ((size_t)(z - (SLAB ? a.zs0 : 0)) * a.Y + y) * a.X + x;
     const short s = __ldg(reinterpret_cast<const short *>(a.vol + i)); // low half = tsdf
     return __fmul_rn((float)s, KFB_DIVSHORTMAX);
 }
 // interpolate (tsdf_volume.cu:137-161)
+template <bool SLAB>
 __device__ float interp(const RaycastArgs &a, float fx, float fy, float fz)
 {
     const int gx = __float2int_rd(fx), gy = __float2int_rd(fy), gz = __float2int_rd(fz);
     if (gx < 0 || gx >= a.X - 1 || gy < 0 || gy >= a.Y - 1 || gz < 0 || gz >= a.Z - 1) return KFB_QNAN;
     const float fa = __fsub_rn(fx, (float)gx), fb = __fsub_rn(fy, (float)gy), fc = __fsub_rn(fz, (float)gz);
     const float a1 = __fsub_rn(1.f, fa), b1 = __fsub_rn(1.f, fb), c1 = __fsub_rn(1.f, fc);
-    const float v000 = vox_tsdf(a, gx, gy, gz), v001 = vox_tsdf(a, gx, gy, gz + 1);
-    const float v010 = vox_tsdf(a, gx, gy + 1, gz), v011 = vox_tsdf(a, gx, gy + 1, gz + 1);
-    const float v100 = vox_tsdf(a, gx + 1, gy, gz), v101 = vox_tsdf(a, gx + 1, gy, gz + 1);
-    const float v110 = vox_tsdf(a, gx + 1, gy + 1, gz), v111 = vox_tsdf(a, gx + 1, gy + 1, gz + 1);
+    const float v000 = vox_tsdf<SLAB>(a, gx, gy, gz), v001 = vox_tsdf<SLAB>(a, gx, gy, gz + 1);
+    const float v010 = vox_tsdf<SLAB>(a, gx, gy + 1, gz), v011 = vox_tsdf<SLAB>(a, gx, gy + 1, gz + 1);
+    const float v100 = vox_tsdf<SLAB>(a, gx + 1, gy, gz), v101 = vox_tsdf<SLAB>(a, gx + 1, gy, gz + 1);
+    const float v110 = vox_tsdf<SLAB>(a, gx + 1, gy + 1, gz), v111 = vox_tsdf<SLAB>(a, gx + 1, gy + 1, gz + 1);
     float t = 0.f;
     t = __fmaf_rn(__fmul_rn(__fmul_rn(v000, a1), b1), c1, t);
     t = __fmaf_rn(__fmul_rn(__fmul_rn(v001, a1), b1), fc, t);
@@ -101,6 +104,7 @@ enum { ST_FETCH = 0, ST_NAN = 1, ST_LEAVE = 2 };
 // volume interior, outside this slab's stored planes, or in a brick that cannot take part in an event --
 // and `cnt` further steps are guaranteed to be NaN for the same reason.  ST_LEAVE: the ray moves away from
 // the stored planes for good.  `own` = the sample's voxel plane belongs to this slab.
+template <bool SLAB>
 __device__ __forceinline__ int classify(const RaycastArgs &a, const RaySkip &rs, float px, float py, float pz, bool &own,
                                         int &cnt, const short *&addr)
 {
@@ -109,7 +113,7 @@ __device__ __forceinline__ int classify(const RaycastArgs &a, const RaySkip &rs,
     own = false; cnt = 0; addr = nullptr;
     if ((unsigned)(x - 1) >= (unsigned)(a.X - 2) || (unsigned)(y - 1) >= (unsigned)(a.Y - 2) || (unsigned)(z - 1) >= (unsigned)(a.Z - 2))
         return ST_NAN;
-    if (z < a.zs0 || z >= a.zs1)
+    if (SLAB && (z < a.zs0 || z >= a.zs1))
     {
         // outside the stored planes: steps until the sample can reach them (1.5 voxels of margin for the
         // drift of the replayed running sum over a long run)
@@ -121,14 +125,14 @@ __device__ __forceinline__ int classify(const RaycastArgs &a, const RaySkip &rs,
         cnt = s > 1.f ? (int)fminf(s, 1e6f) - 1 : 0;
         return ST_NAN;
     }
-    own = z >= a.zo0 && z < a.zo1;
+    own = !SLAB || (z >= a.zo0 && z < a.zo1);
     // Chebyshev distance D (in bricks) to the nearest brick that may hold a negative voxel; 0 = such a brick.
     // Index moves by at most n + 1 per axis over n steps, an active brick is at least (D-1)*8 + 1 voxels
     // away along some axis, so the next (D-1)*8 - 1 samples cannot lie in one.
-    const int D = __ldg(a.bdist + ((size_t)((z >> 3) - a.bz0) * a.by + (y >> 3)) * a.bx + (x >> 3));
+    const int D = __ldg(a.bdist + ((size_t)((z >> 3) - (SLAB ? a.bz0 : 0)) * a.by + (y >> 3)) * a.bx + (x >> 3));
     if (D == 0)
     {
-        addr = reinterpret_cast<const short *>(a.vol + ((size_t)(z - a.zs0) * a.Y + y) * a.X + x); // low half = tsdf
+        addr = reinterpret_cast<const short *>(a.vol + ((size_t)(z - (SLAB ? a.zs0 : 0)) * a.Y + y) * a.X + x); // low half = tsdf
         return ST_FETCH;
     }
     cnt = max((D - 1) * 8 - 1, 0);
@@ -145,6 +149,7 @@ __device__ __forceinline__ float load_tsdf(const short *addr)
 // running-sum instructions only; otherwise KFB_RC_BATCH steps are classified and their loads issued before
 // the first sign test (sample positions do not depend on fetched values).  Candidate hits are parked and
 // their normals are computed after the march, when the warp has reconverged.
+template <bool SLAB>
 __global__ void __launch_bounds__(32) raycast_kernel(const RaycastArgs a)
 {
     const unsigned FULL = 0xffffffffu;
@@ -196,7 +201,7 @@ __global__ void __launch_bounds__(32) raycast_kernel(const RaycastArgs a)
         ray_len = __fadd_rn(ray_len, a.step_len);
         nx = __fmaf_rn(dx, ray_len, ox); ny = __fmaf_rn(dy, ray_len, oy); nz = __fmaf_rn(dz, ray_len, oz);
         bool own; int cnt; const short *addr;
-        const int st = classify(a, rs, nx, ny, nz, own, cnt, addr);
+        const int st = classify<SLAB>(a, rs, nx, ny, nz, own, cnt, addr);
         if (st == ST_FETCH) tnext = load_tsdf(addr);
         if (st == ST_LEAVE) marching = false;
     }
@@ -217,7 +222,7 @@ __global__ void __launch_bounds__(32) raycast_kernel(const RaycastArgs a)
             const short *addr[KFB_RC_BATCH];
             qx[0] = __fmaf_rn(dx, a.vs[0], nx); qy[0] = __fmaf_rn(dy, a.vs[1], ny); qz[0] = __fmaf_rn(dz, a.vs[2], nz);
             st[0] = ST_NAN; own[0] = false; addr[0] = nullptr;
-            if (alive) st[0] = classify(a, rs, qx[0], qy[0], qz[0], own[0], cnt0, addr[0]);
+            if (alive) st[0] = classify<SLAB>(a, rs, qx[0], qy[0], qz[0], own[0], cnt0, addr[0]);
             if (__all_sync(FULL, !alive || st[0] != ST_FETCH))
             {
                 // no ray of the warp needs this sample: it is NaN for all; then skip what every ray can skip.
@@ -256,7 +261,7 @@ __global__ void __launch_bounds__(32) raycast_kernel(const RaycastArgs a)
                 qx[b] = __fmaf_rn(dx, a.vs[0], qx[b - 1]); qy[b] = __fmaf_rn(dy, a.vs[1], qy[b - 1]); qz[b] = __fmaf_rn(dz, a.vs[2], qz[b - 1]);
                 st[b] = ST_NAN; own[b] = false; addr[b] = nullptr;
                 int c;
-                if (alive) st[b] = classify(a, rs, qx[b], qy[b], qz[b], own[b], c, addr[b]);
+                if (alive) st[b] = classify<SLAB>(a, rs, qx[b], qy[b], qz[b], own[b], c, addr[b]);
             }
             float val[KFB_RC_BATCH];
 #pragma unroll
@@ -299,12 +304,12 @@ __global__ void __launch_bounds__(32) raycast_kernel(const RaycastArgs a)
             const float vx = __fmaf_rn(dx, Ts, ox), vy = __fmaf_rn(dy, Ts, oy), vz = __fmaf_rn(dz, Ts, oz);
             // compute_normal (tsdf_volume.cu:192-209)
             const float ux = __fmul_rn(vx, a.vsinv[0]), uy = __fmul_rn(vy, a.vsinv[1]), uz = __fmul_rn(vz, a.vsinv[2]);
-            const float Fx1 = interp(a, __fmul_rn(__fadd_rn(vx, a.gd[0]), a.vsinv[0]), uy, uz);
-            const float Fx2 = interp(a, __fmul_rn(__fsub_rn(vx, a.gd[0]), a.vsinv[0]), uy, uz);
-            const float Fy1 = interp(a, ux, __fmul_rn(__fadd_rn(vy, a.gd[1]), a.vsinv[1]), uz);
-            const float Fy2 = interp(a, ux, __fmul_rn(__fsub_rn(vy, a.gd[1]), a.vsinv[1]), uz);
-            const float Fz1 = interp(a, ux, uy, __fmul_rn(__fadd_rn(vz, a.gd[2]), a.vsinv[2]));
-            const float Fz2 = interp(a, ux, uy, __fmul_rn(__fsub_rn(vz, a.gd[2]), a.vsinv[2]));
+            const float Fx1 = interp<SLAB>(a, __fmul_rn(__fadd_rn(vx, a.gd[0]), a.vsinv[0]), uy, uz);
+            const float Fx2 = interp<SLAB>(a, __fmul_rn(__fsub_rn(vx, a.gd[0]), a.vsinv[0]), uy, uz);
+            const float Fy1 = interp<SLAB>(a, ux, __fmul_rn(__fadd_rn(vy, a.gd[1]), a.vsinv[1]), uz);
+            const float Fy2 = interp<SLAB>(a, ux, __fmul_rn(__fsub_rn(vy, a.gd[1]), a.vsinv[1]), uz);
+            const float Fz1 = interp<SLAB>(a, ux, uy, __fmul_rn(__fadd_rn(vz, a.gd[2]), a.vsinv[2]));
+            const float Fz2 = interp<SLAB>(a, ux, uy, __fmul_rn(__fsub_rn(vz, a.gd[2]), a.vsinv[2]));
             float gx = __fdividef(__fsub_rn(Fx1, Fx2), a.gd[0]);
             float gy = __fdividef(__fsub_rn(Fy1, Fy2), a.gd[1]);
             float gz = __fdividef(__fsub_rn(Fz1, Fz2), a.gd[2]);
@@ -508,7 +513,9 @@ int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9]
     ctx->pyramid_fresh = a.fuse_pyramid;
     dim3 block(8, 4), grid((a.k.w + 7) / 8, (a.k.h + 3) / 4);
     if (ctx->profiling) cudaEventRecord(ctx->events[58], ctx->stream);
-    raycast_kernel<<<grid, block, 0, ctx->stream>>>(a);
+    const bool whole = a.zs0 == 0 && a.zs1 == a.Z && a.zo0 == 0 && a.zo1 == a.Z && a.bz0 == 0 && !getenv("KFB_RAYCAST_SLABCODE");
+    if (whole) raycast_kernel<false><<<grid, block, 0, ctx->stream>>>(a);
+    else raycast_kernel<true><<<grid, block, 0, ctx->stream>>>(a);
     KFB_LAUNCH_CHECK(ctx);
     if (ctx->profiling) cudaEventRecord(ctx->events[59], ctx->stream);
     return KFB_OK;
