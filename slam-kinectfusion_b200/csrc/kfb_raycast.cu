@@ -149,13 +149,19 @@ __device__ __forceinline__ float load_tsdf(const short *addr)
 // running-sum instructions only; otherwise KFB_RC_BATCH steps are classified and their loads issued before
 // the first sign test (sample positions do not depend on fetched values).  Candidate hits are parked and
 // their normals are computed after the march, when the warp has reconverged.
+#ifndef KFB_RC_WARPS
+#define KFB_RC_WARPS 1 // warps (8x4 pixel tiles, stacked in y) per block; 2 warps with 16 / 18 / 21 blocks per SM measured 155 / 154 / 159 us against 152
+#endif
+#ifndef KFB_RC_MINB
+#define KFB_RC_MINB 1  // launch-bounds hint: resident blocks per SM the register allocation must allow
+#endif
 template <bool SLAB>
-__global__ void __launch_bounds__(32) raycast_kernel(const RaycastArgs a)
+__global__ void __launch_bounds__(32 * KFB_RC_WARPS, KFB_RC_MINB) raycast_kernel(const RaycastArgs a)
 {
     const unsigned FULL = 0xffffffffu;
     // block = warp = 8x4 pixel tile (rays of very different length share nothing: fine-grained scheduling)
     const int x = blockIdx.x * 8 + threadIdx.x;
-    const int y = blockIdx.y * 4 + threadIdx.y;
+    const int y = blockIdx.y * (4 * KFB_RC_WARPS) + threadIdx.y;
     const bool inside = x < a.k.w && y < a.k.h;
     const int pix = y * a.k.w + x;
     float4 vout = make_float4(0.f, 0.f, 0.f, 0.f), nout = vout;
@@ -369,7 +375,7 @@ __global__ void __launch_bounds__(32) raycast_kernel(const RaycastArgs a)
             v = vo; n = no;
             lw >>= 1; lx >>= 1; ly >>= 1;
             const int mask = (1 << l) - 1;
-            if (((threadIdx.x & mask) == 0) && ((threadIdx.y & mask) == 0))
+            if (inside && ((threadIdx.x & mask) == 0) && ((threadIdx.y & mask) == 0))
             {
                 a.pyr_v[l - 1][ly * lw + lx] = v;
                 a.pyr_n[l - 1][ly * lw + lx] = n;
@@ -511,7 +517,7 @@ int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9]
         a.pyr_n[l - 1] = a.fuse_pyramid ? ctx->L[l].n[ctx->prev] : nullptr;
     }
     ctx->pyramid_fresh = a.fuse_pyramid;
-    dim3 block(8, 4), grid((a.k.w + 7) / 8, (a.k.h + 3) / 4);
+    dim3 block(8, 4 * KFB_RC_WARPS), grid((a.k.w + 7) / 8, (a.k.h + 4 * KFB_RC_WARPS - 1) / (4 * KFB_RC_WARPS));
     if (ctx->profiling) cudaEventRecord(ctx->events[58], ctx->stream);
     const bool whole = a.zs0 == 0 && a.zs1 == a.Z && a.zo0 == 0 && a.zo1 == a.Z && a.bz0 == 0 && !getenv("KFB_RAYCAST_SLABCODE");
     if (whole) raycast_kernel<false><<<grid, block, 0, ctx->stream>>>(a);
