@@ -153,7 +153,7 @@ __device__ __forceinline__ float load_tsdf(const short *addr)
 #define KFB_RC_WARPS 1 // warps (8x4 pixel tiles, stacked in y) per block; 2 warps with 16 / 18 / 21 blocks per SM measured 155 / 154 / 159 us against 152
 #endif
 #ifndef KFB_RC_MINB
-#define KFB_RC_MINB 1  // launch-bounds hint: resident blocks per SM the register allocation must allow
+#define KFB_RC_MINB 32 // launch-bounds hint: 32 one-warp blocks per SM (the hardware limit) => at most 64 registers
 #endif
 template <bool SLAB>
 __global__ void __launch_bounds__(32 * KFB_RC_WARPS, KFB_RC_MINB) raycast_kernel(const RaycastArgs a)
