@@ -287,7 +287,10 @@ def run_ours(args):
             k_ms.append(ctx.event_elapsed_ms(60, 61))
             call_ms.append(ctx.event_elapsed_ms(56, 57))
             rc_ms.append(ctx.event_elapsed_ms(58, 59))
-            icp_ms.append(ctx.event_elapsed_ms(54, 55))
+            try:
+                icp_ms.append(ctx.event_elapsed_ms(54, 55))
+            except Exception:  # KFB_ICP_DIRECT (profiler runs): no persistent kernel, the events were never recorded
+                pass
     ctx.set_profiling(False)
     # (2) updated-voxel counts (the counting variant of the kernel, on sampled frames at their tracked poses)
     volpose = np.array(hp.volu_pose, np.float32).reshape(3, 4)
@@ -356,7 +359,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "integrate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
                      "kernel_ms": k_ms_mean, "kernel_ms_how": "CUDA events around the launch, in situ in the pipelined sequence",
-                     "integrate_call_ms": float(np.mean(call_ms)), "raycast_kernel_ms": float(np.mean(rc_ms)), "icp_kernel_ms": float(np.mean(icp_ms)),
+                     "integrate_call_ms": float(np.mean(call_ms)), "raycast_kernel_ms": float(np.mean(rc_ms)), "icp_kernel_ms": float(np.mean(icp_ms)) if icp_ms else None,
                      "algorithmic_bytes": 8.0 * U_mean,
                      "dense_model_gbs": 8.0 * swept / (k_ms_mean * 1e-3) / 1e9, "dense_microconfig": dense},
         "clocks": clocks,
