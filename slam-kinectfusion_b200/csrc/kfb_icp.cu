@@ -49,14 +49,20 @@ struct IcpProbe
     float4 nc4;
     int j; // model pixel, -1 = no correspondence
 };
+__device__ __forceinline__ void icp_probe_values(const IcpArgs &a, const float4 nc4, const float4 vc4, IcpProbe &o);
 __device__ __forceinline__ void icp_probe(const IcpArgs &a, int p, int npix, IcpProbe &o)
 {
     o.j = -1;
     if (p >= npix) return;
     const int y = p / a.cov_w, x = p - y * a.cov_w;
     const int i = y * a.k.w + x;
-    o.nc4 = __ldg(a.cur_n + i);
-    const float4 vc4 = __ldg(a.cur_v + i);
+    const float4 nc4 = __ldg(a.cur_n + i);
+    icp_probe_values(a, nc4, __ldg(a.cur_v + i), o);
+}
+// the same from values the caller already holds (o.j must be -1 on entry)
+__device__ __forceinline__ void icp_probe_values(const IcpArgs &a, const float4 nc4, const float4 vc4, IcpProbe &o)
+{
+    o.nc4 = nc4;
     if (isnan(o.nc4.x)) return;
     const float3 r = rot3(a.pose.R, vc4.x, vc4.y, vc4.z);
     o.sx = __fadd_rn(r.x, a.pose.t[0]); o.sy = __fadd_rn(r.y, a.pose.t[1]); o.sz = __fadd_rn(r.z, a.pose.t[2]);
@@ -120,15 +126,44 @@ struct IcpLevel
 };
 
 #define ICP_BATCH 4
-__device__ __forceinline__ void icp_accumulate_pixels(const IcpArgs &a, double acc[27], int first, int stride)
+// A thread visits the same pixels in every iteration of a level (fixed pixel -> thread map), and the current
+// frame's vertex / normal of a pixel do not change while the pose does: the persistent kernel keeps the first
+// ICP_CACHE_SLOTS pixels of every thread in shared memory (thread-private slots, no synchronisation), which takes
+// one L2 round trip out of each batch's dependent chain (current maps -> projection -> model gathers).
+#define ICP_CACHE_SLOTS 5 // 640x480 on 148 SMs: 4.3 pixels per thread; 2 x 16 B x 5 x 480 = 75 KB per CTA
+template <bool CACHED>
+__device__ __forceinline__ void icp_accumulate_pixels(const IcpArgs &a, double acc[27], int first, int stride, float4 *cache = nullptr,
+                                                      bool fill = false)
 {
     const int npix = a.cov_w * a.cov_h;
-    for (int p0 = first; p0 < npix; p0 += ICP_BATCH * stride)
+    int slot0 = 0;
+    for (int p0 = first; p0 < npix; p0 += ICP_BATCH * stride, slot0 += ICP_BATCH)
     {
         IcpProbe pr[ICP_BATCH];
         float4 vp[ICP_BATCH], np[ICP_BATCH];
 #pragma unroll
-        for (int b = 0; b < ICP_BATCH; ++b) icp_probe(a, p0 + b * stride, npix, pr[b]);
+        for (int b = 0; b < ICP_BATCH; ++b)
+        {
+            if (!CACHED) icp_probe(a, p0 + b * stride, npix, pr[b]);
+            else
+            {
+                const int p = p0 + b * stride, slot = slot0 + b;
+                pr[b].j = -1;
+                if (p < npix)
+                {
+                    float4 *c = cache + (size_t)(2 * slot) * ICP_THREADS + threadIdx.x;
+                    if (slot < ICP_CACHE_SLOTS && !fill) icp_probe_values(a, c[0], c[ICP_THREADS], pr[b]);
+                    else
+                    {
+                        const int y = p / a.cov_w, x = p - y * a.cov_w;
+                        const int i = y * a.k.w + x;
+                        const float4 nc4 = __ldg(a.cur_n + i), vc4 = __ldg(a.cur_v + i);
+                        if (slot < ICP_CACHE_SLOTS) { c[0] = nc4; c[ICP_THREADS] = vc4; }
+                        icp_probe_values(a, nc4, vc4, pr[b]);
+                    }
+                }
+            }
+        }
 #pragma unroll
         for (int b = 0; b < ICP_BATCH; ++b)
         {
@@ -226,7 +261,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpArgs a)
     double acc[27];
 #pragma unroll
     for (int i = 0; i < 27; ++i) acc[i] = 0.0;
-    icp_accumulate_pixels(a, acc, blockIdx.x * ICP_THREADS + threadIdx.x, a.stride);
+    icp_accumulate_pixels<false>(a, acc, blockIdx.x * ICP_THREADS + threadIdx.x, a.stride);
     __shared__ double sm[ICP_THREADS / 32][27];
     __shared__ double red[ICP_THREADS / 32][28];
     __shared__ bool is_last;
@@ -378,6 +413,7 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
     __shared__ bool is_last;
     __shared__ int s_cmd, s_iter, s_spec, s_ok, s_pred;
     __shared__ float spose[12], npose[12], hpose[12];
+    extern __shared__ float4 cur_cache[]; // [ICP_CACHE_SLOTS][normal, vertex][ICP_THREADS]
 
     // ---- service warp: CTA 0 mirrors the host's poses into device memory; elsewhere it has nothing to do -------
     if (threadIdx.x >= ICP_THREADS)
@@ -427,6 +463,7 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
     a.dist_thres = P.dist_thres; a.sine_thres = P.sine_thres;
     if (threadIdx.x < 12) spose[threadIdx.x] = P.pose0[threadIdx.x];
     int k = 0, spec_used = 0;
+    int cached_level = -1; // level whose current-frame pixels this thread holds in cur_cache
     unsigned long long round = P.round0;
     ICP_BAR();
     for (;;)
@@ -452,7 +489,8 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
             double acc[27];
 #pragma unroll
             for (int i = 0; i < 27; ++i) acc[i] = 0.0;
-            icp_accumulate_pixels(a, acc, blockIdx.x * ICP_THREADS + threadIdx.x, gridDim.x * ICP_THREADS);
+            icp_accumulate_pixels<true>(a, acc, blockIdx.x * ICP_THREADS + threadIdx.x, gridDim.x * ICP_THREADS, cur_cache, level != cached_level);
+            cached_level = level;
             ts1 = globaltimer_ns();
             const double s = icp_block_reduce(acc, sm);
             if (threadIdx.x < 27)
@@ -747,7 +785,13 @@ static int icp_launch_persistent(kfb_ctx *ctx, const float pose12[12])
     const int blocks = ctx->sm_count;
     (void)max_pix;
     if (ctx->profiling) cudaEventRecord(ctx->events[54], ctx->stream); // the frame's whole ICP: 54 .. 55
-    icp_persistent_kernel<<<blocks, ICP_THREADS + 32, 0, ctx->stream>>>(P);
+    const size_t cache_bytes = (size_t)ICP_CACHE_SLOTS * 2 * ICP_THREADS * sizeof(float4);
+    if (!ctx->icp_smem_set) // per device, hence per context
+    {
+        KFB_CUDA(ctx, cudaFuncSetAttribute(icp_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cache_bytes));
+        ctx->icp_smem_set = 1;
+    }
+    icp_persistent_kernel<<<blocks, ICP_THREADS + 32, cache_bytes, ctx->stream>>>(P);
     KFB_LAUNCH_CHECK(ctx);
     if (ctx->profiling) cudaEventRecord(ctx->events[55], ctx->stream);
     S.enq = S.total;
