@@ -73,6 +73,7 @@ struct IntegrateArgs
     float Sx, Sy, Sz, invSz, driftE; // per-plane step of vc (float), 1/Sz, bound on the running-sum drift
     int max_weight;
     int no_fastpath;            // KFB_INTEGRATE_NOFAST: disable the deep-free-space path (tuning / testing)
+    int no_prefix;              // KFB_INTEGRATE_NOPREFIX: fast path only for warps whose whole interval is free space
     int diag;                   // KFB_INTEGRATE_DIAG (timing experiments ONLY, results are wrong): 1 = general-path warps return, 2 = fast-path warps return
     int use_jump, jump_min; // exact jump of the running sum for prefixes of at least jump_min planes
     uint8_t *bricks;
@@ -650,6 +651,7 @@ __global__ void __launch_bounds__(32 * KFB_INT_WARPS, KFB_INT_MINB * 4 / KFB_INT
     {
         const unsigned act = __activemask();
         zfw = __reduce_min_sync(act, free_end);
+        if (a.no_prefix) zfw = __ballot_sync(act, free_end >= zb) == act ? 0x7fffffff : -0x7fffffff; // all or nothing
     }
     unsigned int n_upd = 0;
     const size_t plane4 = ((size_t)a.X * a.Y) >> 2; // uint4 per plane
@@ -964,6 +966,7 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
     a.zexit = ctx->zexit;
     a.max_weight = ctx->p.tsdf_max_weight;
     a.no_fastpath = getenv("KFB_INTEGRATE_NOFAST") ? 1 : 0;
+    a.no_prefix = getenv("KFB_INTEGRATE_NOPREFIX") ? 1 : 0;
     a.diag = getenv("KFB_INTEGRATE_DIAG") ? atoi(getenv("KFB_INTEGRATE_DIAG")) : 0;
     a.use_jump = getenv("KFB_INTEGRATE_NOJUMP") ? 0 : 1;
     // measured on B200: a jump costs about as much as 600 replayed planes (warps that straddle vc.x == 0 walk
@@ -991,11 +994,11 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
     if (planes <= 0) return KFB_OK;
     // z-chunks give resident warps and load balance (the visited interval differs per column); the running
     // sum at each chunk start comes from column_states_kernel, so chunks cost no replay.  48 B per thread per
-    // chunk of state: bounded to max(128 MB, 1/32 of the volume).  KFB_INTEGRATE_ZCHUNKS overrides for tuning.
+    // chunk of state: bounded to max(128 MB, 1/8 of the volume).  KFB_INTEGRATE_ZCHUNKS overrides for tuning.
     const size_t nthr = (size_t)(a.X >> 2) * a.Y;
     int zc = (planes + 15) / 16;
     if (zc > 32) zc = 32;
-    const size_t state_cap = std::max((size_t)128 << 20, ctx->vol_voxels * sizeof(uint32_t) / 32); // <= 3 % of the volume
+    const size_t state_cap = std::max((size_t)128 << 20, ctx->vol_voxels * sizeof(uint32_t) / 8); // <= 1/8 of the volume (measured: 1024^3 wants 32 chunks, 403 MB)
     while (zc > 1 && (size_t)zc * 48 * nthr > state_cap) --zc;
     if (const char *e = getenv("KFB_INTEGRATE_ZCHUNKS")) zc = atoi(e) > 0 ? atoi(e) : zc;
     if (zc > planes) zc = planes;

@@ -15,7 +15,7 @@ def main():
     poses = [kfo.trajectory_pose(30 + k) for k in range(12)]
     frames = [kfo.render_depth_mm(p, Ko) for p in poses]
     for zc in chunks:
-        for diag in (0, 3, 1, 2):
+        for diag in ((0, 3, 1, 2) if len(chunks) == 1 else (0,)):
             os.environ.pop("KFB_INTEGRATE_DIAG", None)
             os.environ.pop("KFB_INTEGRATE_ZCHUNKS", None)
             if zc: os.environ["KFB_INTEGRATE_ZCHUNKS"] = str(zc)
