@@ -348,7 +348,6 @@ __global__ void __launch_bounds__(32 * KFB_RC_WARPS, KFB_RC_MINB) raycast_kernel
     // reference's summation order ((d00 + d01) + d10) + d11, * 0.25, zero when any vertex x is NaN.
     if (a.fuse_pyramid)
     {
-        const int lane = threadIdx.y * 8 + threadIdx.x;
         float4 v = vout, n = nout;
         int lw = a.k.w, lx = x, ly = y;
 #pragma unroll
@@ -381,7 +380,6 @@ __global__ void __launch_bounds__(32 * KFB_RC_WARPS, KFB_RC_MINB) raycast_kernel
                 a.pyr_n[l - 1][ly * lw + lx] = n;
             }
         }
-        (void)lane;
     }
 }
 
