@@ -141,3 +141,41 @@ def test_pipeline_from_dataset_equals_pipeline_from_memory(tmp_path):
     for (_, depth), (_, d) in zip(s, frames):
         assert a.pipeline(depth) == 0 and b.pipeline(d) == 0
     assert np.array_equal(np.asarray(a.poses()), np.asarray(b.poses()))
+
+
+def _example_binary():
+    """examples/kinfu_dataset.cpp -- the reference's main.cpp loop, headless -- compiled against the facade."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    kfb.build_all()
+    subprocess.check_call(["make", "-C", os.path.join(root, "slam-kinectfusion_b200", "kfusion"), "example"],
+                          stdout=subprocess.DEVNULL)
+    exe = os.path.join(root, "slam-kinectfusion_b200", "kinfu_dataset")
+    assert os.access(exe, os.X_OK)
+    return exe
+
+
+def test_reference_style_application_compiles_against_the_facade():
+    _example_binary()
+
+
+@pytest.mark.gpu
+def test_reference_style_application_runs(tmp_path):
+    import subprocess
+    from slam_kinectfusion_b200 import synth
+    exe = _example_binary()
+    K = kfb.Intrinsics(**kfb.SENSORS["kinect1"])
+    data, out = tmp_path / "dataset", tmp_path / "out"
+    (data / "color").mkdir(parents=True)
+    (data / "depth").mkdir()
+    out.mkdir()
+    for k, (_, d) in enumerate(synth.sequence(7, K)):
+        assert kfb.write_png_gray16(data / "depth" / f"{k:04d}.png", d.astype(np.uint16))
+        assert kfb.write_png_rgb8(data / "color" / f"{k:04d}.png", np.full((K.height, K.width, 3), 90, np.uint8))
+    (data / "intr.txt").write_text(f"{K.fx} 0 {K.cx}\n0 {K.fy} {K.cy}\n0 0 1\n")
+    r = subprocess.run([exe, str(data), str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "7 frames, end!" in r.stdout and "tracking fail" not in r.stdout, r.stdout + r.stderr
+    assert len(open(out / "poses.txt").read().strip().splitlines()) == 7 * 4  # one 4x4 matrix per frame
+    assert open(out / "pointcloud.ply").readline().strip() == "ply"
+    view = cv2.imread(str(out / "scene.png"), 1)
+    assert view.shape == (K.height, K.width, 3) and view.any()
