@@ -21,14 +21,19 @@
 //     inequalities, vc.z > 0 and vc.z <= max accepted depth are half-lines in z) and an occlusion cut from a
 //     max-pyramid of the thresholds over the pixels the columns can reach; planes outside are not visited,
 //     inside the interval the exact per-voxel predicate still decides;
-//   * a deep-free-space path: when every pixel a warp's columns can land on still sees free space at the
-//     chunk's largest vc.z, all voxels of the interval get tsdf = 1.0f -- no projection, no running sums;
+//   * a deep-free-space path: while every pixel a warp's columns can land on still sees free space at a
+//     plane's largest vc.z, all voxels of that plane get tsdf = 1.0f -- no projection, no running sums.  vc.z
+//     grows with z, so these planes are a prefix of a chunk: the warp streams through it and takes the general
+//     path only behind it;
+//   * in the general path every stage's dependent loads (thresholds, exact depth, weight table, brick flags)
+//     are issued together: the warps wait on memory with every slot of the SM taken, so time is the sum of the
+//     warps' lifetimes;
 //   * the update runs without the quarter-rate XU pipe: int->float by magic-number add, the reciprocal of
 //     weight+1 from a device-built table of MUFU.RCP results, float->int truncation by an RZ add of 2^23;
 //   * when a thread's four voxels hold the same word and receive the same tsdf (free space), the update is
 //     computed once; stores whose value equals the loaded one are dropped.
-// Measured (profiles/): 58 M warp instructions per 640x480 / 512^3 frame (the first version: 271 M), DRAM
-// traffic = algorithmic bytes; 85-92 % of the measured HBM copy bandwidth when every voxel is updated.
+// Measured (profiles/): 56 M warp instructions per 640x480 / 512^3 frame (the first version: 271 M), DRAM
+// traffic within 10 % of the algorithmic bytes; 82 % of the measured HBM copy bandwidth when every voxel is updated.
 // Side product for the raycaster: a voxel that turns negative marks the 8^3 bricks within two voxels of it in
 // a byte map; three separable passes turn the map into the brick distance field kfb_raycast.cu skips with.
 #include "kfb_common.cuh"
@@ -548,8 +553,8 @@ __device__ __forceinline__ void update_quad(const IntegrateArgs &a, uint4 *vp, c
 template <int U, bool COUNT>
 __global__ void __launch_bounds__(32 * KFB_INT_WARPS, KFB_INT_MINB * 4 / KFB_INT_WARPS) integrate_kernel(const IntegrateArgs a)
 {
-    // a warp owns a compact 32 x 4 voxel patch (8 threads x 4 rows; 128 B per row): its columns see nearly the
-    // same part of the image, so warp-level decisions (fast path, loop bounds) are mostly unanimous
+    // a warp owns a compact 16 x 8 voxel patch (KFB_INT_PX = 4 threads x 8 rows; 64 B per row): its columns see
+    // nearly the same part of the image, so warp-level decisions (fast path, loop bounds) are mostly unanimous
     const int x0 = (blockIdx.x * (KFB_INT_WARPS * KFB_INT_PX) + threadIdx.y * KFB_INT_PX + (threadIdx.x & (KFB_INT_PX - 1))) * 4;
     const int y = blockIdx.y * (32 / KFB_INT_PX) + (threadIdx.x / KFB_INT_PX);
     if (x0 >= a.X || y >= a.Y) return;
