@@ -23,7 +23,7 @@ struct Image
     std::vector<unsigned char> data8;   // bit_depth <= 8 (1/2/4-bit samples are widened to 8 without scaling)
     std::vector<unsigned short> data16; // bit_depth == 16
 };
-// false + `err` on anything that is not a well-formed, non-interlaced PNG
+// false + `err` on anything that is not a well-formed PNG (all colour types and bit depths, Adam7 interlace)
 bool read(const std::string &path, Image &out, std::string *err = nullptr);
 // writer for tests and tools: 8-bit RGB (channels == 3) or 16-bit grey (channels == 1)
 bool write_gray16(const std::string &path, const unsigned short *pix, int width, int height);

@@ -82,7 +82,7 @@ bool kf::png::read(const std::string &path, Image &out, std::string *err)
 
     int width = 0, height = 0, bit_depth = 0, color_type = -1;
     std::vector<u8> zdata, palette;
-    bool seen_end = false;
+    bool seen_end = false, interlaced = false;
     for (size_t at = 8; at + 12 <= file.size() && !seen_end;)
     {
         const u32 len = be32(&file[at]);
@@ -95,7 +95,8 @@ bool kf::png::read(const std::string &path, Image &out, std::string *err)
             width = (int)be32(data); height = (int)be32(data + 4);
             bit_depth = data[8]; color_type = data[9];
             if (data[10] != 0 || data[11] != 0) return fail(err, path + ": unknown compression / filter method");
-            if (data[12] != 0) return fail(err, path + ": interlaced PNG is not supported");
+            if (data[12] > 1) return fail(err, path + ": unknown interlace method");
+            interlaced = data[12] == 1;
         }
         else if (!std::memcmp(type, "PLTE", 4)) palette.assign(data, data + len);
         else if (!std::memcmp(type, "IDAT", 4)) zdata.insert(zdata.end(), data, data + len);
@@ -120,68 +121,83 @@ bool kf::png::read(const std::string &path, Image &out, std::string *err)
     if (!depth_ok) return fail(err, path + ": bad bit depth for its colour type");
     if (color_type == 3 && (palette.empty() || palette.size() % 3)) return fail(err, path + ": palette image without a valid PLTE");
 
-    // inflate: height rows of (filter byte + stride bytes)
-    const size_t stride = ((size_t)width * file_channels * bit_depth + 7) / 8;
-    std::vector<u8> raw((stride + 1) * (size_t)height);
+    // Sub-images in file order: the whole image, or the seven Adam7 passes (PNG spec 8.2): pixel i of row j of a
+    // pass lands at (x0 + i dx, y0 + j dy).  Each is filtered on its own: rows of (filter byte + stride bytes).
+    struct Pass { int x0, y0, dx, dy; };
+    static const Pass whole[1] = {{0, 0, 1, 1}};
+    static const Pass adam7[7] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+    const Pass *passes = interlaced ? adam7 : whole;
+    const int npasses = interlaced ? 7 : 1;
+    const size_t bits_px = (size_t)file_channels * bit_depth;
+    size_t total = 0;
+    for (int k = 0; k < npasses; ++k)
+    {
+        const int pw = (width - passes[k].x0 + passes[k].dx - 1) / passes[k].dx, ph = (height - passes[k].y0 + passes[k].dy - 1) / passes[k].dy;
+        if (pw > 0 && ph > 0) total += (((size_t)pw * bits_px + 7) / 8 + 1) * (size_t)ph;
+    }
+    std::vector<u8> raw(total);
     uLongf raw_len = (uLongf)raw.size();
     if (uncompress(raw.data(), &raw_len, zdata.data(), (uLong)zdata.size()) != Z_OK || raw_len != raw.size())
         return fail(err, path + ": corrupt image data");
-
-    // undo the row filters in place (PNG spec 9.2); bpp = bytes per complete pixel, at least 1
-    const size_t bpp = std::max<size_t>(1, (size_t)file_channels * bit_depth / 8);
-    for (int y = 0; y < height; ++y)
-    {
-        u8 *row = &raw[(stride + 1) * (size_t)y + 1];
-        const u8 *up = y ? row - (stride + 1) : nullptr;
-        const int filter = row[-1];
-        if (filter > 4) return fail(err, path + ": bad row filter");
-        for (size_t i = 0; i < stride; ++i)
-        {
-            const int a = i >= bpp ? row[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= bpp) ? up[i - bpp] : 0;
-            int pred = 0;
-            if (filter == 1) pred = a;
-            else if (filter == 2) pred = b;
-            else if (filter == 3) pred = (a + b) >> 1;
-            else if (filter == 4) pred = paeth(a, b, c);
-            row[i] = (u8)(row[i] + pred);
-        }
-    }
 
     out = Image();
     out.width = width; out.height = height;
     out.channels = color_type == 3 ? 3 : file_channels;
     out.bit_depth = bit_depth == 16 ? 16 : 8;
     const size_t n = (size_t)width * height * out.channels;
-    if (bit_depth == 16)
+    if (bit_depth == 16) out.data16.resize(n);
+    else out.data8.resize(n);
+
+    const size_t bpp = std::max<size_t>(1, bits_px / 8); // bytes per complete pixel, at least 1 (PNG spec 9.2)
+    size_t at = 0;
+    for (int k = 0; k < npasses; ++k)
     {
-        out.data16.resize(n);
-        for (int y = 0; y < height; ++y)
+        const Pass &ps = passes[k];
+        const int pw = (width - ps.x0 + ps.dx - 1) / ps.dx, ph = (height - ps.y0 + ps.dy - 1) / ps.dy;
+        if (pw <= 0 || ph <= 0) continue;
+        const size_t stride = ((size_t)pw * bits_px + 7) / 8;
+        for (int j = 0; j < ph; ++j)
         {
-            const u8 *row = &raw[(stride + 1) * (size_t)y + 1];
-            unsigned short *dst = &out.data16[(size_t)y * width * out.channels];
-            for (size_t i = 0; i < (size_t)width * out.channels; ++i) dst[i] = (unsigned short)((row[2 * i] << 8) | row[2 * i + 1]);
-        }
-        return true;
-    }
-    out.data8.resize(n);
-    for (int y = 0; y < height; ++y)
-    {
-        const u8 *row = &raw[(stride + 1) * (size_t)y + 1];
-        u8 *dst = &out.data8[(size_t)y * width * out.channels];
-        if (bit_depth == 8 && color_type != 3) std::memcpy(dst, row, (size_t)width * out.channels);
-        else
-            for (int x = 0; x < width; ++x)
+            // undo the row filter in place
+            u8 *row = &raw[at + (stride + 1) * (size_t)j + 1];
+            const u8 *up = j ? row - (stride + 1) : nullptr;
+            const int filter = row[-1];
+            if (filter > 4) return fail(err, path + ": bad row filter");
+            for (size_t i = 0; i < stride; ++i)
             {
-                // 1/2/4/8-bit sample x of the row, most significant bits first
-                const int per = 8 / bit_depth, shift = (per - 1 - x % per) * bit_depth;
-                const int v = (row[x / per] >> shift) & ((1 << bit_depth) - 1);
-                if (color_type == 3)
-                {
-                    if ((size_t)v * 3 + 2 >= palette.size()) return fail(err, path + ": palette index out of range");
-                    dst[3 * x] = palette[3 * v]; dst[3 * x + 1] = palette[3 * v + 1]; dst[3 * x + 2] = palette[3 * v + 2];
-                }
-                else dst[x] = (u8)(v * 255 / ((1 << bit_depth) - 1)); // grey 1/2/4 -> 8 bits, libpng's expansion
+                const int a = i >= bpp ? row[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= bpp) ? up[i - bpp] : 0;
+                int pred = 0;
+                if (filter == 1) pred = a;
+                else if (filter == 2) pred = b;
+                else if (filter == 3) pred = (a + b) >> 1;
+                else if (filter == 4) pred = paeth(a, b, c);
+                row[i] = (u8)(row[i] + pred);
             }
+            // scatter the row's pixels
+            const int y = ps.y0 + j * ps.dy;
+            for (int i = 0; i < pw; ++i)
+            {
+                const size_t o = ((size_t)y * width + (ps.x0 + i * ps.dx)) * out.channels;
+                if (bit_depth == 16)
+                    for (int ch = 0; ch < file_channels; ++ch)
+                        out.data16[o + ch] = (unsigned short)((row[2 * ((size_t)i * file_channels + ch)] << 8) | row[2 * ((size_t)i * file_channels + ch) + 1]);
+                else if (bit_depth == 8 && color_type != 3)
+                    for (int ch = 0; ch < file_channels; ++ch) out.data8[o + ch] = row[(size_t)i * file_channels + ch];
+                else
+                {
+                    // 1/2/4/8-bit sample i of the row, most significant bits first
+                    const int per = 8 / bit_depth, shift = (per - 1 - i % per) * bit_depth;
+                    const int v = (row[i / per] >> shift) & ((1 << bit_depth) - 1);
+                    if (color_type == 3)
+                    {
+                        if ((size_t)v * 3 + 2 >= palette.size()) return fail(err, path + ": palette index out of range");
+                        out.data8[o] = palette[3 * v]; out.data8[o + 1] = palette[3 * v + 1]; out.data8[o + 2] = palette[3 * v + 2];
+                    }
+                    else out.data8[o] = (u8)(v * 255 / ((1 << bit_depth) - 1)); // grey 1/2/4 -> 8 bits, libpng's expansion
+                }
+            }
+        }
+        at += (stride + 1) * (size_t)ph;
     }
     return true;
 }

@@ -179,3 +179,44 @@ def test_reference_style_application_runs(tmp_path):
     assert open(out / "pointcloud.ply").readline().strip() == "ply"
     view = cv2.imread(str(out / "scene.png"), 1)
     assert view.shape == (K.height, K.width, 3) and view.any()
+
+
+@pytest.mark.parametrize("kind", ["rgb8", "gray16", "gray1"])
+def test_png_decoder_reads_adam7_interlaced_files(tmp_path, kind):
+    """Interlaced files (assembled by hand: cv2 cannot write them) against cv2.imread, sizes that leave passes empty."""
+    rng = np.random.default_rng(11)
+    for h, w in ((37, 53), (2, 3), (1, 1), (9, 4)):
+        if kind == "rgb8":
+            img, bits, ctype = rng.integers(0, 255, (h, w, 3), dtype=np.uint8), 8, 2
+        elif kind == "gray16":
+            img, bits, ctype = rng.integers(0, 65535, (h, w), dtype=np.uint16), 16, 0
+        else:
+            img, bits, ctype = rng.integers(0, 2, (h, w), dtype=np.uint8), 1, 0
+        data = b""
+        for x0, y0, dx, dy in ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)):
+            sub = img[y0::dy, x0::dx]
+            if sub.size == 0:
+                continue
+            for r in sub:
+                if bits == 16:
+                    row = r.astype(">u2").tobytes()
+                elif bits == 8:
+                    row = r.tobytes()
+                else:
+                    row = np.packbits(r).tobytes()  # most significant bit first, zero padded
+                data += b"\x00" + row
+
+        def chunk(t, d):
+            return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d))
+
+        d = tmp_path / f"{kind}_{h}x{w}"
+        (d / "color").mkdir(parents=True)
+        (d / "depth").mkdir()
+        name = str(d / "color" / "a.png")
+        open(name, "wb").write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, bits, ctype, 0, 0, 1))
+                               + chunk(b"IDAT", zlib.compress(data)) + chunk(b"IEND", b""))
+        ref = cv2.imread(name, 1)
+        assert ref is not None and ref.shape == (h, w, 3)
+        cv2.imwrite(str(d / "depth" / "a.png"), np.zeros((h, w), np.uint16))
+        bgr, _ = kfb.DatasetSensor(d).get_frame()
+        assert np.array_equal(bgr, ref), (kind, h, w)
