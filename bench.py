@@ -337,7 +337,9 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        nb = 1 + 6
+        # ~10-15 s of host work: ~0.33 s per frame at 512^3 on 16 cores, cubic in the volume side
+        nb = 1 + max(3, min(40, int(40 * (512.0 / dims) ** 3)))
+        nb = min(nb, len(frames))
         cval, csec, cU = oracle_frames_per_s(dims, frames[:nb], cores)
         cpu = {"value": cval, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{nb - 1} frames after the bootstrap frame of the same sequence, whole pipeline "
