@@ -603,7 +603,7 @@ def test_integrate_switches_bit_identical(kfo, kfb):
         plain, n_plain = run({"KFB_INTEGRATE_NOCULL": "1", "KFB_INTEGRATE_NOFAST": "1", "KFB_INTEGRATE_ZCHUNKS": "1"})
         assert plain[..., 1].max() >= 6
         for env in ({}, {"KFB_INTEGRATE_NOFAST": "1"}, {"KFB_INTEGRATE_NOOCC": "1"}, {"KFB_INTEGRATE_ZCHUNKS": "3"},
-                    {"KFB_INTEGRATE_ZCHUNKS": "32"}, {"KFB_INTEGRATE_NOPREFIX": "1"}, {"KFB_INTEGRATE_U": "1"}, {"KFB_INTEGRATE_U": "4"}):
+                    {"KFB_INTEGRATE_ZCHUNKS": "32"}, {"KFB_INTEGRATE_NOPREFIX": "1"}, {"KFB_INTEGRATE_U": "2"}, {"KFB_INTEGRATE_U": "4"}):
             vol, n = run(env)
             assert n == n_plain, env
             assert np.array_equal(vol, plain), env
