@@ -4,14 +4,7 @@
 #include <safe_call.hpp>
 #include <cstring>
 
-kf::ICPRegistration::ICPRegistration(const float d, const float a) : dist_thres(d)
-{
-    angle_thres = sinf(deg2rad(a)); // icp_registration.cpp:5 -- the gate is a sine
-}
-void kf::ICPRegistration::setMaxDistThres(const float v) { dist_thres = v; }
-void kf::ICPRegistration::setMaxAngleThres(const float v) { angle_thres = deg2rad(v); } // sic, as the reference (:10)
-void kf::ICPRegistration::setIterationNum(const std::vector<int> &iters_) { iters = iters_; }
-void kf::ICPRegistration::setIntrinsics(const Intrinsics intrs_) { intrs = intrs_; }
+kf::ICPRegistration::ICPRegistration(const float d, const float a) : gate_distance_(d), gate_sine_(sinf(deg2rad(a))) {}
 
 // rigid_icp.cu:156-165 (unpack) + icp_registration.cpp:35-39 (guard + solve)
 bool kf::ICPRegistration::solve(const double in27[27], double x6[6])
@@ -86,12 +79,12 @@ bool kf::ICPRegistration::rigidTransform(cv::Affine3f &camera_pose, const cv::Af
     // of time by kfb_icp_begin and is released by kfb_icp_step, so no launch latency sits between the
     // host solve and the next accumulation.
     int sched[KFB_MAX_LEVELS] = {0};
-    for (size_t l = 0; l < iters.size() && l < KFB_MAX_LEVELS; ++l) sched[l] = iters[l];
+    for (size_t l = 0; l < schedule_.size() && l < KFB_MAX_LEVELS; ++l) sched[l] = schedule_[l];
     if (kfbSafeCall(ctx, kfb_icp_begin(ctx, sched)) != KFB_OK) return false;
     bool ok = true;
-    for (int level = (int)iters.size() - 1; level >= 0 && ok; level--)
+    for (int level = (int)schedule_.size() - 1; level >= 0 && ok; level--)
     {
-        for (int i = 0; i < iters[level] && ok; i++)
+        for (int i = 0; i < schedule_[level] && ok; i++)
         {
             float pose12[12];
             double sums[27], x[6];

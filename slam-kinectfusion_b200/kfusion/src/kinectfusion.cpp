@@ -198,24 +198,13 @@ bool kf::file::readIntrinsics(const std::string &filename, kf::Intrinsics &intr)
     return true;
 }
 
+// The values of kinectfusion.cpp:167-190; the scalar ones are the struct's in-class initialisers.
 kf::kinectfuison_params kf::kinectfuison_params::default_params()
 {
     kf::kinectfuison_params p;
-    p.pyramid_height = 3;
-    p.bfilter_color_sigma = 10;
-    p.bfilter_spatial_sigma = 10;
-    p.bfilter_kernel_size = 5;
-    p.dfilter_dist = 5.f;
-    p.icp_angle__threshold = 30.f;
-    p.icp_dist_threshold = 0.015f;
-    p.icp_iter_count = std::vector<int>{4, 5, 10};
-    p.volu_dims = cv::Vec3i::all(512);
-    p.volu_range = cv::Vec3f::all(3.f);
     p.volu_trun_dist = 2.1f * p.volu_range(0) / p.volu_dims(0);
+    // the volume is centred on the first camera's optical axis and starts half a metre in front of it
     p.volu_pose = cv::Affine3f().translate(cv::Vec3f(-p.volu_range[0] / 2, -p.volu_range[1] / 2, 0.5f));
-    p.init_cam_model_dist = 0.f;
-    p.min_pose_move = 0.008f;
-    p.tsdf_max_weight = 64;
     return p;
 }
 void kf::kinectfusion::release()

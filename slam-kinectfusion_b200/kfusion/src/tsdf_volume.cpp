@@ -9,8 +9,8 @@ namespace kf
 {
 std::vector<int16_t> TSDFVolume::Data()
 {
-    std::vector<int16_t> out(2 * kfb_volume_voxels(dev->ctx));
-    kfbSafeCall(dev->ctx, kfb_download_volume(dev->ctx, out.data()));
+    std::vector<int16_t> out(2 * kfb_volume_voxels(dev_->ctx));
+    kfbSafeCall(dev_->ctx, kfb_download_volume(dev_->ctx, out.data()));
     return out;
 }
 namespace
@@ -29,8 +29,8 @@ bool TSDFVolume::save(const std::string &path)
     const std::vector<int16_t> data = Data();
     CheckpointHeader h;
     std::memcpy(h.magic, "KFB200V1", 8);
-    for (int i = 0; i < 3; ++i) { h.dims[i] = dims(i); h.range[i] = scene_size(i); }
-    h.trunc = trun_dist;
+    for (int i = 0; i < 3; ++i) { h.dims[i] = grid_(i); h.range[i] = extent_(i); }
+    h.trunc = truncation_;
     h.voxels = data.size() / 2;
     std::FILE *f = std::fopen(path.c_str(), "wb");
     if (!f) return false;
@@ -44,8 +44,8 @@ bool TSDFVolume::load(const std::string &path)
     if (!f) return false;
     CheckpointHeader h;
     bool ok = std::fread(&h, sizeof(h), 1, f) == 1 && std::memcmp(h.magic, "KFB200V1", 8) == 0;
-    for (int i = 0; i < 3 && ok; ++i) ok = h.dims[i] == dims(i) && h.range[i] == scene_size(i);
-    ok = ok && h.voxels == kfb_volume_voxels(dev->ctx);
+    for (int i = 0; i < 3 && ok; ++i) ok = h.dims[i] == grid_(i) && h.range[i] == extent_(i);
+    ok = ok && h.voxels == kfb_volume_voxels(dev_->ctx);
     std::vector<int16_t> data;
     if (ok)
     {
@@ -54,50 +54,43 @@ bool TSDFVolume::load(const std::string &path)
     }
     std::fclose(f);
     if (!ok) return false;
-    return kfbSafeCall(dev->ctx, kfb_upload_volume(dev->ctx, data.data())) == KFB_OK;
+    return kfbSafeCall(dev_->ctx, kfb_upload_volume(dev_->ctx, data.data())) == KFB_OK;
 }
-cv::Vec3f TSDFVolume::VoxelSize() { return voxel_size; }
-cv::Vec3f TSDFVolume::SceneSize() { return scene_size; }
-cv::Vec3i TSDFVolume::Dims() { return dims; }
-void TSDFVolume::setTrunDist(const float v) { trun_dist = v; }
-void TSDFVolume::setMaxWeight(const int w) { max_weight = w; }
-void TSDFVolume::setPose(const cv::Affine3f p) { volume_pose = p; }
-void TSDFVolume::setIntrinsics(const Intrinsics i) { intr = i; }
 
-TSDFVolume::TSDFVolume(const DeviceContextPtr &dev_, const cv::Vec3f scene_size_, const cv::Vec3i dims_)
-    : dev(dev_), scene_size(scene_size_), dims(dims_)
+TSDFVolume::TSDFVolume(const DeviceContextPtr &dev_arg, const cv::Vec3f scene_size_, const cv::Vec3i dims_)
+    : dev_(dev_arg), grid_(dims_), extent_(scene_size_)
 {
-    voxel_size = cv::Vec3f(scene_size_(0) / dims_(0), scene_size_(1) / dims_(1), scene_size_(2) / dims_(2)); // :16
+    cell_ = cv::Vec3f(scene_size_(0) / dims_(0), scene_size_(1) / dims_(1), scene_size_(2) / dims_(2)); // :16
     reset();
 }
-void TSDFVolume::reset() { if (dev) kfbSafeCall(dev->ctx, kfb_reset_volume(dev->ctx)); }
-void TSDFVolume::release() { dev.reset(); }
+void TSDFVolume::reset() { if (dev_) kfbSafeCall(dev_->ctx, kfb_reset_volume(dev_->ctx)); }
+void TSDFVolume::release() { dev_.reset(); }
 
 void TSDFVolume::integrate(const cv::Affine3f &camera_pose)
 {
-    const cv::Affine3f vol2cam = camera_pose.inv() * volume_pose; // :50
+    const cv::Affine3f vol2cam = camera_pose.inv() * pose_; // :50
     float p[12];
     vol2cam.to12(p);
-    kfbSafeCall(dev->ctx, kfb_integrate(dev->ctx, p, nullptr));
+    kfbSafeCall(dev_->ctx, kfb_integrate(dev_->ctx, p, nullptr));
 }
 void TSDFVolume::raycast(const cv::Affine3f &camera_pose)
 {
-    const cv::Affine3f cam2vol = volume_pose.inv() * camera_pose; // :59
+    const cv::Affine3f cam2vol = pose_.inv() * camera_pose; // :59
     // cam2vol.rotation().inv(DECOMP_SVD) (:61): inverse of the rotation block
     cv::Affine3f rot_only(cam2vol.rotation(), cv::Vec3f(0.f, 0.f, 0.f));
     const cv::Matx33f Rinv = rot_only.inv().rotation();
     float p[12];
     cam2vol.to12(p);
-    kfbSafeCall(dev->ctx, kfb_raycast(dev->ctx, p, Rinv.val));
+    kfbSafeCall(dev_->ctx, kfb_raycast(dev_->ctx, p, Rinv.val));
 }
 cv::Mat TSDFVolume::fetchPointCloud()
 {
     enum { DEFAULT_CLOUD_BUFFER_SIZE = 10 * 1000 * 1000 }; // :65-68
     std::vector<float> pts((size_t)DEFAULT_CLOUD_BUFFER_SIZE * 3);
     float vp[12];
-    volume_pose.to12(vp);
+    pose_.to12(vp);
     size_t n = 0;
-    kfbSafeCall(dev->ctx, kfb_extract_points(dev->ctx, vp, pts.data(), DEFAULT_CLOUD_BUFFER_SIZE, &n));
+    kfbSafeCall(dev_->ctx, kfb_extract_points(dev_->ctx, vp, pts.data(), DEFAULT_CLOUD_BUFFER_SIZE, &n));
     return cv::Mat(1, (int)n, cv::CV_32FC3, pts.data());
 }
 } // namespace kf
