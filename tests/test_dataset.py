@@ -220,3 +220,17 @@ def test_png_decoder_reads_adam7_interlaced_files(tmp_path, kind):
         cv2.imwrite(str(d / "depth" / "a.png"), np.zeros((h, w), np.uint16))
         bgr, _ = kfb.DatasetSensor(d).get_frame()
         assert np.array_equal(bgr, ref), (kind, h, w)
+
+
+@pytest.mark.parametrize("h,w", [(1, 1), (1, 7), (7, 1), (3, 5), (48, 64)])
+def test_own_writer_and_decoder_agree_on_odd_sizes(tmp_path, h, w):
+    rng = np.random.default_rng(h * 100 + w)
+    (tmp_path / "color").mkdir()
+    (tmp_path / "depth").mkdir()
+    d = rng.integers(0, 65535, (h, w), dtype=np.uint16)
+    c = rng.integers(0, 255, (h, w, 3), dtype=np.uint8)
+    assert kfb.write_png_gray16(tmp_path / "depth" / "0.png", d) and kfb.write_png_rgb8(tmp_path / "color" / "0.png", c)
+    s = kfb.DatasetSensor(tmp_path)
+    assert (s.height, s.width) == (h, w)
+    bgr, depth = s.get_frame()
+    assert np.array_equal(bgr[..., ::-1], c) and np.array_equal(depth, d.astype(np.float32))
