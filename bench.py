@@ -38,13 +38,25 @@ UNIT = "voxel-updates/s"
 WEAK_DIMS = {1: 512, 2: 640, 4: 812, 8: 1024}
 
 
+TRAFFIC_FILE = "r02_integrate_traffic.json"
+
+
 def ncu_traffic():
-    """dram bytes per launch of the integrate kernel from the committed ncu --set full capture (profiles/)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_integrate_traffic.json")) as f:
-            return float(json.load(f)["dram_bytes_per_launch"])
-    except Exception:
-        return None
+    """dram bytes per launch of the integrate kernel.  NOT measured in this run (ncu cannot run inside a timed
+    bench): read from the committed `ncu --set full` capture of this same command under profiles/."""
+    for name in (TRAFFIC_FILE, "r01_integrate_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return float(json.load(f)["dram_bytes_per_launch"]), f"committed ncu capture profiles/{name} (not measured in this run)"
+        except Exception:
+            continue
+    return None, "no capture committed"
+
+
+def workload_label(dims):
+    """One string for both arms (the driver compares them): the job, not how an arm runs it."""
+    return (f"640x480 depth, {dims}^3 TSDF over 3 m, ICP 10/5/4, 300-frame looped synthetic box+sphere room trajectory"
+            + (" (BASELINE configs[1])" if dims == 512 else ""))
 
 
 def measured_peak_hbm():
@@ -126,7 +138,9 @@ def run_reference(args):
         return
     from slam_kinectfusion_b200 import synth
     import slam_kinectfusion_b200 as kfb
-    dims = 512 if args.dims is None else args.dims      # N > 1: the per-GPU share of the weak-scaled job
+    # the same job as the other arm at this N (the weak-scaled volume); the reference cannot shard, so it runs
+    # the whole volume on one GPU
+    dims = WEAK_DIMS.get(args.gpus, 512) if args.dims is None else args.dims
     cores = os.cpu_count() or 1
     K = kfb.Intrinsics(**kfb.SENSORS["kinect1"])
     W, S = args.warmup, args.steps
@@ -139,7 +153,7 @@ def run_reference(args):
             gpu = torch.cuda.is_available()
         except Exception:
             gpu = False
-    workload = f"640x480 depth, {dims}^3 TSDF over 3 m, ICP 10/5/4, synthetic box+sphere room trajectory"
+    workload = workload_label(dims)
     if gpu:
         import torch
         S = min(S, 100)
@@ -164,7 +178,7 @@ def run_reference(args):
         Ko = kfo.intr()
         vd = kfo.volume_desc(dims)
         U = []
-        for i in (1 + W, n - 1):
+        for i in ((1 + W, n - 1) if dims <= 512 else (1 + W,)):
             vol = kfo.new_volume(vd)
             dm = kfo.frontend(frames[i][1], Ko, levels=1)[0][0]
             U.append(kfo.integrate(vol, vd, kfo.pose_mul(kfo.pose_inv(frames[i][0]), volpose), dm, Ko))
@@ -190,7 +204,11 @@ def run_reference(args):
         "config": {"workload": workload, "l2": "inputs larger than L2 (volume swept every frame)",
                    "updated_voxels_per_frame": U_mean},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": kind, "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        # the contract fixes the two byte counts of this arm at 0; what the reference loop really moves per frame
+        # is stated next to them
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "actual_h2d_bytes_per_step": (K.width * K.height * 4) if kind == "reference" else 0,
+                "actual_d2h_bytes_per_step": (19 * 27 * 4) if kind == "reference" else 0},
         "gpu_launches": 0, "wall_s": time.perf_counter() - t_start,
     }
     print(json.dumps(line))
@@ -233,7 +251,7 @@ def run_ours(args):
         from slam_kinectfusion_b200 import sharded
         try:
             return sharded.run_bench(args, dist, rank, world, local, dims, K, frames, host_pin, dev_frames,
-                                     METRIC, UNIT, measured_peak_hbm, ClockSampler)
+                                     METRIC, UNIT, measured_peak_hbm, ClockSampler, workload_label)
         finally:
             dist.barrier()
             dist.destroy_process_group()
@@ -349,8 +367,7 @@ def run_ours(args):
         "metric": METRIC, "value": U_mean / (ms_per_frame * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": S, "warmup": W,
         "ms_per_step": ms_per_frame, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 -> int16 tsdf", "data": "synthetic",
-        "config": {"workload": f"640x480 depth, {dims}^3 TSDF over 3 m, ICP 10/5/4, 300-frame looped synthetic "
-                               "box+sphere room trajectory (BASELINE configs[1])",
+        "config": {"workload": workload_label(dims),
                    "l2": f"inputs larger than L2: the {dims ** 3 * 4 >> 20} MiB volume is swept by integrate and raycast every frame",
                    "frames_timed": S, "updated_voxels_per_frame": U_mean, "swept_voxels_per_frame": swept},
         "frame_device_ms": ms_per_frame,
@@ -359,7 +376,7 @@ def run_ours(args):
                 "api": "kf::kinectfusion::pipeline(depth_mm) via libkfusion_b200.so, pinned host frames"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "integrate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                     "frac": achieved / peak, "traffic": ncu_traffic()[0], "traffic_source": ncu_traffic()[1], "peak_source": peak_src,
                      "kernel_ms": k_ms_mean, "kernel_ms_how": "CUDA events around the launch, in situ in the pipelined sequence",
                      "integrate_call_ms": float(np.mean(call_ms)), "raycast_kernel_ms": float(np.mean(rc_ms)), "icp_kernel_ms": float(np.mean(icp_ms)) if icp_ms else None,
                      "algorithmic_bytes": 8.0 * U_mean,
@@ -379,6 +396,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dims", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong-dims", type=int, default=2048,
+                    help="N > 1: also run this volume (BASELINE configs[3]/[4]) on the N GPUs and on one GPU; 0 = skip")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -40,7 +40,8 @@ enum
     KFB_ERR_INVALID = 1,     /* bad argument */
     KFB_ERR_CUDA = 2,        /* CUDA runtime error, see kfb_last_error_string */
     KFB_ERR_UNSUPPORTED = 3, /* e.g. dims[0] % 4 != 0 */
-    KFB_ERR_TRACKING = 4     /* reserved for host facades (icp_registration.cpp:35-37) */
+    KFB_ERR_TRACKING = 4,    /* reserved for host facades (icp_registration.cpp:35-37) */
+    KFB_ERR_TIMEOUT = 5      /* a host<->device handshake timed out (not a tracking failure; the map is intact) */
 };
 
 /* kf::Intrinsics, kfusion/include/types.hpp:13-29 (the unused depth scale `c` omitted). */
@@ -169,6 +170,9 @@ int kfb_ipc_export(kfb_ctx *ctx, int which, void *handle64);
 int kfb_shard_attach(kfb_ctx *ctx, int rank, int world, const void *handles);
 int kfb_shard_composite(kfb_ctx *ctx);
 int kfb_shard_attached(const kfb_ctx *ctx);
+/* Unmap the peers' buffers again (waits for this context's stream first).  Every rank must have detached before any
+ * rank destroys its context: freeing memory a peer still has mapped is undefined. */
+int kfb_shard_detach(kfb_ctx *ctx);
 
 /* ---- export ("next" rows) ------------------------------------------ */
 /* device::extract_points (device_types.hpp:128, tsdf_volume.cu:483-499) + the D2H of
@@ -198,7 +202,7 @@ void kfb_level_intrinsics(const kfb_intrinsics *in, int level, kfb_intrinsics *o
 int kfb_event_record(kfb_ctx *ctx, int slot);
 int kfb_event_elapsed_ms(kfb_ctx *ctx, int slot_a, int slot_b, float *ms);
 /* opt-in stage profiling: when on, launchers bracket their main kernel with events in reserved
- * slots (persistent ICP kernel: 54/55, integrate kernel: 60/61, whole kfb_integrate call: 56/57, raycast: 58/59) so a caller can read that
+ * slots (persistent ICP kernel: 54/55, shard composite kernel: 52/53, integrate kernel: 60/61, whole kfb_integrate call: 56/57, raycast: 58/59) so a caller can read that
  * kernel's own duration. */
 int kfb_set_profiling(kfb_ctx *ctx, int on);
 /* number of kernels this library has launched on this context since creation */
@@ -214,6 +218,9 @@ void *kfb_stream(kfb_ctx *ctx);
 void kfb_debug_icp_stamps(kfb_ctx *ctx, uint64_t out8[8]);
 /* debug: per iteration (row = iteration index % 32) {entry, final sums ready, validated + posted, grid released} */
 void kfb_debug_icp_ring(kfb_ctx *ctx, uint64_t out128[128]);
+/* number of ICP schedules (or rests of schedules) that ran as ordinary per-iteration launches because the persistent
+ * kernel could not be made co-resident or its host handshake timed out (results are bit-identical either way) */
+uint64_t kfb_icp_fallback_count(const kfb_ctx *ctx);
 
 #ifdef __cplusplus
 }

@@ -82,6 +82,7 @@ def load_library():
         "kfb_shard_attach": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
         "kfb_shard_composite": (C.c_int, [_vp]),
         "kfb_shard_attached": (C.c_int, [_vp]),
+        "kfb_shard_detach": (C.c_int, [_vp]),
         "kfb_reset_volume": (C.c_int, [_vp]),
         "kfb_reset_frames": (C.c_int, [_vp]),
         "kfb_upload_depth_mm": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
@@ -116,6 +117,7 @@ def load_library():
         "kfb_stream": (_vp, [_vp]),
         "kfb_debug_icp_stamps": (None, [_vp, _vp]),
         "kfb_debug_icp_ring": (None, [_vp, _vp]),
+        "kfb_icp_fallback_count": (C.c_uint64, [_vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -251,6 +253,9 @@ class Context:
         assert h.size == world * 256
         self._ck(self.lib.kfb_shard_attach(self.h, int(rank), int(world), _ptr(h)))
 
+    def shard_detach(self):
+        self._ck(self.lib.kfb_shard_detach(self.h))
+
     def shard_composite(self):
         self._ck(self.lib.kfb_shard_composite(self.h))
 
@@ -351,6 +356,9 @@ class Context:
         out = np.zeros((32, 4), np.uint64)
         self.lib.kfb_debug_icp_ring(self.h, _ptr(out))
         return out
+
+    def icp_fallback_count(self):
+        return int(self.lib.kfb_icp_fallback_count(self.h))
 
     def stream(self):
         return self.lib.kfb_stream(self.h)

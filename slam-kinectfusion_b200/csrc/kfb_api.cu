@@ -108,6 +108,8 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->fstream = nullptr; ctx->ev_front = nullptr; ctx->ev_free = nullptr; ctx->ev_tables_free = nullptr; ctx->front_pending = 0;
     ctx->icp_host = nullptr; ctx->icp_gate_host = nullptr; ctx->icp_devgate = nullptr; ctx->icp_mirror = nullptr;
     ctx->icp_smem_set = 0;
+    ctx->icp_fallbacks = 0; ctx->icp_direct_left = 0;
+    ctx->dev_err_host = ctx->dev_err_dev = nullptr;
     memset(ctx->L, 0, sizeof(ctx->L));
     memset(ctx->events, 0, sizeof(ctx->events));
     *out = ctx; // returned even on failure so the caller can read the error string, then destroy
@@ -194,6 +196,9 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     memset((void *)ctx->icp_gate_host, 0, sizeof(IcpHostGate));
     KFB_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->icp_gate_dev, (void *)ctx->icp_gate_host, 0));
     memset(&ctx->icp_sched, 0, sizeof(ctx->icp_sched));
+    KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->dev_err_host, 64, cudaHostAllocMapped));
+    memset((void *)ctx->dev_err_host, 0, 64);
+    KFB_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->dev_err_dev, (void *)ctx->dev_err_host, 0));
     KFB_CUDA(ctx, cudaMalloc(&ctx->icp_devgate, sizeof(IcpDevGate)));
     KFB_CUDA(ctx, cudaMemset(ctx->icp_devgate, 0, sizeof(IcpDevGate)));
     KFB_CUDA(ctx, cudaMalloc(&ctx->icp_mirror, 8192));
@@ -217,6 +222,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     return KFB_OK;
 }
 
+static void shard_close_peers(kfb_ctx *ctx);
 void kfb_destroy(kfb_ctx *ctx)
 {
     if (!ctx) return;
@@ -247,19 +253,13 @@ void kfb_destroy(kfb_ctx *ctx)
     if (ctx->bdirty) cudaFree(ctx->bdirty);
     if (ctx->tab_exact) cudaFree(ctx->tab_exact);
     if (ctx->hit_t) cudaFree(ctx->hit_t);
-    for (int r = 0; r < ctx->shard_world && r < 16; ++r)
-        if (r != ctx->shard_rank)
-        {
-            if (ctx->peer_keys[r]) cudaIpcCloseMemHandle(ctx->peer_keys[r]);
-            if (ctx->peer_maps[0][r]) cudaIpcCloseMemHandle(ctx->peer_maps[0][r]);
-            if (ctx->peer_maps[1][r]) cudaIpcCloseMemHandle(ctx->peer_maps[1][r]);
-            if (ctx->peer_flag[r]) cudaIpcCloseMemHandle(ctx->peer_flag[r]);
-        }
+    shard_close_peers(ctx);
     if (ctx->shard_flag) cudaFree(ctx->shard_flag);
     if (ctx->icp_partials) cudaFree(ctx->icp_partials);
     if (ctx->icp_ticket) cudaFree(ctx->icp_ticket);
     if (ctx->icp_host) cudaFreeHost((void *)ctx->icp_host);
     if (ctx->icp_gate_host) cudaFreeHost((void *)ctx->icp_gate_host);
+    if (ctx->dev_err_host) cudaFreeHost((void *)ctx->dev_err_host);
     if (ctx->icp_devgate) cudaFree(ctx->icp_devgate);
     if (ctx->icp_mirror) cudaFree(ctx->icp_mirror);
     if (ctx->counters) cudaFree(ctx->counters);
@@ -284,7 +284,7 @@ int kfb_synchronize(kfb_ctx *ctx)
     KFB_JOIN(ctx);
     KFB_CUDA(ctx, cudaStreamSynchronize(ctx->fstream));
     KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return KFB_OK;
+    return check_device_error(ctx);
 }
 
 int kfb_set_stream(kfb_ctx *ctx, void *stream)
@@ -469,6 +469,26 @@ int kfb_shard_attach(kfb_ctx *ctx, int rank, int world, const void *handles)
     return KFB_OK;
 }
 int kfb_shard_attached(const kfb_ctx *ctx) { return ctx->shard_world > 0; }
+static void shard_close_peers(kfb_ctx *ctx)
+{
+    for (int r = 0; r < ctx->shard_world && r < 16; ++r)
+        if (r != ctx->shard_rank)
+        {
+            if (ctx->peer_keys[r]) cudaIpcCloseMemHandle(ctx->peer_keys[r]);
+            if (ctx->peer_maps[0][r]) cudaIpcCloseMemHandle(ctx->peer_maps[0][r]);
+            if (ctx->peer_maps[1][r]) cudaIpcCloseMemHandle(ctx->peer_maps[1][r]);
+            if (ctx->peer_flag[r]) cudaIpcCloseMemHandle(ctx->peer_flag[r]);
+        }
+    memset(ctx->peer_keys, 0, sizeof(ctx->peer_keys)); memset(ctx->peer_maps, 0, sizeof(ctx->peer_maps)); memset(ctx->peer_flag, 0, sizeof(ctx->peer_flag));
+    ctx->shard_world = 0;
+}
+int kfb_shard_detach(kfb_ctx *ctx)
+{
+    KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    shard_close_peers(ctx);
+    cudaGetLastError();
+    return KFB_OK;
+}
 int kfb_shard_composite(kfb_ctx *ctx)
 {
     if (!ctx->shard_world) { ctx->err = "kfb_shard_composite without kfb_shard_attach"; return KFB_ERR_INVALID; }
@@ -637,5 +657,6 @@ void kfb_debug_icp_ring(kfb_ctx *ctx, uint64_t out128[128])
 {
     for (int i = 0; i < 128; ++i) out128[i] = ctx->icp_host->post_ns[i / 4][i % 4];
 }
+uint64_t kfb_icp_fallback_count(const kfb_ctx *ctx) { return ctx ? ctx->icp_fallbacks : 0; }
 
 } // extern "C"

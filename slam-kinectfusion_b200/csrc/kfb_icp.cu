@@ -18,6 +18,7 @@
 #include "kfb_common.cuh"
 #include <xmmintrin.h>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 namespace kfb
@@ -296,7 +297,8 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpArgs a)
 // memory; at the end of a speculative iteration the pose it used is compared, bit for bit, with the host's:
 // equal => its sums are posted, different => the iteration is repeated with the host's pose.  The host's solve
 // stays authoritative and every result equals the non-speculative schedule's (KFB_ICP_NOSPEC=1 runs that).
-// Polls are bounded (KFB_ICP_GATE_TIMEOUT_NS); on timeout or abort every CTA leaves.
+// Polls are bounded (KFB_ICP_GATE_TIMEOUT_NS, KFB_ICP_TIMEOUT_NS=<ns> overrides); on timeout or abort every CTA leaves and
+// the host finishes the schedule with ordinary launches (icp_step).
 #define ICP_MIRROR_RING 64
 struct IcpMirror // device memory, written by the service warp
 {
@@ -318,6 +320,7 @@ struct IcpPersistArgs
     unsigned long long seq0;   // iteration k carries sequence number seq0 + k + 1
     unsigned long long round0; // release counter base (monotonic across schedules)
     int speculate;
+    unsigned long long timeout_ns; // bound of every poll (x1 host pose, x2 mirrored pose, x3 device gate)
     float pose0[12];
 };
 
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
                 if (ab >= want) break;
                 if (__float_as_uint(c0.w) == tag && __float_as_uint(c1.w) == tag && __float_as_uint(c2.w) == tag &&
                     __float_as_uint(c3.w) == tag) { ok = true; break; }
-                if (globaltimer_ns() - t0 > KFB_ICP_GATE_TIMEOUT_NS) break;
+                if (globaltimer_ns() - t0 > P.timeout_ns) break;
             }
             if (!ok)
             {
@@ -529,7 +532,7 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
                     {
                         v = ld_volatile_u64(&P.mirror->tag[slot]);
                         if ((v & ~(1ull << 63)) == seq) break;
-                        if (globaltimer_ns() - t0 > 2ull * KFB_ICP_GATE_TIMEOUT_NS) { v = 1ull << 63; break; }
+                        if (globaltimer_ns() - t0 > 2ull * P.timeout_ns) { v = 1ull << 63; break; }
                     }
                     if (v >> 63) cmd = ICP_CMD_LEAVE;
                     else
@@ -580,7 +583,7 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
                             {
                                 v = ld_volatile_u64(&P.mirror->tag[slot]);
                                 if ((v & ~(1ull << 63)) == want) break;
-                                if (globaltimer_ns() - t0 > 2ull * KFB_ICP_GATE_TIMEOUT_NS) { v = 1ull << 63; break; }
+                                if (globaltimer_ns() - t0 > 2ull * P.timeout_ns) { v = 1ull << 63; break; }
                             }
                             if (v >> 63) cmd = ICP_CMD_LEAVE;
                             else
@@ -637,7 +640,7 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
                     if (__float_as_uint(c0.w) == t && __float_as_uint(c1.w) == t && __float_as_uint(c2.w) == t) break;
                 }
                 else if ((int)blockIdx.x >= nact) __nanosleep(200);
-                if (globaltimer_ns() - t0 > 3ull * KFB_ICP_GATE_TIMEOUT_NS) { cmd = ICP_CMD_LEAVE; break; }
+                if (globaltimer_ns() - t0 > 3ull * P.timeout_ns) { cmd = ICP_CMD_LEAVE; break; }
             }
             if (cmd == ICP_CMD_RUN)
             {
@@ -682,6 +685,7 @@ static int icp_setup(kfb_ctx *ctx, int level, IcpArgs &a, int &blocks)
     return KFB_OK;
 }
 
+#define ICP_RC_NO_RESULT (-7) // internal: the stream went idle without the awaited result (never returned through the C-ABI)
 // spin on the tagged result chunks in mapped host memory (with a stream query as the failure detector)
 static int icp_wait(kfb_ctx *ctx, unsigned long long seq, double out27[27])
 {
@@ -703,14 +707,15 @@ static int icp_wait(kfb_ctx *ctx, unsigned long long seq, double out27[27])
                 for (int i = 0; i < 27; ++i) ready += (h->chunk[i].tag == seq);
                 if (ready == 27) break;
                 ctx->err = "icp result never arrived (gate timeout or abort)";
-                return KFB_ERR_CUDA;
+                return ICP_RC_NO_RESULT;
             }
         }
     }
     __sync_synchronize();
     // a chunk is written by one aligned 16-byte store, so value and tag arrive together
     for (int i = 0; i < 27; ++i) out27[i] = h->chunk[i].value;
-    return KFB_OK;
+    // everything enqueued before this ICP has run: a composite that gave up on a peer has said so by now
+    return check_device_error(ctx);
 }
 
 int launch_icp(kfb_ctx *ctx, int level, const float pose12[12], double out27[27])
@@ -726,9 +731,12 @@ int launch_icp(kfb_ctx *ctx, int level, const float pose12[12], double out27[27]
         for (int i = 0; i < 27; ++i) out27[i] = 0.0;
         return KFB_OK;
     }
+    // a kernel that was torn down mid-reduction (timeout, abort) may have left the ticket non-zero
+    KFB_CUDA(ctx, cudaMemsetAsync(ctx->icp_ticket, 0, sizeof(unsigned int), ctx->stream));
     icp_kernel<<<blocks, ICP_THREADS, 0, ctx->stream>>>(a);
     KFB_LAUNCH_CHECK(ctx);
-    return icp_wait(ctx, a.seq, out27);
+    const int rcw = icp_wait(ctx, a.seq, out27);
+    return rcw == ICP_RC_NO_RESULT ? KFB_ERR_CUDA : rcw; // an ordinary kernel that posts nothing is a device fault
 }
 
 // ---- persistent schedule -------------------------------------------------------------------------------
@@ -743,8 +751,14 @@ int icp_begin(kfb_ctx *ctx, const int *iters_per_level)
         if (S.iters[l] < 0) S.iters[l] = 0;
         S.total += S.iters[l];
     }
+    // the release tag of the persistent kernel carries the iteration in 8 bits (IcpDevGate)
+    if (S.total > 255) { ctx->err = "icp schedule longer than 255 iterations"; return KFB_ERR_INVALID; }
     S.seq0 = ctx->icp_seq;
     S.enq = S.done = 0;
+    S.direct = getenv("KFB_ICP_DIRECT") ? 1 : 0;
+    // after a transport timeout (typically a profiler or debugger that serialises launches: the host cannot
+    // answer a kernel whose launch call has not returned) the next schedules stay on ordinary launches
+    if (ctx->icp_direct_left > 0) { --ctx->icp_direct_left; S.direct = 1; }
     S.active = 1;
     return KFB_OK;
 }
@@ -780,6 +794,8 @@ static int icp_launch_persistent(kfb_ctx *ctx, const float pose12[12])
     P.round0 = ctx->icp_round;
     ctx->icp_round += (unsigned long long)(4 * S.total + 8); // rounds this launch can consume (repeats included)
     P.speculate = getenv("KFB_ICP_NOSPEC") ? 0 : 1;
+    P.timeout_ns = KFB_ICP_GATE_TIMEOUT_NS;
+    if (const char *e = getenv("KFB_ICP_TIMEOUT_NS")) { const long long v = atoll(e); if (v > 0) P.timeout_ns = (unsigned long long)v; }
     memcpy(P.pose0, pose12, sizeof(P.pose0));
     // every CTA must be resident at once (they wait on each other): one per SM (see icp_setup)
     const int blocks = ctx->sm_count;
@@ -791,8 +807,41 @@ static int icp_launch_persistent(kfb_ctx *ctx, const float pose12[12])
         KFB_CUDA(ctx, cudaFuncSetAttribute(icp_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cache_bytes));
         ctx->icp_smem_set = 1;
     }
-    icp_persistent_kernel<<<blocks, ICP_THREADS + 32, cache_bytes, ctx->stream>>>(P);
-    KFB_LAUNCH_CHECK(ctx);
+    KFB_CUDA(ctx, cudaMemsetAsync(ctx->icp_ticket, 0, sizeof(unsigned int), ctx->stream));
+    // The CTAs wait on each other through the device gate, so the whole grid has to be co-resident.  A
+    // cooperative launch makes the driver check exactly that (SM limits under MPS / MIG included) and refuse
+    // the launch otherwise; the caller then runs the schedule with one ordinary launch per iteration, which
+    // gives the same sums bit for bit.  KFB_ICP_PLAIN_LAUNCH=1: ordinary launch behind an occupancy query.
+    cudaError_t le;
+    if (getenv("KFB_ICP_PLAIN_LAUNCH"))
+    {
+        int per_sm = 0;
+        le = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_persistent_kernel, ICP_THREADS + 32, cache_bytes);
+        if (le == cudaSuccess && per_sm * ctx->sm_count < blocks) le = cudaErrorCooperativeLaunchTooLarge;
+        if (le == cudaSuccess)
+        {
+            icp_persistent_kernel<<<blocks, ICP_THREADS + 32, cache_bytes, ctx->stream>>>(P);
+            le = cudaGetLastError();
+        }
+    }
+    else
+    {
+        void *kargs[] = {(void *)&P};
+        le = cudaLaunchCooperativeKernel((const void *)icp_persistent_kernel, dim3(blocks), dim3(ICP_THREADS + 32), kargs, cache_bytes, ctx->stream);
+    }
+    if (le != cudaSuccess)
+    {
+        (void)cudaGetLastError(); // launch-configuration errors are not sticky
+        if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources || le == cudaErrorNotSupported ||
+            le == cudaErrorInvalidConfiguration)
+        {
+            S.direct = 1;
+            ctx->icp_fallbacks++;
+            return KFB_OK;
+        }
+        KFB_CUDA(ctx, le);
+    }
+    ctx->launches++;
     if (ctx->profiling) cudaEventRecord(ctx->events[55], ctx->stream);
     S.enq = S.total;
     return KFB_OK;
@@ -804,23 +853,12 @@ int icp_step(kfb_ctx *ctx, const float pose12[12], double out27[27])
     if (!S.active || S.done >= S.total) { ctx->err = "icp_step outside an active schedule"; return KFB_ERR_INVALID; }
     const unsigned long long seq = S.seq0 + (unsigned long long)S.done + 1ull;
     int rc;
-    if (getenv("KFB_ICP_DIRECT"))
+    if (S.done == 0 && !S.direct)
     {
-        // profiling aid: one ordinary launch per iteration (kernel replay by a profiler breaks the host/device
-        // handshake of the persistent kernel).  Same sums, bit for bit (see icp_setup).
-        int k = S.done, level = ctx->levels - 1;
-        while (level >= 0 && k >= S.iters[level]) { k -= S.iters[level]; --level; }
-        rc = launch_icp(ctx, level, pose12, out27);
-        if (rc) return rc;
-        ++S.done;
-        return KFB_OK;
-    }
-    if (S.done == 0)
-    {
-        rc = icp_launch_persistent(ctx, pose12); // first pose by parameter
+        rc = icp_launch_persistent(ctx, pose12); // first pose by parameter; may switch the schedule to direct launches
         if (rc) return rc;
     }
-    else
+    else if (!S.direct)
     {
         // publish this iteration's pose: four tagged 16-byte chunks (x86 TSO keeps each store whole);
         // the last CTA of the previous iteration is polling for it
@@ -838,11 +876,37 @@ int icp_step(kfb_ctx *ctx, const float pose12[12], double out27[27])
         _mm_store_ps((float *)g->chunk + 12, k3);
         _mm_sfence();
     }
-    rc = icp_wait(ctx, seq, out27);
-    if (rc) return rc;
-    ++S.done;
-    ctx->icp_seq = seq;
-    return KFB_OK;
+    if (!S.direct)
+    {
+        rc = icp_wait(ctx, seq, out27);
+        if (rc == KFB_OK)
+        {
+            ++S.done;
+            ctx->icp_seq = seq;
+            return KFB_OK;
+        }
+        if (rc != ICP_RC_NO_RESULT) return rc;
+        // Transport failure: the persistent kernel gave up waiting (a descheduled host thread, a debugger, a
+        // profiler replaying kernels) and has left the device -- icp_wait saw the stream idle.  That is not a
+        // tracking failure: the remaining iterations of this frame run as ordinary launches.
+        S.direct = 1;
+        S.enq = 0;
+        ctx->icp_fallbacks++;
+        ctx->icp_direct_left = 64;
+        const unsigned long long last = S.seq0 + (unsigned long long)S.total;
+        if (last > ctx->icp_seq) ctx->icp_seq = last; // no tag the dead kernel may have posted can be mistaken for a new one
+        ctx->err.clear();
+    }
+    {
+        // one ordinary launch per iteration: the fallback above, and KFB_ICP_DIRECT=1 for profilers that replay
+        // kernels.  Same sums, bit for bit (see icp_setup).
+        int k = S.done, level = ctx->levels - 1;
+        while (level >= 0 && k >= S.iters[level]) { k -= S.iters[level]; --level; }
+        rc = launch_icp(ctx, level, pose12, out27);
+        if (rc) return rc;
+        ++S.done;
+        return KFB_OK;
+    }
 }
 
 int icp_end(kfb_ctx *ctx)

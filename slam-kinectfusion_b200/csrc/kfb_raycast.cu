@@ -416,6 +416,7 @@ struct ShardArgs
     float4 *out;                             // rank 0's own model maps
     int world, self, npix;
     unsigned long long seq;
+    unsigned long long *err;                 // mapped host word: set to the frame's sequence number when a peer never signalled
 };
 __global__ void shard_signal_kernel(unsigned long long *flag, unsigned long long seq)
 {
@@ -433,7 +434,13 @@ __global__ void __launch_bounds__(256) shard_composite_kernel(const ShardArgs a)
         {
             unsigned long long t;
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-            if (t - t0 > 2000000000ull) break; // 2 s: a peer died; leave rather than hang the GPU
+            if (t - t0 > 2000000000ull)
+            {
+                // 2 s: a peer died or stalled.  Leave rather than hang the GPU, and say so: the host finds the
+                // word before it uses the composited maps (check_device_error) and fails the frame
+                *(volatile unsigned long long *)a.err = a.seq;
+                break;
+            }
         }
         __threadfence_system();
     }
@@ -458,9 +465,21 @@ __global__ void __launch_bounds__(256) shard_composite_kernel(const ShardArgs a)
     }
 }
 
+int check_device_error(kfb_ctx *ctx)
+{
+    if (ctx->dev_err_host && *(volatile unsigned long long *)ctx->dev_err_host != 0ull)
+    {
+        ctx->err = "shard composite: a peer's slab never arrived (frame " + std::to_string(*(volatile unsigned long long *)ctx->dev_err_host) +
+                   "); the model maps of that frame are incomplete";
+        return KFB_ERR_TIMEOUT;
+    }
+    return KFB_OK;
+}
+
 int launch_shard_composite(kfb_ctx *ctx)
 {
     const Intr &k = ctx->L[0].k;
+    if (const int rce = check_device_error(ctx)) return rce;
     const unsigned long long seq = ++ctx->shard_seq;
     shard_signal_kernel<<<1, 1, 0, ctx->stream>>>(ctx->shard_flag, seq);
     KFB_LAUNCH_CHECK(ctx);
@@ -475,8 +494,11 @@ int launch_shard_composite(kfb_ctx *ctx)
     }
     a.out = ctx->L[0].v[ctx->prev];
     a.world = ctx->shard_world; a.self = ctx->shard_rank; a.npix = k.w * k.h; a.seq = seq;
-    shard_composite_kernel<<<148 * 2, 256, 0, ctx->stream>>>(a);
+    a.err = ctx->dev_err_dev;
+    if (ctx->profiling) cudaEventRecord(ctx->events[52], ctx->stream); // composite (its wait for the slowest slab included): 52 .. 53
+    shard_composite_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a);
     KFB_LAUNCH_CHECK(ctx);
+    if (ctx->profiling) cudaEventRecord(ctx->events[53], ctx->stream);
     ctx->pyramid_fresh = 0;
     return KFB_OK;
 }

@@ -80,7 +80,9 @@ bool kf::ICPRegistration::rigidTransform(cv::Affine3f &camera_pose, const cv::Af
     // host solve and the next accumulation.
     int sched[KFB_MAX_LEVELS] = {0};
     for (size_t l = 0; l < schedule_.size() && l < KFB_MAX_LEVELS; ++l) sched[l] = schedule_[l];
-    if (kfbSafeCall(ctx, kfb_icp_begin(ctx, sched)) != KFB_OK) return false;
+    // false is reserved for the reference's meaning (singular system => tracking failure => the caller resets the
+    // map); a device or transport error is raised as kf::DeviceError instead and leaves the map alone
+    kfbCheck(ctx, kfb_icp_begin(ctx, sched));
     bool ok = true;
     for (int level = (int)schedule_.size() - 1; level >= 0 && ok; level--)
     {
@@ -89,7 +91,12 @@ bool kf::ICPRegistration::rigidTransform(cv::Affine3f &camera_pose, const cv::Af
             float pose12[12];
             double sums[27], x[6];
             camera_pose.to12(pose12);
-            if (kfbSafeCall(ctx, kfb_icp_step(ctx, pose12, sums)) != KFB_OK) { ok = false; break; }
+            const int rc = kfb_icp_step(ctx, pose12, sums);
+            if (rc != KFB_OK)
+            {
+                kfb_icp_end(ctx);
+                kfbCheck(ctx, rc);
+            }
             if (!solve(sums, x)) { ok = false; break; }
             // Tinc = Affine3f(rvec = x[0..2] (float), t = x[3..5]); pose = pose * Tinc (right-multiply, :41-42)
             cv::Affine3f Tinc(cv::Vec3f((float)x[0], (float)x[1], (float)x[2]), cv::Vec3f((float)x[3], (float)x[4], (float)x[5]));

@@ -10,6 +10,8 @@
 
 kf::kinectfusion::kinectfusion(const kf::Intrinsics intr, const kf::kinectfuison_params params) : vdata(nullptr), intr_(intr), params_(params)
 {
+    if ((int)params_.icp_iter_count.size() != params_.pyramid_height)
+        throw std::invalid_argument("kf::kinectfusion: icp_iter_count needs one entry per pyramid level");
     kfb_params p;
     kfb_default_params(&p, params_.volu_dims(0));
     p.pyramid_height = params_.pyramid_height;
@@ -35,7 +37,7 @@ kf::kinectfusion::kinectfusion(const kf::Intrinsics intr, const kf::kinectfuison
         const std::string why = dev->ctx ? kfb_last_error_string(dev->ctx) : "invalid parameters";
         throw std::runtime_error("kf::kinectfusion: kfb_create failed: " + why);
     }
-    // 初始化视频帧 -> handles onto the context's current / model frames
+    //  -> handles onto the context's current / model frames
     cframe = Frame(dev, KFB_FRAME_CUR, params_.pyramid_height, intr_);
     pframe = Frame(dev, KFB_FRAME_PREV, params_.pyramid_height, intr_);
     frame_count = 1;
@@ -66,8 +68,8 @@ cv::Mat kf::kinectfusion::getRenderMap(DISPLAY_TYPES V)
 
 void kf::kinectfusion::imageProcess(const float *depth_mm, int width, int height)
 {
-    kfbSafeCall(dev->ctx, kfb_upload_depth_mm(dev->ctx, depth_mm, width, height));
-    kfbSafeCall(dev->ctx, kfb_frontend(dev->ctx));
+    kfbCheck(dev->ctx, kfb_upload_depth_mm(dev->ctx, depth_mm, width, height));
+    kfbCheck(dev->ctx, kfb_frontend(dev->ctx));
 }
 
 void kf::kinectfusion::pipeline(cv::Mat /*cmap_*/, cv::Mat dmap_)
@@ -83,7 +85,7 @@ void kf::kinectfusion::pipeline(const float *depth_mm, int width, int height)
     if (frame_count == 1)
     {
         vdata->integrate(pose_record.back());
-        kfbSafeCall(dev->ctx, kfb_swap_frames(dev->ctx)); // cframe->vmap.swap(pframe->vmap); nmap likewise (:88-89)
+        kfbCheck(dev->ctx, kfb_swap_frames(dev->ctx)); // cframe->vmap.swap(pframe->vmap); nmap likewise (:88-89)
         frame_count++;
         return;
     }
@@ -116,10 +118,10 @@ void kf::kinectfusion::pipeline(const float *depth_mm, int width, int height)
     {
         // first-hit composite over the slabs: one kernel over NVLink peer memory when the launcher attached the
         // peers (kfb_shard_attach), else the launcher's collectives
-        if (kfb_shard_attached(dev->ctx)) kfbSafeCall(dev->ctx, kfb_shard_composite(dev->ctx));
+        if (kfb_shard_attached(dev->ctx)) kfbCheck(dev->ctx, kfb_shard_composite(dev->ctx));
         else if (comm.composite(comm.user) != 0) throw std::runtime_error("kf::kinectfusion: raycast composite failed");
     }
-    if (params_.shard_rank == 0) kfbSafeCall(dev->ctx, kfb_model_pyramid(dev->ctx));
+    if (params_.shard_rank == 0) kfbCheck(dev->ctx, kfb_model_pyramid(dev->ctx));
     std::chrono::duration<double, std::milli> ms = std::chrono::steady_clock::now() - start_time;
     frame_time = std::to_string(ms.count());
     frame_count++;

@@ -71,7 +71,7 @@ void TSDFVolume::integrate(const cv::Affine3f &camera_pose)
     const cv::Affine3f vol2cam = camera_pose.inv() * pose_; // :50
     float p[12];
     vol2cam.to12(p);
-    kfbSafeCall(dev_->ctx, kfb_integrate(dev_->ctx, p, nullptr));
+    kfbCheck(dev_->ctx, kfb_integrate(dev_->ctx, p, nullptr));
 }
 void TSDFVolume::raycast(const cv::Affine3f &camera_pose)
 {
@@ -81,7 +81,7 @@ void TSDFVolume::raycast(const cv::Affine3f &camera_pose)
     const cv::Matx33f Rinv = rot_only.inv().rotation();
     float p[12];
     cam2vol.to12(p);
-    kfbSafeCall(dev_->ctx, kfb_raycast(dev_->ctx, p, Rinv.val));
+    kfbCheck(dev_->ctx, kfb_raycast(dev_->ctx, p, Rinv.val));
 }
 cv::Mat TSDFVolume::fetchPointCloud()
 {

@@ -189,7 +189,9 @@ class ShardedKinectFusion:
         # all device work of the context and the collectives are ordered on torch's current stream
         self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self.P = K.width * K.height
-        self.mailbox = PoseMailbox(dist, rank, os.environ.get("MASTER_PORT", "0")) if os.environ.get("KFB_POSE_NCCL") is None else None
+        tag = os.environ.get("KFB_MAILBOX_TAG", os.environ.get("MASTER_PORT", "0"))
+        self.mailbox = PoseMailbox(dist, rank, tag) if os.environ.get("KFB_POSE_NCCL") is None else None
+        self.mailbox_us = []
         self.min_keys = torch.empty(self.P, dtype=torch.float32, device=self.device)
         self._view_cache = {}
         self.kf.set_shard_comm(self._bcast, self._composite)
@@ -212,11 +214,13 @@ class ShardedKinectFusion:
 
     def _bcast(self, p):
         try:
+            t0 = time.perf_counter()
             msg = np.ctypeslib.as_array(p, shape=(13,))
             if self.mailbox is not None:
                 self.mailbox.exchange(msg)
             else:
                 msg[:] = broadcast_pose(self.dist, msg, self.device)
+            self.mailbox_us.append((time.perf_counter() - t0) * 1e6)
             return 0
         except Exception as e:  # noqa: BLE001 - reported through the C return code
             print("broadcast_pose failed:", e, flush=True)
@@ -235,22 +239,29 @@ class ShardedKinectFusion:
         return self.kf.pipeline_ptr(ptr, w, h)
 
     def close(self):
+        if self.p2p:
+            # every rank unmaps its peers' buffers before anybody frees them
+            self.ctx.shard_detach()
+            self.p2p = False
+        self.dist.barrier()
         if self.mailbox is not None:
-            self.dist.barrier()
             self.mailbox.close()
             self.mailbox = None
 
 
-def run_bench(args, dist, rank, world, local, dims, K, frames, host_pin, dev_frames, METRIC, UNIT, measured_peak_hbm,
-              ClockSampler):
-    """bench.py's N > 1 leg: every rank runs the sharded pipeline on the same frames; value = updated voxels
-    per frame summed over the ranks' OWNED planes / device time per frame (max over ranks)."""
+def _measure_config(args, dist, rank, world, local, dims, K, frames, host_pin, dev_frames, ClockSampler, with_e2e, tag):
+    """One sharded configuration (a `dims`^3 volume cut into `world` z-slabs) on the given frames: device-timed
+    frame loop (max over ranks), optionally the same from pinned host frames, the per-stage kernel durations in
+    situ (slowest rank), updated-voxel counts, and -- on rank 0, after the slab contexts are gone -- the SAME
+    frames through the single-GPU pipeline at the same dims: its poses must equal the sharded run's bit for bit
+    (N-GPU == 1-GPU), and its frame time is the N = 1 point of the strong-scaling curve."""
     import torch
     from . import host
     W, S = args.warmup, args.steps
     n_frames = len(frames)
     w, h = K.width, K.height
     hp = host.default_host_params(dims)
+    os.environ["KFB_MAILBOX_TAG"] = tag
     skf = ShardedKinectFusion(K, hp, dist, rank, world, local, first_depth=frames[0][1])
     ctx = skf.ctx
     dev = torch.device("cuda", local)
@@ -286,12 +297,35 @@ def run_bench(args, dist, rank, world, local, dims, K, frames, host_pin, dev_fra
         sampler.start()
     dev_ms, _, launches = run(dptr)
     clocks = sampler.stop() if rank == 0 else None
-    e2e_ms, e2e_wall, _ = run(hptr)
-    e2e_ms = max(e2e_ms, e2e_wall)
+    e2e_ms = None
+    if with_e2e:
+        e2e_ms, e2e_wall, _ = run(hptr)
+        e2e_ms = max(e2e_ms, e2e_wall)
     poses = skf.kf.poses()
 
-    # outside the timed region: updated voxels of this rank's stored planes, and the integrate kernel's duration
+    # ---- per-stage durations in situ: the same pipelined sequence with the library's profiling events on; every
+    # 4th frame all ranks synchronise and read that frame's events (integrate kernel 60/61, whole integrate call
+    # 56/57, slab raycast 58/59; rank 0: persistent ICP kernel 54/55, composite kernel 52/53)
     ctx.set_profiling(True)
+    skf.kf.reset()
+    skf.mailbox_us = []
+    st = {k: [] for k in ("integrate_kernel", "integrate_call", "raycast", "icp", "composite")}
+    for i, p in enumerate(dptr):
+        if skf.pipeline_ptr(p, w, h) != 0:
+            raise SystemExit(f"rank {rank}: tracking failure at frame {i} (profiled pass)")
+        if i > W and i % 4 == 0:
+            ctx.synchronize()
+            st["integrate_kernel"].append(ctx.event_elapsed_ms(60, 61))
+            st["integrate_call"].append(ctx.event_elapsed_ms(56, 57))
+            st["raycast"].append(ctx.event_elapsed_ms(58, 59))
+            if rank == 0:
+                for name, (a, b) in (("icp", (54, 55)), ("composite", (52, 53))):
+                    try:
+                        st[name].append(ctx.event_elapsed_ms(a, b))
+                    except Exception:  # noqa: BLE001 - events never recorded (KFB_ICP_DIRECT, NCCL composite)
+                        pass
+    mailbox_us = float(np.mean(skf.mailbox_us[1 + W:])) if len(skf.mailbox_us) > 1 + W else 0.0
+    # ---- updated voxels of this rank's stored planes (counting variant) at the tracked poses
     volpose = np.array(hp.volu_pose, np.float32).reshape(3, 4)
 
     def vol2cam(p12):
@@ -299,50 +333,128 @@ def run_bench(args, dist, rank, world, local, dims, K, frames, host_pin, dev_fra
         V = np.vstack([volpose.astype(np.float64), [0, 0, 0, 1]])
         return (np.linalg.inv(Pm) @ V)[:3].astype(np.float32).reshape(12)
 
-    U, k_ms = [], []
+    U = []
     for i in range(1 + W, n_frames, max(1, S // 8)):
         ctx.upload_depth_mm_ptr(dptr[i], w, h)
         ctx.frontend()
-        v2c = vol2cam(poses[i])
-        U.append(ctx.integrate(v2c, count=True))
-        for _ in range(2):
-            ctx.integrate(v2c)
-            k_ms.append(ctx.event_elapsed_ms(60, 61))
+        U.append(ctx.integrate(vol2cam(poses[i]), count=True))
     ctx.set_profiling(False)
     zs0, zs1 = stored_range(dims, world, rank, skf.bounds)
     zb, ze = (skf.bounds[rank], skf.bounds[rank + 1]) if skf.bounds is not None else slab_range(dims, world, rank)
     own_frac = (ze - max(zb, 1)) / max(zs1 - max(zs0, 1), 1)   # halo planes are integrated redundantly: not counted
-    stat = torch.tensor([float(np.mean(U)) * own_frac, float(np.mean(U)), float(np.mean(k_ms))], device=dev, dtype=torch.float64)
+    mean = lambda v: float(np.mean(v)) if len(v) else 0.0  # noqa: E731
+    stat = torch.tensor([mean(U) * own_frac, mean(U), mean(st["integrate_kernel"]), mean(st["integrate_call"]), mean(st["raycast"])],
+                        device=dev, dtype=torch.float64)
     gathered = [torch.zeros_like(stat) for _ in range(world)]
     dist.all_gather(gathered, stat)
+    bounds = skf.bounds if skf.bounds is not None else [slab_range(dims, world, r)[0] for r in range(world)] + [dims]
+    p2p = skf.p2p
     skf.close()
+    skf.kf.close()
+    del skf
+    torch.cuda.synchronize(dev)
+    # ---- rank 0: the same frames on ONE GPU at the same dims (parity + the N = 1 point of the strong curve)
+    single = None
+    if rank == 0:
+        hp1 = host.default_host_params(dims)
+        hp1.device = local
+        kf1 = host.KinectFusion(K, hp1)
+        c1 = kf1.context()
+        c1.set_profiling(True)
+        k1 = []
+        for i, p in enumerate(dptr):
+            if i == 1 + W:
+                c1.synchronize()
+                c1.event_record(0)
+            if kf1.pipeline_ptr(p, w, h) != 0:
+                raise SystemExit(f"single-GPU check run lost tracking at frame {i}")
+        c1.event_record(1)
+        c1.synchronize()
+        k1.append(c1.event_elapsed_ms(60, 61))
+        poses1 = kf1.poses()
+        single = {"ms_per_step": c1.event_elapsed_ms(0, 1) / S, "integrate_kernel_ms_last_frame": k1[-1],
+                  "poses_equal": bool(len(poses1) == len(poses) and np.array_equal(np.asarray(poses1), np.asarray(poses)))}
+        kf1.close()
+    dist.barrier()
+    return {
+        "dims": dims, "ms_per_step": dev_ms / S, "e2e_ms_per_step": (e2e_ms / S) if e2e_ms is not None else None,
+        "launches": launches, "clocks": clocks, "poses": poses, "bounds": bounds, "p2p": p2p,
+        "U_owned": sum(float(g[0]) for g in gathered), "U_stored": sum(float(g[1]) for g in gathered),
+        "stage_ms": {"integrate_kernel_slowest_rank": max(float(g[2]) for g in gathered),
+                     "integrate_call_slowest_rank": max(float(g[3]) for g in gathered),
+                     "raycast_slowest_rank": max(float(g[4]) for g in gathered),
+                     "integrate_kernel_per_rank": [float(g[2]) for g in gathered],
+                     "raycast_per_rank": [float(g[4]) for g in gathered],
+                     "icp_kernel_rank0": mean(st["icp"]), "composite_kernel_rank0": mean(st["composite"]),
+                     "pose_mailbox_host_us_rank0": mailbox_us},
+        "single": single,
+    }
+
+
+def run_bench(args, dist, rank, world, local, dims, K, frames, host_pin, dev_frames, METRIC, UNIT, measured_peak_hbm,
+              ClockSampler, workload_label=None):
+    """bench.py's N > 1 leg.  The driver's line is the WEAK-scaled job (~512^3 voxels per GPU: every rank runs
+    the sharded pipeline on the same frames; value = updated voxels per frame summed over the ranks' OWNED
+    planes / device time per frame, max over ranks).  The same line carries, under "strong", BASELINE's large
+    volume (--strong-dims, default 2048^3) on the same N GPUs next to the same volume on ONE GPU, and under
+    "parity" the bit-for-bit comparison of the sharded poses with the single-GPU pipeline's."""
+    w, h = K.width, K.height
+    S, W = args.steps, args.warmup
+    port = os.environ.get("MASTER_PORT", "0")
+    main = _measure_config(args, dist, rank, world, local, dims, K, frames, host_pin, dev_frames, ClockSampler, True, f"{port}_w")
+    strong = None
+    sd = getattr(args, "strong_dims", 0) or 0
+    if sd and sd != dims:
+        strong = _measure_config(args, dist, rank, world, local, sd, K, frames, host_pin, dev_frames, ClockSampler, False, f"{port}_s")
     if rank != 0:
         return
-    U_owned = sum(float(g[0]) for g in gathered)
-    k_max = max(float(g[2]) for g in gathered)
-    U_stored = sum(float(g[1]) for g in gathered)
     peak, peak_src = measured_peak_hbm()
-    achieved = 8.0 * U_stored / (k_max * 1e-3) / 1e9       # aggregate over the ranks, slowest rank's kernel time
-    ms_per_frame = dev_ms / S
+    k_max = main["stage_ms"]["integrate_kernel_slowest_rank"]
+    achieved = 8.0 * main["U_stored"] / (k_max * 1e-3) / 1e9       # aggregate over the ranks, slowest rank's kernel time
+    ms_per_frame = main["ms_per_step"]
+    label = workload_label(dims) if workload_label else f"640x480 depth, {dims}^3 TSDF over 3 m"
+    parity = {"final_pose_equal": bool(main["single"]["poses_equal"]),
+              "what": f"all {1 + W + S} poses of the {world}-GPU sharded run == the single-GPU pipeline's at {dims}^3, bit for bit"}
     line = {
-        "metric": METRIC, "value": U_owned / (ms_per_frame * 1e-3), "unit": UNIT, "n_gpus": world, "steps": S, "warmup": W,
+        "metric": METRIC, "value": main["U_owned"] / (ms_per_frame * 1e-3), "unit": UNIT, "n_gpus": world, "steps": S, "warmup": W,
         "ms_per_step": ms_per_frame, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 -> int16 tsdf", "data": "synthetic",
-        "config": {"workload": f"640x480 depth, {dims}^3 TSDF over 3 m sharded into {world} z-slabs (~512^3 voxels per GPU), "
-                               "ICP 10/5/4 on rank 0, per-slab raycast + first-hit composite, 300-frame looped synthetic trajectory",
+        "config": {"workload": label,
+                   "sharding": f"{world} z-slabs (~512^3 voxels per GPU), ICP on rank 0, per-slab raycast + first-hit composite",
                    "l2": "inputs larger than L2: every rank sweeps its >= 512 MiB slab each frame",
-                   "frames_timed": S, "updated_voxels_per_frame": U_owned, "swept_voxels_per_frame": dims * dims * (dims - 1),
-                   "collectives_per_frame": ("pose mailbox 52 B (shared memory); composite = one kernel over NVLink peer memory" if skf.p2p else "pose mailbox 52 B (shared memory), all_reduce(min) 1.2 MB, reduce(sum) 9.8 MB")},
+                   "frames_timed": S, "updated_voxels_per_frame": main["U_owned"], "swept_voxels_per_frame": dims * dims * (dims - 1),
+                   "collectives_per_frame": ("pose mailbox 52 B (shared memory); composite = one kernel over NVLink peer memory" if main["p2p"] else "pose mailbox 52 B (shared memory), all_reduce(min) 1.2 MB, reduce(sum) 9.8 MB")},
         "frame_device_ms": ms_per_frame,
-        "slab_bounds": skf.bounds if skf.bounds is not None else [slab_range(dims, world, r)[0] for r in range(world)] + [dims],
-        "final_pose": [float(x) for x in poses[-1]],
-        "e2e": {"value": U_owned / (e2e_ms / S * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / S,
+        "slab_bounds": main["bounds"],
+        "final_pose": [float(x) for x in main["poses"][-1]],
+        "parity": parity,
+        "stage_ms": main["stage_ms"],
+        "single_gpu_same_dims": {k: v for k, v in main["single"].items()},
+        "e2e": {"value": main["U_owned"] / (main["e2e_ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": main["e2e_ms_per_step"],
                 "h2d_bytes_per_step": w * h * 4 * world, "d2h_bytes_per_step": 19 * 27 * 16 + 52 * world,
-                "api": "kf::kinectfusion::pipeline(depth_mm) on every rank (z-slab sharded, kf::ShardComm over NCCL), pinned host frames"},
-        "gpu_launches": int(launches) * world,
+                "api": "kf::kinectfusion::pipeline(depth_mm) on every rank (z-slab sharded, kf::ShardComm), pinned host frames"},
+        "gpu_launches": int(main["launches"]) * world,
         "roofline": {"bound": "hbm", "kernel": "integrate_kernel", "achieved": achieved, "peak": peak * world, "unit": "GB/s",
-                     "frac": achieved / (peak * world), "traffic": None, "peak_source": peak_src + f" x {world} GPUs",
-                     "kernel_ms": k_max, "algorithmic_bytes": 8.0 * U_stored},
-        "clocks": clocks,
+                     "frac": achieved / (peak * world), "traffic": None,
+                     "traffic_source": "not captured at N > 1 (ncu runs on one GPU; see the N = 1 line)",
+                     "peak_source": peak_src + f" x {world} GPUs",
+                     "kernel_ms": k_max, "algorithmic_bytes": 8.0 * main["U_stored"]},
+        "clocks": main["clocks"],
     }
+    if strong is not None:
+        s1 = strong["single"]
+        ks = strong["stage_ms"]["integrate_kernel_slowest_rank"]
+        line["strong"] = {
+            "scaling": "strong", "workload": workload_label(sd) if workload_label else f"{sd}^3",
+            "n_gpus": world, "ms_per_step": strong["ms_per_step"], "value": strong["U_owned"] / (strong["ms_per_step"] * 1e-3), "unit": UNIT,
+            "single_gpu_ms_per_step": s1["ms_per_step"], "frame_speedup_vs_1gpu": s1["ms_per_step"] / strong["ms_per_step"],
+            "integrate_kernel_ms_slowest_rank": ks, "single_gpu_integrate_kernel_ms": s1["integrate_kernel_ms_last_frame"],
+            "integrate_kernel_speedup_vs_1gpu": s1["integrate_kernel_ms_last_frame"] / ks if ks > 0 else None,
+            "roofline_frac_aggregate": 8.0 * strong["U_stored"] / (ks * 1e-3) / 1e9 / (peak * world) if ks > 0 else None,
+            "stage_ms": strong["stage_ms"], "slab_bounds": strong["bounds"],
+            "poses_equal_single_gpu": bool(s1["poses_equal"]),
+        }
+        parity["strong_final_pose_equal"] = bool(s1["poses_equal"])
     print(json.dumps(line))
+    if not parity["final_pose_equal"] or not parity.get("strong_final_pose_equal", True):
+        raise SystemExit("sharded run and single-GPU run disagree (see \"parity\" in the line above)")

@@ -341,6 +341,39 @@ def test_icp_gated_schedule_equals_direct(kfo, kfb):
     assert np.array_equal(a, b)
 
 
+def test_icp_transport_timeout_falls_back_without_losing_the_map(kfo, kfb, monkeypatch):
+    """A persistent ICP kernel that gives up on the host (here: a 2 us poll bound instead of 1 s) is a transport
+    failure, not a tracking failure: the schedule finishes on ordinary launches with bit-identical sums, the
+    facade neither resets the volume nor loses the pose history, and the poses equal an undisturbed run's."""
+    Ko = kfo.intr()
+    Kb = kfb.Intrinsics(**kfb.SENSORS["kinect1"])
+    frames = [kfo.render_depth_mm(kfo.trajectory_pose(k), Ko) for k in range(5)]
+
+    def run():
+        kf = kfb.KinectFusion(Kb, kfb.default_host_params(64))
+        for d in frames:
+            assert kf.pipeline(d) == 0
+        return kf, np.stack([np.asarray(p) for p in kf.poses()])
+
+    _, want = run()
+    monkeypatch.setenv("KFB_ICP_TIMEOUT_NS", "2000")
+    kf, got = run()
+    monkeypatch.delenv("KFB_ICP_TIMEOUT_NS")
+    assert kf.frame_count == len(frames) + 1 and len(got) == len(want)
+    assert np.array_equal(got, want)
+    assert kf.context().icp_fallback_count() >= 1
+    assert kf.context().download_volume()[..., 1].max() == len(frames)
+
+
+def test_icp_schedule_bounds(kfo, kfb):
+    Ko, Kb, Po, Pb = make_pair(kfo, kfb, 64, 320, 240)
+    ctx = _ctx(kfb, Kb, Pb)
+    with pytest.raises(kfb.KfbError):
+        ctx.icp_begin([100, 100, 100])        # 300 iterations: more than the release tag can number
+    ctx.icp_begin([1, 1, 1])
+    ctx.icp_end()
+
+
 def test_icp_degenerate_inputs(kfo, kfb):
     Ko, Kb, Po, Pb = make_pair(kfo, kfb, 64, 320, 240)
     ctx = _ctx(kfb, Kb, Pb)
