@@ -221,6 +221,10 @@ void kfb_debug_icp_ring(kfb_ctx *ctx, uint64_t out128[128]);
 /* number of ICP schedules (or rests of schedules) that ran as ordinary per-iteration launches because the persistent
  * kernel could not be made co-resident or its host handshake timed out (results are bit-identical either way) */
 uint64_t kfb_icp_fallback_count(const kfb_ctx *ctx);
+/* debug / measurement: numbers of the last COUNTING kfb_integrate call (n_updated != NULL): {updated voxels, 16-byte
+ * voxel quads loaded, quads stored, stream work items, general work items, 0}.  Loads + stores x 16 B is the
+ * kernel's own count of the bytes it moved (stores of unchanged values are dropped). */
+void kfb_debug_integrate_counts(kfb_ctx *ctx, uint64_t out6[6]);
 
 #ifdef __cplusplus
 }

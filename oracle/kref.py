@@ -45,6 +45,7 @@ def lib():
         L.ref_kinfu_get_pose.argtypes = [_vp, _vp]
         L.ref_kinfu_pipeline.restype = C.c_int
         L.ref_kinfu_pipeline.argtypes = [_vp, _vp]
+        L.ref_kinfu_sync_from.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_int]
         L.ref_event_ms.restype = C.c_float
         L.ref_event_ms.argtypes = [C.c_int]
         _lib = L
@@ -129,6 +130,12 @@ class RefKinfu:
         p = np.empty(12, np.float32)
         lib().ref_kinfu_get_pose(self.h, _p(p))
         return p
+
+    def sync_from(self, vol_packed_dev, vmap4_dev, nmap4_dev, pose12, frame_count):
+        """Adopt another pipeline's state (device pointers, same process): packed 4-byte voxels, float4 model
+        maps of level 0, camera pose.  The caller has synchronised the producer's stream."""
+        p = _f(pose12)
+        lib().ref_kinfu_sync_from(self.h, _vp(int(vol_packed_dev)), _vp(int(vmap4_dev)), _vp(int(nmap4_dev)), _p(p), int(frame_count))
 
 
 def event_tic():

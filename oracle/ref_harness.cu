@@ -515,3 +515,50 @@ float ref_event_ms(int which) // 0: tic now, 1: toc -> ms since tic (legacy defa
 }
 
 } // extern "C"
+
+// ---- lock-step checking (tests/test_ref_full.py): put the reference loop into the state of another pipeline ----
+// vol_packed: device pointer to packed {int16 tsdf, int16 weight} voxels in the reference's index order;
+// vmap4 / nmap4: device pointers to level-0 model maps as float4 (w unused); pose12: camera pose.  Everything is
+// converted on the device into the reference's own layouts (8-byte Voxel, float3 maps); the coarser model levels are
+// rebuilt with the reference's resizePointsNormals, as its frame loop does after every raycast.
+namespace
+{
+__global__ void unpack_volume(const uint32_t *src, Voxel *dst, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    {
+        const uint32_t w = src[i];
+        Voxel v;
+        memset(&v, 0, sizeof(v));
+        v.tsdf = (short)(w & 0xffffu);
+        v.weight = (short)(w >> 16);
+        dst[i] = v;
+    }
+}
+__global__ void f4_to_f3(const float4 *src, float3 *dst, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const float4 v = src[i]; dst[i] = make_float3(v.x, v.y, v.z); }
+}
+} // namespace
+extern "C" void ref_kinfu_sync_from(void *hnd, const void *vol_packed, const void *vmap4, const void *nmap4, const float pose12[12], int frame_count)
+{
+    RefKinfu *k = (RefKinfu *)hnd;
+    const size_t n = (size_t)k->dims[0] * k->dims[1] * k->dims[2];
+    unpack_volume<<<148 * 8, 256>>>((const uint32_t *)vol_packed, (Voxel *)k->vol->p, n);
+    const int np = k->w * k->h;
+    f4_to_f3<<<(np + 255) / 256, 256>>>((const float4 *)vmap4, (float3 *)k->prev.v[0]->p, np);
+    f4_to_f3<<<(np + 255) / 256, 256>>>((const float4 *)nmap4, (float3 *)k->prev.n[0]->p, np);
+    for (int l = 1; l < 3; ++l)
+    {
+        const int bw = k->w >> (l - 1), bh = k->h >> (l - 1), sw = k->w >> l, sh = k->h >> l;
+        GpuMat gvb(bh, bw, 12, k->prev.v[l - 1]->p), gnb(bh, bw, 12, k->prev.n[l - 1]->p);
+        GpuMat gvs(sh, sw, 12, k->prev.v[l]->p), gns(sh, sw, 12, k->prev.n[l]->p);
+        gvs.setTo(0); gns.setTo(0);
+        resizePointsNormals(gvb, gnb, gvs, gns);
+    }
+    k->pose = ident4();
+    memcpy(k->pose.m, pose12, 12 * sizeof(float));
+    k->frame_count = frame_count;
+    cudaDeviceSynchronize();
+}

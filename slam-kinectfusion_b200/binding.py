@@ -118,6 +118,7 @@ def load_library():
         "kfb_debug_icp_stamps": (None, [_vp, _vp]),
         "kfb_debug_icp_ring": (None, [_vp, _vp]),
         "kfb_icp_fallback_count": (C.c_uint64, [_vp]),
+        "kfb_debug_integrate_counts": (None, [_vp, _vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -356,6 +357,12 @@ class Context:
         out = np.zeros((32, 4), np.uint64)
         self.lib.kfb_debug_icp_ring(self.h, _ptr(out))
         return out
+
+    def integrate_counts(self):
+        """{updated, quads_loaded, quads_stored, stream_items, general_items} of the last integrate(count=True)."""
+        out = np.zeros(6, np.uint64)
+        self.lib.kfb_debug_integrate_counts(self.h, _ptr(out))
+        return dict(updated=int(out[0]), quads_loaded=int(out[1]), quads_stored=int(out[2]), stream_items=int(out[3]), general_items=int(out[4]))
 
     def icp_fallback_count(self):
         return int(self.lib.kfb_icp_fallback_count(self.h))

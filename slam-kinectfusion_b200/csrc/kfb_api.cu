@@ -101,6 +101,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     memset(ctx->peer_keys, 0, sizeof(ctx->peer_keys)); memset(ctx->peer_maps, 0, sizeof(ctx->peer_maps)); memset(ctx->peer_flag, 0, sizeof(ctx->peer_flag));
     ctx->vol = nullptr; ctx->cloud = nullptr; ctx->cloud_cap = 0;
     ctx->tab_thrz = nullptr; ctx->tab_exact = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->zmip = nullptr; ctx->bricks = nullptr; ctx->states = nullptr; ctx->states_bytes = 0;
+    ctx->tab4 = nullptr; ctx->plan_buf = nullptr; ctx->plan_bytes = 0; ctx->plan_hint_host = nullptr;
     ctx->bdist = ctx->bdist_tmp = ctx->bdist_tmp2 = nullptr; ctx->bdirty = nullptr;
     ctx->hit_t = nullptr; ctx->icp_partials = nullptr; ctx->icp_ticket = nullptr; ctx->counters = nullptr;
     ctx->counters_host = nullptr; ctx->pinned_depth = nullptr; ctx->depth_u16 = nullptr; ctx->render_dev = nullptr; ctx->render_host = nullptr;
@@ -109,6 +110,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->icp_host = nullptr; ctx->icp_gate_host = nullptr; ctx->icp_devgate = nullptr; ctx->icp_mirror = nullptr;
     ctx->icp_smem_set = 0;
     ctx->icp_fallbacks = 0; ctx->icp_direct_left = 0;
+    ctx->istream = nullptr; ctx->ev_ifork = nullptr; ctx->ev_ijoin = nullptr;
     ctx->dev_err_host = ctx->dev_err_dev = nullptr;
     memset(ctx->L, 0, sizeof(ctx->L));
     memset(ctx->events, 0, sizeof(ctx->events));
@@ -122,6 +124,13 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     }
     KFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     KFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->fstream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        KFB_CUDA(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        KFB_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->istream, cudaStreamNonBlocking, hi));
+    }
+    KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ifork, cudaEventDisableTiming));
+    KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ijoin, cudaEventDisableTiming));
     KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_front, cudaEventDisableTiming));
     KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_free, cudaEventDisableTiming));
     KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_tables_free, cudaEventDisableTiming));
@@ -183,6 +192,9 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
         KFB_CUDA(ctx, cudaMalloc(&ctx->bdirty, sizeof(int)));
     }
     KFB_CUDA(ctx, cudaMalloc(&ctx->tab_exact, n0 * sizeof(float2)));
+    KFB_CUDA(ctx, cudaMalloc(&ctx->tab4, n0 * sizeof(float4)));
+    KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->plan_hint_host, 64, cudaHostAllocDefault));
+    memset(ctx->plan_hint_host, 0, 64);
     KFB_CUDA(ctx, cudaMalloc(&ctx->hit_t, n0 * sizeof(float)));
     KFB_CUDA(ctx, cudaMalloc(&ctx->shard_flag, 256));
     KFB_CUDA(ctx, cudaMemset(ctx->shard_flag, 0, 256));
@@ -229,6 +241,10 @@ void kfb_destroy(kfb_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->fstream) cudaStreamSynchronize(ctx->fstream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->istream) cudaStreamSynchronize(ctx->istream);
+    if (ctx->ev_ifork) cudaEventDestroy(ctx->ev_ifork);
+    if (ctx->ev_ijoin) cudaEventDestroy(ctx->ev_ijoin);
+    if (ctx->istream) cudaStreamDestroy(ctx->istream);
     if (ctx->ev_front) cudaEventDestroy(ctx->ev_front);
     if (ctx->ev_free) cudaEventDestroy(ctx->ev_free);
     if (ctx->ev_tables_free) cudaEventDestroy(ctx->ev_tables_free);
@@ -252,6 +268,9 @@ void kfb_destroy(kfb_ctx *ctx)
     if (ctx->bdist_tmp2) cudaFree(ctx->bdist_tmp2);
     if (ctx->bdirty) cudaFree(ctx->bdirty);
     if (ctx->tab_exact) cudaFree(ctx->tab_exact);
+    if (ctx->tab4) cudaFree(ctx->tab4);
+    if (ctx->plan_buf) cudaFree(ctx->plan_buf);
+    if (ctx->plan_hint_host) cudaFreeHost(ctx->plan_hint_host);
     if (ctx->hit_t) cudaFree(ctx->hit_t);
     shard_close_peers(ctx);
     if (ctx->shard_flag) cudaFree(ctx->shard_flag);
@@ -658,5 +677,12 @@ void kfb_debug_icp_ring(kfb_ctx *ctx, uint64_t out128[128])
     for (int i = 0; i < 128; ++i) out128[i] = ctx->icp_host->post_ns[i / 4][i % 4];
 }
 uint64_t kfb_icp_fallback_count(const kfb_ctx *ctx) { return ctx ? ctx->icp_fallbacks : 0; }
+void kfb_debug_integrate_counts(kfb_ctx *ctx, uint64_t out6[6])
+{
+    // valid after a counting kfb_integrate call (n_updated != NULL), which synchronises
+    out6[0] = ctx->counters_host[0]; out6[1] = ctx->counters_host[2]; out6[2] = ctx->counters_host[3];
+    const unsigned int *pc = reinterpret_cast<const unsigned int *>(ctx->counters_host + 4);
+    out6[3] = pc[0]; out6[4] = pc[1]; out6[5] = 0;
+}
 
 } // extern "C"

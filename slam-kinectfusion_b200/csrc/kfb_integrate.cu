@@ -86,6 +86,17 @@ struct IntegrateArgs
     int bx, by, bz, bz0; // brick grid dims (x, y, stored z bricks) and first stored z brick
     CullPlane cull[KFB_NCULL];
     unsigned long long *counter;
+    // ---- work plan (integrate_plan_kernel): the sweep as two lists of (patch, plane range) items ----
+    const float4 *tab4;           // per pixel {hi_z, lo_z, depth, 1/lambda}
+    int npx, npy;                 // 16 x 8 voxel patches in x and y
+    int mask_words;               // 32-bit words of a patch's "chunk has a general item" mask
+    uint2 *items_stream;          // {patch, z0 | z1 << 16}: every voxel of these planes gets tsdf = 1.0f
+    uint2 *items_general;         // {patch, z0 | z1 << 16}: planes that need the per-voxel predicate (within one chunk)
+    unsigned int *plan_counts;    // [0] stream items, [1] general items
+    unsigned int *patch_mask;     // [patch][mask_words]
+    unsigned int *slot_of;        // [patch][chunk] -> general item index
+    unsigned long long *gstates;  // [general item][6][32]: packed vc of the item's 32 threads after plane zstart(chunk) - 1
+    int gstate_cap;               // general items that have a state slot (the others replay their running sums)
 };
 
 #define KFB_MAGIC_F 12582912.0f   // 1.5 * 2^23
@@ -149,7 +160,7 @@ __device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsign
 // *zexit = max lo_z over the image: a voxel with vc.z above it is rejected whatever pixel it lands on.
 __global__ void build_tables_kernel(const float *__restrict__ depth, int w, int h, float fx, float fy, float cx,
                                     float cy, float trunc, float2 *__restrict__ thrz, float2 *__restrict__ exact,
-                                    float *__restrict__ zexit)
+                                    float4 *__restrict__ tab4, float *__restrict__ zexit)
 {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y * blockDim.y + threadIdx.y;
@@ -184,6 +195,7 @@ __global__ void build_tables_kernel(const float *__restrict__ depth, int w, int 
             lo_z = sqrtf(lo2 / lmin2) * (1.f + 1e-6f);
         }
         thrz[p] = make_float2(hi_z, lo_z);
+        tab4[p] = make_float4(hi_z, lo_z, d, il); // the sweep's general path reads everything about a pixel with one load
     }
     // image-wide max of lo_z (positive floats order like their bit patterns)
 #pragma unroll
@@ -898,6 +910,565 @@ __global__ void __launch_bounds__(128) column_states_kernel(const IntegrateArgs 
     }
 }
 
+// =====================================================================================================
+// The sweep as a work plan (round 2).  The kernel above decides per warp and per z-chunk, inside the sweep, what
+// its patch needs (frustum interval, occlusion cut, deep free space) before it touches a voxel; with every warp
+// slot taken by warps that wait on memory, that setup, the streaming part and the per-voxel part simply add up
+// (DESIGN.md 3.2).  Here the decisions are taken once, by a small kernel with one thread per (16 x 8 voxel patch,
+// 16-plane chunk), which writes two compact work lists:
+//   stream items  {patch, z0..z1}: every voxel of these planes passes the reference's predicate with tsdf == 1.0f
+//                 exactly (same proof as the fast path above, at patch granularity) -- integrate_stream_kernel does
+//                 nothing but load -> running mean -> store, eight planes in flight per thread;
+//   general items {patch, z0..z1}: planes on which the exact per-voxel predicate decides (the band around the
+//                 surface, the frustum border, holes) -- integrate_general_kernel runs the reference's arithmetic
+//                 as a two-stage software pipeline: the table entries and the voxel words of plane z + 1 are in
+//                 flight while plane z is classified and updated, so a warp pays one memory latency per plane
+//                 instead of three dependent ones.
+// The running sums of the reference (vc += zstep) are only needed by the general items: integrate_states_kernel
+// walks the patches that have any, one warp per patch, and stores the 32 threads' sums at the chunk starts the
+// plan asked for (48 B per thread per general item instead of per column per chunk).
+// Culling is conservative and the per-voxel predicate is exact, so no split of the work can change a result:
+// tests/test_ref_ab.py and tests/test_ref_full.py compare whole volumes with the reference kernels' bit for bit.
+#define KFB_PATCH_X 16
+#define KFB_PATCH_Y 8
+#define KFB_PLAN_ZCHUNK 16
+
+// conservative interval of planes on which any column of a patch can pass the predicate; (cx, cy, cz)[k] = vc at
+// z = 0 of the patch's corner columns (g is affine in x and y, so its maximum over the patch sits at a corner)
+template <int N>
+__device__ __forceinline__ void frustum_interval_n(const IntegrateArgs &a, const float cx[N], const float cy[N], const float cz[N], int zstart,
+                                                   int zend, float &lo, float &hi)
+{
+    lo = (float)zstart;
+    hi = (float)(zend - 1);
+    const float zx = __ldg(a.zexit);
+#pragma unroll
+    for (int c = 0; c < KFB_NCULL; ++c)
+    {
+        const CullPlane &cp = a.cull[c];
+        if (cp.kind == 3) continue;
+        float g0 = -3.0e38f;
+#pragma unroll
+        for (int k = 0; k < N; ++k) g0 = fmaxf(g0, fmaf(cp.a, cx[k], fmaf(cp.b, cy[k], cp.g * cz[k])));
+        g0 += cp.slack;
+        if (c == KFB_NCULL - 1) g0 += zx; // vc.z <= zexit
+        const float zc = g0 * cp.ninv;
+        if (cp.kind == 0) lo = fmaxf(lo, zc - 1.f);
+        else if (cp.kind == 1) hi = fminf(hi, zc + 1.f);
+        else if (g0 < 0.f) hi = -1.f;
+    }
+    lo = fminf(lo, (float)zend);
+    hi = fmaxf(hi, (float)zstart - 2.f);
+}
+
+__global__ void __launch_bounds__(128) integrate_plan_kernel(const IntegrateArgs a)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x; // (chunk, patch row, patch column), column fastest:
+    const int npatch = a.npx * a.npy;                    // a warp plans a row of patches, its items stay neighbours
+    bool s_item = false, g_item = false;
+    int s_z0 = 0, s_z1 = 0, g_z0 = 0, g_z1 = 0, patch = 0, c = 0;
+    if (t < npatch * a.nchunks)
+    {
+        c = t / npatch;
+        patch = t - c * npatch;
+        const int py = patch / a.npx, px = patch - py * a.npx;
+        const int zstart = a.zb + c * a.zchunk, zend = min(zstart + a.zchunk, a.ze);
+        const int xa = px * KFB_PATCH_X, xb = min(xa + KFB_PATCH_X - 1, a.X - 1), ya = py * KFB_PATCH_Y, yb = min(ya + KFB_PATCH_Y - 1, a.Y - 1);
+        float cx[4], cy[4], cz[4];
+        const float pz = __fmul_rn(0.f, a.vsz);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            const float3 r = rot3(a.pose.R, __fmul_rn((float)((k & 1) ? xb : xa), a.vsx), __fmul_rn((float)((k & 2) ? yb : ya), a.vsy), pz);
+            cx[k] = __fadd_rn(r.x, a.pose.t[0]); cy[k] = __fadd_rn(r.y, a.pose.t[1]); cz[k] = __fadd_rn(r.z, a.pose.t[2]);
+        }
+        float lo, hi;
+        frustum_interval_n<4>(a, cx, cy, cz, zstart, zend, lo, hi);
+        int za = max(zstart, (int)floorf(lo)), zb = min(zend - 1, (int)ceilf(hi));
+        int free_end = za - 1;
+        // Occlusion cut and deep free space at patch granularity (see the per-thread version above for the proofs):
+        // over planes [za, zb] the patch projects into a pixel rectangle; beyond max lo_z of it every voxel is
+        // rejected, up to min hi_z of it (all pixels inside the image) every voxel is free space.
+        if (za <= zb && a.Sz > 1e-6f)
+        {
+            float umin = 1e30f, umax = -1e30f, vmin = 1e30f, vmax = -1e30f, zmin = 1e30f;
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+            {
+                const float zf = (float)(e ? zb : za);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                {
+                    const float X = fmaf(zf, a.Sx, cx[k]), Y = fmaf(zf, a.Sy, cy[k]), Zc = fmaf(zf, a.Sz, cz[k]);
+                    const float r = mufu_rcp(fmaxf(Zc, 1e-3f));
+                    const float u = fmaf(a.fx * X, r, a.cx), v = fmaf(a.fy * Y, r, a.cy);
+                    umin = fminf(umin, u); umax = fmaxf(umax, u);
+                    vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+                    zmin = fminf(zmin, Zc);
+                }
+            }
+            if (zmin > 0.05f)
+            {
+                const float pad = 1.5f + (a.fx + a.fy + (float)(a.w + a.h)) * a.driftE * (1.001f * mufu_rcp(zmin));
+                const bool all_inside = umin - pad >= 0.f && umax + pad <= (float)(a.w - 1) && vmin - pad >= 0.f && vmax + pad <= (float)(a.h - 1);
+                const int u0 = max((int)floorf(fmaxf(umin - pad, -1e6f)), 0), u1 = min((int)ceilf(fminf(umax + pad, 1e6f)), a.w - 1);
+                const int v0 = max((int)floorf(fmaxf(vmin - pad, -1e6f)), 0), v1 = min((int)ceilf(fminf(vmax + pad, 1e6f)), a.h - 1);
+                if (u0 > u1 || v0 > v1) zb = za - 1; // never inside the image on these planes
+                else
+                {
+                    const int span = max(u1 - u0, v1 - v0) + 1;
+                    const int l = max(32 - __clz(span - 1) - 2, 2); // tiles a quarter of the span wide: at most 5 x 5 cover the rectangle
+                    if (l <= 7)
+                    {
+                        const float2 *m = a.zmip + a.mip_off[l - 2];
+                        const int mw = a.mip_w[l - 2];
+                        const int tx0 = u0 >> l, tx1 = u1 >> l, ty0 = v0 >> l, ty1 = v1 >> l;
+                        // 25 loads in flight; tiles beyond the rectangle repeat its last one (harmless for min / max)
+                        float2 q = make_float2(-1.f, 3.0e38f);
+                        float2 tl[25];
+#pragma unroll
+                        for (int j = 0; j < 5; ++j)
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) tl[j * 5 + i] = __ldg(m + min(ty0 + j, ty1) * mw + min(tx0 + i, tx1));
+#pragma unroll
+                        for (int i = 0; i < 25; ++i) q = mm2(q, tl[i]);
+                        const float zmin0 = fminf(fminf(cz[0], cz[1]), fminf(cz[2], cz[3])), zmax0 = fmaxf(fmaxf(cz[0], cz[1]), fmaxf(cz[2], cz[3]));
+                        const float e2 = 2.f * a.driftE;
+                        const float zc = (q.x + e2 - zmin0) * a.invSz + 1.f;
+                        zb = min(zb, (int)ceilf(fminf(zc, 1e6f)));
+                        if (all_inside && !a.no_fastpath && za <= zb)
+                        {
+                            int zf = min(zb, (int)floorf(fminf(fmaxf((q.y - e2 - zmax0) * a.invSz, -1.f), 1e6f)));
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+                                if (zf >= za && fmaf((float)zf, a.Sz, zmax0) + e2 > q.y) --zf;
+                            if (zf >= za && fmaf((float)zf, a.Sz, zmax0) + e2 <= q.y) free_end = zf;
+                        }
+                    }
+                }
+            }
+        }
+        if (za <= zb)
+        {
+            const int fe = min(free_end, zb);
+            if (fe >= za) { s_item = true; s_z0 = za; s_z1 = fe; }
+            if (fe < zb) { g_item = true; g_z0 = max(za, fe + 1); g_z1 = zb; }
+        }
+    }
+    // warp-aggregated append (keeps the warp's items in patch order)
+    const unsigned ms = __ballot_sync(FULL, s_item), mg = __ballot_sync(FULL, g_item);
+    const int lane = threadIdx.x & 31;
+    unsigned bs = 0, bg = 0;
+    if (lane == 0)
+    {
+        if (ms) bs = atomicAdd(a.plan_counts + 0, __popc(ms));
+        if (mg) bg = atomicAdd(a.plan_counts + 1, __popc(mg));
+    }
+    bs = __shfl_sync(FULL, bs, 0);
+    bg = __shfl_sync(FULL, bg, 0);
+    const unsigned below = (1u << lane) - 1u;
+    if (s_item) a.items_stream[bs + __popc(ms & below)] = make_uint2((unsigned)patch, (unsigned)s_z0 | ((unsigned)s_z1 << 16));
+    if (g_item)
+    {
+        const unsigned idx = bg + __popc(mg & below);
+        a.items_general[idx] = make_uint2((unsigned)patch, (unsigned)g_z0 | ((unsigned)g_z1 << 16));
+        a.slot_of[(size_t)patch * a.nchunks + c] = idx;
+        atomicOr(a.patch_mask + (size_t)patch * a.mask_words + (c >> 5), 1u << (c & 31));
+    }
+}
+
+// running sums at the chunk starts of the general items: one warp per patch, lane = the sweep's thread of that patch
+__global__ void __launch_bounds__(128) integrate_states_kernel(const IntegrateArgs a)
+{
+    const int patch = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (patch >= a.npx * a.npy) return;
+    int c_last = -1;
+    for (int w = a.mask_words - 1; w >= 0 && c_last < 0; --w)
+    {
+        const unsigned m = __ldg(a.patch_mask + (size_t)patch * a.mask_words + w);
+        if (m) c_last = w * 32 + 31 - __clz(m);
+    }
+    if (c_last < 0) return;
+    const int py = patch / a.npx, px = patch - py * a.npx;
+    // lanes beyond the volume's edge compute a valid neighbour's sums (never read)
+    const int x0 = min(px * KFB_PATCH_X + (lane & 3) * 4, a.X - 4), y = min(py * KFB_PATCH_Y + (lane >> 2), a.Y - 1);
+    float vx[4], vy[4], vz[4];
+    {
+        const float pyf = __fmul_rn((float)y, a.vsy), pz = __fmul_rn(0.f, a.vsz);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            const float3 r = rot3(a.pose.R, __fmul_rn((float)(x0 + k), a.vsx), pyf, pz);
+            vx[k] = __fadd_rn(r.x, a.pose.t[0]); vy[k] = __fadd_rn(r.y, a.pose.t[1]); vz[k] = __fadd_rn(r.z, a.pose.t[2]);
+        }
+    }
+    const float sx = a.pose.R.m[2], sy = a.pose.R.m[5], sz = a.pose.R.m[8];
+    int done = 0; // planes applied so far
+    if (a.use_jump && a.zb - 1 >= a.jump_min)
+    {
+        jump4(vx, a.vsx, sx, a.zb - 1);
+        jump4(vy, a.vsx, sy, a.zb - 1);
+        jump4(vz, a.vsx, sz, a.zb - 1);
+        done = a.zb - 1;
+    }
+    unsigned long long xy[4], zz[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xy[k] = pack2(vx[k], vy[k]);
+    zz[0] = pack2(vz[0], vz[1]);
+    zz[1] = pack2(vz[2], vz[3]);
+    const unsigned long long vs2 = pack2(a.vsx, a.vsx), sxy = pack2(sx, sy), szz = pack2(sz, sz);
+    for (int c = 0; c <= c_last; ++c)
+    {
+        const int target = a.zb + c * a.zchunk - 1; // state after this plane
+#pragma unroll 4
+        for (; done < target; ++done)
+        {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) xy[k] = ffma2(vs2, sxy, xy[k]);
+            zz[0] = ffma2(vs2, szz, zz[0]);
+            zz[1] = ffma2(vs2, szz, zz[1]);
+        }
+        if (!((__ldg(a.patch_mask + (size_t)patch * a.mask_words + (c >> 5)) >> (c & 31)) & 1u)) continue;
+        const unsigned slot = __ldg(a.slot_of + (size_t)patch * a.nchunks + c);
+        if (slot >= (unsigned)a.gstate_cap) continue; // no slot: the item replays by itself
+        unsigned long long *o = a.gstates + (size_t)slot * 192 + lane;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k * 32] = xy[k];
+        o[128] = zz[0];
+        o[160] = zz[1];
+    }
+}
+
+// running mean of a quad that receives tsdf = 1.0f in all four voxels; WT = per-weight table (shared or global)
+template <bool COUNT>
+__device__ __forceinline__ void update_free_quad(const IntegrateArgs &a, const float4 *__restrict__ wt, uint4 *vp, const uint4 wd, unsigned int &n_upd,
+                                                 unsigned int &n_st)
+{
+    uint4 o;
+    const unsigned int mw = (unsigned)a.max_weight;
+    if ((wd.x == wd.y) & (wd.x == wd.z) & (wd.x == wd.w))
+    {
+        const unsigned int w0 = wd.x >> 16;
+        o.x = w0 <= mw ? update_word_e(wd.x, 1.0f, wt[w0]) : update_generic(wd.x, 1.0f, a.max_weight);
+        o.y = o.z = o.w = o.x;
+    }
+    else
+    {
+        const unsigned int w0 = wd.x >> 16, w1 = wd.y >> 16, w2 = wd.z >> 16, w3 = wd.w >> 16;
+        if (max(max(w0, w1), max(w2, w3)) <= mw)
+        {
+            const float4 e0 = wt[w0], e1 = wt[w1], e2 = wt[w2], e3 = wt[w3];
+            o.x = update_word_e(wd.x, 1.0f, e0); o.y = update_word_e(wd.y, 1.0f, e1);
+            o.z = update_word_e(wd.z, 1.0f, e2); o.w = update_word_e(wd.w, 1.0f, e3);
+        }
+        else
+        {
+            o.x = update_generic(wd.x, 1.0f, a.max_weight); o.y = update_generic(wd.y, 1.0f, a.max_weight);
+            o.z = update_generic(wd.z, 1.0f, a.max_weight); o.w = update_generic(wd.w, 1.0f, a.max_weight);
+        }
+    }
+    if (COUNT) n_upd += 4;
+    // a mean with +1 cannot turn a non-negative value negative: no brick can become active here
+    if ((o.x != wd.x) | (o.y != wd.y) | (o.z != wd.z) | (o.w != wd.w))
+    {
+        __stcs(vp, o);
+        if (COUNT) ++n_st;
+    }
+}
+
+#define KFB_WTAB_SMEM 256 // per-weight table entries kept in shared memory (max_weight < 256; the default is 64)
+#define KFB_STREAM_DEPTH 8
+template <bool COUNT, bool SMEM>
+__global__ void __launch_bounds__(128, 8) integrate_stream_kernel(const IntegrateArgs a)
+{
+    __shared__ float4 s_wt[SMEM ? KFB_WTAB_SMEM : 1];
+    if (SMEM)
+    {
+        for (int i = threadIdx.x; i <= a.max_weight; i += blockDim.x) s_wt[i] = __ldg(a.wtab + i);
+        __syncthreads();
+    }
+    const float4 *wt = SMEM ? s_wt : a.wtab;
+    const int lane = threadIdx.x & 31;
+    const unsigned int n_items = __ldg(a.plan_counts + 0);
+    const size_t plane4 = ((size_t)a.X * a.Y) >> 2;
+    unsigned int n_upd = 0, n_ld = 0, n_st = 0;
+    for (unsigned int item = blockIdx.x * 4 + (threadIdx.x >> 5); item < n_items; item += gridDim.x * 4)
+    {
+        const uint2 it = __ldg(a.items_stream + item);
+        const int py = (int)it.x / a.npx, px = (int)it.x - py * a.npx;
+        const int x0 = px * KFB_PATCH_X + (lane & 3) * 4, y = py * KFB_PATCH_Y + (lane >> 2);
+        if (x0 >= a.X || y >= a.Y) continue;
+        const int z0 = (int)(it.y & 0xffffu), z1 = (int)(it.y >> 16);
+        uint4 *vp = reinterpret_cast<uint4 *>(a.vol) + ((size_t)(z0 - a.z_store0) * a.Y + y) * (a.X >> 2) + (x0 >> 2);
+        for (int z = z0; z <= z1; z += KFB_STREAM_DEPTH, vp += KFB_STREAM_DEPTH * plane4)
+        {
+            uint4 w[KFB_STREAM_DEPTH];
+#pragma unroll
+            for (int i = 0; i < KFB_STREAM_DEPTH; ++i)
+                if (z + i <= z1) w[i] = __ldcs(vp + i * plane4);
+#pragma unroll
+            for (int i = 0; i < KFB_STREAM_DEPTH; ++i)
+                if (z + i <= z1)
+                {
+                    update_free_quad<COUNT>(a, wt, vp + i * plane4, w[i], n_upd, n_st);
+                    if (COUNT) ++n_ld;
+                }
+        }
+    }
+    if (COUNT)
+    {
+        if (n_upd) atomicAdd(a.counter, (unsigned long long)n_upd);
+        if (n_ld) atomicAdd(a.counter + 2, (unsigned long long)n_ld);
+        if (n_st) atomicAdd(a.counter + 3, (unsigned long long)n_st);
+    }
+}
+
+// ---- general items: the reference's per-voxel arithmetic, software-pipelined over the planes ----------------------
+struct GenStage // one plane of one thread between "loads issued" and "classified and updated"
+{
+    float cz[4];   // vc.z per voxel (+inf: projects outside the image)
+    float d2[4];   // |vc|^2 as the reference computes it (for the band)
+    float4 tb[4];  // {hi_z, lo_z, depth, 1/lambda} of the pixel each voxel lands on
+    uint4 word;    // the four voxels
+};
+struct GenConst
+{
+    unsigned long long vs2, sxy, szz, fxy, cxy, magic2;
+    unsigned int last_pix;
+    float rtrunc;
+};
+__device__ __forceinline__ void gen_issue(const IntegrateArgs &a, const GenConst &g, unsigned long long xy[4], unsigned long long zz[2],
+                                          const uint4 *vp, GenStage &s)
+{
+    s.word = __ldcs(vp); // unconditional: inside an item's plane range nearly every quad is updated
+#pragma unroll
+    for (int k = 0; k < 4; ++k) xy[k] = ffma2(g.vs2, g.sxy, xy[k]);
+    zz[0] = ffma2(g.vs2, g.szz, zz[0]);
+    zz[1] = ffma2(g.vs2, g.szz, zz[1]);
+    unpack2(zz[0], s.cz[0], s.cz[1]);
+    unpack2(zz[1], s.cz[2], s.cz[3]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        const float r = mufu_rcp(s.cz[k]);
+        const unsigned long long q = fmul2(pack2(r, r), xy[k]);
+        const unsigned long long m = fadd2(ffma2(q, g.fxy, g.cxy), g.magic2);
+        float mu, mv, vxk, vyk;
+        unpack2(m, mu, mv);
+        unpack2(xy[k], vxk, vyk);
+        s.d2[k] = dot3c(vxk, vyk, s.cz[k], vxk, vyk, s.cz[k]);
+        const int ui = __float_as_int(mu) - KFB_MAGIC_I;
+        const int vi = __float_as_int(mv) - KFB_MAGIC_I;
+        const bool ok = ((unsigned)ui < (unsigned)a.w) & ((unsigned)vi < (unsigned)a.h);
+        // an out-of-image voxel is classified as "behind everything": vc.z = +inf fails `<= hi_z` and passes
+        // `> lo_z` for whatever (clamped) table entry it reads
+        s.cz[k] = ok ? s.cz[k] : __int_as_float(0x7f800000);
+        s.tb[k] = __ldg(a.tab4 + min((unsigned int)(vi * a.w + ui), g.last_pix));
+    }
+}
+template <bool COUNT>
+__device__ __forceinline__ void gen_process(const IntegrateArgs &a, const GenConst &g, const float4 *__restrict__ wt, const GenStage &s, uint4 *vp,
+                                            int x0, int y, int z, unsigned int &n_upd, unsigned int &n_st)
+{
+    float t[4];
+    bool band = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        t[k] = s.cz[k] <= s.tb[k].x ? 1.0f : (s.cz[k] > s.tb[k].y ? KFB_SKIP : KFB_BAND);
+        band |= (t[k] == KFB_BAND);
+    }
+    if (band)
+    {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            // exact sdf (tsdf_volume.cu:63-71): only here, between the two conservative thresholds
+            const float nsdf = __fmaf_rn(s.tb[k].w, __fsqrt_rn(s.d2[k]), -s.tb[k].z);
+            const float tb = nsdf <= a.trunc ? fminf(1.f, __fmul_rn(g.rtrunc, -nsdf)) : KFB_SKIP;
+            t[k] = t[k] == KFB_BAND ? tb : t[k];
+        }
+    }
+    if (!((t[0] != KFB_SKIP) | (t[1] != KFB_SKIP) | (t[2] != KFB_SKIP) | (t[3] != KFB_SKIP))) return;
+    const uint4 wd = s.word;
+    uint4 o = wd;
+    const unsigned int w0 = wd.x >> 16, w1 = wd.y >> 16, w2 = wd.z >> 16, w3 = wd.w >> 16, mw = (unsigned)a.max_weight;
+    if ((wd.x == wd.y) & (wd.x == wd.z) & (wd.x == wd.w) & (t[0] == t[1]) & (t[0] == t[2]) & (t[0] == t[3]) & (w0 <= mw))
+    {
+        // four equal words receive the same tsdf (free space in front of the band): one update
+        o.x = o.y = o.z = o.w = update_word_e(wd.x, t[0], wt[w0]);
+    }
+    else if (max(max(w0, w1), max(w2, w3)) <= mw)
+    {
+        const float4 e0 = wt[w0], e1 = wt[w1], e2 = wt[w2], e3 = wt[w3];
+        const unsigned int n0 = update_word_e(wd.x, t[0], e0), n1 = update_word_e(wd.y, t[1], e1);
+        const unsigned int n2 = update_word_e(wd.z, t[2], e2), n3 = update_word_e(wd.w, t[3], e3);
+        o.x = t[0] != KFB_SKIP ? n0 : wd.x;
+        o.y = t[1] != KFB_SKIP ? n1 : wd.y;
+        o.z = t[2] != KFB_SKIP ? n2 : wd.z;
+        o.w = t[3] != KFB_SKIP ? n3 : wd.w;
+    }
+    else
+    {
+        if (t[0] != KFB_SKIP) o.x = update_generic(wd.x, t[0], a.max_weight);
+        if (t[1] != KFB_SKIP) o.y = update_generic(wd.y, t[1], a.max_weight);
+        if (t[2] != KFB_SKIP) o.z = update_generic(wd.z, t[2], a.max_weight);
+        if (t[3] != KFB_SKIP) o.w = update_generic(wd.w, t[3], a.max_weight);
+    }
+    if (COUNT) n_upd += (t[0] != KFB_SKIP) + (t[1] != KFB_SKIP) + (t[2] != KFB_SKIP) + (t[3] != KFB_SKIP);
+    if ((o.x != wd.x) | (o.y != wd.y) | (o.z != wd.z) | (o.w != wd.w))
+    {
+        __stcs(vp, o);
+        if (COUNT) ++n_st;
+        // a voxel that turns negative here (it was not before) activates the bricks around it
+        if (((o.x & ~wd.x) | (o.y & ~wd.y) | (o.z & ~wd.z) | (o.w & ~wd.w)) & 0x8000u)
+            mark_bricks(a.bricks, a.bdirty, a.bx, a.by, a.bz, a.bz0, x0, y, z);
+    }
+}
+
+#ifndef KFB_GEN_MINB
+#define KFB_GEN_MINB 5 // blocks of 4 warps per SM the register budget is sized for (<= 96 registers)
+#endif
+template <bool COUNT, bool SMEM>
+__global__ void __launch_bounds__(128, KFB_GEN_MINB) integrate_general_kernel(const IntegrateArgs a)
+{
+    __shared__ float4 s_wt[SMEM ? KFB_WTAB_SMEM : 1];
+    if (SMEM)
+    {
+        for (int i = threadIdx.x; i <= a.max_weight; i += blockDim.x) s_wt[i] = __ldg(a.wtab + i);
+        __syncthreads();
+    }
+    const float4 *wt = SMEM ? s_wt : a.wtab;
+    const int lane = threadIdx.x & 31;
+    const unsigned int n_items = __ldg(a.plan_counts + 1);
+    const size_t plane4 = ((size_t)a.X * a.Y) >> 2;
+    GenConst g;
+    {
+        const float sz = a.pose.R.m[8];
+        g.vs2 = pack2(a.vsx, a.vsx); g.sxy = pack2(a.pose.R.m[2], a.pose.R.m[5]); g.szz = pack2(sz, sz);
+        g.fxy = pack2(a.fx, a.fy); g.cxy = pack2(a.cx, a.cy); g.magic2 = pack2(KFB_MAGIC_F, KFB_MAGIC_F);
+        g.last_pix = (unsigned int)(a.w * a.h - 1);
+        g.rtrunc = rcp_fdividef(a.trunc);
+    }
+    unsigned int n_upd = 0, n_ld = 0, n_st = 0;
+    for (unsigned int item = blockIdx.x * 4 + (threadIdx.x >> 5); item < n_items; item += gridDim.x * 4)
+    {
+        const uint2 it = __ldg(a.items_general + item);
+        const int py = (int)it.x / a.npx, px = (int)it.x - py * a.npx;
+        const int x0 = px * KFB_PATCH_X + (lane & 3) * 4, y = py * KFB_PATCH_Y + (lane >> 2);
+        if (x0 >= a.X || y >= a.Y) continue;
+        const int z0 = (int)(it.y & 0xffffu), z1 = (int)(it.y >> 16);
+        const int zstart = a.zb + ((z0 - a.zb) / a.zchunk) * a.zchunk; // first plane of the item's chunk
+        unsigned long long xy[4], zz[2];
+        {
+            int zfrom = zstart;
+            if (item < (unsigned int)a.gstate_cap)
+            {
+                const unsigned long long *st = a.gstates + (size_t)item * 192 + lane;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) xy[k] = __ldcg(st + k * 32);
+                zz[0] = __ldcg(st + 128);
+                zz[1] = __ldcg(st + 160);
+            }
+            else
+            {
+                // more general items than state slots (a scene that is all surface): this item replays the
+                // reference's running sum from the first plane by itself
+                float vx[4], vy[4], vz[4];
+                const float pyf = __fmul_rn((float)y, a.vsy), pz = __fmul_rn(0.f, a.vsz);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                {
+                    const float3 r = rot3(a.pose.R, __fmul_rn((float)(x0 + k), a.vsx), pyf, pz);
+                    vx[k] = __fadd_rn(r.x, a.pose.t[0]); vy[k] = __fadd_rn(r.y, a.pose.t[1]); vz[k] = __fadd_rn(r.z, a.pose.t[2]);
+                }
+                zfrom = 1;
+                if (a.use_jump && a.zb - 1 >= a.jump_min)
+                {
+                    jump4(vx, a.vsx, a.pose.R.m[2], a.zb - 1);
+                    jump4(vy, a.vsx, a.pose.R.m[5], a.zb - 1);
+                    jump4(vz, a.vsx, a.pose.R.m[8], a.zb - 1);
+                    zfrom = a.zb;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) xy[k] = pack2(vx[k], vy[k]);
+                zz[0] = pack2(vz[0], vz[1]);
+                zz[1] = pack2(vz[2], vz[3]);
+            }
+#pragma unroll 4
+            for (int z = zfrom; z < z0; ++z)
+            {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) xy[k] = ffma2(g.vs2, g.sxy, xy[k]);
+                zz[0] = ffma2(g.vs2, g.szz, zz[0]);
+                zz[1] = ffma2(g.vs2, g.szz, zz[1]);
+            }
+        }
+        uint4 *vp = reinterpret_cast<uint4 *>(a.vol) + ((size_t)(z0 - a.z_store0) * a.Y + y) * (a.X >> 2) + (x0 >> 2);
+        // the pipelined path needs vc.z >= FLT_MIN on every visited plane (MUFU.RCP without the denormal
+        // pre-scaling); vc.z is affine in z up to the running-sum drift, so the two ends decide with a 1 cm margin
+        bool fast;
+        {
+            const float span = (float)(z1 - z0 + 1) * __fmul_rn(a.vsx, a.pose.R.m[8]);
+            float c0, c1, c2, c3;
+            unpack2(zz[0], c0, c1);
+            unpack2(zz[1], c2, c3);
+            const float m = fminf(fminf(c0, c1), fminf(c2, c3)); // plane z0 - 1
+            fast = fminf(m, m + span) > 0.01f;
+        }
+        if (!fast)
+        {
+            // cold path (camera within a centimetre of this thread's planes): one plane at a time, any vc.z
+            for (int z = z0; z <= z1; ++z, vp += plane4)
+            {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) xy[k] = ffma2(g.vs2, g.sxy, xy[k]);
+                zz[0] = ffma2(g.vs2, g.szz, zz[0]);
+                zz[1] = ffma2(g.vs2, g.szz, zz[1]);
+                float cz[4], t[4];
+                unpack2(zz[0], cz[0], cz[1]);
+                unpack2(zz[1], cz[2], cz[3]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                {
+                    float vxk, vyk;
+                    unpack2(xy[k], vxk, vyk);
+                    t[k] = classify_generic(a, vxk, vyk, cz[k], g.rtrunc);
+                }
+                if ((t[0] != KFB_SKIP) | (t[1] != KFB_SKIP) | (t[2] != KFB_SKIP) | (t[3] != KFB_SKIP))
+                {
+                    update_quad<COUNT>(a, vp, __ldcs(vp), t, x0, y, z, n_upd);
+                    if (COUNT) { ++n_ld; ++n_st; }
+                }
+            }
+            continue;
+        }
+        // two-stage pipeline, unrolled by two so that the stages live in fixed registers
+        GenStage A, B;
+        gen_issue(a, g, xy, zz, vp, A);
+        for (int z = z0;; z += 2, vp += 2 * plane4)
+        {
+            const bool more1 = z + 1 <= z1;
+            if (more1) gen_issue(a, g, xy, zz, vp + plane4, B);
+            gen_process<COUNT>(a, g, wt, A, vp, x0, y, z, n_upd, n_st);
+            if (COUNT) ++n_ld;
+            if (!more1) break;
+            const bool more2 = z + 2 <= z1;
+            if (more2) gen_issue(a, g, xy, zz, vp + 2 * plane4, A);
+            gen_process<COUNT>(a, g, wt, B, vp + plane4, x0, y, z + 1, n_upd, n_st);
+            if (COUNT) ++n_ld;
+            if (!more2) break;
+        }
+    }
+    if (COUNT)
+    {
+        if (n_upd) atomicAdd(a.counter, (unsigned long long)n_upd);
+        if (n_ld) atomicAdd(a.counter + 2, (unsigned long long)n_ld);
+        if (n_st) atomicAdd(a.counter + 3, (unsigned long long)n_st);
+    }
+}
+
 // Conservative frustum planes for this launch (see CullPlane).  vc(x, y, z) = P0(x, y) + z * S in exact
 // arithmetic; the float running sum drifts from it by at most E = planes * 2^-24 * max|vc| per component.
 static void make_cull_planes(const kfb_ctx *ctx, const IntegrateArgs &a, CullPlane out[KFB_NCULL])
@@ -940,12 +1511,166 @@ int launch_build_tables(kfb_ctx *ctx, cudaStream_t stream)
     KFB_CUDA(ctx, cudaMemsetAsync(ctx->zexit, 0, sizeof(float), stream));
     dim3 b(32, 8), g((k.w + 31) / 32, (k.h + 7) / 8);
     build_tables_kernel<<<g, b, 0, stream>>>(ctx->L[0].depth, k.w, k.h, k.fx, k.fy, k.cx, k.cy, ctx->p.volu_trun_dist, ctx->tab_thrz,
-                                            ctx->tab_exact, ctx->zexit);
+                                            ctx->tab_exact, ctx->tab4, ctx->zexit);
     KFB_LAUNCH_CHECK(ctx);
     dim3 mg((k.w + 127) / 128, (k.h + 127) / 128);
     build_zmip_kernel<<<mg, 256, 0, stream>>>(ctx->tab_thrz, k.w, k.h, ctx->zmip, ctx->mip_off[0], ctx->mip_off[1], ctx->mip_off[2],
                                               ctx->mip_off[3], ctx->mip_off[4], ctx->mip_off[5]);
     KFB_LAUNCH_CHECK(ctx);
+    return KFB_OK;
+}
+
+// round-1 sweep: one kernel that decides and sweeps per warp and z-chunk (kept behind KFB_INTEGRATE_V1=1 as the
+// A/B partner of the planned sweep)
+static int launch_integrate_v1(kfb_ctx *ctx, IntegrateArgs &a, int planes, uint64_t *n_updated)
+{
+    // z-chunks give resident warps and load balance (the visited interval differs per column); the running
+    // sum at each chunk start comes from column_states_kernel, so chunks cost no replay.  48 B per thread per
+    // chunk of state: bounded to max(128 MB, 1/8 of the volume).  KFB_INTEGRATE_ZCHUNKS overrides for tuning.
+    const size_t nthr = (size_t)(a.X >> 2) * a.Y;
+    int zc = (planes + 15) / 16;
+    if (zc > 32) zc = 32;
+    const size_t state_cap = std::max((size_t)128 << 20, ctx->vol_voxels * sizeof(uint32_t) / 8); // <= 1/8 of the volume (measured: 1024^3 wants 32 chunks, 403 MB)
+    while (zc > 1 && (size_t)zc * 48 * nthr > state_cap) --zc;
+    if (const char *e = getenv("KFB_INTEGRATE_ZCHUNKS")) zc = atoi(e) > 0 ? atoi(e) : zc;
+    if (zc > planes) zc = planes;
+    a.zchunk = (planes + zc - 1) / zc;
+    a.nchunks = zc;
+    {
+        const size_t need = (size_t)zc * 48 * nthr + nthr * sizeof(int2);
+        if (need > ctx->states_bytes)
+        {
+            KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (ctx->states) cudaFree(ctx->states);
+            ctx->states = nullptr; ctx->states_bytes = 0;
+            KFB_CUDA(ctx, cudaMalloc(&ctx->states, need));
+            ctx->states_bytes = need;
+        }
+        a.states = ctx->states;
+        a.col_range = reinterpret_cast<int2 *>(ctx->states + (size_t)zc * 6 * nthr);
+        dim3 sb(32, 4), sg((a.X + 127) / 128, (a.Y + 3) / 4);
+        column_states_kernel<<<sg, sb, 0, ctx->stream>>>(a);
+        KFB_LAUNCH_CHECK(ctx);
+    }
+    dim3 block(32, KFB_INT_WARPS), grid((a.X + 4 * KFB_INT_WARPS * KFB_INT_PX - 1) / (4 * KFB_INT_WARPS * KFB_INT_PX), (a.Y + 32 / KFB_INT_PX - 1) / (32 / KFB_INT_PX), zc);
+    if (n_updated)
+    {
+        KFB_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
+        integrate_kernel<2, true><<<grid, block, 0, ctx->stream>>>(a);
+        KFB_LAUNCH_CHECK(ctx);
+        KFB_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, ctx->counters, sizeof(unsigned long long),
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+        KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *n_updated = ctx->counters_host[0];
+    }
+    else
+    {
+        if (ctx->profiling) cudaEventRecord(ctx->events[60], ctx->stream);
+        // planes per iteration of the general path: with the stages' loads batched and short chunks, one plane
+        // per iteration (fewest live registers) measured 2-3 % faster than two at 512^3, 1024^3 and 2048^3
+        const int U = getenv("KFB_INTEGRATE_U") ? atoi(getenv("KFB_INTEGRATE_U")) : 1;
+        if (U == 2) integrate_kernel<2, false><<<grid, block, 0, ctx->stream>>>(a);
+        else if (U == 4) integrate_kernel<4, false><<<grid, block, 0, ctx->stream>>>(a);
+        else integrate_kernel<1, false><<<grid, block, 0, ctx->stream>>>(a);
+        KFB_LAUNCH_CHECK(ctx);
+        if (ctx->profiling) cudaEventRecord(ctx->events[61], ctx->stream);
+    }
+    return KFB_OK;
+}
+
+// planned sweep: plan -> states of the general items -> general items || stream items
+static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, uint64_t *n_updated)
+{
+    a.zchunk = KFB_PLAN_ZCHUNK;
+    a.nchunks = (planes + a.zchunk - 1) / a.zchunk;
+    a.npx = (a.X + KFB_PATCH_X - 1) / KFB_PATCH_X;
+    a.npy = (a.Y + KFB_PATCH_Y - 1) / KFB_PATCH_Y;
+    a.mask_words = (a.nchunks + 31) / 32;
+    if (a.ze > 65535) { ctx->err = "volumes deeper than 65535 planes are not supported"; return KFB_ERR_UNSUPPORTED; }
+    const size_t npatch = (size_t)a.npx * a.npy, ncell = npatch * a.nchunks;
+    const size_t gcap = std::max<size_t>(4096, ncell / 4);
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_counts = 0, o_mask = 256, o_slot = o_mask + up(npatch * a.mask_words * 4), o_is = o_slot + up(ncell * 4),
+                 o_ig = o_is + up(ncell * 8), o_st = o_ig + up(ncell * 8), need = o_st + gcap * 192 * 8;
+    if (need > ctx->plan_bytes)
+    {
+        KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->plan_buf) cudaFree(ctx->plan_buf);
+        ctx->plan_buf = nullptr; ctx->plan_bytes = 0;
+        KFB_CUDA(ctx, cudaMalloc(&ctx->plan_buf, need));
+        ctx->plan_bytes = need;
+    }
+    char *pb = (char *)ctx->plan_buf;
+    a.plan_counts = (unsigned int *)(pb + o_counts);
+    a.patch_mask = (unsigned int *)(pb + o_mask);
+    a.slot_of = (unsigned int *)(pb + o_slot);
+    a.items_stream = (uint2 *)(pb + o_is);
+    a.items_general = (uint2 *)(pb + o_ig);
+    a.gstates = (unsigned long long *)(pb + o_st);
+    a.gstate_cap = (int)std::min<size_t>(gcap, 0x7fffffff);
+    KFB_CUDA(ctx, cudaMemsetAsync(pb, 0, o_slot, ctx->stream)); // counters + masks
+    if (n_updated) KFB_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    integrate_plan_kernel<<<(unsigned)((ncell + 127) / 128), 128, 0, ctx->stream>>>(a);
+    KFB_LAUNCH_CHECK(ctx);
+    integrate_states_kernel<<<(unsigned)((npatch + 3) / 4), 128, 0, ctx->stream>>>(a);
+    KFB_LAUNCH_CHECK(ctx);
+    if (ctx->profiling) cudaEventRecord(ctx->events[60], ctx->stream);
+    const bool smem = a.max_weight < KFB_WTAB_SMEM;
+    // The general items are latency- and issue-bound and move few bytes, the stream items are bandwidth-bound: side
+    // by side on two streams they fill each other's gaps (KFB_INTEGRATE_SERIAL=1: one after the other).  The stream
+    // kernel is persistent with half an SM's warp slots; the general kernel gets about one block per four items
+    // (sized from the previous frame's count; it strides, so any grid is correct) and takes whatever the SMs have
+    // left, all of them once the stream items are done.
+    const bool overlap = !getenv("KFB_INTEGRATE_SERIAL");
+    const int gs = ctx->sm_count * (overlap ? 4 : 8);
+    int gg = ctx->sm_count * KFB_GEN_MINB;
+    if (overlap)
+    {
+        const size_t hint = ctx->plan_hint_host ? (size_t)ctx->plan_hint_host[1] : 0; // last frame's general items
+        const size_t want = (hint + hint / 4 + 3) / 4;
+        gg = (int)std::min<size_t>(std::max<size_t>(want, (size_t)gg), std::max<size_t>((ncell + 3) / 4, 1));
+    }
+    cudaStream_t gstr = ctx->stream;
+    if (overlap)
+    {
+        KFB_CUDA(ctx, cudaEventRecord(ctx->ev_ifork, ctx->stream));
+        KFB_CUDA(ctx, cudaStreamWaitEvent(ctx->istream, ctx->ev_ifork, 0));
+        gstr = ctx->istream;
+    }
+    if (n_updated)
+    {
+        if (smem) integrate_general_kernel<true, true><<<gg, 128, 0, gstr>>>(a);
+        else integrate_general_kernel<true, false><<<gg, 128, 0, gstr>>>(a);
+        KFB_LAUNCH_CHECK(ctx);
+        if (smem) integrate_stream_kernel<true, true><<<gs, 128, 0, ctx->stream>>>(a);
+        else integrate_stream_kernel<true, false><<<gs, 128, 0, ctx->stream>>>(a);
+        KFB_LAUNCH_CHECK(ctx);
+    }
+    else
+    {
+        if (smem) integrate_general_kernel<false, true><<<gg, 128, 0, gstr>>>(a);
+        else integrate_general_kernel<false, false><<<gg, 128, 0, gstr>>>(a);
+        KFB_LAUNCH_CHECK(ctx);
+        if (smem) integrate_stream_kernel<false, true><<<gs, 128, 0, ctx->stream>>>(a);
+        else integrate_stream_kernel<false, false><<<gs, 128, 0, ctx->stream>>>(a);
+        KFB_LAUNCH_CHECK(ctx);
+    }
+    if (overlap)
+    {
+        KFB_CUDA(ctx, cudaEventRecord(ctx->ev_ijoin, ctx->istream));
+        KFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_ijoin, 0));
+    }
+    if (ctx->profiling) cudaEventRecord(ctx->events[61], ctx->stream);
+    // item counts of this frame -> pinned host memory, read (one frame late, unsynchronised) as the next grid hint
+    if (ctx->plan_hint_host)
+        KFB_CUDA(ctx, cudaMemcpyAsync(ctx->plan_hint_host, a.plan_counts, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_updated)
+    {
+        KFB_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, ctx->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        KFB_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host + 4, a.plan_counts, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *n_updated = ctx->counters_host[0];
+    }
     return KFB_OK;
 }
 
@@ -997,56 +1722,16 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
 
     const int planes = a.ze - a.zb;
     if (planes <= 0) return KFB_OK;
-    // z-chunks give resident warps and load balance (the visited interval differs per column); the running
-    // sum at each chunk start comes from column_states_kernel, so chunks cost no replay.  48 B per thread per
-    // chunk of state: bounded to max(128 MB, 1/8 of the volume).  KFB_INTEGRATE_ZCHUNKS overrides for tuning.
-    const size_t nthr = (size_t)(a.X >> 2) * a.Y;
-    int zc = (planes + 15) / 16;
-    if (zc > 32) zc = 32;
-    const size_t state_cap = std::max((size_t)128 << 20, ctx->vol_voxels * sizeof(uint32_t) / 8); // <= 1/8 of the volume (measured: 1024^3 wants 32 chunks, 403 MB)
-    while (zc > 1 && (size_t)zc * 48 * nthr > state_cap) --zc;
-    if (const char *e = getenv("KFB_INTEGRATE_ZCHUNKS")) zc = atoi(e) > 0 ? atoi(e) : zc;
-    if (zc > planes) zc = planes;
-    a.zchunk = (planes + zc - 1) / zc;
-    a.nchunks = zc;
+    a.tab4 = ctx->tab4;
+    if (!getenv("KFB_INTEGRATE_V1"))
     {
-        const size_t need = (size_t)zc * 48 * nthr + nthr * sizeof(int2);
-        if (need > ctx->states_bytes)
-        {
-            KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            if (ctx->states) cudaFree(ctx->states);
-            ctx->states = nullptr; ctx->states_bytes = 0;
-            KFB_CUDA(ctx, cudaMalloc(&ctx->states, need));
-            ctx->states_bytes = need;
-        }
-        a.states = ctx->states;
-        a.col_range = reinterpret_cast<int2 *>(ctx->states + (size_t)zc * 6 * nthr);
-        dim3 sb(32, 4), sg((a.X + 127) / 128, (a.Y + 3) / 4);
-        column_states_kernel<<<sg, sb, 0, ctx->stream>>>(a);
-        KFB_LAUNCH_CHECK(ctx);
-    }
-    dim3 block(32, KFB_INT_WARPS), grid((a.X + 4 * KFB_INT_WARPS * KFB_INT_PX - 1) / (4 * KFB_INT_WARPS * KFB_INT_PX), (a.Y + 32 / KFB_INT_PX - 1) / (32 / KFB_INT_PX), zc);
-    if (n_updated)
-    {
-        KFB_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
-        integrate_kernel<2, true><<<grid, block, 0, ctx->stream>>>(a);
-        KFB_LAUNCH_CHECK(ctx);
-        KFB_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, ctx->counters, sizeof(unsigned long long),
-                                      cudaMemcpyDeviceToHost, ctx->stream));
-        KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        *n_updated = ctx->counters_host[0];
+        const int rcp = launch_integrate_planned(ctx, a, planes, n_updated);
+        if (rcp) return rcp;
     }
     else
     {
-        if (ctx->profiling) cudaEventRecord(ctx->events[60], ctx->stream);
-        // planes per iteration of the general path: with the stages' loads batched and short chunks, one plane
-        // per iteration (fewest live registers) measured 2-3 % faster than two at 512^3, 1024^3 and 2048^3
-        const int U = getenv("KFB_INTEGRATE_U") ? atoi(getenv("KFB_INTEGRATE_U")) : 1;
-        if (U == 2) integrate_kernel<2, false><<<grid, block, 0, ctx->stream>>>(a);
-        else if (U == 4) integrate_kernel<4, false><<<grid, block, 0, ctx->stream>>>(a);
-        else integrate_kernel<1, false><<<grid, block, 0, ctx->stream>>>(a);
-        KFB_LAUNCH_CHECK(ctx);
-        if (ctx->profiling) cudaEventRecord(ctx->events[61], ctx->stream);
+        const int rc1 = launch_integrate_v1(ctx, a, planes, n_updated);
+        if (rc1) return rc1;
     }
     KFB_CUDA(ctx, cudaEventRecord(ctx->ev_tables_free, ctx->stream)); // the next frame's tables may now be built
     const int rcd = launch_brick_distance(ctx);

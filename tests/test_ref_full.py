@@ -101,13 +101,27 @@ def _pose_err(a, b):
 @pytest.mark.parametrize("dims,frames", [(256, 100), (512, 300)])
 def test_sequence_pose_parity_vs_reference_loop(kfo, kfb, kref, dims, frames):
     """BASELINE configs[0] / configs[1]: the product's frame loop (C++ facade) against the reference's kernels
-    under the reference's frame loop (oracle/ref_harness.cu ref_kinfu_*), same raw frames, every frame."""
+    under the reference's frame loop (oracle/ref_harness.cu ref_kinfu_*), same raw frames, EVERY frame of the
+    sequence, against north_star's per-frame budget of 1e-4 m / 1e-4 rad.
+
+    Per-frame means: both sides process frame k from the same state.  KinectFusion's closed loop amplifies any
+    perturbation -- a 1 mm change of ONE pixel of ONE frame moves the oracle's own trajectory by more than a
+    millimetre sixty frames later (tests/test_oracle.py::test_closed_loop_sensitivity) -- so two free-running
+    implementations that differ in the last bit of the bilateral filter cannot stay within 0.1 mm of each other
+    for 300 frames, whatever their quality.  Hence lock-step: after every frame the reference loop adopts the
+    product's state (volume, model maps, pose; device-to-device, ref_kinfu_sync_from) and the NEXT frame's pose
+    is compared.  A free-running pair is tracked alongside and reported, with a loose bound (two voxels)."""
     Ko = kfo.intr()
     Kb = kfb.Intrinsics(**kfb.SENSORS["kinect1"])
     hp = kfb.default_host_params(dims)
+    volpose = np.array(hp.volu_pose, np.float32)
     ours = kfb.KinectFusion(Kb, hp)
-    ref = kref.RefKinfu(Kb, dims, np.array(hp.volu_pose, np.float32))
+    ref = kref.RefKinfu(Kb, dims, volpose)
+    ours_free = kfb.KinectFusion(Kb, kfb.default_host_params(dims))
+    ref_free = kref.RefKinfu(Kb, dims, volpose)
+    ctx = ours.context()
     worst = (0.0, 0.0, -1)
+    free_worst = (0.0, -1)
     for k in range(frames):
         d = kfo.render_depth_mm(kfo.trajectory_pose(k), Ko)
         assert ours.pipeline(d) == 0, k
@@ -115,8 +129,18 @@ def test_sequence_pose_parity_vs_reference_loop(kfo, kfb, kref, dims, frames):
         dt, dr = _pose_err(ours.pose(), ref.pose())
         if max(dt, dr) > max(worst[0], worst[1]):
             worst = (dt, dr, k)
-    print("worst frame %d of %d at %d^3: |dt| = %.3g m, angle = %.3g rad" % (worst[2], frames, dims, worst[0], worst[1]))
+        ctx.synchronize()
+        ref.sync_from(ctx.device_ptr(0), ctx.device_ptr(1), ctx.device_ptr(2), ours.pose(), ours.frame_count)
+        assert ours_free.pipeline(d) == 0 and ref_free.pipeline(d) == 0, k
+        fdt, _ = _pose_err(ours_free.pose(), ref_free.pose())
+        if fdt > free_worst[0]:
+            free_worst = (fdt, k)
+    voxel = 3.0 / dims
+    print("%d frames at %d^3, lock-step: worst frame %d, |dt| = %.3g m, angle = %.3g rad; free-running pair: worst |dt| = %.3g m "
+          "(%.2f voxels) at frame %d" % (frames, dims, worst[2], worst[0], worst[1], free_worst[0], free_worst[0] / voxel, free_worst[1]))
     assert worst[0] < 1e-4 and worst[1] < 1e-4, worst
-    # both reached the weight cap on the way at 300 frames
+    assert free_worst[0] < 2 * voxel, free_worst
+    # the lock-step product instance IS a free-running product run (nothing was ever written into it)
+    assert np.array_equal(ours.pose(), ours_free.pose())
     if frames > 64:
         assert ours.context().download_volume()[..., 1].max() == 64

@@ -1,0 +1,68 @@
+"""Timing A/B of the integrate variants inside the pipelined frame sequence (profiling events: sweep kernels
+60/61, whole call 56/57), and a bit-for-bit comparison of the resulting volumes.  Variants are switched through
+the library's environment switches, which are read at every launch.
+    python tools/integrate_ab.py [dims] [frames]"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import slam_kinectfusion_b200 as kfb  # noqa: E402
+from slam_kinectfusion_b200 import synth  # noqa: E402
+
+VARIANTS = {
+    "v1 (round-1 kernel)": {"KFB_INTEGRATE_V1": "1"},
+    "planned, serial": {"KFB_INTEGRATE_SERIAL": "1"},
+    "planned, two streams": {},
+}
+
+
+def main():
+    dims = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 28
+    K = kfb.Intrinsics(**kfb.SENSORS["kinect1"])
+    frames = synth.sequence(n, K)
+    dev = torch.stack([torch.from_numpy(d) for _, d in frames]).cuda()
+    hp = kfb.default_host_params(dims)
+    kf = kfb.KinectFusion(K, hp)
+    ctx = kf.context()
+    ctx.set_profiling(True)
+    digests = {}
+    for name, env in VARIANTS.items():
+        for k in ("KFB_INTEGRATE_V1", "KFB_INTEGRATE_SERIAL"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        kf.reset()
+        k_ms, c_ms, f_ms = [], [], []
+        for i in range(n):
+            if i == 8:
+                ctx.synchronize()
+                ctx.event_record(0)
+            assert kf.pipeline_ptr(dev[i].data_ptr(), K.width, K.height) == 0
+            if i >= 8 and i % 4 == 3:
+                ctx.synchronize()
+                k_ms.append(ctx.event_elapsed_ms(60, 61))
+                c_ms.append(ctx.event_elapsed_ms(56, 57))
+        ctx.event_record(1)
+        ctx.synchronize()
+        vol = ctx.download_volume()
+        digests[name] = hashlib.sha1(vol.tobytes()).hexdigest()
+        # counts at the last pose
+        ctx.upload_depth_mm_ptr(dev[n - 1].data_ptr(), K.width, K.height)
+        ctx.frontend()
+        P = np.vstack([kf.pose().astype(np.float64).reshape(3, 4), [0, 0, 0, 1]])
+        V = np.vstack([np.array(hp.volu_pose, np.float64).reshape(3, 4), [0, 0, 0, 1]])
+        U = ctx.integrate((np.linalg.inv(P) @ V)[:3].astype(np.float32).reshape(12), count=True)
+        cnt = ctx.integrate_counts() if "v1" not in name else {}
+        print(f"{name:24s} sweep {np.mean(k_ms) * 1e3:7.1f} us  call {np.mean(c_ms) * 1e3:7.1f} us  U {U}  "
+              f"8U/t {8 * U / np.mean(k_ms) / 1e6:7.1f} GB/s  {cnt}  sha1 {digests[name][:12]}", flush=True)
+    assert len(set(digests.values())) == 1, digests
+    print("volumes identical across variants")
+
+
+if __name__ == "__main__":
+    main()
