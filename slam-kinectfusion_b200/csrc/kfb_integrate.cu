@@ -37,6 +37,7 @@
 // Side product for the raycaster: a voxel that turns negative marks the 8^3 bricks within two voxels of it in
 // a byte map; three separable passes turn the map into the brick distance field kfb_raycast.cu skips with.
 #include "kfb_common.cuh"
+#include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -44,6 +45,7 @@
 
 namespace kfb
 {
+namespace cg = cooperative_groups;
 
 struct CullPlane // conservative half-line in z: g0(x, y) + z * g1 >= 0
 {
@@ -1330,8 +1332,8 @@ __device__ __forceinline__ void gen_process(const IntegrateArgs &a, const GenCon
 #ifndef KFB_GEN_MINB
 #define KFB_GEN_MINB 5 // blocks of 4 warps per SM the register budget is sized for (<= 96 registers)
 #endif
-template <bool COUNT, bool SMEM>
-__global__ void __launch_bounds__(128, KFB_GEN_MINB) integrate_general_kernel(const IntegrateArgs a)
+template <bool COUNT, bool SMEM, int MINB>
+__global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const IntegrateArgs a)
 {
     __shared__ float4 s_wt[SMEM ? KFB_WTAB_SMEM : 1];
     if (SMEM)
@@ -1444,17 +1446,114 @@ __global__ void __launch_bounds__(128, KFB_GEN_MINB) integrate_general_kernel(co
             }
             continue;
         }
-        // two-stage pipeline, unrolled by two so that the stages live in fixed registers
+        // ---- per-thread refinement of the item's plane range -------------------------------------------------
+        // The plan decided for the whole 16 x 8 patch; a thread's four columns see a far smaller part of the image
+        // (a few pixels), so its own free-space prefix [z0, fe_t] is longer and its own occlusion cut zb_t earlier
+        // (same proofs as in the plan, with this thread's running sums after plane z0 - 1 as the affine base).
+        // Each thread then walks its planes on its own: a cheap phase (tsdf = 1, no projection) and the full
+        // per-voxel phase only on the planes in between -- for a surface seen at a grazing angle that is the
+        // depth variation over the thread's few pixels instead of over the patch's footprint.
+        int fe_t = z0 - 1, zb_t = z1;
+        if (a.Sz > 1e-6f)
+        {
+            float ax, ay, bx_, by_, c0, c1, c2, c3;
+            unpack2(xy[0], ax, ay);
+            unpack2(xy[3], bx_, by_);
+            unpack2(zz[0], c0, c1);
+            unpack2(zz[1], c2, c3);
+            float umin = 1e30f, umax = -1e30f, vmin = 1e30f, vmax = -1e30f, zmin = 1e30f;
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+            {
+                const float zf = e ? (float)(z1 - z0 + 1) : 1.f; // planes z0 and z1, counted from the base plane z0 - 1
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                {
+                    const float X = fmaf(zf, a.Sx, k ? bx_ : ax), Y = fmaf(zf, a.Sy, k ? by_ : ay), Zc = fmaf(zf, a.Sz, k ? c3 : c0);
+                    const float r = mufu_rcp(fmaxf(Zc, 1e-3f));
+                    const float u = fmaf(a.fx * X, r, a.cx), v = fmaf(a.fy * Y, r, a.cy);
+                    umin = fminf(umin, u); umax = fmaxf(umax, u);
+                    vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+                    zmin = fminf(zmin, Zc);
+                }
+            }
+            if (zmin > 0.05f)
+            {
+                const float pad = 1.5f + (a.fx + a.fy + (float)(a.w + a.h)) * a.driftE * (1.001f * mufu_rcp(zmin));
+                const bool all_inside = umin - pad >= 0.f && umax + pad <= (float)(a.w - 1) && vmin - pad >= 0.f && vmax + pad <= (float)(a.h - 1);
+                const int u0 = max((int)floorf(fmaxf(umin - pad, -1e6f)), 0), u1 = min((int)ceilf(fminf(umax + pad, 1e6f)), a.w - 1);
+                const int v0 = max((int)floorf(fmaxf(vmin - pad, -1e6f)), 0), v1 = min((int)ceilf(fminf(vmax + pad, 1e6f)), a.h - 1);
+                if (u0 > u1 || v0 > v1) zb_t = z0 - 1; // never inside the image on these planes
+                else
+                {
+                    const int span = max(u1 - u0, v1 - v0) + 1;
+                    const int l = max(32 - __clz(span - 1) - 2, 2);
+                    if (l <= 7)
+                    {
+                        const float2 *m = a.zmip + a.mip_off[l - 2];
+                        const int mw = a.mip_w[l - 2];
+                        const int tx0 = u0 >> l, tx1 = u1 >> l, ty1 = v1 >> l;
+                        float2 q = make_float2(-1.f, 3.0e38f);
+                        for (int ty = v0 >> l; ty <= ty1; ++ty)
+                        {
+                            float2 tl[5]; // a row of tiles in flight (the rectangle is at most 5 tiles wide)
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) tl[i] = __ldg(m + ty * mw + min(tx0 + i, tx1));
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) q = mm2(q, tl[i]);
+                        }
+                        const float zmin0 = fminf(c0, c3), zmax0 = fmaxf(c0, c3), e2 = 2.f * a.driftE;
+                        const float zc = (q.x + e2 - zmin0) * a.invSz + 1.f;
+                        zb_t = min(z1, z0 - 1 + (int)ceilf(fminf(zc, 1e6f)));
+                        if (all_inside && !a.no_fastpath)
+                        {
+                            int zf = min(zb_t - (z0 - 1), (int)floorf(fminf(fmaxf((q.y - e2 - zmax0) * a.invSz, -1.f), 1e6f)));
+#pragma unroll
+                            for (int i = 0; i < 2; ++i)
+                                if (zf >= 1 && fmaf((float)zf, a.Sz, zmax0) + e2 > q.y) --zf;
+                            if (zf >= 1 && fmaf((float)zf, a.Sz, zmax0) + e2 <= q.y) fe_t = z0 - 1 + zf;
+                        }
+                    }
+                }
+            }
+        }
+        // ---- cheap phase: planes z0 .. fe_t are deep free space for this thread's four columns -----------------------
+        int z = z0;
+        for (; z <= fe_t; z += 4, vp += 4 * plane4)
+        {
+            uint4 w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (z + i <= fe_t) w[i] = __ldcs(vp + i * plane4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (z + i <= fe_t)
+                {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) xy[k] = ffma2(g.vs2, g.sxy, xy[k]);
+                    zz[0] = ffma2(g.vs2, g.szz, zz[0]);
+                    zz[1] = ffma2(g.vs2, g.szz, zz[1]);
+                    update_free_quad<COUNT>(a, wt, vp + i * plane4, w[i], n_upd, n_st);
+                    if (COUNT) ++n_ld;
+                }
+        }
+        if (fe_t >= z0)
+        {
+            vp -= (size_t)(z - (fe_t + 1)) * plane4; // the loop stepped past fe_t in units of four planes
+            z = fe_t + 1;
+        }
+        if (z > zb_t) continue;
+        // ---- full phase: two-stage pipeline, unrolled by two so that the stages live in fixed registers ----------------
         GenStage A, B;
         gen_issue(a, g, xy, zz, vp, A);
-        for (int z = z0;; z += 2, vp += 2 * plane4)
+        for (;; z += 2, vp += 2 * plane4)
         {
-            const bool more1 = z + 1 <= z1;
+            const bool more1 = z + 1 <= zb_t;
             if (more1) gen_issue(a, g, xy, zz, vp + plane4, B);
             gen_process<COUNT>(a, g, wt, A, vp, x0, y, z, n_upd, n_st);
             if (COUNT) ++n_ld;
             if (!more1) break;
-            const bool more2 = z + 2 <= z1;
+            const bool more2 = z + 2 <= zb_t;
             if (more2) gen_issue(a, g, xy, zz, vp + 2 * plane4, A);
             gen_process<COUNT>(a, g, wt, B, vp + plane4, x0, y, z + 1, n_upd, n_st);
             if (COUNT) ++n_ld;
@@ -1622,13 +1721,15 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
     // (sized from the previous frame's count; it strides, so any grid is correct) and takes whatever the SMs have
     // left, all of them once the stream items are done.
     const bool overlap = !getenv("KFB_INTEGRATE_SERIAL");
-    const int gs = ctx->sm_count * (overlap ? 4 : 8);
-    int gg = ctx->sm_count * KFB_GEN_MINB;
-    if (overlap)
+    int gs = ctx->sm_count * 8, gg = ctx->sm_count * KFB_GEN_MINB;
+    if (!getenv("KFB_INTEGRATE_PERSISTENT"))
     {
-        const size_t hint = ctx->plan_hint_host ? (size_t)ctx->plan_hint_host[1] : 0; // last frame's general items
-        const size_t want = (hint + hint / 4 + 3) / 4;
-        gg = (int)std::min<size_t>(std::max<size_t>(want, (size_t)gg), std::max<size_t>((ncell + 3) / 4, 1));
+        // about one warp per item, sized from the previous frame's counts (both kernels stride, so any grid is
+        // correct): the block scheduler balances the two kernels over whatever the SMs have free
+        const size_t hs = ctx->plan_hint_host ? (size_t)ctx->plan_hint_host[0] : 0, hg = ctx->plan_hint_host ? (size_t)ctx->plan_hint_host[1] : 0;
+        const size_t cap = std::max<size_t>((ncell + 3) / 4, 1);
+        gs = (int)std::min<size_t>(std::max<size_t>((hs + hs / 4 + 3) / 4, (size_t)gs), cap);
+        gg = (int)std::min<size_t>(std::max<size_t>((hg + hg / 4 + 3) / 4, (size_t)gg), cap);
     }
     cudaStream_t gstr = ctx->stream;
     if (overlap)
@@ -1639,8 +1740,8 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
     }
     if (n_updated)
     {
-        if (smem) integrate_general_kernel<true, true><<<gg, 128, 0, gstr>>>(a);
-        else integrate_general_kernel<true, false><<<gg, 128, 0, gstr>>>(a);
+        if (smem) integrate_general_kernel<true, true, KFB_GEN_MINB><<<gg, 128, 0, gstr>>>(a);
+        else integrate_general_kernel<true, false, KFB_GEN_MINB><<<gg, 128, 0, gstr>>>(a);
         KFB_LAUNCH_CHECK(ctx);
         if (smem) integrate_stream_kernel<true, true><<<gs, 128, 0, ctx->stream>>>(a);
         else integrate_stream_kernel<true, false><<<gs, 128, 0, ctx->stream>>>(a);
@@ -1648,8 +1749,11 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
     }
     else
     {
-        if (smem) integrate_general_kernel<false, true><<<gg, 128, 0, gstr>>>(a);
-        else integrate_general_kernel<false, false><<<gg, 128, 0, gstr>>>(a);
+        const int minb = getenv("KFB_GEN_MINB") ? atoi(getenv("KFB_GEN_MINB")) : KFB_GEN_MINB; // register budget variant (tuning)
+        if (!smem) integrate_general_kernel<false, false, KFB_GEN_MINB><<<gg, 128, 0, gstr>>>(a);
+        else if (minb == 4) integrate_general_kernel<false, true, 4><<<gg, 128, 0, gstr>>>(a);
+        else if (minb == 6) integrate_general_kernel<false, true, 6><<<gg, 128, 0, gstr>>>(a);
+        else integrate_general_kernel<false, true, 5><<<gg, 128, 0, gstr>>>(a);
         KFB_LAUNCH_CHECK(ctx);
         if (smem) integrate_stream_kernel<false, true><<<gs, 128, 0, ctx->stream>>>(a);
         else integrate_stream_kernel<false, false><<<gs, 128, 0, ctx->stream>>>(a);
@@ -1808,9 +1912,74 @@ __global__ void brick_distance_kernel(const uint8_t *__restrict__ src, uint8_t *
     dst[i] = (uint8_t)best;
 }
 
+// The three passes in ONE cooperative launch (a grid-wide barrier between passes): a frame whose sweep activated
+// no new brick -- nearly every frame once the scene has been seen -- pays one early-exit launch instead of three
+// and a memset.  `dirty` is read by every block before the first barrier and cleared after the last one.
+__device__ __forceinline__ void brick_pass(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int bx, int by, int bz, int axis, int from_flags,
+                                           int first, int stride)
+{
+    const int n = bx * by * bz;
+    for (int i = first; i < n; i += stride)
+    {
+        const int x = i % bx, y = (i / bx) % by, z = i / (bx * by);
+        const int pos = axis == 0 ? x : (axis == 1 ? y : z);
+        const int len = axis == 0 ? bx : (axis == 1 ? by : bz);
+        const int st = axis == 0 ? 1 : (axis == 1 ? bx : bx * by);
+        int best = KFB_BDIST_CAP;
+        const int j0 = max(-KFB_BDIST_CAP, -pos), j1 = min(KFB_BDIST_CAP, len - 1 - pos);
+        for (int j = j0; j <= j1; ++j)
+        {
+            int v = __ldcg(src + i + j * st); // L2: written by other blocks before the grid barrier
+            if (from_flags) v = v ? 0 : KFB_BDIST_CAP;
+            best = min(best, max(v, abs(j)));
+        }
+        dst[i] = (uint8_t)best;
+    }
+}
+__global__ void __launch_bounds__(256) brick_distance_fused_kernel(const uint8_t *flags, uint8_t *tmp, uint8_t *tmp2, uint8_t *dist, int bx, int by,
+                                                                   int bz, int *dirty)
+{
+    if (*(volatile int *)dirty == 0) return; // same answer in every block (see above)
+    cg::grid_group grid = cg::this_grid();
+    const int first = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    brick_pass(flags, tmp, bx, by, bz, 0, 1, first, stride);
+    grid.sync();
+    brick_pass(tmp, tmp2, bx, by, bz, 1, 0, first, stride);
+    grid.sync();
+    brick_pass(tmp2, dist, bx, by, bz, 2, 0, first, stride);
+    grid.sync();
+    if (first == 0) *dirty = 0;
+}
+
 int launch_brick_distance(kfb_ctx *ctx)
 {
     const int n = ctx->bdim[0] * ctx->bdim[1] * ctx->bdim[2];
+    if (!getenv("KFB_BRICKS_3PASS"))
+    {
+        if (ctx->bdist_grid == 0)
+        {
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, brick_distance_fused_kernel, 256, 0) != cudaSuccess || per_sm < 1)
+            {
+                (void)cudaGetLastError();
+                ctx->bdist_grid = -1;
+            }
+            else ctx->bdist_grid = per_sm * ctx->sm_count;
+        }
+        if (ctx->bdist_grid > 0)
+        {
+            const int blocks = std::min(ctx->bdist_grid, (n + 255) / 256);
+            const uint8_t *flags = ctx->bricks;
+            uint8_t *tmp = ctx->bdist_tmp, *tmp2 = ctx->bdist_tmp2, *dist = ctx->bdist;
+            int bx = ctx->bdim[0], by = ctx->bdim[1], bz = ctx->bdim[2];
+            int *dirty = ctx->bdirty;
+            void *kargs[] = {(void *)&flags, (void *)&tmp, (void *)&tmp2, (void *)&dist, (void *)&bx, (void *)&by, (void *)&bz, (void *)&dirty};
+            const cudaError_t le = cudaLaunchCooperativeKernel((const void *)brick_distance_fused_kernel, dim3(blocks), dim3(256), kargs, 0, ctx->stream);
+            if (le == cudaSuccess) { ctx->launches++; return KFB_OK; }
+            (void)cudaGetLastError();
+            ctx->bdist_grid = -1; // no cooperative launches on this device / partition: three ordinary passes from now on
+        }
+    }
     const int blocks = (n + 255) / 256;
     brick_distance_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bricks, ctx->bdist_tmp, ctx->bdim[0], ctx->bdim[1], ctx->bdim[2], 0, ctx->bdirty, 1);
     KFB_LAUNCH_CHECK(ctx);

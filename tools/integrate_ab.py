@@ -17,8 +17,13 @@ from slam_kinectfusion_b200 import synth  # noqa: E402
 VARIANTS = {
     "v1 (round-1 kernel)": {"KFB_INTEGRATE_V1": "1"},
     "planned, serial": {"KFB_INTEGRATE_SERIAL": "1"},
-    "planned, two streams": {},
+    "planned, persistent": {"KFB_INTEGRATE_PERSISTENT": "1"},
+    "planned minb4": {"KFB_GEN_MINB": "4"},
+    "planned minb6": {"KFB_GEN_MINB": "6"},
+    "planned 3-pass bricks": {"KFB_BRICKS_3PASS": "1"},
+    "planned (default)": {},
 }
+SWITCHES = ("KFB_INTEGRATE_V1", "KFB_INTEGRATE_SERIAL", "KFB_INTEGRATE_PERSISTENT", "KFB_GEN_MINB", "KFB_BRICKS_3PASS")
 
 
 def main():
@@ -33,7 +38,7 @@ def main():
     ctx.set_profiling(True)
     digests = {}
     for name, env in VARIANTS.items():
-        for k in ("KFB_INTEGRATE_V1", "KFB_INTEGRATE_SERIAL"):
+        for k in SWITCHES:
             os.environ.pop(k, None)
         os.environ.update(env)
         kf.reset()
