@@ -29,6 +29,7 @@ SWITCHES = ("KFB_INTEGRATE_V1", "KFB_INTEGRATE_SERIAL", "KFB_INTEGRATE_PERSISTEN
 def main():
     dims = int(sys.argv[1]) if len(sys.argv) > 1 else 512
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 28
+    only = sys.argv[3] if len(sys.argv) > 3 else None      # run a single variant (profiler runs)
     K = kfb.Intrinsics(**kfb.SENSORS["kinect1"])
     frames = synth.sequence(n, K)
     dev = torch.stack([torch.from_numpy(d) for _, d in frames]).cuda()
@@ -38,6 +39,8 @@ def main():
     ctx.set_profiling(True)
     digests = {}
     for name, env in VARIANTS.items():
+        if only and only not in name:
+            continue
         for k in SWITCHES:
             os.environ.pop(k, None)
         os.environ.update(env)
