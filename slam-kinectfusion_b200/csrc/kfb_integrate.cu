@@ -1227,39 +1227,30 @@ __global__ void __launch_bounds__(128, 8) integrate_stream_kernel(const Integrat
 }
 
 // ---- general items: the reference's per-voxel arithmetic, software-pipelined over the planes ----------------------
-// A plane of a thread between "loads issued" and "classified and updated" lives in two places: vc.z and |vc|^2 of
-// its four voxels in registers (GenRegs), the four voxels themselves and the four table entries in shared memory,
-// brought there by cp.async (LDGSTS).  The asynchronous copies are what makes the pipeline real: a register-staged
-// version left it to ptxas whether the loads of plane z + 1 share a scoreboard with those of plane z (they did: a
-// plane cost two full memory latencies, profiles/r02_v1_*), and it needed 96 registers.
-struct GenRegs
+// One plane of one thread: every load the plane needs -- the voxel quad (unconditionally: inside a thread's plane
+// range nearly every quad is updated) and one 16-byte table entry per voxel -- is issued before the first use, so a
+// plane costs ONE memory latency (the round-1 sweep paid thresholds -> exact depth -> voxels -> weight table in
+// turn).  Tried and dropped (profiles/README.md, r02 integrate experiments): a two-stage software pipeline with the
+// next plane's loads in flight, register-staged (96-128 registers: the lost occupancy cost more than the overlap
+// gained, and ptxas put both stages' loads on one scoreboard) and cp.async-staged through shared memory (slower
+// still).  This path lives on thread-level parallelism: 64 registers, 32 warps per SM.
+struct GenStage
 {
-    float cz[4]; // vc.z per voxel (+inf: projects outside the image)
-    float d2[4]; // |vc|^2 as the reference computes it (for the band)
+    float cz[4];   // vc.z per voxel (+inf: projects outside the image)
+    float d2[4];   // |vc|^2 as the reference computes it (for the band)
+    float4 tb[4];  // {hi_z, lo_z, depth, 1/lambda} of the pixel each voxel lands on
+    uint4 word;    // the four voxels
 };
-#define KFB_GEN_SLOTS 5 // 16-byte slots per thread and stage: the voxel quad, then {hi_z, lo_z, depth, 1/lambda} of each voxel's pixel
-__device__ __forceinline__ void cp_async16_cg(void *smem, const void *gmem)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async16_ca(void *smem, const void *gmem)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 struct GenConst
 {
     unsigned long long vs2, sxy, szz, fxy, cxy, magic2;
     unsigned int last_pix;
     float rtrunc;
 };
-// stage = this thread's first slot of the stage (slots are 128 threads apart)
 __device__ __forceinline__ void gen_issue(const IntegrateArgs &a, const GenConst &g, unsigned long long xy[4], unsigned long long zz[2],
-                                          const uint4 *vp, GenRegs &s, uint4 *stage)
+                                          const uint4 *vp, GenStage &s)
 {
-    cp_async16_cg(stage, vp); // unconditional: inside a thread's plane range nearly every quad is updated
+    s.word = __ldcs(vp);
 #pragma unroll
     for (int k = 0; k < 4; ++k) xy[k] = ffma2(g.vs2, g.sxy, xy[k]);
     zz[0] = ffma2(g.vs2, g.szz, zz[0]);
@@ -1282,19 +1273,16 @@ __device__ __forceinline__ void gen_issue(const IntegrateArgs &a, const GenConst
         // an out-of-image voxel is classified as "behind everything": vc.z = +inf fails `<= hi_z` and passes
         // `> lo_z` for whatever (clamped) table entry it reads
         s.cz[k] = ok ? s.cz[k] : __int_as_float(0x7f800000);
-        cp_async16_ca(stage + (1 + k) * 128, a.tab4 + min((unsigned int)(vi * a.w + ui), g.last_pix));
+        s.tb[k] = __ldg(a.tab4 + min((unsigned int)(vi * a.w + ui), g.last_pix));
     }
-    cp_async_commit();
 }
 template <bool COUNT>
-__device__ __forceinline__ void gen_process(const IntegrateArgs &a, const GenConst &g, const float4 *__restrict__ wt, const GenRegs &s,
-                                            const uint4 *stage, uint4 *vp, int x0, int y, int z, unsigned int &n_upd, unsigned int &n_st)
+__device__ __forceinline__ void gen_process(const IntegrateArgs &a, const GenConst &g, const float4 *__restrict__ wt, const GenStage &s,
+                                            uint4 *vp, int x0, int y, int z, unsigned int &n_upd, unsigned int &n_st)
 {
     float t[4];
-    float4 tb[4];
+    const float4 *tb = s.tb;
     bool band = false;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) tb[k] = reinterpret_cast<const float4 *>(stage)[(1 + k) * 128];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
     {
@@ -1313,7 +1301,7 @@ __device__ __forceinline__ void gen_process(const IntegrateArgs &a, const GenCon
         }
     }
     if (!((t[0] != KFB_SKIP) | (t[1] != KFB_SKIP) | (t[2] != KFB_SKIP) | (t[3] != KFB_SKIP))) return;
-    const uint4 wd = stage[0];
+    const uint4 wd = s.word;
     uint4 o = wd;
     const unsigned int w0 = wd.x >> 16, w1 = wd.y >> 16, w2 = wd.z >> 16, w3 = wd.w >> 16, mw = (unsigned)a.max_weight;
     if ((wd.x == wd.y) & (wd.x == wd.z) & (wd.x == wd.w) & (t[0] == t[1]) & (t[0] == t[2]) & (t[0] == t[3]) & (w0 <= mw))
@@ -1350,20 +1338,18 @@ __device__ __forceinline__ void gen_process(const IntegrateArgs &a, const GenCon
 }
 
 #ifndef KFB_GEN_MINB
-#define KFB_GEN_MINB 5 // blocks of 4 warps per SM the register budget is sized for (<= 96 registers)
+#define KFB_GEN_MINB 8 // blocks of 4 warps per SM the register budget is sized for (64 registers)
 #endif
 template <bool COUNT, bool SMEM, int MINB>
 __global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const IntegrateArgs a)
 {
     __shared__ float4 s_wt[SMEM ? KFB_WTAB_SMEM : 1];
-    __shared__ uint4 s_stage[2 * KFB_GEN_SLOTS * 128]; // [stage][slot][thread]: conflict-free 16-byte accesses
     if (SMEM)
     {
         for (int i = threadIdx.x; i <= a.max_weight; i += blockDim.x) s_wt[i] = __ldg(a.wtab + i);
         __syncthreads();
     }
     const float4 *wt = SMEM ? s_wt : a.wtab;
-    uint4 *const stage0 = s_stage + threadIdx.x, *const stage1 = s_stage + KFB_GEN_SLOTS * 128 + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const unsigned int n_items = __ldg(a.plan_counts + 1);
     const size_t plane4 = ((size_t)a.X * a.Y) >> 2;
@@ -1565,23 +1551,13 @@ __global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const Inte
             z = fe_t + 1;
         }
         if (z > zb_t) continue;
-        // ---- full phase: two-stage cp.async pipeline, unrolled by two so that the stages live in fixed places ---------------
-        GenRegs A, B;
-        gen_issue(a, g, xy, zz, vp, A, stage0);
-        for (;; z += 2, vp += 2 * plane4)
+        // ---- full phase: the exact per-voxel predicate, one plane (one memory latency) at a time ---------------------------
+        for (; z <= zb_t; ++z, vp += plane4)
         {
-            const bool more1 = z + 1 <= zb_t;
-            if (more1) { gen_issue(a, g, xy, zz, vp + plane4, B, stage1); cp_async_wait<1>(); }
-            else cp_async_wait<0>();
-            gen_process<COUNT>(a, g, wt, A, stage0, vp, x0, y, z, n_upd, n_st);
+            GenStage S;
+            gen_issue(a, g, xy, zz, vp, S);
+            gen_process<COUNT>(a, g, wt, S, vp, x0, y, z, n_upd, n_st);
             if (COUNT) ++n_ld;
-            if (!more1) break;
-            const bool more2 = z + 2 <= zb_t;
-            if (more2) { gen_issue(a, g, xy, zz, vp + 2 * plane4, A, stage0); cp_async_wait<1>(); }
-            else cp_async_wait<0>();
-            gen_process<COUNT>(a, g, wt, B, stage1, vp + plane4, x0, y, z + 1, n_upd, n_st);
-            if (COUNT) ++n_ld;
-            if (!more2) break;
         }
     }
     if (COUNT)
@@ -1760,16 +1736,6 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
         KFB_CUDA(ctx, cudaStreamWaitEvent(ctx->istream, ctx->ev_ifork, 0));
         gstr = ctx->istream;
     }
-    if (!ctx->gen_attr_set)
-    {
-        // the general kernel stages its pipeline in shared memory (24.5 KB per block): ask for the large carve-out
-        cudaFuncSetAttribute(integrate_general_kernel<false, true, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(integrate_general_kernel<false, true, 5>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(integrate_general_kernel<false, true, 6>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(integrate_general_kernel<false, false, KFB_GEN_MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        (void)cudaGetLastError();
-        ctx->gen_attr_set = 1;
-    }
     // the running sums of the general items (FMA-pipe bound) run next to the stream items (bandwidth bound)
     integrate_states_kernel<<<(unsigned)((npatch + 3) / 4), 128, 0, gstr>>>(a);
     KFB_LAUNCH_CHECK(ctx);
@@ -1786,9 +1752,9 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
     {
         const int minb = getenv("KFB_GEN_MINB") ? atoi(getenv("KFB_GEN_MINB")) : KFB_GEN_MINB; // register budget variant (tuning)
         if (!smem) integrate_general_kernel<false, false, KFB_GEN_MINB><<<gg, 128, 0, gstr>>>(a);
-        else if (minb == 4) integrate_general_kernel<false, true, 4><<<gg, 128, 0, gstr>>>(a);
+        else if (minb == 5) integrate_general_kernel<false, true, 5><<<gg, 128, 0, gstr>>>(a);
         else if (minb == 6) integrate_general_kernel<false, true, 6><<<gg, 128, 0, gstr>>>(a);
-        else integrate_general_kernel<false, true, 5><<<gg, 128, 0, gstr>>>(a);
+        else integrate_general_kernel<false, true, 8><<<gg, 128, 0, gstr>>>(a);
         KFB_LAUNCH_CHECK(ctx);
         if (smem) integrate_stream_kernel<false, true><<<gs, 128, 0, ctx->stream>>>(a);
         else integrate_stream_kernel<false, false><<<gs, 128, 0, ctx->stream>>>(a);

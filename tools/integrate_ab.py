@@ -18,7 +18,7 @@ VARIANTS = {
     "v1 (round-1 kernel)": {"KFB_INTEGRATE_V1": "1"},
     "planned, serial": {"KFB_INTEGRATE_SERIAL": "1"},
     "planned, persistent": {"KFB_INTEGRATE_PERSISTENT": "1"},
-    "planned minb4": {"KFB_GEN_MINB": "4"},
+    "planned minb5": {"KFB_GEN_MINB": "5"},
     "planned minb6": {"KFB_GEN_MINB": "6"},
     "planned 3-pass bricks": {"KFB_BRICKS_3PASS": "1"},
     "planned (default)": {},
