@@ -37,7 +37,6 @@
 // Side product for the raycaster: a voxel that turns negative marks the 8^3 bricks within two voxels of it in
 // a byte map; three separable passes turn the map into the brick distance field kfb_raycast.cu skips with.
 #include "kfb_common.cuh"
-#include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -45,7 +44,6 @@
 
 namespace kfb
 {
-namespace cg = cooperative_groups;
 
 struct CullPlane // conservative half-line in z: g0(x, y) + z * g1 >= 0
 {
@@ -1462,7 +1460,7 @@ __global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const Inte
         // per-voxel phase only on the planes in between -- for a surface seen at a grazing angle that is the
         // depth variation over the thread's few pixels instead of over the patch's footprint.
         int fe_t = z0 - 1, zb_t = z1;
-        if (a.Sz > 1e-6f)
+        if (a.Sz > 1e-6f && !a.no_prefix)
         {
             float ax, ay, bx_, by_, c0, c1, c2, c3;
             unpack2(xy[0], ax, ay);
@@ -1681,6 +1679,7 @@ static int launch_integrate_v1(kfb_ctx *ctx, IntegrateArgs &a, int planes, uint6
 static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, uint64_t *n_updated)
 {
     a.zchunk = KFB_PLAN_ZCHUNK;
+    if (const char *e = getenv("KFB_PLAN_ZCHUNK")) { const int v = atoi(e); if (v >= 2 && v <= 64) a.zchunk = v; }
     a.nchunks = (planes + a.zchunk - 1) / a.zchunk;
     a.npx = (a.X + KFB_PATCH_X - 1) / KFB_PATCH_X;
     a.npy = (a.Y + KFB_PATCH_Y - 1) / KFB_PATCH_Y;
@@ -1913,74 +1912,9 @@ __global__ void brick_distance_kernel(const uint8_t *__restrict__ src, uint8_t *
     dst[i] = (uint8_t)best;
 }
 
-// The three passes in ONE cooperative launch (a grid-wide barrier between passes): a frame whose sweep activated
-// no new brick -- nearly every frame once the scene has been seen -- pays one early-exit launch instead of three
-// and a memset.  `dirty` is read by every block before the first barrier and cleared after the last one.
-__device__ __forceinline__ void brick_pass(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int bx, int by, int bz, int axis, int from_flags,
-                                           int first, int stride)
-{
-    const int n = bx * by * bz;
-    for (int i = first; i < n; i += stride)
-    {
-        const int x = i % bx, y = (i / bx) % by, z = i / (bx * by);
-        const int pos = axis == 0 ? x : (axis == 1 ? y : z);
-        const int len = axis == 0 ? bx : (axis == 1 ? by : bz);
-        const int st = axis == 0 ? 1 : (axis == 1 ? bx : bx * by);
-        int best = KFB_BDIST_CAP;
-        const int j0 = max(-KFB_BDIST_CAP, -pos), j1 = min(KFB_BDIST_CAP, len - 1 - pos);
-        for (int j = j0; j <= j1; ++j)
-        {
-            int v = __ldcg(src + i + j * st); // L2: written by other blocks before the grid barrier
-            if (from_flags) v = v ? 0 : KFB_BDIST_CAP;
-            best = min(best, max(v, abs(j)));
-        }
-        dst[i] = (uint8_t)best;
-    }
-}
-__global__ void __launch_bounds__(256) brick_distance_fused_kernel(const uint8_t *flags, uint8_t *tmp, uint8_t *tmp2, uint8_t *dist, int bx, int by,
-                                                                   int bz, int *dirty)
-{
-    if (*(volatile int *)dirty == 0) return; // same answer in every block (see above)
-    cg::grid_group grid = cg::this_grid();
-    const int first = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
-    brick_pass(flags, tmp, bx, by, bz, 0, 1, first, stride);
-    grid.sync();
-    brick_pass(tmp, tmp2, bx, by, bz, 1, 0, first, stride);
-    grid.sync();
-    brick_pass(tmp2, dist, bx, by, bz, 2, 0, first, stride);
-    grid.sync();
-    if (first == 0) *dirty = 0;
-}
-
 int launch_brick_distance(kfb_ctx *ctx)
 {
     const int n = ctx->bdim[0] * ctx->bdim[1] * ctx->bdim[2];
-    if (!getenv("KFB_BRICKS_3PASS"))
-    {
-        if (ctx->bdist_grid == 0)
-        {
-            int per_sm = 0;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, brick_distance_fused_kernel, 256, 0) != cudaSuccess || per_sm < 1)
-            {
-                (void)cudaGetLastError();
-                ctx->bdist_grid = -1;
-            }
-            else ctx->bdist_grid = per_sm * ctx->sm_count;
-        }
-        if (ctx->bdist_grid > 0)
-        {
-            const int blocks = std::min(ctx->bdist_grid, (n + 255) / 256);
-            const uint8_t *flags = ctx->bricks;
-            uint8_t *tmp = ctx->bdist_tmp, *tmp2 = ctx->bdist_tmp2, *dist = ctx->bdist;
-            int bx = ctx->bdim[0], by = ctx->bdim[1], bz = ctx->bdim[2];
-            int *dirty = ctx->bdirty;
-            void *kargs[] = {(void *)&flags, (void *)&tmp, (void *)&tmp2, (void *)&dist, (void *)&bx, (void *)&by, (void *)&bz, (void *)&dirty};
-            const cudaError_t le = cudaLaunchCooperativeKernel((const void *)brick_distance_fused_kernel, dim3(blocks), dim3(256), kargs, 0, ctx->stream);
-            if (le == cudaSuccess) { ctx->launches++; return KFB_OK; }
-            (void)cudaGetLastError();
-            ctx->bdist_grid = -1; // no cooperative launches on this device / partition: three ordinary passes from now on
-        }
-    }
     const int blocks = (n + 255) / 256;
     brick_distance_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bricks, ctx->bdist_tmp, ctx->bdim[0], ctx->bdim[1], ctx->bdim[2], 0, ctx->bdirty, 1);
     KFB_LAUNCH_CHECK(ctx);
