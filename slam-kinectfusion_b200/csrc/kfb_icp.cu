@@ -124,6 +124,7 @@ struct IcpLevel
     const float4 *cur_v, *cur_n, *pre_v, *pre_n;
     Intr k;
     int cov_w, cov_h;
+    int nact; // CTAs that own pixels at this level (see icp_setup); thread t of CTA c visits pixels c * 480 + t + k * nact * 480
 };
 
 #define ICP_BATCH 4
@@ -483,8 +484,8 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
 #pragma unroll
         for (int i = 0; i < 3; ++i) a.pose.t[i] = spose[4 * i + 3];
         const unsigned long long ts0 = globaltimer_ns();
-        // only the CTAs that own pixels at this level take part in the reduction (the others would add zeros)
-        const int nact = min((int)gridDim.x, (a.cov_w * a.cov_h + ICP_THREADS - 1) / ICP_THREADS);
+        // only the CTAs that own pixels at this level take part in the reduction
+        const int nact = L.nact;
         unsigned long long ts1 = ts0;
         if (threadIdx.x == 0) is_last = false;
         if ((int)blockIdx.x < nact)
@@ -492,7 +493,7 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
             double acc[27];
 #pragma unroll
             for (int i = 0; i < 27; ++i) acc[i] = 0.0;
-            icp_accumulate_pixels<true>(a, acc, blockIdx.x * ICP_THREADS + threadIdx.x, gridDim.x * ICP_THREADS, cur_cache, level != cached_level);
+            icp_accumulate_pixels<true>(a, acc, blockIdx.x * ICP_THREADS + threadIdx.x, nact * ICP_THREADS, cur_cache, level != cached_level);
             cached_level = level;
             ts1 = globaltimer_ns();
             const double s = icp_block_reduce(acc, sm);
@@ -677,11 +678,15 @@ static int icp_setup(kfb_ctx *ctx, int level, IcpArgs &a, int &blocks)
     a.partials = ctx->icp_partials;
     a.ticket = ctx->icp_ticket;
     a.out = ctx->icp_dev;
-    // one CTA per SM at every level (two were measured slower: the ticket / final stage grows), for the direct and the persistent kernel alike: the pixel -> thread
-    // mapping and hence the summation order is a function of the SM count only => identical bits
-    a.stride = ctx->sm_count * ICP_THREADS;
+    // CTAs that take part at this level: enough for about KFB_ICP_PXT (default 4) pixels per thread, at most one per
+    // SM.  A thread keeps a batch of four pixels in flight, so four pixels cost it hardly more than one, while every
+    // CTA fewer makes the grid-wide part of an iteration (partials, ticket, final sum) cheaper.  The direct and the
+    // persistent kernel use the same count, hence the same pixel -> thread map and summation order => identical bits.
     const int npix = a.cov_w * a.cov_h;
-    blocks = npix > 0 ? std::min(ctx->sm_count, (npix + ICP_THREADS - 1) / ICP_THREADS) : 0; // CTAs that own pixels
+    int pxt = 4;
+    if (const char *e = getenv("KFB_ICP_PXT")) { const int v = atoi(e); if (v >= 1 && v <= 64) pxt = v; }
+    blocks = npix > 0 ? std::min(ctx->sm_count, (npix + ICP_THREADS * pxt - 1) / (ICP_THREADS * pxt)) : 0;
+    a.stride = blocks * ICP_THREADS;
     return KFB_OK;
 }
 
@@ -777,7 +782,7 @@ static int icp_launch_persistent(kfb_ctx *ctx, const float pose12[12])
         if (rc) return rc;
         if (S.iters[l] > 0 && a.cov_w * a.cov_h <= 0) { ctx->err = "icp level has no pixels to visit"; return KFB_ERR_INVALID; }
         P.lv[l].cur_v = a.cur_v; P.lv[l].cur_n = a.cur_n; P.lv[l].pre_v = a.pre_v; P.lv[l].pre_n = a.pre_n;
-        P.lv[l].k = a.k; P.lv[l].cov_w = a.cov_w; P.lv[l].cov_h = a.cov_h;
+        P.lv[l].k = a.k; P.lv[l].cov_w = a.cov_w; P.lv[l].cov_h = a.cov_h; P.lv[l].nact = blocks;
         P.iters[l] = S.iters[l];
         P.dist_thres = a.dist_thres; P.sine_thres = a.sine_thres;
         if (S.iters[l] > 0 && a.cov_w * a.cov_h > max_pix) max_pix = a.cov_w * a.cov_h;

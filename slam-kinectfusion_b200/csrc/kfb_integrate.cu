@@ -97,6 +97,7 @@ struct IntegrateArgs
     unsigned int *slot_of;        // [patch][chunk] -> general item index
     unsigned long long *gstates;  // [general item][6][32]: packed vc of the item's 32 threads after plane zstart(chunk) - 1
     int gstate_cap;               // general items that have a state slot (the others replay their running sums)
+    int refine;                   // KFB_INTEGRATE_REFINE: per-thread refinement of a general item's plane range (measured slower; kept for experiments)
 };
 
 #define KFB_MAGIC_F 12582912.0f   // 1.5 * 2^23
@@ -931,7 +932,7 @@ __global__ void __launch_bounds__(128) column_states_kernel(const IntegrateArgs 
 // tests/test_ref_ab.py and tests/test_ref_full.py compare whole volumes with the reference kernels' bit for bit.
 #define KFB_PATCH_X 16
 #define KFB_PATCH_Y 8
-#define KFB_PLAN_ZCHUNK 16
+#define KFB_PLAN_ZCHUNK 8
 
 // conservative interval of planes on which any column of a patch can pass the predicate; (cx, cy, cz)[k] = vc at
 // z = 0 of the patch's corner columns (g is affine in x and y, so its maximum over the patch sits at a corner)
@@ -1460,7 +1461,7 @@ __global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const Inte
         // per-voxel phase only on the planes in between -- for a surface seen at a grazing angle that is the
         // depth variation over the thread's few pixels instead of over the patch's footprint.
         int fe_t = z0 - 1, zb_t = z1;
-        if (a.Sz > 1e-6f && !a.no_prefix)
+        if (a.Sz > 1e-6f && a.refine)
         {
             float ax, ay, bx_, by_, c0, c1, c2, c3;
             unpack2(xy[0], ax, ay);
@@ -1678,6 +1679,7 @@ static int launch_integrate_v1(kfb_ctx *ctx, IntegrateArgs &a, int planes, uint6
 // planned sweep: plan -> states of the general items -> general items || stream items
 static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, uint64_t *n_updated)
 {
+    a.refine = getenv("KFB_INTEGRATE_REFINE") ? 1 : 0;
     a.zchunk = KFB_PLAN_ZCHUNK;
     if (const char *e = getenv("KFB_PLAN_ZCHUNK")) { const int v = atoi(e); if (v >= 2 && v <= 64) a.zchunk = v; }
     a.nchunks = (planes + a.zchunk - 1) / a.zchunk;
