@@ -457,7 +457,8 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
     __shared__ unsigned int cl_tag[ICP_CLUSTER];    // round whose partial of rank r is complete (CTA 0's copy)
     __shared__ __align__(16) float cl_gate[16];     // this CTA's orders for the next round, written by CTA 0
     __shared__ unsigned int cl_gate_tag;
-    __shared__ int s_abort;
+    __shared__ int s_abort, s_cl_next;
+    __shared__ unsigned int s_cl_tag;
     extern __shared__ float4 cur_cache[]; // [ICP_CACHE_SLOTS][normal, vertex][ICP_THREADS]
 
     if (threadIdx.x < ICP_CLUSTER) cl_tag[threadIdx.x] = 0xffffffffu;
@@ -688,15 +689,9 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
                                              ((unsigned int)(spec & 1) << 2) | (unsigned int)(cmd & 3);
                     if (cl)
                     {
-                        // cluster 0 gets its orders through shared memory: four chunks, then the tag with release
-                        for (unsigned int r = 0; r < ICP_CLUSTER; ++r)
-                        {
-                            const unsigned int gaddr = mapa_u32(smem_u32(cl_gate), r);
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) st_cluster_f4(gaddr + 16 * c, make_float4(next[4 * c], next[4 * c + 1], next[4 * c + 2], __uint_as_float(tag)));
-                            st_cluster_f4(gaddr + 48, make_float4(next[3], next[7], next[11], __uint_as_float(tag)));
-                            st_release_cluster_u32(mapa_u32(smem_u32(&cl_gate_tag), r), tag);
-                        }
+                        // cluster 0 gets its orders through shared memory: handed to eight threads below, one per CTA
+                        s_cl_tag = tag;
+                        s_cl_next = (next == hpose) ? 1 : 0;
                     }
                     // the other CTAs (every CTA outside cluster mode) follow the rounds through the device gate
 #pragma unroll
@@ -716,6 +711,20 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
                     pr[0] = ts0; pr[1] = ts3; pr[2] = ts4; pr[3] = ts6;
                 }
                 st[5] = ts5; st[6] = ts6;
+            }
+            if (cl)
+            {
+                ICP_BAR();
+                if (threadIdx.x < ICP_CLUSTER)
+                {
+                    // thread r -> CTA r: four chunks, then the tag with release (one release store per thread, in parallel)
+                    const float *next = s_cl_next ? hpose : npose;
+                    const unsigned int tag = s_cl_tag, gaddr = mapa_u32(smem_u32(cl_gate), threadIdx.x);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) st_cluster_f4(gaddr + 16 * c, make_float4(next[4 * c], next[4 * c + 1], next[4 * c + 2], __uint_as_float(tag)));
+                    st_cluster_f4(gaddr + 48, make_float4(next[3], next[7], next[11], __uint_as_float(tag)));
+                    st_release_cluster_u32(mapa_u32(smem_u32(&cl_gate_tag), threadIdx.x), tag);
+                }
             }
         }
         // every CTA (the last one included) picks its orders up from the device gate

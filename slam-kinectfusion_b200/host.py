@@ -67,6 +67,10 @@ def load_host_library():
         "kfh_png_write_gray16": (C.c_int, [C.c_char_p, _vp, C.c_int, C.c_int]),
         "kfh_png_write_rgb8": (C.c_int, [C.c_char_p, _vp, C.c_int, C.c_int]),
         "kfh_set_shard_comm": (None, [_vp, BCAST_FN, COMPOSITE_FN, _vp]),
+        "kfh_mailbox_open": (_vp, [C.c_char_p, C.c_int, C.c_int]),
+        "kfh_mailbox_close": (None, [_vp]),
+        "kfh_mailbox_exchange": (C.c_int, [_vp, _vp]),
+        "kfh_set_pose_mailbox": (None, [_vp, _vp, COMPOSITE_FN, _vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -174,6 +178,31 @@ class _BorrowedContext(Context):
         self.h = None
 
 
+class NativePoseMailbox:
+    """kf::PoseMailbox (kfusion/include/pose_mailbox.hpp): rank 0 must open before the others (barrier in between)."""
+
+    def __init__(self, name, rank, world):
+        self.lib = load_host_library()
+        self.h = self.lib.kfh_mailbox_open(name.encode(), int(rank), int(world))
+        if not self.h:
+            raise KfbError("pose mailbox: " + self.lib.kfh_last_error().decode())
+
+    def exchange(self, msg13):
+        """msg13: contiguous float32[13] numpy array (in place)."""
+        return self.lib.kfh_mailbox_exchange(self.h, msg13.ctypes.data_as(_vp))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.kfh_mailbox_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class KinectFusion:
     """kf::kinectfusion(intr, params).pipeline(cmap, dmap) -- the public API a user calls."""
 
@@ -212,6 +241,12 @@ class KinectFusion:
         """broadcast_pose(msg13: ctypes float*) -> int, composite() -> int (kf::ShardComm)."""
         self._cb = (BCAST_FN(lambda p, u: int(broadcast_pose(p))), COMPOSITE_FN(lambda u: int(composite())))
         self.lib.kfh_set_shard_comm(self.h, self._cb[0], self._cb[1], None)
+
+    def set_pose_mailbox(self, mailbox, composite):
+        """The native kf::PoseMailbox as broadcast_pose (no Python on the pose path); composite() -> int as above."""
+        self._cb = (COMPOSITE_FN(lambda u: int(composite())),)
+        self._mailbox = mailbox
+        self.lib.kfh_set_pose_mailbox(self.h, mailbox.h, self._cb[0], None)
 
     def reset(self):
         self.lib.kfh_reset(self.h)

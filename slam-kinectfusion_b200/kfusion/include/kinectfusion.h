@@ -55,6 +55,7 @@ struct ShardComm
     // integer SUM reduction of the model maps to rank 0 (include/kfb200.h, kfb_composite_mask)
     int (*composite)(void *user) = nullptr;
     void *user = nullptr;
+    void *pose_user = nullptr; // argument of broadcast_pose when it differs from `user` (kf::PoseMailbox::callback)
 };
 
 // The tracker-and-mapper.  Construction allocates everything on the device (one kfb_ctx); pipeline() is the only

@@ -1,6 +1,7 @@
 // c_api.cpp -- extern "C" handle API over kf::kinectfusion so the facade can be driven from
 // ctypes (tests, bench.py) exactly as a C++ application drives the reference's class.
 #include <kinectfusion.h>
+#include <pose_mailbox.hpp>
 #include <depth_sensor.h>
 #include <cstring>
 #include <string>
@@ -97,6 +98,22 @@ void kfh_set_shard_comm(void *h, int (*bcast)(float *, void *), int (*composite)
 {
     kf::ShardComm c;
     c.broadcast_pose = bcast; c.composite = composite; c.user = user;
+    static_cast<kf::kinectfusion *>(h)->setShardComm(c);
+}
+/* native pose mailbox (pose_mailbox.hpp): handle or NULL; kfh_set_pose_mailbox installs it as the instance's
+ * broadcast_pose (the composite callback stays whatever kfh_set_shard_comm installed, or none with peer memory) */
+void *kfh_mailbox_open(const char *name, int rank, int world)
+{
+    kf::PoseMailbox *m = new kf::PoseMailbox();
+    if (!m->open(name, rank, world)) { g_err = m->lastError(); delete m; return nullptr; }
+    return m;
+}
+void kfh_mailbox_close(void *m) { delete static_cast<kf::PoseMailbox *>(m); }
+int kfh_mailbox_exchange(void *m, float *msg13) { return static_cast<kf::PoseMailbox *>(m)->exchange(msg13); }
+void kfh_set_pose_mailbox(void *h, void *m, int (*composite)(void *), void *user)
+{
+    kf::ShardComm c;
+    c.broadcast_pose = &kf::PoseMailbox::callback; c.pose_user = m; c.composite = composite; c.user = user;
     static_cast<kf::kinectfusion *>(h)->setShardComm(c);
 }
 double kfh_last_icp_us(void *h) { return static_cast<kf::kinectfusion *>(h)->last_icp_us; }

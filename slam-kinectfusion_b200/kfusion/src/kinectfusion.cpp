@@ -103,7 +103,7 @@ void kf::kinectfusion::pipeline(const float *depth_mm, int width, int height)
         msg[0] = ok ? 1.f : 0.f;
         if (ok) (pose_record.back() * cam_pose).to12(msg + 1);
     }
-    if (sharded && comm.broadcast_pose(msg, comm.user) != 0) throw std::runtime_error("kf::kinectfusion: pose broadcast failed");
+    if (sharded && comm.broadcast_pose(msg, comm.pose_user ? comm.pose_user : comm.user) != 0) throw std::runtime_error("kf::kinectfusion: pose broadcast failed");
     if (msg[0] == 0.f)
     {
         last_tracking_ok = false;

@@ -190,11 +190,28 @@ class ShardedKinectFusion:
         self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self.P = K.width * K.height
         tag = os.environ.get("KFB_MAILBOX_TAG", os.environ.get("MASTER_PORT", "0"))
-        self.mailbox = PoseMailbox(dist, rank, tag) if os.environ.get("KFB_POSE_NCCL") is None else None
+        # pose hand-off: the facade's native shared-memory mailbox (default; no Python on the per-frame path), the
+        # Python one (KFB_POSE_PYMAILBOX=1) or a torch.distributed broadcast (KFB_POSE_NCCL=1)
+        self.mailbox = None
+        self.native_mailbox = None
         self.mailbox_us = []
+        if os.environ.get("KFB_POSE_NCCL") is None:
+            if os.environ.get("KFB_POSE_PYMAILBOX") is not None:
+                self.mailbox = PoseMailbox(dist, rank, tag)
+            else:
+                name = f"/kfb_pose_{os.getuid()}_{tag}"
+                if rank == 0:
+                    self.native_mailbox = host.NativePoseMailbox(name, rank, world)
+                dist.barrier()
+                if rank != 0:
+                    self.native_mailbox = host.NativePoseMailbox(name, rank, world)
+                dist.barrier()
         self.min_keys = torch.empty(self.P, dtype=torch.float32, device=self.device)
         self._view_cache = {}
-        self.kf.set_shard_comm(self._bcast, self._composite)
+        if self.native_mailbox is not None:
+            self.kf.set_pose_mailbox(self.native_mailbox, self._composite)
+        else:
+            self.kf.set_shard_comm(self._bcast, self._composite)
         self.p2p = os.environ.get("KFB_COMPOSITE_NCCL") is None
         if self.p2p:
             # exchange CUDA IPC handles once; from then on the composite is one kernel over NVLink peer memory
@@ -247,6 +264,9 @@ class ShardedKinectFusion:
         if self.mailbox is not None:
             self.mailbox.close()
             self.mailbox = None
+        if self.native_mailbox is not None:
+            self.native_mailbox.close()
+            self.native_mailbox = None
 
 
 def _measure_config(args, dist, rank, world, local, dims, K, frames, host_pin, dev_frames, ClockSampler, with_e2e, tag):

@@ -125,3 +125,42 @@ def test_two_gpu_sharded_run_equals_single_gpu(kfb):
     for _, d in synth.sequence(1 + warm + steps, K):
         assert kf.pipeline(d) == 0
     assert np.array_equal(np.asarray(line["final_pose"], np.float32), kf.pose())
+
+
+def _mailbox_peer(name, rank, world, n, q):
+    import slam_kinectfusion_b200 as kfb
+    from slam_kinectfusion_b200 import host
+    mb = host.NativePoseMailbox(name, rank, world)
+    got = []
+    for i in range(n):
+        msg = np.zeros(13, np.float32)
+        assert mb.exchange(msg) == 0
+        got.append(msg.copy())
+    mb.close()
+    q.put((rank, np.array(got)))
+
+
+def test_native_pose_mailbox_three_ranks(kfb):
+    """kf::PoseMailbox (the facade's own broadcast_pose): rank 0 publishes 200 messages back to back, two reader
+    processes receive every one of them, in order, none overwritten before both have taken it."""
+    import multiprocessing as mp
+    from slam_kinectfusion_b200 import host
+    name, world, n = f"/kfb_test_mailbox_{os.getpid()}", 3, 200
+    mb0 = host.NativePoseMailbox(name, 0, world)          # rank 0 creates the segment first
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_mailbox_peer, args=(name, r, world, n, q)) for r in (1, 2)]
+    for p in procs:
+        p.start()
+    sent = []
+    for i in range(n):
+        msg = np.arange(13, dtype=np.float32) + 100.0 * i
+        sent.append(msg.copy())
+        assert mb0.exchange(msg) == 0
+    res = dict(q.get(timeout=60) for _ in procs)
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    mb0.close()
+    for r in (1, 2):
+        assert np.array_equal(res[r], np.array(sent))
