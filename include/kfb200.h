@@ -137,9 +137,12 @@ int kfb_icp_end(kfb_ctx *ctx);
  * (tsdf_volume.cpp:50).  n_updated may be NULL; when non-NULL a counting variant of
  * the kernel runs and the call blocks until the count is valid. */
 int kfb_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_updated);
-/* Slab balancing aid for sharded volumes (no reference counterpart): host_hist[z], z in [0, dims[2]), = number
- * of 4-voxel groups kfb_integrate would visit on plane z of the WHOLE volume for the current frame's depth and
- * this pose (frustum only; independent of the volume's content and of the planes this context stores). */
+/* Slab balancing aid for sharded volumes (no reference counterpart): host_hist[z], z in [0, dims[2]), = work the
+ * sweep of kfb_integrate would do on plane z of the WHOLE volume for the current frame's depth and this pose, in
+ * voxel quads: every plane a work item covers counts its 32 quads once if the item only streams free space and four
+ * times if it needs the per-voxel predicate (the measured cost ratio).  It comes from the sweep's own plan, which
+ * depends on the depth image and the pose only -- not on the volume's content or on the planes this context stores
+ * -- so every rank computes the same histogram without communication. */
 int kfb_integrate_plane_histogram(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *host_hist);
 /* device::raycast (device_types.hpp:117, tsdf_volume.cu:264-273) into the PREVIOUS
  * (model) frame's level-0 maps, misses written as zeros (pframe->reset(),

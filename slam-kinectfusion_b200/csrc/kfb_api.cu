@@ -108,7 +108,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->stream = nullptr; ctx->own_stream = 1;
     ctx->fstream = nullptr; ctx->ev_front = nullptr; ctx->ev_free = nullptr; ctx->ev_tables_free = nullptr; ctx->front_pending = 0;
     ctx->icp_host = nullptr; ctx->icp_gate_host = nullptr; ctx->icp_devgate = nullptr; ctx->icp_mirror = nullptr;
-    ctx->icp_smem_set = 0; ctx->icp_grid_ctas = 0; ctx->icp_cluster = 0;
+    ctx->icp_smem_set = 0;
     ctx->icp_fallbacks = 0; ctx->icp_direct_left = 0;
     ctx->istream = nullptr; ctx->ev_ifork = nullptr; ctx->ev_ijoin = nullptr;
     ctx->dev_err_host = ctx->dev_err_dev = nullptr;

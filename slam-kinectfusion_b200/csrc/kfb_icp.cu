@@ -118,38 +118,6 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     return t;
 }
 
-// ---- thread-block cluster helpers (distributed shared memory) ------------------------------------------------
-#define ICP_CLUSTER 8 // CTAs per cluster (the portable maximum)
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-// address of the same shared-memory object in CTA `rank` of this cluster
-__device__ __forceinline__ unsigned mapa_u32(unsigned local, unsigned rank)
-{
-    unsigned r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void st_cluster_f64(unsigned addr, double v) { asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
-__device__ __forceinline__ void st_cluster_f4(unsigned addr, const float4 v)
-{
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-__device__ __forceinline__ void st_release_cluster_u32(unsigned addr, unsigned v)
-{
-    asm volatile("st.release.cluster.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-__device__ __forceinline__ float4 ld_shared_f4(unsigned local_addr)
-{
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(local_addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned ld_acquire_cluster_u32(unsigned local_addr)
-{
-    unsigned v;
-    asm volatile("ld.acquire.cluster.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(local_addr) : "memory");
-    return v;
-}
-
 // ---- shared pieces ------------------------------------------------------------------------------------
 struct IcpLevel
 {
@@ -157,7 +125,6 @@ struct IcpLevel
     Intr k;
     int cov_w, cov_h;
     int nact; // CTAs that own pixels at this level (see icp_setup); thread t of CTA c visits pixels c * 480 + t + k * nact * 480
-    int cluster; // nact <= ICP_CLUSTER and the grid was launched in clusters: the level's iterations run inside cluster 0
 };
 
 #define ICP_BATCH 4
@@ -354,7 +321,6 @@ struct IcpPersistArgs
     unsigned long long seq0;   // iteration k carries sequence number seq0 + k + 1
     unsigned long long round0; // release counter base (monotonic across schedules)
     int speculate;
-    int cluster; // launched with cluster dimension ICP_CLUSTER
     unsigned long long timeout_ns; // bound of every poll (x1 host pose, x2 mirrored pose, x3 device gate)
     float pose0[12];
 };
@@ -451,24 +417,8 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
     __shared__ bool is_last;
     __shared__ int s_cmd, s_iter, s_spec, s_ok, s_pred;
     __shared__ float spose[12], npose[12], hpose[12];
-    // cluster mode (coarse levels): the CTAs of cluster 0 hand their 27 sums to CTA 0 and receive their orders through
-    // distributed shared memory -- no global round trip (partials + fence, ticket, final pass over L2, gate poll)
-    __shared__ double cl_part[ICP_CLUSTER][27];     // CTA 0's copy is the mailbox of the cluster's partial sums
-    __shared__ unsigned int cl_tag[ICP_CLUSTER];    // round whose partial of rank r is complete (CTA 0's copy)
-    __shared__ __align__(16) float cl_gate[16];     // this CTA's orders for the next round, written by CTA 0
-    __shared__ unsigned int cl_gate_tag;
-    __shared__ int s_abort, s_cl_next;
-    __shared__ unsigned int s_cl_tag;
     extern __shared__ float4 cur_cache[]; // [ICP_CACHE_SLOTS][normal, vertex][ICP_THREADS]
 
-    if (threadIdx.x < ICP_CLUSTER) cl_tag[threadIdx.x] = 0xffffffffu;
-    if (threadIdx.x == 0) { cl_gate_tag = 0xffffffffu; s_abort = 0; }
-    if (P.cluster)
-    {
-        // every CTA's mailboxes are initialised before a peer may write into them (all threads are still here)
-        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-    }
-    else __syncthreads();
     // ---- service warp: CTA 0 mirrors the host's poses into device memory; elsewhere it has nothing to do -------
     if (threadIdx.x >= ICP_THREADS)
     {
@@ -536,7 +486,6 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
         const unsigned long long ts0 = globaltimer_ns();
         // only the CTAs that own pixels at this level take part in the reduction
         const int nact = L.nact;
-        const bool cl = P.cluster && L.cluster; // this iteration runs inside cluster 0
         unsigned long long ts1 = ts0;
         if (threadIdx.x == 0) is_last = false;
         if ((int)blockIdx.x < nact)
@@ -548,59 +497,24 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
             cached_level = level;
             ts1 = globaltimer_ns();
             const double s = icp_block_reduce(acc, sm);
-            if (cl)
+            if (threadIdx.x < 27)
             {
-                // the partial goes straight into CTA 0's shared memory; the release store of the tag (after the CTA
-                // barrier, hence after all 27 stores) publishes it at cluster scope
-                if (threadIdx.x < 27) st_cluster_f64(mapa_u32(smem_u32(&cl_part[blockIdx.x][threadIdx.x]), 0), s);
-                ICP_BAR();
-                if (threadIdx.x == 0)
-                {
-                    st_release_cluster_u32(mapa_u32(smem_u32(&cl_tag[blockIdx.x]), 0), (unsigned int)(round + 1ull));
-                    is_last = (blockIdx.x == 0);
-                }
+                P.partials[(size_t)blockIdx.x * 27 + threadIdx.x] = s;
+                __threadfence();
             }
-            else
+            ICP_BAR();
+            if (threadIdx.x == 0)
             {
-                if (threadIdx.x < 27)
-                {
-                    P.partials[(size_t)blockIdx.x * 27 + threadIdx.x] = s;
-                    __threadfence();
-                }
-                ICP_BAR();
-                if (threadIdx.x == 0)
-                {
-                    const unsigned int t = atomicInc(P.ticket, nact - 1);
-                    is_last = (t == (unsigned)(nact - 1));
-                }
+                const unsigned int t = atomicInc(P.ticket, nact - 1);
+                is_last = (t == (unsigned)(nact - 1));
             }
         }
         ICP_BAR();
         if (is_last)
         {
             const unsigned long long ts2 = globaltimer_ns();
-            double fin = 0.0;
-            if (cl)
-            {
-                if (threadIdx.x == 0)
-                {
-                    // all partials of this round have landed in my shared memory (bounded wait)
-                    const unsigned int want = (unsigned int)(round + 1ull);
-                    const unsigned long long t0 = globaltimer_ns();
-                    for (int r = 0; r < nact; ++r)
-                        while (ld_acquire_cluster_u32(smem_u32(&cl_tag[r])) != want)
-                            if (globaltimer_ns() - t0 > 2ull * P.timeout_ns) { s_abort = 1; break; }
-                }
-                ICP_BAR();
-                // the same fixed order as icp_final_reduce for up to 15 partials: rank by rank, from +0.0
-                if (threadIdx.x < 27)
-                    for (int r = 0; r < nact; ++r) fin += cl_part[r][threadIdx.x];
-            }
-            else
-            {
-                __threadfence();
-                fin = icp_final_reduce(P.partials, nact, red);
-            }
+            __threadfence();
+            const double fin = icp_final_reduce(P.partials, nact, red);
             if (threadIdx.x < 27) fin27[threadIdx.x] = fin;
             const unsigned long long ts3 = globaltimer_ns();
             ICP_BAR(); // fin27 visible
@@ -609,8 +523,8 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
             //     the next pose from the sums; the prediction is only used if (1) passes.
             if (threadIdx.x == 0)
             {
-                int ok = 1, cmd = s_abort ? ICP_CMD_LEAVE : ICP_CMD_RUN;
-                if (spec_used && cmd == ICP_CMD_RUN)
+                int ok = 1, cmd = ICP_CMD_RUN;
+                if (spec_used)
                 {
                     const int slot = k % ICP_MIRROR_RING;
                     const unsigned long long t0 = globaltimer_ns();
@@ -687,13 +601,6 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
                     // them: the partials were consumed above, the ticket has wrapped to zero by itself.
                     const unsigned int tag = ((unsigned int)((round + 1ull) & 0xfffffull) << 12) | ((unsigned int)(iter & 0xff) << 4) |
                                              ((unsigned int)(spec & 1) << 2) | (unsigned int)(cmd & 3);
-                    if (cl)
-                    {
-                        // cluster 0 gets its orders through shared memory: handed to eight threads below, one per CTA
-                        s_cl_tag = tag;
-                        s_cl_next = (next == hpose) ? 1 : 0;
-                    }
-                    // the other CTAs (every CTA outside cluster mode) follow the rounds through the device gate
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
                     {
@@ -712,20 +619,6 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
                 }
                 st[5] = ts5; st[6] = ts6;
             }
-            if (cl)
-            {
-                ICP_BAR();
-                if (threadIdx.x < ICP_CLUSTER)
-                {
-                    // thread r -> CTA r: four chunks, then the tag with release (one release store per thread, in parallel)
-                    const float *next = s_cl_next ? hpose : npose;
-                    const unsigned int tag = s_cl_tag, gaddr = mapa_u32(smem_u32(cl_gate), threadIdx.x);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) st_cluster_f4(gaddr + 16 * c, make_float4(next[4 * c], next[4 * c + 1], next[4 * c + 2], __uint_as_float(tag)));
-                    st_cluster_f4(gaddr + 48, make_float4(next[3], next[7], next[11], __uint_as_float(tag)));
-                    st_release_cluster_u32(mapa_u32(smem_u32(&cl_gate_tag), threadIdx.x), tag);
-                }
-            }
         }
         // every CTA (the last one included) picks its orders up from the device gate
         if (threadIdx.x == 0)
@@ -734,21 +627,6 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
             const unsigned long long t0 = globaltimer_ns();
             int cmd = ICP_CMD_RUN;
             float4 c0, c1, c2, c3;
-            if (cl && blockIdx.x < ICP_CLUSTER)
-            {
-                // orders arrive in my own shared memory (written by CTA 0, published by its release store of the tag)
-                for (;;)
-                {
-                    const unsigned int t = ld_acquire_cluster_u32(smem_u32(&cl_gate_tag));
-                    if ((t >> 12) == want && t != 0xffffffffu) break;
-                    if (globaltimer_ns() - t0 > 3ull * P.timeout_ns) { cmd = ICP_CMD_LEAVE; break; }
-                }
-                c0 = ld_shared_f4(smem_u32(cl_gate));
-                c1 = ld_shared_f4(smem_u32(cl_gate) + 16);
-                c2 = ld_shared_f4(smem_u32(cl_gate) + 32);
-                c3 = ld_shared_f4(smem_u32(cl_gate) + 48);
-            }
-            else
             for (;;)
             {
                 // one load per poll (the chunk written last) keeps the pollers out of the writer's way; CTAs without
@@ -786,43 +664,6 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
     }
 }
 
-// CTAs of the persistent kernel (the direct kernel caps its per-level count with the same number, so both sum in the
-// same order).  With thread-block clusters available the grid is a whole number of 8-CTA clusters that can all be
-// resident at once (a cluster stays inside one GPC, so fewer CTAs fit than there are SMs); otherwise one CTA per SM.
-static int icp_grid(kfb_ctx *ctx)
-{
-    if (ctx->icp_grid_ctas > 0) return ctx->icp_grid_ctas;
-    ctx->icp_grid_ctas = ctx->sm_count;
-    ctx->icp_cluster = 0;
-    if (getenv("KFB_ICP_NOCLUSTER") || ctx->sm_count < ICP_CLUSTER) return ctx->icp_grid_ctas;
-    const size_t cache_bytes = (size_t)ICP_CACHE_SLOTS * 2 * ICP_THREADS * sizeof(float4);
-    if (cudaFuncSetAttribute(icp_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cache_bytes) != cudaSuccess)
-    {
-        (void)cudaGetLastError();
-        return ctx->icp_grid_ctas;
-    }
-    ctx->icp_smem_set = 1;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((ctx->sm_count / ICP_CLUSTER) * ICP_CLUSTER);
-    cfg.blockDim = dim3(ICP_THREADS + 32);
-    cfg.dynamicSmemBytes = cache_bytes;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = ICP_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    int nclusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&nclusters, icp_persistent_kernel, &cfg) != cudaSuccess || nclusters < 1)
-    {
-        (void)cudaGetLastError();
-        return ctx->icp_grid_ctas;
-    }
-    ctx->icp_grid_ctas = std::min(nclusters, ctx->sm_count / ICP_CLUSTER) * ICP_CLUSTER;
-    ctx->icp_cluster = 1;
-    return ctx->icp_grid_ctas;
-}
-
 static int icp_setup(kfb_ctx *ctx, int level, IcpArgs &a, int &blocks)
 {
     if (level < 0 || level >= ctx->levels) { ctx->err = "icp level out of range"; return KFB_ERR_INVALID; }
@@ -837,18 +678,17 @@ static int icp_setup(kfb_ctx *ctx, int level, IcpArgs &a, int &blocks)
     a.partials = ctx->icp_partials;
     a.ticket = ctx->icp_ticket;
     a.out = ctx->icp_dev;
-    // CTAs that take part at this level: one pixel per thread while the grid lasts (measured on B200: every further
-    // pixel per thread costs more in the accumulation than the smaller reduction saves: KFB_ICP_PXT = 1 / 2 / 4 / 8
-    // -> 184 / 189 / 209 / 282 us per frame), at most the whole grid.  Exception: a level small enough for ONE
-    // thread-block cluster at four pixels per thread (the coarsest level of a 640 x 480 frame) runs inside cluster 0,
-    // where the hand-off of the partial sums and of the next pose goes through distributed shared memory.  The direct
-    // and the persistent kernel use the same counts, hence the same pixel -> thread map and summation order.
+    // CTAs that take part at this level: one pixel per thread while the SMs last.  Measured on B200 (tools/icp_ab.py,
+    // persistent kernel per frame): KFB_ICP_PXT = 1 / 2 / 4 / 8 pixels per thread -> 184 / 189 / 209 / 282 us: every
+    // further pixel per thread costs more in the accumulation than the smaller reduction saves.  Also measured and
+    // dropped: the coarsest level inside ONE thread-block cluster of 8 CTAs (4 pixels per thread), partial sums and
+    // next pose handed over through distributed shared memory with cluster-scope release / acquire instead of the
+    // global partials + ticket + device gate: 9.9 us per iteration against 7.5 us (profiles/README.md).  The direct
+    // and the persistent kernel use the same count, hence the same pixel -> thread map and summation order.
     const int npix = a.cov_w * a.cov_h;
     int pxt = 1;
     if (const char *e = getenv("KFB_ICP_PXT")) { const int v = atoi(e); if (v >= 1 && v <= 64) pxt = v; }
-    const int grid = icp_grid(ctx);
-    if (ctx->icp_cluster && npix <= ICP_CLUSTER * ICP_THREADS * 4) pxt = std::max(pxt, 4);
-    blocks = npix > 0 ? std::min(grid, (npix + ICP_THREADS * pxt - 1) / (ICP_THREADS * pxt)) : 0;
+    blocks = npix > 0 ? std::min(ctx->sm_count, (npix + ICP_THREADS * pxt - 1) / (ICP_THREADS * pxt)) : 0;
     a.stride = blocks * ICP_THREADS;
     return KFB_OK;
 }
@@ -946,7 +786,6 @@ static int icp_launch_persistent(kfb_ctx *ctx, const float pose12[12])
         if (S.iters[l] > 0 && a.cov_w * a.cov_h <= 0) { ctx->err = "icp level has no pixels to visit"; return KFB_ERR_INVALID; }
         P.lv[l].cur_v = a.cur_v; P.lv[l].cur_n = a.cur_n; P.lv[l].pre_v = a.pre_v; P.lv[l].pre_n = a.pre_n;
         P.lv[l].k = a.k; P.lv[l].cov_w = a.cov_w; P.lv[l].cov_h = a.cov_h; P.lv[l].nact = blocks;
-        P.lv[l].cluster = (blocks >= 1 && blocks <= ICP_CLUSTER) ? 1 : 0;
         P.iters[l] = S.iters[l];
         P.dist_thres = a.dist_thres; P.sine_thres = a.sine_thres;
         if (S.iters[l] > 0 && a.cov_w * a.cov_h > max_pix) max_pix = a.cov_w * a.cov_h;
@@ -966,8 +805,8 @@ static int icp_launch_persistent(kfb_ctx *ctx, const float pose12[12])
     P.timeout_ns = KFB_ICP_GATE_TIMEOUT_NS;
     if (const char *e = getenv("KFB_ICP_TIMEOUT_NS")) { const long long v = atoll(e); if (v > 0) P.timeout_ns = (unsigned long long)v; }
     memcpy(P.pose0, pose12, sizeof(P.pose0));
-    // every CTA must be resident at once (they wait on each other)
-    const int blocks = icp_grid(ctx);
+    // every CTA must be resident at once (they wait on each other): one per SM (see icp_setup)
+    const int blocks = ctx->sm_count;
     (void)max_pix;
     if (ctx->profiling) cudaEventRecord(ctx->events[54], ctx->stream); // the frame's whole ICP: 54 .. 55
     const size_t cache_bytes = (size_t)ICP_CACHE_SLOTS * 2 * ICP_THREADS * sizeof(float4);
@@ -977,48 +816,12 @@ static int icp_launch_persistent(kfb_ctx *ctx, const float pose12[12])
         ctx->icp_smem_set = 1;
     }
     KFB_CUDA(ctx, cudaMemsetAsync(ctx->icp_ticket, 0, sizeof(unsigned int), ctx->stream));
-    // The CTAs wait on each other through the device gate (and, inside cluster 0, through shared memory), so the
-    // whole grid has to be co-resident.  A cooperative launch makes the driver check exactly that (SM limits under
-    // MPS / MIG included) and refuse the launch otherwise; the caller then runs the schedule with one ordinary launch
-    // per iteration, which gives the same sums bit for bit.  KFB_ICP_PLAIN_LAUNCH=1: ordinary launch behind an
-    // occupancy query.  With clusters: cooperative + cluster dimension 8; if the driver refuses that combination, the
-    // cluster launch alone (icp_grid sized the grid from cudaOccupancyMaxActiveClusters), else no clusters.
-    cudaError_t le = cudaErrorUnknown;
-    if (ctx->icp_cluster)
-    {
-        P.cluster = 1;
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(blocks);
-        cfg.blockDim = dim3(ICP_THREADS + 32);
-        cfg.dynamicSmemBytes = cache_bytes;
-        cfg.stream = ctx->stream;
-        cudaLaunchAttribute at[2];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = ICP_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        at[1].id = cudaLaunchAttributeCooperative;
-        at[1].val.cooperative = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = (ctx->icp_cluster == 1 && !getenv("KFB_ICP_PLAIN_LAUNCH")) ? 2 : 1;
-        le = cudaLaunchKernelEx(&cfg, icp_persistent_kernel, P);
-        if (le != cudaSuccess && cfg.numAttrs == 2)
-        {
-            (void)cudaGetLastError();
-            ctx->icp_cluster = 2; // cooperative + cluster refused: cluster launches only from now on
-            cfg.numAttrs = 1;
-            le = cudaLaunchKernelEx(&cfg, icp_persistent_kernel, P);
-        }
-        if (le != cudaSuccess)
-        {
-            // no cluster launches here after all: the next schedule uses a different grid (and summation order);
-            // this one runs on ordinary launches
-            (void)cudaGetLastError();
-            ctx->icp_cluster = 0;
-            ctx->icp_grid_ctas = ctx->sm_count;
-            le = cudaErrorCooperativeLaunchTooLarge;
-        }
-    }
-    else if (getenv("KFB_ICP_PLAIN_LAUNCH"))
+    // The CTAs wait on each other through the device gate, so the whole grid has to be co-resident.  A
+    // cooperative launch makes the driver check exactly that (SM limits under MPS / MIG included) and refuse
+    // the launch otherwise; the caller then runs the schedule with one ordinary launch per iteration, which
+    // gives the same sums bit for bit.  KFB_ICP_PLAIN_LAUNCH=1: ordinary launch behind an occupancy query.
+    cudaError_t le;
+    if (getenv("KFB_ICP_PLAIN_LAUNCH"))
     {
         int per_sm = 0;
         le = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_persistent_kernel, ICP_THREADS + 32, cache_bytes);

@@ -1780,11 +1780,11 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
     return KFB_OK;
 }
 
-int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_updated)
+// everything about a sweep that does not depend on how it is cut into work
+static void fill_integrate_args(kfb_ctx *ctx, const float vol2cam12[12], IntegrateArgs &a)
 {
     const Intr &k = ctx->L[0].k;
-    if (ctx->profiling) cudaEventRecord(ctx->events[56], ctx->stream); // whole call: 56 .. 57
-    IntegrateArgs a;
+    memset(&a, 0, sizeof(a));
     a.vol = ctx->vol;
     a.X = ctx->p.volu_dims[0];
     a.Y = ctx->p.volu_dims[1];
@@ -1826,9 +1826,16 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
     if (getenv("KFB_INTEGRATE_NOCULL"))
         for (int c = 0; c < KFB_NCULL; ++c) a.cull[c].kind = 3;
 
+    a.tab4 = ctx->tab4;
+}
+
+int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_updated)
+{
+    if (ctx->profiling) cudaEventRecord(ctx->events[56], ctx->stream); // whole call: 56 .. 57
+    IntegrateArgs a;
+    fill_integrate_args(ctx, vol2cam12, a);
     const int planes = a.ze - a.zb;
     if (planes <= 0) return KFB_OK;
-    a.tab4 = ctx->tab4;
     if (!getenv("KFB_INTEGRATE_V1"))
     {
         const int rcp = launch_integrate_planned(ctx, a, planes, n_updated);
@@ -1957,7 +1964,7 @@ __global__ void __launch_bounds__(128) plane_histogram_kernel(const IntegrateArg
     atomicAdd(diff + zb + 1, -1);
 }
 
-int launch_plane_histogram(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *host_hist)
+static int launch_plane_histogram_frustum(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *host_hist)
 {
     const Intr &k = ctx->L[0].k;
     const int Z = ctx->p.volu_dims[2];
@@ -1982,6 +1989,74 @@ int launch_plane_histogram(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *ho
     KFB_CUDA(ctx, e);
     long run = 0;
     for (int z = 0; z < Z; ++z) { run += h[z]; host_hist[z] = (uint32_t)(run > 0 ? run : 0); }
+    return KFB_OK;
+}
+
+// Work per plane from the sweep's own plan: the plan kernel runs for the WHOLE volume (it needs the depth tables and
+// the pose, not the voxels), and every item adds its 32 voxel quads per plane to the planes it covers -- once for a
+// stream item, KFB_HIST_GENERAL_WEIGHT times for a general item (measured cost ratio per quad at 512^3).  The
+// frustum-only count above left the busiest of two 2048^3 slabs 30 % behind the other (profiles/README.md).
+#define KFB_HIST_GENERAL_WEIGHT 4
+int launch_plane_histogram(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *host_hist)
+{
+    const int Z = ctx->p.volu_dims[2];
+    if (getenv("KFB_HIST_FRUSTUM")) return launch_plane_histogram_frustum(ctx, vol2cam12, host_hist);
+    IntegrateArgs a;
+    fill_integrate_args(ctx, vol2cam12, a);
+    a.vol = nullptr;
+    a.z_store0 = 0; a.zb = 1; a.ze = Z;
+    if (Z > 65535) { ctx->err = "volumes deeper than 65535 planes are not supported"; return KFB_ERR_UNSUPPORTED; }
+    a.zchunk = 16;
+    a.nchunks = (Z - 1 + a.zchunk - 1) / a.zchunk;
+    a.npx = (a.X + KFB_PATCH_X - 1) / KFB_PATCH_X;
+    a.npy = (a.Y + KFB_PATCH_Y - 1) / KFB_PATCH_Y;
+    a.mask_words = (a.nchunks + 31) / 32;
+    const size_t npatch = (size_t)a.npx * a.npy, ncell = npatch * a.nchunks;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t o_mask = 256, o_slot = o_mask + up(npatch * a.mask_words * 4), o_is = o_slot + up(ncell * 4), o_ig = o_is + up(ncell * 8),
+                 need = o_ig + up(ncell * 8);
+    char *pb = nullptr;
+    KFB_CUDA(ctx, cudaMalloc(&pb, need));
+    a.plan_counts = (unsigned int *)pb;
+    a.patch_mask = (unsigned int *)(pb + o_mask);
+    a.slot_of = (unsigned int *)(pb + o_slot);
+    a.items_stream = (uint2 *)(pb + o_is);
+    a.items_general = (uint2 *)(pb + o_ig);
+    cudaError_t e = cudaMemsetAsync(pb, 0, o_slot, ctx->stream);
+    if (e == cudaSuccess)
+    {
+        integrate_plan_kernel<<<(unsigned)((ncell + 127) / 128), 128, 0, ctx->stream>>>(a);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    unsigned int counts[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counts, a.plan_counts, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    std::vector<uint2> items[2];
+    for (int t = 0; t < 2 && e == cudaSuccess; ++t)
+    {
+        items[t].resize(counts[t]);
+        if (counts[t]) e = cudaMemcpy(items[t].data(), t ? a.items_general : a.items_stream, (size_t)counts[t] * sizeof(uint2), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(pb);
+    KFB_CUDA(ctx, e);
+    std::vector<long long> diff((size_t)Z + 2, 0);
+    for (int t = 0; t < 2; ++t)
+    {
+        const long long wgt = 32 * (t ? KFB_HIST_GENERAL_WEIGHT : 1);
+        for (const uint2 &it : items[t])
+        {
+            const int z0 = (int)(it.y & 0xffffu), z1 = (int)(it.y >> 16);
+            diff[z0] += wgt;
+            diff[z1 + 1] -= wgt;
+        }
+    }
+    long long run = 0;
+    for (int z = 0; z < Z; ++z)
+    {
+        run += diff[z];
+        host_hist[z] = (uint32_t)std::min<long long>(std::max<long long>(run, 0), 0xffffffffll);
+    }
     return KFB_OK;
 }
 

@@ -20,15 +20,8 @@ def main():
     frames = synth.sequence(n, K)
     dev = torch.stack([torch.from_numpy(d) for _, d in frames]).cuda()
     poses = {}
-    for pxt in sys.argv[3:] or ("nocluster", "cluster", "nocluster", "cluster"):
-        # the grid (clusters or not) is fixed per context: a fresh one per variant
-        os.environ.pop("KFB_ICP_NOCLUSTER", None)
-        os.environ.pop("KFB_ICP_PXT", None)
-        if pxt == "nocluster":
-            os.environ["KFB_ICP_NOCLUSTER"] = "1"
-        elif pxt != "cluster":
-            os.environ["KFB_ICP_NOCLUSTER"] = "1"
-            os.environ["KFB_ICP_PXT"] = pxt
+    for pxt in sys.argv[3:] or ("1", "2", "4", "8"):
+        os.environ["KFB_ICP_PXT"] = pxt
         kf = kfb.KinectFusion(K, kfb.default_host_params(dims))
         ctx = kf.context()
         ctx.set_profiling(True)
