@@ -284,92 +284,8 @@ __global__ void build_wtab_kernel(float4 *__restrict__ wtab, int max_weight)
     wtab[wt] = make_float4((float)wt, rcp_fdividef((float)wp1), __uint_as_float((unsigned)min(wp1, max_weight) << 16), 0.f);
 }
 
-// ---- exact jump of the reference's running sum ---------------------------------------------------------
-// v_{k+1} = RN(v_k + c) with c = a*b exact (fma).  While v stays inside one binade [2^e, 2^(e+1)) its ulp u is
-// constant and v = M*u with an integer mantissa M, so RN(v + c) = (M + RN(c/u))*u unless c/u lies exactly half
-// way between two integers (then tie-to-even depends on M's parity; the code falls back to single steps).
-// Hence n steps inside a binade are one integer multiply-add on M, exactly.  Everything is integer arithmetic
-// (FP64 is slow on this part): c = +-Mc * 2^ec with the 48-bit product of the two mantissas, c/u is a shift of
-// Mc.  The four voxels of a thread share c and nearly always share binade and sign, so the per-step increment
-// is derived once; steps that could leave the binade, and anything irregular (zero, subnormal, huge ratios,
-// ties), are taken as real fma steps.  Bit-identical to n sequential fmas
-// (tests/test_gpu_parity.py::test_integrate_jump_equals_replay).
-__device__ __noinline__ void jump4(float v[4], float a, float b, int n)
-{
-    const unsigned ab = __float_as_uint(a), bb = __float_as_uint(b);
-    const int ea = (int)((ab >> 23) & 0xff), eb = (int)((bb >> 23) & 0xff);
-    const bool c_ok = ea > 0 && ea < 255 && eb > 0 && eb < 255;                       // both normal
-    const unsigned long long Mc = (unsigned long long)((ab & 0x7fffffu) | 0x800000u) * (unsigned long long)((bb & 0x7fffffu) | 0x800000u);
-    const unsigned sc = (ab ^ bb) >> 31;                                               // sign of c
-    if ((ab << 1) == 0u || (bb << 1) == 0u)
-    {
-        // c == +-0: RN(v + c) == v for every step (a -0.0 becomes +0.0 on the first one, as in the reference)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = __fmaf_rn(a, b, v[k]);
-        return;
-    }
-    while (n > 0)
-    {
-        const unsigned v0 = __float_as_uint(v[0]);
-        const int e0 = (int)((v0 >> 23) & 0xff);
-        bool regular = c_ok && n >= 4 && e0 > 0 && e0 < 255;
-        unsigned mmin = 0xffffffffu, mmax = 0u;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-        {
-            const unsigned vb = __float_as_uint(v[k]);
-            regular = regular && ((vb >> 23) == (v0 >> 23));                            // same sign and exponent
-            const unsigned m = (vb & 0x7fffffu) | 0x800000u;
-            mmin = min(mmin, m);
-            mmax = max(mmax, m);
-        }
-        int m_steps = 0;
-        unsigned kq = 0;
-        bool grow = false;
-        if (regular)
-        {
-            // c / u = Mc * 2^sh with sh = (ea - 127) + (eb - 127) - 46 - (e0 - 127 - 23)
-            const int sh = ea + eb - e0 - 150;
-            if (sh >= 0) regular = false;                       // |c| >= 2^46 ulps: leaves the binade at once
-            else
-            {
-                const int t = -sh;
-                if (t >= 49) return;                            // |c| < u/2: every step rounds back, v never moves again
-                const unsigned long long q = Mc >> t, rem = Mc & ((1ull << t) - 1ull), half = 1ull << (t - 1);
-                if (rem == half || q >= (1ull << 24)) regular = false; // tie, or more than a binade per step
-                else
-                {
-                    kq = (unsigned)q + (rem > half ? 1u : 0u);
-                    if (kq == 0u) return;
-                    grow = (sc == (v0 >> 31));                  // |v| grows when c and v have the same sign
-                    const float dist = grow ? (float)(int)(0xffffffu - mmax) : (float)((int)mmin - 0x800001);
-                    // conservative floor(dist / kq): rcp.approx and the multiply err by < 2^-21 relative
-                    const float mf = dist * mufu_rcp((float)kq) * (1.f - 9.5367431640625e-7f);
-                    m_steps = min((int)mf, n);
-                }
-            }
-        }
-        if (regular && m_steps >= 1)
-        {
-            const unsigned add = (unsigned)m_steps * kq;        // <= 2^24
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-            {
-                const unsigned vb = __float_as_uint(v[k]);
-                const unsigned m = (vb & 0x7fffffu) | 0x800000u;
-                const unsigned mn = grow ? m + add : m - add;   // stays in [2^23 + 1, 2^24 - 1]
-                v[k] = __uint_as_float((vb & 0xff800000u) | (mn & 0x7fffffu));
-            }
-            n -= m_steps;
-        }
-        else
-        {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = __fmaf_rn(a, b, v[k]);
-            --n;
-        }
-    }
-}
+// (the exact jump of the reference's running sums, jump_fma<N>, lives in kfb_common.cuh: the raycaster uses it too)
+__device__ __forceinline__ void jump4(float v[4], float a, float b, int n) { jump_fma<4>(v, a, b, n); }
 
 // ---- the update (tsdf_volume.cu:69-79) ---------------------------------------------------
 // generic form, any stored word

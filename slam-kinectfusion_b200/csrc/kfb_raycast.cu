@@ -144,11 +144,56 @@ __device__ __forceinline__ float load_tsdf(const short *addr)
     return __fmul_rn(i2f_magic(s), KFB_DIVSHORTMAX);
 }
 
+// Model pyramid (device::resizePointsNormals, image_process.cu:95-135) from a warp's 8x4 pixel tile: the tile holds
+// complete 2x2 and 4x4 pixel groups, so levels 1 and 2 come from register shuffles in the reference's summation order
+// ((d00 + d01) + d10) + d11, * 0.25, zero when any vertex x is NaN.  All 32 lanes must call it (lane = ty * 8 + tx).
+__device__ __forceinline__ void pyramid_from_tile(float4 vout, float4 nout, int x, int y, int tx, int ty, bool inside, int w0, float4 *const pyr_v[2],
+                                                  float4 *const pyr_n[2])
+{
+    const unsigned FULL = 0xffffffffu;
+
+        float4 v = vout, n = nout;
+        int lw = w0, lx = x, ly = y;
+#pragma unroll
+        for (int l = 1; l <= 2; ++l)
+        {
+            const int dxl = 1 << (l - 1), dyl = 8 << (l - 1); // lane distance of the +x / +y neighbour at this level
+            float4 v01, v10, v11, n01, n10, n11;
+            v01.x = __shfl_down_sync(FULL, v.x, dxl); v01.y = __shfl_down_sync(FULL, v.y, dxl); v01.z = __shfl_down_sync(FULL, v.z, dxl);
+            v10.x = __shfl_down_sync(FULL, v.x, dyl); v10.y = __shfl_down_sync(FULL, v.y, dyl); v10.z = __shfl_down_sync(FULL, v.z, dyl);
+            v11.x = __shfl_down_sync(FULL, v.x, dxl + dyl); v11.y = __shfl_down_sync(FULL, v.y, dxl + dyl); v11.z = __shfl_down_sync(FULL, v.z, dxl + dyl);
+            n01.x = __shfl_down_sync(FULL, n.x, dxl); n01.y = __shfl_down_sync(FULL, n.y, dxl); n01.z = __shfl_down_sync(FULL, n.z, dxl);
+            n10.x = __shfl_down_sync(FULL, n.x, dyl); n10.y = __shfl_down_sync(FULL, n.y, dyl); n10.z = __shfl_down_sync(FULL, n.z, dyl);
+            n11.x = __shfl_down_sync(FULL, n.x, dxl + dyl); n11.y = __shfl_down_sync(FULL, n.y, dxl + dyl); n11.z = __shfl_down_sync(FULL, n.z, dxl + dyl);
+            float4 vo = make_float4(0.f, 0.f, 0.f, 0.f), no = vo;
+            if (!isnan(__fmul_rn(__fmul_rn(__fmul_rn(v.x, v01.x), v10.x), v11.x)))
+            {
+                vo.x = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(v.x, v01.x), v10.x), v11.x), 0.25f);
+                vo.y = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(v.y, v01.y), v10.y), v11.y), 0.25f);
+                vo.z = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(v.z, v01.z), v10.z), v11.z), 0.25f);
+                no.x = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(n.x, n01.x), n10.x), n11.x), 0.25f);
+                no.y = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(n.y, n01.y), n10.y), n11.y), 0.25f);
+                no.z = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(n.z, n01.z), n10.z), n11.z), 0.25f);
+            }
+            v = vo; n = no;
+            lw >>= 1; lx >>= 1; ly >>= 1;
+            const int mask = (1 << l) - 1;
+            if (inside && ((tx & mask) == 0) && ((ty & mask) == 0))
+            {
+                pyr_v[l - 1][ly * lw + lx] = v;
+                pyr_n[l - 1][ly * lw + lx] = n;
+            }
+        }
+}
+
 // The march is warp-cooperative: all rays of an 8x4 tile step together.  When no ray of the warp needs a
 // fetch for its next sample, the warp skips the minimum of the rays' guaranteed-NaN step counts with the
 // running-sum instructions only; otherwise KFB_RC_BATCH steps are classified and their loads issued before
 // the first sign test (sample positions do not depend on fetched values).  Candidate hits are parked and
 // their normals are computed after the march, when the warp has reconverged.
+#ifndef KFB_RC_JUMP_MIN
+#define KFB_RC_JUMP_MIN 192 // steps from which the exact jump of the ray's running sums beats replaying them (4 instructions per step)
+#endif
 #ifndef KFB_RC_WARPS
 #define KFB_RC_WARPS 1 // warps (8x4 pixel tiles, stacked in y) per block; 2 warps with 16 / 18 / 21 blocks per SM measured 155 / 154 / 159 us against 152
 #endif
@@ -251,11 +296,24 @@ __global__ void __launch_bounds__(32 * KFB_RC_WARPS, KFB_RC_MINB) raycast_kernel
                 }
                 if (marching && alive)
                 {
-#pragma unroll 4
-                    for (int i = 0; i < nskip; ++i)
+                    if (SLAB && nskip >= KFB_RC_JUMP_MIN) // whole volumes never skip this far (the brick distance is capped)
                     {
-                        nx = __fmaf_rn(dx, a.vs[0], nx); ny = __fmaf_rn(dy, a.vs[1], ny); nz = __fmaf_rn(dz, a.vs[2], nz);
-                        ray_len = __fadd_rn(ray_len, a.step_len);
+                        // a long run (the way to a far z-slab, a large empty volume): the four running sums are
+                        // advanced by the exact integer jump instead of step by step (kfb_common.cuh: jump_fma)
+                        float t[1];
+                        t[0] = nx; jump_fma<1>(t, dx, a.vs[0], nskip); nx = t[0];
+                        t[0] = ny; jump_fma<1>(t, dy, a.vs[1], nskip); ny = t[0];
+                        t[0] = nz; jump_fma<1>(t, dz, a.vs[2], nskip); nz = t[0];
+                        t[0] = ray_len; jump_fma<1>(t, a.step_len, 1.0f, nskip); ray_len = t[0];
+                    }
+                    else
+                    {
+#pragma unroll 4
+                        for (int i = 0; i < nskip; ++i)
+                        {
+                            nx = __fmaf_rn(dx, a.vs[0], nx); ny = __fmaf_rn(dy, a.vs[1], ny); nz = __fmaf_rn(dz, a.vs[2], nz);
+                            ray_len = __fadd_rn(ray_len, a.step_len);
+                        }
                     }
                 }
                 continue;
@@ -343,44 +401,8 @@ __global__ void __launch_bounds__(32 * KFB_RC_WARPS, KFB_RC_MINB) raycast_kernel
         a.nmap[pix] = nout;
         a.key[pix] = key;
     }
-    // ---- model pyramid (device::resizePointsNormals, image_process.cu:95-135) as an epilogue: the warp tile
-    // holds complete 2x2 and 4x4 pixel groups, so levels 1 and 2 come from register shuffles in the
-    // reference's summation order ((d00 + d01) + d10) + d11, * 0.25, zero when any vertex x is NaN.
-    if (a.fuse_pyramid)
-    {
-        float4 v = vout, n = nout;
-        int lw = a.k.w, lx = x, ly = y;
-#pragma unroll
-        for (int l = 1; l <= 2; ++l)
-        {
-            const int dxl = 1 << (l - 1), dyl = 8 << (l - 1); // lane distance of the +x / +y neighbour at this level
-            float4 v01, v10, v11, n01, n10, n11;
-            v01.x = __shfl_down_sync(FULL, v.x, dxl); v01.y = __shfl_down_sync(FULL, v.y, dxl); v01.z = __shfl_down_sync(FULL, v.z, dxl);
-            v10.x = __shfl_down_sync(FULL, v.x, dyl); v10.y = __shfl_down_sync(FULL, v.y, dyl); v10.z = __shfl_down_sync(FULL, v.z, dyl);
-            v11.x = __shfl_down_sync(FULL, v.x, dxl + dyl); v11.y = __shfl_down_sync(FULL, v.y, dxl + dyl); v11.z = __shfl_down_sync(FULL, v.z, dxl + dyl);
-            n01.x = __shfl_down_sync(FULL, n.x, dxl); n01.y = __shfl_down_sync(FULL, n.y, dxl); n01.z = __shfl_down_sync(FULL, n.z, dxl);
-            n10.x = __shfl_down_sync(FULL, n.x, dyl); n10.y = __shfl_down_sync(FULL, n.y, dyl); n10.z = __shfl_down_sync(FULL, n.z, dyl);
-            n11.x = __shfl_down_sync(FULL, n.x, dxl + dyl); n11.y = __shfl_down_sync(FULL, n.y, dxl + dyl); n11.z = __shfl_down_sync(FULL, n.z, dxl + dyl);
-            float4 vo = make_float4(0.f, 0.f, 0.f, 0.f), no = vo;
-            if (!isnan(__fmul_rn(__fmul_rn(__fmul_rn(v.x, v01.x), v10.x), v11.x)))
-            {
-                vo.x = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(v.x, v01.x), v10.x), v11.x), 0.25f);
-                vo.y = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(v.y, v01.y), v10.y), v11.y), 0.25f);
-                vo.z = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(v.z, v01.z), v10.z), v11.z), 0.25f);
-                no.x = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(n.x, n01.x), n10.x), n11.x), 0.25f);
-                no.y = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(n.y, n01.y), n10.y), n11.y), 0.25f);
-                no.z = __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(n.z, n01.z), n10.z), n11.z), 0.25f);
-            }
-            v = vo; n = no;
-            lw >>= 1; lx >>= 1; ly >>= 1;
-            const int mask = (1 << l) - 1;
-            if (inside && ((threadIdx.x & mask) == 0) && ((threadIdx.y & mask) == 0))
-            {
-                a.pyr_v[l - 1][ly * lw + lx] = v;
-                a.pyr_n[l - 1][ly * lw + lx] = n;
-            }
-        }
-    }
+    // ---- model pyramid as an epilogue of the warp tile (see pyramid_from_tile)
+    if (a.fuse_pyramid) pyramid_from_tile(vout, nout, x, y, threadIdx.x, threadIdx.y & 3, inside, a.k.w, a.pyr_v, a.pyr_n);
 }
 
 // cross-slab composite, step 2 (see include/kfb200.h): keep the payload only where this slab holds the
@@ -414,7 +436,9 @@ struct ShardArgs
     const float4 *maps[16];                  // vertex map, then normal map (contiguous), of every rank's model slot
     const volatile unsigned long long *flag[16];
     float4 *out;                             // rank 0's own model maps
-    int world, self, npix;
+    int world, self, npix, w, h;
+    int fuse_pyramid;                        // write levels 1 and 2 of the model maps from the tiles
+    float4 *pyr_v[2], *pyr_n[2];
     unsigned long long seq;
     unsigned long long *err;                 // mapped host word: set to the frame's sequence number when a peer never signalled
 };
@@ -423,6 +447,10 @@ __global__ void shard_signal_kernel(unsigned long long *flag, unsigned long long
     __threadfence_system(); // the raycast kernel before this launch has completed: publish its results to the peers
     *(volatile unsigned long long *)flag = seq;
 }
+// One pixel per thread, a warp = an 8x4 pixel tile (as in the raycast): all peers' keys of a pixel are requested
+// together (one NVLink round trip), then the winner's vertex and normal (a second one), and -- when the image sizes
+// allow -- the two coarser levels of the model pyramid are written from the tile by register shuffles, exactly as the
+// single-GPU raycast does in its epilogue (no resize launches afterwards).
 __global__ void __launch_bounds__(256) shard_composite_kernel(const ShardArgs a)
 {
     // wait until every slab of this frame has been raycast (flags live in the peers' memory, read over NVLink)
@@ -445,24 +473,30 @@ __global__ void __launch_bounds__(256) shard_composite_kernel(const ShardArgs a)
         __threadfence_system();
     }
     __syncthreads();
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.npix; i += gridDim.x * blockDim.x)
+    const int lane = threadIdx.x & 31, tx = lane & 7, ty = lane >> 3;
+    const int tiles_x = (a.w + 7) >> 3;
+    const int tile = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int x = (tile % tiles_x) * 8 + tx, y = (tile / tiles_x) * 4 + ty;
+    const bool inside = x < a.w && y < a.h;
+    const int i = inside ? y * a.w + x : 0;
+    float best = __int_as_float(0x7f800000);
+    int win = -1;
     {
-        float best = __int_as_float(0x7f800000);
-        int win = -1;
-#pragma unroll 4
-        for (int r = 0; r < a.world; ++r)
-        {
-            const float k = __ldcv(a.keys[r] + i);
-            if (k < best) { best = k; win = r; }
-        }
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f), n = v;
-        if (win >= 0)
-        {
-            v = __ldcv(a.maps[win] + i);
-            n = __ldcv(a.maps[win] + a.npix + i);
-        }
-        if (win != a.self) { a.out[i] = v; a.out[a.npix + i] = n; }
+        float k[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) k[r] = (r < a.world && inside) ? __ldcv(a.keys[r] + i) : __int_as_float(0x7f800000);
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+            if (k[r] < best) { best = k[r]; win = r; }
     }
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), n = v;
+    if (win >= 0)
+    {
+        v = __ldcv(a.maps[win] + i);
+        n = __ldcv(a.maps[win] + a.npix + i);
+    }
+    if (inside && win != a.self) { a.out[i] = v; a.out[a.npix + i] = n; }
+    if (a.fuse_pyramid) pyramid_from_tile(v, n, x, y, tx, ty, inside, a.w, a.pyr_v, a.pyr_n);
 }
 
 int check_device_error(kfb_ctx *ctx)
@@ -494,12 +528,20 @@ int launch_shard_composite(kfb_ctx *ctx)
     }
     a.out = ctx->L[0].v[ctx->prev];
     a.world = ctx->shard_world; a.self = ctx->shard_rank; a.npix = k.w * k.h; a.seq = seq;
+    a.w = k.w; a.h = k.h;
     a.err = ctx->dev_err_dev;
+    a.fuse_pyramid = (ctx->levels == 3 && k.w % 8 == 0 && k.h % 4 == 0 && !getenv("KFB_RAYCAST_NOFUSE")) ? 1 : 0;
+    for (int l = 1; l <= 2; ++l)
+    {
+        a.pyr_v[l - 1] = a.fuse_pyramid ? ctx->L[l].v[ctx->prev] : nullptr;
+        a.pyr_n[l - 1] = a.fuse_pyramid ? ctx->L[l].n[ctx->prev] : nullptr;
+    }
+    const int tiles = ((k.w + 7) / 8) * ((k.h + 3) / 4);
     if (ctx->profiling) cudaEventRecord(ctx->events[52], ctx->stream); // composite (its wait for the slowest slab included): 52 .. 53
-    shard_composite_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(a);
+    shard_composite_kernel<<<(tiles + 7) / 8, 256, 0, ctx->stream>>>(a);
     KFB_LAUNCH_CHECK(ctx);
     if (ctx->profiling) cudaEventRecord(ctx->events[53], ctx->stream);
-    ctx->pyramid_fresh = 0;
+    ctx->pyramid_fresh = a.fuse_pyramid;
     return KFB_OK;
 }
 
