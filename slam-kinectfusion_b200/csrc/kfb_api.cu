@@ -99,7 +99,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->pyramid_fresh = 0;
     ctx->shard_rank = 0; ctx->shard_world = 0; ctx->shard_flag = nullptr; ctx->shard_seq = 0;
     memset(ctx->peer_keys, 0, sizeof(ctx->peer_keys)); memset(ctx->peer_maps, 0, sizeof(ctx->peer_maps)); memset(ctx->peer_flag, 0, sizeof(ctx->peer_flag));
-    ctx->vol = nullptr; ctx->cloud = nullptr; ctx->cloud_cap = 0;
+    ctx->vol = nullptr; ctx->vol_blocked = nullptr; ctx->cloud = nullptr; ctx->cloud_cap = 0;
     ctx->tab_thrz = nullptr; ctx->tab_exact = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->zmip = nullptr; ctx->bricks = nullptr; ctx->states = nullptr; ctx->states_bytes = 0;
     ctx->tab4 = nullptr; ctx->plan_buf = nullptr; ctx->plan_bytes = 0; ctx->plan_hint_host = nullptr; ctx->gen_attr_set = 0;
     ctx->bdist = ctx->bdist_tmp = ctx->bdist_tmp2 = nullptr; ctx->bdirty = nullptr;
@@ -257,6 +257,7 @@ void kfb_destroy(kfb_ctx *ctx)
         for (int f = 0; f < 2; ++f) { if (L.v[f]) cudaFree(L.v[f]); }
     }
     if (ctx->vol) cudaFree(ctx->vol);
+    if (ctx->vol_blocked) cudaFree(ctx->vol_blocked);
     if (ctx->tab_thrz) cudaFree(ctx->tab_thrz);
     if (ctx->wtab) cudaFree(ctx->wtab);
     if (ctx->zexit) cudaFree(ctx->zexit);

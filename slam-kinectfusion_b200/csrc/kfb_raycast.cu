@@ -57,27 +57,38 @@ __device__ __forceinline__ int rn_magic(float v) { return __float_as_int(__fadd_
 // (float)i for |i| < 2^22
 __device__ __forceinline__ float i2f_magic(int i) { return __fsub_rn(__int_as_float(KFB_RC_MAGIC_I + i), KFB_RC_MAGIC_F); }
 
-// SLAB = false: the context stores the whole volume (zs0 = zo0 = bz0 = 0, zs1 = zo1 = Z); the slab tests fold away
-template <bool SLAB>
+// MODE 0: the context stores the whole volume (zs0 = zo0 = bz0 = 0, zs1 = zo1 = Z); the slab tests fold away
+// MODE 1: z-slab (stored planes [zs0, zs1), owned planes [zo0, zo1))
+// MODE 2: whole volume read from a BRICK-MAJOR copy (8x8x8 voxel bricks contiguous, bricks in x, y, z order): the
+//         "L2-friendly voxel layout" experiment of north_star item 4 (KFB_RAYCAST_BLOCKED=1; measured, not adopted:
+//         profiles/README.md)
+enum { RC_WHOLE = 0, RC_SLAB = 1, RC_BLOCKED = 2 };
+template <int MODE>
+__device__ __forceinline__ size_t vox_index(const RaycastArgs &a, int x, int y, int z)
+{
+    if (MODE == RC_BLOCKED)
+        return ((size_t)(((z >> 3) * a.by + (y >> 3)) * a.bx + (x >> 3)) << 9) + (size_t)(((z & 7) << 6) | ((y & 7) << 3) | (x & 7));
+    return ((size_t)(z - (MODE == RC_SLAB ? a.zs0 : 0)) * a.Y + y) * a.X + x;
+}
+template <int MODE>
 __device__ __forceinline__ float vox_tsdf(const RaycastArgs &a, int x, int y, int z)
 {
-    if (SLAB) z = min(max(z, a.zs0), a.zs1 - 1); // slab mode: never read outside the stored planes
-    const size_t i = ((size_t)(z - (SLAB ? a.zs0 : 0)) * a.Y + y) * a.X + x;
-    const short s = __ldg(reinterpret_cast<const short *>(a.vol + i)); // low half = tsdf
+    if (MODE == RC_SLAB) z = min(max(z, a.zs0), a.zs1 - 1); // slab mode: never read outside the stored planes
+    const short s = __ldg(reinterpret_cast<const short *>(a.vol + vox_index<MODE>(a, x, y, z))); // low half = tsdf
     return __fmul_rn((float)s, KFB_DIVSHORTMAX);
 }
 // interpolate (tsdf_volume.cu:137-161)
-template <bool SLAB>
+template <int MODE>
 __device__ float interp(const RaycastArgs &a, float fx, float fy, float fz)
 {
     const int gx = __float2int_rd(fx), gy = __float2int_rd(fy), gz = __float2int_rd(fz);
     if (gx < 0 || gx >= a.X - 1 || gy < 0 || gy >= a.Y - 1 || gz < 0 || gz >= a.Z - 1) return KFB_QNAN;
     const float fa = __fsub_rn(fx, (float)gx), fb = __fsub_rn(fy, (float)gy), fc = __fsub_rn(fz, (float)gz);
     const float a1 = __fsub_rn(1.f, fa), b1 = __fsub_rn(1.f, fb), c1 = __fsub_rn(1.f, fc);
-    const float v000 = vox_tsdf<SLAB>(a, gx, gy, gz), v001 = vox_tsdf<SLAB>(a, gx, gy, gz + 1);
-    const float v010 = vox_tsdf<SLAB>(a, gx, gy + 1, gz), v011 = vox_tsdf<SLAB>(a, gx, gy + 1, gz + 1);
-    const float v100 = vox_tsdf<SLAB>(a, gx + 1, gy, gz), v101 = vox_tsdf<SLAB>(a, gx + 1, gy, gz + 1);
-    const float v110 = vox_tsdf<SLAB>(a, gx + 1, gy + 1, gz), v111 = vox_tsdf<SLAB>(a, gx + 1, gy + 1, gz + 1);
+    const float v000 = vox_tsdf<MODE>(a, gx, gy, gz), v001 = vox_tsdf<MODE>(a, gx, gy, gz + 1);
+    const float v010 = vox_tsdf<MODE>(a, gx, gy + 1, gz), v011 = vox_tsdf<MODE>(a, gx, gy + 1, gz + 1);
+    const float v100 = vox_tsdf<MODE>(a, gx + 1, gy, gz), v101 = vox_tsdf<MODE>(a, gx + 1, gy, gz + 1);
+    const float v110 = vox_tsdf<MODE>(a, gx + 1, gy + 1, gz), v111 = vox_tsdf<MODE>(a, gx + 1, gy + 1, gz + 1);
     float t = 0.f;
     t = __fmaf_rn(__fmul_rn(__fmul_rn(v000, a1), b1), c1, t);
     t = __fmaf_rn(__fmul_rn(__fmul_rn(v001, a1), b1), fc, t);
@@ -104,10 +115,11 @@ enum { ST_FETCH = 0, ST_NAN = 1, ST_LEAVE = 2 };
 // volume interior, outside this slab's stored planes, or in a brick that cannot take part in an event --
 // and `cnt` further steps are guaranteed to be NaN for the same reason.  ST_LEAVE: the ray moves away from
 // the stored planes for good.  `own` = the sample's voxel plane belongs to this slab.
-template <bool SLAB>
+template <int MODE>
 __device__ __forceinline__ int classify(const RaycastArgs &a, const RaySkip &rs, float px, float py, float pz, bool &own,
                                         int &cnt, const short *&addr)
 {
+    constexpr bool SLAB = MODE == RC_SLAB;
     const float qx = __fmul_rn(px, a.vsinv[0]), qy = __fmul_rn(py, a.vsinv[1]), qz = __fmul_rn(pz, a.vsinv[2]);
     const int x = rn_magic(qx), y = rn_magic(qy), z = rn_magic(qz);
     own = false; cnt = 0; addr = nullptr;
@@ -132,7 +144,7 @@ __device__ __forceinline__ int classify(const RaycastArgs &a, const RaySkip &rs,
     const int D = __ldg(a.bdist + ((size_t)((z >> 3) - (SLAB ? a.bz0 : 0)) * a.by + (y >> 3)) * a.bx + (x >> 3));
     if (D == 0)
     {
-        addr = reinterpret_cast<const short *>(a.vol + ((size_t)(z - (SLAB ? a.zs0 : 0)) * a.Y + y) * a.X + x); // low half = tsdf
+        addr = reinterpret_cast<const short *>(a.vol + vox_index<MODE>(a, x, y, z)); // low half = tsdf
         return ST_FETCH;
     }
     cnt = max((D - 1) * 8 - 1, 0);
@@ -200,9 +212,10 @@ __device__ __forceinline__ void pyramid_from_tile(float4 vout, float4 nout, int 
 #ifndef KFB_RC_MINB
 #define KFB_RC_MINB 32 // launch-bounds hint: 32 one-warp blocks per SM (the hardware limit) => at most 64 registers
 #endif
-template <bool SLAB>
+template <int MODE>
 __global__ void __launch_bounds__(32 * KFB_RC_WARPS, KFB_RC_MINB) raycast_kernel(const RaycastArgs a)
 {
+    constexpr bool SLAB = MODE == RC_SLAB;
     const unsigned FULL = 0xffffffffu;
     // block = warp = 8x4 pixel tile (rays of very different length share nothing: fine-grained scheduling)
     const int x = blockIdx.x * 8 + threadIdx.x;
@@ -252,7 +265,7 @@ __global__ void __launch_bounds__(32 * KFB_RC_WARPS, KFB_RC_MINB) raycast_kernel
         ray_len = __fadd_rn(ray_len, a.step_len);
         nx = __fmaf_rn(dx, ray_len, ox); ny = __fmaf_rn(dy, ray_len, oy); nz = __fmaf_rn(dz, ray_len, oz);
         bool own; int cnt; const short *addr;
-        const int st = classify<SLAB>(a, rs, nx, ny, nz, own, cnt, addr);
+        const int st = classify<MODE>(a, rs, nx, ny, nz, own, cnt, addr);
         if (st == ST_FETCH) tnext = load_tsdf(addr);
         if (st == ST_LEAVE) marching = false;
     }
@@ -273,7 +286,7 @@ __global__ void __launch_bounds__(32 * KFB_RC_WARPS, KFB_RC_MINB) raycast_kernel
             const short *addr[KFB_RC_BATCH];
             qx[0] = __fmaf_rn(dx, a.vs[0], nx); qy[0] = __fmaf_rn(dy, a.vs[1], ny); qz[0] = __fmaf_rn(dz, a.vs[2], nz);
             st[0] = ST_NAN; own[0] = false; addr[0] = nullptr;
-            if (alive) st[0] = classify<SLAB>(a, rs, qx[0], qy[0], qz[0], own[0], cnt0, addr[0]);
+            if (alive) st[0] = classify<MODE>(a, rs, qx[0], qy[0], qz[0], own[0], cnt0, addr[0]);
             if (__all_sync(FULL, !alive || st[0] != ST_FETCH))
             {
                 // no ray of the warp needs this sample: it is NaN for all; then skip what every ray can skip.
@@ -325,7 +338,7 @@ __global__ void __launch_bounds__(32 * KFB_RC_WARPS, KFB_RC_MINB) raycast_kernel
                 qx[b] = __fmaf_rn(dx, a.vs[0], qx[b - 1]); qy[b] = __fmaf_rn(dy, a.vs[1], qy[b - 1]); qz[b] = __fmaf_rn(dz, a.vs[2], qz[b - 1]);
                 st[b] = ST_NAN; own[b] = false; addr[b] = nullptr;
                 int c;
-                if (alive) st[b] = classify<SLAB>(a, rs, qx[b], qy[b], qz[b], own[b], c, addr[b]);
+                if (alive) st[b] = classify<MODE>(a, rs, qx[b], qy[b], qz[b], own[b], c, addr[b]);
             }
             float val[KFB_RC_BATCH];
 #pragma unroll
@@ -368,12 +381,12 @@ __global__ void __launch_bounds__(32 * KFB_RC_WARPS, KFB_RC_MINB) raycast_kernel
             const float vx = __fmaf_rn(dx, Ts, ox), vy = __fmaf_rn(dy, Ts, oy), vz = __fmaf_rn(dz, Ts, oz);
             // compute_normal (tsdf_volume.cu:192-209)
             const float ux = __fmul_rn(vx, a.vsinv[0]), uy = __fmul_rn(vy, a.vsinv[1]), uz = __fmul_rn(vz, a.vsinv[2]);
-            const float Fx1 = interp<SLAB>(a, __fmul_rn(__fadd_rn(vx, a.gd[0]), a.vsinv[0]), uy, uz);
-            const float Fx2 = interp<SLAB>(a, __fmul_rn(__fsub_rn(vx, a.gd[0]), a.vsinv[0]), uy, uz);
-            const float Fy1 = interp<SLAB>(a, ux, __fmul_rn(__fadd_rn(vy, a.gd[1]), a.vsinv[1]), uz);
-            const float Fy2 = interp<SLAB>(a, ux, __fmul_rn(__fsub_rn(vy, a.gd[1]), a.vsinv[1]), uz);
-            const float Fz1 = interp<SLAB>(a, ux, uy, __fmul_rn(__fadd_rn(vz, a.gd[2]), a.vsinv[2]));
-            const float Fz2 = interp<SLAB>(a, ux, uy, __fmul_rn(__fsub_rn(vz, a.gd[2]), a.vsinv[2]));
+            const float Fx1 = interp<MODE>(a, __fmul_rn(__fadd_rn(vx, a.gd[0]), a.vsinv[0]), uy, uz);
+            const float Fx2 = interp<MODE>(a, __fmul_rn(__fsub_rn(vx, a.gd[0]), a.vsinv[0]), uy, uz);
+            const float Fy1 = interp<MODE>(a, ux, __fmul_rn(__fadd_rn(vy, a.gd[1]), a.vsinv[1]), uz);
+            const float Fy2 = interp<MODE>(a, ux, __fmul_rn(__fsub_rn(vy, a.gd[1]), a.vsinv[1]), uz);
+            const float Fz1 = interp<MODE>(a, ux, uy, __fmul_rn(__fadd_rn(vz, a.gd[2]), a.vsinv[2]));
+            const float Fz2 = interp<MODE>(a, ux, uy, __fmul_rn(__fsub_rn(vz, a.gd[2]), a.vsinv[2]));
             float gx = __fdividef(__fsub_rn(Fx1, Fx2), a.gd[0]);
             float gy = __fdividef(__fsub_rn(Fy1, Fy2), a.gd[1]);
             float gz = __fdividef(__fsub_rn(Fz1, Fz2), a.gd[2]);
@@ -545,6 +558,19 @@ int launch_shard_composite(kfb_ctx *ctx)
     return KFB_OK;
 }
 
+// linear -> brick-major copy (layout experiment only): a thread moves four consecutive x voxels
+__global__ void relayout_blocked_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int X, int Y, int Z)
+{
+    const size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const size_t nq = ((size_t)X * Y * Z) >> 2;
+    if (q >= nq) return;
+    const size_t i = q << 2;
+    const int x = (int)(i % X), y = (int)((i / X) % Y), z = (int)(i / ((size_t)X * Y));
+    const int bx = X >> 3, by = Y >> 3;
+    const size_t o = ((size_t)(((z >> 3) * by + (y >> 3)) * bx + (x >> 3)) << 9) + (size_t)(((z & 7) << 6) | ((y & 7) << 3) | (x & 7));
+    *reinterpret_cast<uint4 *>(dst + o) = __ldg(reinterpret_cast<const uint4 *>(src + i));
+}
+
 int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9])
 {
     RaycastArgs a;
@@ -580,10 +606,22 @@ int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9]
     }
     ctx->pyramid_fresh = a.fuse_pyramid;
     dim3 block(8, 4 * KFB_RC_WARPS), grid((a.k.w + 7) / 8, (a.k.h + 4 * KFB_RC_WARPS - 1) / (4 * KFB_RC_WARPS));
+    const bool whole_ = a.zs0 == 0 && a.zs1 == a.Z && a.zo0 == 0 && a.zo1 == a.Z && a.bz0 == 0 && !getenv("KFB_RAYCAST_SLABCODE");
+    // layout experiment: march a brick-major copy of the volume (the copy itself is not part of the timed kernel)
+    const bool blocked = whole_ && getenv("KFB_RAYCAST_BLOCKED") && a.X % 8 == 0 && a.Y % 8 == 0 && a.Z % 8 == 0;
+    if (blocked)
+    {
+        if (!ctx->vol_blocked) KFB_CUDA(ctx, cudaMalloc(&ctx->vol_blocked, ctx->vol_voxels * sizeof(uint32_t)));
+        const size_t n4 = ctx->vol_voxels / 4;
+        relayout_blocked_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, ctx->stream>>>(ctx->vol, ctx->vol_blocked, a.X, a.Y, a.Z);
+        KFB_LAUNCH_CHECK(ctx);
+        a.vol = ctx->vol_blocked;
+    }
     if (ctx->profiling) cudaEventRecord(ctx->events[58], ctx->stream);
     const bool whole = a.zs0 == 0 && a.zs1 == a.Z && a.zo0 == 0 && a.zo1 == a.Z && a.bz0 == 0 && !getenv("KFB_RAYCAST_SLABCODE");
-    if (whole) raycast_kernel<false><<<grid, block, 0, ctx->stream>>>(a);
-    else raycast_kernel<true><<<grid, block, 0, ctx->stream>>>(a);
+    if (whole && blocked) raycast_kernel<RC_BLOCKED><<<grid, block, 0, ctx->stream>>>(a);
+    else if (whole) raycast_kernel<RC_WHOLE><<<grid, block, 0, ctx->stream>>>(a);
+    else raycast_kernel<RC_SLAB><<<grid, block, 0, ctx->stream>>>(a);
     KFB_LAUNCH_CHECK(ctx);
     if (ctx->profiling) cudaEventRecord(ctx->events[59], ctx->stream);
     return KFB_OK;
