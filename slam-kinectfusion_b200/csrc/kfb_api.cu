@@ -100,7 +100,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->shard_rank = 0; ctx->shard_world = 0; ctx->shard_flag = nullptr; ctx->shard_seq = 0;
     memset(ctx->peer_keys, 0, sizeof(ctx->peer_keys)); memset(ctx->peer_maps, 0, sizeof(ctx->peer_maps)); memset(ctx->peer_flag, 0, sizeof(ctx->peer_flag));
     ctx->vol = nullptr; ctx->vol_blocked = nullptr; ctx->cloud = nullptr; ctx->cloud_cap = 0;
-    ctx->tab_thrz = nullptr; ctx->tab_exact = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->zmip = nullptr; ctx->bricks = nullptr; ctx->states = nullptr; ctx->states_bytes = 0;
+    ctx->tab_thrz = nullptr; ctx->tab_exact = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->zmip = nullptr; ctx->zsparse = nullptr; ctx->bricks = nullptr; ctx->states = nullptr; ctx->states_bytes = 0;
     ctx->tab4 = nullptr; ctx->plan_buf = nullptr; ctx->plan_bytes = 0; ctx->plan_hint_host = nullptr; ctx->gen_attr_set = 0;
     ctx->bdist = ctx->bdist_tmp = ctx->bdist_tmp2 = nullptr; ctx->bdirty = nullptr;
     ctx->hit_t = nullptr; ctx->icp_partials = nullptr; ctx->icp_ticket = nullptr; ctx->counters = nullptr;
@@ -193,6 +193,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     }
     KFB_CUDA(ctx, cudaMalloc(&ctx->tab_exact, n0 * sizeof(float2)));
     KFB_CUDA(ctx, cudaMalloc(&ctx->tab4, n0 * sizeof(float4)));
+    KFB_CUDA(ctx, cudaMalloc(&ctx->zsparse, 6 * n0 * sizeof(float2)));
     KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->plan_hint_host, 64, cudaHostAllocDefault));
     memset(ctx->plan_hint_host, 0, 64);
     KFB_CUDA(ctx, cudaMalloc(&ctx->hit_t, n0 * sizeof(float)));
@@ -262,6 +263,7 @@ void kfb_destroy(kfb_ctx *ctx)
     if (ctx->wtab) cudaFree(ctx->wtab);
     if (ctx->zexit) cudaFree(ctx->zexit);
     if (ctx->zmip) cudaFree(ctx->zmip);
+    if (ctx->zsparse) cudaFree(ctx->zsparse);
     if (ctx->states) cudaFree(ctx->states);
     if (ctx->bricks) cudaFree(ctx->bricks);
     if (ctx->bdist) cudaFree(ctx->bdist);

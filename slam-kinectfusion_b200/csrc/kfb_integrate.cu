@@ -88,6 +88,8 @@ struct IntegrateArgs
     unsigned long long *counter;
     // ---- work plan (integrate_plan_kernel): the sweep as two lists of (patch, plane range) items ----
     const float4 *tab4;           // per pixel {hi_z, lo_z, depth, 1/lambda}
+    const float2 *zsparse;        // sparse table of {max lo_z, min hi_z}: level k (1..6) at pixel (x, y) covers the 2^k x 2^k window from (x, y)
+    int use_sparse;
     int npx, npy;                 // 16 x 8 voxel patches in x and y
     int mask_words;               // 32-bit words of a patch's "chunk has a general item" mask
     uint2 *items_stream;          // {patch, z0 | z1 << 16}: every voxel of these planes gets tsdf = 1.0f
@@ -271,6 +273,33 @@ __global__ void __launch_bounds__(256) build_zmip_kernel(const float2 *__restric
     }
     __syncthreads();
     if (t == 0) mip[o7 + blockIdx.y * w7 + blockIdx.x] = mm2(mm2(s6[0][0], s6[0][1]), mm2(s6[1][0], s6[1][1]));
+}
+
+// Sparse table over the image of {max lo_z, min hi_z}: level k holds, at EVERY pixel (x, y), the extremes over the
+// 2^k x 2^k window that starts there (clipped to the image).  A pixel rectangle of any position and size is then
+// covered exactly by a few overlapping windows -- no tile alignment, no slop: the plan's free-space prefix and
+// occlusion cut see precisely the pixels a patch can land on (the tile pyramid above widens the rectangle to whole
+// tiles, by up to half its size again; on surfaces seen at a grazing angle every extra pixel costs planes).
+// Level k from level k - 1 (h = 2^(k-1)); level 1 straight from the per-pixel thresholds.
+__global__ void __launch_bounds__(256) build_zsparse_kernel(const float2 *__restrict__ thrz, const float2 *__restrict__ prev, float2 *__restrict__ cur, int w, int h,
+                                                            int half)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= w || y >= h) return;
+    float2 m = make_float2(-1.f, 3.0e38f);
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+        {
+            const int xx = x + i * half, yy = y + j * half;
+            if (xx < w && yy < h)
+            {
+                if (prev) m = mm2(m, __ldg(prev + (size_t)yy * w + xx));
+                else { const float2 th = __ldg(thrz + (size_t)yy * w + xx); m = mm2(m, make_float2(th.y, th.x)); } // {hi_z, lo_z} -> {lo_z, hi_z}
+            }
+        }
+    cur[(size_t)y * w + x] = m;
 }
 
 // wtab[wt] = {(float)wt, MUFU.RCP(wt + 1), bits(min(wt + 1, max_weight) << 16), 0}: the weight-dependent
@@ -938,18 +967,45 @@ __global__ void __launch_bounds__(128) integrate_plan_kernel(const IntegrateArgs
                     const int l = max(32 - __clz(span - 1) - 2, 2); // tiles a quarter of the span wide: at most 5 x 5 cover the rectangle
                     if (l <= 7)
                     {
-                        const float2 *m = a.zmip + a.mip_off[l - 2];
-                        const int mw = a.mip_w[l - 2];
-                        const int tx0 = u0 >> l, tx1 = u1 >> l, ty0 = v0 >> l, ty1 = v1 >> l;
-                        // 25 loads in flight; tiles beyond the rectangle repeat its last one (harmless for min / max)
                         float2 q = make_float2(-1.f, 3.0e38f);
-                        float2 tl[25];
+                        if (a.use_sparse)
+                        {
+                            // exact cover of the rectangle by overlapping 2^k x 2^k windows of the sparse table: k from
+                            // the shorter side, raised until five windows reach along the longer one
+                            const int W = u1 - u0 + 1, H = v1 - v0 + 1;
+                            int k = min(max(31 - __clz(min(W, H)), 1), 6);
+                            while (k < 6 && ((max(W, H) + (1 << k) - 1) >> k) > 5) ++k;
+                            const int sw = 1 << k;
+                            if (((max(W, H) + sw - 1) >> k) > 5) q = make_float2(3.0e38f, -1.f); // wider than 5 x 64 pixels: decide per voxel
+                            else
+                            {
+                                const float2 *m = a.zsparse + (size_t)(k - 1) * a.w * a.h;
+                                const int xl = max(u0, u1 - sw + 1), yl = max(v0, v1 - sw + 1), ny = (H + sw - 1) >> k;
+                                for (int j = 0; j < ny; ++j)
+                                {
+                                    const int yy = min(v0 + j * sw, yl);
+                                    float2 tl[5];
 #pragma unroll
-                        for (int j = 0; j < 5; ++j)
+                                    for (int i = 0; i < 5; ++i) tl[i] = __ldg(m + (size_t)yy * a.w + min(u0 + i * sw, xl));
 #pragma unroll
-                            for (int i = 0; i < 5; ++i) tl[j * 5 + i] = __ldg(m + min(ty0 + j, ty1) * mw + min(tx0 + i, tx1));
+                                    for (int i = 0; i < 5; ++i) q = mm2(q, tl[i]);
+                                }
+                            }
+                        }
+                        else
+                        {
+                            const float2 *m = a.zmip + a.mip_off[l - 2];
+                            const int mw = a.mip_w[l - 2];
+                            const int tx0 = u0 >> l, tx1 = u1 >> l, ty0 = v0 >> l, ty1 = v1 >> l;
+                            // 25 loads in flight; tiles beyond the rectangle repeat its last one (harmless for min / max)
+                            float2 tl[25];
 #pragma unroll
-                        for (int i = 0; i < 25; ++i) q = mm2(q, tl[i]);
+                            for (int j = 0; j < 5; ++j)
+#pragma unroll
+                                for (int i = 0; i < 5; ++i) tl[j * 5 + i] = __ldg(m + min(ty0 + j, ty1) * mw + min(tx0 + i, tx1));
+#pragma unroll
+                            for (int i = 0; i < 25; ++i) q = mm2(q, tl[i]);
+                        }
                         const float zmin0 = fminf(fminf(cz[0], cz[1]), fminf(cz[2], cz[3])), zmax0 = fmaxf(fmaxf(cz[0], cz[1]), fmaxf(cz[2], cz[3]));
                         const float e2 = 2.f * a.driftE;
                         const float zc = (q.x + e2 - zmin0) * a.invSz + 1.f;
@@ -1531,6 +1587,16 @@ int launch_build_tables(kfb_ctx *ctx, cudaStream_t stream)
     build_zmip_kernel<<<mg, 256, 0, stream>>>(ctx->tab_thrz, k.w, k.h, ctx->zmip, ctx->mip_off[0], ctx->mip_off[1], ctx->mip_off[2],
                                               ctx->mip_off[3], ctx->mip_off[4], ctx->mip_off[5]);
     KFB_LAUNCH_CHECK(ctx);
+    {
+        const size_t n0 = (size_t)k.w * k.h;
+        dim3 sg((k.w + 31) / 32, (k.h + 7) / 8);
+        for (int lv = 1; lv <= 6; ++lv)
+        {
+            build_zsparse_kernel<<<sg, 256, 0, stream>>>(ctx->tab_thrz, lv == 1 ? nullptr : ctx->zsparse + (size_t)(lv - 2) * n0,
+                                                        ctx->zsparse + (size_t)(lv - 1) * n0, k.w, k.h, 1 << (lv - 1));
+            KFB_LAUNCH_CHECK(ctx);
+        }
+    }
     return KFB_OK;
 }
 
@@ -1743,6 +1809,8 @@ static void fill_integrate_args(kfb_ctx *ctx, const float vol2cam12[12], Integra
         for (int c = 0; c < KFB_NCULL; ++c) a.cull[c].kind = 3;
 
     a.tab4 = ctx->tab4;
+    a.zsparse = ctx->zsparse;
+    a.use_sparse = (ctx->zsparse && !getenv("KFB_PLAN_TILES")) ? 1 : 0;
 }
 
 int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_updated)

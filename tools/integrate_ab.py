@@ -16,16 +16,15 @@ from slam_kinectfusion_b200 import synth  # noqa: E402
 
 VARIANTS = {
     "v1 (round-1 kernel)": {"KFB_INTEGRATE_V1": "1"},
+    "planned, tile pyramid": {"KFB_PLAN_TILES": "1"},
     "planned, serial": {"KFB_INTEGRATE_SERIAL": "1"},
     "planned zchunk16": {"KFB_PLAN_ZCHUNK": "16"},
-    "planned zchunk8 refine": {"KFB_PLAN_ZCHUNK": "8", "KFB_INTEGRATE_REFINE": "1"},
-    "planned zchunk12": {"KFB_PLAN_ZCHUNK": "12"},
     "planned zchunk6": {"KFB_PLAN_ZCHUNK": "6"},
-    "planned minb6": {"KFB_GEN_MINB": "6"},
+    "planned zchunk4": {"KFB_PLAN_ZCHUNK": "4"},
     "planned (default)": {},
 }
 SWITCHES = ("KFB_INTEGRATE_V1", "KFB_INTEGRATE_SERIAL", "KFB_INTEGRATE_PERSISTENT", "KFB_GEN_MINB", "KFB_BRICKS_3PASS", "KFB_PLAN_ZCHUNK",
-            "KFB_INTEGRATE_NOPREFIX", "KFB_INTEGRATE_REFINE")
+            "KFB_INTEGRATE_NOPREFIX", "KFB_INTEGRATE_REFINE", "KFB_PLAN_TILES")
 
 
 def main():
