@@ -14,9 +14,13 @@
  *            (r00 r01 r02 tx r10 r11 r12 ty r20 r21 r22 tz) == cv::Affine3f::matrix.val[0..11]
  *   map3   : float3 array-of-structs, 12 B per pixel, row-major (the reference's
  *            continuous CV_32FC3 GpuMat, types.hpp:45-46); device storage is float4
- *   volume : packed {int16 tsdf, int16 weight} voxels, linear index
- *            x + y*X + z*X*Y (device_utils.cuh:30-37); the reference's 3 colour
- *            bytes are write-only dead state and are dropped
+ *   volume : packed {int16 tsdf, int16 weight} voxels; the reference's 3 colour
+ *            bytes are write-only dead state and are dropped.
+ *            Hosts exchange volumes in the reference's linear order x + y*X + z*X*Y
+ *            (device_utils.cuh:30-37); in HBM the voxels live in 8x8x8 bricks of 2 KB
+ *            (bricks in x, y, z order, voxels inside a brick in x, y, z order, dims
+ *            padded to whole bricks): the layout the raycaster's gathers and the
+ *            sweep's patches want.  dims[0] % 4 == 0 is required (128-bit accesses).
  *   Threading: one host thread per context; all work runs on a context-owned
  *            non-blocking CUDA stream.  Functions that return host data block
  *            until that data is valid; the others only enqueue.
@@ -210,7 +214,7 @@ int kfb_event_elapsed_ms(kfb_ctx *ctx, int slot_a, int slot_b, float *ms);
 int kfb_set_profiling(kfb_ctx *ctx, int on);
 /* number of kernels this library has launched on this context since creation */
 uint64_t kfb_launch_count(const kfb_ctx *ctx);
-/* raw device pointers for zero-copy interop (NCCL / torch views); which: 0 volume,
+/* raw device pointers for zero-copy interop (NCCL / torch views); which: 0 volume (brick-major, see "volume" above),
  * 1 prev vmap L0 (float4; the nmap follows it contiguously), 2 prev nmap L0 (float4), 3 cur depth L0 (float),
  * 4 raycast event keys (float) */
 void *kfb_device_ptr(kfb_ctx *ctx, int which);

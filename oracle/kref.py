@@ -132,7 +132,8 @@ class RefKinfu:
         return p
 
     def sync_from(self, vol_packed_dev, vmap4_dev, nmap4_dev, pose12, frame_count):
-        """Adopt another pipeline's state (device pointers, same process): packed 4-byte voxels, float4 model
+        """Adopt another pipeline's state (device pointers, same process): packed 4-byte voxels in the product's
+        brick-major order (kfb_device_ptr(ctx, 0) of a whole-volume context), float4 model
         maps of level 0, camera pose.  The caller has synchronised the producer's stream."""
         p = _f(pose12)
         lib().ref_kinfu_sync_from(self.h, _vp(int(vol_packed_dev)), _vp(int(vmap4_dev)), _vp(int(nmap4_dev)), _p(p), int(frame_count))

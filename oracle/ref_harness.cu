@@ -517,17 +517,23 @@ float ref_event_ms(int which) // 0: tic now, 1: toc -> ms since tic (legacy defa
 } // extern "C"
 
 // ---- lock-step checking (tests/test_ref_full.py): put the reference loop into the state of another pipeline ----
-// vol_packed: device pointer to packed {int16 tsdf, int16 weight} voxels in the reference's index order;
+// vol_packed: device pointer to the product's volume (kfb_device_ptr(ctx, 0): packed voxels, brick-major);
 // vmap4 / nmap4: device pointers to level-0 model maps as float4 (w unused); pose12: camera pose.  Everything is
 // converted on the device into the reference's own layouts (8-byte Voxel, float3 maps); the coarser model levels are
 // rebuilt with the reference's resizePointsNormals, as its frame loop does after every raycast.
 namespace
 {
-__global__ void unpack_volume(const uint32_t *src, Voxel *dst, size_t n)
+// src: the product's brick-major volume (8x8x8 voxel bricks of packed {int16 tsdf, int16 weight}, bricks and voxels
+// in x, y, z order, dims padded to whole bricks); dst: the reference's linear array of 8-byte voxels
+__global__ void unpack_volume(const uint32_t *src, Voxel *dst, int X, int Y, int Z)
 {
+    const size_t n = (size_t)X * Y * Z;
+    const int bx = (X + 7) >> 3, by = (Y + 7) >> 3;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     {
-        const uint32_t w = src[i];
+        const int x = (int)(i % X), y = (int)((i / X) % Y), z = (int)(i / ((size_t)X * Y));
+        const size_t b = ((size_t)(((z >> 3) * by + (y >> 3)) * bx + (x >> 3)) << 9) + (size_t)(((z & 7) << 6) | ((y & 7) << 3) | (x & 7));
+        const uint32_t w = src[b];
         Voxel v;
         memset(&v, 0, sizeof(v));
         v.tsdf = (short)(w & 0xffffu);
@@ -544,8 +550,7 @@ __global__ void f4_to_f3(const float4 *src, float3 *dst, int n)
 extern "C" void ref_kinfu_sync_from(void *hnd, const void *vol_packed, const void *vmap4, const void *nmap4, const float pose12[12], int frame_count)
 {
     RefKinfu *k = (RefKinfu *)hnd;
-    const size_t n = (size_t)k->dims[0] * k->dims[1] * k->dims[2];
-    unpack_volume<<<148 * 8, 256>>>((const uint32_t *)vol_packed, (Voxel *)k->vol->p, n);
+    unpack_volume<<<148 * 8, 256>>>((const uint32_t *)vol_packed, (Voxel *)k->vol->p, k->dims[0], k->dims[1], k->dims[2]);
     const int np = k->w * k->h;
     f4_to_f3<<<(np + 255) / 256, 256>>>((const float4 *)vmap4, (float3 *)k->prev.v[0]->p, np);
     f4_to_f3<<<(np + 255) / 256, 256>>>((const float4 *)nmap4, (float3 *)k->prev.n[0]->p, np);

@@ -99,8 +99,8 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->pyramid_fresh = 0;
     ctx->shard_rank = 0; ctx->shard_world = 0; ctx->shard_flag = nullptr; ctx->shard_seq = 0;
     memset(ctx->peer_keys, 0, sizeof(ctx->peer_keys)); memset(ctx->peer_maps, 0, sizeof(ctx->peer_maps)); memset(ctx->peer_flag, 0, sizeof(ctx->peer_flag));
-    ctx->vol = nullptr; ctx->vol_blocked = nullptr; ctx->cloud = nullptr; ctx->cloud_cap = 0;
-    ctx->tab_thrz = nullptr; ctx->tab_exact = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->zmip = nullptr; ctx->zsparse = nullptr; ctx->bricks = nullptr; ctx->states = nullptr; ctx->states_bytes = 0;
+    ctx->vol = nullptr; ctx->cloud = nullptr; ctx->cloud_cap = 0;
+    ctx->tab_thrz = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->zsparse = nullptr; ctx->bricks = nullptr;
     ctx->tab4 = nullptr; ctx->plan_buf = nullptr; ctx->plan_bytes = 0; ctx->plan_hint_host = nullptr; ctx->gen_attr_set = 0;
     ctx->bdist = ctx->bdist_tmp = ctx->bdist_tmp2 = nullptr; ctx->bdirty = nullptr;
     ctx->hit_t = nullptr; ctx->icp_partials = nullptr; ctx->icp_ticket = nullptr; ctx->counters = nullptr;
@@ -162,27 +162,20 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
         ctx->z1 = p->slab_z_end + KFB_HALO > Z ? Z : p->slab_z_end + KFB_HALO;
     }
     else { ctx->z0 = 0; ctx->z1 = Z; }
-    ctx->vol_voxels = (size_t)p->volu_dims[0] * p->volu_dims[1] * (size_t)(ctx->z1 - ctx->z0);
+    ctx->vol_logical = (size_t)p->volu_dims[0] * p->volu_dims[1] * (size_t)(ctx->z1 - ctx->z0);
     for (int i = 0; i < 3; ++i) ctx->voxel_size[i] = p->volu_range[i] / (float)p->volu_dims[i]; // tsdf_volume.cpp:16
+    // brick grid of the stored planes: of the voxels (vol_index) and of the brick flags / distance map alike
+    ctx->bdim[0] = (p->volu_dims[0] + 7) >> 3;
+    ctx->bdim[1] = (p->volu_dims[1] + 7) >> 3;
+    ctx->bz0 = ctx->z0 >> 3;
+    ctx->bdim[2] = ((ctx->z1 - 1) >> 3) - ctx->bz0 + 1;
+    ctx->vol_voxels = ((size_t)ctx->bdim[0] * ctx->bdim[1] * ctx->bdim[2]) << 9;
     KFB_CUDA(ctx, cudaMalloc(&ctx->vol, ctx->vol_voxels * sizeof(uint32_t)));
     const size_t n0 = (size_t)intr->width * intr->height;
     KFB_CUDA(ctx, cudaMalloc(&ctx->tab_thrz, n0 * sizeof(float2)));
     if (p->tsdf_max_weight < 1 || p->tsdf_max_weight > 32767) { ctx->err = "tsdf_max_weight must be in [1, 32767]"; return KFB_ERR_INVALID; }
     KFB_CUDA(ctx, cudaMalloc(&ctx->wtab, (size_t)(p->tsdf_max_weight + 1) * sizeof(float4)));
     KFB_CUDA(ctx, cudaMalloc(&ctx->zexit, sizeof(float)));
-    {
-        int off = 0;
-        for (int i = 0; i < 6; ++i)
-        {
-            ctx->mip_off[i] = off;
-            off += ((intr->width + (1 << (i + 2)) - 1) >> (i + 2)) * ((intr->height + (1 << (i + 2)) - 1) >> (i + 2));
-        }
-        KFB_CUDA(ctx, cudaMalloc(&ctx->zmip, (size_t)off * sizeof(float2)));
-    }
-    ctx->bdim[0] = (p->volu_dims[0] + 7) >> 3;
-    ctx->bdim[1] = (p->volu_dims[1] + 7) >> 3;
-    ctx->bz0 = ctx->z0 >> 3;
-    ctx->bdim[2] = ((ctx->z1 - 1) >> 3) - ctx->bz0 + 1;
     {
         const size_t nb = (size_t)ctx->bdim[0] * ctx->bdim[1] * ctx->bdim[2];
         KFB_CUDA(ctx, cudaMalloc(&ctx->bricks, nb));
@@ -191,7 +184,6 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
         KFB_CUDA(ctx, cudaMalloc(&ctx->bdist_tmp2, nb));
         KFB_CUDA(ctx, cudaMalloc(&ctx->bdirty, sizeof(int)));
     }
-    KFB_CUDA(ctx, cudaMalloc(&ctx->tab_exact, n0 * sizeof(float2)));
     KFB_CUDA(ctx, cudaMalloc(&ctx->tab4, n0 * sizeof(float4)));
     KFB_CUDA(ctx, cudaMalloc(&ctx->zsparse, 6 * n0 * sizeof(float2)));
     KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->plan_hint_host, 64, cudaHostAllocDefault));
@@ -258,19 +250,15 @@ void kfb_destroy(kfb_ctx *ctx)
         for (int f = 0; f < 2; ++f) { if (L.v[f]) cudaFree(L.v[f]); }
     }
     if (ctx->vol) cudaFree(ctx->vol);
-    if (ctx->vol_blocked) cudaFree(ctx->vol_blocked);
     if (ctx->tab_thrz) cudaFree(ctx->tab_thrz);
     if (ctx->wtab) cudaFree(ctx->wtab);
     if (ctx->zexit) cudaFree(ctx->zexit);
-    if (ctx->zmip) cudaFree(ctx->zmip);
     if (ctx->zsparse) cudaFree(ctx->zsparse);
-    if (ctx->states) cudaFree(ctx->states);
     if (ctx->bricks) cudaFree(ctx->bricks);
     if (ctx->bdist) cudaFree(ctx->bdist);
     if (ctx->bdist_tmp) cudaFree(ctx->bdist_tmp);
     if (ctx->bdist_tmp2) cudaFree(ctx->bdist_tmp2);
     if (ctx->bdirty) cudaFree(ctx->bdirty);
-    if (ctx->tab_exact) cudaFree(ctx->tab_exact);
     if (ctx->tab4) cudaFree(ctx->tab4);
     if (ctx->plan_buf) cudaFree(ctx->plan_buf);
     if (ctx->plan_hint_host) cudaFreeHost(ctx->plan_hint_host);
@@ -339,7 +327,7 @@ int kfb_reset_frames(kfb_ctx *ctx)
             KFB_CUDA(ctx, cudaMemsetAsync(L.n[f], 0, n * sizeof(float4), ctx->stream));
         }
     }
-    if (ctx->zmip)
+    if (ctx->zsparse)
     {
         const int rc = launch_build_tables(ctx, ctx->stream); // tables of the (now empty) depth image
         if (rc) return rc;
@@ -625,21 +613,17 @@ int kfb_upload_maps(kfb_ctx *ctx, int frame, int level, const float *host_v3, co
     if (rc == KFB_ERR_CUDA && ctx->err.empty()) ctx->err = cudaGetErrorString(cudaGetLastError());
     return rc;
 }
-int kfb_download_volume(kfb_ctx *ctx, int16_t *host)
-{
-    KFB_CUDA(ctx, cudaMemcpyAsync(host, ctx->vol, ctx->vol_voxels * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return KFB_OK;
-}
+int kfb_download_volume(kfb_ctx *ctx, int16_t *host) { return launch_volume_copy(ctx, host, 0); }
 int kfb_upload_volume(kfb_ctx *ctx, const int16_t *host)
 {
-    KFB_CUDA(ctx, cudaMemcpyAsync(ctx->vol, host, ctx->vol_voxels * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    const int rc = launch_rebuild_bricks(ctx);
+    int rc = launch_volume_copy(ctx, const_cast<int16_t *>(host), 1);
+    if (rc) return rc;
+    rc = launch_rebuild_bricks(ctx);
     if (rc) return rc;
     KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return KFB_OK;
 }
-size_t kfb_volume_voxels(const kfb_ctx *ctx) { return ctx->vol_voxels; }
+size_t kfb_volume_voxels(const kfb_ctx *ctx) { return ctx->vol_logical; }
 
 // ---- measurement ------------------------------------------------------------------------------------
 int kfb_event_record(kfb_ctx *ctx, int slot)

@@ -16,11 +16,10 @@ namespace kfb
 
 struct ExtractArgs
 {
-    const uint32_t *vol;
+    const uint32_t *vol; // brick-major (kfb_common.cuh: vol_index)
     int X, Y, Z;      // global dims
-    int z_store0;     // first stored plane
+    int bx, by, bz0;  // brick grid of the stored planes
     int zb, ze;       // planes whose voxels this context owns: [zb, ze)
-    int z_avail;      // planes [z_store0, z_avail) are readable (for the +z neighbour)
     float vs[3];
     Pose aff;
     float *out;       // xyz triples
@@ -39,13 +38,11 @@ __global__ void __launch_bounds__(256) extract_kernel(const ExtractArgs a)
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int y = blockIdx.y * 8 + threadIdx.y;
     const bool inside = x < a.X && y < a.Y;
-    const size_t plane = (size_t)a.X * a.Y;
     const float Vx = __fmul_rn(__fadd_rn((float)x, 0.5f), a.vs[0]);
     const float Vy = __fmul_rn(__fadd_rn((float)y, 0.5f), a.vs[1]);
-    const uint32_t *col = a.vol + (size_t)y * a.X + x;
     const int zlast = min(a.ze, a.Z - 1); // z + 1 must exist (tsdf_volume.cu:340)
     uint32_t wz = 0;
-    if (inside && a.zb < zlast) wz = __ldg(col + (size_t)(a.zb - a.z_store0) * plane);
+    if (inside && a.zb < zlast) wz = __ldg(a.vol + vol_index(a.bx, a.by, a.bz0, x, y, a.zb));
     const unsigned lane = threadIdx.x; // blockDim.x == 32
     for (int z = a.zb; z < zlast; ++z)
     {
@@ -54,8 +51,7 @@ __global__ void __launch_bounds__(256) extract_kernel(const ExtractArgs a)
         uint32_t wnext = 0;
         if (inside)
         {
-            const uint32_t *p = col + (size_t)(z - a.z_store0) * plane;
-            wnext = __ldg(p + plane);
+            wnext = __ldg(a.vol + vol_index(a.bx, a.by, a.bz0, x, y, z + 1));
             float F; int W;
             unpack(wz, F, W);
             if (W != 0 && F != 1.f)
@@ -65,8 +61,8 @@ __global__ void __launch_bounds__(256) extract_kernel(const ExtractArgs a)
                 for (int axis = 0; axis < 3; ++axis)
                 {
                     uint32_t wn;
-                    if (axis == 0) { if (x + 1 >= a.X) continue; wn = __ldg(p + 1); }
-                    else if (axis == 1) { if (y + 1 >= a.Y) continue; wn = __ldg(p + a.X); }
+                    if (axis == 0) { if (x + 1 >= a.X) continue; wn = __ldg(a.vol + vol_index(a.bx, a.by, a.bz0, x + 1, y, z)); }
+                    else if (axis == 1) { if (y + 1 >= a.Y) continue; wn = __ldg(a.vol + vol_index(a.bx, a.by, a.bz0, x, y + 1, z)); }
                     else wn = wnext;
                     float Fn; int Wn;
                     unpack(wn, Fn, Wn);
@@ -130,11 +126,10 @@ int launch_extract(kfb_ctx *ctx, const float volpose12[12], float *host_points3,
     ExtractArgs a;
     a.vol = ctx->vol;
     a.X = ctx->p.volu_dims[0]; a.Y = ctx->p.volu_dims[1]; a.Z = ctx->p.volu_dims[2];
-    a.z_store0 = ctx->z0;
+    a.bx = ctx->bdim[0]; a.by = ctx->bdim[1]; a.bz0 = ctx->bz0;
     const bool slab = ctx->p.slab_z_end > ctx->p.slab_z_begin;
     a.zb = slab ? ctx->p.slab_z_begin : 0;
     a.ze = slab ? ctx->p.slab_z_end : a.Z;
-    a.z_avail = ctx->z1;
     for (int i = 0; i < 3; ++i) a.vs[i] = ctx->voxel_size[i];
     a.aff = make_pose(volpose12);
     a.out = ctx->cloud;

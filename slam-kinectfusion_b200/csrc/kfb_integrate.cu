@@ -56,40 +56,30 @@ struct CullPlane // conservative half-line in z: g0(x, y) + z * g1 >= 0
 
 struct IntegrateArgs
 {
-    uint32_t *vol;
+    uint32_t *vol;  // brick-major packed voxels (kfb_common.cuh: vol_index)
     int X, Y;
-    int z_store0;   // global z of the first stored plane
     int zb, ze;     // global planes to process: [zb, ze), zb >= 1
-    int zchunk;     // planes per blockIdx.z
+    int zchunk;     // planes per plan chunk
+    int nchunks;
     Pose pose;      // vol2cam
     float vsx, vsy, vsz;
     float trunc;
     float fx, fy, cx, cy;
     int w, h;
-    const float2 *thrz;
-    unsigned long long *states; // [chunk][6][X/4 * Y]: packed vc of every thread after plane zstart(chunk) - 1
-    int2 *col_range;            // [X/4 * Y]: first and last plane of the column group's frustum interval (empty: {1, 0})
-    int nchunks;
-    const float2 *exact;
     const float4 *wtab;
     const float *zexit;
-    const float2 *zmip;         // pyramid of {max lo_z, min hi_z}, levels 2..7 (tiles of 4..128 px), see build_zmip_kernel
-    int mip_off[6], mip_w[6];
     float Sx, Sy, Sz, invSz, driftE; // per-plane step of vc (float), 1/Sz, bound on the running-sum drift
     int max_weight;
-    int no_fastpath;            // KFB_INTEGRATE_NOFAST: disable the deep-free-space path (tuning / testing)
-    int no_prefix;              // KFB_INTEGRATE_NOPREFIX: fast path only for warps whose whole interval is free space
-    int diag;                   // KFB_INTEGRATE_DIAG (timing experiments ONLY, results are wrong): 1 = general-path warps return, 2 = fast-path warps return
-    int use_jump, jump_min; // exact jump of the running sum for prefixes of at least jump_min planes
+    int no_fastpath;            // KFB_INTEGRATE_NOFAST: no stream items (tuning / testing)
+    int use_jump, jump_min;     // exact jump of the running sum for prefixes of at least jump_min planes
     uint8_t *bricks;
     int *bdirty;         // set when a brick flag flips 0 -> 1 (the distance map must be rebuilt)
-    int bx, by, bz, bz0; // brick grid dims (x, y, stored z bricks) and first stored z brick
+    int bx, by, bz, bz0; // brick grid dims (x, y, stored z bricks) and first stored z brick -- of the flags AND of the voxels
     CullPlane cull[KFB_NCULL];
     unsigned long long *counter;
     // ---- work plan (integrate_plan_kernel): the sweep as two lists of (patch, plane range) items ----
     const float4 *tab4;           // per pixel {hi_z, lo_z, depth, 1/lambda}
     const float2 *zsparse;        // sparse table of {max lo_z, min hi_z}: level k (1..6) at pixel (x, y) covers the 2^k x 2^k window from (x, y)
-    int use_sparse;
     int npx, npy;                 // 16 x 8 voxel patches in x and y
     int mask_words;               // 32-bit words of a patch's "chunk has a general item" mask
     uint2 *items_stream;          // {patch, z0 | z1 << 16}: every voxel of these planes gets tsdf = 1.0f
@@ -99,7 +89,6 @@ struct IntegrateArgs
     unsigned int *slot_of;        // [patch][chunk] -> general item index
     unsigned long long *gstates;  // [general item][6][32]: packed vc of the item's 32 threads after plane zstart(chunk) - 1
     int gstate_cap;               // general items that have a state slot (the others replay their running sums)
-    int refine;                   // KFB_INTEGRATE_REFINE: per-thread refinement of a general item's plane range (measured slower; kept for experiments)
 };
 
 #define KFB_MAGIC_F 12582912.0f   // 1.5 * 2^23
@@ -162,8 +151,7 @@ __device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsign
 // skip; NaN depth makes sdf NaN, which fails `sdf >= -trunc`).
 // *zexit = max lo_z over the image: a voxel with vc.z above it is rejected whatever pixel it lands on.
 __global__ void build_tables_kernel(const float *__restrict__ depth, int w, int h, float fx, float fy, float cx,
-                                    float cy, float trunc, float2 *__restrict__ thrz, float2 *__restrict__ exact,
-                                    float4 *__restrict__ tab4, float *__restrict__ zexit)
+                                    float cy, float trunc, float2 *__restrict__ thrz, float4 *__restrict__ tab4, float *__restrict__ zexit)
 {
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y * blockDim.y + threadIdx.y;
@@ -176,7 +164,6 @@ __global__ void build_tables_kernel(const float *__restrict__ depth, int w, int 
         const float ly = __fmul_rn(rcp_fdividef(fy), __fsub_rn((float)v, cy));
         const float lam = __fsqrt_rn(__fadd_rn(__fmaf_rn(lx, lx, __fmul_rn(ly, ly)), 1.0f));
         const float il = rcp_fdividef(lam);
-        exact[p] = make_float2(d, il);
         float hi_z = -1.f;
         if (d > 0.f)
         {
@@ -206,75 +193,7 @@ __global__ void build_tables_kernel(const float *__restrict__ depth, int w, int 
     if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && lo_z > 0.f) atomicMax((int *)zexit, __float_as_int(lo_z));
 }
 
-// Pyramid over the image of {max lo_z, min hi_z}: level l (2..7) holds, per 2^l x 2^l pixel tile, the largest
-// vc.z any pixel of the tile would still accept and the largest vc.z that is free space (tsdf == 1) for EVERY
-// pixel of the tile (-1 as soon as one pixel has no valid depth).  One block builds all levels of a 128 x 128
-// pixel region.
-__device__ __forceinline__ float2 mm2(float2 a, float2 b) { return make_float2(fmaxf(a.x, b.x), fminf(a.y, b.y)); }
-__global__ void __launch_bounds__(256) build_zmip_kernel(const float2 *__restrict__ thrz, int w, int h, float2 *__restrict__ mip,
-                                                         int o2, int o3, int o4, int o5, int o6, int o7)
-{
-    __shared__ float2 s2[32][33], s3[16][17], s4[8][9], s5[4][5], s6[2][3];
-    const int rx = blockIdx.x * 128, ry = blockIdx.y * 128, t = threadIdx.x;
-    const int w2 = (w + 3) >> 2, w3 = (w + 7) >> 3, w4 = (w + 15) >> 4, w5 = (w + 31) >> 5, w6 = (w + 63) >> 6, w7 = (w + 127) >> 7;
-    const float2 none = make_float2(-1.f, 3.0e38f); // neutral element (tiles outside the image)
-    for (int i = t; i < 1024; i += 256)
-    {
-        const int ty = i >> 5, tx = i & 31;
-        float2 m = none;
-        for (int dy = 0; dy < 4; ++dy)
-            for (int dx = 0; dx < 4; ++dx)
-            {
-                const int x = rx + tx * 4 + dx, y = ry + ty * 4 + dy;
-                if (x < w && y < h)
-                {
-                    const float2 th = thrz[(size_t)y * w + x]; // {hi_z, lo_z}
-                    m = mm2(m, make_float2(th.y, th.x));
-                }
-            }
-        s2[ty][tx] = m;
-        const int gx = (rx >> 2) + tx, gy = (ry >> 2) + ty;
-        if (gx < w2 && gy < ((h + 3) >> 2)) mip[o2 + gy * w2 + gx] = m;
-    }
-    __syncthreads();
-    {
-        const int ty = t >> 4, tx = t & 15;
-        const float2 m = mm2(mm2(s2[2 * ty][2 * tx], s2[2 * ty][2 * tx + 1]), mm2(s2[2 * ty + 1][2 * tx], s2[2 * ty + 1][2 * tx + 1]));
-        s3[ty][tx] = m;
-        const int gx = (rx >> 3) + tx, gy = (ry >> 3) + ty;
-        if (gx < w3 && gy < ((h + 7) >> 3)) mip[o3 + gy * w3 + gx] = m;
-    }
-    __syncthreads();
-    if (t < 64)
-    {
-        const int ty = t >> 3, tx = t & 7;
-        const float2 m = mm2(mm2(s3[2 * ty][2 * tx], s3[2 * ty][2 * tx + 1]), mm2(s3[2 * ty + 1][2 * tx], s3[2 * ty + 1][2 * tx + 1]));
-        s4[ty][tx] = m;
-        const int gx = (rx >> 4) + tx, gy = (ry >> 4) + ty;
-        if (gx < w4 && gy < ((h + 15) >> 4)) mip[o4 + gy * w4 + gx] = m;
-    }
-    __syncthreads();
-    if (t < 16)
-    {
-        const int ty = t >> 2, tx = t & 3;
-        const float2 m = mm2(mm2(s4[2 * ty][2 * tx], s4[2 * ty][2 * tx + 1]), mm2(s4[2 * ty + 1][2 * tx], s4[2 * ty + 1][2 * tx + 1]));
-        s5[ty][tx] = m;
-        const int gx = (rx >> 5) + tx, gy = (ry >> 5) + ty;
-        if (gx < w5 && gy < ((h + 31) >> 5)) mip[o5 + gy * w5 + gx] = m;
-    }
-    __syncthreads();
-    if (t < 4)
-    {
-        const int ty = t >> 1, tx = t & 1;
-        const float2 m = mm2(mm2(s5[2 * ty][2 * tx], s5[2 * ty][2 * tx + 1]), mm2(s5[2 * ty + 1][2 * tx], s5[2 * ty + 1][2 * tx + 1]));
-        s6[ty][tx] = m;
-        const int gx = (rx >> 6) + tx, gy = (ry >> 6) + ty;
-        if (gx < w6 && gy < ((h + 63) >> 6)) mip[o6 + gy * w6 + gx] = m;
-    }
-    __syncthreads();
-    if (t == 0) mip[o7 + blockIdx.y * w7 + blockIdx.x] = mm2(mm2(s6[0][0], s6[0][1]), mm2(s6[1][0], s6[1][1]));
-}
-
+__device__ __forceinline__ float2 mm2(float2 a, float2 b) { return make_float2(fmaxf(a.x, b.x), fminf(a.y, b.y)); } // {max, min}
 // Sparse table over the image of {max lo_z, min hi_z}: level k holds, at EVERY pixel (x, y), the extremes over the
 // 2^k x 2^k window that starts there (clipped to the image).  A pixel rectangle of any position and size is then
 // covered exactly by a few overlapping windows -- no tile alignment, no slop: the plan's free-space prefix and
@@ -360,15 +279,6 @@ __device__ __forceinline__ unsigned int update_word(unsigned int wv, float t, co
     return ((unsigned)q & 0xffffu) | __float_as_uint(e.z);
 }
 
-// exact sdf evaluation for a voxel in the band around the surface (tsdf_volume.cu:63-71)
-__device__ __forceinline__ float band_tsdf(const IntegrateArgs &a, unsigned long long xy, float cz, const float2 e, float rtrunc)
-{
-    float vxk, vyk;
-    unpack2(xy, vxk, vyk);
-    const float d2 = dot3c(vxk, vyk, cz, vxk, vyk, cz);
-    const float nsdf = __fmaf_rn(e.y, __fsqrt_rn(d2), -e.x);
-    return nsdf <= a.trunc ? fminf(1.f, __fmul_rn(rtrunc, -nsdf)) : KFB_SKIP;
-}
 // exact per-voxel predicate + tsdf for any vc.z (cameras inside the volume); cold path
 __device__ __forceinline__ float classify_generic(const IntegrateArgs &a, float cx_, float cy_, float cz, float rtrunc)
 {
@@ -392,11 +302,11 @@ __device__ __forceinline__ float classify_generic(const IntegrateArgs &a, float 
         if ((unsigned)ui < (unsigned)a.w && (unsigned)vi < (unsigned)a.h)
         {
             const int p = vi * a.w + ui;
-            const float2 e = __ldg(a.exact + p);
-            if (e.x > 0.f)
+            const float4 e = __ldg(a.tab4 + p); // {hi_z, lo_z, depth, 1/lambda}
+            if (e.z > 0.f)
             {
                 const float d2 = dot3c(cx_, cy_, cz, cx_, cy_, cz);
-                const float nsdf = __fmaf_rn(e.y, __fsqrt_rn(d2), -e.x);
+                const float nsdf = __fmaf_rn(e.w, __fsqrt_rn(d2), -e.z);
                 if (nsdf <= a.trunc) t = fminf(1.f, __fmul_rn(rtrunc, -nsdf));
             }
         }
@@ -424,33 +334,6 @@ __device__ __noinline__ void mark_bricks(uint8_t *flags, int *dirty, int gbx, in
     for (int i = 0; i < 8; ++i)
         if (v[i] == 0) { *f[i] = 1; any = true; }
     if (any) *dirty = 1;
-}
-
-// Conservative interval [lo, hi] of planes in [zstart, zend) on which any of a thread's four columns can pass the
-// reference's predicate (never excludes a voxel the exact predicate would accept: each plane is relaxed by `slack`
-// and the bound is widened by one step).  (ax, ay, az) / (bx, by, bz) = vc of the first / last column at z = 0.
-__device__ __forceinline__ void frustum_interval(const IntegrateArgs &a, float ax, float ay, float az, float bx, float by, float bz,
-                                                 int zstart, int zend, float &lo, float &hi)
-{
-    lo = (float)zstart;
-    hi = (float)(zend - 1);
-    const float zx = __ldg(a.zexit);
-#pragma unroll
-    for (int c = 0; c < KFB_NCULL; ++c)
-    {
-        const CullPlane &cp = a.cull[c];
-        if (cp.kind == 3) continue;
-        const float ga = fmaf(cp.a, ax, fmaf(cp.b, ay, cp.g * az));
-        const float gb = fmaf(cp.a, bx, fmaf(cp.b, by, cp.g * bz));
-        float g0 = fmaxf(ga, gb) + cp.slack;
-        if (c == KFB_NCULL - 1) g0 += zx; // vc.z <= zexit
-        const float zc = g0 * cp.ninv;
-        if (cp.kind == 0) lo = fmaxf(lo, zc - 1.f);
-        else if (cp.kind == 1) hi = fminf(hi, zc + 1.f);
-        else if (g0 < 0.f) hi = -1.f;
-    }
-    lo = fminf(lo, (float)zend);
-    hi = fmaxf(hi, (float)zstart - 2.f);
 }
 
 // phase B of one plane: running weighted mean, re-encode, store (tsdf_volume.cu:69-79)
@@ -497,387 +380,55 @@ __device__ __forceinline__ void update_quad(const IntegrateArgs &a, uint4 *vp, c
     }
 }
 
-// ---- the sweep ------------------------------------------------------------------------
 #define KFB_BAND (-8.0f)
-#ifndef KFB_INT_PX
-#define KFB_INT_PX 4 // threads of a warp along x (each owns 4 voxels); 32 / KFB_INT_PX rows
-#endif
-#ifndef KFB_INT_WARPS
-#define KFB_INT_WARPS 4 // warps per block (one warp per block was measured slower: 32k tiny blocks per chunk layer)
-#endif
-#ifndef KFB_INT_MINB
-#define KFB_INT_MINB 8
-#endif
-template <int U, bool COUNT>
-__global__ void __launch_bounds__(32 * KFB_INT_WARPS, KFB_INT_MINB * 4 / KFB_INT_WARPS) integrate_kernel(const IntegrateArgs a)
-{
-    // a warp owns a compact 16 x 8 voxel patch (KFB_INT_PX = 4 threads x 8 rows; 64 B per row): its columns see
-    // nearly the same part of the image, so warp-level decisions (fast path, loop bounds) are mostly unanimous
-    const int x0 = (blockIdx.x * (KFB_INT_WARPS * KFB_INT_PX) + threadIdx.y * KFB_INT_PX + (threadIdx.x & (KFB_INT_PX - 1))) * 4;
-    const int y = blockIdx.y * (32 / KFB_INT_PX) + (threadIdx.x / KFB_INT_PX);
-    if (x0 >= a.X || y >= a.Y) return;
-
-    const int zstart = a.zb + blockIdx.z * a.zchunk;
-    const int zend = min(zstart + a.zchunk, a.ze);
-    if (zstart >= zend) return;
-
-    // whole-column frustum interval, computed once per column by column_states_kernel (see frustum_interval)
-    const int2 cr = __ldg(a.col_range + (size_t)y * (a.X >> 2) + (x0 >> 2));
-    const int za = max(zstart, cr.x);
-    int zb = min(zend - 1, cr.y);
-    if (za > zb) return;
-    // vc at z = 0 of the first and the last of the four columns: R * (x*vs.x, y*vs.y, 0*vs.z) + t
-    // (tsdf_volume.cu:49-50); the running sums themselves come from the stored chunk states below
-    unsigned long long xy[4], zz[2];
-    float z0v[4];
-    {
-        const float py = __fmul_rn((float)y, a.vsy);
-        const float pz = __fmul_rn(0.f, a.vsz);
-#pragma unroll
-        for (int k = 0; k < 4; k += 3)
-        {
-            const float px = __fmul_rn((float)(x0 + k), a.vsx);
-            const float3 r = rot3(a.pose.R, px, py, pz);
-            z0v[k] = __fadd_rn(r.z, a.pose.t[2]);
-            xy[k] = pack2(__fadd_rn(r.x, a.pose.t[0]), __fadd_rn(r.y, a.pose.t[1]));
-        }
-    }
-    // last plane of this thread's interval that certainly still is deep free space (za - 1: none)
-    int free_end = za - 1;
-    // Occlusion cut: over planes [za, zb] the four columns project into a pixel rectangle (a line segment per
-    // column; computed from the affine model and widened by the drift bound).  A voxel is rejected once vc.z
-    // exceeds lo_z of its pixel, hence certainly once it exceeds the maximum of lo_z over that rectangle, which
-    // the max-pyramid gives with four lookups.  Planes beyond that are never visited.
-    if (a.Sz > 1e-6f)
-    {
-        float ax, ay, bx_, by_;
-        unpack2(xy[0], ax, ay);
-        unpack2(xy[3], bx_, by_);
-        float umin = 1e30f, umax = -1e30f, vmin = 1e30f, vmax = -1e30f, zmin = 1e30f;
-#pragma unroll
-        for (int e = 0; e < 2; ++e)
-        {
-            const float zf = (float)(e ? zb : za);
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-            {
-                const float X = fmaf(zf, a.Sx, k ? bx_ : ax), Y = fmaf(zf, a.Sy, k ? by_ : ay), Zc = fmaf(zf, a.Sz, k ? z0v[3] : z0v[0]);
-                const float r = mufu_rcp(fmaxf(Zc, 1e-3f)); // approximate is fine: the rectangle is padded below
-                const float u = fmaf(a.fx * X, r, a.cx), v = fmaf(a.fy * Y, r, a.cy);
-                umin = fminf(umin, u); umax = fmaxf(umax, u);
-                vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
-                zmin = fminf(zmin, Zc);
-            }
-        }
-        if (zmin > 0.05f)
-        {
-            // pixel error of the model: (fx + |u - cx|) * E / z per axis, plus rounding to the nearest pixel
-            const float pad = 1.5f + (a.fx + a.fy + (float)(a.w + a.h)) * a.driftE * (1.001f * mufu_rcp(zmin));
-            const bool all_inside = umin - pad >= 0.f && umax + pad <= (float)(a.w - 1) && vmin - pad >= 0.f && vmax + pad <= (float)(a.h - 1);
-            const int u0 = max((int)floorf(fmaxf(umin - pad, -1e6f)), 0), u1 = min((int)ceilf(fminf(umax + pad, 1e6f)), a.w - 1);
-            const int v0 = max((int)floorf(fmaxf(vmin - pad, -1e6f)), 0), v1 = min((int)ceilf(fminf(vmax + pad, 1e6f)), a.h - 1);
-            if (u0 > u1 || v0 > v1) return; // never inside the image on these planes
-            const int span = max(u1 - u0, v1 - v0) + 1;
-            // tiles a quarter of the span wide: the rectangle is covered by at most 5 x 5 of them
-            const int l = max(32 - __clz(span - 1) - 2, 2);
-            if (l <= 7)
-            {
-                const float2 *m = a.zmip + a.mip_off[l - 2];
-                const int mw = a.mip_w[l - 2];
-                float2 q = make_float2(-1.f, 3.0e38f);
-                for (int ty = v0 >> l; ty <= (v1 >> l); ++ty)
-                    for (int tx = u0 >> l; tx <= (u1 >> l); ++tx) q = mm2(q, __ldg(m + ty * mw + tx));
-                const float zc = (q.x + 2.f * a.driftE - fminf(z0v[0], z0v[3])) * a.invSz + 1.f;
-                zb = min(zb, (int)ceilf(fminf(zc, 1e6f)));
-                if (za > zb) return;
-                // Deep free space: while the largest vc.z of a plane (+ drift) does not exceed the smallest hi_z
-                // of the pixels the columns can land on (all inside the image), every voxel of that plane passes
-                // the predicate with tsdf == 1.0f exactly; neither projection nor running sums are needed.
-                // vc.z grows with z (Sz > 0), so these planes are a prefix [za, free_end] of the interval.
-                if (all_inside && !a.no_fastpath)
-                {
-                    const float zmaxv = fmaxf(z0v[0], z0v[3]), e2 = 2.f * a.driftE;
-                    int zf = min(zb, (int)floorf(fminf(fmaxf((q.y - e2 - zmaxv) * a.invSz, -1.f), 1e6f)));
-                    // the estimate may be off by rounding: step back until the exact test holds
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-                        if (zf >= za && fmaf((float)zf, a.Sz, zmaxv) + e2 > q.y) --zf;
-                    if (zf >= za && fmaf((float)zf, a.Sz, zmaxv) + e2 <= q.y) free_end = zf;
-                }
-            }
-        }
-    }
-    // The fast prefix only pays for planes on which the WHOLE warp takes it (a mixed plane would run both paths
-    // in turn): planes up to the warp's smallest free_end.  Whatever set of lanes votes together, a lane's own
-    // free_end is >= the minimum it receives, so the split can never change a result.
-    int zfw;
-    {
-        const unsigned act = __activemask();
-        zfw = __reduce_min_sync(act, free_end);
-        if (a.no_prefix) zfw = __ballot_sync(act, free_end >= zb) == act ? 0x7fffffff : -0x7fffffff; // all or nothing
-    }
-    unsigned int n_upd = 0;
-    const size_t plane4 = ((size_t)a.X * a.Y) >> 2; // uint4 per plane
-    if (!(a.diag & 2))
-    {
-        const int pe = min(zfw, zb);
-        uint4 *vp = reinterpret_cast<uint4 *>(a.vol) + ((size_t)(za - a.z_store0) * a.Y + y) * (a.X >> 2) + (x0 >> 2);
-        const float ones[4] = {1.f, 1.f, 1.f, 1.f};
-        int z = za;
-        for (; z + 3 <= pe; z += 4, vp += 4 * plane4)
-        {
-            const uint4 w0 = __ldcs(vp), w1 = __ldcs(vp + plane4), w2 = __ldcs(vp + 2 * plane4), w3 = __ldcs(vp + 3 * plane4);
-            update_quad<COUNT>(a, vp, w0, ones, x0, y, z, n_upd);
-            update_quad<COUNT>(a, vp + plane4, w1, ones, x0, y, z + 1, n_upd);
-            update_quad<COUNT>(a, vp + 2 * plane4, w2, ones, x0, y, z + 2, n_upd);
-            update_quad<COUNT>(a, vp + 3 * plane4, w3, ones, x0, y, z + 3, n_upd);
-        }
-        for (; z <= pe; ++z, vp += plane4) update_quad<COUNT>(a, vp, __ldcs(vp), ones, x0, y, z, n_upd);
-    }
-    if (zfw >= zb || (a.diag & 1))
-    {
-        if (COUNT && n_upd) atomicAdd(a.counter, (unsigned long long)n_upd);
-        return;
-    }
-    const int za_g = max(za, zfw + 1); // first plane of the general path
-
-    const float sz = a.pose.R.m[8];
-    const unsigned long long vs2 = pack2(a.vsx, a.vsx), sxy = pack2(a.pose.R.m[2], a.pose.R.m[5]), szz = pack2(sz, sz);
-    // the reference's running sum (tsdf_volume.cu:56) up to the first visited plane: column_states_kernel has
-    // stored vc after plane zstart - 1 for every chunk; only the planes zstart .. za - 1 are replayed here
-    {
-        const size_t nthr = (size_t)(a.X >> 2) * a.Y;
-        const unsigned long long *st = a.states + (size_t)blockIdx.z * 6 * nthr + (size_t)y * (a.X >> 2) + (x0 >> 2);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) xy[k] = __ldg(st + (size_t)k * nthr);
-        zz[0] = __ldg(st + 4 * nthr);
-        zz[1] = __ldg(st + 5 * nthr);
-#pragma unroll 4
-        for (int z = zstart; z < za_g; ++z)
-        {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) xy[k] = ffma2(vs2, sxy, xy[k]);
-            zz[0] = ffma2(vs2, szz, zz[0]);
-            zz[1] = ffma2(vs2, szz, zz[1]);
-        }
-    }
-    // fast path needs vc.z >= FLT_MIN on every visited plane; vc.z is affine in z up to the running-sum
-    // drift (millimetres at most), so the two ends decide with a 1 cm margin
-    bool fast;
-    {
-        const float span = (float)(zb - za_g + 1) * __fmul_rn(a.vsx, sz);
-        float c0, c1, c2, c3;
-        unpack2(zz[0], c0, c1);
-        unpack2(zz[1], c2, c3);
-        const float m = fminf(fminf(c0, c1), fminf(c2, c3)); // plane za - 1
-        fast = fminf(m, m + span) > 0.01f;
-    }
-
-    const float rtrunc = rcp_fdividef(a.trunc);
-    uint4 *vp = reinterpret_cast<uint4 *>(a.vol) + ((size_t)(za_g - a.z_store0) * a.Y + y) * (a.X >> 2) + (x0 >> 2);
-
-    if (!fast)
-    {
-        // cold path (camera within a centimetre of this column's planes): one plane at a time, any vc.z
-        for (int z = za_g; z <= zb; ++z, vp += plane4)
-        {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) xy[k] = ffma2(vs2, sxy, xy[k]);
-            zz[0] = ffma2(vs2, szz, zz[0]);
-            zz[1] = ffma2(vs2, szz, zz[1]);
-            float cz[4], t[4];
-            unpack2(zz[0], cz[0], cz[1]);
-            unpack2(zz[1], cz[2], cz[3]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-            {
-                float vxk, vyk;
-                unpack2(xy[k], vxk, vyk);
-                t[k] = classify_generic(a, vxk, vyk, cz[k], rtrunc);
-            }
-            if ((t[0] != KFB_SKIP) | (t[1] != KFB_SKIP) | (t[2] != KFB_SKIP) | (t[3] != KFB_SKIP))
-                update_quad<COUNT>(a, vp, __ldcs(vp), t, x0, y, z, n_upd);
-        }
-        if (COUNT && n_upd) atomicAdd(a.counter, (unsigned long long)n_upd);
-        return;
-    }
-
-    const unsigned long long fxy = pack2(a.fx, a.fy), cxy = pack2(a.cx, a.cy), magic2 = pack2(KFB_MAGIC_F, KFB_MAGIC_F);
-    for (int z = za_g; z <= zb; z += U)
-    {
-        float ts[U][4], cz[U][4];
-        unsigned int pix[U][4];
-        float2 th[U][4];
-        unsigned long long sxyv[U][4];
-        const unsigned int last_pix = (unsigned int)(a.w * a.h - 1);
-        // ---- phase A1: advance, project, issue all threshold loads -------------------------------
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-        {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) xy[k] = ffma2(vs2, sxy, xy[k]);
-            zz[0] = ffma2(vs2, szz, zz[0]);
-            zz[1] = ffma2(vs2, szz, zz[1]);
-            unpack2(zz[0], cz[u][0], cz[u][1]);
-            unpack2(zz[1], cz[u][2], cz[u][3]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-            {
-                sxyv[u][k] = xy[k];
-                const float r = mufu_rcp(cz[u][k]);
-                const unsigned long long q = fmul2(pack2(r, r), xy[k]);
-                const unsigned long long m = fadd2(ffma2(q, fxy, cxy), magic2);
-                float mu, mv;
-                unpack2(m, mu, mv);
-                const int ui = __float_as_int(mu) - KFB_MAGIC_I;
-                const int vi = __float_as_int(mv) - KFB_MAGIC_I;
-                const bool ok = ((unsigned)ui < (unsigned)a.w) & ((unsigned)vi < (unsigned)a.h);
-                // an out-of-image voxel is classified as "behind everything": vc.z = +inf fails `<= hi_z` and
-                // passes `> lo_z` for whatever (clamped) table entry it reads
-                cz[u][k] = ok ? cz[u][k] : __int_as_float(0x7f800000);
-                pix[u][k] = min((unsigned int)(vi * a.w + ui), last_pix);
-                th[u][k] = __ldg(a.thrz + pix[u][k]);
-            }
-        }
-        // ---- phase A2: classify against the thresholds; exact sdf only in the band -------------------
-        bool band = false;
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-            {
-                const float t = cz[u][k] <= th[u][k].x ? 1.0f : (cz[u][k] > th[u][k].y ? KFB_SKIP : KFB_BAND);
-                band |= (t == KFB_BAND);
-                ts[u][k] = t;
-            }
-        if (band)
-        {
-            // all exact-depth entries first (the addresses are valid for every voxel), so that the warp waits for
-            // one load latency and not for one per voxel a lane happens to have in the band
-            float2 ex[U][4];
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) ex[u][k] = __ldg(a.exact + pix[u][k]);
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                {
-                    const float tb = band_tsdf(a, sxyv[u][k], cz[u][k], ex[u][k], rtrunc);
-                    ts[u][k] = ts[u][k] == KFB_BAND ? tb : ts[u][k];
-                }
-        }
-        // ---- loads, then phase B ------------------------------------------------------------------------
-        uint4 word[U];
-        bool need[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-        {
-            need[u] = ((ts[u][0] != KFB_SKIP) | (ts[u][1] != KFB_SKIP) | (ts[u][2] != KFB_SKIP) | (ts[u][3] != KFB_SKIP)) & (z + u <= zb);
-            if (need[u]) word[u] = __ldcs(vp + (size_t)u * plane4);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (need[u]) update_quad<COUNT>(a, vp + (size_t)u * plane4, word[u], ts[u], x0, y, z + u, n_upd);
-        vp += (size_t)U * plane4;
-    }
-    if (COUNT && n_upd) atomicAdd(a.counter, (unsigned long long)n_upd); // threads leave at different times: no shuffles
-}
-
-// vc of every thread's four columns at the start of every z-chunk, by the reference's recurrence from z = 1
-// (exact jump for a long prefix in front of a far z-slab).  One sequential pass per column instead of one
-// replay per chunk.
-__global__ void __launch_bounds__(128) column_states_kernel(const IntegrateArgs a)
-{
-    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int y = blockIdx.y * 4 + threadIdx.y;
-    if (x0 >= a.X || y >= a.Y) return;
-    float vx[4], vy[4], vz[4];
-    {
-        const float py = __fmul_rn((float)y, a.vsy);
-        const float pz = __fmul_rn(0.f, a.vsz);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-        {
-            const float px = __fmul_rn((float)(x0 + k), a.vsx);
-            const float3 r = rot3(a.pose.R, px, py, pz);
-            vx[k] = __fadd_rn(r.x, a.pose.t[0]);
-            vy[k] = __fadd_rn(r.y, a.pose.t[1]);
-            vz[k] = __fadd_rn(r.z, a.pose.t[2]);
-        }
-    }
-    // columns that never enter the frustum need no states (their sweep threads return before reading them), and
-    // no chunk past the last visited plane does
-    int z_first, z_last;
-    {
-        float lo, hi;
-        frustum_interval(a, vx[0], vy[0], vz[0], vx[3], vy[3], vz[3], a.zb, a.ze, lo, hi);
-        z_first = max(a.zb, (int)floorf(lo));
-        z_last = min(a.ze - 1, (int)ceilf(hi));
-        a.col_range[(size_t)y * (a.X >> 2) + (x0 >> 2)] = make_int2(z_first, z_last);
-        if (z_first > z_last) return;
-    }
-    const float sx = a.pose.R.m[2], sy = a.pose.R.m[5], sz = a.pose.R.m[8];
-    int done = 0; // planes applied so far
-    if (a.use_jump && a.zb - 1 >= a.jump_min)
-    {
-        jump4(vx, a.vsx, sx, a.zb - 1);
-        jump4(vy, a.vsx, sy, a.zb - 1);
-        jump4(vz, a.vsx, sz, a.zb - 1);
-        done = a.zb - 1;
-    }
-    unsigned long long xy[4], zz[2];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) xy[k] = pack2(vx[k], vy[k]);
-    zz[0] = pack2(vz[0], vz[1]);
-    zz[1] = pack2(vz[2], vz[3]);
-    const unsigned long long vs2 = pack2(a.vsx, a.vsx), sxy = pack2(sx, sy), szz = pack2(sz, sz);
-    const size_t nthr = (size_t)(a.X >> 2) * a.Y;
-    unsigned long long *st = a.states + (size_t)y * (a.X >> 2) + (x0 >> 2);
-    for (int c = 0; c < a.nchunks; ++c)
-    {
-        const int target = a.zb + c * a.zchunk - 1; // state after this plane
-        if (target + 1 > z_last) break;
-#pragma unroll 4
-        for (; done < target; ++done)
-        {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) xy[k] = ffma2(vs2, sxy, xy[k]);
-            zz[0] = ffma2(vs2, szz, zz[0]);
-            zz[1] = ffma2(vs2, szz, zz[1]);
-        }
-        if (target + a.zchunk < z_first) continue; // the chunk ends before the first visited plane: nobody reads its state
-        unsigned long long *o = st + (size_t)c * 6 * nthr;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) o[(size_t)k * nthr] = xy[k];
-        o[4 * nthr] = zz[0];
-        o[5 * nthr] = zz[1];
-    }
-}
-
-// =====================================================================================================
-// The sweep as a work plan (round 2).  The kernel above decides per warp and per z-chunk, inside the sweep, what
-// its patch needs (frustum interval, occlusion cut, deep free space) before it touches a voxel; with every warp
-// slot taken by warps that wait on memory, that setup, the streaming part and the per-voxel part simply add up
-// (DESIGN.md 3.2).  Here the decisions are taken once, by a small kernel with one thread per (16 x 8 voxel patch,
-// 16-plane chunk), which writes two compact work lists:
-//   stream items  {patch, z0..z1}: every voxel of these planes passes the reference's predicate with tsdf == 1.0f
-//                 exactly (same proof as the fast path above, at patch granularity) -- integrate_stream_kernel does
-//                 nothing but load -> running mean -> store, eight planes in flight per thread;
+// ---- the sweep as a work plan ---------------------------------------------------------------------------------
+// The decisions a sweep needs -- which planes of which voxel columns can pass the reference's predicate at all, which
+// of them are deep free space, which need the per-voxel predicate -- are taken once, by a small kernel with one thread
+// per (16 x 8 voxel patch, 8-plane chunk), which writes two compact work lists (round 1 took them inside the sweep,
+// per warp and chunk: with every warp slot taken by warps that wait on memory, set-up, streaming and per-voxel work
+// simply added up):
+//   stream items  {patch, z0..z1}: every voxel of these planes passes the predicate with tsdf == 1.0f exactly --
+//                 integrate_stream_kernel does nothing but load -> running mean -> store, eight planes in flight;
 //   general items {patch, z0..z1}: planes on which the exact per-voxel predicate decides (the band around the
-//                 surface, the frustum border, holes) -- integrate_general_kernel runs the reference's arithmetic
-//                 as a two-stage software pipeline: the table entries and the voxel words of plane z + 1 are in
-//                 flight while plane z is classified and updated, so a warp pays one memory latency per plane
-//                 instead of three dependent ones.
+//                 surface, the frustum border, holes) -- integrate_general_kernel runs the reference's arithmetic,
+//                 one plane per iteration with all of the plane's loads issued together.
 // The running sums of the reference (vc += zstep) are only needed by the general items: integrate_states_kernel
 // walks the patches that have any, one warp per patch, and stores the 32 threads' sums at the chunk starts the
-// plan asked for (48 B per thread per general item instead of per column per chunk).
+// plan asked for (48 B per thread per general item).  States and general items run on a second stream next to the
+// stream items (FMA-bound, latency-bound and bandwidth-bound work side by side).
 // Culling is conservative and the per-voxel predicate is exact, so no split of the work can change a result:
 // tests/test_ref_ab.py and tests/test_ref_full.py compare whole volumes with the reference kernels' bit for bit.
+//
+// Voxel layout: 8 x 8 x 8 bricks (kfb_common.cuh: vol_index).  A warp's 16 x 8 patch is two bricks wide, so one plane
+// of it is two contiguous 256-byte runs (lane = brick half * 16 + row * 2 + quad), and its z-march stays inside the
+// same two bricks for eight planes.
 #define KFB_PATCH_X 16
 #define KFB_PATCH_Y 8
 #define KFB_PLAN_ZCHUNK 8
+
+// A sweep thread of a patch: lane = brick half * 16 + row * 2 + quad.  x0 / y = its four voxels; quad_index(z) = index,
+// in 16-byte units, of those voxels on plane z in the brick-major volume.
+struct PatchLane
+{
+    int x0, y;
+    size_t brick_xy; // index of the thread's brick column among the bricks of one brick layer
+    int in_plane;    // (y & 7) * 2 + quad: offset inside a brick's plane, 16-byte units
+};
+__device__ __forceinline__ PatchLane patch_lane(const IntegrateArgs &a, int patch, int lane)
+{
+    const int py = patch / a.npx, px = patch - py * a.npx;
+    const int half = lane >> 4, row = (lane >> 1) & 7, quad = lane & 1;
+    PatchLane p;
+    p.x0 = px * KFB_PATCH_X + half * 8 + quad * 4;
+    p.y = py * KFB_PATCH_Y + row;
+    p.brick_xy = (size_t)py * a.bx + (size_t)(2 * px + half);
+    p.in_plane = row * 2 + quad;
+    return p;
+}
+__device__ __forceinline__ size_t quad_index(const IntegrateArgs &a, const PatchLane &p, int z)
+{
+    return ((((size_t)((z >> 3) - a.bz0)) * ((size_t)a.bx * a.by) + p.brick_xy) << 7) + (size_t)(((z & 7) << 4) | p.in_plane);
+}
 
 // conservative interval of planes on which any column of a patch can pass the predicate; (cx, cy, cz)[k] = vc at
 // z = 0 of the patch's corner columns (g is affine in x and y, so its maximum over the patch sits at a corner)
@@ -963,48 +514,28 @@ __global__ void __launch_bounds__(128) integrate_plan_kernel(const IntegrateArgs
                 if (u0 > u1 || v0 > v1) zb = za - 1; // never inside the image on these planes
                 else
                 {
-                    const int span = max(u1 - u0, v1 - v0) + 1;
-                    const int l = max(32 - __clz(span - 1) - 2, 2); // tiles a quarter of the span wide: at most 5 x 5 cover the rectangle
-                    if (l <= 7)
                     {
+                        // exact cover of the rectangle by overlapping 2^k x 2^k windows of the sparse table: k from the
+                        // shorter side, raised until five windows reach along the longer one
                         float2 q = make_float2(-1.f, 3.0e38f);
-                        if (a.use_sparse)
-                        {
-                            // exact cover of the rectangle by overlapping 2^k x 2^k windows of the sparse table: k from
-                            // the shorter side, raised until five windows reach along the longer one
-                            const int W = u1 - u0 + 1, H = v1 - v0 + 1;
-                            int k = min(max(31 - __clz(min(W, H)), 1), 6);
-                            while (k < 6 && ((max(W, H) + (1 << k) - 1) >> k) > 5) ++k;
-                            const int sw = 1 << k;
-                            if (((max(W, H) + sw - 1) >> k) > 5) q = make_float2(3.0e38f, -1.f); // wider than 5 x 64 pixels: decide per voxel
-                            else
-                            {
-                                const float2 *m = a.zsparse + (size_t)(k - 1) * a.w * a.h;
-                                const int xl = max(u0, u1 - sw + 1), yl = max(v0, v1 - sw + 1), ny = (H + sw - 1) >> k;
-                                for (int j = 0; j < ny; ++j)
-                                {
-                                    const int yy = min(v0 + j * sw, yl);
-                                    float2 tl[5];
-#pragma unroll
-                                    for (int i = 0; i < 5; ++i) tl[i] = __ldg(m + (size_t)yy * a.w + min(u0 + i * sw, xl));
-#pragma unroll
-                                    for (int i = 0; i < 5; ++i) q = mm2(q, tl[i]);
-                                }
-                            }
-                        }
+                        const int W = u1 - u0 + 1, H = v1 - v0 + 1;
+                        int k = min(max(31 - __clz(min(W, H)), 1), 6);
+                        while (k < 6 && ((max(W, H) + (1 << k) - 1) >> k) > 5) ++k;
+                        const int sw = 1 << k;
+                        if (((max(W, H) + sw - 1) >> k) > 5) q = make_float2(3.0e38f, -1.f); // wider than 5 x 64 pixels: decide per voxel
                         else
                         {
-                            const float2 *m = a.zmip + a.mip_off[l - 2];
-                            const int mw = a.mip_w[l - 2];
-                            const int tx0 = u0 >> l, tx1 = u1 >> l, ty0 = v0 >> l, ty1 = v1 >> l;
-                            // 25 loads in flight; tiles beyond the rectangle repeat its last one (harmless for min / max)
-                            float2 tl[25];
+                            const float2 *m = a.zsparse + (size_t)(k - 1) * a.w * a.h;
+                            const int xl = max(u0, u1 - sw + 1), yl = max(v0, v1 - sw + 1), ny = (H + sw - 1) >> k;
+                            for (int j = 0; j < ny; ++j)
+                            {
+                                const int yy = min(v0 + j * sw, yl);
+                                float2 tl[5];
 #pragma unroll
-                            for (int j = 0; j < 5; ++j)
+                                for (int i = 0; i < 5; ++i) tl[i] = __ldg(m + (size_t)yy * a.w + min(u0 + i * sw, xl));
 #pragma unroll
-                                for (int i = 0; i < 5; ++i) tl[j * 5 + i] = __ldg(m + min(ty0 + j, ty1) * mw + min(tx0 + i, tx1));
-#pragma unroll
-                            for (int i = 0; i < 25; ++i) q = mm2(q, tl[i]);
+                                for (int i = 0; i < 5; ++i) q = mm2(q, tl[i]);
+                            }
                         }
                         const float zmin0 = fminf(fminf(cz[0], cz[1]), fminf(cz[2], cz[3])), zmax0 = fmaxf(fmaxf(cz[0], cz[1]), fmaxf(cz[2], cz[3]));
                         const float e2 = 2.f * a.driftE;
@@ -1063,9 +594,9 @@ __global__ void __launch_bounds__(128) integrate_states_kernel(const IntegrateAr
         if (m) c_last = w * 32 + 31 - __clz(m);
     }
     if (c_last < 0) return;
-    const int py = patch / a.npx, px = patch - py * a.npx;
     // lanes beyond the volume's edge compute a valid neighbour's sums (never read)
-    const int x0 = min(px * KFB_PATCH_X + (lane & 3) * 4, a.X - 4), y = min(py * KFB_PATCH_Y + (lane >> 2), a.Y - 1);
+    const PatchLane pl = patch_lane(a, patch, lane);
+    const int x0 = min(pl.x0, a.X - 4), y = min(pl.y, a.Y - 1);
     float vx[4], vy[4], vz[4];
     {
         const float pyf = __fmul_rn((float)y, a.vsy), pz = __fmul_rn(0.f, a.vsz);
@@ -1164,27 +695,25 @@ __global__ void __launch_bounds__(128, 8) integrate_stream_kernel(const Integrat
     const float4 *wt = SMEM ? s_wt : a.wtab;
     const int lane = threadIdx.x & 31;
     const unsigned int n_items = __ldg(a.plan_counts + 0);
-    const size_t plane4 = ((size_t)a.X * a.Y) >> 2;
     unsigned int n_upd = 0, n_ld = 0, n_st = 0;
     for (unsigned int item = blockIdx.x * 4 + (threadIdx.x >> 5); item < n_items; item += gridDim.x * 4)
     {
         const uint2 it = __ldg(a.items_stream + item);
-        const int py = (int)it.x / a.npx, px = (int)it.x - py * a.npx;
-        const int x0 = px * KFB_PATCH_X + (lane & 3) * 4, y = py * KFB_PATCH_Y + (lane >> 2);
-        if (x0 >= a.X || y >= a.Y) continue;
+        const PatchLane pl = patch_lane(a, (int)it.x, lane);
+        if (pl.x0 >= a.X || pl.y >= a.Y) continue;
         const int z0 = (int)(it.y & 0xffffu), z1 = (int)(it.y >> 16);
-        uint4 *vp = reinterpret_cast<uint4 *>(a.vol) + ((size_t)(z0 - a.z_store0) * a.Y + y) * (a.X >> 2) + (x0 >> 2);
-        for (int z = z0; z <= z1; z += KFB_STREAM_DEPTH, vp += KFB_STREAM_DEPTH * plane4)
+        uint4 *const vol4 = reinterpret_cast<uint4 *>(a.vol);
+        for (int z = z0; z <= z1; z += KFB_STREAM_DEPTH)
         {
             uint4 w[KFB_STREAM_DEPTH];
 #pragma unroll
             for (int i = 0; i < KFB_STREAM_DEPTH; ++i)
-                if (z + i <= z1) w[i] = __ldcs(vp + i * plane4);
+                if (z + i <= z1) w[i] = __ldcs(vol4 + quad_index(a, pl, z + i));
 #pragma unroll
             for (int i = 0; i < KFB_STREAM_DEPTH; ++i)
                 if (z + i <= z1)
                 {
-                    update_free_quad<COUNT>(a, wt, vp + i * plane4, w[i], n_upd, n_st);
+                    update_free_quad<COUNT>(a, wt, vol4 + quad_index(a, pl, z + i), w[i], n_upd, n_st);
                     if (COUNT) ++n_ld;
                 }
         }
@@ -1323,7 +852,6 @@ __global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const Inte
     const float4 *wt = SMEM ? s_wt : a.wtab;
     const int lane = threadIdx.x & 31;
     const unsigned int n_items = __ldg(a.plan_counts + 1);
-    const size_t plane4 = ((size_t)a.X * a.Y) >> 2;
     GenConst g;
     {
         const float sz = a.pose.R.m[8];
@@ -1336,8 +864,8 @@ __global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const Inte
     for (unsigned int item = blockIdx.x * 4 + (threadIdx.x >> 5); item < n_items; item += gridDim.x * 4)
     {
         const uint2 it = __ldg(a.items_general + item);
-        const int py = (int)it.x / a.npx, px = (int)it.x - py * a.npx;
-        const int x0 = px * KFB_PATCH_X + (lane & 3) * 4, y = py * KFB_PATCH_Y + (lane >> 2);
+        const PatchLane pl = patch_lane(a, (int)it.x, lane);
+        const int x0 = pl.x0, y = pl.y;
         if (x0 >= a.X || y >= a.Y) continue;
         const int z0 = (int)(it.y & 0xffffu), z1 = (int)(it.y >> 16);
         const int zstart = a.zb + ((z0 - a.zb) / a.zchunk) * a.zchunk; // first plane of the item's chunk
@@ -1386,8 +914,8 @@ __global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const Inte
                 zz[1] = ffma2(g.vs2, g.szz, zz[1]);
             }
         }
-        uint4 *vp = reinterpret_cast<uint4 *>(a.vol) + ((size_t)(z0 - a.z_store0) * a.Y + y) * (a.X >> 2) + (x0 >> 2);
-        // the pipelined path needs vc.z >= FLT_MIN on every visited plane (MUFU.RCP without the denormal
+        uint4 *const vol4 = reinterpret_cast<uint4 *>(a.vol);
+        // the fast path needs vc.z >= FLT_MIN on every visited plane (MUFU.RCP without the denormal
         // pre-scaling); vc.z is affine in z up to the running-sum drift, so the two ends decide with a 1 cm margin
         bool fast;
         {
@@ -1401,8 +929,9 @@ __global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const Inte
         if (!fast)
         {
             // cold path (camera within a centimetre of this thread's planes): one plane at a time, any vc.z
-            for (int z = z0; z <= z1; ++z, vp += plane4)
+            for (int z = z0; z <= z1; ++z)
             {
+                uint4 *vp = vol4 + quad_index(a, pl, z);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) xy[k] = ffma2(g.vs2, g.sxy, xy[k]);
                 zz[0] = ffma2(g.vs2, g.szz, zz[0]);
@@ -1425,106 +954,10 @@ __global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const Inte
             }
             continue;
         }
-        // ---- per-thread refinement of the item's plane range -------------------------------------------------
-        // The plan decided for the whole 16 x 8 patch; a thread's four columns see a far smaller part of the image
-        // (a few pixels), so its own free-space prefix [z0, fe_t] is longer and its own occlusion cut zb_t earlier
-        // (same proofs as in the plan, with this thread's running sums after plane z0 - 1 as the affine base).
-        // Each thread then walks its planes on its own: a cheap phase (tsdf = 1, no projection) and the full
-        // per-voxel phase only on the planes in between -- for a surface seen at a grazing angle that is the
-        // depth variation over the thread's few pixels instead of over the patch's footprint.
-        int fe_t = z0 - 1, zb_t = z1;
-        if (a.Sz > 1e-6f && a.refine)
+        // the exact per-voxel predicate, one plane (one memory latency) at a time
+        for (int z = z0; z <= z1; ++z)
         {
-            float ax, ay, bx_, by_, c0, c1, c2, c3;
-            unpack2(xy[0], ax, ay);
-            unpack2(xy[3], bx_, by_);
-            unpack2(zz[0], c0, c1);
-            unpack2(zz[1], c2, c3);
-            float umin = 1e30f, umax = -1e30f, vmin = 1e30f, vmax = -1e30f, zmin = 1e30f;
-#pragma unroll
-            for (int e = 0; e < 2; ++e)
-            {
-                const float zf = e ? (float)(z1 - z0 + 1) : 1.f; // planes z0 and z1, counted from the base plane z0 - 1
-#pragma unroll
-                for (int k = 0; k < 2; ++k)
-                {
-                    const float X = fmaf(zf, a.Sx, k ? bx_ : ax), Y = fmaf(zf, a.Sy, k ? by_ : ay), Zc = fmaf(zf, a.Sz, k ? c3 : c0);
-                    const float r = mufu_rcp(fmaxf(Zc, 1e-3f));
-                    const float u = fmaf(a.fx * X, r, a.cx), v = fmaf(a.fy * Y, r, a.cy);
-                    umin = fminf(umin, u); umax = fmaxf(umax, u);
-                    vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
-                    zmin = fminf(zmin, Zc);
-                }
-            }
-            if (zmin > 0.05f)
-            {
-                const float pad = 1.5f + (a.fx + a.fy + (float)(a.w + a.h)) * a.driftE * (1.001f * mufu_rcp(zmin));
-                const bool all_inside = umin - pad >= 0.f && umax + pad <= (float)(a.w - 1) && vmin - pad >= 0.f && vmax + pad <= (float)(a.h - 1);
-                const int u0 = max((int)floorf(fmaxf(umin - pad, -1e6f)), 0), u1 = min((int)ceilf(fminf(umax + pad, 1e6f)), a.w - 1);
-                const int v0 = max((int)floorf(fmaxf(vmin - pad, -1e6f)), 0), v1 = min((int)ceilf(fminf(vmax + pad, 1e6f)), a.h - 1);
-                if (u0 > u1 || v0 > v1) zb_t = z0 - 1; // never inside the image on these planes
-                else
-                {
-                    const int span = max(u1 - u0, v1 - v0) + 1;
-                    const int l = max(32 - __clz(span - 1) - 2, 2);
-                    if (l <= 7)
-                    {
-                        const float2 *m = a.zmip + a.mip_off[l - 2];
-                        const int mw = a.mip_w[l - 2];
-                        const int tx0 = u0 >> l, tx1 = u1 >> l, ty1 = v1 >> l;
-                        float2 q = make_float2(-1.f, 3.0e38f);
-                        for (int ty = v0 >> l; ty <= ty1; ++ty)
-                        {
-                            float2 tl[5]; // a row of tiles in flight (the rectangle is at most 5 tiles wide)
-#pragma unroll
-                            for (int i = 0; i < 5; ++i) tl[i] = __ldg(m + ty * mw + min(tx0 + i, tx1));
-#pragma unroll
-                            for (int i = 0; i < 5; ++i) q = mm2(q, tl[i]);
-                        }
-                        const float zmin0 = fminf(c0, c3), zmax0 = fmaxf(c0, c3), e2 = 2.f * a.driftE;
-                        const float zc = (q.x + e2 - zmin0) * a.invSz + 1.f;
-                        zb_t = min(z1, z0 - 1 + (int)ceilf(fminf(zc, 1e6f)));
-                        if (all_inside && !a.no_fastpath)
-                        {
-                            int zf = min(zb_t - (z0 - 1), (int)floorf(fminf(fmaxf((q.y - e2 - zmax0) * a.invSz, -1.f), 1e6f)));
-#pragma unroll
-                            for (int i = 0; i < 2; ++i)
-                                if (zf >= 1 && fmaf((float)zf, a.Sz, zmax0) + e2 > q.y) --zf;
-                            if (zf >= 1 && fmaf((float)zf, a.Sz, zmax0) + e2 <= q.y) fe_t = z0 - 1 + zf;
-                        }
-                    }
-                }
-            }
-        }
-        // ---- cheap phase: planes z0 .. fe_t are deep free space for this thread's four columns -----------------------
-        int z = z0;
-        for (; z <= fe_t; z += 4, vp += 4 * plane4)
-        {
-            uint4 w[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (z + i <= fe_t) w[i] = __ldcs(vp + i * plane4);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (z + i <= fe_t)
-                {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) xy[k] = ffma2(g.vs2, g.sxy, xy[k]);
-                    zz[0] = ffma2(g.vs2, g.szz, zz[0]);
-                    zz[1] = ffma2(g.vs2, g.szz, zz[1]);
-                    update_free_quad<COUNT>(a, wt, vp + i * plane4, w[i], n_upd, n_st);
-                    if (COUNT) ++n_ld;
-                }
-        }
-        if (fe_t >= z0)
-        {
-            vp -= (size_t)(z - (fe_t + 1)) * plane4; // the loop stepped past fe_t in units of four planes
-            z = fe_t + 1;
-        }
-        if (z > zb_t) continue;
-        // ---- full phase: the exact per-voxel predicate, one plane (one memory latency) at a time ---------------------------
-        for (; z <= zb_t; ++z, vp += plane4)
-        {
+            uint4 *vp = vol4 + quad_index(a, pl, z);
             GenStage S;
             gen_issue(a, g, xy, zz, vp, S);
             gen_process<COUNT>(a, g, wt, S, vp, x0, y, z, n_upd, n_st);
@@ -1581,11 +1014,7 @@ int launch_build_tables(kfb_ctx *ctx, cudaStream_t stream)
     KFB_CUDA(ctx, cudaMemsetAsync(ctx->zexit, 0, sizeof(float), stream));
     dim3 b(32, 8), g((k.w + 31) / 32, (k.h + 7) / 8);
     build_tables_kernel<<<g, b, 0, stream>>>(ctx->L[0].depth, k.w, k.h, k.fx, k.fy, k.cx, k.cy, ctx->p.volu_trun_dist, ctx->tab_thrz,
-                                            ctx->tab_exact, ctx->tab4, ctx->zexit);
-    KFB_LAUNCH_CHECK(ctx);
-    dim3 mg((k.w + 127) / 128, (k.h + 127) / 128);
-    build_zmip_kernel<<<mg, 256, 0, stream>>>(ctx->tab_thrz, k.w, k.h, ctx->zmip, ctx->mip_off[0], ctx->mip_off[1], ctx->mip_off[2],
-                                              ctx->mip_off[3], ctx->mip_off[4], ctx->mip_off[5]);
+                                            ctx->tab4, ctx->zexit);
     KFB_LAUNCH_CHECK(ctx);
     {
         const size_t n0 = (size_t)k.w * k.h;
@@ -1600,68 +1029,9 @@ int launch_build_tables(kfb_ctx *ctx, cudaStream_t stream)
     return KFB_OK;
 }
 
-// round-1 sweep: one kernel that decides and sweeps per warp and z-chunk (kept behind KFB_INTEGRATE_V1=1 as the
-// A/B partner of the planned sweep)
-static int launch_integrate_v1(kfb_ctx *ctx, IntegrateArgs &a, int planes, uint64_t *n_updated)
-{
-    // z-chunks give resident warps and load balance (the visited interval differs per column); the running
-    // sum at each chunk start comes from column_states_kernel, so chunks cost no replay.  48 B per thread per
-    // chunk of state: bounded to max(128 MB, 1/8 of the volume).  KFB_INTEGRATE_ZCHUNKS overrides for tuning.
-    const size_t nthr = (size_t)(a.X >> 2) * a.Y;
-    int zc = (planes + 15) / 16;
-    if (zc > 32) zc = 32;
-    const size_t state_cap = std::max((size_t)128 << 20, ctx->vol_voxels * sizeof(uint32_t) / 8); // <= 1/8 of the volume (measured: 1024^3 wants 32 chunks, 403 MB)
-    while (zc > 1 && (size_t)zc * 48 * nthr > state_cap) --zc;
-    if (const char *e = getenv("KFB_INTEGRATE_ZCHUNKS")) zc = atoi(e) > 0 ? atoi(e) : zc;
-    if (zc > planes) zc = planes;
-    a.zchunk = (planes + zc - 1) / zc;
-    a.nchunks = zc;
-    {
-        const size_t need = (size_t)zc * 48 * nthr + nthr * sizeof(int2);
-        if (need > ctx->states_bytes)
-        {
-            KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            if (ctx->states) cudaFree(ctx->states);
-            ctx->states = nullptr; ctx->states_bytes = 0;
-            KFB_CUDA(ctx, cudaMalloc(&ctx->states, need));
-            ctx->states_bytes = need;
-        }
-        a.states = ctx->states;
-        a.col_range = reinterpret_cast<int2 *>(ctx->states + (size_t)zc * 6 * nthr);
-        dim3 sb(32, 4), sg((a.X + 127) / 128, (a.Y + 3) / 4);
-        column_states_kernel<<<sg, sb, 0, ctx->stream>>>(a);
-        KFB_LAUNCH_CHECK(ctx);
-    }
-    dim3 block(32, KFB_INT_WARPS), grid((a.X + 4 * KFB_INT_WARPS * KFB_INT_PX - 1) / (4 * KFB_INT_WARPS * KFB_INT_PX), (a.Y + 32 / KFB_INT_PX - 1) / (32 / KFB_INT_PX), zc);
-    if (n_updated)
-    {
-        KFB_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, sizeof(unsigned long long), ctx->stream));
-        integrate_kernel<2, true><<<grid, block, 0, ctx->stream>>>(a);
-        KFB_LAUNCH_CHECK(ctx);
-        KFB_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, ctx->counters, sizeof(unsigned long long),
-                                      cudaMemcpyDeviceToHost, ctx->stream));
-        KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        *n_updated = ctx->counters_host[0];
-    }
-    else
-    {
-        if (ctx->profiling) cudaEventRecord(ctx->events[60], ctx->stream);
-        // planes per iteration of the general path: with the stages' loads batched and short chunks, one plane
-        // per iteration (fewest live registers) measured 2-3 % faster than two at 512^3, 1024^3 and 2048^3
-        const int U = getenv("KFB_INTEGRATE_U") ? atoi(getenv("KFB_INTEGRATE_U")) : 1;
-        if (U == 2) integrate_kernel<2, false><<<grid, block, 0, ctx->stream>>>(a);
-        else if (U == 4) integrate_kernel<4, false><<<grid, block, 0, ctx->stream>>>(a);
-        else integrate_kernel<1, false><<<grid, block, 0, ctx->stream>>>(a);
-        KFB_LAUNCH_CHECK(ctx);
-        if (ctx->profiling) cudaEventRecord(ctx->events[61], ctx->stream);
-    }
-    return KFB_OK;
-}
-
 // planned sweep: plan -> states of the general items -> general items || stream items
 static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, uint64_t *n_updated)
 {
-    a.refine = getenv("KFB_INTEGRATE_REFINE") ? 1 : 0;
     a.zchunk = KFB_PLAN_ZCHUNK;
     if (const char *e = getenv("KFB_PLAN_ZCHUNK")) { const int v = atoi(e); if (v >= 2 && v <= 64) a.zchunk = v; }
     a.nchunks = (planes + a.zchunk - 1) / a.zchunk;
@@ -1770,7 +1140,6 @@ static void fill_integrate_args(kfb_ctx *ctx, const float vol2cam12[12], Integra
     a.vol = ctx->vol;
     a.X = ctx->p.volu_dims[0];
     a.Y = ctx->p.volu_dims[1];
-    a.z_store0 = ctx->z0;
     a.zb = ctx->z0 < 1 ? 1 : ctx->z0;
     a.ze = ctx->z1;
     a.pose = make_pose(vol2cam12);
@@ -1778,25 +1147,19 @@ static void fill_integrate_args(kfb_ctx *ctx, const float vol2cam12[12], Integra
     a.trunc = ctx->p.volu_trun_dist;
     a.fx = k.fx; a.fy = k.fy; a.cx = k.cx; a.cy = k.cy;
     a.w = k.w; a.h = k.h;
-    a.thrz = ctx->tab_thrz;
-    a.exact = ctx->tab_exact;
     a.wtab = ctx->wtab;
     a.zexit = ctx->zexit;
     a.max_weight = ctx->p.tsdf_max_weight;
     a.no_fastpath = getenv("KFB_INTEGRATE_NOFAST") ? 1 : 0;
-    a.no_prefix = getenv("KFB_INTEGRATE_NOPREFIX") ? 1 : 0;
-    a.diag = getenv("KFB_INTEGRATE_DIAG") ? atoi(getenv("KFB_INTEGRATE_DIAG")) : 0;
     a.use_jump = getenv("KFB_INTEGRATE_NOJUMP") ? 0 : 1;
     // measured on B200: a jump costs about as much as 600 replayed planes (warps that straddle vc.x == 0 walk
-    // many binades), so it pays for far z-slabs / large volumes, not for the z-chunks of a 512^3 sweep
+    // many binades), so it pays for far z-slabs / large volumes, not inside a 512^3 sweep
     a.jump_min = getenv("KFB_INTEGRATE_JUMPMIN") ? atoi(getenv("KFB_INTEGRATE_JUMPMIN")) : 640;
     a.bricks = ctx->bricks;
     a.bdirty = ctx->bdirty;
     a.bx = ctx->bdim[0]; a.by = ctx->bdim[1]; a.bz = ctx->bdim[2]; a.bz0 = ctx->bz0;
     a.counter = ctx->counters;
     make_cull_planes(ctx, a, a.cull);
-    a.zmip = ctx->zmip;
-    for (int i = 0; i < 6; ++i) { a.mip_off[i] = ctx->mip_off[i]; a.mip_w[i] = (k.w + (1 << (i + 2)) - 1) >> (i + 2); }
     a.Sx = a.vsx * a.pose.R.m[2]; a.Sy = a.vsx * a.pose.R.m[5]; a.Sz = a.vsx * a.pose.R.m[8];
     a.invSz = a.Sz > 1e-6f ? 1.f / a.Sz : 0.f;
     {
@@ -1804,13 +1167,11 @@ static void fill_integrate_args(kfb_ctx *ctx, const float vol2cam12[12], Integra
                          ctx->p.volu_range[2] + (double)a.vsx * ctx->p.volu_dims[2] * 1.01;
         a.driftE = (float)(((double)ctx->p.volu_dims[2] + 16.0) * 1.2e-7 * M + 4e-6 * M); // as in make_cull_planes + float model evaluation
     }
-    if (getenv("KFB_INTEGRATE_NOCULL") || getenv("KFB_INTEGRATE_NOOCC")) a.Sz = 0.f;
+    if (getenv("KFB_INTEGRATE_NOCULL") || getenv("KFB_INTEGRATE_NOOCC")) a.Sz = 0.f; // no occlusion cut, no stream items
     if (getenv("KFB_INTEGRATE_NOCULL"))
         for (int c = 0; c < KFB_NCULL; ++c) a.cull[c].kind = 3;
-
     a.tab4 = ctx->tab4;
     a.zsparse = ctx->zsparse;
-    a.use_sparse = (ctx->zsparse && !getenv("KFB_PLAN_TILES")) ? 1 : 0;
 }
 
 int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_updated)
@@ -1820,16 +1181,8 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
     fill_integrate_args(ctx, vol2cam12, a);
     const int planes = a.ze - a.zb;
     if (planes <= 0) return KFB_OK;
-    if (!getenv("KFB_INTEGRATE_V1"))
-    {
-        const int rcp = launch_integrate_planned(ctx, a, planes, n_updated);
-        if (rcp) return rcp;
-    }
-    else
-    {
-        const int rc1 = launch_integrate_v1(ctx, a, planes, n_updated);
-        if (rc1) return rc1;
-    }
+    const int rcp = launch_integrate_planned(ctx, a, planes, n_updated);
+    if (rcp) return rcp;
     KFB_CUDA(ctx, cudaEventRecord(ctx->ev_tables_free, ctx->stream)); // the next frame's tables may now be built
     const int rcd = launch_brick_distance(ctx);
     if (ctx->profiling) cudaEventRecord(ctx->events[57], ctx->stream);
@@ -1845,18 +1198,19 @@ int launch_build_wtab(kfb_ctx *ctx)
 }
 
 // ---- brick map maintenance -------------------------------------------------------------------------
-// full rescan (after kfb_upload_volume): same marking rule as the integrate kernel
-__global__ void rebuild_bricks_kernel(const IntegrateArgs a, int zs0, int zs1)
+// full rescan (after kfb_upload_volume): same marking rule as the integrate kernel; a thread looks at one 16-byte
+// quad of the brick-major volume
+__global__ void rebuild_bricks_kernel(const IntegrateArgs a, size_t nquads, int Z)
 {
-    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x0 >= a.X || y >= a.Y) return;
-    const size_t plane4 = ((size_t)a.X * a.Y) >> 2;
-    const uint4 *vp = reinterpret_cast<const uint4 *>(a.vol) + (size_t)y * (a.X >> 2) + (x0 >> 2);
-    for (int z = zs0 + blockIdx.z; z < zs1; z += gridDim.z)
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < nquads; q += (size_t)gridDim.x * blockDim.x)
     {
-        const uint4 o = __ldg(vp + (size_t)(z - zs0) * plane4);
-        if ((o.x | o.y | o.z | o.w) & 0x8000u) mark_bricks(a.bricks, a.bdirty, a.bx, a.by, a.bz, a.bz0, x0, y, z);
+        const uint4 o = __ldg(reinterpret_cast<const uint4 *>(a.vol) + q);
+        if (!((o.x | o.y | o.z | o.w) & 0x8000u)) continue;
+        const size_t brick = q >> 7;
+        const int in = (int)(q & 127), bxy = a.bx * a.by;
+        const int bzi = (int)(brick / bxy), r = (int)(brick - (size_t)bzi * bxy);
+        const int x0 = ((r % a.bx) << 3) + ((in & 1) << 2), y = ((r / a.bx) << 3) + ((in >> 1) & 7), z = ((bzi + a.bz0) << 3) + (in >> 4);
+        if (x0 < a.X && y < a.Y && z < Z) mark_bricks(a.bricks, a.bdirty, a.bx, a.by, a.bz, a.bz0, x0, y, z);
     }
 }
 
@@ -1871,8 +1225,7 @@ int launch_rebuild_bricks(kfb_ctx *ctx)
     a.bricks = ctx->bricks;
     a.bdirty = ctx->bdirty;
     a.bx = ctx->bdim[0]; a.by = ctx->bdim[1]; a.bz = ctx->bdim[2]; a.bz0 = ctx->bz0;
-    dim3 block(32, 4), grid((a.X / 4 + 31) / 32, (a.Y + 3) / 4, 32);
-    rebuild_bricks_kernel<<<grid, block, 0, ctx->stream>>>(a, ctx->z0, ctx->z1);
+    rebuild_bricks_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(a, ctx->vol_voxels / 4, ctx->p.volu_dims[2]);
     KFB_LAUNCH_CHECK(ctx);
     KFB_CUDA(ctx, cudaMemsetAsync(ctx->bdirty, 1, sizeof(int), ctx->stream)); // non-zero: force a distance rebuild
     return launch_brick_distance(ctx);
@@ -1920,75 +1273,18 @@ int launch_brick_distance(kfb_ctx *ctx)
 }
 
 // ---- work histogram over planes (slab balancing for sharded volumes) -----------------------------------------
-// Number of 4-voxel groups the sweep would visit on every plane of the WHOLE volume for this depth image and
-// pose (frustum interval only; independent of the volume's content and of the planes this context stores).
-// Written as a difference array: +1 at the first visited plane, -1 after the last.
-__global__ void __launch_bounds__(128) plane_histogram_kernel(const IntegrateArgs a, int Z, int *__restrict__ diff)
-{
-    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int y = blockIdx.y * 4 + threadIdx.y;
-    if (x0 >= a.X || y >= a.Y) return;
-    float vx[2], vy[2], vz[2];
-    const float py = __fmul_rn((float)y, a.vsy);
-    const float pz = __fmul_rn(0.f, a.vsz);
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-    {
-        const float px = __fmul_rn((float)(x0 + 3 * k), a.vsx);
-        const float3 r = rot3(a.pose.R, px, py, pz);
-        vx[k] = __fadd_rn(r.x, a.pose.t[0]);
-        vy[k] = __fadd_rn(r.y, a.pose.t[1]);
-        vz[k] = __fadd_rn(r.z, a.pose.t[2]);
-    }
-    float lo, hi;
-    frustum_interval(a, vx[0], vy[0], vz[0], vx[1], vy[1], vz[1], 1, Z, lo, hi);
-    const int za = max(1, (int)floorf(lo)), zb = min(Z - 1, (int)ceilf(hi));
-    if (za > zb) return;
-    atomicAdd(diff + za, 1);
-    atomicAdd(diff + zb + 1, -1);
-}
-
-static int launch_plane_histogram_frustum(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *host_hist)
-{
-    const Intr &k = ctx->L[0].k;
-    const int Z = ctx->p.volu_dims[2];
-    IntegrateArgs a;
-    memset(&a, 0, sizeof(a));
-    a.X = ctx->p.volu_dims[0]; a.Y = ctx->p.volu_dims[1];
-    a.pose = make_pose(vol2cam12);
-    a.vsx = ctx->voxel_size[0]; a.vsy = ctx->voxel_size[1]; a.vsz = ctx->voxel_size[2];
-    a.fx = k.fx; a.fy = k.fy; a.cx = k.cx; a.cy = k.cy; a.w = k.w; a.h = k.h;
-    a.zexit = ctx->zexit;
-    make_cull_planes(ctx, a, a.cull);
-    int *diff = nullptr;
-    KFB_CUDA(ctx, cudaMalloc(&diff, (size_t)(Z + 2) * sizeof(int)));
-    KFB_CUDA(ctx, cudaMemsetAsync(diff, 0, (size_t)(Z + 2) * sizeof(int), ctx->stream));
-    dim3 block(32, 4), grid((a.X + 127) / 128, (a.Y + 3) / 4);
-    plane_histogram_kernel<<<grid, block, 0, ctx->stream>>>(a, Z, diff);
-    ctx->launches++;
-    std::vector<int> h((size_t)Z + 2);
-    cudaError_t e = cudaMemcpyAsync(h.data(), diff, h.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(diff);
-    KFB_CUDA(ctx, e);
-    long run = 0;
-    for (int z = 0; z < Z; ++z) { run += h[z]; host_hist[z] = (uint32_t)(run > 0 ? run : 0); }
-    return KFB_OK;
-}
-
 // Work per plane from the sweep's own plan: the plan kernel runs for the WHOLE volume (it needs the depth tables and
 // the pose, not the voxels), and every item adds its 32 voxel quads per plane to the planes it covers -- once for a
-// stream item, KFB_HIST_GENERAL_WEIGHT times for a general item (measured cost ratio per quad at 512^3).  The
-// frustum-only count above left the busiest of two 2048^3 slabs 30 % behind the other (profiles/README.md).
+// stream item, KFB_HIST_GENERAL_WEIGHT times for a general item (measured cost ratio per quad at 512^3).  (A count
+// of the frustum alone left the busiest of two 2048^3 slabs 30 % behind the other, profiles/README.md.)
 #define KFB_HIST_GENERAL_WEIGHT 4
 int launch_plane_histogram(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *host_hist)
 {
     const int Z = ctx->p.volu_dims[2];
-    if (getenv("KFB_HIST_FRUSTUM")) return launch_plane_histogram_frustum(ctx, vol2cam12, host_hist);
     IntegrateArgs a;
     fill_integrate_args(ctx, vol2cam12, a);
     a.vol = nullptr;
-    a.z_store0 = 0; a.zb = 1; a.ze = Z;
+    a.zb = 1; a.ze = Z;
     if (Z > 65535) { ctx->err = "volumes deeper than 65535 planes are not supported"; return KFB_ERR_UNSUPPORTED; }
     a.zchunk = 16;
     a.nchunks = (Z - 1 + a.zchunk - 1) / a.zchunk;
@@ -2041,6 +1337,44 @@ int launch_plane_histogram(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *ho
         run += diff[z];
         host_hist[z] = (uint32_t)std::min<long long>(std::max<long long>(run, 0), 0xffffffffll);
     }
+    return KFB_OK;
+}
+
+// ---- host <-> device volume copies in the reference's order (GpuMat download / upload of the tests and checkpoints) ----
+// lin: X * Y * (z1 - z0) packed voxels, x fastest; a thread moves four consecutive x voxels
+__global__ void volume_relayout_kernel(uint32_t *__restrict__ vol, uint32_t *__restrict__ lin, int X, int Y, int z0, int z1, int bx, int by, int bz0,
+                                       int to_bricks)
+{
+    const size_t nq = ((size_t)X * Y * (size_t)(z1 - z0)) >> 2;
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < nq; q += (size_t)gridDim.x * blockDim.x)
+    {
+        const size_t i = q << 2;
+        const int x = (int)(i % X), y = (int)((i / X) % Y), z = z0 + (int)(i / ((size_t)X * Y));
+        uint4 *b = reinterpret_cast<uint4 *>(vol + vol_index(bx, by, bz0, x, y, z));
+        uint4 *l = reinterpret_cast<uint4 *>(lin + i);
+        if (to_bricks) *b = *l;
+        else *l = *b;
+    }
+}
+
+int launch_volume_copy(kfb_ctx *ctx, int16_t *host_pairs, int to_device)
+{
+    uint32_t *lin = nullptr;
+    const size_t bytes = ctx->vol_logical * sizeof(uint32_t);
+    KFB_CUDA(ctx, cudaMalloc(&lin, bytes));
+    cudaError_t e = cudaSuccess;
+    if (to_device) e = cudaMemcpyAsync(lin, host_pairs, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+    {
+        volume_relayout_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(ctx->vol, lin, ctx->p.volu_dims[0], ctx->p.volu_dims[1], ctx->z0, ctx->z1,
+                                                                           ctx->bdim[0], ctx->bdim[1], ctx->bz0, to_device);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && !to_device) e = cudaMemcpyAsync(host_pairs, lin, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(lin);
+    KFB_CUDA(ctx, e);
     return KFB_OK;
 }
 

@@ -57,18 +57,14 @@ __device__ __forceinline__ int rn_magic(float v) { return __float_as_int(__fadd_
 // (float)i for |i| < 2^22
 __device__ __forceinline__ float i2f_magic(int i) { return __fsub_rn(__int_as_float(KFB_RC_MAGIC_I + i), KFB_RC_MAGIC_F); }
 
-// MODE 0: the context stores the whole volume (zs0 = zo0 = bz0 = 0, zs1 = zo1 = Z); the slab tests fold away
-// MODE 1: z-slab (stored planes [zs0, zs1), owned planes [zo0, zo1))
-// MODE 2: whole volume read from a BRICK-MAJOR copy (8x8x8 voxel bricks contiguous, bricks in x, y, z order): the
-//         "L2-friendly voxel layout" experiment of north_star item 4 (KFB_RAYCAST_BLOCKED=1; measured, not adopted:
-//         profiles/README.md)
-enum { RC_WHOLE = 0, RC_SLAB = 1, RC_BLOCKED = 2 };
+// MODE RC_WHOLE: the context stores the whole volume (zs0 = zo0 = bz0 = 0, zs1 = zo1 = Z); the slab tests fold away
+// MODE RC_SLAB:  z-slab (stored planes [zs0, zs1), owned planes [zo0, zo1))
+// Voxels are read from the brick-major volume (kfb_common.cuh: vol_index; the brick grid is the distance map's).
+enum { RC_WHOLE = 0, RC_SLAB = 1 };
 template <int MODE>
 __device__ __forceinline__ size_t vox_index(const RaycastArgs &a, int x, int y, int z)
 {
-    if (MODE == RC_BLOCKED)
-        return ((size_t)(((z >> 3) * a.by + (y >> 3)) * a.bx + (x >> 3)) << 9) + (size_t)(((z & 7) << 6) | ((y & 7) << 3) | (x & 7));
-    return ((size_t)(z - (MODE == RC_SLAB ? a.zs0 : 0)) * a.Y + y) * a.X + x;
+    return vol_index(a.bx, a.by, MODE == RC_SLAB ? a.bz0 : 0, x, y, z);
 }
 template <int MODE>
 __device__ __forceinline__ float vox_tsdf(const RaycastArgs &a, int x, int y, int z)
@@ -558,19 +554,6 @@ int launch_shard_composite(kfb_ctx *ctx)
     return KFB_OK;
 }
 
-// linear -> brick-major copy (layout experiment only): a thread moves four consecutive x voxels
-__global__ void relayout_blocked_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, int X, int Y, int Z)
-{
-    const size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    const size_t nq = ((size_t)X * Y * Z) >> 2;
-    if (q >= nq) return;
-    const size_t i = q << 2;
-    const int x = (int)(i % X), y = (int)((i / X) % Y), z = (int)(i / ((size_t)X * Y));
-    const int bx = X >> 3, by = Y >> 3;
-    const size_t o = ((size_t)(((z >> 3) * by + (y >> 3)) * bx + (x >> 3)) << 9) + (size_t)(((z & 7) << 6) | ((y & 7) << 3) | (x & 7));
-    *reinterpret_cast<uint4 *>(dst + o) = __ldg(reinterpret_cast<const uint4 *>(src + i));
-}
-
 int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9])
 {
     RaycastArgs a;
@@ -606,21 +589,9 @@ int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9]
     }
     ctx->pyramid_fresh = a.fuse_pyramid;
     dim3 block(8, 4 * KFB_RC_WARPS), grid((a.k.w + 7) / 8, (a.k.h + 4 * KFB_RC_WARPS - 1) / (4 * KFB_RC_WARPS));
-    const bool whole_ = a.zs0 == 0 && a.zs1 == a.Z && a.zo0 == 0 && a.zo1 == a.Z && a.bz0 == 0 && !getenv("KFB_RAYCAST_SLABCODE");
-    // layout experiment: march a brick-major copy of the volume (the copy itself is not part of the timed kernel)
-    const bool blocked = whole_ && getenv("KFB_RAYCAST_BLOCKED") && a.X % 8 == 0 && a.Y % 8 == 0 && a.Z % 8 == 0;
-    if (blocked)
-    {
-        if (!ctx->vol_blocked) KFB_CUDA(ctx, cudaMalloc(&ctx->vol_blocked, ctx->vol_voxels * sizeof(uint32_t)));
-        const size_t n4 = ctx->vol_voxels / 4;
-        relayout_blocked_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, ctx->stream>>>(ctx->vol, ctx->vol_blocked, a.X, a.Y, a.Z);
-        KFB_LAUNCH_CHECK(ctx);
-        a.vol = ctx->vol_blocked;
-    }
     if (ctx->profiling) cudaEventRecord(ctx->events[58], ctx->stream);
     const bool whole = a.zs0 == 0 && a.zs1 == a.Z && a.zo0 == 0 && a.zo1 == a.Z && a.bz0 == 0 && !getenv("KFB_RAYCAST_SLABCODE");
-    if (whole && blocked) raycast_kernel<RC_BLOCKED><<<grid, block, 0, ctx->stream>>>(a);
-    else if (whole) raycast_kernel<RC_WHOLE><<<grid, block, 0, ctx->stream>>>(a);
+    if (whole) raycast_kernel<RC_WHOLE><<<grid, block, 0, ctx->stream>>>(a);
     else raycast_kernel<RC_SLAB><<<grid, block, 0, ctx->stream>>>(a);
     KFB_LAUNCH_CHECK(ctx);
     if (ctx->profiling) cudaEventRecord(ctx->events[59], ctx->stream);

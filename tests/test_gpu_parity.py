@@ -562,9 +562,10 @@ def test_full_size_properties_512(kfo, kfb):
 
 
 def test_integrate_jump_equals_replay(kfo, kfb):
-    """The closed-form jump of the float running sum (kfb_integrate.cu: jump4) against plain replay
+    """The closed-form jump of the float running sum (kfb_common.cuh: jump_fma) against plain replay
     (KFB_INTEGRATE_NOJUMP=1): volumes must be bit-identical for poses whose vc.x / vc.y cross zero and
-    binade boundaries inside the skipped prefix, for several z-chunk counts and for a far z-slab."""
+    binade boundaries inside the skipped prefix, for several plan chunk heights and for far z-slabs (whose states
+    kernel jumps over the prefix in front of the slab)."""
     dims = 256
     Ko, Kb, Po, Pb = make_pair(kfo, kfb, dims, 320, 240)
     volpose = np.array(Po.volu_pose, np.float32)
@@ -578,17 +579,19 @@ def test_integrate_jump_equals_replay(kfo, kfb):
         poses.append(np.concatenate([R, t[:, None]], axis=1).astype(np.float32).reshape(12))
     Pslab = kfb.default_params(dims)
     Pslab.slab_z_begin, Pslab.slab_z_end = 192, 256
-    saved = {k: os.environ.get(k) for k in ("KFB_INTEGRATE_NOJUMP", "KFB_INTEGRATE_ZCHUNKS", "KFB_INTEGRATE_JUMPMIN")}
+    Pmid = kfb.default_params(dims)
+    Pmid.slab_z_begin, Pmid.slab_z_end = 61, 131       # not brick-aligned
+    saved = {k: os.environ.get(k) for k in ("KFB_INTEGRATE_NOJUMP", "KFB_PLAN_ZCHUNK", "KFB_INTEGRATE_JUMPMIN")}
     os.environ["KFB_INTEGRATE_JUMPMIN"] = "16"
     try:
-        for P, chunks in ((Pb, "1"), (Pb, "4"), (Pb, "16"), (Pslab, "2")):
+        for P, chunks in ((Pb, "8"), (Pslab, "8"), (Pslab, "16"), (Pmid, "5")):
             vols = []
             for nojump in (False, True):
                 if nojump:
                     os.environ["KFB_INTEGRATE_NOJUMP"] = "1"
                 else:
                     os.environ.pop("KFB_INTEGRATE_NOJUMP", None)
-                os.environ["KFB_INTEGRATE_ZCHUNKS"] = chunks
+                os.environ["KFB_PLAN_ZCHUNK"] = chunks
                 ctx = _ctx(kfb, Kb, P)
                 for pose in poses:
                     ctx.upload_depth_mm(kfo.render_depth_mm(pose, Ko))
@@ -607,15 +610,17 @@ def test_integrate_jump_equals_replay(kfo, kfb):
 
 
 def test_integrate_switches_bit_identical(kfo, kfb):
-    """Every work-skipping device (frustum interval, occlusion cut, deep-free-space path, z-chunking, planes per
-    iteration) must leave the volume bit-identical: compare each switch against the plain sweep."""
+    """Every work-skipping device of the planned sweep (frustum interval, occlusion cut, stream items, chunk height,
+    one or two streams) must leave the volume bit-identical: compare each switch against the plain sweep, in which
+    every voxel of every plane goes through the per-voxel predicate (that run also has more general items than
+    state slots, so the items that replay their running sums themselves are covered)."""
     dims = 256
     Ko, Kb, Po, Pb = make_pair(kfo, kfb, dims, 640, 480)
     volpose = np.array(Po.volu_pose, np.float32)
     poses = [kfo.trajectory_pose(k) for k in (0, 25, 60)]
     frames = [kfo.render_depth_mm(p, Ko) for p in poses]
-    keys = ("KFB_INTEGRATE_NOCULL", "KFB_INTEGRATE_NOOCC", "KFB_INTEGRATE_NOFAST", "KFB_INTEGRATE_NOPREFIX", "KFB_INTEGRATE_ZCHUNKS",
-            "KFB_INTEGRATE_U")
+    keys = ("KFB_INTEGRATE_NOCULL", "KFB_INTEGRATE_NOOCC", "KFB_INTEGRATE_NOFAST", "KFB_PLAN_ZCHUNK", "KFB_INTEGRATE_SERIAL",
+            "KFB_INTEGRATE_PERSISTENT", "KFB_GEN_MINB")
     saved = {k: os.environ.get(k) for k in keys}
 
     def run(env):
@@ -634,10 +639,11 @@ def test_integrate_switches_bit_identical(kfo, kfb):
         return vol, n
 
     try:
-        plain, n_plain = run({"KFB_INTEGRATE_NOCULL": "1", "KFB_INTEGRATE_NOFAST": "1", "KFB_INTEGRATE_ZCHUNKS": "1"})
+        plain, n_plain = run({"KFB_INTEGRATE_NOCULL": "1", "KFB_INTEGRATE_NOFAST": "1", "KFB_PLAN_ZCHUNK": "16"})
         assert plain[..., 1].max() >= 6
-        for env in ({}, {"KFB_INTEGRATE_NOFAST": "1"}, {"KFB_INTEGRATE_NOOCC": "1"}, {"KFB_INTEGRATE_ZCHUNKS": "3"},
-                    {"KFB_INTEGRATE_ZCHUNKS": "32"}, {"KFB_INTEGRATE_NOPREFIX": "1"}, {"KFB_INTEGRATE_U": "2"}, {"KFB_INTEGRATE_U": "4"}):
+        for env in ({}, {"KFB_INTEGRATE_NOFAST": "1"}, {"KFB_INTEGRATE_NOOCC": "1"}, {"KFB_PLAN_ZCHUNK": "3"},
+                    {"KFB_PLAN_ZCHUNK": "32"}, {"KFB_INTEGRATE_SERIAL": "1"}, {"KFB_INTEGRATE_PERSISTENT": "1"},
+                    {"KFB_GEN_MINB": "5"}, {"KFB_GEN_MINB": "6"}):
             vol, n = run(env)
             assert n == n_plain, env
             assert np.array_equal(vol, plain), env

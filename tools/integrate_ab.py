@@ -15,16 +15,14 @@ import slam_kinectfusion_b200 as kfb  # noqa: E402
 from slam_kinectfusion_b200 import synth  # noqa: E402
 
 VARIANTS = {
-    "v1 (round-1 kernel)": {"KFB_INTEGRATE_V1": "1"},
-    "planned, tile pyramid": {"KFB_PLAN_TILES": "1"},
-    "planned, serial": {"KFB_INTEGRATE_SERIAL": "1"},
-    "planned zchunk16": {"KFB_PLAN_ZCHUNK": "16"},
-    "planned zchunk6": {"KFB_PLAN_ZCHUNK": "6"},
-    "planned zchunk4": {"KFB_PLAN_ZCHUNK": "4"},
-    "planned (default)": {},
+    "serial (one stream)": {"KFB_INTEGRATE_SERIAL": "1"},
+    "persistent grids": {"KFB_INTEGRATE_PERSISTENT": "1"},
+    "chunks of 16 planes": {"KFB_PLAN_ZCHUNK": "16"},
+    "chunks of 6 planes": {"KFB_PLAN_ZCHUNK": "6"},
+    "general kernel 80 regs": {"KFB_GEN_MINB": "6"},
+    "default": {},
 }
-SWITCHES = ("KFB_INTEGRATE_V1", "KFB_INTEGRATE_SERIAL", "KFB_INTEGRATE_PERSISTENT", "KFB_GEN_MINB", "KFB_BRICKS_3PASS", "KFB_PLAN_ZCHUNK",
-            "KFB_INTEGRATE_NOPREFIX", "KFB_INTEGRATE_REFINE", "KFB_PLAN_TILES")
+SWITCHES = ("KFB_INTEGRATE_SERIAL", "KFB_INTEGRATE_PERSISTENT", "KFB_GEN_MINB", "KFB_PLAN_ZCHUNK")
 
 
 def main():
@@ -66,7 +64,7 @@ def main():
         P = np.vstack([kf.pose().astype(np.float64).reshape(3, 4), [0, 0, 0, 1]])
         V = np.vstack([np.array(hp.volu_pose, np.float64).reshape(3, 4), [0, 0, 0, 1]])
         U = ctx.integrate((np.linalg.inv(P) @ V)[:3].astype(np.float32).reshape(12), count=True)
-        cnt = ctx.integrate_counts() if "v1" not in name else {}
+        cnt = ctx.integrate_counts()
         print(f"{name:24s} sweep {np.mean(k_ms) * 1e3:7.1f} us  call {np.mean(c_ms) * 1e3:7.1f} us  U {U}  "
               f"8U/t {8 * U / np.mean(k_ms) / 1e6:7.1f} GB/s  {cnt}  sha1 {digests[name][:12]}", flush=True)
     assert len(set(digests.values())) == 1, digests
