@@ -384,7 +384,7 @@ __device__ __forceinline__ void update_quad(const IntegrateArgs &a, uint4 *vp, c
 // ---- the sweep as a work plan ---------------------------------------------------------------------------------
 // The decisions a sweep needs -- which planes of which voxel columns can pass the reference's predicate at all, which
 // of them are deep free space, which need the per-voxel predicate -- are taken once, by a small kernel with one thread
-// per (16 x 8 voxel patch, 8-plane chunk), which writes two compact work lists (round 1 took them inside the sweep,
+// per (16 x 8 voxel patch, 16-plane chunk), which writes two compact work lists (round 1 took them inside the sweep,
 // per warp and chunk: with every warp slot taken by warps that wait on memory, set-up, streaming and per-voxel work
 // simply added up):
 //   stream items  {patch, z0..z1}: every voxel of these planes passes the predicate with tsdf == 1.0f exactly --
@@ -404,7 +404,7 @@ __device__ __forceinline__ void update_quad(const IntegrateArgs &a, uint4 *vp, c
 // same two bricks for eight planes.
 #define KFB_PATCH_X 16
 #define KFB_PATCH_Y 8
-#define KFB_PLAN_ZCHUNK 8
+#define KFB_PLAN_ZCHUNK 16 // planes per plan chunk: two brick layers (measured at 512^3, brick-major: 6 / 8 / 16 planes -> sweep 122 / 112 / 104 us)
 
 // A sweep thread of a patch: lane = brick half * 16 + row * 2 + quad.  x0 / y = its four voxels; quad_index(z) = index,
 // in 16-byte units, of those voxels on plane z in the brick-major volume.

@@ -17,8 +17,9 @@ from slam_kinectfusion_b200 import synth  # noqa: E402
 VARIANTS = {
     "serial (one stream)": {"KFB_INTEGRATE_SERIAL": "1"},
     "persistent grids": {"KFB_INTEGRATE_PERSISTENT": "1"},
-    "chunks of 16 planes": {"KFB_PLAN_ZCHUNK": "16"},
-    "chunks of 6 planes": {"KFB_PLAN_ZCHUNK": "6"},
+    "chunks of 8 planes": {"KFB_PLAN_ZCHUNK": "8"},
+    "chunks of 24 planes": {"KFB_PLAN_ZCHUNK": "24"},
+    "chunks of 32 planes": {"KFB_PLAN_ZCHUNK": "32"},
     "general kernel 80 regs": {"KFB_GEN_MINB": "6"},
     "default": {},
 }
