@@ -425,6 +425,10 @@ __device__ __forceinline__ PatchLane patch_lane(const IntegrateArgs &a, int patc
     p.in_plane = row * 2 + quad;
     return p;
 }
+// plan chunks sit at absolute multiples of the chunk height (a multiple of the brick height by default), so that a
+// chunk is made of whole brick layers; the first chunk starts at the first processed plane
+__device__ __forceinline__ int chunk_first_plane(const IntegrateArgs &a, int c) { return max(a.zb, (a.zb / a.zchunk + c) * a.zchunk); }
+__device__ __forceinline__ int chunk_end_plane(const IntegrateArgs &a, int c) { return min(a.ze, (a.zb / a.zchunk + c + 1) * a.zchunk); }
 __device__ __forceinline__ size_t quad_index(const IntegrateArgs &a, const PatchLane &p, int z)
 {
     return ((((size_t)((z >> 3) - a.bz0)) * ((size_t)a.bx * a.by) + p.brick_xy) << 7) + (size_t)(((z & 7) << 4) | p.in_plane);
@@ -470,7 +474,7 @@ __global__ void __launch_bounds__(128) integrate_plan_kernel(const IntegrateArgs
         c = t / npatch;
         patch = t - c * npatch;
         const int py = patch / a.npx, px = patch - py * a.npx;
-        const int zstart = a.zb + c * a.zchunk, zend = min(zstart + a.zchunk, a.ze);
+        const int zstart = chunk_first_plane(a, c), zend = chunk_end_plane(a, c);
         const int xa = px * KFB_PATCH_X, xb = min(xa + KFB_PATCH_X - 1, a.X - 1), ya = py * KFB_PATCH_Y, yb = min(ya + KFB_PATCH_Y - 1, a.Y - 1);
         float cx[4], cy[4], cz[4];
         const float pz = __fmul_rn(0.f, a.vsz);
@@ -624,7 +628,7 @@ __global__ void __launch_bounds__(128) integrate_states_kernel(const IntegrateAr
     const unsigned long long vs2 = pack2(a.vsx, a.vsx), sxy = pack2(sx, sy), szz = pack2(sz, sz);
     for (int c = 0; c <= c_last; ++c)
     {
-        const int target = a.zb + c * a.zchunk - 1; // state after this plane
+        const int target = chunk_first_plane(a, c) - 1; // state after this plane
 #pragma unroll 4
         for (; done < target; ++done)
         {
@@ -682,7 +686,6 @@ __device__ __forceinline__ void update_free_quad(const IntegrateArgs &a, const f
 }
 
 #define KFB_WTAB_SMEM 256 // per-weight table entries kept in shared memory (max_weight < 256; the default is 64)
-#define KFB_STREAM_DEPTH 8
 template <bool COUNT, bool SMEM>
 __global__ void __launch_bounds__(128, 8) integrate_stream_kernel(const IntegrateArgs a)
 {
@@ -703,17 +706,18 @@ __global__ void __launch_bounds__(128, 8) integrate_stream_kernel(const Integrat
         if (pl.x0 >= a.X || pl.y >= a.Y) continue;
         const int z0 = (int)(it.y & 0xffffu), z1 = (int)(it.y >> 16);
         uint4 *const vol4 = reinterpret_cast<uint4 *>(a.vol);
-        for (int z = z0; z <= z1; z += KFB_STREAM_DEPTH)
+        for (int zl = z0 & ~7; zl <= z1; zl += 8) // one brick layer at a time: its eight planes are 256 B apart
         {
-            uint4 w[KFB_STREAM_DEPTH];
+            uint4 *const base = vol4 + quad_index(a, pl, zl);
+            uint4 w[8];
 #pragma unroll
-            for (int i = 0; i < KFB_STREAM_DEPTH; ++i)
-                if (z + i <= z1) w[i] = __ldcs(vol4 + quad_index(a, pl, z + i));
+            for (int i = 0; i < 8; ++i)
+                if (zl + i >= z0 && zl + i <= z1) w[i] = __ldcs(base + i * 16);
 #pragma unroll
-            for (int i = 0; i < KFB_STREAM_DEPTH; ++i)
-                if (z + i <= z1)
+            for (int i = 0; i < 8; ++i)
+                if (zl + i >= z0 && zl + i <= z1)
                 {
-                    update_free_quad<COUNT>(a, wt, vol4 + quad_index(a, pl, z + i), w[i], n_upd, n_st);
+                    update_free_quad<COUNT>(a, wt, base + i * 16, w[i], n_upd, n_st);
                     if (COUNT) ++n_ld;
                 }
         }
@@ -868,7 +872,7 @@ __global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const Inte
         const int x0 = pl.x0, y = pl.y;
         if (x0 >= a.X || y >= a.Y) continue;
         const int z0 = (int)(it.y & 0xffffu), z1 = (int)(it.y >> 16);
-        const int zstart = a.zb + ((z0 - a.zb) / a.zchunk) * a.zchunk; // first plane of the item's chunk
+        const int zstart = max(a.zb, (z0 / a.zchunk) * a.zchunk); // first plane of the item's chunk
         unsigned long long xy[4], zz[2];
         {
             int zfrom = zstart;
@@ -955,13 +959,14 @@ __global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const Inte
             continue;
         }
         // the exact per-voxel predicate, one plane (one memory latency) at a time
+        uint4 *vp = vol4 + quad_index(a, pl, z0);
         for (int z = z0; z <= z1; ++z)
         {
-            uint4 *vp = vol4 + quad_index(a, pl, z);
             GenStage S;
             gen_issue(a, g, xy, zz, vp, S);
             gen_process<COUNT>(a, g, wt, S, vp, x0, y, z, n_upd, n_st);
             if (COUNT) ++n_ld;
+            vp = ((z + 1) & 7) ? vp + 16 : vol4 + quad_index(a, pl, z + 1); // next plane of the brick, or the next brick layer
         }
     }
     if (COUNT)
@@ -1034,7 +1039,7 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
 {
     a.zchunk = KFB_PLAN_ZCHUNK;
     if (const char *e = getenv("KFB_PLAN_ZCHUNK")) { const int v = atoi(e); if (v >= 2 && v <= 64) a.zchunk = v; }
-    a.nchunks = (planes + a.zchunk - 1) / a.zchunk;
+    a.nchunks = (a.ze - 1) / a.zchunk - a.zb / a.zchunk + 1;
     a.npx = (a.X + KFB_PATCH_X - 1) / KFB_PATCH_X;
     a.npy = (a.Y + KFB_PATCH_Y - 1) / KFB_PATCH_Y;
     a.mask_words = (a.nchunks + 31) / 32;
@@ -1287,7 +1292,7 @@ int launch_plane_histogram(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *ho
     a.zb = 1; a.ze = Z;
     if (Z > 65535) { ctx->err = "volumes deeper than 65535 planes are not supported"; return KFB_ERR_UNSUPPORTED; }
     a.zchunk = 16;
-    a.nchunks = (Z - 1 + a.zchunk - 1) / a.zchunk;
+    a.nchunks = (a.ze - 1) / a.zchunk - a.zb / a.zchunk + 1;
     a.npx = (a.X + KFB_PATCH_X - 1) / KFB_PATCH_X;
     a.npy = (a.Y + KFB_PATCH_Y - 1) / KFB_PATCH_Y;
     a.mask_words = (a.nchunks + 31) / 32;

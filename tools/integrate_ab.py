@@ -28,7 +28,7 @@ SWITCHES = ("KFB_INTEGRATE_SERIAL", "KFB_INTEGRATE_PERSISTENT", "KFB_GEN_MINB", 
 
 def main():
     dims = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-    n = int(sys.argv[2]) if len(sys.argv) > 2 else 28
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 60
     only = sys.argv[3] if len(sys.argv) > 3 else None      # run a single variant (profiler runs)
     K = kfb.Intrinsics(**kfb.SENSORS["kinect1"])
     frames = synth.sequence(n, K)
@@ -51,7 +51,7 @@ def main():
                 ctx.synchronize()
                 ctx.event_record(0)
             assert kf.pipeline_ptr(dev[i].data_ptr(), K.width, K.height) == 0
-            if i >= 8 and i % 4 == 3:
+            if i >= 8 and i % 3 == 2:
                 ctx.synchronize()
                 k_ms.append(ctx.event_elapsed_ms(60, 61))
                 c_ms.append(ctx.event_elapsed_ms(56, 57))
@@ -66,8 +66,8 @@ def main():
         V = np.vstack([np.array(hp.volu_pose, np.float64).reshape(3, 4), [0, 0, 0, 1]])
         U = ctx.integrate((np.linalg.inv(P) @ V)[:3].astype(np.float32).reshape(12), count=True)
         cnt = ctx.integrate_counts()
-        print(f"{name:24s} sweep {np.mean(k_ms) * 1e3:7.1f} us  call {np.mean(c_ms) * 1e3:7.1f} us  U {U}  "
-              f"8U/t {8 * U / np.mean(k_ms) / 1e6:7.1f} GB/s  {cnt}  sha1 {digests[name][:12]}", flush=True)
+        print(f"{name:24s} sweep median {np.median(k_ms) * 1e3:6.1f} (min {np.min(k_ms) * 1e3:6.1f}) us  call median {np.median(c_ms) * 1e3:6.1f} us  "
+              f"U {U}  8U/t {8 * U / np.median(k_ms) / 1e6:7.1f} GB/s  {cnt}  sha1 {digests[name][:12]}", flush=True)
     assert len(set(digests.values())) == 1, digests
     print("volumes identical across variants")
 
