@@ -405,6 +405,7 @@ def run_ours(args):
                    "frames_timed": S, "updated_voxels_per_frame": U_mean, "swept_voxels_per_frame": swept},
         "frame_device_ms": ms_per_frame,
         "e2e": {"value": U_mean / (e2e_ms_per_frame * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms_per_frame,
+                "device_ms_per_step": e2e_ms / S, "wall_ms_per_step": e2e_wall * 1e3 / S,
                 "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": 19 * 27 * 16,
                 "api": "kf::kinectfusion::pipeline(depth_mm) via libkfusion_b200.so, pinned host frames"},
         "gpu_launches": int(launches),

@@ -1266,7 +1266,7 @@ __global__ void brick_distance_kernel(const uint8_t *__restrict__ src, uint8_t *
 
 // x and y passes of one brick layer in shared memory (one block per layer): a layer is bx * by bytes (4 KB at 512^3,
 // 64 KB at 2048^3), so both passes read their 2 x 31 taps from shared memory and the layer crosses L2 once each way.
-__global__ void __launch_bounds__(256) brick_distance_xy_kernel(const uint8_t *__restrict__ flags, uint8_t *__restrict__ dst, int bx, int by,
+__global__ void __launch_bounds__(1024) brick_distance_xy_kernel(const uint8_t *__restrict__ flags, uint8_t *__restrict__ dst, int bx, int by,
                                                                 const int *__restrict__ dirty)
 {
     extern __shared__ uint8_t s_layer[]; // [2][by][bx]
@@ -1308,7 +1308,7 @@ int launch_brick_distance(kfb_ctx *ctx)
             KFB_CUDA(ctx, cudaFuncSetAttribute(brick_distance_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)layer2));
             ctx->bdist_smem_set = 1;
         }
-        brick_distance_xy_kernel<<<ctx->bdim[2], 256, layer2, ctx->stream>>>(ctx->bricks, ctx->bdist_tmp2, ctx->bdim[0], ctx->bdim[1], ctx->bdirty);
+        brick_distance_xy_kernel<<<ctx->bdim[2], 1024, layer2, ctx->stream>>>(ctx->bricks, ctx->bdist_tmp2, ctx->bdim[0], ctx->bdim[1], ctx->bdirty);
         KFB_LAUNCH_CHECK(ctx);
     }
     else
