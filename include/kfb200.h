@@ -163,15 +163,18 @@ int kfb_model_pyramid(kfb_ctx *ctx);
  * hold the winning key, so that an integer SUM reduction of the maps over the slabs yields exactly the
  * single-GPU raycast. */
 int kfb_composite_mask(kfb_ctx *ctx, const float *min_key_dev);
-/* The same composite without a communication library, over NVLink peer memory (one process per GPU on one
- * NVLink box): every slab context exports CUDA IPC handles of its key buffer, its two model-map buffers and a
- * flag word (kfb_ipc_export, `which` = 0..3, 64 bytes each); the launcher gathers them over any channel and
- * hands every context the full table (kfb_shard_attach: world x 4 handles, rank-major).  After that,
- * kfb_shard_composite, called by every rank after kfb_raycast, publishes "my slab of this frame is done" in the
- * rank's flag and, on rank 0, runs ONE kernel that waits for all flags, reads the peers' keys through NVLink,
- * selects the first terminal event per pixel and pulls the winner's vertex and normal into rank 0's model maps
- * (bit-identical to the single-GPU raycast).  Peers may overwrite their buffers only after rank 0 has consumed
- * them; in the frame loop that is implied by waiting for the next pose from rank 0. */
+/* The same composite without a communication library, over NVLink peer memory (one process per GPU on one NVLink
+ * box): every slab context exports CUDA IPC handles of the buffers its peers may write into -- staging for event
+ * keys, staging for vertex + normal maps (one slot per rank) and a set of "slab done" counters (kfb_ipc_export,
+ * `which` = 0..3, 64 bytes each; 3 repeats 2); the launcher gathers them over any channel and hands every context the
+ * full table (kfb_shard_attach: world x 4 handles, rank-major).  From then on the raycast of an attached rank other
+ * than 0 PUSHES its keys and maps into its slot of rank 0's staging (posted NVLink stores from the kernel's epilogue),
+ * and kfb_shard_composite, called by every rank after kfb_raycast, raises the rank's counter in rank 0's memory and,
+ * on rank 0, runs ONE kernel that waits for all counters, selects the first terminal event per pixel from local
+ * memory, writes the winner's vertex and normal into rank 0's model maps (bit-identical to the single-GPU raycast)
+ * and derives the coarser pyramid levels from the same tiles.  A peer that never signals within 2 s is reported
+ * (KFB_ERR_TIMEOUT from the next blocking call) instead of compositing stale data.  Slot r of the staging is written
+ * by rank r only, once per frame, after rank 0 consumed the previous frame's (implied by waiting for the next pose). */
 #define KFB_IPC_HANDLE_BYTES 64
 int kfb_ipc_export(kfb_ctx *ctx, int which, void *handle64);
 int kfb_shard_attach(kfb_ctx *ctx, int rank, int world, const void *handles);

@@ -97,7 +97,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->profiling = 0;
     ctx->icp_seq = 0;
     ctx->pyramid_fresh = 0;
-    ctx->shard_rank = 0; ctx->shard_world = 0; ctx->shard_flag = nullptr; ctx->shard_seq = 0;
+    ctx->shard_rank = 0; ctx->shard_world = 0; ctx->shard_flag = nullptr; ctx->shard_seq = 0; ctx->stage_keys = nullptr; ctx->stage_maps = nullptr;
     memset(ctx->peer_keys, 0, sizeof(ctx->peer_keys)); memset(ctx->peer_maps, 0, sizeof(ctx->peer_maps)); memset(ctx->peer_flag, 0, sizeof(ctx->peer_flag));
     ctx->vol = nullptr; ctx->cloud = nullptr; ctx->cloud_cap = 0;
     ctx->tab_thrz = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->zsparse = nullptr; ctx->bricks = nullptr;
@@ -265,6 +265,8 @@ void kfb_destroy(kfb_ctx *ctx)
     if (ctx->hit_t) cudaFree(ctx->hit_t);
     shard_close_peers(ctx);
     if (ctx->shard_flag) cudaFree(ctx->shard_flag);
+    if (ctx->stage_keys) cudaFree(ctx->stage_keys);
+    if (ctx->stage_maps) cudaFree(ctx->stage_maps);
     if (ctx->icp_partials) cudaFree(ctx->icp_partials);
     if (ctx->icp_ticket) cudaFree(ctx->icp_ticket);
     if (ctx->icp_host) cudaFreeHost((void *)ctx->icp_host);
@@ -437,13 +439,26 @@ int kfb_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9])
 
 int kfb_model_pyramid(kfb_ctx *ctx) { return launch_model_pyramid(ctx); }
 
+// Buffers a slab context lets its peers write into (push composite): 0 = event keys [16][P] float,
+// 1 = vertex + normal maps [16][2 P] float4 (slot r is written by rank r's raycast), 2 and 3 = "slab done" counters
+// [16] (slot r written by rank r).  Only rank 0's copies are ever written, but every rank allocates and exports the
+// same set so that the handle table is symmetric.  Allocated on first export.
+#define KFB_SHARD_MAX 16
+static int shard_alloc_stage(kfb_ctx *ctx)
+{
+    if (ctx->stage_keys) return KFB_OK;
+    const size_t P = (size_t)ctx->intr.width * ctx->intr.height;
+    KFB_CUDA(ctx, cudaMalloc(&ctx->stage_keys, KFB_SHARD_MAX * P * sizeof(float)));
+    KFB_CUDA(ctx, cudaMalloc(&ctx->stage_maps, KFB_SHARD_MAX * 2 * P * sizeof(float4)));
+    return KFB_OK;
+}
 static void *shard_export_ptr(kfb_ctx *ctx, int which)
 {
     switch (which)
     {
-    case 0: return ctx->hit_t;
-    case 1: return ctx->L[0].v[0];
-    case 2: return ctx->L[0].v[1];
+    case 0: return ctx->stage_keys;
+    case 1: return ctx->stage_maps;
+    case 2: return ctx->shard_flag;
     case 3: return ctx->shard_flag;
     default: return nullptr;
     }
@@ -451,6 +466,7 @@ static void *shard_export_ptr(kfb_ctx *ctx, int which)
 int kfb_ipc_export(kfb_ctx *ctx, int which, void *handle64)
 {
     static_assert(sizeof(cudaIpcMemHandle_t) == KFB_IPC_HANDLE_BYTES, "IPC handle size");
+    if (const int rcs = shard_alloc_stage(ctx)) return rcs;
     void *p = shard_export_ptr(ctx, which);
     if (!p || !handle64) return KFB_ERR_INVALID;
     cudaIpcMemHandle_t h;
@@ -462,18 +478,19 @@ int kfb_shard_attach(kfb_ctx *ctx, int rank, int world, const void *handles)
 {
     if (world < 2 || world > 16 || rank < 0 || rank >= world || !handles) return KFB_ERR_INVALID;
     if (ctx->shard_world) { ctx->err = "already attached"; return KFB_ERR_INVALID; }
+    if (const int rcs = shard_alloc_stage(ctx)) return rcs;
     const unsigned char *hb = (const unsigned char *)handles;
     for (int r = 0; r < world; ++r)
     {
         void *ptr[4];
-        for (int w = 0; w < 4; ++w)
+        for (int w = 0; w < 3; ++w) // (the fourth handle repeats the third)
         {
             if (r == rank) { ptr[w] = shard_export_ptr(ctx, w); continue; }
             cudaIpcMemHandle_t h;
             memcpy(&h, hb + ((size_t)r * 4 + w) * KFB_IPC_HANDLE_BYTES, sizeof(h));
             KFB_CUDA(ctx, cudaIpcOpenMemHandle(&ptr[w], h, cudaIpcMemLazyEnablePeerAccess));
         }
-        ctx->peer_keys[r] = ptr[0]; ctx->peer_maps[0][r] = ptr[1]; ctx->peer_maps[1][r] = ptr[2]; ctx->peer_flag[r] = ptr[3];
+        ctx->peer_keys[r] = ptr[0]; ctx->peer_maps[0][r] = ptr[1]; ctx->peer_maps[1][r] = nullptr; ctx->peer_flag[r] = ptr[2];
     }
     ctx->shard_rank = rank; ctx->shard_world = world; ctx->shard_seq = 0;
     return KFB_OK;

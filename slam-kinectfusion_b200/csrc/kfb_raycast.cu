@@ -453,7 +453,9 @@ struct ShardArgs
 };
 __global__ void shard_signal_kernel(unsigned long long *flag, unsigned long long seq)
 {
-    __threadfence_system(); // the raycast kernel before this launch has completed: publish its results to the peers
+    // the raycast kernel before this launch has completed and pushed its results into rank 0's memory; the fence
+    // orders them before the counter (rank 0's slot for this rank, a peer store as well)
+    __threadfence_system();
     *(volatile unsigned long long *)flag = seq;
 }
 // One pixel per thread, a warp = an 8x4 pixel tile (as in the raycast): all peers' keys of a pixel are requested
@@ -463,7 +465,7 @@ __global__ void shard_signal_kernel(unsigned long long *flag, unsigned long long
 __global__ void __launch_bounds__(256) shard_composite_kernel(const ShardArgs a)
 {
     // wait until every slab of this frame has been raycast (flags live in the peers' memory, read over NVLink)
-    if (threadIdx.x < a.world)
+    if (threadIdx.x < a.world && threadIdx.x != a.self)
     {
         unsigned long long t0;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
@@ -524,16 +526,21 @@ int launch_shard_composite(kfb_ctx *ctx)
     const Intr &k = ctx->L[0].k;
     if (const int rce = check_device_error(ctx)) return rce;
     const unsigned long long seq = ++ctx->shard_seq;
-    shard_signal_kernel<<<1, 1, 0, ctx->stream>>>(ctx->shard_flag, seq);
-    KFB_LAUNCH_CHECK(ctx);
-    if (ctx->shard_rank != 0) return KFB_OK;
+    const size_t P = (size_t)k.w * k.h;
+    if (ctx->shard_rank != 0)
+    {
+        shard_signal_kernel<<<1, 1, 0, ctx->stream>>>((unsigned long long *)ctx->peer_flag[0] + ctx->shard_rank, seq);
+        KFB_LAUNCH_CHECK(ctx);
+        return KFB_OK;
+    }
     ShardArgs a;
     memset(&a, 0, sizeof(a));
     for (int r = 0; r < ctx->shard_world; ++r)
     {
-        a.keys[r] = (const float *)ctx->peer_keys[r];
-        a.maps[r] = (const float4 *)ctx->peer_maps[ctx->prev][r];
-        a.flag[r] = (const volatile unsigned long long *)ctx->peer_flag[r];
+        // rank 0's own slab sits in its raycast outputs, the peers' slabs in the slots they pushed into
+        a.keys[r] = r == 0 ? ctx->hit_t : ctx->stage_keys + (size_t)r * P;
+        a.maps[r] = r == 0 ? ctx->L[0].v[ctx->prev] : ctx->stage_maps + (size_t)r * 2 * P;
+        a.flag[r] = (const volatile unsigned long long *)(ctx->shard_flag + r);
     }
     a.out = ctx->L[0].v[ctx->prev];
     a.world = ctx->shard_world; a.self = ctx->shard_rank; a.npix = k.w * k.h; a.seq = seq;
@@ -577,6 +584,15 @@ int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9]
     a.vmap = ctx->L[0].v[ctx->prev];
     a.nmap = ctx->L[0].n[ctx->prev];
     a.key = ctx->hit_t;
+    if (ctx->shard_world > 0 && ctx->shard_rank != 0)
+    {
+        // attached slab rank: the kernel writes its keys and maps straight into its slot of rank 0's staging buffers
+        // (posted NVLink stores from the epilogue; rank 0 then composites from its own memory)
+        const size_t P = (size_t)a.k.w * a.k.h;
+        a.key = (float *)ctx->peer_keys[0] + (size_t)ctx->shard_rank * P;
+        a.vmap = (float4 *)ctx->peer_maps[0][0] + (size_t)ctx->shard_rank * 2 * P;
+        a.nmap = a.vmap + P;
+    }
     a.ts_sign_compat = ctx->p.compat_raycast_ts_sign;
     a.bdist = ctx->bdist;
     a.bx = ctx->bdim[0]; a.by = ctx->bdim[1]; a.bz = ctx->bdim[2]; a.bz0 = ctx->bz0;
