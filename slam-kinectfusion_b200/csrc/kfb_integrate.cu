@@ -699,7 +699,8 @@ __global__ void __launch_bounds__(128, 8) integrate_stream_kernel(const Integrat
     const int lane = threadIdx.x & 31;
     const unsigned int n_items = __ldg(a.plan_counts + 0);
     unsigned int n_upd = 0, n_ld = 0, n_st = 0;
-    for (unsigned int item = blockIdx.x * 4 + (threadIdx.x >> 5); item < n_items; item += gridDim.x * 4)
+    const unsigned int wpb = blockDim.x >> 5; // one item per warp
+    for (unsigned int item = blockIdx.x * wpb + (threadIdx.x >> 5); item < n_items; item += gridDim.x * wpb)
     {
         const uint2 it = __ldg(a.items_stream + item);
         const PatchLane pl = patch_lane(a, (int)it.x, lane);
@@ -865,7 +866,8 @@ __global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const Inte
         g.rtrunc = rcp_fdividef(a.trunc);
     }
     unsigned int n_upd = 0, n_ld = 0, n_st = 0;
-    for (unsigned int item = blockIdx.x * 4 + (threadIdx.x >> 5); item < n_items; item += gridDim.x * 4)
+    const unsigned int wpb = blockDim.x >> 5; // one item per warp
+    for (unsigned int item = blockIdx.x * wpb + (threadIdx.x >> 5); item < n_items; item += gridDim.x * wpb)
     {
         const uint2 it = __ldg(a.items_general + item);
         const PatchLane pl = patch_lane(a, (int)it.x, lane);
@@ -1078,6 +1080,8 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
     // left, all of them once the stream items are done.
     const bool overlap = !getenv("KFB_INTEGRATE_SERIAL");
     int gs = ctx->sm_count * 8, gg = ctx->sm_count * KFB_GEN_MINB;
+    int gwarps = 4; // warps (items) per block of the general kernel (KFB_GEN_WARPS: tuning)
+    if (const char *e = getenv("KFB_GEN_WARPS")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) gwarps = v; }
     if (!getenv("KFB_INTEGRATE_PERSISTENT"))
     {
         // about one warp per item, sized from the previous frame's counts (both kernels stride, so any grid is
@@ -1085,8 +1089,9 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
         const size_t hs = ctx->plan_hint_host ? (size_t)ctx->plan_hint_host[0] : 0, hg = ctx->plan_hint_host ? (size_t)ctx->plan_hint_host[1] : 0;
         const size_t cap = std::max<size_t>((ncell + 3) / 4, 1);
         gs = (int)std::min<size_t>(std::max<size_t>((hs + hs / 4 + 3) / 4, (size_t)gs), cap);
-        gg = (int)std::min<size_t>(std::max<size_t>((hg + hg / 4 + 3) / 4, (size_t)gg), cap);
+        gg = (int)std::min<size_t>(std::max<size_t>((hg + hg / 4 + gwarps - 1) / gwarps, (size_t)gg), cap * (4 / gwarps));
     }
+    const int gthreads = 32 * gwarps;
     cudaStream_t gstr = ctx->stream;
     if (overlap)
     {
@@ -1099,8 +1104,8 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
     KFB_LAUNCH_CHECK(ctx);
     if (n_updated)
     {
-        if (smem) integrate_general_kernel<true, true, KFB_GEN_MINB><<<gg, 128, 0, gstr>>>(a);
-        else integrate_general_kernel<true, false, KFB_GEN_MINB><<<gg, 128, 0, gstr>>>(a);
+        if (smem) integrate_general_kernel<true, true, KFB_GEN_MINB><<<gg, gthreads, 0, gstr>>>(a);
+        else integrate_general_kernel<true, false, KFB_GEN_MINB><<<gg, gthreads, 0, gstr>>>(a);
         KFB_LAUNCH_CHECK(ctx);
         if (smem) integrate_stream_kernel<true, true><<<gs, 128, 0, ctx->stream>>>(a);
         else integrate_stream_kernel<true, false><<<gs, 128, 0, ctx->stream>>>(a);
@@ -1109,10 +1114,10 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
     else
     {
         const int minb = getenv("KFB_GEN_MINB") ? atoi(getenv("KFB_GEN_MINB")) : KFB_GEN_MINB; // register budget variant (tuning)
-        if (!smem) integrate_general_kernel<false, false, KFB_GEN_MINB><<<gg, 128, 0, gstr>>>(a);
-        else if (minb == 5) integrate_general_kernel<false, true, 5><<<gg, 128, 0, gstr>>>(a);
-        else if (minb == 6) integrate_general_kernel<false, true, 6><<<gg, 128, 0, gstr>>>(a);
-        else integrate_general_kernel<false, true, 8><<<gg, 128, 0, gstr>>>(a);
+        if (!smem) integrate_general_kernel<false, false, KFB_GEN_MINB><<<gg, gthreads, 0, gstr>>>(a);
+        else if (minb == 5) integrate_general_kernel<false, true, 5><<<gg, gthreads, 0, gstr>>>(a);
+        else if (minb == 6) integrate_general_kernel<false, true, 6><<<gg, gthreads, 0, gstr>>>(a);
+        else integrate_general_kernel<false, true, 8><<<gg, gthreads, 0, gstr>>>(a);
         KFB_LAUNCH_CHECK(ctx);
         if (smem) integrate_stream_kernel<false, true><<<gs, 128, 0, ctx->stream>>>(a);
         else integrate_stream_kernel<false, false><<<gs, 128, 0, ctx->stream>>>(a);

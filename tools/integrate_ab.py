@@ -16,14 +16,14 @@ from slam_kinectfusion_b200 import synth  # noqa: E402
 
 VARIANTS = {
     "serial (one stream)": {"KFB_INTEGRATE_SERIAL": "1"},
-    "persistent grids": {"KFB_INTEGRATE_PERSISTENT": "1"},
     "chunks of 8 planes": {"KFB_PLAN_ZCHUNK": "8"},
-    "chunks of 24 planes": {"KFB_PLAN_ZCHUNK": "24"},
-    "chunks of 32 planes": {"KFB_PLAN_ZCHUNK": "32"},
-    "general kernel 80 regs": {"KFB_GEN_MINB": "6"},
+    "general: 2 warps/block": {"KFB_GEN_WARPS": "2"},
+    "general: 1 warp/block": {"KFB_GEN_WARPS": "1"},
     "default": {},
+    "general: 2 warps/block (again)": {"KFB_GEN_WARPS": "2"},
+    "default (again)": {},
 }
-SWITCHES = ("KFB_INTEGRATE_SERIAL", "KFB_INTEGRATE_PERSISTENT", "KFB_GEN_MINB", "KFB_PLAN_ZCHUNK")
+SWITCHES = ("KFB_INTEGRATE_SERIAL", "KFB_INTEGRATE_PERSISTENT", "KFB_GEN_MINB", "KFB_PLAN_ZCHUNK", "KFB_GEN_WARPS")
 
 
 def main():
