@@ -1332,9 +1332,12 @@ int launch_brick_distance(kfb_ctx *ctx)
 // ---- work histogram over planes (slab balancing for sharded volumes) -----------------------------------------
 // Work per plane from the sweep's own plan: the plan kernel runs for the WHOLE volume (it needs the depth tables and
 // the pose, not the voxels), and every item adds its 32 voxel quads per plane to the planes it covers -- once for a
-// stream item, KFB_HIST_GENERAL_WEIGHT times for a general item (measured cost ratio per quad at 512^3).  (A count
+// stream item, KFB_HIST_GENERAL_WEIGHT times for a general item: about 4 for the sweep itself (measured cost ratio
+// per quad at 512^3) plus the slab's share of the raycast, whose fetches and normals happen on the same planes
+// (KFB_HIST_GENERAL_WEIGHT=<n> in the environment overrides; 8 GPUs / 1024^3 with weight 4: rank 0 at 0.08 + 0.03 ms,
+// rank 7 at 0.14 + 0.21 ms).  (A count
 // of the frustum alone left the busiest of two 2048^3 slabs 30 % behind the other, profiles/README.md.)
-#define KFB_HIST_GENERAL_WEIGHT 4
+#define KFB_HIST_GENERAL_WEIGHT 10
 int launch_plane_histogram(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *host_hist)
 {
     const int Z = ctx->p.volu_dims[2];
@@ -1377,10 +1380,12 @@ int launch_plane_histogram(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *ho
     }
     cudaFree(pb);
     KFB_CUDA(ctx, e);
+    int gweight = KFB_HIST_GENERAL_WEIGHT;
+    if (const char *e = getenv("KFB_HIST_GENERAL_WEIGHT")) { const int v = atoi(e); if (v >= 1 && v <= 1000) gweight = v; }
     std::vector<long long> diff((size_t)Z + 2, 0);
     for (int t = 0; t < 2; ++t)
     {
-        const long long wgt = 32 * (t ? KFB_HIST_GENERAL_WEIGHT : 1);
+        const long long wgt = 32 * (t ? gweight : 1);
         for (const uint2 &it : items[t])
         {
             const int z0 = (int)(it.y & 0xffffu), z1 = (int)(it.y >> 16);
