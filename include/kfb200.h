@@ -144,7 +144,8 @@ int kfb_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_updated);
 /* Slab balancing aid for sharded volumes (no reference counterpart): host_hist[z], z in [0, dims[2]), = work the
  * sweep of kfb_integrate would do on plane z of the WHOLE volume for the current frame's depth and this pose, in
  * voxel quads: every plane a work item covers counts its 32 quads once if the item only streams free space and ten
- * times if it needs the per-voxel predicate (the sweep's measured cost ratio plus the raycast work on the same planes).  It comes from the sweep's own plan, which
+ * times if it needs the per-voxel predicate (the sweep's measured cost ratio), plus the raycast's share: 190 quads'
+ * worth per pixel with a valid depth, spread over the 16 planes in front of the pixel's surface point.  It comes from the sweep's own plan, which
  * depends on the depth image and the pose only -- not on the volume's content or on the planes this context stores
  * -- so every rank computes the same histogram without communication. */
 int kfb_integrate_plane_histogram(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *host_hist);

@@ -1338,6 +1338,27 @@ int launch_brick_distance(kfb_ctx *ctx)
 // rank 7 at 0.14 + 0.21 ms).  (A count
 // of the frustum alone left the busiest of two 2048^3 slabs 30 % behind the other, profiles/README.md.)
 #define KFB_HIST_GENERAL_WEIGHT 10
+#define KFB_HIST_RAY_UNITS 190 // raycast cost of one pixel in the unit of the histogram (a streamed quad): measured 0.144 ms per
+                               // 307 200 rays against 0.103 ms per 6.8 M streamed + 10 x 3.5 M per-voxel quads at 512^3
+#define KFB_HIST_RAY_PLANES 16 // planes in front of a pixel's surface over which that cost is spread (the near-surface march)
+// raycast share of the work histogram: every pixel with a valid depth puts its cost on the planes just in front of the
+// plane its surface point falls on (volume coordinates through cam2vol = the inverse of the rigid vol2cam)
+__global__ void ray_histogram_kernel(const float *__restrict__ depth, int w, int h, float fx, float fy, float cx, float cy, Pose v2c, float vsz, int Z,
+                                     int units, int *__restrict__ diff)
+{
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y * blockDim.y + threadIdx.y;
+    if (u >= w || v >= h) return;
+    const float d = depth[v * w + u];
+    if (!(d > 0.f)) return;
+    const float px = d * ((float)u - cx) / fx - v2c.t[0], py = d * ((float)v - cy) / fy - v2c.t[1], pz = d - v2c.t[2];
+    const float zv = v2c.R.m[2] * px + v2c.R.m[5] * py + v2c.R.m[8] * pz; // third row of R^T
+    const int zh = (int)floorf(zv / vsz);
+    const int z1 = min(max(zh, 1), Z - 1), z0 = max(z1 - (KFB_HIST_RAY_PLANES - 1), 1);
+    const int per = units / (z1 - z0 + 1);
+    atomicAdd(diff + z0, per);
+    atomicAdd(diff + z1 + 1, -per);
+}
+
 int launch_plane_histogram(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *host_hist)
 {
     const int Z = ctx->p.volu_dims[2];
@@ -1372,6 +1393,26 @@ int launch_plane_histogram(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *ho
     unsigned int counts[2] = {0, 0};
     if (e == cudaSuccess) e = cudaMemcpyAsync(counts, a.plan_counts, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    // raycast share
+    std::vector<int> rdiff((size_t)Z + 2, 0);
+    if (e == cudaSuccess && !getenv("KFB_HIST_NORAY"))
+    {
+        int *dd = reinterpret_cast<int *>(pb + o_mask); // the plan has run: its patch masks are not needed any more
+        if ((size_t)(Z + 2) * sizeof(int) <= o_slot - o_mask)
+        {
+            const Intr &k = ctx->L[0].k;
+            e = cudaMemsetAsync(dd, 0, (size_t)(Z + 2) * sizeof(int), ctx->stream);
+            if (e == cudaSuccess)
+            {
+                dim3 rb(32, 8), rg((k.w + 31) / 32, (k.h + 7) / 8);
+                ray_histogram_kernel<<<rg, rb, 0, ctx->stream>>>(ctx->L[0].depth, k.w, k.h, k.fx, k.fy, k.cx, k.cy, a.pose, a.vsz, Z, KFB_HIST_RAY_UNITS, dd);
+                ctx->launches++;
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaMemcpyAsync(rdiff.data(), dd, (size_t)(Z + 2) * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        }
+    }
     std::vector<uint2> items[2];
     for (int t = 0; t < 2 && e == cudaSuccess; ++t)
     {
@@ -1396,7 +1437,7 @@ int launch_plane_histogram(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *ho
     long long run = 0;
     for (int z = 0; z < Z; ++z)
     {
-        run += diff[z];
+        run += diff[z] + (long long)rdiff[z];
         host_hist[z] = (uint32_t)std::min<long long>(std::max<long long>(run, 0), 0xffffffffll);
     }
     return KFB_OK;
