@@ -168,16 +168,20 @@ def dev_tensor(ptr, shape, typestr, device):
 class ShardedKinectFusion:
     """kf::kinectfusion on one z-slab of the volume; `dist` is an initialised torch.distributed (NCCL)."""
 
-    def __init__(self, K, hp, dist, rank, world, local, first_depth=None):
-        """first_depth: the first frame (mm).  When given, slab heights are balanced by the integration work it
-        implies (balanced_bounds); otherwise the volume is cut into equal slabs."""
+    def __init__(self, K, hp, dist, rank, world, local, first_depth=None, bounds=None):
+        """first_depth: the first frame (mm).  When given, slab heights are balanced by the work it implies
+        (balanced_bounds over kfb_integrate_plane_histogram); `bounds` (world + 1 plane numbers) overrides that
+        (calibrated(): bounds corrected by measured per-rank times); otherwise the volume is cut into equal slabs."""
         import torch
         from . import host
         self.dist, self.rank, self.world = dist, rank, world
         self.device = torch.device("cuda", local)
         Z = hp.volu_dims[2]
         self.bounds = None
-        if first_depth is not None and os.environ.get("KFB_SLABS_EQUAL") is None:
+        if bounds is not None:
+            self.bounds = [int(b) for b in bounds]
+            hp.slab_z_begin, hp.slab_z_end = self.bounds[rank], self.bounds[rank + 1]
+        elif first_depth is not None and os.environ.get("KFB_SLABS_EQUAL") is None:
             self.bounds = balanced_bounds(measure_plane_histogram(K, hp, first_depth, local), world)
             hp.slab_z_begin, hp.slab_z_end = self.bounds[rank], self.bounds[rank + 1]
         else:
@@ -282,7 +286,8 @@ def _measure_config(args, dist, rank, world, local, dims, K, frames, host_pin, d
     w, h = K.width, K.height
     hp = host.default_host_params(dims)
     os.environ["KFB_MAILBOX_TAG"] = tag
-    skf = ShardedKinectFusion(K, hp, dist, rank, world, local, first_depth=frames[0][1])
+    # slabs cut by the sweep's plan, then corrected by two measured rounds over the first frames (outside any timed region)
+    skf = calibrated(K, lambda: host.default_host_params(dims), dist, rank, world, local, [f[1] for f in frames[:min(6, n_frames)]])
     ctx = skf.ctx
     dev = torch.device("cuda", local)
 
@@ -369,6 +374,7 @@ def _measure_config(args, dist, rank, world, local, dims, K, frames, host_pin, d
     dist.all_gather(gathered, stat)
     bounds = skf.bounds if skf.bounds is not None else [slab_range(dims, world, r)[0] for r in range(world)] + [dims]
     p2p = skf.p2p
+    calibration = getattr(skf, "calibration", None)
     skf.close()
     skf.kf.close()
     del skf
@@ -398,7 +404,7 @@ def _measure_config(args, dist, rank, world, local, dims, K, frames, host_pin, d
     dist.barrier()
     return {
         "dims": dims, "ms_per_step": dev_ms / S, "e2e_ms_per_step": (e2e_ms / S) if e2e_ms is not None else None,
-        "launches": launches, "clocks": clocks, "poses": poses, "bounds": bounds, "p2p": p2p,
+        "launches": launches, "clocks": clocks, "poses": poses, "bounds": bounds, "p2p": p2p, "calibration": calibration,
         "U_owned": sum(float(g[0]) for g in gathered), "U_stored": sum(float(g[1]) for g in gathered),
         "stage_ms": {"integrate_kernel_slowest_rank": max(float(g[2]) for g in gathered),
                      "integrate_call_slowest_rank": max(float(g[3]) for g in gathered),
@@ -409,6 +415,62 @@ def _measure_config(args, dist, rank, world, local, dims, K, frames, host_pin, d
                      "pose_mailbox_host_us_rank0": mailbox_us},
         "single": single,
     }
+
+
+def rebalance(bounds, times, min_planes=8):
+    """New slab bounds from measured per-rank times: the cost density is taken as constant inside each old slab and
+    the total is cut into equal parts.  Deterministic (every rank computes the same from the gathered times)."""
+    b = [int(x) for x in bounds]
+    world = len(b) - 1
+    Z = b[-1]
+    dens = np.zeros(Z)
+    for r in range(world):
+        dens[b[r]:b[r + 1]] = max(float(times[r]), 1e-9) / max(b[r + 1] - b[r], 1)
+    cum = np.concatenate([[0.0], np.cumsum(dens)])
+    nb = [0]
+    for r in range(1, world):
+        z = int(np.searchsorted(cum, cum[-1] * r / world))
+        z = max(z, nb[-1] + min_planes)
+        z = min(z, Z - (world - r) * min_planes)
+        nb.append(z)
+    nb.append(Z)
+    return nb
+
+
+def calibrated(K, make_hp, dist, rank, world, local, frames_mm, rounds=2):
+    """A ShardedKinectFusion whose slab bounds were corrected by measurement: the plan-based cut (cheap, no
+    communication) balances the sweep but knows the raycast only by a model; here the first frames are run `rounds`
+    times, every rank reports integrate call + raycast of the last one (the library's profiling events), and the slabs
+    are re-cut (rebalance).  Volumes are rebuilt in between, so this belongs before the sequence starts; a running
+    system would have to move planes between ranks instead (not built).  make_hp() -> fresh HostParams."""
+    import torch
+    skf = ShardedKinectFusion(K, make_hp(), dist, rank, world, local, first_depth=frames_mm[0])
+    if os.environ.get("KFB_SLABS_NOCALIB") is not None or skf.bounds is None:
+        return skf
+    w, h = K.width, K.height
+    dev = torch.device("cuda", local)
+    gpu_frames = [torch.from_numpy(np.ascontiguousarray(f, np.float32)).to(dev) for f in frames_mm]
+    for _ in range(rounds):
+        skf.ctx.set_profiling(True)
+        for f in gpu_frames:
+            if skf.pipeline_ptr(f.data_ptr(), w, h) != 0:
+                raise RuntimeError("calibration run lost tracking")
+        skf.ctx.synchronize()
+        t = skf.ctx.event_elapsed_ms(56, 57) + skf.ctx.event_elapsed_ms(58, 59)
+        skf.ctx.set_profiling(False)
+        tt = torch.tensor([t], device=dev, dtype=torch.float64)
+        allt = [torch.zeros_like(tt) for _ in range(world)]
+        dist.all_gather(allt, tt)
+        times = [float(x[0]) for x in allt]
+        nb = rebalance(skf.bounds, times)
+        old = skf.bounds
+        skf.close()
+        skf.kf.close()
+        del skf
+        torch.cuda.synchronize(dev)
+        skf = ShardedKinectFusion(K, make_hp(), dist, rank, world, local, bounds=nb)
+        skf.calibration = {"times_ms": times, "from": old, "to": nb}
+    return skf
 
 
 def run_bench(args, dist, rank, world, local, dims, K, frames, host_pin, dev_frames, METRIC, UNIT, measured_peak_hbm,
@@ -445,7 +507,7 @@ def run_bench(args, dist, rank, world, local, dims, K, frames, host_pin, dev_fra
                    "frames_timed": S, "updated_voxels_per_frame": main["U_owned"], "swept_voxels_per_frame": dims * dims * (dims - 1),
                    "collectives_per_frame": ("pose mailbox 52 B (shared memory); composite = one kernel over NVLink peer memory" if main["p2p"] else "pose mailbox 52 B (shared memory), all_reduce(min) 1.2 MB, reduce(sum) 9.8 MB")},
         "frame_device_ms": ms_per_frame,
-        "slab_bounds": main["bounds"],
+        "slab_bounds": main["bounds"], "slab_calibration": main["calibration"],
         "final_pose": [float(x) for x in main["poses"][-1]],
         "parity": parity,
         "stage_ms": main["stage_ms"],

@@ -164,3 +164,20 @@ def test_native_pose_mailbox_three_ranks(kfb):
     mb0.close()
     for r in (1, 2):
         assert np.array_equal(res[r], np.array(sent))
+
+
+def test_rebalance_from_measured_times(kfb):
+    """sharded.rebalance: bounds stay a partition, the slow rank's slab shrinks, equal times leave the cut alone."""
+    from slam_kinectfusion_b200 import sharded
+    b = [0, 311, 437, 555, 639, 714, 792, 872, 1024]
+    t = [0.18, 0.29, 0.33, 0.33, 0.34, 0.35, 0.36, 0.38]
+    nb = sharded.rebalance(b, t)
+    assert nb[0] == 0 and nb[-1] == 1024 and len(nb) == len(b)
+    assert all(nb[i + 1] - nb[i] >= 8 for i in range(8))
+    assert nb[1] > b[1] and (nb[8] - nb[7]) < (b[8] - b[7])          # the idle first rank takes planes, the busy last one sheds them
+    # predicted times under the piecewise-constant model are closer together than the measured ones
+    dens = np.concatenate([np.full(b[i + 1] - b[i], t[i] / (b[i + 1] - b[i])) for i in range(8)])
+    pred = [dens[nb[i]:nb[i + 1]].sum() for i in range(8)]
+    assert max(pred) - min(pred) < 0.25 * (max(t) - min(t))
+    same = sharded.rebalance([0, 100, 200, 300, 400], [1.0, 1.0, 1.0, 1.0])
+    assert same == [0, 100, 200, 300, 400]
