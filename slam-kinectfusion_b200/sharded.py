@@ -437,11 +437,13 @@ def rebalance(bounds, times, min_planes=8):
     return nb
 
 
-def calibrated(K, make_hp, dist, rank, world, local, frames_mm, rounds=2):
+def calibrated(K, make_hp, dist, rank, world, local, frames_mm, rounds=3):
     """A ShardedKinectFusion whose slab bounds were corrected by measurement: the plan-based cut (cheap, no
-    communication) balances the sweep but knows the raycast only by a model; here the first frames are run `rounds`
-    times, every rank reports integrate call + raycast of the last one (the library's profiling events), and the slabs
-    are re-cut (rebalance).  Volumes are rebuilt in between, so this belongs before the sequence starts; a running
+    communication) balances the sweep but knows the raycast only by a model; here the first frames are run, every rank
+    reports integrate call + raycast of the last one (the library's profiling events), and the slabs are re-cut half
+    way towards the cut the measurement suggests (rebalance assumes a constant cost density inside a slab, which
+    overshoots where the cost sits at one end of it).  After `rounds` corrections the best cut seen (smallest time of
+    the slowest rank) is kept.  Volumes are rebuilt in between, so this belongs before the sequence starts; a running
     system would have to move planes between ranks instead (not built).  make_hp() -> fresh HostParams."""
     import torch
     skf = ShardedKinectFusion(K, make_hp(), dist, rank, world, local, first_depth=frames_mm[0])
@@ -450,26 +452,42 @@ def calibrated(K, make_hp, dist, rank, world, local, frames_mm, rounds=2):
     w, h = K.width, K.height
     dev = torch.device("cuda", local)
     gpu_frames = [torch.from_numpy(np.ascontiguousarray(f, np.float32)).to(dev) for f in frames_mm]
-    for _ in range(rounds):
-        skf.ctx.set_profiling(True)
+
+    def measure(s):
+        s.ctx.set_profiling(True)
         for f in gpu_frames:
-            if skf.pipeline_ptr(f.data_ptr(), w, h) != 0:
+            if s.pipeline_ptr(f.data_ptr(), w, h) != 0:
                 raise RuntimeError("calibration run lost tracking")
-        skf.ctx.synchronize()
-        t = skf.ctx.event_elapsed_ms(56, 57) + skf.ctx.event_elapsed_ms(58, 59)
-        skf.ctx.set_profiling(False)
+        s.ctx.synchronize()
+        t = s.ctx.event_elapsed_ms(56, 57) + s.ctx.event_elapsed_ms(58, 59)
+        s.ctx.set_profiling(False)
         tt = torch.tensor([t], device=dev, dtype=torch.float64)
         allt = [torch.zeros_like(tt) for _ in range(world)]
         dist.all_gather(allt, tt)
-        times = [float(x[0]) for x in allt]
-        nb = rebalance(skf.bounds, times)
-        old = skf.bounds
-        skf.close()
-        skf.kf.close()
-        del skf
+        return [float(x[0]) for x in allt]
+
+    def rebuild(s, nb):
+        s.close()
+        s.kf.close()
+        del s
         torch.cuda.synchronize(dev)
-        skf = ShardedKinectFusion(K, make_hp(), dist, rank, world, local, bounds=nb)
-        skf.calibration = {"times_ms": times, "from": old, "to": nb}
+        return ShardedKinectFusion(K, make_hp(), dist, rank, world, local, bounds=nb)
+
+    seen = []
+    for r in range(rounds + 1):
+        times = measure(skf)
+        seen.append({"bounds": list(skf.bounds), "times_ms": times})
+        if r == rounds:
+            break
+        target = rebalance(skf.bounds, times)
+        nb = [int(round(0.5 * (a + b))) for a, b in zip(skf.bounds, target)]
+        nb[0], nb[-1] = 0, skf.bounds[-1]
+        if nb == list(skf.bounds):
+            break
+        skf = rebuild(skf, nb)
+    best = min(seen, key=lambda c: max(c["times_ms"]))
+    skf = rebuild(skf, best["bounds"])       # fresh volume for the sequence, at the best cut seen
+    skf.calibration = {"rounds": seen, "chosen": best["bounds"]}
     return skf
 
 
