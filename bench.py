@@ -271,7 +271,7 @@ def run_ours(args):
                 t0 = time.perf_counter()
             rc = kf.pipeline_ptr(ptr, w, h)
             if rc != 0:
-                raise SystemExit(f"tracking failure at frame {i}")
+                raise SystemExit(f"pipeline rc={rc} at frame {i} ({'tracking failure' if rc == 1 else kf.last_error()})")
             _ = kf.pose()                      # the frame's result on the host (ICP sums already crossed PCIe)
         ctx.event_record(1)
         ctx.synchronize()
@@ -298,8 +298,9 @@ def run_ours(args):
     kf.reset()
     k_ms, call_ms, rc_ms, icp_ms = [], [], [], []
     for i, ptr in enumerate(dptr):
-        if kf.pipeline_ptr(ptr, w, h) != 0:
-            raise SystemExit(f"tracking failure at frame {i}")
+        rc = kf.pipeline_ptr(ptr, w, h)
+        if rc != 0:
+            raise SystemExit(f"pipeline rc={rc} at frame {i} of the profiled pass ({'tracking failure' if rc == 1 else kf.last_error()})")
         if i > W and i % 4 == 0:
             ctx.synchronize()
             k_ms.append(ctx.event_elapsed_ms(60, 61))

@@ -103,6 +103,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->tab_thrz = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->zsparse = nullptr; ctx->bricks = nullptr;
     ctx->tab4 = nullptr; ctx->plan_buf = nullptr; ctx->plan_bytes = 0; ctx->plan_hint_host = nullptr; ctx->gen_attr_set = 0;
     ctx->bdist = ctx->bdist_tmp = ctx->bdist_tmp2 = nullptr; ctx->bdirty = nullptr; ctx->bdist_smem_set = 0;
+    ctx->ray_cost = nullptr; ctx->ray_order = nullptr; ctx->ray_order_valid = 0; ctx->ev_ray_done = nullptr; ctx->ev_ray_order = nullptr;
     ctx->hit_t = nullptr; ctx->icp_partials = nullptr; ctx->icp_ticket = nullptr; ctx->counters = nullptr;
     ctx->counters_host = nullptr; ctx->pinned_depth = nullptr; ctx->depth_u16 = nullptr; ctx->render_dev = nullptr; ctx->render_host = nullptr;
     ctx->stream = nullptr; ctx->own_stream = 1;
@@ -263,6 +264,9 @@ void kfb_destroy(kfb_ctx *ctx)
     if (ctx->plan_buf) cudaFree(ctx->plan_buf);
     if (ctx->plan_hint_host) cudaFreeHost(ctx->plan_hint_host);
     if (ctx->hit_t) cudaFree(ctx->hit_t);
+    if (ctx->ray_cost) cudaFree(ctx->ray_cost);
+    if (ctx->ev_ray_done) cudaEventDestroy(ctx->ev_ray_done);
+    if (ctx->ev_ray_order) cudaEventDestroy(ctx->ev_ray_order);
     shard_close_peers(ctx);
     if (ctx->shard_flag) cudaFree(ctx->shard_flag);
     if (ctx->stage_keys) cudaFree(ctx->stage_keys);

@@ -46,6 +46,11 @@ struct RaycastArgs
     int bx, by, bz, bz0;
     int fuse_pyramid;     // write levels 1 and 2 of the model maps from the warp tile (single-GPU, aligned image sizes)
     float4 *pyr_v[2], *pyr_n[2];
+    // tile scheduling: block b marches tile order[b] (most expensive tiles of the previous frame first) and leaves
+    // its own cost (SM cycles) for the next frame's order
+    const unsigned int *order;
+    unsigned int *cost;
+    int tiles_x;
 };
 
 #define KFB_RC_MAGIC_F 12582912.0f
@@ -214,8 +219,10 @@ __global__ void __launch_bounds__(32 * KFB_RC_WARPS, KFB_RC_MINB) raycast_kernel
     constexpr bool SLAB = MODE == RC_SLAB;
     const unsigned FULL = 0xffffffffu;
     // block = warp = 8x4 pixel tile (rays of very different length share nothing: fine-grained scheduling)
-    const int x = blockIdx.x * 8 + threadIdx.x;
-    const int y = blockIdx.y * (4 * KFB_RC_WARPS) + threadIdx.y;
+    const long long t_begin = clock64();
+    const int tile = a.order ? (int)__ldg(a.order + blockIdx.x) : (int)blockIdx.x;
+    const int x = (tile % a.tiles_x) * 8 + threadIdx.x;
+    const int y = (tile / a.tiles_x) * 4 + threadIdx.y;
     const bool inside = x < a.k.w && y < a.k.h;
     const int pix = y * a.k.w + x;
     float4 vout = make_float4(0.f, 0.f, 0.f, 0.f), nout = vout;
@@ -412,6 +419,33 @@ __global__ void __launch_bounds__(32 * KFB_RC_WARPS, KFB_RC_MINB) raycast_kernel
     }
     // ---- model pyramid as an epilogue of the warp tile (see pyramid_from_tile)
     if (a.fuse_pyramid) pyramid_from_tile(vout, nout, x, y, threadIdx.x, threadIdx.y & 3, inside, a.k.w, a.pyr_v, a.pyr_n);
+    if (a.cost && threadIdx.x == 0 && threadIdx.y == 0) a.cost[tile] = (unsigned int)min((long long)0xffffffffll, clock64() - t_begin);
+}
+
+// Tile order for the next raycast: a counting sort of the tiles by the cost they just reported, most expensive
+// first (one block).  Rays differ in length by two orders of magnitude (a ray that leaves the volume at once against
+// one that creeps along a wall), the block scheduler hands tiles out in index order, and with image rows of floor
+// at the bottom the expensive tiles used to come last: the kernel ended in a long tail of a few resident warps
+// (achieved occupancy 32 % of a possible 50 %).  The camera moves slowly, so last frame's cost predicts this frame's.
+#define KFB_RC_COST_SHIFT 11 // bucket = cycles / 2048, 256 buckets
+__global__ void __launch_bounds__(1024) raycast_order_kernel(const unsigned int *__restrict__ cost, unsigned int *__restrict__ order, int ntiles)
+{
+    __shared__ unsigned int hist[256], base[256];
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < ntiles; i += blockDim.x) atomicAdd(&hist[255 - min(255u, cost[i] >> KFB_RC_COST_SHIFT)], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        unsigned int run = 0;
+        for (int b = 0; b < 256; ++b) { base[b] = run; run += hist[b]; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ntiles; i += blockDim.x)
+    {
+        const unsigned int b = 255 - min(255u, cost[i] >> KFB_RC_COST_SHIFT);
+        order[atomicAdd(&base[b], 1u)] = (unsigned int)i;
+    }
 }
 
 // cross-slab composite, step 2 (see include/kfb200.h): keep the payload only where this slab holds the
@@ -604,13 +638,37 @@ int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9]
         a.pyr_n[l - 1] = a.fuse_pyramid ? ctx->L[l].n[ctx->prev] : nullptr;
     }
     ctx->pyramid_fresh = a.fuse_pyramid;
-    dim3 block(8, 4 * KFB_RC_WARPS), grid((a.k.w + 7) / 8, (a.k.h + 4 * KFB_RC_WARPS - 1) / (4 * KFB_RC_WARPS));
+    a.tiles_x = (a.k.w + 7) / 8;
+    const int ntiles = a.tiles_x * ((a.k.h + 3) / 4);
+    const bool sorted = !getenv("KFB_RAYCAST_NOSORT");
+    if (sorted && !ctx->ray_cost)
+    {
+        KFB_CUDA(ctx, cudaMalloc(&ctx->ray_cost, 2 * (size_t)ntiles * sizeof(unsigned int)));
+        ctx->ray_order = ctx->ray_cost + ntiles;
+        ctx->ray_order_valid = 0;
+        KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ray_done, cudaEventDisableTiming));
+        KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ray_order, cudaEventDisableTiming));
+    }
+    a.cost = sorted ? ctx->ray_cost : nullptr;
+    a.order = (sorted && ctx->ray_order_valid) ? ctx->ray_order : nullptr;
+    if (a.order) KFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_ray_order, 0)); // long done: it ran behind the previous raycast
+    dim3 block(8, 4), grid(ntiles);
     if (ctx->profiling) cudaEventRecord(ctx->events[58], ctx->stream);
     const bool whole = a.zs0 == 0 && a.zs1 == a.Z && a.zo0 == 0 && a.zo1 == a.Z && a.bz0 == 0 && !getenv("KFB_RAYCAST_SLABCODE");
     if (whole) raycast_kernel<RC_WHOLE><<<grid, block, 0, ctx->stream>>>(a);
     else raycast_kernel<RC_SLAB><<<grid, block, 0, ctx->stream>>>(a);
     KFB_LAUNCH_CHECK(ctx);
     if (ctx->profiling) cudaEventRecord(ctx->events[59], ctx->stream);
+    if (sorted)
+    {
+        // next frame's order, on the front-end stream: nothing on the frame's critical path waits for it
+        KFB_CUDA(ctx, cudaEventRecord(ctx->ev_ray_done, ctx->stream));
+        KFB_CUDA(ctx, cudaStreamWaitEvent(ctx->fstream, ctx->ev_ray_done, 0));
+        raycast_order_kernel<<<1, 1024, 0, ctx->fstream>>>(ctx->ray_cost, ctx->ray_order, ntiles);
+        KFB_LAUNCH_CHECK(ctx);
+        KFB_CUDA(ctx, cudaEventRecord(ctx->ev_ray_order, ctx->fstream));
+        ctx->ray_order_valid = 1;
+    }
     return KFB_OK;
 }
 
