@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(32 * KFB_RC_WARPS, KFB_RC_MINB) raycast_kernel
 }
 
 // Tile order for the next raycast: a counting sort of the tiles by the cost they just reported, most expensive
-// first (one block).  Rays differ in length by two orders of magnitude (a ray that leaves the volume at once against
+// first (one block, on a side stream).  Rays differ in length by two orders of magnitude (a ray that leaves the volume at once against
 // one that creeps along a wall), the block scheduler hands tiles out in index order, and with image rows of floor
 // at the bottom the expensive tiles used to come last: the kernel ended in a long tail of a few resident warps
 // (achieved occupancy 32 % of a possible 50 %).  The camera moves slowly, so last frame's cost predicts this frame's.
@@ -661,12 +661,13 @@ int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9]
     if (ctx->profiling) cudaEventRecord(ctx->events[59], ctx->stream);
     if (sorted)
     {
-        // next frame's order, on the front-end stream: nothing on the frame's critical path waits for it
+        // next frame's order, on the sweep's side stream (idle until the next integrate): nothing on the frame's critical
+        // path waits for it, and the front-end stream stays free to run the next frame's front end under this raycast
         KFB_CUDA(ctx, cudaEventRecord(ctx->ev_ray_done, ctx->stream));
-        KFB_CUDA(ctx, cudaStreamWaitEvent(ctx->fstream, ctx->ev_ray_done, 0));
-        raycast_order_kernel<<<1, 1024, 0, ctx->fstream>>>(ctx->ray_cost, ctx->ray_order, ntiles);
+        KFB_CUDA(ctx, cudaStreamWaitEvent(ctx->istream, ctx->ev_ray_done, 0));
+        raycast_order_kernel<<<1, 1024, 0, ctx->istream>>>(ctx->ray_cost, ctx->ray_order, ntiles);
         KFB_LAUNCH_CHECK(ctx);
-        KFB_CUDA(ctx, cudaEventRecord(ctx->ev_ray_order, ctx->fstream));
+        KFB_CUDA(ctx, cudaEventRecord(ctx->ev_ray_order, ctx->istream));
         ctx->ray_order_valid = 1;
     }
     return KFB_OK;
