@@ -25,39 +25,29 @@ __device__ __forceinline__ int reflect101(int p, int len)
 }
 
 // ---- pyrDown ------------------------------------------------------------------------------
-// vertical 5-tap chain first, then horizontal, every `sum + w*v` one FMA (upstream pyr_down.cu).  A block makes a
-// 32 x 8 output tile from a shared-memory tile of the source (19 rows x 67 columns, borders by REFLECT_101): the
-// vertical sums of a source column are formed once and shared by the five outputs that use them (a thread of the
-// untiled form loaded 25 values and did 30 multiply-adds per output; here 5.3 loads and 11.4).
-#define PD_W 32
-#define PD_H 8
-__global__ void __launch_bounds__(PD_W *PD_H) pyrdown_kernel(const float *__restrict__ src, int sw, int sh, float *__restrict__ dst, int dw, int dh)
+// vertical 5-tap chain first, then horizontal, every `sum + w*v` one FMA (upstream pyr_down.cu).  The 25 loads of an
+// output hit L1 (neighbouring outputs share 15 of them); a shared-memory tiled version (source tile + shared vertical
+// sums, 5.3 loads and 11.4 FMAs per output) measured SLOWER on B200: 5.4 us against 3.6 us per launch (round 2).
+__global__ void pyrdown_kernel(const float *__restrict__ src, int sw, int sh, float *__restrict__ dst, int dw, int dh)
 {
-    constexpr int TW = 2 * PD_W + 3, TH = 2 * PD_H + 3;
-    __shared__ float tile[TH][TW + 1];
-    __shared__ float vsum[PD_H][TW + 1];
-    const int tid = threadIdx.y * PD_W + threadIdx.x;
-    const int ox = blockIdx.x * PD_W, oy = blockIdx.y * PD_H;
-    for (int i = tid; i < TW * TH; i += PD_W * PD_H)
-    {
-        const int r = i / TW, c = i - r * TW;
-        tile[r][c] = __ldg(src + (size_t)reflect101(2 * oy - 2 + r, sh) * sw + reflect101(2 * ox - 2 + c, sw));
-    }
-    __syncthreads();
-    for (int i = tid; i < TW * PD_H; i += PD_W * PD_H)
-    {
-        const int r = i / TW, c = i - r * TW; // output row r of the tile, source column c
-        float s = __fmul_rn(0.0625f, tile[2 * r][c]);
-        s = __fmaf_rn(0.25f, tile[2 * r + 1][c], s);
-        s = __fmaf_rn(0.375f, tile[2 * r + 2][c], s);
-        s = __fmaf_rn(0.25f, tile[2 * r + 3][c], s);
-        s = __fmaf_rn(0.0625f, tile[2 * r + 4][c], s);
-        vsum[r][c] = s;
-    }
-    __syncthreads();
-    const int x = ox + threadIdx.x, y = oy + threadIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= dw || y >= dh) return;
-    const float *col = &vsum[threadIdx.y][2 * threadIdx.x];
+    int rows[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) rows[i] = reflect101(2 * y - 2 + i, sh) * sw;
+    float col[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+    {
+        const int c = reflect101(2 * x - 2 + k, sw);
+        float s = __fmul_rn(0.0625f, __ldg(src + rows[0] + c));
+        s = __fmaf_rn(0.25f, __ldg(src + rows[1] + c), s);
+        s = __fmaf_rn(0.375f, __ldg(src + rows[2] + c), s);
+        s = __fmaf_rn(0.25f, __ldg(src + rows[3] + c), s);
+        s = __fmaf_rn(0.0625f, __ldg(src + rows[4] + c), s);
+        col[k] = s;
+    }
     float s = __fmul_rn(0.0625f, col[0]);
     s = __fmaf_rn(0.25f, col[1], s);
     s = __fmaf_rn(0.375f, col[2], s);

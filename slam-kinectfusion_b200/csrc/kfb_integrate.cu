@@ -1269,60 +1269,16 @@ __global__ void brick_distance_kernel(const uint8_t *__restrict__ src, uint8_t *
     dst[i] = (uint8_t)best;
 }
 
-// x and y passes of one brick layer in shared memory (one block per layer): a layer is bx * by bytes (4 KB at 512^3,
-// 64 KB at 2048^3), so both passes read their 2 x 31 taps from shared memory and the layer crosses L2 once each way.
-__global__ void __launch_bounds__(1024) brick_distance_xy_kernel(const uint8_t *__restrict__ flags, uint8_t *__restrict__ dst, int bx, int by,
-                                                                const int *__restrict__ dirty)
-{
-    extern __shared__ uint8_t s_layer[]; // [2][by][bx]
-    if (*dirty == 0) return;
-    const int n = bx * by;
-    uint8_t *s0 = s_layer, *s1 = s_layer + n;
-    const uint8_t *src = flags + (size_t)blockIdx.x * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s0[i] = src[i] ? 0 : KFB_BDIST_CAP;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-    {
-        const int x = i % bx;
-        int best = KFB_BDIST_CAP;
-        const int j0 = max(-KFB_BDIST_CAP, -x), j1 = min(KFB_BDIST_CAP, bx - 1 - x);
-        for (int j = j0; j <= j1; ++j) best = min(best, max((int)s0[i + j], abs(j)));
-        s1[i] = (uint8_t)best;
-    }
-    __syncthreads();
-    uint8_t *out = dst + (size_t)blockIdx.x * n;
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-    {
-        const int y = i / bx;
-        int best = KFB_BDIST_CAP;
-        const int j0 = max(-KFB_BDIST_CAP, -y), j1 = min(KFB_BDIST_CAP, by - 1 - y);
-        for (int j = j0; j <= j1; ++j) best = min(best, max((int)s1[i + j * bx], abs(j)));
-        out[i] = (uint8_t)best;
-    }
-}
-
 int launch_brick_distance(kfb_ctx *ctx)
 {
     const int n = ctx->bdim[0] * ctx->bdim[1] * ctx->bdim[2];
     const int blocks = (n + 255) / 256;
-    const size_t layer2 = 2 * (size_t)ctx->bdim[0] * ctx->bdim[1];
-    if (layer2 <= 200 * 1024 && !getenv("KFB_BRICKS_3PASS"))
-    {
-        if (layer2 > 48 * 1024 && !ctx->bdist_smem_set)
-        {
-            KFB_CUDA(ctx, cudaFuncSetAttribute(brick_distance_xy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)layer2));
-            ctx->bdist_smem_set = 1;
-        }
-        brick_distance_xy_kernel<<<ctx->bdim[2], 1024, layer2, ctx->stream>>>(ctx->bricks, ctx->bdist_tmp2, ctx->bdim[0], ctx->bdim[1], ctx->bdirty);
-        KFB_LAUNCH_CHECK(ctx);
-    }
-    else
-    {
-        brick_distance_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bricks, ctx->bdist_tmp, ctx->bdim[0], ctx->bdim[1], ctx->bdim[2], 0, ctx->bdirty, 1);
-        KFB_LAUNCH_CHECK(ctx);
-        brick_distance_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bdist_tmp, ctx->bdist_tmp2, ctx->bdim[0], ctx->bdim[1], ctx->bdim[2], 1, ctx->bdirty, 0);
-        KFB_LAUNCH_CHECK(ctx);
-    }
+    // (measured and dropped in round 2: the x and y passes of a brick layer fused in shared memory, one block per layer
+    // -- 15.4 us against 2 x 7.3 us: too few blocks; and all three passes in one cooperative launch: +25 us per call)
+    brick_distance_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bricks, ctx->bdist_tmp, ctx->bdim[0], ctx->bdim[1], ctx->bdim[2], 0, ctx->bdirty, 1);
+    KFB_LAUNCH_CHECK(ctx);
+    brick_distance_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bdist_tmp, ctx->bdist_tmp2, ctx->bdim[0], ctx->bdim[1], ctx->bdim[2], 1, ctx->bdirty, 0);
+    KFB_LAUNCH_CHECK(ctx);
     brick_distance_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bdist_tmp2, ctx->bdist, ctx->bdim[0], ctx->bdim[1], ctx->bdim[2], 2, ctx->bdirty, 0);
     KFB_LAUNCH_CHECK(ctx);
     KFB_CUDA(ctx, cudaMemsetAsync(ctx->bdirty, 0, sizeof(int), ctx->stream));
