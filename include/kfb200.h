@@ -107,6 +107,11 @@ int kfb_upload_depth_mm(kfb_ctx *ctx, const float *host, int width, int height);
  * the host before the upload): half the PCIe bytes, the conversion to f32 runs on the device.  Pinned host or
  * device pointers are used in place, pageable ones are staged. */
 int kfb_upload_depth_mm_u16(kfb_ctx *ctx, const uint16_t *host, int width, int height);
+/* Buffer lifetime: from pinned host memory (or a device pointer) the upload is asynchronous and reads the caller's buffer
+ * after the call has returned; kfb_upload_wait blocks until the last upload has left that buffer, i.e. until it may be
+ * reused (GpuMat::upload is synchronous, kinectfusion.cpp:50).  kf::kinectfusion::pipeline calls it before it returns
+ * on the frames that did not wait for the device anyway (the bootstrap frame; slab ranks other than 0). */
+int kfb_upload_wait(kfb_ctx *ctx);
 /* cv::cuda::pyrDown x(L-1), cv::cuda::bilateralFilter xL, device::depthTruncation xL,
  * device::getVertexmap xL, device::getNormalmap xL -- kinectfusion.cpp:54-75,
  * device_types.hpp:122-124.  Fills the CURRENT frame's depth/vertex/normal pyramids. */

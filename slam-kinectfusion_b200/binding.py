@@ -87,6 +87,7 @@ def load_library():
         "kfb_reset_frames": (C.c_int, [_vp]),
         "kfb_upload_depth_mm": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
         "kfb_upload_depth_mm_u16": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+        "kfb_upload_wait": (C.c_int, [_vp]),
         "kfb_frontend": (C.c_int, [_vp]),
         "kfb_swap_frames": (C.c_int, [_vp]),
         "kfb_icp_accumulate": (C.c_int, [_vp, C.c_int, _vp, _vp]),

@@ -107,7 +107,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->hit_t = nullptr; ctx->icp_partials = nullptr; ctx->icp_ticket = nullptr; ctx->counters = nullptr;
     ctx->counters_host = nullptr; ctx->pinned_depth = nullptr; ctx->depth_u16 = nullptr; ctx->render_dev = nullptr; ctx->render_host = nullptr;
     ctx->stream = nullptr; ctx->own_stream = 1;
-    ctx->fstream = nullptr; ctx->ev_front = nullptr; ctx->ev_free = nullptr; ctx->ev_tables_free = nullptr; ctx->front_pending = 0;
+    ctx->fstream = nullptr; ctx->ev_upload = nullptr; ctx->ev_front = nullptr; ctx->ev_free = nullptr; ctx->ev_tables_free = nullptr; ctx->front_pending = 0;
     ctx->icp_host = nullptr; ctx->icp_gate_host = nullptr; ctx->icp_devgate = nullptr; ctx->icp_mirror = nullptr;
     ctx->icp_smem_set = 0;
     ctx->icp_fallbacks = 0; ctx->icp_direct_left = 0;
@@ -132,6 +132,8 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     }
     KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ifork, cudaEventDisableTiming));
     KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ijoin, cudaEventDisableTiming));
+    KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_upload, cudaEventDisableTiming));
+    KFB_CUDA(ctx, cudaEventRecord(ctx->ev_upload, ctx->fstream));
     KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_front, cudaEventDisableTiming));
     KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_free, cudaEventDisableTiming));
     KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_tables_free, cudaEventDisableTiming));
@@ -239,6 +241,7 @@ void kfb_destroy(kfb_ctx *ctx)
     if (ctx->ev_ifork) cudaEventDestroy(ctx->ev_ifork);
     if (ctx->ev_ijoin) cudaEventDestroy(ctx->ev_ijoin);
     if (ctx->istream) cudaStreamDestroy(ctx->istream);
+    if (ctx->ev_upload) cudaEventDestroy(ctx->ev_upload);
     if (ctx->ev_front) cudaEventDestroy(ctx->ev_front);
     if (ctx->ev_free) cudaEventDestroy(ctx->ev_free);
     if (ctx->ev_tables_free) cudaEventDestroy(ctx->ev_tables_free);
@@ -361,6 +364,7 @@ int kfb_upload_depth_mm(kfb_ctx *ctx, const float *host, int width, int height)
     const int rc = fork_front(ctx);
     if (rc) return rc;
     KFB_CUDA(ctx, cudaMemcpyAsync(ctx->L[0].raw, host, bytes, cudaMemcpyDefault, ctx->fstream));
+    KFB_CUDA(ctx, cudaEventRecord(ctx->ev_upload, ctx->fstream));
     KFB_CUDA(ctx, cudaEventRecord(ctx->ev_front, ctx->fstream));
     ctx->front_pending = 1;
     return KFB_OK;
@@ -384,10 +388,17 @@ int kfb_upload_depth_mm_u16(kfb_ctx *ctx, const uint16_t *host, int width, int h
     int rc = fork_front(ctx);
     if (rc) return rc;
     KFB_CUDA(ctx, cudaMemcpyAsync(ctx->depth_u16, host, bytes, cudaMemcpyDefault, ctx->fstream));
+    KFB_CUDA(ctx, cudaEventRecord(ctx->ev_upload, ctx->fstream));
     rc = launch_u16_to_f32(ctx, ctx->depth_u16, ctx->L[0].raw, n, ctx->fstream);
     if (rc) return rc;
     KFB_CUDA(ctx, cudaEventRecord(ctx->ev_front, ctx->fstream));
     ctx->front_pending = 1;
+    return KFB_OK;
+}
+
+int kfb_upload_wait(kfb_ctx *ctx)
+{
+    KFB_CUDA(ctx, cudaEventSynchronize(ctx->ev_upload));
     return KFB_OK;
 }
 

@@ -86,6 +86,7 @@ void kf::kinectfusion::pipeline(const float *depth_mm, int width, int height)
     {
         vdata->integrate(pose_record.back());
         kfbCheck(dev->ctx, kfb_swap_frames(dev->ctx)); // cframe->vmap.swap(pframe->vmap); nmap likewise (:88-89)
+        kfbCheck(dev->ctx, kfb_upload_wait(dev->ctx));  // the caller may reuse its frame buffer when pipeline() returns
         frame_count++;
         return;
     }
@@ -122,6 +123,7 @@ void kf::kinectfusion::pipeline(const float *depth_mm, int width, int height)
         else if (comm.composite(comm.user) != 0) throw std::runtime_error("kf::kinectfusion: raycast composite failed");
     }
     if (params_.shard_rank == 0) kfbCheck(dev->ctx, kfb_model_pyramid(dev->ctx));
+    else kfbCheck(dev->ctx, kfb_upload_wait(dev->ctx)); // rank 0 waited for the device in ICP; the others did not
     std::chrono::duration<double, std::milli> ms = std::chrono::steady_clock::now() - start_time;
     frame_time = std::to_string(ms.count());
     frame_count++;
