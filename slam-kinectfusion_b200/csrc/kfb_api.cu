@@ -701,7 +701,7 @@ void kfb_debug_integrate_counts(kfb_ctx *ctx, uint64_t out6[6])
     // valid after a counting kfb_integrate call (n_updated != NULL), which synchronises
     out6[0] = ctx->counters_host[0]; out6[1] = ctx->counters_host[2]; out6[2] = ctx->counters_host[3];
     const unsigned int *pc = reinterpret_cast<const unsigned int *>(ctx->counters_host + 4);
-    out6[3] = pc[0]; out6[4] = (uint64_t)pc[1] + pc[2]; out6[5] = pc[1];
+    out6[3] = pc[0]; out6[4] = pc[1]; out6[5] = 0;
 }
 
 } // extern "C"

@@ -84,8 +84,7 @@ struct IntegrateArgs
     int mask_words;               // 32-bit words of a patch's "chunk has a general item" mask
     uint2 *items_stream;          // {patch, z0 | z1 << 16}: every voxel of these planes gets tsdf = 1.0f
     uint2 *items_general;         // {patch, z0 | z1 << 16}: planes that need the per-voxel predicate (within one chunk)
-    unsigned int *plan_counts;    // [0] stream items, [1] long general items (stored from the front of items_general), [2] short ones (from the back)
-    unsigned int gen_cap;         // entries of items_general
+    unsigned int *plan_counts;    // [0] stream items, [1] general items
     unsigned int *patch_mask;     // [patch][mask_words]
     unsigned int *slot_of;        // [patch][chunk] -> general item index
     unsigned long long *gstates;  // [general item][6][32]: packed vc of the item's 32 threads after plane zstart(chunk) - 1
@@ -426,19 +425,6 @@ __device__ __forceinline__ PatchLane patch_lane(const IntegrateArgs &a, int patc
     p.in_plane = row * 2 + quad;
     return p;
 }
-// General items are handed out longest first: with one warp per item and two to three waves of warps, the kernel
-// would otherwise end in a tail of a few long items (the same effect as in the raycaster, kfb_raycast.cu).  The plan
-// stores items of at least KFB_GEN_LONG planes from the front of the list and the shorter ones from its back; item
-// number i (what the general kernel and the state slots count in) is long item i, then short item i - n_long.
-#define KFB_GEN_LONG 9
-__device__ __forceinline__ unsigned int gen_item_pos(const IntegrateArgs &a, unsigned int i, unsigned int n_long)
-{
-    return i < n_long ? i : a.gen_cap - 1u - (i - n_long);
-}
-__device__ __forceinline__ unsigned int gen_item_index(const IntegrateArgs &a, unsigned int pos, unsigned int n_long)
-{
-    return pos < n_long ? pos : n_long + (a.gen_cap - 1u - pos);
-}
 // plan chunks sit at absolute multiples of the chunk height (a multiple of the brick height by default), so that a
 // chunk is made of whole brick layers; the first chunk starts at the first processed plane
 __device__ __forceinline__ int chunk_first_plane(const IntegrateArgs &a, int c) { return max(a.zb, (a.zb / a.zchunk + c) * a.zchunk); }
@@ -579,26 +565,23 @@ __global__ void __launch_bounds__(128) integrate_plan_kernel(const IntegrateArgs
         }
     }
     // warp-aggregated append (keeps the warp's items in patch order)
-    const bool g_long = g_item && (g_z1 - g_z0 + 1) >= KFB_GEN_LONG, g_short = g_item && !g_long;
-    const unsigned ms = __ballot_sync(FULL, s_item), ml = __ballot_sync(FULL, g_long), mh = __ballot_sync(FULL, g_short);
+    const unsigned ms = __ballot_sync(FULL, s_item), mg = __ballot_sync(FULL, g_item);
     const int lane = threadIdx.x & 31;
-    unsigned bs = 0, bl = 0, bh = 0;
+    unsigned bs = 0, bg = 0;
     if (lane == 0)
     {
         if (ms) bs = atomicAdd(a.plan_counts + 0, __popc(ms));
-        if (ml) bl = atomicAdd(a.plan_counts + 1, __popc(ml));
-        if (mh) bh = atomicAdd(a.plan_counts + 2, __popc(mh));
+        if (mg) bg = atomicAdd(a.plan_counts + 1, __popc(mg));
     }
     bs = __shfl_sync(FULL, bs, 0);
-    bl = __shfl_sync(FULL, bl, 0);
-    bh = __shfl_sync(FULL, bh, 0);
+    bg = __shfl_sync(FULL, bg, 0);
     const unsigned below = (1u << lane) - 1u;
     if (s_item) a.items_stream[bs + __popc(ms & below)] = make_uint2((unsigned)patch, (unsigned)s_z0 | ((unsigned)s_z1 << 16));
     if (g_item)
     {
-        const unsigned pos = g_long ? bl + __popc(ml & below) : a.gen_cap - 1u - (bh + __popc(mh & below));
-        a.items_general[pos] = make_uint2((unsigned)patch, (unsigned)g_z0 | ((unsigned)g_z1 << 16));
-        a.slot_of[(size_t)patch * a.nchunks + c] = pos;
+        const unsigned idx = bg + __popc(mg & below);
+        a.items_general[idx] = make_uint2((unsigned)patch, (unsigned)g_z0 | ((unsigned)g_z1 << 16));
+        a.slot_of[(size_t)patch * a.nchunks + c] = idx;
         atomicOr(a.patch_mask + (size_t)patch * a.mask_words + (c >> 5), 1u << (c & 31));
     }
 }
@@ -615,7 +598,6 @@ __global__ void __launch_bounds__(128) integrate_states_kernel(const IntegrateAr
         if (m) c_last = w * 32 + 31 - __clz(m);
     }
     if (c_last < 0) return;
-    const unsigned int n_long = __ldg(a.plan_counts + 1);
     // lanes beyond the volume's edge compute a valid neighbour's sums (never read)
     const PatchLane pl = patch_lane(a, patch, lane);
     const int x0 = min(pl.x0, a.X - 4), y = min(pl.y, a.Y - 1);
@@ -656,7 +638,7 @@ __global__ void __launch_bounds__(128) integrate_states_kernel(const IntegrateAr
             zz[1] = ffma2(vs2, szz, zz[1]);
         }
         if (!((__ldg(a.patch_mask + (size_t)patch * a.mask_words + (c >> 5)) >> (c & 31)) & 1u)) continue;
-        const unsigned slot = gen_item_index(a, __ldg(a.slot_of + (size_t)patch * a.nchunks + c), n_long);
+        const unsigned slot = __ldg(a.slot_of + (size_t)patch * a.nchunks + c);
         if (slot >= (unsigned)a.gstate_cap) continue; // no slot: the item replays by itself
         unsigned long long *o = a.gstates + (size_t)slot * 192 + lane;
 #pragma unroll
@@ -874,7 +856,7 @@ __global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const Inte
     }
     const float4 *wt = SMEM ? s_wt : a.wtab;
     const int lane = threadIdx.x & 31;
-    const unsigned int n_long = __ldg(a.plan_counts + 1), n_items = n_long + __ldg(a.plan_counts + 2);
+    const unsigned int n_items = __ldg(a.plan_counts + 1);
     GenConst g;
     {
         const float sz = a.pose.R.m[8];
@@ -887,7 +869,7 @@ __global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const Inte
     const unsigned int wpb = blockDim.x >> 5; // one item per warp
     for (unsigned int item = blockIdx.x * wpb + (threadIdx.x >> 5); item < n_items; item += gridDim.x * wpb)
     {
-        const uint2 it = __ldg(a.items_general + gen_item_pos(a, item, n_long));
+        const uint2 it = __ldg(a.items_general + item);
         const PatchLane pl = patch_lane(a, (int)it.x, lane);
         const int x0 = pl.x0, y = pl.y;
         if (x0 >= a.X || y >= a.Y) continue;
@@ -1085,7 +1067,6 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
     a.items_general = (uint2 *)(pb + o_ig);
     a.gstates = (unsigned long long *)(pb + o_st);
     a.gstate_cap = (int)std::min<size_t>(gcap, 0x7fffffff);
-    a.gen_cap = (unsigned int)ncell;
     KFB_CUDA(ctx, cudaMemsetAsync(pb, 0, o_slot, ctx->stream)); // counters + masks
     if (n_updated) KFB_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     integrate_plan_kernel<<<(unsigned)((ncell + 127) / 128), 128, 0, ctx->stream>>>(a);
@@ -1105,7 +1086,7 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
     {
         // about one warp per item, sized from the previous frame's counts (both kernels stride, so any grid is
         // correct): the block scheduler balances the two kernels over whatever the SMs have free
-        const size_t hs = ctx->plan_hint_host ? (size_t)ctx->plan_hint_host[0] : 0, hg = ctx->plan_hint_host ? (size_t)ctx->plan_hint_host[1] + ctx->plan_hint_host[2] : 0;
+        const size_t hs = ctx->plan_hint_host ? (size_t)ctx->plan_hint_host[0] : 0, hg = ctx->plan_hint_host ? (size_t)ctx->plan_hint_host[1] : 0;
         const size_t cap = std::max<size_t>((ncell + 3) / 4, 1);
         gs = (int)std::min<size_t>(std::max<size_t>((hs + hs / 4 + 3) / 4, (size_t)gs), cap);
         gg = (int)std::min<size_t>(std::max<size_t>((hg + hg / 4 + gwarps - 1) / gwarps, (size_t)gg), cap * (4 / gwarps));
@@ -1151,11 +1132,11 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
     // item counts of this frame -> pinned host memory, read (one frame late, unsynchronised) as the next grid hint;
     // on the second stream behind the join event, so that nothing on the frame's critical path waits for the copy
     if (ctx->plan_hint_host)
-        KFB_CUDA(ctx, cudaMemcpyAsync(ctx->plan_hint_host, a.plan_counts, 3 * sizeof(unsigned int), cudaMemcpyDeviceToHost, overlap ? ctx->istream : ctx->stream));
+        KFB_CUDA(ctx, cudaMemcpyAsync(ctx->plan_hint_host, a.plan_counts, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, overlap ? ctx->istream : ctx->stream));
     if (n_updated)
     {
         KFB_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, ctx->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-        KFB_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host + 4, a.plan_counts, 3 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+        KFB_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host + 4, a.plan_counts, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
         KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         *n_updated = ctx->counters_host[0];
     }
@@ -1348,7 +1329,6 @@ int launch_plane_histogram(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *ho
     a.npy = (a.Y + KFB_PATCH_Y - 1) / KFB_PATCH_Y;
     a.mask_words = (a.nchunks + 31) / 32;
     const size_t npatch = (size_t)a.npx * a.npy, ncell = npatch * a.nchunks;
-    a.gen_cap = (unsigned int)ncell;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t o_mask = 256, o_slot = o_mask + up(npatch * a.mask_words * 4), o_is = o_slot + up(ncell * 4), o_ig = o_is + up(ncell * 8),
                  need = o_ig + up(ncell * 8);
@@ -1366,7 +1346,7 @@ int launch_plane_histogram(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *ho
         ctx->launches++;
         e = cudaGetLastError();
     }
-    unsigned int counts[3] = {0, 0, 0};
+    unsigned int counts[2] = {0, 0};
     if (e == cudaSuccess) e = cudaMemcpyAsync(counts, a.plan_counts, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     // raycast share
@@ -1390,14 +1370,10 @@ int launch_plane_histogram(kfb_ctx *ctx, const float vol2cam12[12], uint32_t *ho
         }
     }
     std::vector<uint2> items[2];
-    if (e == cudaSuccess)
+    for (int t = 0; t < 2 && e == cudaSuccess; ++t)
     {
-        items[0].resize(counts[0]);
-        if (counts[0]) e = cudaMemcpy(items[0].data(), a.items_stream, (size_t)counts[0] * sizeof(uint2), cudaMemcpyDeviceToHost);
-        items[1].resize((size_t)counts[1] + counts[2]); // long items from the front of the list, short ones from its back
-        if (e == cudaSuccess && counts[1]) e = cudaMemcpy(items[1].data(), a.items_general, (size_t)counts[1] * sizeof(uint2), cudaMemcpyDeviceToHost);
-        if (e == cudaSuccess && counts[2])
-            e = cudaMemcpy(items[1].data() + counts[1], a.items_general + (ncell - counts[2]), (size_t)counts[2] * sizeof(uint2), cudaMemcpyDeviceToHost);
+        items[t].resize(counts[t]);
+        if (counts[t]) e = cudaMemcpy(items[t].data(), t ? a.items_general : a.items_stream, (size_t)counts[t] * sizeof(uint2), cudaMemcpyDeviceToHost);
     }
     cudaFree(pb);
     KFB_CUDA(ctx, e);

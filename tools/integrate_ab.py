@@ -14,13 +14,14 @@ import torch  # noqa: E402
 import slam_kinectfusion_b200 as kfb  # noqa: E402
 from slam_kinectfusion_b200 import synth  # noqa: E402
 
+# NOTE: the GPU's clocks sag over the first seconds of sustained load, so variants that run later in the process look
+# slower (the same variant measured 104 us as the first and 117 us as the fourth of a run): repeat the variants of
+# interest at both ends of the list, or compare runs of the whole tool.
 VARIANTS = {
+    "default": {},
     "serial (one stream)": {"KFB_INTEGRATE_SERIAL": "1"},
     "chunks of 8 planes": {"KFB_PLAN_ZCHUNK": "8"},
-    "general: 2 warps/block": {"KFB_GEN_WARPS": "2"},
-    "general: 1 warp/block": {"KFB_GEN_WARPS": "1"},
-    "default": {},
-    "general: 2 warps/block (again)": {"KFB_GEN_WARPS": "2"},
+    "general kernel 80 regs": {"KFB_GEN_MINB": "6"},
     "default (again)": {},
 }
 SWITCHES = ("KFB_INTEGRATE_SERIAL", "KFB_INTEGRATE_PERSISTENT", "KFB_GEN_MINB", "KFB_PLAN_ZCHUNK", "KFB_GEN_WARPS")
