@@ -101,7 +101,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     memset(ctx->peer_keys, 0, sizeof(ctx->peer_keys)); memset(ctx->peer_maps, 0, sizeof(ctx->peer_maps)); memset(ctx->peer_flag, 0, sizeof(ctx->peer_flag));
     ctx->vol = nullptr; ctx->cloud = nullptr; ctx->cloud_cap = 0;
     ctx->tab_thrz = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->zsparse = nullptr; ctx->bricks = nullptr;
-    ctx->tab4 = nullptr; ctx->plan_buf = nullptr; ctx->plan_bytes = 0; ctx->plan_hint_host = nullptr; ctx->gen_attr_set = 0;
+    ctx->tab4 = nullptr; ctx->plan_buf = nullptr; ctx->plan_bytes = 0; ctx->plan_hint_host = nullptr; ctx->gen_attr_set = 0; ctx->integrate_seq = 0;
     ctx->bdist = ctx->bdist_tmp = ctx->bdist_tmp2 = nullptr; ctx->bdirty = nullptr;
     ctx->ray_cost = nullptr; ctx->ray_order = nullptr; ctx->ray_order_valid = 0; ctx->ev_ray_done = nullptr; ctx->ev_ray_order = nullptr;
     ctx->hit_t = nullptr; ctx->icp_partials = nullptr; ctx->icp_ticket = nullptr; ctx->counters = nullptr;

@@ -89,6 +89,12 @@ struct IntegrateArgs
     unsigned int *slot_of;        // [patch][chunk] -> general item index
     unsigned long long *gstates;  // [general item][6][32]: packed vc of the item's 32 threads after plane zstart(chunk) - 1
     int gstate_cap;               // general items that have a state slot (the others replay their running sums)
+    // fused mode: the first producer_blocks blocks of the general kernel walk the running sums and publish each item's
+    // state with ready[item] = ready_tag (release); the item's warp waits for it (acquire)
+    unsigned int *ready;
+    unsigned int ready_tag;
+    int producer_blocks;
+    unsigned long long *err;      // mapped host word: set when a wait gave up
 };
 
 #define KFB_MAGIC_F 12582912.0f   // 1.5 * 2^23
@@ -587,9 +593,9 @@ __global__ void __launch_bounds__(128) integrate_plan_kernel(const IntegrateArgs
 }
 
 // running sums at the chunk starts of the general items: one warp per patch, lane = the sweep's thread of that patch
-__global__ void __launch_bounds__(128) integrate_states_kernel(const IntegrateArgs a)
+template <bool PUBLISH>
+__device__ __forceinline__ void states_walk(const IntegrateArgs &a, int patch, int lane)
 {
-    const int patch = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (patch >= a.npx * a.npy) return;
     int c_last = -1;
     for (int w = a.mask_words - 1; w >= 0 && c_last < 0; --w)
@@ -645,8 +651,19 @@ __global__ void __launch_bounds__(128) integrate_states_kernel(const IntegrateAr
         for (int k = 0; k < 4; ++k) o[k * 32] = xy[k];
         o[128] = zz[0];
         o[160] = zz[1];
+        if (PUBLISH)
+        {
+            // the 32 lanes' stores, then one release store of the frame's tag: the item's warp may start
+            __syncwarp();
+            if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.ready + slot), "r"(a.ready_tag) : "memory");
+        }
     }
 }
+__global__ void __launch_bounds__(128) integrate_states_kernel(const IntegrateArgs a)
+{
+    states_walk<false>(a, blockIdx.x * 4 + (threadIdx.x >> 5), threadIdx.x & 31);
+}
+
 
 // running mean of a quad that receives tsdf = 1.0f in all four voxels; WT = per-weight table (shared or global)
 template <bool COUNT>
@@ -867,7 +884,17 @@ __global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const Inte
     }
     unsigned int n_upd = 0, n_ld = 0, n_st = 0;
     const unsigned int wpb = blockDim.x >> 5; // one item per warp
-    for (unsigned int item = blockIdx.x * wpb + (threadIdx.x >> 5); item < n_items; item += gridDim.x * wpb)
+    // Fused mode: the first producer_blocks blocks walk the running sums (one warp per patch, chunk by chunk) while the
+    // blocks behind them already work on the items whose states are there -- the walk (22 us, FMA-bound) no longer
+    // precedes the items, it runs under them.  Blocks are dispatched in index order, so every producer is resident
+    // (or waiting for a slot that the independent stream kernel will free) before the first item block can spin.
+    if ((int)blockIdx.x < a.producer_blocks)
+    {
+        states_walk<true>(a, (int)(blockIdx.x * wpb + (threadIdx.x >> 5)), lane);
+        return;
+    }
+    const unsigned int cblock = blockIdx.x - (unsigned)a.producer_blocks, cgrid = gridDim.x - (unsigned)a.producer_blocks;
+    for (unsigned int item = cblock * wpb + (threadIdx.x >> 5); item < n_items; item += cgrid * wpb)
     {
         const uint2 it = __ldg(a.items_general + item);
         const PatchLane pl = patch_lane(a, (int)it.x, lane);
@@ -880,6 +907,21 @@ __global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const Inte
             int zfrom = zstart;
             if (item < (unsigned int)a.gstate_cap)
             {
+                if (a.producer_blocks > 0)
+                {
+                    if (lane == 0)
+                    {
+                        unsigned int v, spins = 0;
+                        for (;;)
+                        {
+                            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.ready + item) : "memory");
+                            if (v == a.ready_tag) break;
+                            __nanosleep(100);
+                            if (++spins > (1u << 22)) { *(volatile unsigned long long *)a.err = 0x1000000000000000ull | item; break; } // ~0.5 s: report, do not hang
+                        }
+                    }
+                    __syncwarp();
+                }
                 const unsigned long long *st = a.gstates + (size_t)item * 192 + lane;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) xy[k] = __ldcg(st + k * 32);
@@ -1050,7 +1092,7 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
     const size_t gcap = std::max<size_t>(4096, ncell / 4);
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t o_counts = 0, o_mask = 256, o_slot = o_mask + up(npatch * a.mask_words * 4), o_is = o_slot + up(ncell * 4),
-                 o_ig = o_is + up(ncell * 8), o_st = o_ig + up(ncell * 8), need = o_st + gcap * 192 * 8;
+                 o_ig = o_is + up(ncell * 8), o_rd = o_ig + up(ncell * 8), o_st = o_rd + up(gcap * 4), need = o_st + gcap * 192 * 8;
     if (need > ctx->plan_bytes)
     {
         KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1058,6 +1100,7 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
         ctx->plan_buf = nullptr; ctx->plan_bytes = 0;
         KFB_CUDA(ctx, cudaMalloc(&ctx->plan_buf, need));
         ctx->plan_bytes = need;
+        KFB_CUDA(ctx, cudaMemsetAsync(ctx->plan_buf, 0, need, ctx->stream)); // the ready tags start from a known value
     }
     char *pb = (char *)ctx->plan_buf;
     a.plan_counts = (unsigned int *)(pb + o_counts);
@@ -1066,6 +1109,10 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
     a.items_stream = (uint2 *)(pb + o_is);
     a.items_general = (uint2 *)(pb + o_ig);
     a.gstates = (unsigned long long *)(pb + o_st);
+    a.ready = (unsigned int *)(pb + o_rd);
+    a.ready_tag = (unsigned int)(++ctx->integrate_seq);
+    if (a.ready_tag == 0) a.ready_tag = (unsigned int)(++ctx->integrate_seq);
+    a.err = ctx->dev_err_dev;
     a.gstate_cap = (int)std::min<size_t>(gcap, 0x7fffffff);
     KFB_CUDA(ctx, cudaMemsetAsync(pb, 0, o_slot, ctx->stream)); // counters + masks
     if (n_updated) KFB_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
@@ -1099,9 +1146,19 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
         KFB_CUDA(ctx, cudaStreamWaitEvent(ctx->istream, ctx->ev_ifork, 0));
         gstr = ctx->istream;
     }
-    // the running sums of the general items (FMA-pipe bound) run next to the stream items (bandwidth bound)
-    integrate_states_kernel<<<(unsigned)((npatch + 3) / 4), 128, 0, gstr>>>(a);
-    KFB_LAUNCH_CHECK(ctx);
+    // the running sums of the general items: walked by the first blocks of the general kernel itself (fused, default)
+    // or by a kernel of their own in front of it (KFB_INTEGRATE_SPLITSTATES=1)
+    a.producer_blocks = 0;
+    if (getenv("KFB_INTEGRATE_SPLITSTATES"))
+    {
+        integrate_states_kernel<<<(unsigned)((npatch + 3) / 4), 128, 0, gstr>>>(a);
+        KFB_LAUNCH_CHECK(ctx);
+    }
+    else
+    {
+        a.producer_blocks = (int)((npatch + gwarps - 1) / gwarps);
+        gg += a.producer_blocks;
+    }
     if (n_updated)
     {
         if (smem) integrate_general_kernel<true, true, KFB_GEN_MINB><<<gg, gthreads, 0, gstr>>>(a);

@@ -548,8 +548,11 @@ int check_device_error(kfb_ctx *ctx)
 {
     if (ctx->dev_err_host && *(volatile unsigned long long *)ctx->dev_err_host != 0ull)
     {
-        ctx->err = "shard composite: a peer's slab never arrived (frame " + std::to_string(*(volatile unsigned long long *)ctx->dev_err_host) +
-                   "); the model maps of that frame are incomplete";
+        const unsigned long long v = *(volatile unsigned long long *)ctx->dev_err_host;
+        if (v >> 60)
+            ctx->err = "integrate: the running sums of work item " + std::to_string(v & 0xffffffffull) + " never arrived; the volume is incomplete";
+        else
+            ctx->err = "shard composite: a peer's slab never arrived (frame " + std::to_string(v) + "); the model maps of that frame are incomplete";
         return KFB_ERR_TIMEOUT;
     }
     return KFB_OK;
