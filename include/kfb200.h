@@ -127,15 +127,15 @@ int kfb_swap_frames(kfb_ctx *ctx);
 int kfb_icp_accumulate(kfb_ctx *ctx, int level, const float pose12[12], double out27[27]);
 /* The same operation for the whole coarse-to-fine loop of ICPRegistration::rigidTransform
  * (icp_registration.cpp:21-43) without per-iteration launch latency: kfb_icp_begin declares the
- * schedule (iters_per_level[l] iterations at level l, coarsest level first); the first kfb_icp_step
- * starts ONE persistent kernel that runs every iteration and posts its 27 sums into mapped host memory; the
- * host solves 6x6 between steps exactly as with kfb_icp_accumulate and publishes each pose in mapped host
- * memory.  The kernel does not wait for that round trip: it predicts the pose with the host's arithmetic and
- * verifies the prediction bit for bit against the host's pose one iteration later (repeating the iteration on
- * a mismatch), so every step returns exactly what kfb_icp_accumulate would for the pose passed in -- PROVIDED
- * the caller's update is the reference's (icp_registration.cpp:35-42: solve, Rodrigues, pose * Tinc); any other
- * update rule is still handled correctly, through mispredictions.  KFB_ICP_NOSPEC=1 disables the prediction.
- * kfb_icp_end retires any iterations not stepped (tracking failure). */
+ * schedule (iters_per_level[l] iterations at level l, coarsest level first; at most 255 in all); the first
+ * kfb_icp_step starts ONE kernel that runs every iteration by itself: it computes each next pose with the
+ * reference's update rule (icp_registration.cpp:35-42: solve, Rodrigues, pose * Tinc, in the facade's arithmetic)
+ * and posts every iteration's 27 sums together with the pose it used into mapped host memory.  kfb_icp_step(k)
+ * waits for iteration k's slot, compares that pose with pose12 bit for bit and returns the sums -- exactly what
+ * kfb_icp_accumulate would return for pose12.  A caller whose update rule gives another pose is still served
+ * correctly: from the first difference on, the schedule (and the context's next 64) runs as one ordinary launch
+ * per step (kfb_icp_mispredict_count / kfb_icp_fallback_count tell).  KFB_ICP_DIRECT=1 forces that mode.
+ * kfb_icp_end closes the schedule; iterations never stepped (tracking failure) cost nothing on the host. */
 int kfb_icp_begin(kfb_ctx *ctx, const int iters_per_level[KFB_MAX_LEVELS]);
 int kfb_icp_step(kfb_ctx *ctx, const float pose12[12], double out27[27]);
 int kfb_icp_end(kfb_ctx *ctx);
@@ -218,7 +218,7 @@ void kfb_level_intrinsics(const kfb_intrinsics *in, int level, kfb_intrinsics *o
 int kfb_event_record(kfb_ctx *ctx, int slot);
 int kfb_event_elapsed_ms(kfb_ctx *ctx, int slot_a, int slot_b, float *ms);
 /* opt-in stage profiling: when on, launchers bracket their main kernel with events in reserved
- * slots (persistent ICP kernel: 54/55, shard composite kernel: 52/53, integrate kernel: 60/61, whole kfb_integrate call: 56/57, raycast: 58/59) so a caller can read that
+ * slots (whole-schedule ICP kernel: 54/55, shard composite kernel: 52/53, integrate kernel: 60/61, whole kfb_integrate call: 56/57, raycast: 58/59) so a caller can read that
  * kernel's own duration. */
 int kfb_set_profiling(kfb_ctx *ctx, int on);
 /* number of kernels this library has launched on this context since creation */
@@ -228,15 +228,16 @@ uint64_t kfb_launch_count(const kfb_ctx *ctx);
  * 4 raycast event keys (float) */
 void *kfb_device_ptr(kfb_ctx *ctx, int which);
 void *kfb_stream(kfb_ctx *ctx);
-/* debug: %globaltimer (ns) at the phase boundaries of the most recent ICP iteration of the persistent kernel, as
- * seen by the reducing CTA: iteration entry, accumulation done, elected last, final sums ready, sums posted,
- * orders for the next round ready, other CTAs released, number of mispredicted (repeated) iterations since creation */
-void kfb_debug_icp_stamps(kfb_ctx *ctx, uint64_t out8[8]);
-/* debug: per iteration (row = iteration index % 32) {entry, final sums ready, validated + posted, grid released} */
+/* debug: %globaltimer (ns) per iteration of the last whole-schedule ICP kernel, as seen by CTA 0 (row = iteration
+ * index % 32): {iteration entry, pixels accumulated, final sums ready, next pose ready} */
 void kfb_debug_icp_ring(kfb_ctx *ctx, uint64_t out128[128]);
-/* number of ICP schedules (or rests of schedules) that ran as ordinary per-iteration launches because the persistent
- * kernel could not be made co-resident or its host handshake timed out (results are bit-identical either way) */
+/* number of ICP schedules (or rests of schedules) that ran as ordinary per-iteration launches because the
+ * whole-schedule kernel could not be made co-resident, gave up on a poll, or had predicted another pose than the
+ * caller's (results are bit-identical either way) */
 uint64_t kfb_icp_fallback_count(const kfb_ctx *ctx);
+/* number of kfb_icp_step calls whose pose differed from the one the free-running kernel had predicted for that
+ * iteration (each one ends the free run of its schedule; 0 for callers that use the reference's update rule) */
+uint64_t kfb_icp_mispredict_count(const kfb_ctx *ctx);
 /* debug / measurement: numbers of the last COUNTING kfb_integrate call (n_updated != NULL): {updated voxels, 16-byte
  * voxel quads loaded, quads stored, stream work items, general work items, 0}.  Loads + stores x 16 B is the
  * kernel's own count of the bytes it moved (stores of unchanged values are dropped). */

@@ -116,9 +116,9 @@ def load_library():
         "kfb_launch_count": (C.c_uint64, [_vp]),
         "kfb_device_ptr": (_vp, [_vp, C.c_int]),
         "kfb_stream": (_vp, [_vp]),
-        "kfb_debug_icp_stamps": (None, [_vp, _vp]),
         "kfb_debug_icp_ring": (None, [_vp, _vp]),
         "kfb_icp_fallback_count": (C.c_uint64, [_vp]),
+        "kfb_icp_mispredict_count": (C.c_uint64, [_vp]),
         "kfb_debug_integrate_counts": (None, [_vp, _vp]),
     }
     for name, (res, args) in sig.items():
@@ -349,11 +349,6 @@ class Context:
     def device_ptr(self, which):
         return self.lib.kfb_device_ptr(self.h, which)
 
-    def debug_icp_stamps(self):
-        out = np.zeros(8, np.uint64)
-        self.lib.kfb_debug_icp_stamps(self.h, _ptr(out))
-        return out
-
     def debug_icp_ring(self):
         out = np.zeros((32, 4), np.uint64)
         self.lib.kfb_debug_icp_ring(self.h, _ptr(out))
@@ -367,6 +362,9 @@ class Context:
 
     def icp_fallback_count(self):
         return int(self.lib.kfb_icp_fallback_count(self.h))
+
+    def icp_mispredict_count(self):
+        return int(self.lib.kfb_icp_mispredict_count(self.h))
 
     def stream(self):
         return self.lib.kfb_stream(self.h)

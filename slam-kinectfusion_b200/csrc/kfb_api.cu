@@ -108,9 +108,10 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->counters_host = nullptr; ctx->pinned_depth = nullptr; ctx->depth_u16 = nullptr; ctx->render_dev = nullptr; ctx->render_host = nullptr;
     ctx->stream = nullptr; ctx->own_stream = 1;
     ctx->fstream = nullptr; ctx->ev_upload = nullptr; ctx->ev_front = nullptr; ctx->ev_free = nullptr; ctx->ev_tables_free = nullptr; ctx->front_pending = 0;
-    ctx->icp_host = nullptr; ctx->icp_gate_host = nullptr; ctx->icp_devgate = nullptr; ctx->icp_mirror = nullptr;
+    ctx->icp_host = nullptr; ctx->icp_devgate = nullptr;
     ctx->icp_smem_set = 0;
     ctx->icp_fallbacks = 0; ctx->icp_direct_left = 0;
+    ctx->icp_slots_host = ctx->icp_slots_dev = nullptr; ctx->icp_tagged = nullptr; ctx->icp_tagged_cap = 0; ctx->icp_mispredicts = 0;
     ctx->istream = nullptr; ctx->ev_ifork = nullptr; ctx->ev_ijoin = nullptr;
     ctx->dev_err_host = ctx->dev_err_dev = nullptr;
     memset(ctx->L, 0, sizeof(ctx->L));
@@ -200,18 +201,18 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->icp_host, sizeof(IcpHostResult), cudaHostAllocMapped));
     memset((void *)ctx->icp_host, 0, sizeof(IcpHostResult));
     KFB_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->icp_dev, (void *)ctx->icp_host, 0));
-    KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->icp_gate_host, sizeof(IcpHostGate), cudaHostAllocMapped));
-    memset((void *)ctx->icp_gate_host, 0, sizeof(IcpHostGate));
-    KFB_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->icp_gate_dev, (void *)ctx->icp_gate_host, 0));
     memset(&ctx->icp_sched, 0, sizeof(ctx->icp_sched));
     KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->dev_err_host, 64, cudaHostAllocMapped));
     memset((void *)ctx->dev_err_host, 0, 64);
     KFB_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->dev_err_dev, (void *)ctx->dev_err_host, 0));
     KFB_CUDA(ctx, cudaMalloc(&ctx->icp_devgate, sizeof(IcpDevGate)));
     KFB_CUDA(ctx, cudaMemset(ctx->icp_devgate, 0, sizeof(IcpDevGate)));
-    KFB_CUDA(ctx, cudaMalloc(&ctx->icp_mirror, 8192));
-    KFB_CUDA(ctx, cudaMemset(ctx->icp_mirror, 0, 8192));
-    ctx->icp_round = 0;
+    KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->icp_slots_host, sizeof(IcpHostSlot) * (KFB_ICP_MAX_ITERS + 1), cudaHostAllocMapped));
+    memset((void *)ctx->icp_slots_host, 0, sizeof(IcpHostSlot) * (KFB_ICP_MAX_ITERS + 1));
+    KFB_CUDA(ctx, cudaHostGetDevicePointer((void **)&ctx->icp_slots_dev, (void *)ctx->icp_slots_host, 0));
+    ctx->icp_tagged_cap = ctx->sm_count;
+    KFB_CUDA(ctx, cudaMalloc(&ctx->icp_tagged, sizeof(IcpTagged) * 2 * 27 * (size_t)ctx->icp_tagged_cap));
+    KFB_CUDA(ctx, cudaMemset(ctx->icp_tagged, 0, sizeof(IcpTagged) * 2 * 27 * (size_t)ctx->icp_tagged_cap));
     KFB_CUDA(ctx, cudaMalloc(&ctx->counters, 8 * sizeof(unsigned long long)));
     KFB_CUDA(ctx, cudaMemset(ctx->counters, 0, 8 * sizeof(unsigned long long)));
     KFB_CUDA(ctx, cudaHostAlloc((void **)&ctx->counters_host, 8 * sizeof(unsigned long long), cudaHostAllocDefault));
@@ -277,10 +278,10 @@ void kfb_destroy(kfb_ctx *ctx)
     if (ctx->icp_partials) cudaFree(ctx->icp_partials);
     if (ctx->icp_ticket) cudaFree(ctx->icp_ticket);
     if (ctx->icp_host) cudaFreeHost((void *)ctx->icp_host);
-    if (ctx->icp_gate_host) cudaFreeHost((void *)ctx->icp_gate_host);
     if (ctx->dev_err_host) cudaFreeHost((void *)ctx->dev_err_host);
     if (ctx->icp_devgate) cudaFree(ctx->icp_devgate);
-    if (ctx->icp_mirror) cudaFree(ctx->icp_mirror);
+    if (ctx->icp_slots_host) cudaFreeHost((void *)ctx->icp_slots_host);
+    if (ctx->icp_tagged) cudaFree(ctx->icp_tagged);
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->counters_host) cudaFreeHost(ctx->counters_host);
     if (ctx->pinned_depth) cudaFreeHost(ctx->pinned_depth);
@@ -687,15 +688,12 @@ void *kfb_device_ptr(kfb_ctx *ctx, int which)
     }
 }
 void *kfb_stream(kfb_ctx *ctx) { return (void *)ctx->stream; }
-void kfb_debug_icp_stamps(kfb_ctx *ctx, uint64_t out8[8])
-{
-    for (int i = 0; i < 8; ++i) out8[i] = ctx->icp_host->stamps[i];
-}
 void kfb_debug_icp_ring(kfb_ctx *ctx, uint64_t out128[128])
 {
     for (int i = 0; i < 128; ++i) out128[i] = ctx->icp_host->post_ns[i / 4][i % 4];
 }
 uint64_t kfb_icp_fallback_count(const kfb_ctx *ctx) { return ctx ? ctx->icp_fallbacks : 0; }
+uint64_t kfb_icp_mispredict_count(const kfb_ctx *ctx) { return ctx ? ctx->icp_mispredicts : 0; }
 void kfb_debug_integrate_counts(kfb_ctx *ctx, uint64_t out6[6])
 {
     // valid after a counting kfb_integrate call (n_updated != NULL), which synchronises

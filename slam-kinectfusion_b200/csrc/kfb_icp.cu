@@ -8,8 +8,8 @@
 // and writes the 27 sums as tagged 16-byte chunks straight into mapped pinned host memory.  The host spins on
 // the tags: no cudaMemcpy, no allocation, no second kernel, no device sync per iteration (the reference does
 // 2 launches + 2 cudaMalloc + 2 cudaFree + a blocking memcpy).  Two drivers share the code:
-// icp_kernel (one launch per kfb_icp_accumulate) and icp_persistent_kernel (the whole schedule in one launch,
-// with the host round trip hidden by verified pose prediction -- see the comment at that kernel).
+// icp_kernel (one launch per kfb_icp_accumulate) and icp_freerun_kernel (the whole schedule in one launch, the
+// host checking every pose the kernel computed for itself -- see the comment at that kernel).
 //
 // Numerics: products are f32 exactly as in the reference (`smem[tid] = row[i]*row[j]`),
 // sums are carried in f64 end to end (the reference rounds per-32x32-tile sums to f32 in between; the
@@ -38,7 +38,7 @@ struct IcpArgs
     unsigned long long seq;
 };
 
-#define ICP_THREADS 480                 // worker threads of a CTA (15 warps); the persistent kernel adds one service warp
+#define ICP_THREADS 480                 // threads of a CTA (15 warps)
 #define ICP_BAR() asm volatile("bar.sync 1, 480;" ::: "memory") // barrier over the workers only
 
 // findCoresp (rigid_icp.cu:46-80) + row (rigid_icp.cu:85-95), split so that the loads of several pixels can
@@ -95,12 +95,6 @@ __device__ __forceinline__ bool icp_row(const IcpArgs &a, const IcpProbe &o, con
     return true;
 }
 
-__device__ __forceinline__ unsigned long long ld_volatile_u64(const volatile unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ float4 ld_volatile_f4(const volatile float *p)
 {
     float4 v;
@@ -129,7 +123,7 @@ struct IcpLevel
 
 #define ICP_BATCH 4
 // A thread visits the same pixels in every iteration of a level (fixed pixel -> thread map), and the current
-// frame's vertex / normal of a pixel do not change while the pose does: the persistent kernel keeps the first
+// frame's vertex / normal of a pixel do not change while the pose does: the whole-schedule kernel keeps the first
 // ICP_CACHE_SLOTS pixels of every thread in shared memory (thread-private slots, no synchronisation), which takes
 // one L2 round trip out of each batch's dependent chain (current maps -> projection -> model gathers).
 #define ICP_CACHE_SLOTS 5 // 640x480 on 148 SMs: 4.3 pixels per thread; 2 x 16 B x 5 x 480 = 75 KB per CTA
@@ -252,9 +246,9 @@ __device__ __forceinline__ double icp_final_reduce(const double *partials, int n
 }
 // result chunk i = {sum_i, tag}: one aligned 16-byte store per lane, the tag (sequence number) travels with
 // the value, so the host needs no separate flag and the device no system fence
-__device__ __forceinline__ void icp_post(IcpHostResult *out, int i, double v, unsigned long long seq)
+__device__ __forceinline__ void icp_post(IcpHostResult::Chunk *chunks, int i, double v, unsigned long long seq)
 {
-    asm volatile("st.volatile.global.v2.b64 [%0], {%1, %2};" ::"l"(&out->chunk[i]), "l"(__double_as_longlong(v)), "l"(seq) : "memory");
+    asm volatile("st.volatile.global.v2.b64 [%0], {%1, %2};" ::"l"(chunks + i), "l"(__double_as_longlong(v)), "l"(seq) : "memory");
 }
 
 // one accumulation, pose by parameter (kfb_icp_accumulate)
@@ -283,47 +277,8 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_kernel(const IcpArgs a)
     if (!is_last) return;
     __threadfence();
     const double fin = icp_final_reduce(a.partials, (int)gridDim.x, red);
-    if (threadIdx.x < 27) icp_post(a.out, threadIdx.x, fin, a.seq);
+    if (threadIdx.x < 27) icp_post(a.out->chunk, threadIdx.x, fin, a.seq);
 }
-
-// ---- the whole coarse-to-fine loop in ONE persistent kernel ----------------------------------------------
-// kfb_icp_begin/step/end: the grid (one CTA per SM, all co-resident) runs every iteration of the schedule.
-// Per iteration: all CTAs accumulate their pixels and publish a partial; the last CTA to arrive (ticket)
-// reduces and posts the 27 tagged sums to mapped host memory, where the host does the reference's 6x6 solve
-// and publishes the next pose in its mapped gate.  The PCIe round trip of that exchange is taken off the
-// critical path by SPECULATION: the last CTA also solves the system itself, with the host's operations in the
-// host's order (IEEE double add/mul/div/sqrt are exactly rounded on both sides; only sin/cos may differ in the
-// last bit, which survives the cast to float with probability ~2^-29), and releases the grid with that pose at
-// once.  A service warp of CTA 0 -- the only PCIe reader -- mirrors each pose the host publishes into device
-// memory; at the end of a speculative iteration the pose it used is compared, bit for bit, with the host's:
-// equal => its sums are posted, different => the iteration is repeated with the host's pose.  The host's solve
-// stays authoritative and every result equals the non-speculative schedule's (KFB_ICP_NOSPEC=1 runs that).
-// Polls are bounded (KFB_ICP_GATE_TIMEOUT_NS, KFB_ICP_TIMEOUT_NS=<ns> overrides); on timeout or abort every CTA leaves and
-// the host finishes the schedule with ordinary launches (icp_step).
-#define ICP_MIRROR_RING 64
-struct IcpMirror // device memory, written by the service warp
-{
-    unsigned long long tag[ICP_MIRROR_RING];   // seq of the iteration the pose is for; | 1<<63 = abort
-    float pose[ICP_MIRROR_RING][12];
-};
-struct IcpPersistArgs
-{
-    IcpLevel lv[KFB_MAX_LEVELS];
-    int iters[KFB_MAX_LEVELS];
-    int levels, total;
-    float dist_thres, sine_thres;
-    double *partials;
-    unsigned int *ticket;
-    IcpHostResult *out;
-    const IcpHostGate *gate;
-    IcpDevGate *devgate;
-    IcpMirror *mirror;
-    unsigned long long seq0;   // iteration k carries sequence number seq0 + k + 1
-    unsigned long long round0; // release counter base (monotonic across schedules)
-    int speculate;
-    unsigned long long timeout_ns; // bound of every poll (x1 host pose, x2 mirrored pose, x3 device gate)
-    float pose0[12];
-};
 
 // the host's ICPRegistration::solve (LDL^T branch) + Tinc + camera_pose * Tinc (kfusion/src/icp_registration.cpp,
 // cvlite.hpp), operation for operation.  false: the system is not numerically positive definite (no prediction).
@@ -407,75 +362,172 @@ __device__ __noinline__ bool icp_predict_pose(const double *in27, const float *c
     return true;
 }
 
-enum { ICP_CMD_RUN = 0, ICP_CMD_LEAVE = 1 };
+// ---- the whole coarse-to-fine loop in ONE free-running kernel ----------------------------------------------
+// kfb_icp_begin/step/end: the grid (one CTA per SM, all co-resident, cooperative launch) runs every iteration of
+// the schedule and nobody waits for anybody's permission:
+//   * every CTA publishes its 27 partial sums as self-validating 16-byte chunks {value, sequence number} (one
+//     trip to L2), then EVERY CTA reads all partials back (one more), sums them in the ordinary kernel's fixed
+//     order and computes the next pose with the host's operations in the host's order (icp_predict_pose: IEEE
+//     double add/mul/div/sqrt are exactly rounded on both sides; only sin/cos may differ in the last bit, which
+//     survives the cast to float with probability ~2^-29) -- identical inputs, identical code, identical pose in
+//     every CTA, so the grid needs no ticket, no fence, no release;
+//   * CTA 0 posts each iteration's sums TOGETHER WITH THE POSE IT USED into that iteration's slot in mapped host
+//     memory and goes on.  The host (icp_step) takes the slot, compares the pose with its own, bit for bit, and
+//     only then uses the sums; a pose that differs (a caller with another update rule, sin/cos one ulp apart) ends
+//     the free run for that schedule: the remaining iterations are ordinary launches with the caller's poses.
+//     The host's solve stays authoritative; the host never writes to the device, the device never reads the host.
+// Round 1's kernel had one CTA reduce, predict, wait for the host's verdict on the previous pose and release the
+// others (store + fence + ticket + loads + release store + poll: five trips through L2 and a PCIe read per
+// iteration): 198 us per frame against 140 us for this one, same box, same poses (profiles/r02_experiments.md).
+// Partials are double-buffered by iteration parity: a CTA can only be one iteration ahead of the slowest one
+// (it needs that CTA's partial of iteration k + 1 before it can post k + 2).  CTAs without pixels at a level
+// sleep until CTA 0 publishes the first pose of the next level they own pixels at (IcpDevGate, tagged chunks).
+// Every poll is bounded (KFB_ICP_GATE_TIMEOUT_NS, KFB_ICP_TIMEOUT_NS=<ns> overrides): a CTA that gives up leaves,
+// the others follow, the host finds the stream idle without its result and finishes with ordinary launches.
+struct IcpFreeArgs
+{
+    IcpLevel lv[KFB_MAX_LEVELS];
+    int iters[KFB_MAX_LEVELS];
+    int levels, total;
+    float dist_thres, sine_thres;
+    IcpTagged *tagged;   // [2][cap][27]
+    int cap;
+    IcpHostSlot *slots;  // mapped host memory, slot k = iteration k
+    IcpDevGate *devgate;
+    IcpHostResult *dbg;  // debug stamps
+    unsigned long long seq0;
+    unsigned long long timeout_ns;
+    float pose0[12];
+};
+__device__ __forceinline__ int icp_level_of(const int *iters, int levels, int k)
+{
+    int level = levels - 1;
+    while (level > 0 && k >= iters[level]) { k -= iters[level]; --level; }
+    return level;
+}
+__device__ __forceinline__ void ld_volatile_tagged(const IcpTagged *p, unsigned long long &v, unsigned long long &t)
+{
+    asm volatile("ld.volatile.global.v2.b64 {%0, %1}, [%2];" : "=l"(v), "=l"(t) : "l"(p) : "memory");
+}
+#define ICP_FREE_MAXM 10 // partials per thread of the final sum: 15 slices x 10 = 150 CTAs
+// icp_final_reduce over tagged partials: the same association (four running sums over the slice, then the slices in
+// order).  All of a thread's chunks are loaded unconditionally and together (one trip to L2 per attempt; slots past
+// the thread's share repeat its last chunk), and reloaded until every tag is the iteration's.
+template <int MAXM>
+__device__ __forceinline__ void icp_slice_sum_tagged(const IcpTagged *part, int nb, unsigned long long seq, double (*red)[28],
+                                                     unsigned long long timeout_ns, volatile int *fail)
+{
+    const int v = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int stride = ICP_THREADS / 32;
+    if (v < 27 && slice < nb)
+    {
+        const int M = (nb - slice + stride - 1) / stride;
+        const IcpTagged *mine = part + (size_t)slice * 27 + v;
+        unsigned long long p[MAXM], tt[MAXM];
+        const unsigned long long t0 = globaltimer_ns();
+        bool ok;
+        for (;;)
+        {
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m) ld_volatile_tagged(mine + (size_t)(min(m, M - 1) * stride) * 27, p[m], tt[m]);
+            ok = true;
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m) ok = ok && (tt[m] == seq);
+            if (ok) break;
+            if (globaltimer_ns() - t0 > timeout_ns || *fail) { *fail = 1; break; }
+        }
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        const int G4 = M & ~3;
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m)
+        {
+            const double x = (ok && m < M) ? __longlong_as_double((long long)p[m]) : 0.0;
+            if (m < M)
+            {
+                if (m >= G4 || (m & 3) == 0) s0 += x;
+                else if ((m & 3) == 1) s1 += x;
+                else if ((m & 3) == 2) s2 += x;
+                else s3 += x;
+            }
+        }
+        red[slice][v] = (s0 + s1) + (s2 + s3);
+    }
+    else if (v < 27) red[slice][v] = 0.0;
+}
+__device__ __forceinline__ double icp_final_reduce_tagged(const IcpTagged *part, int nb, unsigned long long seq, double (*red)[28],
+                                                         unsigned long long timeout_ns, volatile int *fail)
+{
+    if (nb <= 3 * (ICP_THREADS / 32)) icp_slice_sum_tagged<3>(part, nb, seq, red, timeout_ns, fail);
+    else icp_slice_sum_tagged<ICP_FREE_MAXM>(part, nb, seq, red, timeout_ns, fail);
+    ICP_BAR();
+    double fin = 0.0;
+    if (threadIdx.x < 27)
+    {
+#pragma unroll
+        for (int w = 0; w < ICP_THREADS / 32; ++w) fin += red[w][threadIdx.x];
+    }
+    return fin;
+}
 
-__global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const IcpPersistArgs P)
+__global__ void __launch_bounds__(ICP_THREADS) icp_freerun_kernel(const IcpFreeArgs P)
 {
     __shared__ double sm[ICP_THREADS / 32][27];
     __shared__ double red[ICP_THREADS / 32][28];
     __shared__ double fin27[27];
-    __shared__ bool is_last;
-    __shared__ int s_cmd, s_iter, s_spec, s_ok, s_pred;
-    __shared__ float spose[12], npose[12], hpose[12];
+    __shared__ int s_fail, s_pred;
+    __shared__ float pose_buf[2][12];
     extern __shared__ float4 cur_cache[]; // [ICP_CACHE_SLOTS][normal, vertex][ICP_THREADS]
 
-    // ---- service warp: CTA 0 mirrors the host's poses into device memory; elsewhere it has nothing to do -------
-    if (threadIdx.x >= ICP_THREADS)
-    {
-        if (blockIdx.x != 0 || threadIdx.x != ICP_THREADS) return;
-        for (int j = 1; j < P.total; ++j)
-        {
-            // Gate: four 16-byte chunks {3 pose floats, tag}; the host rewrites each chunk with one aligned
-            // 16-byte store and the tag is the low 32 bits of the sequence number, so a chunk is either wholly
-            // old or wholly new and one poll (4 loads in flight) yields a consistent pose.
-            const unsigned long long want = P.seq0 + (unsigned long long)j + 1ull;
-            const unsigned int tag = (unsigned int)want;
-            const unsigned long long t0 = globaltimer_ns();
-            bool ok = false;
-            float4 c0, c1, c2, c3;
-            for (;;)
-            {
-                c0 = ld_volatile_f4(P.gate->chunk);
-                c1 = ld_volatile_f4(P.gate->chunk + 4);
-                c2 = ld_volatile_f4(P.gate->chunk + 8);
-                c3 = ld_volatile_f4(P.gate->chunk + 12);
-                const unsigned long long ab = ld_volatile_u64(&P.gate->abort_upto);
-                if (ab >= want) break;
-                if (__float_as_uint(c0.w) == tag && __float_as_uint(c1.w) == tag && __float_as_uint(c2.w) == tag &&
-                    __float_as_uint(c3.w) == tag) { ok = true; break; }
-                if (globaltimer_ns() - t0 > P.timeout_ns) break;
-            }
-            if (!ok)
-            {
-                // abort / timeout: every pose still awaited is answered with "leave"
-                for (int r = j; r < P.total; ++r)
-                    *(volatile unsigned long long *)&P.mirror->tag[r % ICP_MIRROR_RING] = (P.seq0 + (unsigned long long)r + 1ull) | (1ull << 63);
-                return;
-            }
-            volatile float *d = P.mirror->pose[j % ICP_MIRROR_RING]; // chunk r = {R[r][0..2]}, chunk 3 = t
-            d[0] = c0.x; d[1] = c0.y; d[2] = c0.z; d[3] = c3.x;
-            d[4] = c1.x; d[5] = c1.y; d[6] = c1.z; d[7] = c3.y;
-            d[8] = c2.x; d[9] = c2.y; d[10] = c2.z; d[11] = c3.z;
-            __threadfence();
-            *(volatile unsigned long long *)&P.mirror->tag[j % ICP_MIRROR_RING] = want;
-        }
-        return;
-    }
-
-    // ---- workers --------------------------------------------------------------------------------------------
     IcpArgs a;
     a.dist_thres = P.dist_thres; a.sine_thres = P.sine_thres;
-    if (threadIdx.x < 12) spose[threadIdx.x] = P.pose0[threadIdx.x];
-    int k = 0, spec_used = 0;
-    int cached_level = -1; // level whose current-frame pixels this thread holds in cur_cache
-    unsigned long long round = P.round0;
+    if (threadIdx.x < 12) pose_buf[0][threadIdx.x] = P.pose0[threadIdx.x];
+    if (threadIdx.x == 0) s_fail = 0;
+    int k = 0, cached_level = -1;
     ICP_BAR();
     for (;;)
     {
-        // level of iteration k (coarse to fine)
-        int level = P.levels - 1, kk = k;
-        while (level > 0 && kk >= P.iters[level]) { kk -= P.iters[level]; --level; }
+        const int level = icp_level_of(P.iters, P.levels, k);
         const IcpLevel &L = P.lv[level];
+        const int nact = L.nact;
+        if ((int)blockIdx.x >= nact)
+        {
+            // no pixels of this level are ours: sleep until the first iteration of a level where some are
+            int k2 = k + 1;
+            while (k2 < P.total && (int)blockIdx.x >= P.lv[icp_level_of(P.iters, P.levels, k2)].nact) ++k2;
+            if (k2 >= P.total) return;
+            if (threadIdx.x == 0)
+            {
+                const unsigned int want = (unsigned int)(P.seq0 + (unsigned long long)k2 + 1ull);
+                const unsigned long long t0 = globaltimer_ns();
+                float4 c0, c1, c2, c3;
+                for (;;)
+                {
+                    c3 = ld_volatile_f4(P.devgate->chunk + 12);
+                    if (__float_as_uint(c3.w) == want)
+                    {
+                        c0 = ld_volatile_f4(P.devgate->chunk);
+                        c1 = ld_volatile_f4(P.devgate->chunk + 4);
+                        c2 = ld_volatile_f4(P.devgate->chunk + 8);
+                        if (__float_as_uint(c0.w) == want && __float_as_uint(c1.w) == want && __float_as_uint(c2.w) == want) break;
+                    }
+                    else __nanosleep(400);
+                    if (globaltimer_ns() - t0 > 3ull * P.timeout_ns) { s_fail = 1; break; }
+                }
+                if (!s_fail)
+                {
+                    float *sp = pose_buf[k2 & 1];
+                    sp[0] = c0.x; sp[1] = c0.y; sp[2] = c0.z; sp[3] = c3.x;
+                    sp[4] = c1.x; sp[5] = c1.y; sp[6] = c1.z; sp[7] = c3.y;
+                    sp[8] = c2.x; sp[9] = c2.y; sp[10] = c2.z; sp[11] = c3.z;
+                }
+            }
+            ICP_BAR();
+            if (s_fail) return;
+            k = k2;
+            continue;
+        }
+        const float *spose = pose_buf[k & 1];
+        float *npose = pose_buf[(k + 1) & 1];
         a.cur_v = L.cur_v; a.cur_n = L.cur_n; a.pre_v = L.pre_v; a.pre_n = L.pre_n;
         a.k = L.k; a.cov_w = L.cov_w; a.cov_h = L.cov_h;
         const unsigned long long seq = P.seq0 + (unsigned long long)k + 1ull;
@@ -484,183 +536,61 @@ __global__ void __launch_bounds__(ICP_THREADS + 32) icp_persistent_kernel(const 
 #pragma unroll
         for (int i = 0; i < 3; ++i) a.pose.t[i] = spose[4 * i + 3];
         const unsigned long long ts0 = globaltimer_ns();
-        // only the CTAs that own pixels at this level take part in the reduction
-        const int nact = L.nact;
-        unsigned long long ts1 = ts0;
-        if (threadIdx.x == 0) is_last = false;
-        if ((int)blockIdx.x < nact)
-        {
-            double acc[27];
+        double acc[27];
 #pragma unroll
-            for (int i = 0; i < 27; ++i) acc[i] = 0.0;
-            icp_accumulate_pixels<true>(a, acc, blockIdx.x * ICP_THREADS + threadIdx.x, nact * ICP_THREADS, cur_cache, level != cached_level);
-            cached_level = level;
-            ts1 = globaltimer_ns();
-            const double s = icp_block_reduce(acc, sm);
-            if (threadIdx.x < 27)
+        for (int i = 0; i < 27; ++i) acc[i] = 0.0;
+        icp_accumulate_pixels<true>(a, acc, blockIdx.x * ICP_THREADS + threadIdx.x, nact * ICP_THREADS, cur_cache, level != cached_level);
+        cached_level = level;
+        const unsigned long long ts1 = globaltimer_ns();
+        const double s = icp_block_reduce(acc, sm);
+        IcpTagged *part = P.tagged + (size_t)(k & 1) * 27 * (size_t)P.cap;
+        if (threadIdx.x < 27)
+            asm volatile("st.volatile.global.v2.b64 [%0], {%1, %2};" ::"l"(part + (size_t)blockIdx.x * 27 + threadIdx.x),
+                         "l"(__double_as_longlong(s)), "l"(seq) : "memory");
+        const double fin = icp_final_reduce_tagged(part, nact, seq, red, P.timeout_ns, &s_fail);
+        if (threadIdx.x < 27) fin27[threadIdx.x] = fin;
+        const unsigned long long ts3 = globaltimer_ns();
+        ICP_BAR(); // fin27 and s_fail visible
+        if (s_fail) return;
+        if (blockIdx.x == 0)
+        {
+            // the iteration's result: sums + the pose they were computed with (posted writes, nobody waits for them)
+            IcpHostSlot *slot = P.slots + k;
+            if (threadIdx.x < 27) icp_post(slot->chunk, threadIdx.x, fin27[threadIdx.x], seq);
+            else if (threadIdx.x >= 32 && threadIdx.x < 36)
             {
-                P.partials[(size_t)blockIdx.x * 27 + threadIdx.x] = s;
-                __threadfence();
+                const int c = threadIdx.x - 32;
+                const float tagf = __uint_as_float((unsigned int)seq);
+                const float4 q = c < 3 ? make_float4(spose[4 * c], spose[4 * c + 1], spose[4 * c + 2], tagf) : make_float4(spose[3], spose[7], spose[11], tagf);
+                st_volatile_f4(slot->pose + 4 * c, q);
             }
-            ICP_BAR();
-            if (threadIdx.x == 0)
+            else if (threadIdx.x == 96)
             {
-                const unsigned int t = atomicInc(P.ticket, nact - 1);
-                is_last = (t == (unsigned)(nact - 1));
+                volatile unsigned long long *pr = P.dbg->post_ns[k & 31]; // debug ring (kfb_debug_icp_ring)
+                pr[0] = ts0; pr[1] = ts1; pr[2] = ts3; pr[3] = ts3;
             }
         }
+        if (k + 1 >= P.total) return;
+        if (threadIdx.x == 64) s_pred = icp_predict_pose(fin27, spose, npose) ? 1 : 0;
         ICP_BAR();
-        if (is_last)
+        if (!s_pred) return; // not positive definite: the same verdict in every CTA; the host takes over (ordinary launches)
+        if (blockIdx.x == 0 && threadIdx.x == 0)
         {
-            const unsigned long long ts2 = globaltimer_ns();
-            __threadfence();
-            const double fin = icp_final_reduce(P.partials, nact, red);
-            if (threadIdx.x < 27) fin27[threadIdx.x] = fin;
-            const unsigned long long ts3 = globaltimer_ns();
-            ICP_BAR(); // fin27 visible
-            // (1) thread 0: a speculative iteration is only as good as its pose -- compare with the host's, bit for
-            //     bit (hpose = the host's pose for this iteration).  Concurrently thread 32 (another warp) predicts
-            //     the next pose from the sums; the prediction is only used if (1) passes.
-            if (threadIdx.x == 0)
+            // CTAs that sat this level out pick the pose up here when their level starts
+            if (P.lv[icp_level_of(P.iters, P.levels, k + 1)].nact > nact)
             {
-                int ok = 1, cmd = ICP_CMD_RUN;
-                if (spec_used)
-                {
-                    const int slot = k % ICP_MIRROR_RING;
-                    const unsigned long long t0 = globaltimer_ns();
-                    unsigned long long v;
-                    for (;;)
-                    {
-                        v = ld_volatile_u64(&P.mirror->tag[slot]);
-                        if ((v & ~(1ull << 63)) == seq) break;
-                        if (globaltimer_ns() - t0 > 2ull * P.timeout_ns) { v = 1ull << 63; break; }
-                    }
-                    if (v >> 63) cmd = ICP_CMD_LEAVE;
-                    else
-                    {
-                        for (int i = 0; i < 12; ++i)
-                        {
-                            const float h = __ldcg(&P.mirror->pose[slot][i]);
-                            hpose[i] = h;
-                            if (__float_as_uint(h) != __float_as_uint(spose[i])) ok = 0;
-                        }
-                    }
-                }
-                s_ok = ok; s_cmd = cmd;
-            }
-            if (threadIdx.x == 32) s_pred = (P.speculate && k + 1 < P.total) ? (icp_predict_pose(fin27, spose, npose) ? 1 : 0) : 0;
-            ICP_BAR();
-            if (s_cmd == ICP_CMD_RUN && s_ok)
-            {
-                if (threadIdx.x < 27) icp_post(P.out, threadIdx.x, fin27[threadIdx.x], seq);
-            }
-            // (2) decide what the grid does next
-            if (threadIdx.x == 0)
-            {
-                const unsigned long long ts4 = globaltimer_ns();
-                const bool posted = s_cmd == ICP_CMD_RUN && s_ok;
-                const int k_posted = k;
-                int cmd = s_cmd, iter = k, spec = 0;
-                const float *next = npose;
-                if (cmd == ICP_CMD_RUN)
-                {
-                    if (!s_ok)
-                    {
-                        iter = k; spec = 0; next = hpose;                 // repeat iteration k with the host's pose
-                        ((volatile unsigned long long *)P.out->stamps)[7] += 1ull; // debug: mispredictions since creation
-                    }
-                    else if (k + 1 == P.total) cmd = ICP_CMD_LEAVE;       // schedule complete
-                    else
-                    {
-                        iter = k + 1;
-                        spec = s_pred;
-                        if (!spec)
-                        {
-                            // no prediction: wait for the host's pose (mirrored by the service warp)
-                            const int slot = iter % ICP_MIRROR_RING;
-                            const unsigned long long want = seq + 1ull, t0 = globaltimer_ns();
-                            unsigned long long v;
-                            for (;;)
-                            {
-                                v = ld_volatile_u64(&P.mirror->tag[slot]);
-                                if ((v & ~(1ull << 63)) == want) break;
-                                if (globaltimer_ns() - t0 > 2ull * P.timeout_ns) { v = 1ull << 63; break; }
-                            }
-                            if (v >> 63) cmd = ICP_CMD_LEAVE;
-                            else
-                            {
-                                for (int i = 0; i < 12; ++i) hpose[i] = __ldcg(&P.mirror->pose[slot][i]);
-                                next = hpose;
-                            }
-                        }
-                    }
-                }
-                const unsigned long long ts5 = globaltimer_ns();
-                {
-                    // release: four self-validating chunks (see IcpDevGate).  Nothing else has to be ordered before
-                    // them: the partials were consumed above, the ticket has wrapped to zero by itself.
-                    const unsigned int tag = ((unsigned int)((round + 1ull) & 0xfffffull) << 12) | ((unsigned int)(iter & 0xff) << 4) |
-                                             ((unsigned int)(spec & 1) << 2) | (unsigned int)(cmd & 3);
+                const float tagf = __uint_as_float((unsigned int)(seq + 1ull));
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                    {
-                        if (c < 3) st_volatile_f4(P.devgate->chunk + 4 * c, make_float4(next[4 * c], next[4 * c + 1], next[4 * c + 2], __uint_as_float(tag)));
-                        else st_volatile_f4(P.devgate->chunk + 12, make_float4(next[3], next[7], next[11], __uint_as_float(tag)));
-                    }
-                }
-                // debug hooks (kfb_debug_icp_stamps / _ring): host-memory stores, after the release on purpose
-                const unsigned long long ts6 = globaltimer_ns();
-                volatile unsigned long long *st = P.out->stamps;
-                if (posted)
+                for (int c = 0; c < 4; ++c)
                 {
-                    st[0] = ts0; st[1] = ts1; st[2] = ts2; st[3] = ts3; st[4] = ts4;
-                    volatile unsigned long long *pr = P.out->post_ns[k_posted & 31];
-                    pr[0] = ts0; pr[1] = ts3; pr[2] = ts4; pr[3] = ts6;
+                    if (c < 3) st_volatile_f4(P.devgate->chunk + 4 * c, make_float4(npose[4 * c], npose[4 * c + 1], npose[4 * c + 2], tagf));
+                    else st_volatile_f4(P.devgate->chunk + 12, make_float4(npose[3], npose[7], npose[11], tagf));
                 }
-                st[5] = ts5; st[6] = ts6;
             }
+            const unsigned long long ts4 = globaltimer_ns();
+            P.dbg->post_ns[k & 31][3] = ts4;
         }
-        // every CTA (the last one included) picks its orders up from the device gate
-        if (threadIdx.x == 0)
-        {
-            const unsigned int want = (unsigned int)((round + 1ull) & 0xfffffull);
-            const unsigned long long t0 = globaltimer_ns();
-            int cmd = ICP_CMD_RUN;
-            float4 c0, c1, c2, c3;
-            for (;;)
-            {
-                // one load per poll (the chunk written last) keeps the pollers out of the writer's way; CTAs without
-                // pixels at this level are in no hurry at all
-                c3 = ld_volatile_f4(P.devgate->chunk + 12);
-                if ((__float_as_uint(c3.w) >> 12) == want)
-                {
-                    c0 = ld_volatile_f4(P.devgate->chunk);
-                    c1 = ld_volatile_f4(P.devgate->chunk + 4);
-                    c2 = ld_volatile_f4(P.devgate->chunk + 8);
-                    const unsigned int t = __float_as_uint(c3.w);
-                    if (__float_as_uint(c0.w) == t && __float_as_uint(c1.w) == t && __float_as_uint(c2.w) == t) break;
-                }
-                else if ((int)blockIdx.x >= nact) __nanosleep(200);
-                if (globaltimer_ns() - t0 > 3ull * P.timeout_ns) { cmd = ICP_CMD_LEAVE; break; }
-            }
-            if (cmd == ICP_CMD_RUN)
-            {
-                const unsigned int t = __float_as_uint(c0.w);
-                cmd = (int)(t & 3u);
-                s_iter = (int)((t >> 4) & 0xffu);
-                s_spec = (int)((t >> 2) & 1u);
-                // rows 0..2 without the translation, then the translation column
-                spose[0] = c0.x; spose[1] = c0.y; spose[2] = c0.z;
-                spose[4] = c1.x; spose[5] = c1.y; spose[6] = c1.z;
-                spose[8] = c2.x; spose[9] = c2.y; spose[10] = c2.z;
-                spose[3] = c3.x; spose[7] = c3.y; spose[11] = c3.z;
-            }
-            s_cmd = cmd;
-        }
-        ICP_BAR();
-        if (s_cmd != ICP_CMD_RUN) return;
-        k = s_iter; spec_used = s_spec;
-        ++round;
+        ++k;
     }
 }
 
@@ -679,12 +609,12 @@ static int icp_setup(kfb_ctx *ctx, int level, IcpArgs &a, int &blocks)
     a.ticket = ctx->icp_ticket;
     a.out = ctx->icp_dev;
     // CTAs that take part at this level: one pixel per thread while the SMs last.  Measured on B200 (tools/icp_ab.py,
-    // persistent kernel per frame): KFB_ICP_PXT = 1 / 2 / 4 / 8 pixels per thread -> 184 / 189 / 209 / 282 us: every
+    // whole-schedule kernel per frame, round 1's protocol): KFB_ICP_PXT = 1 / 2 / 4 / 8 pixels per thread -> 184 / 189 / 209 / 282 us: every
     // further pixel per thread costs more in the accumulation than the smaller reduction saves.  Also measured and
     // dropped: the coarsest level inside ONE thread-block cluster of 8 CTAs (4 pixels per thread), partial sums and
     // next pose handed over through distributed shared memory with cluster-scope release / acquire instead of the
     // global partials + ticket + device gate: 9.9 us per iteration against 7.5 us (profiles/README.md).  The direct
-    // and the persistent kernel use the same count, hence the same pixel -> thread map and summation order.
+    // and the whole-schedule kernel use the same count, hence the same pixel -> thread map and summation order.
     const int npix = a.cov_w * a.cov_h;
     int pxt = 1;
     if (const char *e = getenv("KFB_ICP_PXT")) { const int v = atoi(e); if (v >= 1 && v <= 64) pxt = v; }
@@ -747,7 +677,7 @@ int launch_icp(kfb_ctx *ctx, int level, const float pose12[12], double out27[27]
     return rcw == ICP_RC_NO_RESULT ? KFB_ERR_CUDA : rcw; // an ordinary kernel that posts nothing is a device fault
 }
 
-// ---- persistent schedule -------------------------------------------------------------------------------
+// ---- whole-schedule driver -------------------------------------------------------------------------------
 int icp_begin(kfb_ctx *ctx, const int *iters_per_level)
 {
     IcpSchedule &S = ctx->icp_sched;
@@ -759,8 +689,8 @@ int icp_begin(kfb_ctx *ctx, const int *iters_per_level)
         if (S.iters[l] < 0) S.iters[l] = 0;
         S.total += S.iters[l];
     }
-    // the release tag of the persistent kernel carries the iteration in 8 bits (IcpDevGate)
-    if (S.total > 255) { ctx->err = "icp schedule longer than 255 iterations"; return KFB_ERR_INVALID; }
+    // one result slot per iteration in mapped host memory (KFB_ICP_MAX_ITERS)
+    if (S.total > KFB_ICP_MAX_ITERS) { ctx->err = "icp schedule longer than 255 iterations"; return KFB_ERR_INVALID; }
     S.seq0 = ctx->icp_seq;
     S.enq = S.done = 0;
     S.direct = getenv("KFB_ICP_DIRECT") ? 1 : 0;
@@ -771,12 +701,34 @@ int icp_begin(kfb_ctx *ctx, const int *iters_per_level)
     return KFB_OK;
 }
 
-static int icp_launch_persistent(kfb_ctx *ctx, const float pose12[12])
+// co-resident grid or nothing: cooperative launch (the driver checks), KFB_ICP_PLAIN_LAUNCH=1: ordinary launch
+// behind an occupancy query.  cudaSuccess, or the reason the grid cannot be resident (the caller falls back).
+template <class Args>
+static cudaError_t icp_launch_resident(kfb_ctx *ctx, void (*kernel)(const Args), const Args &P, int blocks, int threads, size_t smem)
+{
+    if (getenv("KFB_ICP_PLAIN_LAUNCH"))
+    {
+        int per_sm = 0;
+        cudaError_t le = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+        if (le == cudaSuccess && per_sm * ctx->sm_count < blocks) le = cudaErrorCooperativeLaunchTooLarge;
+        if (le != cudaSuccess) return le;
+        kernel<<<blocks, threads, smem, ctx->stream>>>(P);
+        return cudaGetLastError();
+    }
+    void *kargs[] = {(void *)&P};
+    return cudaLaunchCooperativeKernel((const void *)kernel, dim3(blocks), dim3(threads), kargs, smem, ctx->stream);
+}
+static bool icp_launch_refused(cudaError_t le)
+{
+    return le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources || le == cudaErrorNotSupported ||
+           le == cudaErrorInvalidConfiguration;
+}
+
+static int icp_launch_freerun(kfb_ctx *ctx, const float pose12[12])
 {
     IcpSchedule &S = ctx->icp_sched;
-    IcpPersistArgs P;
+    IcpFreeArgs P;
     memset(&P, 0, sizeof(P));
-    int max_pix = 0;
     for (int l = 0; l < ctx->levels; ++l)
     {
         IcpArgs a;
@@ -788,60 +740,33 @@ static int icp_launch_persistent(kfb_ctx *ctx, const float pose12[12])
         P.lv[l].k = a.k; P.lv[l].cov_w = a.cov_w; P.lv[l].cov_h = a.cov_h; P.lv[l].nact = blocks;
         P.iters[l] = S.iters[l];
         P.dist_thres = a.dist_thres; P.sine_thres = a.sine_thres;
-        if (S.iters[l] > 0 && a.cov_w * a.cov_h > max_pix) max_pix = a.cov_w * a.cov_h;
     }
     P.levels = ctx->levels;
     P.total = S.total;
-    P.partials = ctx->icp_partials;
-    P.ticket = ctx->icp_ticket;
-    P.out = ctx->icp_dev;
-    P.gate = ctx->icp_gate_dev;
+    P.tagged = ctx->icp_tagged;
+    P.cap = ctx->icp_tagged_cap;
+    P.slots = ctx->icp_slots_dev;
     P.devgate = ctx->icp_devgate;
-    P.mirror = (IcpMirror *)ctx->icp_mirror;
+    P.dbg = ctx->icp_dev;
     P.seq0 = S.seq0;
-    P.round0 = ctx->icp_round;
-    ctx->icp_round += (unsigned long long)(4 * S.total + 8); // rounds this launch can consume (repeats included)
-    P.speculate = getenv("KFB_ICP_NOSPEC") ? 0 : 1;
     P.timeout_ns = KFB_ICP_GATE_TIMEOUT_NS;
     if (const char *e = getenv("KFB_ICP_TIMEOUT_NS")) { const long long v = atoll(e); if (v > 0) P.timeout_ns = (unsigned long long)v; }
     memcpy(P.pose0, pose12, sizeof(P.pose0));
-    // every CTA must be resident at once (they wait on each other): one per SM (see icp_setup)
     const int blocks = ctx->sm_count;
-    (void)max_pix;
+    // the final sum keeps a thread's share of the partials in registers (ICP_FREE_MAXM per thread)
+    if (blocks > (ICP_THREADS / 32) * ICP_FREE_MAXM || blocks > ctx->icp_tagged_cap) { S.direct = 1; ctx->icp_fallbacks++; return KFB_OK; }
     if (ctx->profiling) cudaEventRecord(ctx->events[54], ctx->stream); // the frame's whole ICP: 54 .. 55
     const size_t cache_bytes = (size_t)ICP_CACHE_SLOTS * 2 * ICP_THREADS * sizeof(float4);
-    if (!ctx->icp_smem_set) // per device, hence per context
+    if (!(ctx->icp_smem_set & 2)) // per device, hence per context
     {
-        KFB_CUDA(ctx, cudaFuncSetAttribute(icp_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cache_bytes));
-        ctx->icp_smem_set = 1;
+        KFB_CUDA(ctx, cudaFuncSetAttribute(icp_freerun_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cache_bytes));
+        ctx->icp_smem_set |= 2;
     }
-    KFB_CUDA(ctx, cudaMemsetAsync(ctx->icp_ticket, 0, sizeof(unsigned int), ctx->stream));
-    // The CTAs wait on each other through the device gate, so the whole grid has to be co-resident.  A
-    // cooperative launch makes the driver check exactly that (SM limits under MPS / MIG included) and refuse
-    // the launch otherwise; the caller then runs the schedule with one ordinary launch per iteration, which
-    // gives the same sums bit for bit.  KFB_ICP_PLAIN_LAUNCH=1: ordinary launch behind an occupancy query.
-    cudaError_t le;
-    if (getenv("KFB_ICP_PLAIN_LAUNCH"))
-    {
-        int per_sm = 0;
-        le = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, icp_persistent_kernel, ICP_THREADS + 32, cache_bytes);
-        if (le == cudaSuccess && per_sm * ctx->sm_count < blocks) le = cudaErrorCooperativeLaunchTooLarge;
-        if (le == cudaSuccess)
-        {
-            icp_persistent_kernel<<<blocks, ICP_THREADS + 32, cache_bytes, ctx->stream>>>(P);
-            le = cudaGetLastError();
-        }
-    }
-    else
-    {
-        void *kargs[] = {(void *)&P};
-        le = cudaLaunchCooperativeKernel((const void *)icp_persistent_kernel, dim3(blocks), dim3(ICP_THREADS + 32), kargs, cache_bytes, ctx->stream);
-    }
+    const cudaError_t le = icp_launch_resident(ctx, icp_freerun_kernel, P, blocks, ICP_THREADS, cache_bytes);
     if (le != cudaSuccess)
     {
         (void)cudaGetLastError(); // launch-configuration errors are not sticky
-        if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorLaunchOutOfResources || le == cudaErrorNotSupported ||
-            le == cudaErrorInvalidConfiguration)
+        if (icp_launch_refused(le))
         {
             S.direct = 1;
             ctx->icp_fallbacks++;
@@ -855,55 +780,89 @@ static int icp_launch_persistent(kfb_ctx *ctx, const float pose12[12])
     return KFB_OK;
 }
 
+// the free-running kernel's result of iteration `it`: sums + the pose they belong to.  KFB_OK with *same_pose = 0:
+// the device ran this iteration with another pose than the caller's.
+static int icp_wait_slot(kfb_ctx *ctx, int it, unsigned long long seq, const float pose12[12], double out27[27], int *same_pose)
+{
+    volatile IcpHostSlot *h = ctx->icp_slots_host + it;
+    const unsigned int tag32 = (unsigned int)seq;
+    unsigned long spins = 0;
+    auto complete = [&]() {
+        int ready = 0;
+        for (int i = 0; i < 27; ++i) ready += (h->chunk[i].tag == seq);
+        for (int c = 0; c < 4; ++c)
+        {
+            unsigned int t;
+            const float f = h->pose[4 * c + 3];
+            memcpy(&t, &f, 4);
+            ready += (t == tag32);
+        }
+        return ready == 31;
+    };
+    for (;;)
+    {
+        if (complete()) break;
+        if ((++spins & 0xfffff) == 0)
+        {
+            cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) KFB_CUDA(ctx, q);
+            if (q == cudaSuccess)
+            {
+                KFB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                if (complete()) break;
+                ctx->err = "icp result never arrived (the kernel gave up or had no prediction)";
+                return ICP_RC_NO_RESULT;
+            }
+        }
+    }
+    __sync_synchronize();
+    for (int i = 0; i < 27; ++i) out27[i] = h->chunk[i].value;
+    float used[12];
+    for (int r = 0; r < 3; ++r)
+    {
+        for (int c = 0; c < 3; ++c) used[4 * r + c] = h->pose[4 * r + c];
+        used[4 * r + 3] = h->pose[12 + r];
+    }
+    *same_pose = memcmp(used, pose12, sizeof(used)) == 0;
+    return check_device_error(ctx);
+}
+
 int icp_step(kfb_ctx *ctx, const float pose12[12], double out27[27])
 {
     IcpSchedule &S = ctx->icp_sched;
     if (!S.active || S.done >= S.total) { ctx->err = "icp_step outside an active schedule"; return KFB_ERR_INVALID; }
     const unsigned long long seq = S.seq0 + (unsigned long long)S.done + 1ull;
     int rc;
-    if (S.done == 0 && !S.direct)
-    {
-        rc = icp_launch_persistent(ctx, pose12); // first pose by parameter; may switch the schedule to direct launches
-        if (rc) return rc;
-    }
-    else if (!S.direct)
-    {
-        // publish this iteration's pose: four tagged 16-byte chunks (x86 TSO keeps each store whole);
-        // the last CTA of the previous iteration is polling for it
-        IcpHostGate *g = ctx->icp_gate_host;
-        const unsigned int tag = (unsigned int)seq;
-        float tagf;
-        memcpy(&tagf, &tag, 4);
-        const __m128 k0 = _mm_set_ps(tagf, pose12[2], pose12[1], pose12[0]);
-        const __m128 k1 = _mm_set_ps(tagf, pose12[6], pose12[5], pose12[4]);
-        const __m128 k2 = _mm_set_ps(tagf, pose12[10], pose12[9], pose12[8]);
-        const __m128 k3 = _mm_set_ps(tagf, pose12[11], pose12[7], pose12[3]);
-        _mm_store_ps((float *)g->chunk, k0);
-        _mm_store_ps((float *)g->chunk + 4, k1);
-        _mm_store_ps((float *)g->chunk + 8, k2);
-        _mm_store_ps((float *)g->chunk + 12, k3);
-        _mm_sfence();
-    }
     if (!S.direct)
     {
-        rc = icp_wait(ctx, seq, out27);
-        if (rc == KFB_OK)
+        if (S.done == 0)
         {
-            ++S.done;
-            ctx->icp_seq = seq;
-            return KFB_OK;
+            rc = icp_launch_freerun(ctx, pose12); // may switch the schedule to direct launches
+            if (rc) return rc;
         }
-        if (rc != ICP_RC_NO_RESULT) return rc;
-        // Transport failure: the persistent kernel gave up waiting (a descheduled host thread, a debugger, a
-        // profiler replaying kernels) and has left the device -- icp_wait saw the stream idle.  That is not a
-        // tracking failure: the remaining iterations of this frame run as ordinary launches.
-        S.direct = 1;
-        S.enq = 0;
-        ctx->icp_fallbacks++;
-        ctx->icp_direct_left = 64;
-        const unsigned long long last = S.seq0 + (unsigned long long)S.total;
-        if (last > ctx->icp_seq) ctx->icp_seq = last; // no tag the dead kernel may have posted can be mistaken for a new one
-        ctx->err.clear();
+        if (!S.direct)
+        {
+            int same = 0;
+            rc = icp_wait_slot(ctx, S.done, seq, pose12, out27, &same);
+            if (rc == KFB_OK && same)
+            {
+                ++S.done;
+                ctx->icp_seq = seq;
+                return KFB_OK;
+            }
+            if (rc != KFB_OK && rc != ICP_RC_NO_RESULT) return rc;
+            // The device's pose for this iteration is not the caller's (another solver than the one the kernel
+            // replicates, sin / cos one ulp apart), or the kernel left without a result (a poll ran into its bound,
+            // a system that is not positive definite).  Neither is a tracking failure: this and the remaining
+            // iterations run as ordinary launches with the caller's poses, behind whatever the kernel still does.
+            if (rc == KFB_OK) ctx->icp_mispredicts++;
+            S.direct = 1;
+            ctx->icp_fallbacks++;
+            ctx->icp_direct_left = 64;
+            const unsigned long long last = S.seq0 + (unsigned long long)S.total;
+            if (last > ctx->icp_seq) ctx->icp_seq = last;
+            ctx->err.clear();
+        }
     }
     {
         // one ordinary launch per iteration: the fallback above, and KFB_ICP_DIRECT=1 for profilers that replay
@@ -921,15 +880,9 @@ int icp_end(kfb_ctx *ctx)
 {
     IcpSchedule &S = ctx->icp_sched;
     if (!S.active) return KFB_OK;
-    // iterations never fed a pose (early exit / tracking failure) retire through the abort gate: the polling
-    // thread releases every CTA with the leave bit
+    // iterations never stepped (early exit / tracking failure): the kernel runs its schedule out by itself; its slots
+    // carry sequence numbers no later schedule uses
     const unsigned long long last = S.seq0 + (unsigned long long)S.total;
-    if (S.enq > 0 && S.done < S.total)
-    {
-        volatile IcpHostGate *g = ctx->icp_gate_host;
-        g->abort_upto = last;
-        __sync_synchronize();
-    }
     if (S.enq > 0) ctx->icp_seq = last > ctx->icp_seq ? last : ctx->icp_seq;
     S.active = 0;
     return KFB_OK;

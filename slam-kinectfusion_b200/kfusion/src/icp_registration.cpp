@@ -38,7 +38,7 @@ bool kf::ICPRegistration::solve(const double in27[27], double x6[6])
     }
     if (singular || std::fabs(det) < 1e-15 || std::isnan(det)) return false;
     // Cholesky in its square-root-free form A = L D L^T with one reciprocal per column (north star: host 6x6
-    // Cholesky solve); LU back-substitution if A is not numerically positive definite.  The device predicts
+    // Cholesky solve); LU back-substitution if A is not numerically positive definite.  The device computes
     // the next pose with EXACTLY this operation sequence (csrc/kfb_icp.cu: icp_predict_pose) -- keep the two in
     // step: every product, difference and reciprocal below is one IEEE double operation (-ffp-contract=off).
     double L[6][6], d[6], inv[6], t[6][6];
@@ -75,9 +75,10 @@ bool kf::ICPRegistration::rigidTransform(cv::Affine3f &camera_pose, const cv::Af
     // The reference's `camera_pose.Identity()` (:18) is a no-op on a default-constructed pose; same start here.
     camera_pose = cv::Affine3f::Identity();
     kfb_ctx *ctx = cframe->dev->ctx;
-    // The loop below is the reference's (:21-43); the device side of every iteration was enqueued ahead
-    // of time by kfb_icp_begin and is released by kfb_icp_step, so no launch latency sits between the
-    // host solve and the next accumulation.
+    // The loop below is the reference's (:21-43).  On the device ONE kernel runs the whole schedule by itself,
+    // computing every next pose with solve()'s arithmetic; kfb_icp_step hands over iteration k's sums once the pose
+    // the kernel used for it has been found equal, bit for bit, to the pose passed in, so this loop stays the
+    // authority on every pose while no launch, PCIe read or host solve sits between two accumulations.
     int sched[KFB_MAX_LEVELS] = {0};
     for (size_t l = 0; l < schedule_.size() && l < KFB_MAX_LEVELS; ++l) sched[l] = schedule_[l];
     // false is reserved for the reference's meaning (singular system => tracking failure => the caller resets the

@@ -302,9 +302,11 @@ def test_icp_sums_vs_oracle(kfo, kfb, compat_rows):
     assert np.array_equal(a, b)
 
 
-def test_icp_gated_schedule_equals_direct(kfo, kfb):
-    """The pre-enqueued, host-gated schedule (kfb_icp_begin/step/end) returns bit-identical sums to the
-    direct call, survives early termination (tracking failure) and leaves the context reusable."""
+def test_icp_schedule_equals_direct(kfo, kfb):
+    """The whole-schedule kernel (kfb_icp_begin/step/end) returns bit-identical sums to the direct call for whatever
+    poses the caller passes (here the numpy oracle's solve, which need not round like the kernel's replica of the
+    facade's: a pose the kernel did not predict moves the rest of the schedule to ordinary launches), survives
+    early termination (tracking failure) and leaves the context reusable."""
     Ko, Kb, Po, Pb = make_pair(kfo, kfb, 64, 640, 480)
     cur = kfo.frontend(kfo.render_depth_mm(kfo.trajectory_pose(7), Ko), Ko)
     pre = kfo.frontend(kfo.render_depth_mm(kfo.trajectory_pose(6), Ko), Ko)
@@ -327,7 +329,27 @@ def test_icp_gated_schedule_equals_direct(kfo, kfb):
         ctx.icp_end()
         for level, p, got in direct[::4]:
             assert np.array_equal(ctx.icp_accumulate(level, p), got)
-    # early exit after 3 of 19 iterations: the remaining gated kernels must retire through the abort gate
+    # a pose the kernel cannot have predicted, in the middle of a schedule (fresh context: after a misprediction the
+    # next schedules of a context start on ordinary launches)
+    ctx = _ctx(kfb, Kb, Pb)
+    for l in range(3):
+        ctx.upload_maps(0, l, cur[l][1], cur[l][2])
+        ctx.upload_maps(1, l, pre[l][1], pre[l][2])
+    ctx.icp_begin(iters)
+    pose = kfo.identity()
+    before = ctx.icp_mispredict_count()
+    for i in range(6):
+        if i == 4:
+            pose = pose.copy()
+            pose[3] += np.float32(1e-3)
+        got = ctx.icp_step(pose)
+        last = (pose.copy(), got)
+        rc, x = kfo.icp_solve(got)
+        pose = kfo.pose_apply_increment(pose, x)
+    ctx.icp_end()
+    assert np.array_equal(ctx.icp_accumulate(2, last[0]), last[1])
+    assert ctx.icp_mispredict_count() > before and ctx.icp_fallback_count() >= 1
+    # early exit after 3 of 19 iterations: whatever is still running must retire by itself
     ctx.icp_begin(iters)
     for i in range(3):
         ctx.icp_step(kfo.identity())
@@ -355,12 +377,13 @@ def test_icp_transport_timeout_falls_back_without_losing_the_map(kfo, kfb, monke
             assert kf.pipeline(d) == 0
         return kf, np.stack([np.asarray(p) for p in kf.poses()])
 
-    _, want = run()
+    first, want = run()
     monkeypatch.setenv("KFB_ICP_TIMEOUT_NS", "2000")
     kf, got = run()
     monkeypatch.delenv("KFB_ICP_TIMEOUT_NS")
     assert kf.frame_count == len(frames) + 1 and len(got) == len(want)
     assert np.array_equal(got, want)
+    assert first.context().icp_fallback_count() == 0 and first.context().icp_mispredict_count() == 0   # the undisturbed run
     assert kf.context().icp_fallback_count() >= 1
     assert kf.context().download_volume()[..., 1].max() == len(frames)
 

@@ -14,7 +14,7 @@ for i, (_, d) in enumerate(frames):
         us.append(kf.last_icp_us())
 ctx = kf.context()
 print("icp us per frame: median %.1f min %.1f max %.1f" % (np.median(us), np.min(us), np.max(us)))
-print("mispredicted iterations since creation:", int(ctx.debug_icp_stamps()[7]), "of", 19 * 39)
+print("mispredicted iterations since creation:", ctx.icp_mispredict_count(), "of", 19 * 39)
 
 # serialized frames (sync between frames): ICP wall time is pure, frame wall = sum of the stages
 import time
@@ -31,10 +31,10 @@ for i, (_, d) in enumerate(frames):
 print("serialized: frame us median %.1f, icp us median %.1f, rest %.1f" % (np.median(fr), np.median(ic), np.median(fr) - np.median(ic)))
 
 R = ctx.debug_icp_ring().astype(np.int64)[:19]
-print("per-iteration ns: entry->final", (R[:, 1] - R[:, 0]).tolist())
-print("final->posted (validation wait)", (R[:, 2] - R[:, 1]).tolist())
-print("posted->released (predict)", (R[:-1, 3] - R[:-1, 2]).tolist())
-print("released->next entry", (R[1:, 0] - R[:-1, 3]).tolist())
+print("per-iteration ns: accumulate", (R[:, 1] - R[:, 0]).tolist())
+print("block sums + exchange + final sums", (R[:, 2] - R[:, 1]).tolist())
+print("post + next pose", (R[:-1, 3] - R[:-1, 2]).tolist())
+print("pose ready -> next entry", (R[1:, 0] - R[:-1, 3]).tolist())
 print("period", np.diff(R[:, 0]).tolist())
 
 # device-side stage times of pipelined frames (events recorded by the library when profiling is on)

@@ -1,6 +1,6 @@
 """ICP timing A/B inside the pipelined frame sequence: persistent-kernel duration (events 54/55) and frame time for
-different CTA counts per level (KFB_ICP_PXT = pixels per thread the count is sized for).
-    python tools/icp_ab.py [dims] [frames]"""
+the whole-schedule kernel (free) and one ordinary launch per iteration (direct = KFB_ICP_DIRECT=1).
+    python tools/icp_ab.py [dims] [frames] [variant ...]"""
 import os
 import sys
 
@@ -20,8 +20,10 @@ def main():
     frames = synth.sequence(n, K)
     dev = torch.stack([torch.from_numpy(d) for _, d in frames]).cuda()
     poses = {}
-    for pxt in sys.argv[3:] or ("1", "2", "4", "8"):
-        os.environ["KFB_ICP_PXT"] = pxt
+    for pxt in sys.argv[3:] or ("free", "direct", "free", "direct"):
+        os.environ.pop("KFB_ICP_DIRECT", None)
+        if pxt == "direct":
+            os.environ["KFB_ICP_DIRECT"] = "1"
         kf = kfb.KinectFusion(K, kfb.default_host_params(dims))
         ctx = kf.context()
         ctx.set_profiling(True)
@@ -41,7 +43,7 @@ def main():
         poses[pxt] = kf.pose().copy()
         print(f"{pxt:>9s}: icp kernel {np.mean(icp) * 1e3:6.1f} us  frame {ctx.event_elapsed_ms(0, 1) / (n - 8) * 1e3:6.1f} us  "
               f"period ns L2 {np.median(per[:9]):.0f} L1 {np.median(per[10:14]):.0f} L0 {np.median(per[15:18]):.0f}  "
-              f"fallbacks {ctx.icp_fallback_count()}", flush=True)
+              f"fallbacks {ctx.icp_fallback_count()} mispredicted {ctx.icp_mispredict_count()}", flush=True)
         kf.close()
     ref = poses[next(iter(poses))]
     print("max pose difference between variants: %.3g" % max(float(np.abs(p - ref).max()) for p in poses.values()))

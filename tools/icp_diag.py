@@ -27,21 +27,9 @@ for trial in range(3):
     us = H.icp_probe(ctx)
     print("C++ step us", [round(float(u), 1) for u in us], "total", round(float(us.sum()), 1))
 
-# phase stamps: step through a schedule, reading the stamps after each step (python-paced, so host gaps are long)
-ctx.icp_begin(iters)
-prev = None
-rows = []
-for k in range(19):
-    ctx.icp_step(I)
-    time.sleep(0.0005)
-    st = ctx.debug_icp_stamps().astype(np.int64)
-    rows.append(st.copy())
-ctx.icp_end()
-R = np.array(rows)
-print("acc ns", (R[:, 1] - R[:, 0]).tolist())
-print("reduce+ticket ns", (R[:, 2] - R[:, 1]).tolist())
-print("final ns", (R[:, 3] - R[:, 2]).tolist())
-print("post ns", (R[:, 4] - R[:, 3]).tolist())
-# stamps 5/6 of row k were written by the tail that preceded iteration k (the poll that fetched ITS pose)
-print("release ns (pose seen -> released)", (R[1:, 6] - R[1:, 5]).tolist())
-print("released -> entry ns", (R[1:, 0] - R[1:, 6]).tolist())
+# per-iteration stamps of the last schedule (CTA 0)
+R = ctx.debug_icp_ring().astype(np.int64)[:19]
+print("accumulate ns", (R[:, 1] - R[:, 0]).tolist())
+print("block sums + exchange + final sums ns", (R[:, 2] - R[:, 1]).tolist())
+print("post + next pose ns", (R[:-1, 3] - R[:-1, 2]).tolist())
+print("period ns", np.diff(R[:, 0]).tolist())
