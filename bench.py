@@ -410,12 +410,12 @@ def run_ours(args):
                 "h2d_bytes_per_step": frame_bytes, "d2h_bytes_per_step": 19 * 27 * 16,
                 "api": "kf::kinectfusion::pipeline(depth_mm) via libkfusion_b200.so, pinned host frames"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "integrate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "integrate sweep", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic()[0], "traffic_source": ncu_traffic()[1], "peak_source": peak_src,
                      "kernel_ms": k_ms_mean, "kernel_ms_how": "CUDA events around the launch, in situ in the pipelined sequence",
                      "integrate_call_ms": float(np.mean(call_ms)), "raycast_kernel_ms": float(np.mean(rc_ms)), "icp_kernel_ms": float(np.mean(icp_ms)) if icp_ms else None,
                      "algorithmic_bytes": 8.0 * U_mean, "bytes_moved_counted": float(np.mean(moved)),
-                     "kernels": "integrate_states_kernel + integrate_general_kernel (second stream) || integrate_stream_kernel, events around all three",
+                     "kernels": "integrate_general_kernel (its first blocks walk the running sums; second stream) || integrate_stream_kernel, events around both",
                      "steady_state": steady,
                      "dense_model_gbs": 8.0 * swept / (k_ms_mean * 1e-3) / 1e9, "dense_microconfig": dense},
         "clocks": clocks,
