@@ -94,6 +94,7 @@ struct IntegrateArgs
     unsigned int *ready;
     unsigned int ready_tag;
     int producer_blocks;
+    int gen_prefetch;    // general items ask L2 for all their planes at once, before the one-plane-at-a-time march
     unsigned long long *err;      // mapped host word: set when a wait gave up
 };
 
@@ -902,6 +903,24 @@ __global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const Inte
         if (x0 >= a.X || y >= a.Y) continue;
         const int z0 = (int)(it.y & 0xffffu), z1 = (int)(it.y >> 16);
         const int zstart = max(a.zb, (z0 / a.zchunk) * a.zchunk); // first plane of the item's chunk
+        uint4 *const vol4 = reinterpret_cast<uint4 *>(a.vol);
+        if (a.gen_prefetch)
+        {
+            // The march below pays one memory latency per plane.  All of the item's voxels are known now: per brick
+            // layer the patch's two bricks are 32 lines of 128 bytes (brick half, plane, half plane = the lane's own
+            // half, row, quad fields), so one prefetch per lane and layer brings every plane the item visits into L2
+            // while the states are fetched and the first planes are processed.
+            for (int zl = z0 & ~7; zl <= z1; zl += 8)
+            {
+                const int pz = zl + ((lane >> 1) & 7);
+                if (pz >= z0 && pz <= z1)
+                {
+                    const uint4 *line = vol4 + ((((size_t)((zl >> 3) - a.bz0)) * ((size_t)a.bx * a.by) + pl.brick_xy) << 7) +
+                                        (size_t)((((lane >> 1) & 7) << 4) | ((lane & 1) << 3));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+                }
+            }
+        }
         unsigned long long xy[4], zz[2];
         {
             int zfrom = zstart;
@@ -962,7 +981,6 @@ __global__ void __launch_bounds__(128, MINB) integrate_general_kernel(const Inte
                 zz[1] = ffma2(g.vs2, g.szz, zz[1]);
             }
         }
-        uint4 *const vol4 = reinterpret_cast<uint4 *>(a.vol);
         // the fast path needs vc.z >= FLT_MIN on every visited plane (MUFU.RCP without the denormal
         // pre-scaling); vc.z is affine in z up to the running-sum drift, so the two ends decide with a 1 cm margin
         bool fast;
@@ -1149,6 +1167,7 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
     // the running sums of the general items: walked by the first blocks of the general kernel itself (fused, default)
     // or by a kernel of their own in front of it (KFB_INTEGRATE_SPLITSTATES=1)
     a.producer_blocks = 0;
+    a.gen_prefetch = getenv("KFB_GEN_NOPREFETCH") ? 0 : 1;
     if (getenv("KFB_INTEGRATE_SPLITSTATES"))
     {
         integrate_states_kernel<<<(unsigned)((npatch + 3) / 4), 128, 0, gstr>>>(a);

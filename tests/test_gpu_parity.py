@@ -643,7 +643,7 @@ def test_integrate_switches_bit_identical(kfo, kfb):
     poses = [kfo.trajectory_pose(k) for k in (0, 25, 60)]
     frames = [kfo.render_depth_mm(p, Ko) for p in poses]
     keys = ("KFB_INTEGRATE_NOCULL", "KFB_INTEGRATE_NOOCC", "KFB_INTEGRATE_NOFAST", "KFB_PLAN_ZCHUNK", "KFB_INTEGRATE_SERIAL",
-            "KFB_INTEGRATE_PERSISTENT", "KFB_GEN_MINB")
+            "KFB_INTEGRATE_PERSISTENT", "KFB_GEN_MINB", "KFB_INTEGRATE_SPLITSTATES", "KFB_GEN_NOPREFETCH")
     saved = {k: os.environ.get(k) for k in keys}
 
     def run(env):
@@ -666,7 +666,8 @@ def test_integrate_switches_bit_identical(kfo, kfb):
         assert plain[..., 1].max() >= 6
         for env in ({}, {"KFB_INTEGRATE_NOFAST": "1"}, {"KFB_INTEGRATE_NOOCC": "1"}, {"KFB_PLAN_ZCHUNK": "3"},
                     {"KFB_PLAN_ZCHUNK": "32"}, {"KFB_INTEGRATE_SERIAL": "1"}, {"KFB_INTEGRATE_PERSISTENT": "1"},
-                    {"KFB_GEN_MINB": "5"}, {"KFB_GEN_MINB": "6"}):
+                    {"KFB_GEN_MINB": "5"}, {"KFB_GEN_MINB": "6"}, {"KFB_INTEGRATE_SPLITSTATES": "1"}, {"KFB_GEN_NOPREFETCH": "1"},
+                    {"KFB_GEN_NOPREFETCH": "1", "KFB_PLAN_ZCHUNK": "3"}):
             vol, n = run(env)
             assert n == n_plain, env
             assert np.array_equal(vol, plain), env

@@ -19,14 +19,15 @@ from slam_kinectfusion_b200 import synth  # noqa: E402
 # interest at both ends of the list, or compare runs of the whole tool.
 VARIANTS = {
     "default": {},
+    "no L2 prefetch": {"KFB_GEN_NOPREFETCH": "1"},
     "states kernel of its own": {"KFB_INTEGRATE_SPLITSTATES": "1"},
     "serial (one stream)": {"KFB_INTEGRATE_SERIAL": "1"},
     "chunks of 8 planes": {"KFB_PLAN_ZCHUNK": "8"},
     "general kernel 80 regs": {"KFB_GEN_MINB": "6"},
     "default (again)": {},
-    "states kernel of its own (again)": {"KFB_INTEGRATE_SPLITSTATES": "1"},
+    "no L2 prefetch (again)": {"KFB_GEN_NOPREFETCH": "1"},
 }
-SWITCHES = ("KFB_INTEGRATE_SERIAL", "KFB_INTEGRATE_PERSISTENT", "KFB_GEN_MINB", "KFB_PLAN_ZCHUNK", "KFB_GEN_WARPS", "KFB_INTEGRATE_SPLITSTATES")
+SWITCHES = ("KFB_GEN_NOPREFETCH", "KFB_INTEGRATE_SERIAL", "KFB_INTEGRATE_PERSISTENT", "KFB_GEN_MINB", "KFB_PLAN_ZCHUNK", "KFB_GEN_WARPS", "KFB_INTEGRATE_SPLITSTATES")
 
 
 def main():
