@@ -388,6 +388,30 @@ def test_icp_transport_timeout_falls_back_without_losing_the_map(kfo, kfb, monke
     assert kf.context().download_volume()[..., 1].max() == len(frames)
 
 
+@pytest.mark.parametrize("switch", ["KFB_ICP_DIRECT", "KFB_ICP_PLAIN_LAUNCH"])
+def test_icp_launch_modes_give_the_same_poses(kfo, kfb, monkeypatch, switch):
+    """One ordinary launch per iteration (KFB_ICP_DIRECT: what every fallback ends in) and the whole-schedule kernel
+    started by an ordinary launch behind an occupancy query (KFB_ICP_PLAIN_LAUNCH) track exactly like the default
+    cooperative launch."""
+    Ko = kfo.intr()
+    Kb = kfb.Intrinsics(**kfb.SENSORS["kinect1"])
+    frames = [kfo.render_depth_mm(kfo.trajectory_pose(k), Ko) for k in range(5)]
+
+    def run():
+        kf = kfb.KinectFusion(Kb, kfb.default_host_params(64))
+        for d in frames:
+            assert kf.pipeline(d) == 0
+        return kf, np.stack([np.asarray(p) for p in kf.poses()])
+
+    _, want = run()
+    monkeypatch.setenv(switch, "1")
+    kf, got = run()
+    monkeypatch.delenv(switch)
+    assert np.array_equal(got, want)
+    assert kf.context().icp_mispredict_count() == 0
+    assert kf.context().icp_fallback_count() == 0      # a forced mode is not a fallback
+
+
 def test_icp_schedule_bounds(kfo, kfb):
     Ko, Kb, Po, Pb = make_pair(kfo, kfb, 64, 320, 240)
     ctx = _ctx(kfb, Kb, Pb)
