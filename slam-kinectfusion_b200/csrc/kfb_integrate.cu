@@ -102,37 +102,6 @@ struct IntegrateArgs
 #define KFB_MAGIC_I 0x4B400000
 #define KFB_SKIP (-4.0f)
 
-// ---- packed f32x2 helpers (sm_100a FFMA2 / FMUL2 / FADD2: two IEEE-rounded ops per issue) ------------
-// NOTE: ptxas contracts mul.rn.f32x2 followed by add.rn.f32x2 into one FFMA2 (checked in SASS); this file
-// never feeds a packed mul into a packed add, only mul -> fma and fma -> add, which cannot be contracted.
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
-{
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi)
-{
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c)
-{
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b)
-{
-    unsigned long long r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b)
-{
-    unsigned long long r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
 
 // ---- per-pixel tables ---------------------------------------------------------------
 // exact[p] = {depth, MUFU.RCP(lambda)} with lambda = sqrt(((u-cx)/fx)^2 + ((v-cy)/fy)^2 + 1)

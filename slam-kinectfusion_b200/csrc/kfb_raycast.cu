@@ -142,7 +142,7 @@ __device__ __forceinline__ int classify(const RaycastArgs &a, const RaySkip &rs,
     // Chebyshev distance D (in bricks) to the nearest brick that may hold a negative voxel; 0 = such a brick.
     // Index moves by at most n + 1 per axis over n steps, an active brick is at least (D-1)*8 + 1 voxels
     // away along some axis, so the next (D-1)*8 - 1 samples cannot lie in one.
-    const int D = __ldg(a.bdist + ((size_t)((z >> 3) - (SLAB ? a.bz0 : 0)) * a.by + (y >> 3)) * a.bx + (x >> 3));
+    const int D = __ldg(a.bdist + (unsigned)((((z >> 3) - (SLAB ? a.bz0 : 0)) * a.by + (y >> 3)) * a.bx + (x >> 3))); // < 2^25 bricks
     if (D == 0)
     {
         addr = reinterpret_cast<const short *>(a.vol + vox_index<MODE>(a, x, y, z)); // low half = tsdf
@@ -324,12 +324,18 @@ __global__ void __launch_bounds__(32 * KFB_RC_WARPS, KFB_RC_MINB) raycast_kernel
                     }
                     else
                     {
+                        // the four running sums as two packed FFMA2 per step (ray_len + step = fma(step, 1, ray_len), exactly)
+                        unsigned long long nxy = pack2(nx, ny), nzl = pack2(nz, ray_len);
+                        const unsigned long long dxy = pack2(dx, dy), vxy = pack2(a.vs[0], a.vs[1]);
+                        const unsigned long long dzl = pack2(dz, a.step_len), vz1 = pack2(a.vs[2], 1.0f);
 #pragma unroll 4
                         for (int i = 0; i < nskip; ++i)
                         {
-                            nx = __fmaf_rn(dx, a.vs[0], nx); ny = __fmaf_rn(dy, a.vs[1], ny); nz = __fmaf_rn(dz, a.vs[2], nz);
-                            ray_len = __fadd_rn(ray_len, a.step_len);
+                            nxy = ffma2(dxy, vxy, nxy);
+                            nzl = ffma2(dzl, vz1, nzl);
                         }
+                        unpack2(nxy, nx, ny);
+                        unpack2(nzl, nz, ray_len);
                     }
                 }
                 continue;
