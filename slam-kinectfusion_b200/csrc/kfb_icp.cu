@@ -594,6 +594,10 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_freerun_kernel(const IcpFreeA
     }
 }
 
+// CTAs of an ICP grid: one per SM, and no more than the whole-schedule kernel's final sum keeps in registers per thread
+// (ICP_FREE_MAXM partials x 15 slices) -- on a part with more SMs the surplus ones stay idle during ICP
+static int icp_grid(const kfb_ctx *ctx) { return std::min(std::min(ctx->sm_count, (ICP_THREADS / 32) * ICP_FREE_MAXM), ctx->icp_tagged_cap); }
+
 static int icp_setup(kfb_ctx *ctx, int level, IcpArgs &a, int &blocks)
 {
     if (level < 0 || level >= ctx->levels) { ctx->err = "icp level out of range"; return KFB_ERR_INVALID; }
@@ -618,7 +622,7 @@ static int icp_setup(kfb_ctx *ctx, int level, IcpArgs &a, int &blocks)
     const int npix = a.cov_w * a.cov_h;
     int pxt = 1;
     if (const char *e = getenv("KFB_ICP_PXT")) { const int v = atoi(e); if (v >= 1 && v <= 64) pxt = v; }
-    blocks = npix > 0 ? std::min(ctx->sm_count, (npix + ICP_THREADS * pxt - 1) / (ICP_THREADS * pxt)) : 0;
+    blocks = npix > 0 ? std::min(icp_grid(ctx), (npix + ICP_THREADS * pxt - 1) / (ICP_THREADS * pxt)) : 0;
     a.stride = blocks * ICP_THREADS;
     return KFB_OK;
 }
@@ -752,9 +756,7 @@ static int icp_launch_freerun(kfb_ctx *ctx, const float pose12[12])
     P.timeout_ns = KFB_ICP_GATE_TIMEOUT_NS;
     if (const char *e = getenv("KFB_ICP_TIMEOUT_NS")) { const long long v = atoll(e); if (v > 0) P.timeout_ns = (unsigned long long)v; }
     memcpy(P.pose0, pose12, sizeof(P.pose0));
-    const int blocks = ctx->sm_count;
-    // the final sum keeps a thread's share of the partials in registers (ICP_FREE_MAXM per thread)
-    if (blocks > (ICP_THREADS / 32) * ICP_FREE_MAXM || blocks > ctx->icp_tagged_cap) { S.direct = 1; ctx->icp_fallbacks++; return KFB_OK; }
+    const int blocks = icp_grid(ctx);
     if (ctx->profiling) cudaEventRecord(ctx->events[54], ctx->stream); // the frame's whole ICP: 54 .. 55
     const size_t cache_bytes = (size_t)ICP_CACHE_SLOTS * 2 * ICP_THREADS * sizeof(float4);
     if (!(ctx->icp_smem_set & 2)) // per device, hence per context
