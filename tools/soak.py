@@ -27,6 +27,6 @@ ctx = kf.context()
 ctx.synchronize()
 print(f"{n} frames ok; translation error vs ground truth: median {np.median(err_t) * 1e3:.2f} mm, max {np.max(err_t) * 1e3:.2f} mm; "
       f"rotation: median {np.median(err_r) * 1e3:.3f} mrad, max {np.max(err_r) * 1e3:.3f} mrad")
-print("mispredicted ICP iterations:", ctx.icp_mispredict_count(), "of", 19 * (n - 1))
+print("mispredicted ICP iterations:", ctx.icp_mispredict_count(), "of", 19 * (n - 1), "; schedules that fell back to ordinary launches:", ctx.icp_fallback_count())
 pts = kf.extract_pointcloud()
 print("point cloud:", len(pts), "points; bbox", pts.min(0).round(3), pts.max(0).round(3))
