@@ -308,7 +308,7 @@ def run_ours(args):
             rc_ms.append(ctx.event_elapsed_ms(58, 59))
             try:
                 icp_ms.append(ctx.event_elapsed_ms(54, 55))
-            except Exception:  # KFB_ICP_DIRECT (profiler runs): no persistent kernel, the events were never recorded
+            except Exception:  # KFB_ICP_DIRECT: no whole-schedule kernel, the events were never recorded
                 pass
     ctx.set_profiling(False)
     # (2) updated-voxel counts (the counting variant of the kernel, on sampled frames at their tracked poses)

@@ -330,7 +330,7 @@ def _measure_config(args, dist, rank, world, local, dims, K, frames, host_pin, d
 
     # ---- per-stage durations in situ: the same pipelined sequence with the library's profiling events on; every
     # 4th frame all ranks synchronise and read that frame's events (integrate kernel 60/61, whole integrate call
-    # 56/57, slab raycast 58/59; rank 0: persistent ICP kernel 54/55, composite kernel 52/53)
+    # 56/57, slab raycast 58/59; rank 0: whole-schedule ICP kernel 54/55, composite kernel 52/53)
     ctx.set_profiling(True)
     skf.kf.reset()
     skf.mailbox_us = []

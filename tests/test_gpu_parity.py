@@ -364,7 +364,7 @@ def test_icp_schedule_equals_direct(kfo, kfb):
 
 
 def test_icp_transport_timeout_falls_back_without_losing_the_map(kfo, kfb, monkeypatch):
-    """A persistent ICP kernel that gives up on the host (here: a 2 us poll bound instead of 1 s) is a transport
+    """A whole-schedule ICP kernel that gives up on a poll (here: a 2 us bound instead of 1 s) is a transport
     failure, not a tracking failure: the schedule finishes on ordinary launches with bit-identical sums, the
     facade neither resets the volume nor loses the pose history, and the poses equal an undisturbed run's."""
     Ko = kfo.intr()

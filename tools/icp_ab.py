@@ -1,4 +1,4 @@
-"""ICP timing A/B inside the pipelined frame sequence: persistent-kernel duration (events 54/55) and frame time for
+"""ICP timing A/B inside the pipelined frame sequence: whole-schedule kernel duration (events 54/55) and frame time for
 the whole-schedule kernel (free) and one ordinary launch per iteration (direct = KFB_ICP_DIRECT=1).
     python tools/icp_ab.py [dims] [frames] [variant ...]"""
 import os

@@ -1,7 +1,7 @@
 """Small-shape run of every kernel on the hot path, for compute-sanitizer (tools/sanitize.sh).
 64^3 volume, 320x240 frames: front end, per-iteration ICP kernel, integrate (3 poses, counting variant too),
 raycast + model pyramid, extraction, render; then -- unless KFB_SAN_NO_PERSISTENT is set -- three frames through
-the C++ facade, which runs the persistent ICP kernel (raise its poll bound with KFB_ICP_TIMEOUT_NS: kernels are
+the C++ facade, which runs the whole-schedule ICP kernel (raise its poll bound with KFB_ICP_TIMEOUT_NS: kernels are
 10-100x slower under the sanitizer)."""
 import os
 import sys
