@@ -102,7 +102,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->vol = nullptr; ctx->cloud = nullptr; ctx->cloud_cap = 0;
     ctx->tab_thrz = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->zsparse = nullptr; ctx->bricks = nullptr;
     ctx->tab4 = nullptr; ctx->plan_buf = nullptr; ctx->plan_bytes = 0; ctx->plan_hint_host = nullptr; ctx->gen_attr_set = 0; ctx->integrate_seq = 0;
-    ctx->bdist = ctx->bdist_tmp = ctx->bdist_tmp2 = nullptr; ctx->bdirty = nullptr;
+    ctx->bdist = ctx->bdist_tmp = ctx->bdist_tmp2 = nullptr; ctx->bdirty = nullptr; ctx->bdirty_tag = 0;
     ctx->ray_cost = nullptr; ctx->ray_order = nullptr; ctx->ray_order_valid = 0; ctx->ev_ray_done = nullptr; ctx->ev_ray_order = nullptr;
     ctx->hit_t = nullptr; ctx->icp_partials = nullptr; ctx->icp_ticket = nullptr; ctx->counters = nullptr;
     ctx->counters_host = nullptr; ctx->pinned_depth = nullptr; ctx->depth_u16 = nullptr; ctx->render_dev = nullptr; ctx->render_host = nullptr;
@@ -112,7 +112,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->icp_smem_set = 0;
     ctx->icp_fallbacks = 0; ctx->icp_direct_left = 0;
     ctx->icp_slots_host = ctx->icp_slots_dev = nullptr; ctx->icp_tagged = nullptr; ctx->icp_tagged_cap = 0; ctx->icp_mispredicts = 0;
-    ctx->istream = nullptr; ctx->ev_ifork = nullptr; ctx->ev_ijoin = nullptr;
+    ctx->istream = nullptr; ctx->ev_ifork = nullptr; ctx->ev_ijoin = nullptr; ctx->ev_plan_clean = nullptr; ctx->ev_sweep_main = nullptr; ctx->plan_clean_bytes = 0;
     ctx->dev_err_host = ctx->dev_err_dev = nullptr;
     memset(ctx->L, 0, sizeof(ctx->L));
     memset(ctx->events, 0, sizeof(ctx->events));
@@ -133,6 +133,8 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     }
     KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ifork, cudaEventDisableTiming));
     KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ijoin, cudaEventDisableTiming));
+    KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_plan_clean, cudaEventDisableTiming));
+    KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_sweep_main, cudaEventDisableTiming));
     KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_upload, cudaEventDisableTiming));
     KFB_CUDA(ctx, cudaEventRecord(ctx->ev_upload, ctx->fstream));
     KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_front, cudaEventDisableTiming));
@@ -241,6 +243,8 @@ void kfb_destroy(kfb_ctx *ctx)
     if (ctx->istream) cudaStreamSynchronize(ctx->istream);
     if (ctx->ev_ifork) cudaEventDestroy(ctx->ev_ifork);
     if (ctx->ev_ijoin) cudaEventDestroy(ctx->ev_ijoin);
+    if (ctx->ev_plan_clean) cudaEventDestroy(ctx->ev_plan_clean);
+    if (ctx->ev_sweep_main) cudaEventDestroy(ctx->ev_sweep_main);
     if (ctx->istream) cudaStreamDestroy(ctx->istream);
     if (ctx->ev_upload) cudaEventDestroy(ctx->ev_upload);
     if (ctx->ev_front) cudaEventDestroy(ctx->ev_front);

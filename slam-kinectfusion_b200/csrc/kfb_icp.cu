@@ -365,7 +365,7 @@ __device__ __noinline__ bool icp_predict_pose(const double *in27, const float *c
 // ---- the whole coarse-to-fine loop in ONE free-running kernel ----------------------------------------------
 // kfb_icp_begin/step/end: the grid (one CTA per SM, all co-resident, cooperative launch) runs every iteration of
 // the schedule and nobody waits for anybody's permission:
-//   * every CTA publishes its 27 partial sums as self-validating 16-byte chunks {value, sequence number} (one
+//   * every CTA publishes its 27 partial sums as self-validating 16-byte chunks {value, sequence number ^ value bits} (one
 //     trip to L2), then EVERY CTA reads all partials back (one more), sums them in the ordinary kernel's fixed
 //     order and computes the next pose with the host's operations in the host's order (icp_predict_pose: IEEE
 //     double add/mul/div/sqrt are exactly rounded on both sides; only sin/cos may differ in the last bit, which
@@ -409,6 +409,15 @@ __device__ __forceinline__ void ld_volatile_tagged(const IcpTagged *p, unsigned 
 {
     asm volatile("ld.volatile.global.v2.b64 {%0, %1}, [%2];" : "=l"(v), "=l"(t) : "l"(p) : "memory");
 }
+// a device-gate chunk {x, y, z, tag ^ bits(x) ^ bits(y) ^ bits(z)}: the tag validates the payload it travels with
+__device__ __forceinline__ float4 gate_chunk(float x, float y, float z, unsigned int tag)
+{
+    return make_float4(x, y, z, __uint_as_float(tag ^ __float_as_uint(x) ^ __float_as_uint(y) ^ __float_as_uint(z)));
+}
+__device__ __forceinline__ unsigned int gate_tag(const float4 c)
+{
+    return __float_as_uint(c.w) ^ __float_as_uint(c.x) ^ __float_as_uint(c.y) ^ __float_as_uint(c.z);
+}
 #define ICP_FREE_MAXM 10 // partials per thread of the final sum: 15 slices x 10 = 150 CTAs
 // icp_final_reduce over tagged partials: the same association (four running sums over the slice, then the slices in
 // order).  All of a thread's chunks are loaded unconditionally and together (one trip to L2 per attempt; slots past
@@ -432,7 +441,7 @@ __device__ __forceinline__ void icp_slice_sum_tagged(const IcpTagged *part, int 
             for (int m = 0; m < MAXM; ++m) ld_volatile_tagged(mine + (size_t)(min(m, M - 1) * stride) * 27, p[m], tt[m]);
             ok = true;
 #pragma unroll
-            for (int m = 0; m < MAXM; ++m) ok = ok && (tt[m] == seq);
+            for (int m = 0; m < MAXM; ++m) ok = ok && ((tt[m] ^ p[m]) == seq); // tag = seq ^ value bits: a torn chunk cannot pass
             if (ok) break;
             if (globaltimer_ns() - t0 > timeout_ns || *fail) { *fail = 1; break; }
         }
@@ -503,12 +512,12 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_freerun_kernel(const IcpFreeA
                 for (;;)
                 {
                     c3 = ld_volatile_f4(P.devgate->chunk + 12);
-                    if (__float_as_uint(c3.w) == want)
+                    if (gate_tag(c3) == want)
                     {
                         c0 = ld_volatile_f4(P.devgate->chunk);
                         c1 = ld_volatile_f4(P.devgate->chunk + 4);
                         c2 = ld_volatile_f4(P.devgate->chunk + 8);
-                        if (__float_as_uint(c0.w) == want && __float_as_uint(c1.w) == want && __float_as_uint(c2.w) == want) break;
+                        if (gate_tag(c0) == want && gate_tag(c1) == want && gate_tag(c2) == want) break;
                     }
                     else __nanosleep(400);
                     if (globaltimer_ns() - t0 > 3ull * P.timeout_ns) { s_fail = 1; break; }
@@ -546,7 +555,7 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_freerun_kernel(const IcpFreeA
         IcpTagged *part = P.tagged + (size_t)(k & 1) * 27 * (size_t)P.cap;
         if (threadIdx.x < 27)
             asm volatile("st.volatile.global.v2.b64 [%0], {%1, %2};" ::"l"(part + (size_t)blockIdx.x * 27 + threadIdx.x),
-                         "l"(__double_as_longlong(s)), "l"(seq) : "memory");
+                         "l"(__double_as_longlong(s)), "l"(seq ^ (unsigned long long)__double_as_longlong(s)) : "memory");
         const double fin = icp_final_reduce_tagged(part, nact, seq, red, P.timeout_ns, &s_fail);
         if (threadIdx.x < 27) fin27[threadIdx.x] = fin;
         const unsigned long long ts3 = globaltimer_ns();
@@ -579,12 +588,12 @@ __global__ void __launch_bounds__(ICP_THREADS) icp_freerun_kernel(const IcpFreeA
             // CTAs that sat this level out pick the pose up here when their level starts
             if (P.lv[icp_level_of(P.iters, P.levels, k + 1)].nact > nact)
             {
-                const float tagf = __uint_as_float((unsigned int)(seq + 1ull));
+                const unsigned int tag = (unsigned int)(seq + 1ull);
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                 {
-                    if (c < 3) st_volatile_f4(P.devgate->chunk + 4 * c, make_float4(npose[4 * c], npose[4 * c + 1], npose[4 * c + 2], tagf));
-                    else st_volatile_f4(P.devgate->chunk + 12, make_float4(npose[3], npose[7], npose[11], tagf));
+                    if (c < 3) st_volatile_f4(P.devgate->chunk + 4 * c, gate_chunk(npose[4 * c], npose[4 * c + 1], npose[4 * c + 2], tag));
+                    else st_volatile_f4(P.devgate->chunk + 12, gate_chunk(npose[3], npose[7], npose[11], tag));
                 }
             }
             const unsigned long long ts4 = globaltimer_ns();

@@ -73,7 +73,8 @@ struct IntegrateArgs
     int no_fastpath;            // KFB_INTEGRATE_NOFAST: no stream items (tuning / testing)
     int use_jump, jump_min;     // exact jump of the running sum for prefixes of at least jump_min planes
     uint8_t *bricks;
-    int *bdirty;         // set when a brick flag flips 0 -> 1 (the distance map must be rebuilt)
+    int *bdirty;         // receives dirty_tag when a brick flag flips 0 -> 1 (the distance map must be rebuilt)
+    int dirty_tag;       // this call's tag (never 0, never reused): nothing has to be cleared between frames
     int bx, by, bz, bz0; // brick grid dims (x, y, stored z bricks) and first stored z brick -- of the flags AND of the voxels
     CullPlane cull[KFB_NCULL];
     unsigned long long *counter;
@@ -291,7 +292,7 @@ __device__ __forceinline__ float classify_generic(const IntegrateArgs &a, float 
 }
 
 // bricks within two voxels of a sample that just turned negative (see kfb_raycast.cu for why two)
-__device__ __noinline__ void mark_bricks(uint8_t *flags, int *dirty, int gbx, int gby, int gbz, int gbz0, int x0, int y, int z)
+__device__ __noinline__ void mark_bricks(uint8_t *flags, int *dirty, int dirty_tag, int gbx, int gby, int gbz, int gbz0, int x0, int y, int z)
 {
     // each axis reaches at most two bricks (x: 8 voxels from x0 - 2; y, z: +-2): the <= 8 flags are read together
     const int bx0 = max(x0 - 2, 0) >> 3, bx1 = min((x0 + 5) >> 3, gbx - 1);
@@ -309,7 +310,7 @@ __device__ __noinline__ void mark_bricks(uint8_t *flags, int *dirty, int gbx, in
 #pragma unroll
     for (int i = 0; i < 8; ++i)
         if (v[i] == 0) { *f[i] = 1; any = true; }
-    if (any) *dirty = 1;
+    if (any) *dirty = dirty_tag;
 }
 
 // phase B of one plane: running weighted mean, re-encode, store (tsdf_volume.cu:69-79)
@@ -352,7 +353,7 @@ __device__ __forceinline__ void update_quad(const IntegrateArgs &a, uint4 *vp, c
         __stcs(vp, o);
         // a voxel that turns negative here (it was not before) activates the bricks around it
         if (((o.x & ~wd.x) | (o.y & ~wd.y) | (o.z & ~wd.z) | (o.w & ~wd.w)) & 0x8000u)
-            mark_bricks(a.bricks, a.bdirty, a.bx, a.by, a.bz, a.bz0, x0, y, z);
+            mark_bricks(a.bricks, a.bdirty, a.dirty_tag, a.bx, a.by, a.bz, a.bz0, x0, y, z);
     }
 }
 
@@ -825,7 +826,7 @@ __device__ __forceinline__ void gen_process(const IntegrateArgs &a, const GenCon
         if (COUNT) ++n_st;
         // a voxel that turns negative here (it was not before) activates the bricks around it
         if (((o.x & ~wd.x) | (o.y & ~wd.y) | (o.z & ~wd.z) | (o.w & ~wd.w)) & 0x8000u)
-            mark_bricks(a.bricks, a.bdirty, a.bx, a.by, a.bz, a.bz0, x0, y, z);
+            mark_bricks(a.bricks, a.bdirty, a.dirty_tag, a.bx, a.by, a.bz, a.bz0, x0, y, z);
     }
 }
 
@@ -1087,6 +1088,7 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
         ctx->plan_buf = nullptr; ctx->plan_bytes = 0;
         KFB_CUDA(ctx, cudaMalloc(&ctx->plan_buf, need));
         ctx->plan_bytes = need;
+        ctx->plan_clean_bytes = 0;
         KFB_CUDA(ctx, cudaMemsetAsync(ctx->plan_buf, 0, need, ctx->stream)); // the ready tags start from a known value
     }
     char *pb = (char *)ctx->plan_buf;
@@ -1101,7 +1103,11 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
     if (a.ready_tag == 0) a.ready_tag = (unsigned int)(++ctx->integrate_seq);
     a.err = ctx->dev_err_dev;
     a.gstate_cap = (int)std::min<size_t>(gcap, 0x7fffffff);
-    KFB_CUDA(ctx, cudaMemsetAsync(pb, 0, o_slot, ctx->stream)); // counters + masks
+    // counters + masks start from zero: normally the previous call has cleared them on the second stream, behind
+    // everything that read them (see the end of this function), and the frame's critical path only waits for that event
+    if (ctx->plan_clean_bytes == o_slot) KFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_plan_clean, 0));
+    else KFB_CUDA(ctx, cudaMemsetAsync(pb, 0, o_slot, ctx->stream));
+    ctx->plan_clean_bytes = 0;
     if (n_updated) KFB_CUDA(ctx, cudaMemsetAsync(ctx->counters, 0, 4 * sizeof(unsigned long long), ctx->stream));
     integrate_plan_kernel<<<(unsigned)((ncell + 127) / 128), 128, 0, ctx->stream>>>(a);
     KFB_LAUNCH_CHECK(ctx);
@@ -1170,6 +1176,7 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
     }
     if (overlap)
     {
+        KFB_CUDA(ctx, cudaEventRecord(ctx->ev_sweep_main, ctx->stream)); // the stream items are done (read by the clearing below)
         KFB_CUDA(ctx, cudaEventRecord(ctx->ev_ijoin, ctx->istream));
         KFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_ijoin, 0));
     }
@@ -1178,6 +1185,15 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
     // on the second stream behind the join event, so that nothing on the frame's critical path waits for the copy
     if (ctx->plan_hint_host)
         KFB_CUDA(ctx, cudaMemcpyAsync(ctx->plan_hint_host, a.plan_counts, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, overlap ? ctx->istream : ctx->stream));
+    if (overlap && !n_updated)
+    {
+        // both sweep kernels and the hint copy are behind us on the second stream: clear the plan's counters and masks
+        // for the next call there, off the critical path
+        KFB_CUDA(ctx, cudaStreamWaitEvent(ctx->istream, ctx->ev_sweep_main, 0));
+        KFB_CUDA(ctx, cudaMemsetAsync(pb, 0, o_slot, ctx->istream));
+        KFB_CUDA(ctx, cudaEventRecord(ctx->ev_plan_clean, ctx->istream));
+        ctx->plan_clean_bytes = o_slot;
+    }
     if (n_updated)
     {
         KFB_CUDA(ctx, cudaMemcpyAsync(ctx->counters_host, ctx->counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1213,6 +1229,7 @@ static void fill_integrate_args(kfb_ctx *ctx, const float vol2cam12[12], Integra
     a.jump_min = getenv("KFB_INTEGRATE_JUMPMIN") ? atoi(getenv("KFB_INTEGRATE_JUMPMIN")) : 640;
     a.bricks = ctx->bricks;
     a.bdirty = ctx->bdirty;
+    a.dirty_tag = ctx->bdirty_tag;
     a.bx = ctx->bdim[0]; a.by = ctx->bdim[1]; a.bz = ctx->bdim[2]; a.bz0 = ctx->bz0;
     a.counter = ctx->counters;
     make_cull_planes(ctx, a, a.cull);
@@ -1234,13 +1251,14 @@ int launch_integrate(kfb_ctx *ctx, const float vol2cam12[12], uint64_t *n_update
 {
     if (ctx->profiling) cudaEventRecord(ctx->events[56], ctx->stream); // whole call: 56 .. 57
     IntegrateArgs a;
+    ctx->bdirty_tag = ctx->bdirty_tag == 0x7fffffff ? 1 : ctx->bdirty_tag + 1;
     fill_integrate_args(ctx, vol2cam12, a);
     const int planes = a.ze - a.zb;
     if (planes <= 0) return KFB_OK;
     const int rcp = launch_integrate_planned(ctx, a, planes, n_updated);
     if (rcp) return rcp;
     KFB_CUDA(ctx, cudaEventRecord(ctx->ev_tables_free, ctx->stream)); // the next frame's tables may now be built
-    const int rcd = launch_brick_distance(ctx);
+    const int rcd = launch_brick_distance(ctx, false);
     if (ctx->profiling) cudaEventRecord(ctx->events[57], ctx->stream);
     return rcd;
 }
@@ -1266,7 +1284,7 @@ __global__ void rebuild_bricks_kernel(const IntegrateArgs a, size_t nquads, int 
         const int in = (int)(q & 127), bxy = a.bx * a.by;
         const int bzi = (int)(brick / bxy), r = (int)(brick - (size_t)bzi * bxy);
         const int x0 = ((r % a.bx) << 3) + ((in & 1) << 2), y = ((r / a.bx) << 3) + ((in >> 1) & 7), z = ((bzi + a.bz0) << 3) + (in >> 4);
-        if (x0 < a.X && y < a.Y && z < Z) mark_bricks(a.bricks, a.bdirty, a.bx, a.by, a.bz, a.bz0, x0, y, z);
+        if (x0 < a.X && y < a.Y && z < Z) mark_bricks(a.bricks, a.bdirty, a.dirty_tag, a.bx, a.by, a.bz, a.bz0, x0, y, z);
     }
 }
 
@@ -1280,22 +1298,23 @@ int launch_rebuild_bricks(kfb_ctx *ctx)
     a.X = ctx->p.volu_dims[0]; a.Y = ctx->p.volu_dims[1];
     a.bricks = ctx->bricks;
     a.bdirty = ctx->bdirty;
+    ctx->bdirty_tag = ctx->bdirty_tag == 0x7fffffff ? 1 : ctx->bdirty_tag + 1;
+    a.dirty_tag = ctx->bdirty_tag;
     a.bx = ctx->bdim[0]; a.by = ctx->bdim[1]; a.bz = ctx->bdim[2]; a.bz0 = ctx->bz0;
     rebuild_bricks_kernel<<<ctx->sm_count * 16, 256, 0, ctx->stream>>>(a, ctx->vol_voxels / 4, ctx->p.volu_dims[2]);
     KFB_LAUNCH_CHECK(ctx);
-    KFB_CUDA(ctx, cudaMemsetAsync(ctx->bdirty, 1, sizeof(int), ctx->stream)); // non-zero: force a distance rebuild
-    return launch_brick_distance(ctx);
+    return launch_brick_distance(ctx, true); // whatever the flags did: the map is rebuilt
 }
 
 // ---- brick distance map ----------------------------------------------------------------------------
 // bdist[b] = min(KFB_BDIST_CAP, Chebyshev distance in bricks from b to the nearest active brick), 0 for an
 // active brick.  Three separable passes: d(b) = min over offsets j along the axis of max(src(b + j), |j|).
-// Every pass returns at once unless a brick flag has flipped since the last rebuild (*dirty != 0); flags
-// only ever flip 0 -> 1 between resets, so a clean map stays exact.
+// Every pass returns at once unless a brick flag has flipped in the sweep it follows (*dirty == that call's tag);
+// flags only ever flip 0 -> 1 between resets, so a clean map stays exact.
 __global__ void brick_distance_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int bx, int by, int bz, int axis,
-                                      const int *__restrict__ dirty, int from_flags)
+                                      const int *__restrict__ dirty, int dirty_tag, int from_flags)
 {
-    if (*dirty == 0) return;
+    if (*dirty != dirty_tag) return; // no flag flipped in the sweep this map follows
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = bx * by * bz;
     if (i >= n) return;
@@ -1314,19 +1333,22 @@ __global__ void brick_distance_kernel(const uint8_t *__restrict__ src, uint8_t *
     dst[i] = (uint8_t)best;
 }
 
-int launch_brick_distance(kfb_ctx *ctx)
+int launch_brick_distance(kfb_ctx *ctx, bool force)
 {
+    // the passes run when the sweep of this call left its tag in *bdirty; `force`: compare with whatever is there
+    const int *dirty = ctx->bdirty;
+    const int tag = ctx->bdirty_tag;
+    if (force) KFB_CUDA(ctx, cudaMemcpyAsync(ctx->bdirty, &ctx->bdirty_tag, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     const int n = ctx->bdim[0] * ctx->bdim[1] * ctx->bdim[2];
     const int blocks = (n + 255) / 256;
     // (measured and dropped in round 2: the x and y passes of a brick layer fused in shared memory, one block per layer
     // -- 15.4 us against 2 x 7.3 us: too few blocks; and all three passes in one cooperative launch: +25 us per call)
-    brick_distance_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bricks, ctx->bdist_tmp, ctx->bdim[0], ctx->bdim[1], ctx->bdim[2], 0, ctx->bdirty, 1);
+    brick_distance_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bricks, ctx->bdist_tmp, ctx->bdim[0], ctx->bdim[1], ctx->bdim[2], 0, dirty, tag, 1);
     KFB_LAUNCH_CHECK(ctx);
-    brick_distance_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bdist_tmp, ctx->bdist_tmp2, ctx->bdim[0], ctx->bdim[1], ctx->bdim[2], 1, ctx->bdirty, 0);
+    brick_distance_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bdist_tmp, ctx->bdist_tmp2, ctx->bdim[0], ctx->bdim[1], ctx->bdim[2], 1, dirty, tag, 0);
     KFB_LAUNCH_CHECK(ctx);
-    brick_distance_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bdist_tmp2, ctx->bdist, ctx->bdim[0], ctx->bdim[1], ctx->bdim[2], 2, ctx->bdirty, 0);
+    brick_distance_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->bdist_tmp2, ctx->bdist, ctx->bdim[0], ctx->bdim[1], ctx->bdim[2], 2, dirty, tag, 0);
     KFB_LAUNCH_CHECK(ctx);
-    KFB_CUDA(ctx, cudaMemsetAsync(ctx->bdirty, 0, sizeof(int), ctx->stream));
     return KFB_OK;
 }
 
