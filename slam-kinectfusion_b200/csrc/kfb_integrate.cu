@@ -1224,9 +1224,10 @@ static void fill_integrate_args(kfb_ctx *ctx, const float vol2cam12[12], Integra
     a.max_weight = ctx->p.tsdf_max_weight;
     a.no_fastpath = getenv("KFB_INTEGRATE_NOFAST") ? 1 : 0;
     a.use_jump = getenv("KFB_INTEGRATE_NOJUMP") ? 0 : 1;
-    // measured on B200: a jump costs about as much as 600 replayed planes (warps that straddle vc.x == 0 walk
-    // many binades), so it pays for far z-slabs / large volumes, not inside a 512^3 sweep
-    a.jump_min = getenv("KFB_INTEGRATE_JUMPMIN") ? atoi(getenv("KFB_INTEGRATE_JUMPMIN")) : 640;
+    // measured on B200 (slabs of 1024^3 and 2048^3, profiles/r02_experiments.md): the jump in front of a slab pays from
+    // a few hundred planes on (thresholds 160 and 320 equal, 640 slower by 4-8 us per sweep at 1024^3); warps whose
+    // four x or y values sit on both sides of zero replay in plain runs inside jump_fma
+    a.jump_min = getenv("KFB_INTEGRATE_JUMPMIN") ? atoi(getenv("KFB_INTEGRATE_JUMPMIN")) : 256;
     a.bricks = ctx->bricks;
     a.bdirty = ctx->bdirty;
     a.dirty_tag = ctx->bdirty_tag;

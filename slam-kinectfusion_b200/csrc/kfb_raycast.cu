@@ -44,6 +44,7 @@ struct RaycastArgs
     int ts_sign_compat;
     const uint8_t *bdist;
     int bx, by, bz, bz0;
+    int sparse_maps;      // slab pushing into a peer's staging: maps are written where the ray had an event only
     int fuse_pyramid;     // write levels 1 and 2 of the model maps from the warp tile (single-GPU, aligned image sizes)
     float4 *pyr_v[2], *pyr_n[2];
     // tile scheduling: block b marches tile order[b] (most expensive tiles of the previous frame first) and leaves
@@ -204,9 +205,6 @@ __device__ __forceinline__ void pyramid_from_tile(float4 vout, float4 nout, int 
 // running-sum instructions only; otherwise KFB_RC_BATCH steps are classified and their loads issued before
 // the first sign test (sample positions do not depend on fetched values).  Candidate hits are parked and
 // their normals are computed after the march, when the warp has reconverged.
-#ifndef KFB_RC_JUMP_MIN
-#define KFB_RC_JUMP_MIN 192 // steps from which the exact jump of the ray's running sums beats replaying them (4 instructions per step)
-#endif
 #ifndef KFB_RC_WARPS
 #define KFB_RC_WARPS 1 // warps (8x4 pixel tiles, stacked in y) per block; 2 warps with 16 / 18 / 21 blocks per SM measured 155 / 154 / 159 us against 152
 #endif
@@ -312,19 +310,11 @@ __global__ void __launch_bounds__(32 * KFB_RC_WARPS, KFB_RC_MINB) raycast_kernel
                 }
                 if (marching && alive)
                 {
-                    if (SLAB && nskip >= KFB_RC_JUMP_MIN) // whole volumes never skip this far (the brick distance is capped)
                     {
-                        // a long run (the way to a far z-slab, a large empty volume): the four running sums are
-                        // advanced by the exact integer jump instead of step by step (kfb_common.cuh: jump_fma)
-                        float t[1];
-                        t[0] = nx; jump_fma<1>(t, dx, a.vs[0], nskip); nx = t[0];
-                        t[0] = ny; jump_fma<1>(t, dy, a.vs[1], nskip); ny = t[0];
-                        t[0] = nz; jump_fma<1>(t, dz, a.vs[2], nskip); nz = t[0];
-                        t[0] = ray_len; jump_fma<1>(t, a.step_len, 1.0f, nskip); ray_len = t[0];
-                    }
-                    else
-                    {
-                        // the four running sums as two packed FFMA2 per step (ray_len + step = fma(step, 1, ray_len), exactly)
+                        // the four running sums as two packed FFMA2 per step (ray_len + step = fma(step, 1, ray_len), exactly).
+                        // Also on the way to a far z-slab: the exact integer jump (kfb_common.cuh: jump_fma) was measured
+                        // against this replay on slabs of 1024^3 and 2048^3 and lost for every run length a ray can have
+                        // (1 800 steps: 264 us against 144 us per slab raycast; profiles/r02_experiments.md)
                         unsigned long long nxy = pack2(nx, ny), nzl = pack2(nz, ray_len);
                         const unsigned long long dxy = pack2(dx, dy), vxy = pack2(a.vs[0], a.vs[1]);
                         const unsigned long long dzl = pack2(dz, a.step_len), vz1 = pack2(a.vs[2], 1.0f);
@@ -419,8 +409,13 @@ __global__ void __launch_bounds__(32 * KFB_RC_WARPS, KFB_RC_MINB) raycast_kernel
     }
     if (inside)
     {
-        a.vmap[pix] = vout;
-        a.nmap[pix] = nout;
+        // a slab rank that pushes into rank 0's staging sends the maps of the pixels that had an event only: the
+        // composite reads the maps of a pixel's winning slab, and a slab without an event (+inf) never wins
+        if (!(SLAB && a.sparse_maps) || key < __int_as_float(0x7f800000))
+        {
+            a.vmap[pix] = vout;
+            a.nmap[pix] = nout;
+        }
         a.key[pix] = key;
     }
     // ---- model pyramid as an epilogue of the warp tile (see pyramid_from_tile)
@@ -627,6 +622,7 @@ int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9]
     a.vmap = ctx->L[0].v[ctx->prev];
     a.nmap = ctx->L[0].n[ctx->prev];
     a.key = ctx->hit_t;
+    a.sparse_maps = 0;
     if (ctx->shard_world > 0 && ctx->shard_rank != 0)
     {
         // attached slab rank: the kernel writes its keys and maps straight into its slot of rank 0's staging buffers
@@ -635,6 +631,7 @@ int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9]
         a.key = (float *)ctx->peer_keys[0] + (size_t)ctx->shard_rank * P;
         a.vmap = (float4 *)ctx->peer_maps[0][0] + (size_t)ctx->shard_rank * 2 * P;
         a.nmap = a.vmap + P;
+        a.sparse_maps = getenv("KFB_PUSH_DENSE") ? 0 : 1;
     }
     a.ts_sign_compat = ctx->p.compat_raycast_ts_sign;
     a.bdist = ctx->bdist;
