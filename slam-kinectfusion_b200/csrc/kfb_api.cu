@@ -103,7 +103,8 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
     ctx->tab_thrz = nullptr; ctx->wtab = nullptr; ctx->zexit = nullptr; ctx->zsparse = nullptr; ctx->bricks = nullptr;
     ctx->tab4 = nullptr; ctx->plan_buf = nullptr; ctx->plan_bytes = 0; ctx->plan_hint_host = nullptr; ctx->gen_attr_set = 0; ctx->integrate_seq = 0;
     ctx->bdist = ctx->bdist_tmp = ctx->bdist_tmp2 = nullptr; ctx->bdirty = nullptr; ctx->bdirty_tag = 0;
-    ctx->ray_cost = nullptr; ctx->ray_order = nullptr; ctx->ray_order_valid = 0; ctx->ev_ray_done = nullptr; ctx->ev_ray_order = nullptr;
+    ctx->ray_cost = nullptr; ctx->ray_order = nullptr; ctx->ray_order_valid = 0; ctx->ev_ray_done = nullptr; ctx->ev_ray_order = nullptr; ctx->ev_order_gate = nullptr;
+    ctx->ray_order_pending = 0; ctx->ray_order_tiles = 0; ctx->ostream = nullptr;
     ctx->hit_t = nullptr; ctx->icp_partials = nullptr; ctx->icp_ticket = nullptr; ctx->counters = nullptr;
     ctx->counters_host = nullptr; ctx->pinned_depth = nullptr; ctx->depth_u16 = nullptr; ctx->render_dev = nullptr; ctx->render_host = nullptr;
     ctx->stream = nullptr; ctx->own_stream = 1;
@@ -133,6 +134,7 @@ int kfb_create(const kfb_intrinsics *intr, const kfb_params *p, int device, kfb_
         KFB_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, (lo + hi) / 2));
         KFB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->fstream, cudaStreamNonBlocking));
         KFB_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->istream, cudaStreamNonBlocking, hi));
+        KFB_CUDA(ctx, cudaStreamCreateWithPriority(&ctx->ostream, cudaStreamNonBlocking, lo));
     }
     KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ifork, cudaEventDisableTiming));
     KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ijoin, cudaEventDisableTiming));
@@ -244,11 +246,13 @@ void kfb_destroy(kfb_ctx *ctx)
     if (ctx->fstream) cudaStreamSynchronize(ctx->fstream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->istream) cudaStreamSynchronize(ctx->istream);
+    if (ctx->ostream) cudaStreamSynchronize(ctx->ostream);
     if (ctx->ev_ifork) cudaEventDestroy(ctx->ev_ifork);
     if (ctx->ev_ijoin) cudaEventDestroy(ctx->ev_ijoin);
     if (ctx->ev_plan_clean) cudaEventDestroy(ctx->ev_plan_clean);
     if (ctx->ev_sweep_main) cudaEventDestroy(ctx->ev_sweep_main);
     if (ctx->istream) cudaStreamDestroy(ctx->istream);
+    if (ctx->ostream) cudaStreamDestroy(ctx->ostream);
     if (ctx->ev_upload) cudaEventDestroy(ctx->ev_upload);
     if (ctx->ev_front) cudaEventDestroy(ctx->ev_front);
     if (ctx->ev_free) cudaEventDestroy(ctx->ev_free);
@@ -278,6 +282,7 @@ void kfb_destroy(kfb_ctx *ctx)
     if (ctx->ray_cost) cudaFree(ctx->ray_cost);
     if (ctx->ev_ray_done) cudaEventDestroy(ctx->ev_ray_done);
     if (ctx->ev_ray_order) cudaEventDestroy(ctx->ev_ray_order);
+    if (ctx->ev_order_gate) cudaEventDestroy(ctx->ev_order_gate);
     shard_close_peers(ctx);
     if (ctx->shard_flag) cudaFree(ctx->shard_flag);
     if (ctx->stage_keys) cudaFree(ctx->stage_keys);

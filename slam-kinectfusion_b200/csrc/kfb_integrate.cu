@@ -1185,6 +1185,8 @@ static int launch_integrate_planned(kfb_ctx *ctx, IntegrateArgs &a, int planes, 
     // on the second stream behind the join event, so that nothing on the frame's critical path waits for the copy
     if (ctx->plan_hint_host)
         KFB_CUDA(ctx, cudaMemcpyAsync(ctx->plan_hint_host, a.plan_counts, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, overlap ? ctx->istream : ctx->stream));
+    // the last raycast's tile order (kfb_raycast.cu: flush_ray_order): behind this call's plan kernel, hence behind the ICP
+    if (const int rco = flush_ray_order(ctx, overlap ? ctx->ev_ifork : nullptr)) return rco;
     if (overlap && !n_updated)
     {
         // both sweep kernels and the hint copy are behind us on the second stream: clear the plan's counters and masks

@@ -654,7 +654,9 @@ int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9]
         ctx->ray_order_valid = 0;
         KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ray_done, cudaEventDisableTiming));
         KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ray_order, cudaEventDisableTiming));
+        KFB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_order_gate, cudaEventDisableTiming));
     }
+    if (ctx->ray_order_pending) { if (const int rco = flush_ray_order(ctx, nullptr)) return rco; } // no integrate since the last raycast
     a.cost = sorted ? ctx->ray_cost : nullptr;
     a.order = (sorted && ctx->ray_order_valid) ? ctx->ray_order : nullptr;
     if (a.order) KFB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_ray_order, 0)); // long done: it ran behind the previous raycast
@@ -667,15 +669,35 @@ int launch_raycast(kfb_ctx *ctx, const float cam2vol12[12], const float rinv9[9]
     if (ctx->profiling) cudaEventRecord(ctx->events[59], ctx->stream);
     if (sorted)
     {
-        // next frame's order, on the sweep's side stream (idle until the next integrate): nothing on the frame's critical
-        // path waits for it, and the front-end stream stays free to run the next frame's front end under this raycast
+        // The costs become next frame's order in a one-block kernel that nothing on the critical path waits for -- but
+        // WHEN it runs matters: right behind this raycast it sat on one SM while the next frame's ICP kernel, which needs
+        // a whole SM's registers on every SM for its co-resident grid, waited for it (12 us per frame).  It is launched
+        // from the next kfb_integrate instead (flush_ray_order), behind that call's plan kernel -- i.e. behind the ICP --
+        // on a stream of the lowest priority, by API calls the host makes while the sweep is already running.
         KFB_CUDA(ctx, cudaEventRecord(ctx->ev_ray_done, ctx->stream));
-        KFB_CUDA(ctx, cudaStreamWaitEvent(ctx->istream, ctx->ev_ray_done, 0));
-        raycast_order_kernel<<<1, 1024, 0, ctx->istream>>>(ctx->ray_cost, ctx->ray_order, ntiles);
-        KFB_LAUNCH_CHECK(ctx);
-        KFB_CUDA(ctx, cudaEventRecord(ctx->ev_ray_order, ctx->istream));
-        ctx->ray_order_valid = 1;
+        ctx->ray_order_pending = 1;
+        ctx->ray_order_tiles = ntiles;
     }
+    return KFB_OK;
+}
+
+// the pending tile order of the last raycast, on the order stream: behind `gate` (an event already recorded on the main
+// stream), or behind everything enqueued on the main stream so far
+int flush_ray_order(kfb_ctx *ctx, cudaEvent_t gate)
+{
+    if (!ctx->ray_order_pending) return KFB_OK;
+    if (!gate)
+    {
+        KFB_CUDA(ctx, cudaEventRecord(ctx->ev_order_gate, ctx->stream));
+        gate = ctx->ev_order_gate;
+    }
+    KFB_CUDA(ctx, cudaStreamWaitEvent(ctx->ostream, gate, 0));
+    KFB_CUDA(ctx, cudaStreamWaitEvent(ctx->ostream, ctx->ev_ray_done, 0));
+    raycast_order_kernel<<<1, 1024, 0, ctx->ostream>>>(ctx->ray_cost, ctx->ray_order, ctx->ray_order_tiles);
+    KFB_LAUNCH_CHECK(ctx);
+    KFB_CUDA(ctx, cudaEventRecord(ctx->ev_ray_order, ctx->ostream));
+    ctx->ray_order_valid = 1;
+    ctx->ray_order_pending = 0;
     return KFB_OK;
 }
 
