@@ -1325,13 +1325,17 @@ __global__ void brick_distance_kernel(const uint8_t *__restrict__ src, uint8_t *
     const int pos = axis == 0 ? x : (axis == 1 ? y : z);
     const int len = axis == 0 ? bx : (axis == 1 ? by : bz);
     const int stride = axis == 0 ? 1 : (axis == 1 ? bx : bx * by);
-    int best = KFB_BDIST_CAP;
-    const int j0 = max(-KFB_BDIST_CAP, -pos), j1 = min(KFB_BDIST_CAP, len - 1 - pos);
-    for (int j = j0; j <= j1; ++j)
+    // taps in rings |j| = 0, 1, 2, ...: a tap at distance r contributes max(v, r) >= r, so the search ends as soon as
+    // r reaches the best value found (near surfaces after a few taps; only far bricks look at all 31)
+    int best = src[i];
+    if (from_flags) best = best ? 0 : KFB_BDIST_CAP;
+    best = min(best, KFB_BDIST_CAP);
+    for (int r = 1; r < best; ++r)
     {
-        int v = src[i + j * stride];
-        if (from_flags) v = v ? 0 : KFB_BDIST_CAP;
-        best = min(best, max(v, abs(j)));
+        int lo = pos - r >= 0 ? src[i - r * stride] : KFB_BDIST_CAP;
+        int hi = pos + r < len ? src[i + r * stride] : KFB_BDIST_CAP;
+        if (from_flags) { lo = (pos - r >= 0 && lo) ? 0 : KFB_BDIST_CAP; hi = (pos + r < len && hi) ? 0 : KFB_BDIST_CAP; }
+        best = min(best, max(min(lo, hi), r));
     }
     dst[i] = (uint8_t)best;
 }
