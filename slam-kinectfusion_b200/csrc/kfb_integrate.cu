@@ -1,41 +1,34 @@
 // kfb_integrate.cu -- TSDF integration (replaces kf::device::integrate,
 // kfusion/src/tsdf_volume.cu:34-111) and volume reset (tsdf_volume.cu:11-32).
 //
-// Voxel-column sweep over the packed {int16 tsdf, int16 weight} volume: a thread owns four consecutive x
-// voxels and marches z; one 128-bit load and one 128-bit store per z step, issued only when at least one of
-// the four voxels passes the reference's update predicate (culled voxels cost no HBM traffic).  A warp owns a
-// compact 16 x 8 voxel patch, a block four of them, and the grid's z dimension cuts the sweep into chunks.
-// The predicate and the update arithmetic are the reference's, rounding for rounding:
-//   * vc(z) is the reference's running sum, vc = fma(voxel_size.x, R[:,2], vc), from z = 1; it is carried as
-//     packed f32x2 pairs (FFMA2); column_states_kernel walks every column once and stores the sums at the
-//     chunk starts, a far z-slab's prefix is crossed by an exact integer jump (jump4);
-//   * pixel = round-half-even(fma(vc.x * MUFU.RCP(vc.z), fx, cx)), done with the 2^23 magic-number add so it
-//     stays off the conversion pipe;
-//   * sdf = depth - |vc| / lambda is only evaluated exactly inside a narrow band around the surface: a
-//     per-pixel table of conservative vc.z thresholds classifies "certainly free space => tsdf == 1.0f exactly"
-//     and "certainly behind the surface => rejected" with two compares.  The thresholds are proved
-//     conservative in build_tables_kernel, so classification never changes a result, only skips work.
-// Everything that is not the reference's arithmetic was taken off the per-voxel path (the first version was
-// instruction-issue bound, profiles/r01_v1_*):
-//   * a per-thread conservative frustum interval [za, zb] in z (vc(z) is affine in z, so the four image-border
-//     inequalities, vc.z > 0 and vc.z <= max accepted depth are half-lines in z) and an occlusion cut from a
-//     max-pyramid of the thresholds over the pixels the columns can reach; planes outside are not visited,
-//     inside the interval the exact per-voxel predicate still decides;
-//   * a deep-free-space path: while every pixel a warp's columns can land on still sees free space at a
-//     plane's largest vc.z, all voxels of that plane get tsdf = 1.0f -- no projection, no running sums.  vc.z
-//     grows with z, so these planes are a prefix of a chunk: the warp streams through it and takes the general
-//     path only behind it;
-//   * in the general path every stage's dependent loads (thresholds, exact depth, weight table, brick flags)
-//     are issued together: the warps wait on memory with every slot of the SM taken, so time is the sum of the
-//     warps' lifetimes;
-//   * the update runs without the quarter-rate XU pipe: int->float by magic-number add, the reciprocal of
-//     weight+1 from a device-built table of MUFU.RCP results, float->int truncation by an RZ add of 2^23;
-//   * when a thread's four voxels hold the same word and receive the same tsdf (free space), the update is
-//     computed once; stores whose value equals the loaded one are dropped.
-// Measured (profiles/): 56 M warp instructions per 640x480 / 512^3 frame (the first version: 271 M), DRAM
-// traffic within 10 % of the algorithmic bytes; 82 % of the measured HBM copy bandwidth when every voxel is updated.
-// Side product for the raycaster: a voxel that turns negative marks the 8^3 bricks within two voxels of it in
-// a byte map; three separable passes turn the map into the brick distance field kfb_raycast.cu skips with.
+// A planned sweep over the packed {int16 tsdf, int16 weight} volume (8 x 8 x 8 voxel bricks, kfb_common.cuh: vol_index).
+// A thread owns four consecutive x voxels (one 128-bit load and store per plane, issued only where the reference's
+// update predicate can pass), a warp a 16 x 8 voxel patch (two bricks wide) that it marches along z.  The predicate and
+// the update arithmetic are the reference's, rounding for rounding:
+//   * vc(z) is the reference's running sum, vc = fma(voxel_size.x, R[:,2], vc), from z = 1, carried as packed f32x2
+//     pairs (FFMA2);
+//   * pixel = round-half-even(fma(vc.x * MUFU.RCP(vc.z), fx, cx)), done with the 2^23 magic-number add so it stays off
+//     the conversion pipe;
+//   * sdf = depth - |vc| / lambda is only evaluated exactly inside a narrow band around the surface: a per-pixel
+//     table of conservative vc.z thresholds classifies "certainly free space => tsdf == 1.0f exactly" and "certainly
+//     behind the surface => rejected" with two compares.  The thresholds are proved conservative in
+//     build_tables_kernel, so classification never changes a result, only skips work;
+//   * the update runs without the quarter-rate XU pipe (int->float by magic-number add, the reciprocal of weight + 1
+//     from a device-built table of MUFU.RCP results, float->int truncation by an RZ add of 2^23); a quad whose four
+//     words and tsdf values agree is updated once; stores whose value equals the loaded one are dropped.
+// What is decided where:
+//   * integrate_plan_kernel, one thread per (patch, 16-plane chunk): conservative frustum interval, occlusion cut and
+//     deep-free-space prefix from an EXACT min/max of the thresholds over the pixel rectangle the patch projects into
+//     (sparse table over 2^k windows) -> two item lists;
+//   * integrate_stream_kernel: items whose every voxel gets tsdf = 1.0f -- load, running mean, store, a brick layer in
+//     flight per thread (bandwidth-bound: 0.94 of the measured copy bandwidth when every voxel is updated);
+//   * integrate_general_kernel: the exact per-voxel predicate, one plane per iteration, all of a plane's loads
+//     requested before the first use, the item's planes prefetched into L2 when it starts; its first blocks walk the
+//     running sums of all patches once and publish them per item (release / acquire), a far z-slab's prefix is
+//     crossed by an exact integer jump (jump_fma);
+//   * the two kernels run side by side on two streams (the general one with priority).
+// Side product for the raycaster: a voxel that turns negative marks the 8^3 bricks within two voxels of it in a byte
+// map; three separable passes turn the map into the brick distance field kfb_raycast.cu skips with.
 #include "kfb_common.cuh"
 #include <algorithm>
 #include <cmath>

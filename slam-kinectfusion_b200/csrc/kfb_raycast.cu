@@ -17,7 +17,8 @@
 //     map kfb_integrate.cu maintains) can take part in no event.  Such samples are not fetched (they count
 //     as NaN, which the reference's `isnan(next)` test already skips); a Chebyshev distance map over the
 //     bricks says how many further steps provably stay clear of every such brick, and those steps are run
-//     with the four running-sum instructions only;
+//     with the running-sum instructions only (two packed FFMA2 per step);
+//   * tiles are marched in the order of their cost in the previous frame (the longest rays first);
 //   * index rounding by magic-number add instead of F2I (the quarter-rate conversion pipe);
 //   * z-slab mode (sharded volumes): samples outside the stored planes are "not mine"
 //     (NaN), events are evaluated only when the `next` sample's voxel plane is owned by this slab, and the
